@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- candidate x point scoring throughput on B200 (BASELINE.json metric).
+
+A "step" = one pass of the hot path (K2 score, + the NCCL all-reduce of the per-candidate counts
+when sharded) over config c3: 4096 candidates (1024 planes/spheres/cylinders/cones) x 16 Mi points
+per GPU (point-range shards; weak scaling: every rank holds its own 16 Mi-point shard).
+
+  value      G candidate.point evals/s, whole job, inputs resident in HBM (device-timed)
+  e2e        same metric through the public call with HOST buffers: every step uploads the cloud
+             (pinned host -> device), the candidates, scores, and reads the counts back
+  roofline   the tiled score kernel against the FP32 roofline (the path is FP32-ALU bound)
+  cpu_baseline  the CPU restatement of the reference (oracle/) on a bounded sample
+
+`--impl reference` times the CPU restatement of RANSAC.jl's scorecandidate loop instead (Julia is
+not installed in this image, so the Julia package itself cannot run).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_EVAL = {"plane": 13, "sphere": 16, "cylinder": 27, "cone": 38}
+MIX_FLOPS = 23.5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=16 << 20, help="points per GPU")
+    ap.add_argument("--cands", type=int, default=4096)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="override the CPU sample (points)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1])), pw.append(float(r[2]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(points: int, ncands: int, rank: int):
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(3 + 1000 * rank, points)
+    # candidates are identical on every rank: generated from rank 0's primitives
+    sc0 = sc if rank == 0 else scenes.Scene(None, None, None, scenes.scene_mixed(3, 1024).primitives)
+    cands = scenes.perturbed_candidates(sc0, ncands // 4, seed=7)
+    return sc, cands
+
+
+def cpu_baseline(sc, cands, params, budget_pts: int):
+    """CPU restatement of the reference (oracle/) on a bounded sample of the same workload."""
+    from oracle import ransac_oracle as O
+    from tests.helpers import oracle_params, to_oracle_shape
+
+    op = oracle_params(params)
+    try:
+        from oracle import c_oracle
+        have_c = c_oracle.available()
+    except Exception:
+        have_c = False
+    n = min(budget_pts, len(sc.vertices))
+    P = sc.vertices[:n].astype(np.float64)
+    N = sc.normals[:n].astype(np.float64)
+    step = max(1, len(cands) // 64)
+    sample = cands[::step]
+    t0 = time.perf_counter()
+    if have_c:
+        cores = c_oracle.score_counts(sample, P, N, op)[1]
+    else:
+        cores = 1
+        for sh in sample:
+            O.compatibles(to_oracle_shape(sh), P, N, op)
+    dt = time.perf_counter() - t0
+    ev = len(sample) * n
+    return {"value": ev / dt / 1e9, "unit": "G evals/s", "cores": cores, "kind": "port",
+            "sample": f"{len(sample)} candidates (every {step}th, all four types) x first {n} points of the workload; "
+                      f"{'C (OpenMP)' if have_c else 'NumPy'} float64 restatement of RANSAC.jl compatibles*, {dt:.2f} s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU algorithm for the path (restated, see module doc)."""
+    if rank != 0:
+        return
+    import ransac_jl_b200  # noqa: F401 (host-side types only; nothing below touches the GPU)
+    from ransac_jl_b200 import params as RP
+
+    pts = args.cpu_sample or (1 << 18)
+    sc, cands = make_workload(pts, args.cands, 0)
+    params = RP.ransacparameters()
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(sc, cands, params, pts)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([x["value"] for x in vals]))
+    ms = float(np.mean([len(cands[:: max(1, len(cands) // 64)]) * pts / (x["value"] * 1e9) * 1e3 for x in vals]))
+    out = {
+        "impl": "reference", "metric": "candidate_point_evals_per_s", "value": v, "unit": "G evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"c3 candidate-scoring microbench, bounded CPU sample: {vals[-1]['sample']}"},
+        "cpu_baseline": dict(vals[-1], value=v),
+        "e2e": {"value": v, "unit": "G evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Julia is not installed in this image: the timed code is the CPU restatement of RANSAC.jl's scorecandidate loop (oracle/), not the Julia package",
+    }
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    import ransac_jl_b200 as R
+    from ransac_jl_b200._lib import lib
+    import ctypes as C
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    sc, cands = make_workload(args.points, args.cands, rank)
+    params = R.ransacparameters()
+    cp = R.to_c(params)
+    Cn = len(cands)
+    n = len(sc.vertices)
+
+    # ---- resident arm: cloud + candidates in HBM --------------------------------------------
+    pc = R.RANSACCloud(sc.vertices, sc.normals, [np.zeros(0, np.int64)], device=local)
+    arr = R.pack_cands(cands)
+    d_cands = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    d_counts = torch.zeros(Cn, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        rc = lib.rsc_score_dev(pc.handle, C.byref(cp), d_cands.data_ptr(), Cn, -1, d_counts.data_ptr(), stream.cuda_stream)
+        pc.ctx.check(rc)
+        if world > 1:
+            dist.all_reduce(d_counts)
+
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    t_a = torch.cuda.Event(enable_timing=True)
+    t_b = torch.cuda.Event(enable_timing=True)
+    t_a.record()
+    for a, b in evs:
+        a.record()
+        step_resident()
+        b.record()
+    t_b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = t_a.elapsed_time(t_b)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    evals_per_step = float(Cn) * n * world
+    value = evals_per_step / (ms_per_step * 1e-3) / 1e9
+
+    # kernel-only time of the tiled score kernel (CUDA events recorded by the library on the same
+    # stream around that launch alone), averaged over a few extra steps
+    kms, guard = [], 0
+    for _ in range(3):
+        step_resident()
+        k, guard = _last_kernel(pc)
+        kms.append(k)
+    kernel_ms = float(np.mean(kms))
+    counts_host = d_counts.cpu().numpy()
+
+    # ---- e2e arm: host buffers through the public call -----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        xyz = torch.from_numpy(sc.vertices).pin_memory()
+        nrm = torch.from_numpy(sc.normals).pin_memory()
+        counts_h = np.zeros(Cn, dtype=np.int32)
+
+        def step_e2e():
+            h = C.c_void_p()
+            pc.ctx.check(lib.rsc_cloud_create(pc.ctx.h, xyz.data_ptr(), nrm.data_ptr(), n, C.byref(h)))
+            try:
+                pc.ctx.check(lib.rsc_score(h, C.byref(cp), arr, Cn, -1, counts_h.ctypes.data, None))
+            finally:
+                lib.rsc_cloud_destroy(h)
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            step_e2e()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+            if world > 1:
+                tt = torch.from_numpy(counts_h).to(dev)
+                dist.all_reduce(tt)
+                counts_h[:] = tt.cpu().numpy()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        if world == 1:
+            assert np.array_equal(counts_h, counts_host), "e2e and resident arms disagree"
+        e2e = {"value": evals_per_step / (dt / args.steps) / 1e9, "unit": "G evals/s",
+               "h2d_bytes_per_step": int(2 * n * 12 + Cn * 64 + Cn * 16), "d2h_bytes_per_step": int(Cn * 4 + 4),
+               "ms_per_step": dt / args.steps * 1e3}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    nsm = torch.cuda.get_device_properties(local).multi_processor_count
+    fp32_peak = nsm * 128 * 2 * sm_max * 1e6 / 1e12
+    ach = MIX_FLOPS * Cn * n / (kernel_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
+        "traffic": None,
+        "peak_source": f"derived: {nsm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry; "
+                       "the path uses no tensor cores and is not HBM bound)",
+        "kernel": "rsc::score_kernel<4>", "kernel_ms": kernel_ms,
+        "algorithmic_flops_per_eval": MIX_FLOPS,
+        "hbm_gbs_algorithmic": (Cn / 512) * 24.125 * n / (kernel_ms * 1e-3) / 1e9,
+        "hbm_peak_gbs": peaks.get("hbm_gbs"),
+    }
+    out = {
+        "metric": "candidate_point_evals_per_s", "value": value, "unit": "G evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c3 candidate-scoring microbench: {Cn} candidates (4 shape types x {Cn // 4}) x "
+                               f"{n} points per GPU, whole-cloud scoring, counts only",
+                   "points_per_gpu": n, "candidates": Cn, "parallelism": f"point-range shards x{world}, "
+                   "int32 count all-reduce (NCCL)" if world > 1 else "single GPU",
+                   "l2": "inputs (403 MB of points per pass) exceed the 126 MB L2; no flush needed"},
+        "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roofline,
+        "fp64_guard_pairs_per_step": int(guard),
+    }
+    if not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or (1 << 16))
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _last_kernel(pc):
+    import ctypes as C
+
+    from ransac_jl_b200._lib import lib
+
+    ms, gp = C.c_double(), C.c_int64()
+    pc.ctx.check(lib.rsc_ctx_last_kernel(pc.ctx.h, C.byref(ms), C.byref(gp)))
+    return ms.value, gp.value
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+/*
+ * rsc.h -- C ABI of libransac_b200: the B200 (sm_100a) hot path of efficient-RANSAC shape
+ * detection, built to sit underneath cserteGT3/RANSAC.jl's public surface.
+ *
+ * The reference has no FFI; its extension boundary is Julia multiple dispatch
+ * (docs/src/newprimitive.md:12-18).  Each entry point below replaces the body of one group of
+ * reference methods for the four built-in shapes, and is what a `ccall` from those methods binds
+ * (see INTEGRATION.md for the Julia stubs).  Citations are relative to the reference root.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative RSC_E_* on failure; the message of the last
+ *     failure on a context is rsc_last_error(ctx).  No exception crosses the boundary.
+ *   - indices are 0-based on this side (Julia adds/subtracts 1).
+ *   - host buffers are copied during the call, never retained; outputs go to caller-owned buffers.
+ *   - a context (and its clouds) is bound to one CUDA device and is not thread-safe.
+ *   - there is NO CPU fallback: without a usable sm_100 device rsc_ctx_create fails.
+ *   - `*_dev` variants take DEVICE pointers and a cudaStream_t (as void*) and do not synchronise;
+ *     they are what a multi-GPU host (one process per GPU) chains with its NCCL collectives.
+ */
+#ifndef RSC_H
+#define RSC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSC_VERSION 100
+
+/* shape kinds (src/shapes/{plane,sphere,cylinder,cone}.jl) */
+#define RSC_PLANE 0
+#define RSC_SPHERE 1
+#define RSC_CYLINDER 2
+#define RSC_CONE 3
+#define RSC_NTYPES 4
+
+/* error codes */
+#define RSC_OK 0
+#define RSC_E_ARG (-1)      /* bad argument (the reference's @assert failures map here) */
+#define RSC_E_CUDA (-2)     /* CUDA runtime error */
+#define RSC_E_NODEVICE (-3) /* no sm_100 device: there is no fallback path */
+#define RSC_E_NOMEM (-4)
+#define RSC_E_STATE (-5)    /* e.g. subset not uploaded */
+#define RSC_E_NCCL (-6)
+
+/* compat_flags: reference behaviours that can be switched off (SURVEY.md 8a' quirk numbers) */
+#define RSC_COMPAT_SPHERE_IGNORES_ENABLED 1u /* Q4: sphere.jl:121,131 */
+#define RSC_COMPAT_DEFAULT (RSC_COMPAT_SPHERE_IGNORES_ENABLED)
+
+/* which counter plays `s` in prob(n,s,N,k): utilities.jl:297-300 */
+#define RSC_S_LENGTHC 0
+#define RSC_S_ALLCAND 1
+#define RSC_S_NOFMINSET 2
+
+typedef struct rsc_ctx rsc_ctx;
+typedef struct rsc_cloud rsc_cloud;
+typedef struct rsc_run rsc_run;
+
+/*
+ * One shape candidate, 64 bytes.  Mirrors the Fitted* structs (float64 like the reference):
+ *   plane    p = point[3], normal[3], -        (plane.jl:8-11)
+ *   sphere   p = center[3], radius, -,-,-      (sphere.jl:9-13)
+ *   cylinder p = axis[3], center[3], radius    (cylinder.jl:11-16)
+ *   cone     p = apex[3], axis[3], opang       (cone.jl:11-19; opang = FULL opening angle, rad)
+ */
+typedef struct rsc_cand {
+  int32_t type;
+  int32_t outwards; /* 0/1; ignored for planes */
+  double p[7];
+} rsc_cand;
+
+/*
+ * Flat mirror of the nested NamedTuple built by ransacparameters (utilities.jl:332-433).
+ * Defaults (rsc_params_default) are the values pinned by test/utilitytests.jl:41-82.
+ * eps/alpha are indexed by RSC_PLANE..RSC_CONE.
+ */
+typedef struct rsc_params {
+  int32_t drawN;       /* iteration.drawN (only 3 is supported by the built-in fits) */
+  int32_t minsubsetN;  /* iteration.minsubsetN */
+  double prob_det;     /* iteration.prob_det */
+  int64_t tau;         /* iteration.tau */
+  int32_t itermax;     /* iteration.itermax */
+  int32_t extract_s;   /* RSC_S_* */
+  int32_t terminate_s; /* RSC_S_* */
+  int32_t n_shape_types;
+  int32_t shape_types[RSC_NTYPES]; /* fit order, e.g. {PLANE, CONE, CYLINDER, SPHERE} (RANSAC.jl:94) */
+  double collin_threshold;         /* common.collin_threshold (ineffective, Q3) */
+  double parallelthrdeg;           /* common.parallelthrdeg, degrees */
+  double eps[RSC_NTYPES];
+  double alpha[RSC_NTYPES];
+  double sphere_par;   /* sphere.sphere_par */
+  double minconeopang; /* cone.minconeopang */
+  uint32_t compat_flags;
+  uint32_t reserved;
+} rsc_params;
+
+/* cumulative counters / device timers of a context */
+typedef struct rsc_stats {
+  int64_t evals;          /* candidate x point pairs evaluated by the score/refit kernels */
+  int64_t exact_pairs;    /* pairs inside the FP32 guard band, re-evaluated in FP64 */
+  int64_t sets_drawn;     /* minimal sets attempted */
+  int64_t cands_scored;
+  int64_t score_launches; /* launches of the tiled score kernel */
+  double score_ms;        /* CUDA-event time of the last score call's kernels */
+  double last_kernel_ms;  /* CUDA-event time of the last tiled score kernel launch alone */
+} rsc_stats;
+
+/* ---- context ----------------------------------------------------------------------- */
+int32_t rsc_version(void);
+void rsc_params_default(rsc_params* p);
+int32_t rsc_ctx_create(int32_t device, rsc_ctx** out);
+void rsc_ctx_destroy(rsc_ctx* ctx);
+const char* rsc_last_error(const rsc_ctx* ctx);
+int32_t rsc_ctx_stats(rsc_ctx* ctx, rsc_stats* out);
+void* rsc_ctx_stream(rsc_ctx* ctx); /* the cudaStream_t all work of this context is ordered on */
+/* After a *_dev call: waits for the device, then reports the CUDA-event duration of the last tiled
+ * score kernel launch alone (ms) and how many guard-band pairs it sent to FP64 (nullable outs). */
+int32_t rsc_ctx_last_kernel(rsc_ctx* ctx, double* kernel_ms, int64_t* guard_pairs);
+
+/* ---- cloud: RANSACCloud (octree.jl:37-59, ctors :78-138) ------------------------------ */
+/* xyz/nrm are AoS (N x 3), bit-compatible with Vector{SVector{3,Float32}}; stored on device as
+ * SoA float32.  `_f64` down-converts Vector{SVector{3,Float64}}.  `_shard` uploads the point range
+ * [global_offset, global_offset+n) of a cloud of n_global points (one shard per GPU/process). */
+int32_t rsc_cloud_create(rsc_ctx* ctx, const float* xyz, const float* nrm, int64_t n, rsc_cloud** out);
+int32_t rsc_cloud_create_f64(rsc_ctx* ctx, const double* xyz, const double* nrm, int64_t n, rsc_cloud** out);
+int32_t rsc_cloud_create_shard(rsc_ctx* ctx, const float* xyz, const float* nrm, int64_t n,
+                               int64_t global_offset, int64_t n_global, rsc_cloud** out);
+void rsc_cloud_destroy(rsc_cloud* cloud);
+int64_t rsc_cloud_size(const rsc_cloud* cloud);
+/* pc.subsets (octree.jl:129-135): `idx` holds subset `subset_id`'s local point indices in subset
+ * order; the device keeps a gathered contiguous copy so that scoring streams it linearly. */
+int32_t rsc_cloud_set_subset(rsc_cloud* cloud, int32_t subset_id, const int64_t* idx, int64_t m);
+int64_t rsc_cloud_subset_size(const rsc_cloud* cloud, int32_t subset_id);
+/* pc.isenabled in BitArray.chunks layout: ceil(n/64) UInt64 words, bit i%64 of word i/64 */
+int32_t rsc_cloud_get_enabled(rsc_cloud* cloud, uint64_t* words);
+int32_t rsc_cloud_set_enabled(rsc_cloud* cloud, const uint64_t* words);
+int32_t rsc_cloud_enable_all(rsc_cloud* cloud); /* ransac(pc, params, true): iterations.jl:15-19 */
+int64_t rsc_cloud_count_enabled(rsc_cloud* cloud);
+
+/* ---- scoring: scorecandidates!/scorecandidate/compatibles* ---------------------------- */
+/* (fitting.jl:181-190; plane.jl:61-71,114-130; sphere.jl:118-172; cylinder.jl:172-221;
+ *  cone.jl:132-167)
+ * Scores C candidates against subset `subset_id` (>= 0) or the whole cloud (-1).
+ *   counts[c]  = number of compatible (and enabled, except Q4) points;
+ *   masks      = NULL, or C x ceil(M/32) words, row c = inlier bitmask of candidate c in subset
+ *                order (bit j%32 of word j/32 = point j): inpoints = subset[mask]. */
+int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C,
+                  int32_t subset_id, int32_t* counts, uint32_t* masks);
+/* device-pointer variant: d_cands/d_counts live on the context's device; enqueues on `stream`
+ * (NULL = the context stream) and returns without synchronising. */
+int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,
+                      int32_t subset_id, int32_t* d_counts, void* stream);
+/* estimatescore (confidenceintervals.jl:53-74), Int64 wrap-around included (Q9). */
+void rsc_estimate_score(int64_t subset_len, int64_t cloud_len, int64_t count, double* out_min,
+                        double* out_max, double* out_E);
+
+/* ---- fitting: forcefitshapes!/fit x4 (fitting.jl:165-173; plane.jl:33-57; sphere.jl:29-114;
+ *      cylinder.jl:34-168; cone.jl:39-128) -------------------------------------------------- */
+/* idx = S x drawN local point indices.  Output candidates are compacted in (set, shape_types)
+ * order (Q16); out_set[i] = source set of candidate i.  Capacity of out/out_set: S*n_shape_types. */
+int32_t rsc_fit_batch(rsc_cloud* cloud, const rsc_params* params, const int64_t* idx, int32_t S,
+                      rsc_cand* out, int32_t* out_set, int32_t* out_n);
+/* Same fits on explicit coordinates: p, n = S x k x 3 doubles (k >= 3 points per set; points beyond
+ * the minimal set only validate, like the 4-point sets of test/dummyspheretest.jl).  This is the
+ * direct counterpart of fit(::Type{S}, p, n, pc, params) and needs no cloud. */
+int32_t rsc_fit_points(rsc_ctx* ctx, const rsc_params* params, const double* p, const double* n,
+                       int32_t S, int32_t k, rsc_cand* out, int32_t* out_set, int32_t* out_n);
+/* samplepointcloud4! (fitting.jl:383-430, root cell only -- Q1) fused with the fits: minimal set
+ * `set0+i` draws from Philox4x32-10 keyed by `seed`.  out_idx (S x drawN) receives the drawn
+ * indices, -1 rows for failed samples (nullable). */
+int32_t rsc_sample_fit(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, uint64_t set0,
+                       int32_t S, rsc_cand* out, int32_t* out_set, int64_t* out_idx, int32_t* out_n);
+
+/* ---- refit + invalidate_indexes! (plane.jl:137-143; sphere.jl:179-190; cylinder.jl:228-234;
+ *      cone.jl:176-182; fitting.jl:197-202) ------------------------------------------------- */
+/* Compatible points among the ENABLED points of the whole cloud, ascending global indices into
+ * out_idx (nullable; capacity = cloud size); *out_n = how many.  disable != 0 also clears their
+ * enabled bits (and those of the uploaded subsets). */
+int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand,
+                          int64_t* out_idx, int64_t* out_n, int32_t disable);
+
+/* ---- the whole loop: ransac(pc, params; ...) iterations.jl:35-162 for built-in shapes ------- */
+int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, rsc_run** out);
+int32_t rsc_run_nshapes(const rsc_run* run);
+int32_t rsc_run_iterations(const rsc_run* run);
+double rsc_run_seconds(const rsc_run* run);
+int32_t rsc_run_shape(const rsc_run* run, int32_t i, rsc_cand* shape, int64_t* n_inpoints);
+int32_t rsc_run_inpoints(const rsc_run* run, int32_t i, int64_t* out_idx);
+void rsc_run_destroy(rsc_run* run);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSC_H */

@@ -1,0 +1,833 @@
+"""CPU oracle: literal float64 restatement of RANSAC.jl's hot path (NumPy).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the shipped package may import this module; only
+`tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` use it, and only as the checker.
+
+What is restated (all citations relative to /root/reference, RANSAC.jl v0.6.0):
+
+  fit(FittedPlane)        src/shapes/plane.jl:33-57
+  compatiblesPlane        src/shapes/plane.jl:82-130   (project2plane :82-103)
+  fit2pointsphere / fit   src/shapes/sphere.jl:29-75, :87-114
+  compatiblesSphere       src/shapes/sphere.jl:144-172
+  fit2pointcylinder / fit src/shapes/cylinder.jl:34-125, :135-168
+  compatiblesCylinder     src/shapes/cylinder.jl:194-221
+  fit3pointcone           src/shapes/cone.jl:39-61
+  project2cone            src/shapes/cone.jl:68-85     (rodrigues: src/utilities.jl:19-43,61-64)
+  validatecone / fit      src/shapes/cone.jl:87-115, :123-128
+  compatiblesCone         src/shapes/cone.jl:132-153
+  scorecandidate x4       plane.jl:61-71 sphere.jl:118-134 cylinder.jl:172-183 cone.jl:155-167
+  refit x4                plane.jl:137-143 sphere.jl:179-190 cylinder.jl:228-234 cone.jl:176-182
+  estimatescore           src/confidenceintervals.jl:53-74 (Int64 wrap-around reproduced)
+  findhighestscore        src/fitting.jl:140-158
+  prob / chooseS          src/utilities.jl:262, :297-300
+  samplepointcloud4!      src/fitting.jl:383-430 (root cell only, see Q1 below)
+  ransac loop             src/iterations.jl:35-162
+  RANSACCloud subsets     src/octree.jl:126-138
+
+Parity status: the reference's own tests pin only the sphere/plane accept-reject answers of
+test/dummyspheretest.jl:14-48, ConfidenceInterval (test/confidenceintervals.jl) and the default
+parameters (test/utilitytests.jl:41-82); those are reproduced in tests/test_oracle_golden.py.
+compatibles*/scorecandidate/refit/estimatescore and the cylinder/cone fits are pinned by NO
+reference test and Julia is not installed here, so for those: PARITY UNPINNED (source
+restatement only, plus analytic on-surface self-checks).  Third-party arithmetic whose exact
+rounding is not restated: StaticArrays dot/cross/normalize (taken as left-to-right sums and
+inv(norm)*v), LinearAlgebra rank (SVD, tol = min(m,n)*eps*smax) and `\\` (LAPACK LU), cosd.
+
+Behavioural quirks kept on purpose (SURVEY.md section 8a'):
+  Q1  the level weights are NaN/zero so every minimal set is drawn from the root cell
+      (octree.jl:82-84 vs :44-45) -> the sampler here draws from all enabled points.
+  Q3  plane collinearity test never fires.         Q4  sphere scoring ignores `isenabled`.
+  Q5  sphere degenerate branch uses p1 twice.      Q6  cone validation distance is signed.
+  Q8  cylinder fit uses raw normals.               Q9  Int64 overflow in estimatescore.
+  Q12 s counts attempted minimal sets.             Q17 NaN (point on axis/centre) -> incompatible.
+  Q18 plane angle test uses the raw normal, the distance the re-normalised one.
+
+Indices are 0-based here (the reference is 1-based); everything else is op-for-op.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+F = np.float64
+
+# --------------------------------------------------------------------------------------
+# small vector helpers (StaticArrays semantics: left-to-right sums, normalize = inv(norm)*v)
+# --------------------------------------------------------------------------------------
+
+
+def dot3(a, b):
+    return a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1] + a[..., 2] * b[..., 2]
+
+
+def norm3(a):
+    return np.sqrt(a[..., 0] * a[..., 0] + a[..., 1] * a[..., 1] + a[..., 2] * a[..., 2])
+
+
+def normalize3(a):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        inv = 1.0 / norm3(a)
+        return inv[..., None] * a if np.ndim(inv) else inv * a
+
+
+def cross3(a, b):
+    return np.stack(
+        [
+            a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1],
+            a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+            a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0],
+        ],
+        axis=-1,
+    )
+
+
+def _v(x):
+    return np.asarray(x, dtype=F)
+
+
+# --------------------------------------------------------------------------------------
+# parameters (utilities.jl:332-399; defaults pinned by test/utilitytests.jl:41-82)
+# --------------------------------------------------------------------------------------
+
+PLANE, SPHERE, CYLINDER, CONE = 0, 1, 2, 3
+SHAPE_NAMES = {PLANE: "plane", SPHERE: "sphere", CYLINDER: "cylinder", CONE: "cone"}
+#: RANSAC.jl:94 -- DEFAULT_PARAMETERS shape order
+DEFAULT_SHAPE_TYPES = (PLANE, CONE, CYLINDER, SPHERE)
+
+
+def default_parameters(shape_types: Sequence[int] = DEFAULT_SHAPE_TYPES) -> dict:
+    """defaultparameters (utilities.jl:391-399) as a nested dict."""
+    p = {
+        "iteration": {
+            "drawN": 3,
+            "minsubsetN": 15,
+            "prob_det": 0.9,
+            "shape_types": list(shape_types),
+            "tau": 900,
+            "itermax": 1000,
+            "extract_s": "nofminset",
+            "terminate_s": "nofminset",
+        },
+        "common": {"collin_threshold": 0.2, "parallelthrdeg": 1.0},
+    }
+    for s in shape_types:
+        if s == PLANE:
+            p["plane"] = {"eps": 0.3, "alpha": math.radians(5)}
+        elif s == SPHERE:
+            p["sphere"] = {"eps": 0.3, "alpha": math.radians(5), "sphere_par": 0.02}
+        elif s == CYLINDER:
+            p["cylinder"] = {"eps": 0.3, "alpha": math.radians(5)}
+        elif s == CONE:
+            p["cone"] = {"eps": 0.3, "alpha": math.radians(5), "minconeopang": math.radians(2)}
+    return p
+
+
+def ransacparameters(base: Optional[dict] = None, **kw) -> dict:
+    """ransacparameters (utilities.jl:425-433): per-group merge of overrides."""
+    if base is None:
+        base = default_parameters()
+    new = {k: dict(v) for k, v in base.items()}
+    for k, v in kw.items():
+        old = dict(base.get(k, v))
+        old.update(v)
+        new[k] = old
+    return new
+
+
+def cosd(deg: float) -> float:
+    return math.cos(math.radians(deg))
+
+
+# --------------------------------------------------------------------------------------
+# shapes
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class Shape:
+    """One fitted candidate.  kind in {PLANE, SPHERE, CYLINDER, CONE}.
+
+    plane   : point, normal                      (plane.jl:8-11)
+    sphere  : center, radius, outwards           (sphere.jl:9-13)
+    cylinder: axis, center, radius, outwards     (cylinder.jl:11-16)
+    cone    : apex, axis, opang, outwards        (cone.jl:11-19)
+    """
+
+    kind: int
+    a: np.ndarray  # plane.point | sphere.center | cylinder.axis | cone.apex
+    b: np.ndarray  # plane.normal | (unused)     | cylinder.center | cone.axis
+    s: float = 0.0  # radius | opang
+    outwards: bool = True
+
+    def params7(self) -> np.ndarray:
+        """Flat 7-double record in the C-ABI order (include/rsc.h, rsc_cand.p)."""
+        if self.kind == PLANE:
+            return np.array([*self.a, *self.b, 0.0])
+        if self.kind == SPHERE:
+            return np.array([*self.a, self.s, 0.0, 0.0, 0.0])
+        return np.array([*self.a, *self.b, self.s])
+
+
+def shape_from_params7(kind: int, outwards: bool, p: Sequence[float]) -> Shape:
+    p = _v(p)
+    if kind == PLANE:
+        return Shape(PLANE, p[0:3].copy(), p[3:6].copy(), 0.0, True)
+    if kind == SPHERE:
+        return Shape(SPHERE, p[0:3].copy(), np.zeros(3), float(p[3]), bool(outwards))
+    return Shape(kind, p[0:3].copy(), p[3:6].copy(), float(p[6]), bool(outwards))
+
+
+# ---- plane ---------------------------------------------------------------------------
+
+
+def fit_plane(p, n, params) -> Optional[Shape]:
+    """plane.jl:33-57."""
+    p, n = _v(p), _v(n)
+    alpha = params["plane"]["alpha"]
+    collin = params["common"]["collin_threshold"]
+    lp = len(p)
+    assert lp > 2 and lp == len(n)
+    crossv = normalize3(cross3(p[1] - p[0], p[2] - p[0]))
+    if norm3(crossv) < collin:  # Q3: norm of a normalised vector is 1 or NaN
+        return None
+    thr = math.cos(alpha)
+    norm_ok = np.zeros(lp, bool)
+    inv_ok = np.zeros(lp, bool)
+    for i in range(lp):
+        d = dot3(crossv, normalize3(n[i]))
+        norm_ok[i] = d > thr
+        inv_ok[i] = d < -thr
+    if norm_ok.all():
+        return Shape(PLANE, p[0].copy(), crossv)
+    if inv_ok.all():
+        return Shape(PLANE, p[0].copy(), -1 * crossv)
+    return None
+
+
+def compatibles_plane(sh: Shape, pts, nrm, params) -> np.ndarray:
+    """plane.jl:114-130 with project2plane :82-103 (only the third coordinate matters)."""
+    eps = params["plane"]["eps"]
+    thr = math.cos(params["plane"]["alpha"])
+    o_z = normalize3(sh.b)
+    v = pts - sh.a
+    pz = dot3(o_z, v)
+    with np.errstate(invalid="ignore"):
+        return (dot3(sh.b, nrm) > thr) & (np.abs(pz) < eps)
+
+
+# ---- sphere --------------------------------------------------------------------------
+
+
+def fit2pointsphere(v, n, params) -> Shape:
+    """sphere.jl:29-75."""
+    sphere_par = params["sphere"]["sphere_par"]
+    par = params["common"]["parallelthrdeg"]
+    n1n = normalize3(n[0])
+    n2n = normalize3(n[1])
+    if abs(dot3(n1n, n2n)) > cosd(par):
+        c = (v[0] + v[1]) / 2
+        return Shape(SPHERE, c, np.zeros(3), float(norm3(c - v[0])), False)
+    g = v[1] - v[0]
+    h = cross3(n2n, g)
+    k = cross3(n2n, n1n)
+    nk = norm3(k)
+    nh = norm3(h)
+    if nk < sphere_par or nh < sphere_par:
+        n2 = cross3(n2n, cross3(n1n, n2n))
+        n1 = cross3(n1n, cross3(n2n, n1n))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            c1 = v[0] + dot3(v[1] - v[0], n2) / dot3(n[0], n2) * n[0]
+            c2 = v[1] + dot3(v[0] - v[1], n1) / dot3(n[1], n1) * n[1]
+        c = (c1 + c2) / 2
+        r = (norm3(v[0] - c) + norm3(v[0] - c)) / 2  # Q5
+        return Shape(SPHERE, c, np.zeros(3), float(r), False)
+    if dot3(h, k) > 0:
+        m = v[0] + nh / nk * n1n
+    else:
+        m = v[0] - nh / nk * n1n
+    return Shape(SPHERE, m, np.zeros(3), float(norm3(m - v[0])), False)
+
+
+def fit_sphere(p, n, params) -> Optional[Shape]:
+    """sphere.jl:87-114."""
+    p, n = _v(p), _v(n)
+    eps = params["sphere"]["eps"]
+    alpha = params["sphere"]["alpha"]
+    pl = len(p)
+    assert pl == len(n) and pl > 2
+    sp = fit2pointsphere(p, n, params)
+    thr = math.cos(alpha)
+    vert_ok = np.zeros(pl, bool)
+    norm_ok = np.zeros(pl, bool)
+    inv_ok = np.zeros(pl, bool)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(pl):
+            vert_ok[i] = abs(norm3(p[i] - sp.a) - sp.s) < eps
+            d = dot3(normalize3(p[i] - sp.a), normalize3(n[i]))
+            norm_ok[i] = d > thr
+            inv_ok[i] = d < -thr
+    if not vert_ok.all():
+        return None
+    if norm_ok.all():
+        sp.outwards = True
+        return sp
+    if inv_ok.all():
+        sp.outwards = False
+        return sp
+    return None
+
+
+def compatibles_sphere(sh: Shape, pts, nrm, params) -> np.ndarray:
+    """sphere.jl:144-172."""
+    eps = params["sphere"]["eps"]
+    thr = math.cos(params["sphere"]["alpha"])
+    o, R = sh.a, sh.s
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if sh.outwards:
+            u = normalize3(pts - o)
+        else:
+            u = normalize3(o - pts)
+        return (dot3(u, nrm) > thr) & (np.abs(norm3(pts - o) - R) < eps)
+
+
+# ---- cylinder ------------------------------------------------------------------------
+
+
+def _project2plane(n, w):
+    # cylinder.jl:46-59: w + n * (dot(-n, w) / dot(n, n))
+    return w + n * (dot3(-n, w) / dot3(n, n))
+
+
+def _projectto2d(xa, ya, za, p):
+    """cylinder.jl:61-85 (Cramer's rule, first two coordinates)."""
+    xx, xy, xz = xa
+    yx, yy, yz = ya
+    zx, zy, zz = za
+    px, py, pz = p
+    den = xz * yy * zx - xy * yz * zx - xz * yx * zy + xx * yz * zy + xy * yx * zz - xx * yy * zz
+    num1 = -(pz * yy * zx) + py * yz * zx + pz * yx * zy - px * yz * zy - py * yx * zz + px * yy * zz
+    num2 = pz * xy * zx - py * xz * zx - pz * xx * zy + px * xz * zy + py * xx * zz - px * xy * zz
+    return np.array([-(num1 / den), -(num2 / den)])
+
+
+def _lineintersection(a, b, c, d):
+    """cylinder.jl:87-101; det of an SMatrix{2,2} is the closed form a11*a22 - a12*a21."""
+    amb = a - b
+    cmd = c - d
+    d1 = a[0] * b[1] - a[1] * b[0]
+    d2 = c[0] * d[1] - c[1] * d[0]
+    d3 = amb[0] * cmd[1] - amb[1] * cmd[0]
+    return (d1 * cmd - d2 * amb) / d3
+
+
+def fit2pointcylinder(p, n, params) -> Optional[Shape]:
+    """cylinder.jl:34-125."""
+    par = params["common"]["parallelthrdeg"]
+    if abs(dot3(n[0], n[1])) > cosd(par):  # Q8: raw normals
+        return None
+    with np.errstate(invalid="ignore", divide="ignore"):
+        an = normalize3(cross3(n[0], n[1]))
+        xax = normalize3(_project2plane(an, p[0]))
+        yax = normalize3(cross3(an, xax))
+        p11 = _projectto2d(xax, yax, an, _project2plane(an, p[0]))
+        p12 = _projectto2d(xax, yax, an, _project2plane(an, p[0] + n[0]))
+        p21 = _projectto2d(xax, yax, an, _project2plane(an, p[1]))
+        p22 = _projectto2d(xax, yax, an, _project2plane(an, p[1] + n[1]))
+        ic = _lineintersection(p11, p12, p21, p22)
+        c = ic[0] * xax + ic[1] * yax
+        nn = [norm3(pt - c - an * dot3(an, pt - c)) for pt in (p[0], p[1])]
+        R = (nn[0] + nn[1]) / 2
+    return Shape(CYLINDER, an, c, float(R), True)
+
+
+def fit_cylinder(p, n, params) -> Optional[Shape]:
+    """cylinder.jl:135-168."""
+    p, n = _v(p), _v(n)
+    eps = params["cylinder"]["eps"]
+    alpha = params["cylinder"]["alpha"]
+    pl = len(p)
+    assert pl == len(n) and pl > 2
+    fc = fit2pointcylinder(p, n, params)
+    if fc is None:
+        return None
+    thr = math.cos(alpha)
+    vert_ok = np.zeros(pl, bool)
+    norm_ok = np.zeros(pl, bool)
+    inv_ok = np.zeros(pl, bool)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(pl):
+            cn = p[i] - fc.a * dot3(fc.a, p[i] - fc.b) - fc.b
+            vert_ok[i] = abs(norm3(cn) - fc.s) < eps
+            d = dot3(normalize3(cn), n[i])
+            norm_ok[i] = d > thr
+            inv_ok[i] = d < -thr
+    if not vert_ok.all():
+        return None
+    if norm_ok.all():
+        fc.outwards = True
+        return fc
+    if inv_ok.all():
+        fc.outwards = False
+        return fc
+    return None
+
+
+def compatibles_cylinder(sh: Shape, pts, nrm, params) -> np.ndarray:
+    """cylinder.jl:194-221."""
+    eps = params["cylinder"]["eps"]
+    thr = math.cos(params["cylinder"]["alpha"])
+    a, c, R = sh.a, sh.b, sh.s
+    with np.errstate(invalid="ignore", divide="ignore"):
+        h = dot3(a, pts - c)
+        cn = pts - a * h[..., None] - c
+        ok_r = np.abs(norm3(cn) - R) < eps
+        u = normalize3(cn)
+        if not sh.outwards:
+            u = -u
+        return ok_r & (dot3(u, nrm) > thr)
+
+
+# ---- cone ----------------------------------------------------------------------------
+
+
+def _rank_julia(m: np.ndarray) -> int:
+    """LinearAlgebra.rank: count(s .> min(size)*eps*maximum(s))."""
+    if not np.isfinite(m).all():
+        return -1
+    s = np.linalg.svd(m, compute_uv=False)
+    tol = min(m.shape) * np.finfo(F).eps * s.max()
+    return int((s > tol).sum())
+
+
+def fit3pointcone(p, n) -> Optional[Shape]:
+    """cone.jl:39-61."""
+    r = np.array([[n[i][j] for j in range(3)] for i in range(3)], dtype=F)
+    if _rank_julia(r) != 3:
+        return None
+    ds = np.array([dot3(p[i], n[i]) for i in range(3)])
+    rv = np.hstack([r, (-1 * ds)[:, None]])
+    if _rank_julia(rv) != 3:
+        return None
+    ap = np.linalg.solve(r, ds)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ax3 = [ap + ((p[i] - ap) / norm3(p[i] - ap)) for i in range(3)]
+        ax = normalize3(cross3(ax3[1] - ax3[0], ax3[2] - ax3[0]))
+        midp = (ax3[0] + ax3[1] + ax3[2]) / 3
+        dirv = normalize3(midp - ap)
+        if dot3(ax, dirv) < 0:
+            ax = -1 * ax
+        angles = [math.acos(_clamp(dot3(normalize3(p[i] - ap), ax))) for i in range(3)]
+    op = 2 * (angles[0] + angles[1] + angles[2]) / 3
+    return Shape(CONE, ap, ax, float(op), True)
+
+
+def _clamp(x):
+    if x != x:
+        return x
+    return min(max(x, -1.0), 1.0)
+
+
+def project2cone(sh: Shape, pts):
+    """cone.jl:68-85, vectorised over points; returns (dist, normal)."""
+    apex, axis, opang = sh.a, sh.b, sh.s
+    pts = np.atleast_2d(pts)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        to_point = apex - pts
+        to_pointn = normalize3(to_point)
+        rot_ax = normalize3(cross3(np.broadcast_to(axis, to_pointn.shape), to_pointn))
+        comp_n = normalize3(cross3(np.broadcast_to(axis, rot_ax.shape), rot_ax))
+        # rodriguesrad(rot_ax, -opang/2): utilities.jl:61-64 -> :19-24 -> :32-43
+        nv = normalize3(rot_ax)
+        th = -opang / 2
+        ct, st = math.cos(th), math.sin(th)
+        eye = np.eye(3)
+        outer = nv[:, :, None] * nv[:, None, :]
+        R = outer + ct * (eye[None] - outer)
+        R[:, 0, 1] -= st * nv[:, 2]
+        R[:, 0, 2] += st * nv[:, 1]
+        R[:, 1, 0] += st * nv[:, 2]
+        R[:, 1, 2] -= st * nv[:, 0]
+        R[:, 2, 0] -= st * nv[:, 1]
+        R[:, 2, 1] += st * nv[:, 0]
+        rv = np.stack(
+            [
+                R[:, i, 0] * comp_n[:, 0] + R[:, i, 1] * comp_n[:, 1] + R[:, i, 2] * comp_n[:, 2]
+                for i in range(3)
+            ],
+            axis=-1,
+        )
+        cur_n = normalize3(rv)
+        dist = dot3(-cur_n, -to_point)
+    return dist, cur_n
+
+
+def validatecone(sh: Shape, ps, ns, params) -> Optional[Shape]:
+    """cone.jl:87-115."""
+    eps = params["cone"]["eps"]
+    alpha = params["cone"]["alpha"]
+    minop = params["cone"]["minconeopang"]
+    dist, nr = project2cone(sh, ps)
+    for i in range(len(ps)):
+        if dist[i] > eps:  # Q6: signed
+            return None
+    if sh.s < minop:
+        return None
+    thr = math.cos(alpha)
+    with np.errstate(invalid="ignore"):
+        d = dot3(nr, ns)
+        norm_ok = d > thr
+        inv_ok = d < -thr
+    if norm_ok.all():
+        sh.outwards = True
+        return sh
+    if inv_ok.all():
+        sh.outwards = False
+        return sh
+    return None
+
+
+def fit_cone(p, n, params) -> Optional[Shape]:
+    """cone.jl:123-128."""
+    p, n = _v(p), _v(n)
+    fc = fit3pointcone(p, n)
+    if fc is None:
+        return None
+    return validatecone(fc, p, n, params)
+
+
+def compatibles_cone(sh: Shape, pts, nrm, params) -> np.ndarray:
+    """cone.jl:132-153."""
+    eps = params["cone"]["eps"]
+    thr = math.cos(params["cone"]["alpha"])
+    dist, nr = project2cone(sh, pts)
+    if not sh.outwards:
+        nr = -nr
+    with np.errstate(invalid="ignore"):
+        return (dot3(nr, nrm) > thr) & (np.abs(dist) < eps)
+
+
+FIT = {PLANE: fit_plane, SPHERE: fit_sphere, CYLINDER: fit_cylinder, CONE: fit_cone}
+COMPAT = {
+    PLANE: compatibles_plane,
+    SPHERE: compatibles_sphere,
+    CYLINDER: compatibles_cylinder,
+    CONE: compatibles_cone,
+}
+
+
+def compatibles(sh: Shape, pts, nrm, params, chunk: int = 1 << 18) -> np.ndarray:
+    """compatibles* for any shape, chunked so the cone's temporaries stay small."""
+    pts = np.asarray(pts, dtype=F)
+    nrm = np.asarray(nrm, dtype=F)
+    out = np.empty(len(pts), bool)
+    f = COMPAT[sh.kind]
+    for s in range(0, len(pts), chunk):
+        out[s : s + chunk] = f(sh, pts[s : s + chunk], nrm[s : s + chunk], params)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# confidence intervals (confidenceintervals.jl)
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class ConfidenceInterval:
+    min: float
+    max: float
+    E: float = field(init=False)
+
+    def __post_init__(self):
+        if self.min > self.max:
+            raise ValueError("out of order")  # confidenceintervals.jl:5
+        self.min = float(self.min)
+        self.max = float(self.max)
+        self.E = (self.min + self.max) / 2
+
+
+def notsoconfident(x, y) -> ConfidenceInterval:
+    # Julia's min/max propagate NaN; Python's do not
+    if x != x or y != y:
+        ci = ConfidenceInterval.__new__(ConfidenceInterval)
+        ci.min = ci.max = ci.E = float("nan")
+        return ci
+    return ConfidenceInterval(min(x, y), max(x, y))
+
+
+def isoverlap(i1: ConfidenceInterval, i2: ConfidenceInterval) -> bool:
+    if i1.min == i2.min:
+        return True
+    if i1.min < i2.min:
+        return i2.min <= i1.max
+    return isoverlap(i2, i1)
+
+
+def _wrap64(x: int) -> int:
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def hypergeomdev(N: int, x: int, n: int):
+    """confidenceintervals.jl:53-59 with Int64 wrap-around (Q9)."""
+    prod = _wrap64(_wrap64(_wrap64(x * n) * (N - x)) * (N - n))
+    sq_ = prod / (N - 1)
+    sq = 0.0 if sq_ < 0 else math.sqrt(sq_)
+    xn = _wrap64(x * n)
+    return (xn + sq) / N, (xn - sq) / N
+
+
+def estimatescore(S1length: int, Plength: int, sigma: int) -> ConfidenceInterval:
+    """confidenceintervals.jl:71-74."""
+    gmin, gmax = hypergeomdev(-2 - S1length, -2 - Plength, -1 - sigma)
+    return notsoconfident(-1 - gmin, -1 - gmax)
+
+
+def prob(n, s, N, k):
+    """utilities.jl:262."""
+    return 1 - (1 - (n / N) ** k) ** s
+
+
+# --------------------------------------------------------------------------------------
+# cloud, scoring, refit (octree.jl:37-138, shapes/*.jl scorecandidate/refit)
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class Cloud:
+    vertices: np.ndarray  # (N,3) float64
+    normals: np.ndarray  # (N,3) float64
+    subsets: List[np.ndarray]  # 0-based index arrays (a partition)
+    isenabled: np.ndarray = None  # (N,) bool
+    size: int = 0
+
+    def __post_init__(self):
+        self.vertices = np.asarray(self.vertices, dtype=F)
+        self.normals = np.asarray(self.normals, dtype=F)
+        self.size = len(self.vertices)
+        if self.isenabled is None:
+            self.isenabled = np.ones(self.size, bool)
+
+
+def make_subsets(n: int, numofsubsets: int, perm: np.ndarray) -> List[np.ndarray]:
+    """octree.jl:129-135 given the permutation (Julia's randperm stream is not reproducible)."""
+    ssl = n // numofsubsets
+    subs = [perm[i * ssl : (i + 1) * ssl] for i in range(numofsubsets - 1)]
+    subs.append(perm[(numofsubsets - 1) * ssl :])
+    return subs
+
+
+def scorecandidate(pc: Cloud, sh: Shape, subset_id: int, params) -> Tuple[ConfidenceInterval, np.ndarray]:
+    sub = pc.subsets[subset_id]
+    cp = compatibles(sh, pc.vertices[sub], pc.normals[sub], params)
+    if sh.kind != SPHERE:  # Q4: sphere.jl:121,131 never applies `ens`
+        cp = cp & pc.isenabled[sub]
+    inpoints = sub[cp]
+    return estimatescore(len(sub), pc.size, len(inpoints)), inpoints
+
+
+def refit(sh: Shape, pc: Cloud, params) -> np.ndarray:
+    """refit: compatible points among the enabled points of the whole cloud (ascending)."""
+    en = np.flatnonzero(pc.isenabled)
+    cp = compatibles(sh, pc.vertices[en], pc.normals[en], params)
+    return en[cp]
+
+
+def findhighestscore(scores: Sequence[ConfidenceInterval]) -> Tuple[int, bool]:
+    """fitting.jl:140-158 (0-based index, -1 when empty)."""
+    if len(scores) == 0:
+        return -1, False
+    ind = 0
+    highest = scores[0].E
+    for i, sc in enumerate(scores):
+        if sc.E > highest:
+            highest = sc.E
+            ind = i
+    for i, sc in enumerate(scores):
+        if i == ind:
+            continue
+        if isoverlap(sc, scores[ind]):
+            return ind, True
+    return ind, False
+
+
+# --------------------------------------------------------------------------------------
+# Philox4x32-10 (Salmon et al., SC'11) -- the stream the CUDA sampler uses, so that the
+# oracle and the device draw identical minimal sets (the reference's own RNG stream is
+# Julia-version dependent, Q19, and therefore not part of the parity contract).
+# --------------------------------------------------------------------------------------
+
+_PH_M0, _PH_M1 = 0xD2511F53, 0xCD9E8D57
+_PH_W0, _PH_W1 = 0x9E3779B9, 0xBB67AE85
+_M32 = 0xFFFFFFFF
+
+
+def philox4x32(counter: Tuple[int, int, int, int], key: Tuple[int, int]) -> Tuple[int, int, int, int]:
+    c0, c1, c2, c3 = counter
+    k0, k1 = key
+    for _ in range(10):
+        p0 = _PH_M0 * c0
+        p1 = _PH_M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & _M32, p1 & _M32, ((p0 >> 32) ^ c3 ^ k1) & _M32, p0 & _M32
+        k0 = (k0 + _PH_W0) & _M32
+        k1 = (k1 + _PH_W1) & _M32
+    return c0, c1, c2, c3
+
+
+class SetStream:
+    """Random draws of ONE minimal set: Philox key = seed, counter = (draw/2, set_lo, set_hi, 0).
+
+    Each Philox block yields two 64-bit words; rand_below(n) = mulhi64(word, n).
+    """
+
+    def __init__(self, seed: int, set_id: int):
+        self.key = (seed & _M32, (seed >> 32) & _M32)
+        self.set_id = set_id
+        self.ndraw = 0
+        self._blk = None
+
+    def next_u64(self) -> int:
+        i = self.ndraw
+        if i % 2 == 0:
+            self._blk = philox4x32((i // 2, self.set_id & _M32, (self.set_id >> 32) & _M32, 0), self.key)
+        b = self._blk
+        self.ndraw += 1
+        return (b[0] | (b[1] << 32)) if i % 2 == 0 else (b[2] | (b[3] << 32))
+
+    def rand_below(self, n: int) -> int:
+        return (self.next_u64() * n) >> 64
+
+
+def sample_minimal_set(pc: Cloud, drawN: int, stream: SetStream, enabled_idx: Optional[np.ndarray] = None):
+    """samplepointcloud4! (fitting.jl:383-430) restricted to the root cell (Q1).
+
+    Returns (ok, code, idx[drawN]) -- code 0 = too few enabled points, 1 = duplicate index.
+    """
+    N = pc.size
+    r1 = stream.rand_below(N)
+    while not pc.isenabled[r1]:
+        r1 = stream.rand_below(N)
+    if enabled_idx is None:
+        enabled_idx = np.flatnonzero(pc.isenabled)
+    ne = len(enabled_idx)
+    idx = np.zeros(drawN, np.int64)
+    if ne < drawN:
+        return False, 0, idx
+    idx[0] = r1
+    for k in range(1, drawN):
+        nexti = stream.rand_below(ne)
+        if idx[0] == enabled_idx[nexti]:
+            nexti = stream.rand_below(ne)
+        idx[k] = enabled_idx[nexti]
+    for i in range(1, drawN):
+        for j in range(i):
+            if idx[i] == idx[j]:
+                return False, 1, idx
+    return True, 1, idx
+
+
+# --------------------------------------------------------------------------------------
+# the loop (iterations.jl:35-162)
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class Extracted:
+    shape: Shape
+    inpoints: np.ndarray
+
+
+@dataclass
+class RansacTrace:
+    iterations: int = 0
+    sets_drawn: int = 0
+    candidates_scored: int = 0
+    evals: int = 0
+    extracted_at: List[int] = field(default_factory=list)
+
+
+def forcefit(p, n, params) -> List[Shape]:
+    """forcefitshapes! (fitting.jl:165-173): candidates in shape_types order."""
+    out = []
+    for s in params["iteration"]["shape_types"]:
+        sh = FIT[s](p, n, params)
+        if sh is not None:
+            out.append(sh)
+    return out
+
+
+def ransac(
+    pc: Cloud,
+    params: dict,
+    setenabled: bool = True,
+    seed: int = 1234,
+    minimal_sets: Optional[Callable[[int, int], Optional[np.ndarray]]] = None,
+    trace: Optional[RansacTrace] = None,
+) -> List[Extracted]:
+    """iterations.jl:14-21 + :35-162.
+
+    `minimal_sets(k, i)` may supply the index triple of minimal set i of iteration k (or None
+    for a failed sample); by default the Philox sampler above is used with set_id =
+    (k-1)*minsubsetN + i.
+    """
+    it = params["iteration"]
+    drawN, minsubsetN, prob_det, tau = it["drawN"], it["minsubsetN"], it["prob_det"], it["tau"]
+    itermax = it["itermax"]
+    sidx = {"lengthC": 0, "allcand": 1, "nofminset": 2}
+    if setenabled:
+        pc.isenabled[:] = True
+    shapes: List[Shape] = []
+    scores: List[ConfidenceInterval] = []
+    inpts: List[np.ndarray] = []
+    extracted: List[Extracted] = []
+    cc = [0, 0, 0]
+    tr = trace if trace is not None else RansacTrace()
+    for k in range(1, itermax + 1):
+        if int(pc.isenabled.sum()) < tau:
+            break
+        tr.iterations = k
+        cands: List[Shape] = []
+        en_idx = np.flatnonzero(pc.isenabled)
+        for i in range(minsubsetN):
+            if minimal_sets is not None:
+                sd = minimal_sets(k, i)
+                if sd is None:
+                    continue
+            else:
+                ok, _, sd = sample_minimal_set(pc, drawN, SetStream(seed, (k - 1) * minsubsetN + i), en_idx)
+                if not ok:
+                    continue
+            cands.extend(forcefit(pc.vertices[sd], pc.normals[sd], params))
+        cc[1] += len(cands)
+        for c in cands:  # scorecandidates! (fitting.jl:181-190), subset 1 only (Q10)
+            sc, ip = scorecandidate(pc, c, 0, params)
+            shapes.append(c)
+            scores.append(sc)
+            inpts.append(ip)
+            tr.candidates_scored += 1
+            tr.evals += len(pc.subsets[0])
+        cc[2] = k * minsubsetN
+        tr.sets_drawn = cc[2]
+        cc[0] = len(shapes)
+        if len(shapes) >= 1:
+            best, _ = findhighestscore(scores)
+            scr = scores[best].E
+            s = cc[sidx[it["extract_s"]]]
+            if prob(scr, s, pc.size, drawN) > prob_det:
+                ip = refit(shapes[best], pc, params)
+                tr.evals += int(pc.isenabled.sum())
+                pc.isenabled[ip] = False
+                extracted.append(Extracted(shapes[best], ip))
+                tr.extracted_at.append(k)
+                del shapes[best], scores[best], inpts[best]
+                keep = [j for j in range(len(shapes)) if pc.isenabled[inpts[j]].all()]
+                shapes = [shapes[j] for j in keep]
+                scores = [scores[j] for j in keep]
+                inpts = [inpts[j] for j in keep]
+        s = cc[sidx[it["terminate_s"]]]
+        if prob(tau, s, pc.size, drawN) > prob_det:
+            break
+    return extracted

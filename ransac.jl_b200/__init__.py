@@ -1,0 +1,50 @@
+"""ransac.jl_b200 -- B200 (sm_100a) hot path of efficient-RANSAC shape detection behind the public
+surface of cserteGT3/RANSAC.jl.  Host layer in Python (Julia is not available in this image; the
+Julia `ccall` binding is in julia/ and INTEGRATION.md), compute in libransac_b200.so (csrc/).
+
+Import fails loudly when the CUDA library has not been built; a context cannot be created without
+an sm_100 device.  There is no CPU fallback anywhere in this package.
+"""
+from . import _lib
+from ._lib import Context, RscError
+from .cloud import RANSACCloud, makesubsets
+from .confidence import ConfidenceInterval, E, estimatescore, isoverlap, notsoconfident, prob
+from .fitting import (
+    IterationCandidates,
+    findhighestscore,
+    fit,
+    fit_batch,
+    fit_points,
+    invalidate_indexes,
+    refit,
+    sample_fit,
+    score_counts,
+    scorecandidate,
+    scorecandidates,
+    unpack_mask,
+)
+from .iterations import ransac
+from .params import (
+    DEFAULT_PARAMETERS,
+    DEFAULT_SHAPE_DICT,
+    DEFAULT_SHAPE_TYPES,
+    defaultcommonparameters,
+    defaultiterationparameters,
+    defaultparameters,
+    defaultshapeparameters,
+    ransacparameters,
+    to_c,
+)
+from .shapes import (
+    ExtractedShape,
+    FittedCone,
+    FittedCylinder,
+    FittedPlane,
+    FittedShape,
+    FittedSphere,
+    from_cand,
+    pack_cands,
+    strt,
+)
+
+__all__ = [n for n in dir() if not n.startswith("_")]

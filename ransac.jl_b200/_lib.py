@@ -1,0 +1,148 @@
+"""ctypes binding of libransac_b200.so (include/rsc.h).
+
+There is no CPU fallback: if the shared library is missing this module raises ImportError, and
+without an sm_100 device `rsc_ctx_create` fails (RSC_E_NODEVICE) -- loudly, by design.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libransac_b200.so")
+
+RSC_PLANE, RSC_SPHERE, RSC_CYLINDER, RSC_CONE = 0, 1, 2, 3
+RSC_NTYPES = 4
+RSC_S_LENGTHC, RSC_S_ALLCAND, RSC_S_NOFMINSET = 0, 1, 2
+RSC_COMPAT_SPHERE_IGNORES_ENABLED = 1
+RSC_E_NODEVICE = -3
+
+ERRORS = {-1: "RSC_E_ARG", -2: "RSC_E_CUDA", -3: "RSC_E_NODEVICE", -4: "RSC_E_NOMEM", -5: "RSC_E_STATE", -6: "RSC_E_NCCL"}
+
+
+class rsc_cand(C.Structure):
+    _fields_ = [("type", C.c_int32), ("outwards", C.c_int32), ("p", C.c_double * 7)]
+
+
+class rsc_params(C.Structure):
+    _fields_ = [
+        ("drawN", C.c_int32),
+        ("minsubsetN", C.c_int32),
+        ("prob_det", C.c_double),
+        ("tau", C.c_int64),
+        ("itermax", C.c_int32),
+        ("extract_s", C.c_int32),
+        ("terminate_s", C.c_int32),
+        ("n_shape_types", C.c_int32),
+        ("shape_types", C.c_int32 * 4),
+        ("collin_threshold", C.c_double),
+        ("parallelthrdeg", C.c_double),
+        ("eps", C.c_double * 4),
+        ("alpha", C.c_double * 4),
+        ("sphere_par", C.c_double),
+        ("minconeopang", C.c_double),
+        ("compat_flags", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+class rsc_stats(C.Structure):
+    _fields_ = [
+        ("evals", C.c_int64),
+        ("exact_pairs", C.c_int64),
+        ("sets_drawn", C.c_int64),
+        ("cands_scored", C.c_int64),
+        ("score_launches", C.c_int64),
+        ("score_ms", C.c_double),
+        ("last_kernel_ms", C.c_double),
+    ]
+
+
+#: every symbol include/rsc.h declares: (restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    "rsc_version": (C.c_int32, []),
+    "rsc_params_default": (None, [C.POINTER(rsc_params)]),
+    "rsc_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(_P)]),
+    "rsc_ctx_destroy": (None, [_P]),
+    "rsc_last_error": (C.c_char_p, [_P]),
+    "rsc_ctx_stats": (C.c_int32, [_P, C.POINTER(rsc_stats)]),
+    "rsc_ctx_stream": (_P, [_P]),
+    "rsc_ctx_last_kernel": (C.c_int32, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "rsc_cloud_create": (C.c_int32, [_P, _P, _P, C.c_int64, C.POINTER(_P)]),
+    "rsc_cloud_create_f64": (C.c_int32, [_P, _P, _P, C.c_int64, C.POINTER(_P)]),
+    "rsc_cloud_create_shard": (C.c_int32, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "rsc_cloud_destroy": (None, [_P]),
+    "rsc_cloud_size": (C.c_int64, [_P]),
+    "rsc_cloud_set_subset": (C.c_int32, [_P, C.c_int32, _P, C.c_int64]),
+    "rsc_cloud_subset_size": (C.c_int64, [_P, C.c_int32]),
+    "rsc_cloud_get_enabled": (C.c_int32, [_P, _P]),
+    "rsc_cloud_set_enabled": (C.c_int32, [_P, _P]),
+    "rsc_cloud_enable_all": (C.c_int32, [_P]),
+    "rsc_cloud_count_enabled": (C.c_int64, [_P]),
+    "rsc_score": (C.c_int32, [_P, C.POINTER(rsc_params), _P, C.c_int32, C.c_int32, _P, _P]),
+    "rsc_score_dev": (C.c_int32, [_P, C.POINTER(rsc_params), _P, C.c_int32, C.c_int32, _P, _P]),
+    "rsc_estimate_score": (None, [C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "rsc_fit_batch": (C.c_int32, [_P, C.POINTER(rsc_params), _P, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
+    "rsc_fit_points": (C.c_int32, [_P, C.POINTER(rsc_params), _P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
+    "rsc_sample_fit": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.c_uint64, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)]),
+    "rsc_refit_extract": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), _P, C.POINTER(C.c_int64), C.c_int32]),
+    "rsc_ransac_run": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.POINTER(_P)]),
+    "rsc_run_nshapes": (C.c_int32, [_P]),
+    "rsc_run_iterations": (C.c_int32, [_P]),
+    "rsc_run_seconds": (C.c_double, [_P]),
+    "rsc_run_shape": (C.c_int32, [_P, C.c_int32, C.POINTER(rsc_cand), C.POINTER(C.c_int64)]),
+    "rsc_run_inpoints": (C.c_int32, [_P, C.c_int32, _P]),
+    "rsc_run_destroy": (None, [_P]),
+}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(make -C ransac.jl_b200/csrc). There is no CPU fallback."
+    )
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SIGNATURES.items():
+    _f = getattr(lib, _name)  # AttributeError here = header/library mismatch
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class RscError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Context:
+    """One CUDA device + stream (rsc_ctx). Created lazily per device."""
+
+    _by_device: dict = {}
+
+    def __init__(self, device: int = 0):
+        h = _P()
+        rc = lib.rsc_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise RscError(rc, "rsc_ctx_create failed (an sm_100 / B200 device is required; no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    @classmethod
+    def get(cls, device: int = 0) -> "Context":
+        if device not in cls._by_device:
+            cls._by_device[device] = Context(device)
+        return cls._by_device[device]
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise RscError(rc, lib.rsc_last_error(self.h).decode())
+
+    def stats(self) -> rsc_stats:
+        s = rsc_stats()
+        self.check(lib.rsc_ctx_stats(self.h, C.byref(s)))
+        return s
+
+    @property
+    def stream(self) -> int:
+        return lib.rsc_ctx_stream(self.h) or 0

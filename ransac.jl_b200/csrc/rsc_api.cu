@@ -1,0 +1,287 @@
+// rsc_api.cu -- extern "C" entry points of libransac_b200 (include/rsc.h): context, scoring,
+// refit/extract, score statistics.  Host-side glue only; the kernels live in rsc_score.cu,
+// rsc_extract.cu, rsc_fit.cu, rsc_cloud.cu.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "rsc_common.cuh"
+
+namespace rsc {
+
+int32_t fail(rsc_ctx* ctx, int32_t code, const char* what) {
+  if (ctx) ctx->err = what ? what : "error";
+  return code;
+}
+
+int32_t fail_cuda(rsc_ctx* ctx, cudaError_t e, const char* where) {
+  if (ctx) {
+    ctx->err = std::string(where ? where : "cuda") + ": " + cudaGetErrorString(e);
+  }
+  return e == cudaErrorMemoryAllocation ? RSC_E_NOMEM : RSC_E_CUDA;
+}
+
+static int32_t check_params(rsc_ctx* ctx, const rsc_params* p) {
+  if (!p) return fail(ctx, RSC_E_ARG, "params is null");
+  for (int t = 0; t < RSC_NTYPES; ++t)
+    if (!(p->eps[t] == p->eps[t]) || !(p->alpha[t] == p->alpha[t])) return fail(ctx, RSC_E_ARG, "params: NaN threshold");
+  return RSC_OK;
+}
+
+static int32_t pick_pointset(rsc_cloud* cloud, int32_t subset_id, PointSet* ps) {
+  rsc_ctx* ctx = cloud->ctx;
+  if (subset_id < 0) {
+    *ps = view_cloud(cloud);
+    return RSC_OK;
+  }
+  if ((size_t)subset_id >= cloud->subsets.size() || !cloud->subsets[subset_id].soa)
+    return fail(ctx, RSC_E_STATE, "score: subset not uploaded (rsc_cloud_set_subset)");
+  *ps = view_subset(&cloud->subsets[subset_id]);
+  return RSC_OK;
+}
+
+}  // namespace rsc
+
+using namespace rsc;
+
+extern "C" {
+
+int32_t rsc_version(void) { return RSC_VERSION; }
+
+void rsc_params_default(rsc_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof(*p));
+  // utilities.jl:345,371; plane.jl:22; sphere.jl:25; cylinder.jl:27; cone.jl:30; RANSAC.jl:94
+  p->drawN = 3;
+  p->minsubsetN = 15;
+  p->prob_det = 0.9;
+  p->tau = 900;
+  p->itermax = 1000;
+  p->extract_s = RSC_S_NOFMINSET;
+  p->terminate_s = RSC_S_NOFMINSET;
+  p->n_shape_types = 4;
+  p->shape_types[0] = RSC_PLANE;
+  p->shape_types[1] = RSC_CONE;
+  p->shape_types[2] = RSC_CYLINDER;
+  p->shape_types[3] = RSC_SPHERE;
+  p->collin_threshold = 0.2;
+  p->parallelthrdeg = 1.0;
+  const double five_deg = 5.0 * 3.14159265358979323846 / 180.0;
+  for (int t = 0; t < RSC_NTYPES; ++t) {
+    p->eps[t] = 0.3;
+    p->alpha[t] = five_deg;
+  }
+  p->sphere_par = 0.02;
+  p->minconeopang = 2.0 * 3.14159265358979323846 / 180.0;
+  p->compat_flags = RSC_COMPAT_DEFAULT;
+}
+
+int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
+  if (!out) return RSC_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return RSC_E_NODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return RSC_E_NODEVICE;
+  if (prop.major != 10) return RSC_E_NODEVICE;  // built for sm_100a only; there is no fallback
+  if (cudaSetDevice(device) != cudaSuccess) return RSC_E_CUDA;
+  rsc_ctx* ctx = new rsc_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+      cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess) {
+    delete ctx;
+    return RSC_E_CUDA;
+  }
+  *out = ctx;
+  return RSC_OK;
+}
+
+void rsc_ctx_destroy(rsc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  rsc::DevBuf* bufs[] = {&ctx->cands,    &ctx->rec,      &ctx->orig,     &ctx->slot_of, &ctx->blktab,
+                         &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count,
+                         &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf};
+  for (auto* b : bufs) b->release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaEventDestroy(ctx->evk0);
+  cudaEventDestroy(ctx->evk1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* rsc_last_error(const rsc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int32_t rsc_ctx_stats(rsc_ctx* ctx, rsc_stats* out) {
+  if (!ctx || !out) return RSC_E_ARG;
+  *out = ctx->stats;
+  return RSC_OK;
+}
+
+void* rsc_ctx_stream(rsc_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t rsc_ctx_last_kernel(rsc_ctx* ctx, double* kernel_ms, int64_t* guard_pairs) {
+  if (!ctx) return RSC_E_ARG;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  RSC_CUDA(ctx, cudaDeviceSynchronize());
+  if (kernel_ms) {
+    float ms = 0.f;
+    RSC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1));
+    *kernel_ms = ms;
+    ctx->stats.last_kernel_ms = ms;
+  }
+  if (guard_pairs) {
+    uint32_t n = 0;
+    if (ctx->wl_count.p) RSC_CUDA(ctx, cudaMemcpy(&n, ctx->wl_count.p, sizeof(n), cudaMemcpyDeviceToHost));
+    *guard_pairs = n;
+  }
+  return RSC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scoring
+// ---------------------------------------------------------------------------------------------
+int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C,
+                  int32_t subset_id, int32_t* counts, uint32_t* masks) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (C < 0 || (C > 0 && (!cands || !counts))) return fail(ctx, RSC_E_ARG, "score: null candidates/counts");
+  int32_t rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (C == 0) return RSC_OK;
+  for (int i = 0; i < C; ++i)
+    if (cands[i].type < 0 || cands[i].type >= RSC_NTYPES) return fail(ctx, RSC_E_ARG, "score: unknown shape type");
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  PointSet ps;
+  if ((rc = pick_pointset(cloud, subset_id, &ps))) return rc;
+  const Thresh th = make_thresh(params);
+  cudaStream_t st = ctx->stream;
+
+  // candidates + host-libm cos/sin(-opang/2) for the FP64 path (cone.jl:78)
+  std::vector<double> trig((size_t)2 * C, 0.0);
+  for (int i = 0; i < C; ++i)
+    if (cands[i].type == RSC_CONE) {
+      trig[2 * i] = cos(-cands[i].p[6] / 2);
+      trig[2 * i + 1] = sin(-cands[i].p[6] / 2);
+    }
+  RSC_CUDA(ctx, ctx->cands.ensure((size_t)C * sizeof(rsc_cand)));
+  RSC_CUDA(ctx, ctx->aux.ensure((size_t)2 * C * sizeof(double)));
+  RSC_CUDA(ctx, ctx->counts.ensure((size_t)3 * C * sizeof(int32_t)));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->cands.p, cands, (size_t)C * sizeof(rsc_cand), cudaMemcpyHostToDevice, st));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->aux.p, trig.data(), (size_t)2 * C * sizeof(double), cudaMemcpyHostToDevice, st));
+
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    RSC_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
+    int32_t* d_policy = ctx->counts.as<int32_t>() + 2 * (size_t)C;
+    rc = score_enqueue(ctx, cloud, ps, th, ctx->cands.as<rsc_cand>(), C, d_policy, masks != nullptr, st,
+                       ctx->counts.as<int32_t>(), ctx->counts.as<int32_t>() + C, ctx->aux.as<double>());
+    if (rc) return rc;
+    RSC_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
+    uint32_t namb = 0;
+    RSC_CUDA(ctx, cudaMemcpyAsync(counts, d_policy, (size_t)C * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RSC_CUDA(ctx, cudaMemcpyAsync(&namb, ctx->wl_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RSC_CUDA(ctx, cudaStreamSynchronize(st));
+    if ((size_t)namb > ctx->wl_cap) {  // guard-band queue overflowed: grow and redo the pass
+      ctx->wl_cap = (size_t)namb + (size_t)namb / 4 + 1024;
+      ctx->stats.evals -= (int64_t)C * ps.n;
+      ctx->stats.cands_scored -= C;
+      continue;
+    }
+    ctx->stats.exact_pairs += namb;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->stats.score_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1);
+    ctx->stats.last_kernel_ms = ms;
+    if (masks) {
+      if ((rc = masks_to_candidate_major(ctx, C, ps.n, st))) return rc;
+      const size_t words = (size_t)((ps.n + 31) / 32);
+      RSC_CUDA(ctx, cudaMemcpyAsync(masks, ctx->masks_cm.p, (size_t)C * words * 4, cudaMemcpyDeviceToHost, st));
+      RSC_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return RSC_OK;
+  }
+  return fail(ctx, RSC_E_STATE, "score: guard-band queue kept overflowing");
+}
+
+int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,
+                      int32_t subset_id, int32_t* d_counts, void* stream) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (C < 0 || (C > 0 && (!d_cands || !d_counts))) return fail(ctx, RSC_E_ARG, "score_dev: null device pointers");
+  int32_t rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (C == 0) return RSC_OK;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  PointSet ps;
+  if ((rc = pick_pointset(cloud, subset_id, &ps))) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  return score_enqueue(ctx, cloud, ps, make_thresh(params), d_cands, C, d_counts, false, st);
+}
+
+static inline int64_t wrapmul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
+
+void rsc_estimate_score(int64_t subset_len, int64_t cloud_len, int64_t count, double* out_min, double* out_max,
+                        double* out_E) {
+  // confidenceintervals.jl:53-74 with Julia's Int64 wrap-around (Q9)
+  const int64_t N = -2 - subset_len, x = -2 - cloud_len, n = -1 - count;
+  const int64_t xn = wrapmul(x, n);
+  const int64_t prod = wrapmul(wrapmul(xn, N - x), N - n);
+  const double sq_ = (double)prod / (double)(N - 1);
+  const double sq = sq_ < 0 ? 0.0 : sqrt(sq_);
+  const double a = -1 - ((double)xn + sq) / (double)N;
+  const double b = -1 - ((double)xn - sq) / (double)N;
+  double lo, hi;
+  if (a != a || b != b) {
+    lo = hi = NAN;
+  } else {
+    lo = a < b ? a : b;
+    hi = a < b ? b : a;
+  }
+  if (out_min) *out_min = lo;
+  if (out_max) *out_max = hi;
+  if (out_E) *out_E = (lo + hi) / 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// refit + invalidate
+// ---------------------------------------------------------------------------------------------
+int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand, int64_t* out_idx,
+                          int64_t* out_n, int32_t disable) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (!cand || !out_n) return fail(ctx, RSC_E_ARG, "refit_extract: null candidate/out_n");
+  if (cand->type < 0 || cand->type >= RSC_NTYPES) return fail(ctx, RSC_E_ARG, "refit_extract: unknown shape type");
+  int32_t rc = check_params(ctx, params);
+  if (rc) return rc;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  Thresh th = make_thresh(params);
+  th.honour_enabled = 0xFu;  // refit always works on the enabled points (e.g. sphere.jl:181-185)
+  if ((rc = refit_mask_enqueue(cloud, th, *cand, st))) return rc;
+  unsigned long long total = 0;
+  RSC_CUDA(ctx, cudaMemcpyAsync(&total, ctx->misc2.p, sizeof(total), cudaMemcpyDeviceToHost, st));
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  *out_n = (int64_t)total;
+  int64_t* d_out = nullptr;
+  if (out_idx && total) {
+    RSC_CUDA(ctx, ctx->misc.ensure((size_t)total * sizeof(int64_t)));
+    d_out = ctx->misc.as<int64_t>();
+  }
+  if (d_out || disable) {
+    if ((rc = refit_write_enqueue(cloud, d_out, disable != 0, st))) return rc;
+    if (d_out)
+      RSC_CUDA(ctx, cudaMemcpyAsync(out_idx, d_out, (size_t)total * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  }
+  return RSC_OK;
+}
+
+}  // extern "C"

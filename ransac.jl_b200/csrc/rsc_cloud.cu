@@ -1,0 +1,279 @@
+// rsc_cloud.cu -- the device-resident RANSACCloud (octree.jl:37-59, constructors :78-138):
+// AoS host arrays -> SoA float32 in HBM, the enabled bitmask (BitArray.chunks layout), and the
+// gathered contiguous copies of the random subsets (octree.jl:129-135) that scoring streams.
+#include <math.h>
+#include <string.h>
+
+#include "rsc_common.cuh"
+
+namespace rsc {
+
+template <class T>
+__global__ void aos_to_soa_kernel(const T* __restrict__ xyz, const T* __restrict__ nrm, int64_t n,
+                                  int64_t n_pad, float* __restrict__ soa, uint32_t* __restrict__ bounds) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float p2 = 0.f, n2 = 0.f;
+  if (i < n) {
+    const float x = (float)xyz[3 * i], y = (float)xyz[3 * i + 1], z = (float)xyz[3 * i + 2];
+    const float a = (float)nrm[3 * i], b = (float)nrm[3 * i + 1], c = (float)nrm[3 * i + 2];
+    soa[i] = x;
+    soa[n_pad + i] = y;
+    soa[2 * n_pad + i] = z;
+    soa[3 * n_pad + i] = a;
+    soa[4 * n_pad + i] = b;
+    soa[5 * n_pad + i] = c;
+    p2 = x * x + y * y + z * z;
+    n2 = a * a + b * b + c * c;
+    if (!(p2 == p2)) p2 = 0.f;  // NaN points do not widen the band
+    if (!(n2 == n2)) n2 = 0.f;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    p2 = fmaxf(p2, __shfl_xor_sync(0xffffffffu, p2, d));
+    n2 = fmaxf(n2, __shfl_xor_sync(0xffffffffu, n2, d));
+  }
+  if ((threadIdx.x & 31) == 0) {  // non-negative floats order like their bit patterns
+    atomicMax(bounds, __float_as_uint(p2));
+    atomicMax(bounds + 1, __float_as_uint(n2));
+  }
+}
+
+__global__ void fill_valid_kernel(uint32_t* __restrict__ valid, uint32_t* __restrict__ enabled,
+                                  int64_t n, int64_t words) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  const int64_t lo = w * 32;
+  uint32_t v = 0;
+  if (lo + 32 <= n)
+    v = 0xffffffffu;
+  else if (lo < n)
+    v = (1u << (n - lo)) - 1u;
+  valid[w] = v;
+  if (enabled) enabled[w] = v;
+}
+
+__global__ void and_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ m, int64_t words) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < words) dst[w] &= m[w];
+}
+
+__global__ void gather_subset_kernel(const float* __restrict__ soa, int64_t n_pad, const int64_t* __restrict__ idx,
+                                     int64_t m, int64_t m_pad, float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const int64_t i = idx[j];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) out[f * m_pad + j] = soa[f * n_pad + i];
+}
+
+// one warp per subset word: bit j = enabled[idx[j]]
+__global__ void gather_enabled_kernel(const uint32_t* __restrict__ enabled, const int64_t* __restrict__ idx,
+                                      int64_t m, int64_t words, uint32_t* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool b = false;
+  if (j < m) {
+    const int64_t i = idx[j];
+    b = (enabled[i >> 5] >> (i & 31)) & 1u;
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0 && (j >> 5) < words) out[j >> 5] = bal;
+}
+
+__global__ void popc_words_kernel(const uint32_t* __restrict__ w, int64_t words, unsigned long long* __restrict__ out) {
+  unsigned long long s = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x)
+    s += __popc(w[i]);
+#pragma unroll
+  for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st) {
+  rsc_ctx* ctx = cloud->ctx;
+  for (auto& s : cloud->subsets) {
+    if (!s.soa) continue;
+    const int64_t words = s.m_pad / 32;
+    const int64_t threads = words * 32;
+    gather_enabled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cloud->enabled, s.idx, s.m, words, s.enabled);
+    RSC_CUDA(ctx, cudaGetLastError());
+  }
+  return RSC_OK;
+}
+
+template <class T>
+static int32_t cloud_create_impl(rsc_ctx* ctx, const T* xyz, const T* nrm, int64_t n, int64_t global_offset,
+                                 int64_t n_global, rsc_cloud** out) {
+  if (!ctx || !out) return RSC_E_ARG;
+  *out = nullptr;
+  if (!xyz || !nrm || n <= 0) return fail(ctx, RSC_E_ARG, "cloud_create: empty cloud or null arrays");
+  if (n >= ((int64_t)1 << 32) - kTile) return fail(ctx, RSC_E_ARG, "cloud_create: shard too large (>= 2^32 points)");
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  rsc_cloud* c = new rsc_cloud();
+  c->ctx = ctx;
+  c->n = n;
+  c->n_pad = (n + kTile - 1) / kTile * kTile;
+  c->global_offset = global_offset;
+  c->n_global = n_global;
+  cudaStream_t st = ctx->stream;
+  const int64_t words = c->n_pad / 32;
+  cudaError_t e;
+  if ((e = cudaMalloc(&c->soa, (size_t)6 * c->n_pad * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&c->enabled, (size_t)words * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&c->valid, (size_t)words * 4)) != cudaSuccess) {
+    rsc_cloud_destroy(c);
+    return fail_cuda(ctx, e, "cloud_create: cudaMalloc");
+  }
+  RSC_CUDA(ctx, cudaMemsetAsync(c->soa, 0, (size_t)6 * c->n_pad * sizeof(float), st));
+  // stage the AoS arrays in device scratch, transpose on the device
+  const size_t bytes = (size_t)3 * n * sizeof(T);
+  RSC_CUDA(ctx, ctx->misc.ensure(bytes));
+  RSC_CUDA(ctx, ctx->misc2.ensure(bytes + 16));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, xyz, bytes, cudaMemcpyHostToDevice, st));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc2.p, nrm, bytes, cudaMemcpyHostToDevice, st));
+  RSC_CUDA(ctx, ctx->wl_count.ensure(sizeof(uint32_t) * 4));
+  uint32_t* bounds = ctx->wl_count.as<uint32_t>() + 2;
+  RSC_CUDA(ctx, cudaMemsetAsync(bounds, 0, 2 * sizeof(uint32_t), st));
+  aos_to_soa_kernel<T><<<(unsigned)((c->n_pad + 255) / 256), 256, 0, st>>>(ctx->misc.as<T>(), ctx->misc2.as<T>(), n,
+                                                                            c->n_pad, c->soa, bounds);
+  RSC_CUDA(ctx, cudaGetLastError());
+  fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(c->valid, c->enabled, n, words);
+  RSC_CUDA(ctx, cudaGetLastError());
+  uint32_t hb[2];
+  RSC_CUDA(ctx, cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  float p2, n2;
+  memcpy(&p2, &hb[0], 4);
+  memcpy(&n2, &hb[1], 4);
+  c->pmax = sqrtf(p2) * 1.000001f;
+  c->nmax = sqrtf(n2) * 1.000001f;
+  *out = c;
+  return RSC_OK;
+}
+
+}  // namespace rsc
+
+using namespace rsc;
+
+extern "C" {
+
+int32_t rsc_cloud_create(rsc_ctx* ctx, const float* xyz, const float* nrm, int64_t n, rsc_cloud** out) {
+  return cloud_create_impl<float>(ctx, xyz, nrm, n, 0, n, out);
+}
+
+int32_t rsc_cloud_create_f64(rsc_ctx* ctx, const double* xyz, const double* nrm, int64_t n, rsc_cloud** out) {
+  return cloud_create_impl<double>(ctx, xyz, nrm, n, 0, n, out);
+}
+
+int32_t rsc_cloud_create_shard(rsc_ctx* ctx, const float* xyz, const float* nrm, int64_t n, int64_t global_offset,
+                               int64_t n_global, rsc_cloud** out) {
+  if (global_offset < 0 || n_global < global_offset + n) return fail(ctx, RSC_E_ARG, "cloud_create_shard: bad range");
+  return cloud_create_impl<float>(ctx, xyz, nrm, n, global_offset, n_global, out);
+}
+
+void rsc_cloud_destroy(rsc_cloud* c) {
+  if (!c) return;
+  if (c->ctx) cudaSetDevice(c->ctx->device);
+  for (auto& s : c->subsets) {
+    if (s.soa) cudaFree(s.soa);
+    if (s.enabled) cudaFree(s.enabled);
+    if (s.valid) cudaFree(s.valid);
+    if (s.idx) cudaFree(s.idx);
+  }
+  if (c->soa) cudaFree(c->soa);
+  if (c->enabled) cudaFree(c->enabled);
+  if (c->valid) cudaFree(c->valid);
+  delete c;
+}
+
+int64_t rsc_cloud_size(const rsc_cloud* c) { return c ? c->n : 0; }
+
+int32_t rsc_cloud_set_subset(rsc_cloud* c, int32_t subset_id, const int64_t* idx, int64_t m) {
+  if (!c) return RSC_E_ARG;
+  rsc_ctx* ctx = c->ctx;
+  if (subset_id < 0 || subset_id > 4095 || !idx || m <= 0) return fail(ctx, RSC_E_ARG, "set_subset: bad arguments");
+  for (int64_t j = 0; j < m; ++j)
+    if (idx[j] < 0 || idx[j] >= c->n) return fail(ctx, RSC_E_ARG, "set_subset: index out of range");
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((size_t)subset_id >= c->subsets.size()) c->subsets.resize(subset_id + 1);
+  rsc_subset& s = c->subsets[subset_id];
+  if (s.soa) {
+    cudaFree(s.soa), cudaFree(s.enabled), cudaFree(s.valid), cudaFree(s.idx);
+    s = rsc_subset();
+  }
+  s.m = m;
+  s.m_pad = (m + kTile - 1) / kTile * kTile;
+  const int64_t words = s.m_pad / 32;
+  cudaStream_t st = ctx->stream;
+  RSC_CUDA(ctx, cudaMalloc(&s.soa, (size_t)6 * s.m_pad * sizeof(float)));
+  RSC_CUDA(ctx, cudaMalloc(&s.enabled, (size_t)words * 4));
+  RSC_CUDA(ctx, cudaMalloc(&s.valid, (size_t)words * 4));
+  RSC_CUDA(ctx, cudaMalloc(&s.idx, (size_t)m * sizeof(int64_t)));
+  RSC_CUDA(ctx, cudaMemsetAsync(s.soa, 0, (size_t)6 * s.m_pad * sizeof(float), st));
+  RSC_CUDA(ctx, cudaMemcpyAsync(s.idx, idx, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  gather_subset_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(c->soa, c->n_pad, s.idx, m, s.m_pad, s.soa);
+  RSC_CUDA(ctx, cudaGetLastError());
+  fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(s.valid, nullptr, m, words);
+  RSC_CUDA(ctx, cudaGetLastError());
+  gather_enabled_kernel<<<(unsigned)((words * 32 + 255) / 256), 256, 0, st>>>(c->enabled, s.idx, m, words, s.enabled);
+  RSC_CUDA(ctx, cudaGetLastError());
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  return RSC_OK;
+}
+
+int64_t rsc_cloud_subset_size(const rsc_cloud* c, int32_t subset_id) {
+  if (!c || subset_id < 0 || (size_t)subset_id >= c->subsets.size()) return -1;
+  return c->subsets[subset_id].soa ? c->subsets[subset_id].m : -1;
+}
+
+int32_t rsc_cloud_get_enabled(rsc_cloud* c, uint64_t* words) {
+  if (!c || !words) return RSC_E_ARG;
+  rsc_ctx* ctx = c->ctx;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)((c->n + 63) / 64) * 8;
+  RSC_CUDA(ctx, cudaMemcpyAsync(words, c->enabled, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  RSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RSC_OK;
+}
+
+int32_t rsc_cloud_set_enabled(rsc_cloud* c, const uint64_t* words) {
+  if (!c || !words) return RSC_E_ARG;
+  rsc_ctx* ctx = c->ctx;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)((c->n + 63) / 64) * 8;
+  const int64_t w = c->n_pad / 32;
+  RSC_CUDA(ctx, cudaMemcpyAsync(c->enabled, words, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  and_words_kernel<<<(unsigned)((w + 255) / 256), 256, 0, ctx->stream>>>(c->enabled, c->valid, w);
+  RSC_CUDA(ctx, cudaGetLastError());
+  int32_t rc = refresh_subsets_enabled(c, ctx->stream);
+  if (rc) return rc;
+  RSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RSC_OK;
+}
+
+int32_t rsc_cloud_enable_all(rsc_cloud* c) {
+  if (!c) return RSC_E_ARG;
+  rsc_ctx* ctx = c->ctx;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  RSC_CUDA(ctx, cudaMemcpyAsync(c->enabled, c->valid, (size_t)(c->n_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  for (auto& s : c->subsets)
+    if (s.soa)
+      RSC_CUDA(ctx, cudaMemcpyAsync(s.enabled, s.valid, (size_t)(s.m_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  RSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return RSC_OK;
+}
+
+int64_t rsc_cloud_count_enabled(rsc_cloud* c) {
+  if (!c) return -1;
+  rsc_ctx* ctx = c->ctx;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
+  if (ctx->misc.ensure(16) != cudaSuccess) return -1;
+  unsigned long long* d = ctx->misc.as<unsigned long long>();
+  cudaMemsetAsync(d, 0, 8, ctx->stream);
+  popc_words_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c->enabled, c->n_pad / 32, d);
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+  return (int64_t)h;
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// rsc_common.cuh -- internal structures shared by the kernels of libransac_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "rsc.h"
+
+namespace rsc {
+
+// ---- tiling constants of the score kernel (K2) ------------------------------------------------
+constexpr int kThreads = 128;      // threads per CTA: one candidate "slot" column per thread
+constexpr int kTile = 512;         // points staged in shared memory per tile
+constexpr int kGroupsPerTile = kTile / 32;
+constexpr int kRecFields = 12;     // floats per compiled candidate record (SoA over slots)
+constexpr int kBandField = 11;     // record field holding the FP32 guard band
+
+// SoA float32 view of a set of points resident in HBM (the whole cloud shard or a gathered subset).
+// All arrays have n_pad (multiple of kTile) elements; padding points are zero with enabled=valid=0.
+struct PointSet {
+  const float* x;
+  const float* y;
+  const float* z;
+  const float* nx;
+  const float* ny;
+  const float* nz;
+  const uint32_t* enabled;  // bit j%32 of word j/32 = pc.isenabled of point j
+  const uint32_t* valid;    // 1 for real points, 0 for padding
+  int64_t n;
+  int64_t n_pad;
+};
+
+// per-type thresholds, FP32 for the tiled kernel and FP64 for the exact re-evaluation
+struct Thresh {
+  float eps[RSC_NTYPES];
+  float cosa[RSC_NTYPES];
+  double eps_d[RSC_NTYPES];
+  double cosa_d[RSC_NTYPES];
+  uint32_t honour_enabled;  // bit t set: type t ANDs pc.isenabled into its inliers (Q4 clears SPHERE)
+};
+
+// a (candidate, point) pair whose FP32 margin fell inside the guard band
+struct AmbPair {
+  uint32_t cand;   // original candidate index
+  uint32_t point;  // position in the point set
+};
+
+// block table written by the candidate compiler: which slots/type each CTA column covers
+struct BlockTab {
+  int32_t type;   // -1: empty column
+  int32_t slot0;  // first slot of the column
+};
+
+// growable device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+}  // namespace rsc
+
+struct rsc_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  std::string err;
+  rsc_stats stats{};
+  // scratch of the score path
+  rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, wl_count, aux;
+  rsc::DevBuf misc, misc2, idxbuf, fitbuf;
+  size_t wl_cap = 1u << 22;  // AmbPair capacity, grows on overflow
+  void* pinned = nullptr;    // small pinned staging area
+  size_t pinned_cap = 0;
+};
+
+struct rsc_subset {
+  int64_t m = 0, m_pad = 0;
+  float* soa = nullptr;        // 6 * m_pad floats
+  uint32_t* enabled = nullptr; // m_pad/32 words
+  uint32_t* valid = nullptr;
+  int64_t* idx = nullptr;      // m local point indices (device)
+};
+
+struct rsc_cloud {
+  rsc_ctx* ctx = nullptr;
+  int64_t n = 0, n_pad = 0;
+  int64_t global_offset = 0, n_global = 0;
+  float* soa = nullptr;        // 6 * n_pad floats: x | y | z | nx | ny | nz
+  uint32_t* enabled = nullptr; // n_pad/32 words
+  uint32_t* valid = nullptr;
+  float pmax = 0.f;            // max |p| over the cloud (guard-band scale)
+  float nmax = 1.f;            // max |n| over the cloud
+  std::vector<rsc_subset> subsets;
+};
+
+namespace rsc {
+
+inline PointSet view_cloud(const rsc_cloud* c) {
+  PointSet ps;
+  ps.x = c->soa;
+  ps.y = c->soa + c->n_pad;
+  ps.z = c->soa + 2 * c->n_pad;
+  ps.nx = c->soa + 3 * c->n_pad;
+  ps.ny = c->soa + 4 * c->n_pad;
+  ps.nz = c->soa + 5 * c->n_pad;
+  ps.enabled = c->enabled;
+  ps.valid = c->valid;
+  ps.n = c->n;
+  ps.n_pad = c->n_pad;
+  return ps;
+}
+
+inline PointSet view_subset(const rsc_subset* s) {
+  PointSet ps;
+  ps.x = s->soa;
+  ps.y = s->soa + s->m_pad;
+  ps.z = s->soa + 2 * s->m_pad;
+  ps.nx = s->soa + 3 * s->m_pad;
+  ps.ny = s->soa + 4 * s->m_pad;
+  ps.nz = s->soa + 5 * s->m_pad;
+  ps.enabled = s->enabled;
+  ps.valid = s->valid;
+  ps.n = s->m;
+  ps.n_pad = s->m_pad;
+  return ps;
+}
+
+// error plumbing
+int32_t fail(rsc_ctx* ctx, int32_t code, const char* what);
+int32_t fail_cuda(rsc_ctx* ctx, cudaError_t e, const char* where);
+
+#define RSC_CUDA(ctx, expr)                                        \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return rsc::fail_cuda((ctx), _e, #expr); \
+  } while (0)
+
+Thresh make_thresh(const rsc_params* p);
+
+// internal launchers (all enqueue on `st`, none synchronise)
+int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th,
+                      const rsc_cand* d_cands, int32_t C, int32_t* d_counts_policy, bool want_masks,
+                      cudaStream_t st, int32_t* d_counts_valid = nullptr,
+                      int32_t* d_counts_enabled = nullptr, const double* d_trig = nullptr);
+// refresh the gathered enabled bits of every uploaded subset from the cloud's enabled mask
+int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st);
+
+int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st);
+
+}  // namespace rsc
+
+namespace rsc {
+int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st);
+int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st);
+}  // namespace rsc

@@ -1,0 +1,203 @@
+// rsc_eval.cuh -- FP32 evaluation of one (candidate, point) pair against a compiled candidate
+// record, and the record compiler (FP64 parameters -> FP32 record with folded constants).
+//
+// eval<T>() returns the MARGIN m = max(|dist| - eps, cos(alpha)*rho - rho*(n_shape . n_point)):
+// the pair is compatible iff m < 0.  |m| <= band (a bound on the FP32 rounding error, record field
+// kBandField) marks the pair ambiguous; those are re-evaluated in FP64 (rsc_exact.cuh).
+//
+// Closed forms used (they equal the reference's compatibles* up to rounding):
+//   plane    dist = o.p - o.q (o = normalize(normal));   angle: normal . n > cos(alpha)
+//   sphere   v = p - c, r = |v|: | r - R | < eps;        +-(v . n) > cos(alpha) r
+//   cylinder w = v - a (a.v), rho = |w|: |rho - R| < eps; +-(w . n) > cos(alpha) rho
+//   cone     h = a.v, w = v - a h, rho = |w|, (c,s) = cos/sin(opang/2):
+//            dist = h s - rho c;   +-(c (w.n) - s rho (a.n)) > cos(alpha) rho
+// The outwards sign is folded into the record (sg = +-1 multiplies v), so a warp never branches.
+#pragma once
+#include "rsc_common.cuh"
+
+namespace rsc {
+
+// error-bound multipliers (units of 2^-24 * magnitude), calibrated in tests/test_guard_band.py
+__host__ __device__ constexpr float kappa(int type) {
+  return type == RSC_PLANE ? 8.f : type == RSC_SPHERE ? 16.f : type == RSC_CYLINDER ? 16.f : 20.f;
+}
+
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+// one MUFU.RSQ; denormal inputs flush to zero (-> inf -> NaN margin -> FP64 path)
+__device__ __forceinline__ float rsqrt_fast(float a) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float fmin_nan(float a, float b) {
+  float r;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+// Number of record fields each type really uses (the rest of the 12 is padding).
+template <int T>
+struct RecN;
+template <>
+struct RecN<RSC_PLANE> {
+  static constexpr int n = 7;
+};
+template <>
+struct RecN<RSC_SPHERE> {
+  static constexpr int n = 5;
+};
+template <>
+struct RecN<RSC_CYLINDER> {
+  static constexpr int n = 8;
+};
+template <>
+struct RecN<RSC_CONE> {
+  static constexpr int n = 9;
+};
+
+// r: the used fields of the record (registers).  p = (x,y,z), n = (nx,ny,nz).
+template <int T>
+__device__ __forceinline__ float eval(const float* r, float px, float py, float pz, float nx, float ny,
+                                      float nz, float eps, float cosa) {
+  if constexpr (T == RSC_PLANE) {
+    // r0..2 = o, r3 = -o.q, r4..6 = -normal
+    float d = fmaf(r[0], px, fmaf(r[1], py, fmaf(r[2], pz, r[3])));
+    float e = fabsf(d) - eps;
+    float nt = fmaf(r[4], nx, fmaf(r[5], ny, fmaf(r[6], nz, cosa)));
+    return fmax_nan(e, nt);
+  } else if constexpr (T == RSC_SPHERE) {
+    // r0 = sg, r1..3 = -sg*center, r4 = R
+    float vx = fmaf(r[0], px, r[1]), vy = fmaf(r[0], py, r[2]), vz = fmaf(r[0], pz, r[3]);
+    float vv = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
+    float rad = vv * rsqrt_fast(vv);
+    float e = fabsf(rad - r[4]) - eps;
+    float s = fmaf(vx, nx, fmaf(vy, ny, vz * nz));
+    float nt = fmaf(cosa, rad, -s);
+    return fmax_nan(e, nt);
+  } else if constexpr (T == RSC_CYLINDER) {
+    // r0 = sg, r1..3 = -sg*center, r4..6 = axis, r7 = R
+    float vx = fmaf(r[0], px, r[1]), vy = fmaf(r[0], py, r[2]), vz = fmaf(r[0], pz, r[3]);
+    float h = fmaf(r[4], vx, fmaf(r[5], vy, r[6] * vz));
+    float wx = fmaf(-r[4], h, vx), wy = fmaf(-r[5], h, vy), wz = fmaf(-r[6], h, vz);
+    float ww = fmaf(wx, wx, fmaf(wy, wy, wz * wz));
+    float rho = ww * rsqrt_fast(ww);
+    float e = fabsf(rho - r[7]) - eps;
+    float wn = fmaf(wx, nx, fmaf(wy, ny, wz * nz));
+    float nt = fmaf(cosa, rho, -wn);
+    return fmax_nan(e, nt);
+  } else {
+    // r0 = sg, r1..3 = -sg*apex, r4..6 = axis, r7 = sg*sin(opang/2), r8 = cos(opang/2)
+    float vx = fmaf(r[0], px, r[1]), vy = fmaf(r[0], py, r[2]), vz = fmaf(r[0], pz, r[3]);
+    float h = fmaf(r[4], vx, fmaf(r[5], vy, r[6] * vz));
+    float wx = fmaf(-r[4], h, vx), wy = fmaf(-r[5], h, vy), wz = fmaf(-r[6], h, vz);
+    float ww = fmaf(wx, wx, fmaf(wy, wy, wz * wz));
+    float rho = ww * rsqrt_fast(ww);
+    float d = fmaf(h, r[7], -(rho * r[8]));
+    float e = fabsf(d) - eps;
+    float wn = fmaf(wx, nx, fmaf(wy, ny, wz * nz));
+    float an = fmaf(r[4], nx, fmaf(r[5], ny, r[6] * nz));
+    float srho = r[7] * rho;
+    float q = fmaf(r[8], wn, -(srho * an));
+    float nt = fmaf(cosa, rho, -q);
+    return fmax_nan(e, nt);
+  }
+}
+
+// runtime-type version for the (rare) slow path
+__device__ __forceinline__ float eval_any(int type, const float* r, float px, float py, float pz,
+                                          float nx, float ny, float nz, float eps, float cosa) {
+  switch (type) {
+    case RSC_PLANE:
+      return eval<RSC_PLANE>(r, px, py, pz, nx, ny, nz, eps, cosa);
+    case RSC_SPHERE:
+      return eval<RSC_SPHERE>(r, px, py, pz, nx, ny, nz, eps, cosa);
+    case RSC_CYLINDER:
+      return eval<RSC_CYLINDER>(r, px, py, pz, nx, ny, nz, eps, cosa);
+    default:
+      return eval<RSC_CONE>(r, px, py, pz, nx, ny, nz, eps, cosa);
+  }
+}
+
+// Compile one candidate (FP64 parameters) into its FP32 record.  pmax/nmax: max |p| and max |n|
+// over the cloud, the scale of every intermediate and therefore of the rounding error.
+// A candidate with a non-finite parameter can match nothing in the reference (NaN compares
+// false); it gets a record that is far from everything so that no NaN reaches the tiled kernel.
+__device__ inline void compile_record(const rsc_cand& c, float pmax, float nmax, float* r /*[12]*/) {
+  const double u = 5.9604644775390625e-08;  // 2^-24
+  for (int i = 0; i < kRecFields; ++i) r[i] = 0.f;
+  bool finite = true;
+  for (int i = 0; i < 7; ++i) finite = finite && isfinite(c.p[i]);
+  double nm = nmax > 1.f ? (double)nmax : 1.0;
+  double P = (double)pmax;
+  double L;
+  switch (c.type) {
+    case RSC_PLANE: {
+      double mx = c.p[3], my = c.p[4], mz = c.p[5];
+      double mn = sqrt(mx * mx + my * my + mz * mz);
+      double inv = 1.0 / mn;
+      if (!finite || !(mn > 0.0) || !isfinite(inv)) {
+        r[3] = 1e30f;  // |dist| = 1e30
+        r[kBandField] = 1.f;
+        return;
+      }
+      double ox = mx * inv, oy = my * inv, oz = mz * inv;
+      double oq = ox * c.p[0] + oy * c.p[1] + oz * c.p[2];
+      r[0] = (float)ox, r[1] = (float)oy, r[2] = (float)oz, r[3] = (float)(-oq);
+      r[4] = (float)(-mx), r[5] = (float)(-my), r[6] = (float)(-mz);
+      L = (P + fabs(oq) + 1.0) * (mn > 1.0 ? mn : 1.0) * nm;
+      break;
+    }
+    case RSC_SPHERE: {
+      double sg = c.outwards ? 1.0 : -1.0;
+      if (!finite) {
+        r[0] = 1.f, r[1] = 1e15f, r[4] = 1e30f, r[kBandField] = 1.f;
+        return;
+      }
+      r[0] = (float)sg;
+      r[1] = (float)(-sg * c.p[0]), r[2] = (float)(-sg * c.p[1]), r[3] = (float)(-sg * c.p[2]);
+      r[4] = (float)c.p[3];
+      double cn = sqrt(c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2]);
+      L = (P + cn + fabs(c.p[3]) + 1.0) * nm;
+      break;
+    }
+    case RSC_CYLINDER: {
+      double sg = c.outwards ? 1.0 : -1.0;
+      if (!finite) {
+        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 1e30f, r[kBandField] = 1.f;
+        return;
+      }
+      r[0] = (float)sg;
+      r[1] = (float)(-sg * c.p[3]), r[2] = (float)(-sg * c.p[4]), r[3] = (float)(-sg * c.p[5]);
+      r[4] = (float)c.p[0], r[5] = (float)c.p[1], r[6] = (float)c.p[2];
+      r[7] = (float)c.p[6];
+      double cn = sqrt(c.p[3] * c.p[3] + c.p[4] * c.p[4] + c.p[5] * c.p[5]);
+      double a2 = c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2];
+      L = (P + cn + fabs(c.p[6]) + 1.0) * (a2 > 1.0 ? a2 : 1.0) * nm;
+      break;
+    }
+    default: {
+      double sg = c.outwards ? 1.0 : -1.0;
+      if (!finite) {
+        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 0.f, r[8] = 1.f, r[kBandField] = 1.f;
+        return;
+      }
+      r[0] = (float)sg;
+      r[1] = (float)(-sg * c.p[0]), r[2] = (float)(-sg * c.p[1]), r[3] = (float)(-sg * c.p[2]);
+      r[4] = (float)c.p[3], r[5] = (float)c.p[4], r[6] = (float)c.p[5];
+      r[7] = (float)(sg * sin(0.5 * c.p[6]));
+      r[8] = (float)cos(0.5 * c.p[6]);
+      double cn = sqrt(c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2]);
+      double a2 = c.p[3] * c.p[3] + c.p[4] * c.p[4] + c.p[5] * c.p[5];
+      L = (P + cn + 1.0) * (a2 > 1.0 ? a2 : 1.0) * nm;
+      break;
+    }
+  }
+  double b = (double)kappa(c.type) * u * L;
+  r[kBandField] = (float)(b * 1.0000002);  // round the band up, never down
+}
+
+}  // namespace rsc

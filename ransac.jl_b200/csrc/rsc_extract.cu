@@ -1,0 +1,194 @@
+// rsc_extract.cu -- K4: refit + invalidate_indexes! for one shape over the whole cloud shard
+// (plane.jl:137-143, sphere.jl:179-190, cylinder.jl:228-234, cone.jl:176-182, fitting.jl:197-202).
+//
+// One thread per point, HBM bound (24 B/point + 1/8 B of enabled mask).  Three launches:
+//   1. extract_mask_kernel   compatibility (FP32, FP64 inside the guard band) AND enabled ->
+//                            inlier bitmask word per warp + inlier count per CTA
+//   2. scan_counts_kernel    exclusive scan of the CTA counts (one CTA)
+//   3. extract_write_kernel  ascending global indices by stream compaction; clears enabled bits
+#include "rsc_eval.cuh"
+#include "rsc_exact.cuh"
+
+namespace rsc {
+
+constexpr int kExThreads = 256;
+constexpr int kExPts = 2048;  // points per CTA (64 mask words)
+
+struct ExtractArgs {
+  PointSet ps;
+  Thresh th;
+  rsc_cand cand;
+  ex::ConeTrig trig;
+  float pmax, nmax;
+  uint32_t* inl;           // [n_pad/32]
+  uint32_t* block_counts;  // [nblocks]
+};
+
+__global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_constant__ ExtractArgs a) {
+  __shared__ float r[kRecFields];
+  __shared__ int wsum[kExThreads / 32];
+  if (threadIdx.x == 0) {
+    float t[kRecFields];
+    compile_record(a.cand, a.pmax, a.nmax, t);
+    for (int f = 0; f < kRecFields; ++f) r[f] = t[f];
+  }
+  __syncthreads();
+  const int type = a.cand.type;
+  const float band = r[kBandField];
+  const float eps = a.th.eps[type], cosa = a.th.cosa[type];
+  float rr[kRecFields];
+#pragma unroll
+  for (int f = 0; f < kRecFields; ++f) rr[f] = r[f];
+  int cnt = 0;
+  const int64_t base = (int64_t)blockIdx.x * kExPts;
+#pragma unroll 2
+  for (int it = 0; it < kExPts / kExThreads; ++it) {
+    const int64_t p = base + it * kExThreads + threadIdx.x;
+    if (p >= a.ps.n_pad) break;  // n_pad is a multiple of 512: whole warps leave together
+    const uint32_t en = __ldg(a.ps.enabled + (p >> 5));
+    bool ok = false;
+    if ((en >> (p & 31)) & 1u) {
+      const float x = __ldg(a.ps.x + p), y = __ldg(a.ps.y + p), z = __ldg(a.ps.z + p);
+      const float nx = __ldg(a.ps.nx + p), ny = __ldg(a.ps.ny + p), nz = __ldg(a.ps.nz + p);
+      const float m = eval_any(type, rr, x, y, z, nx, ny, nz, eps, cosa);
+      ok = m < 0.f;
+      if (!(fabsf(m) > band))
+        ok = ex::compat(a.cand, a.trig, a.th, ex::V3{(double)x, (double)y, (double)z},
+                        ex::V3{(double)nx, (double)ny, (double)nz});
+    }
+    const unsigned w = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) {
+      a.inl[p >> 5] = w;
+      cnt += __popc(w);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int i = 0; i < kExThreads / 32; ++i) s += wsum[i];
+    a.block_counts[blockIdx.x] = s;
+  }
+}
+
+// exclusive scan of `n` counts by one CTA; total -> out_total[0]
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const uint32_t* __restrict__ counts, int n,
+                                                           unsigned long long* __restrict__ offsets,
+                                                           unsigned long long* __restrict__ out_total) {
+  __shared__ unsigned long long wex[32];
+  __shared__ unsigned long long carry, chunk_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const unsigned long long v = i < n ? counts[i] : 0ull;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) wex[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long t = wex[lane];
+      unsigned long long ti = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, ti, d);
+        if (lane >= d) ti += o;
+      }
+      wex[lane] = ti - t;
+      if (lane == 31) chunk_total = ti;
+    }
+    __syncthreads();
+    if (i < n) offsets[i] = carry + wex[warp] + (inc - v);
+    __syncthreads();
+    if (tid == 0) carry += chunk_total;
+    __syncthreads();
+  }
+  if (tid == 0) *out_total = carry;
+}
+
+__global__ void __launch_bounds__(kExThreads) extract_write_kernel(const uint32_t* __restrict__ inl,
+                                                                   const unsigned long long* __restrict__ offsets,
+                                                                   int64_t n_pad, int64_t global_offset,
+                                                                   int64_t* __restrict__ out,
+                                                                   uint32_t* __restrict__ enabled /*nullable*/) {
+  __shared__ uint32_t woff[kExPts / 32];
+  const int64_t base = (int64_t)blockIdx.x * kExPts;
+  const int64_t w0 = base >> 5;
+  const int64_t nwords = n_pad >> 5;
+  if (threadIdx.x < 32) {  // exclusive scan over this CTA's 64 words (2 per lane)
+    const int lane = threadIdx.x;
+    const uint32_t a0 = (w0 + 2 * lane < nwords) ? __popc(inl[w0 + 2 * lane]) : 0;
+    const uint32_t a1 = (w0 + 2 * lane + 1 < nwords) ? __popc(inl[w0 + 2 * lane + 1]) : 0;
+    uint32_t s = a0 + a1, inc = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    woff[2 * lane] = inc - s;
+    woff[2 * lane + 1] = inc - s + a0;
+  }
+  __syncthreads();
+  const unsigned long long boff = offsets[blockIdx.x];
+#pragma unroll 2
+  for (int it = 0; it < kExPts / kExThreads; ++it) {
+    const int64_t p = base + it * kExThreads + threadIdx.x;
+    if (p >= n_pad) break;
+    const uint32_t w = inl[p >> 5];
+    const int bit = (int)(p & 31);
+    if (out && ((w >> bit) & 1u)) {
+      const unsigned long long pos = boff + woff[(p >> 5) - w0] + __popc(w & ((1u << bit) - 1u));
+      out[pos] = p + global_offset;
+    }
+    if (enabled && bit == 0 && w) enabled[p >> 5] &= ~w;
+  }
+}
+
+// Enqueue steps 1+2; the caller reads the total (ctx->misc2[0]) and then calls extract_write.
+int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st) {
+  rsc_ctx* ctx = cloud->ctx;
+  const int64_t n_pad = cloud->n_pad;
+  const int nblocks = (int)((n_pad + kExPts - 1) / kExPts);
+  RSC_CUDA(ctx, ctx->idxbuf.ensure((size_t)(n_pad / 32) * 4 + (size_t)nblocks * (4 + 8) + 64));
+  ExtractArgs a;
+  a.ps = view_cloud(cloud);
+  a.th = th;
+  a.cand = cand;
+  a.trig.ct = cos(-cand.p[6] / 2);
+  a.trig.st = sin(-cand.p[6] / 2);
+  a.pmax = cloud->pmax;
+  a.nmax = cloud->nmax;
+  char* b = ctx->idxbuf.as<char>();
+  a.inl = reinterpret_cast<uint32_t*>(b);
+  unsigned long long* offsets = reinterpret_cast<unsigned long long*>(b + ((size_t)(n_pad / 32) * 4 + 15) / 16 * 16);
+  a.block_counts = reinterpret_cast<uint32_t*>(offsets + nblocks);
+  RSC_CUDA(ctx, ctx->misc2.ensure(64));
+  extract_mask_kernel<<<nblocks, kExThreads, 0, st>>>(a);
+  RSC_CUDA(ctx, cudaGetLastError());
+  scan_counts_kernel<<<1, 1024, 0, st>>>(a.block_counts, nblocks, offsets, ctx->misc2.as<unsigned long long>());
+  RSC_CUDA(ctx, cudaGetLastError());
+  ctx->stats.evals += cloud->n;
+  return RSC_OK;
+}
+
+int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st) {
+  rsc_ctx* ctx = cloud->ctx;
+  const int64_t n_pad = cloud->n_pad;
+  const int nblocks = (int)((n_pad + kExPts - 1) / kExPts);
+  char* b = ctx->idxbuf.as<char>();
+  const uint32_t* inl = reinterpret_cast<const uint32_t*>(b);
+  const unsigned long long* offsets =
+      reinterpret_cast<const unsigned long long*>(b + ((size_t)(n_pad / 32) * 4 + 15) / 16 * 16);
+  extract_write_kernel<<<nblocks, kExThreads, 0, st>>>(inl, offsets, n_pad, cloud->global_offset, d_out,
+                                                       disable ? cloud->enabled : nullptr);
+  RSC_CUDA(ctx, cudaGetLastError());
+  if (disable) return refresh_subsets_enabled(cloud, st);
+  return RSC_OK;
+}
+
+}  // namespace rsc

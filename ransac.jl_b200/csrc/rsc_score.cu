@@ -1,0 +1,468 @@
+// rsc_score.cu -- K2: candidate x point compatibility scoring (the hot kernel), the candidate
+// compiler that feeds it, and the FP64 fix-up of guard-band pairs.
+//
+// Replaces scorecandidates!/scorecandidate/compatibles* (fitting.jl:181-190, plane.jl:61-130,
+// sphere.jl:118-172, cylinder.jl:172-221, cone.jl:132-167).
+//
+// Mapping (B200-first, the path is FP32-ALU bound):
+//   * candidates are register resident: every thread owns K compiled candidates of ONE shape type
+//     (a CTA column = 128*K "slots" of one type, so no warp ever diverges on the type);
+//   * points stream HBM (SoA, 128-bit loads) -> shared memory (re-packed as {x,y,z,nx},{ny,nz}) and
+//     are read back as warp-wide BROADCAST loads: 2 LDS per point feed K*32 evaluations per warp;
+//   * the inlier bit of each evaluation is shifted into a per-candidate register (one 32-bit mask
+//     word per 32 points), so counting is one POPC per 32 evaluations and bitmasks come for free;
+//   * per evaluation the kernel also tracks min|margin|; only if that falls inside the FP32 guard
+//     band is the 32-point group re-examined and the ambiguous pairs queued for FP64 (fixup_kernel).
+#include <math.h>
+
+#include "rsc_eval.cuh"
+#include "rsc_exact.cuh"
+
+namespace rsc {
+
+struct ScoreArgs {
+  PointSet ps;
+  Thresh th;
+  const float* rec;        // [kRecFields][cslots]
+  const int32_t* orig;     // [cslots] original candidate index, -1 for padding slots
+  const BlockTab* tab;     // [gridDim.x]
+  int32_t cslots;          // slot stride of rec / masks
+  int32_t tiles_per_chunk;
+  int32_t ntiles;
+  int32_t* counts_valid;   // [C] compatible real points
+  int32_t* counts_enabled; // [C] compatible enabled points
+  uint32_t* masks;         // nullable, group-major [n_pad/32][cslots]
+  AmbPair* wl;
+  uint32_t* wl_count;
+  uint32_t wl_cap;
+};
+
+// ---------------------------------------------------------------------------------------------
+// slow path: a 32-point group whose min|margin| fell inside the band.  Re-evaluates the group for
+// one slot, clears the ambiguous bits and queues those pairs for the FP64 fix-up.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ uint32_t resolve_group(const ScoreArgs& a, int type, int slot, uint32_t w,
+                                               const float4* sA, const float2* sB, int64_t p0) {
+  float r[kRecFields];
+#pragma unroll
+  for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
+  const float band = r[kBandField];
+  const float eps = a.th.eps[type], cosa = a.th.cosa[type];
+  const int orig = a.orig[slot];
+  for (int i = 0; i < 32; ++i) {
+    float4 A = sA[i];
+    float2 B = sB[i];
+    float m = eval_any(type, r, A.x, A.y, A.z, A.w, B.x, B.y, eps, cosa);
+    if (!(fabsf(m) > band)) {
+      w &= ~(1u << i);
+      if (orig >= 0 && p0 + i < a.ps.n) {
+        uint32_t pos = atomicAdd(a.wl_count, 1u);
+        if (pos < a.wl_cap) a.wl[pos] = AmbPair{(uint32_t)orig, (uint32_t)(p0 + i)};
+      }
+    }
+  }
+  return w;
+}
+
+template <int T, int K>
+__device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float4* sA, float2* sB) {
+  constexpr int NR = RecN<T>::n;
+  float r[K][NR];
+  float band[K];
+  int cntv[K], cnte[K];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int slot = slot0 + k * kThreads + tid;
+#pragma unroll
+    for (int f = 0; f < NR; ++f) r[k][f] = a.rec[(size_t)f * a.cslots + slot];
+    band[k] = a.rec[(size_t)kBandField * a.cslots + slot];
+    cntv[k] = 0;
+    cnte[k] = 0;
+  }
+  const float eps = a.th.eps[T], cosa = a.th.cosa[T];
+  const bool honour = (a.th.honour_enabled >> T) & 1u;
+
+  const int tile0 = blockIdx.y * a.tiles_per_chunk;
+  const int tile1 = min(tile0 + a.tiles_per_chunk, a.ntiles);
+  for (int tile = tile0; tile < tile1; ++tile) {
+    const int64_t base = (int64_t)tile * kTile;
+    {  // stage: 6 x 128-bit loads per thread (4 consecutive points), re-packed per point
+      const int64_t i = base + 4 * tid;
+      const float4 X = __ldg(reinterpret_cast<const float4*>(a.ps.x + i));
+      const float4 Y = __ldg(reinterpret_cast<const float4*>(a.ps.y + i));
+      const float4 Z = __ldg(reinterpret_cast<const float4*>(a.ps.z + i));
+      const float4 U = __ldg(reinterpret_cast<const float4*>(a.ps.nx + i));
+      const float4 V = __ldg(reinterpret_cast<const float4*>(a.ps.ny + i));
+      const float4 W = __ldg(reinterpret_cast<const float4*>(a.ps.nz + i));
+      sA[4 * tid + 0] = make_float4(X.x, Y.x, Z.x, U.x);
+      sA[4 * tid + 1] = make_float4(X.y, Y.y, Z.y, U.y);
+      sA[4 * tid + 2] = make_float4(X.z, Y.z, Z.z, U.z);
+      sA[4 * tid + 3] = make_float4(X.w, Y.w, Z.w, U.w);
+      sB[4 * tid + 0] = make_float2(V.x, W.x);
+      sB[4 * tid + 1] = make_float2(V.y, W.y);
+      sB[4 * tid + 2] = make_float2(V.z, W.z);
+      sB[4 * tid + 3] = make_float2(V.w, W.w);
+    }
+    __syncthreads();
+    for (int g = 0; g < kGroupsPerTile; ++g) {
+      uint32_t mask[K];
+      float mabs[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        mask[k] = 0u;
+        mabs[k] = __int_as_float(0x7f800000);
+      }
+      const float4* gA = sA + g * 32;
+      const float2* gB = sB + g * 32;
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const float4 A = gA[i];
+        const float2 B = gB[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float m = eval<T>(r[k], A.x, A.y, A.z, A.w, B.x, B.y, eps, cosa);
+          mask[k] = __funnelshift_l(__float_as_uint(m), mask[k], 1);  // sign bit = compatible
+          mabs[k] = fmin_nan(mabs[k], fabsf(m));
+        }
+      }
+      const int64_t gw = (int64_t)tile * kGroupsPerTile + g;
+      const uint32_t en = __ldg(a.ps.enabled + gw);
+      const uint32_t va = __ldg(a.ps.valid + gw);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        uint32_t w = __brev(mask[k]);
+        const int slot = slot0 + k * kThreads + tid;
+        if (!(mabs[k] > band[k])) w = resolve_group(a, T, slot, w, gA, gB, base + g * 32);
+        cntv[k] += __popc(w & va);
+        cnte[k] += __popc(w & en);
+        if (a.masks) a.masks[(size_t)gw * a.cslots + slot] = w & (honour ? en : va);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int o = a.orig[slot0 + k * kThreads + tid];
+    if (o >= 0) {
+      if (cntv[k]) atomicAdd(a.counts_valid + o, cntv[k]);
+      if (cnte[k]) atomicAdd(a.counts_enabled + o, cnte[k]);
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kThreads) score_kernel(const __grid_constant__ ScoreArgs a) {
+  __shared__ float4 sA[kTile];
+  __shared__ float2 sB[kTile];
+  const BlockTab bt = a.tab[blockIdx.x];
+  if (bt.type < 0) return;
+  switch (bt.type) {
+    case RSC_PLANE:
+      score_body<RSC_PLANE, K>(a, bt.slot0, sA, sB);
+      break;
+    case RSC_SPHERE:
+      score_body<RSC_SPHERE, K>(a, bt.slot0, sA, sB);
+      break;
+    case RSC_CYLINDER:
+      score_body<RSC_CYLINDER, K>(a, bt.slot0, sA, sB);
+      break;
+    default:
+      score_body<RSC_CONE, K>(a, bt.slot0, sA, sB);
+      break;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FP64 fix-up of the queued pairs (reference operation order, rsc_exact.cuh)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fixup_kernel(const __grid_constant__ ScoreArgs a,
+                                                    const rsc_cand* __restrict__ cands,
+                                                    const ex::ConeTrig* __restrict__ trig,
+                                                    const int32_t* __restrict__ slot_of) {
+  const uint32_t n = min(*a.wl_count, a.wl_cap);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const AmbPair pr = a.wl[e];
+    const rsc_cand c = cands[pr.cand];
+    ex::ConeTrig tr{1.0, 0.0};
+    if (c.type == RSC_CONE) {
+      if (trig) {
+        tr = trig[pr.cand];
+      } else {
+        tr.ct = cos(-c.p[6] / 2);
+        tr.st = sin(-c.p[6] / 2);
+      }
+    }
+    const uint32_t pt = pr.point;
+    ex::V3 p = {(double)a.ps.x[pt], (double)a.ps.y[pt], (double)a.ps.z[pt]};
+    ex::V3 nn = {(double)a.ps.nx[pt], (double)a.ps.ny[pt], (double)a.ps.nz[pt]};
+    if (!ex::compat(c, tr, a.th, p, nn)) continue;
+    const uint32_t word = pt >> 5, bit = 1u << (pt & 31);
+    const bool va = a.ps.valid[word] & bit;
+    const bool en = a.ps.enabled[word] & bit;
+    if (va) atomicAdd(a.counts_valid + pr.cand, 1);
+    if (en) atomicAdd(a.counts_enabled + pr.cand, 1);
+    if (a.masks) {
+      const bool honour = (a.th.honour_enabled >> c.type) & 1u;
+      if (honour ? en : va) atomicOr(a.masks + (size_t)word * a.cslots + slot_of[pr.cand], bit);
+    }
+  }
+}
+
+// counts[c] = enabled-gated or validity-gated count, by the type's policy (Q4)
+__global__ void select_counts_kernel(const rsc_cand* __restrict__ cands, int C,
+                                     const int32_t* __restrict__ cv, const int32_t* __restrict__ ce,
+                                     uint32_t honour_enabled, int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const int t = cands[i].type;
+  const bool honour = (t >= 0 && t < RSC_NTYPES) ? ((honour_enabled >> t) & 1u) : true;
+  out[i] = honour ? ce[i] : cv[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidate compiler: FP64 rsc_cand[C] -> type-segmented FP32 records + the CTA column table.
+// One CTA; slots are assigned stably (candidate order within a type is kept).
+// Column order is cone, cylinder, sphere, plane: the most expensive columns are scheduled first.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restrict__ cands, int C,
+                                                       int spc /*slots per column*/, int cslots,
+                                                       int ncols, float pmax, float nmax,
+                                                       float* __restrict__ rec, int32_t* __restrict__ orig,
+                                                       int32_t* __restrict__ slot_of,
+                                                       BlockTab* __restrict__ tab) {
+  __shared__ int cnt[RSC_NTYPES], off[RSC_NTYPES], run[RSC_NTYPES], tot[RSC_NTYPES];
+  __shared__ int wcnt[RSC_NTYPES][32], woff[RSC_NTYPES][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < RSC_NTYPES) {
+    cnt[tid] = 0;
+    run[tid] = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += blockDim.x) {
+    const int t = cands[i].type;
+    if (t >= 0 && t < RSC_NTYPES) atomicAdd(&cnt[t], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int order[RSC_NTYPES] = {RSC_CONE, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
+    int s = 0, col = 0;
+    for (int oi = 0; oi < RSC_NTYPES; ++oi) {
+      const int t = order[oi];
+      off[t] = s;
+      const int nb = (cnt[t] + spc - 1) / spc;
+      for (int b = 0; b < nb && col < ncols; ++b) tab[col++] = BlockTab{t, s + b * spc};
+      s += nb * spc;
+    }
+    for (; col < ncols; ++col) tab[col] = BlockTab{-1, 0};
+  }
+  __syncthreads();
+  for (int base = 0; base < C; base += blockDim.x) {
+    const int i = base + tid;
+    int t = -1;
+    if (i < C) {
+      t = cands[i].type;
+      if (t < 0 || t >= RSC_NTYPES) t = -1;
+    }
+    int myrank = 0;
+#pragma unroll
+    for (int tt = 0; tt < RSC_NTYPES; ++tt) {
+      const unsigned b = __ballot_sync(0xffffffffu, t == tt);
+      if (t == tt) myrank = __popc(b & ((1u << lane) - 1u));
+      if (lane == 0) wcnt[tt][warp] = __popc(b);
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int tt = 0; tt < RSC_NTYPES; ++tt) {
+        const int v = wcnt[tt][lane];
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, inc, d);
+          if (lane >= d) inc += o;
+        }
+        woff[tt][lane] = inc - v;
+        if (lane == 31) tot[tt] = inc;
+      }
+    }
+    __syncthreads();
+    if (i < C) {
+      if (t >= 0) {
+        const int slot = off[t] + run[t] + woff[t][warp] + myrank;
+        float r[kRecFields];
+        compile_record(cands[i], pmax, nmax, r);
+#pragma unroll
+        for (int f = 0; f < kRecFields; ++f) rec[(size_t)f * cslots + slot] = r[f];
+        orig[slot] = i;
+        slot_of[i] = slot;
+      } else {
+        slot_of[i] = -1;
+      }
+    }
+    __syncthreads();
+    if (tid < RSC_NTYPES) run[tid] += tot[tid];
+    __syncthreads();
+  }
+  // padding slots replicate the last real candidate of their type (orig = -1: results dropped)
+  for (int t = 0; t < RSC_NTYPES; ++t) {
+    const int n = cnt[t];
+    if (n == 0) continue;
+    const int padded = ((n + spc - 1) / spc) * spc;
+    const int src = off[t] + n - 1;
+    for (int s = n + tid; s < padded; s += blockDim.x) {
+      const int dst = off[t] + s;
+#pragma unroll
+      for (int f = 0; f < kRecFields; ++f) rec[(size_t)f * cslots + dst] = rec[(size_t)f * cslots + src];
+      orig[dst] = -1;
+    }
+  }
+}
+
+// group-major [G][cslots] -> candidate-major [C][words] (32x32 tiles through shared memory)
+__global__ void __launch_bounds__(1024) masks_transpose_kernel(const uint32_t* __restrict__ gm,
+                                                               const int32_t* __restrict__ slot_of,
+                                                               int C, int cslots, int64_t words,
+                                                               uint32_t* __restrict__ out) {
+  __shared__ uint32_t t[32][33];
+  const int c0 = blockIdx.x * 32;
+  const int64_t g0 = (int64_t)blockIdx.y * 32;
+  {  // read: lanes run over candidates (slots are near-contiguous), rows over groups
+    const int c = c0 + threadIdx.x;
+    const int64_t g = g0 + threadIdx.y;
+    uint32_t v = 0;
+    if (c < C && g < words) {
+      const int s = slot_of[c];
+      if (s >= 0) v = gm[(size_t)g * cslots + s];
+    }
+    t[threadIdx.y][threadIdx.x] = v;
+  }
+  __syncthreads();
+  {
+    const int c = c0 + threadIdx.y;
+    const int64_t g = g0 + threadIdx.x;
+    if (c < C && g < words) out[(size_t)c * words + g] = t[threadIdx.x][threadIdx.y];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------------------------
+Thresh make_thresh(const rsc_params* p) {
+  Thresh th;
+  for (int t = 0; t < RSC_NTYPES; ++t) {
+    th.eps_d[t] = p->eps[t];
+    th.cosa_d[t] = cos(p->alpha[t]);
+    th.eps[t] = (float)th.eps_d[t];
+    th.cosa[t] = (float)th.cosa_d[t];
+  }
+  th.honour_enabled = 0xFu;
+  if (p->compat_flags & RSC_COMPAT_SPHERE_IGNORES_ENABLED) th.honour_enabled &= ~(1u << RSC_SPHERE);
+  return th;
+}
+
+static int pick_k(int C) { return C >= 3072 ? 4 : (C >= 768 ? 2 : 1); }
+
+int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th,
+                      const rsc_cand* d_cands, int32_t C, int32_t* d_counts_policy, bool want_masks,
+                      cudaStream_t st, int32_t* d_counts_valid, int32_t* d_counts_enabled,
+                      const double* d_trig) {
+  if (C <= 0) return RSC_OK;
+  if (ps.n_pad >= ((int64_t)1 << 32)) return fail(ctx, RSC_E_ARG, "point set too large for one shard (>= 2^32)");
+  const int K = pick_k(C);
+  const int spc = kThreads * K;
+  const int ncols = (C + spc - 1) / spc + RSC_NTYPES;
+  const int cslots = ncols * spc;
+  const int ntiles = (int)(ps.n_pad / kTile);
+  const int64_t groups = ps.n_pad / 32;
+
+  RSC_CUDA(ctx, ctx->rec.ensure((size_t)kRecFields * cslots * sizeof(float)));
+  RSC_CUDA(ctx, ctx->orig.ensure((size_t)cslots * sizeof(int32_t)));
+  RSC_CUDA(ctx, ctx->slot_of.ensure((size_t)C * sizeof(int32_t)));
+  RSC_CUDA(ctx, ctx->blktab.ensure((size_t)ncols * sizeof(BlockTab)));
+  RSC_CUDA(ctx, ctx->counts.ensure((size_t)2 * C * sizeof(int32_t)));
+  RSC_CUDA(ctx, ctx->worklist.ensure(ctx->wl_cap * sizeof(AmbPair)));
+  RSC_CUDA(ctx, ctx->wl_count.ensure(16));
+  if (want_masks) RSC_CUDA(ctx, ctx->masks_gm.ensure((size_t)groups * cslots * sizeof(uint32_t)));
+
+  int32_t* cv = d_counts_valid ? d_counts_valid : ctx->counts.as<int32_t>();
+  int32_t* ce = d_counts_enabled ? d_counts_enabled : ctx->counts.as<int32_t>() + C;
+  RSC_CUDA(ctx, cudaMemsetAsync(cv, 0, (size_t)C * sizeof(int32_t), st));
+  RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C * sizeof(int32_t), st));
+  RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.p, 0, sizeof(uint32_t), st));
+
+  compile_kernel<<<1, 1024, 0, st>>>(d_cands, C, spc, cslots, ncols, cloud->pmax, cloud->nmax,
+                                     ctx->rec.as<float>(), ctx->orig.as<int32_t>(),
+                                     ctx->slot_of.as<int32_t>(), ctx->blktab.as<BlockTab>());
+  RSC_CUDA(ctx, cudaGetLastError());
+
+  ScoreArgs a;
+  a.ps = ps;
+  a.th = th;
+  a.rec = ctx->rec.as<float>();
+  a.orig = ctx->orig.as<int32_t>();
+  a.tab = ctx->blktab.as<BlockTab>();
+  a.cslots = cslots;
+  a.ntiles = ntiles;
+  a.counts_valid = cv;
+  a.counts_enabled = ce;
+  a.masks = want_masks ? ctx->masks_gm.as<uint32_t>() : nullptr;
+  a.wl = ctx->worklist.as<AmbPair>();
+  a.wl_count = ctx->wl_count.as<uint32_t>();
+  a.wl_cap = (uint32_t)ctx->wl_cap;
+
+  // grid: columns x point chunks; aim at >= 8 waves of 5 CTAs/SM so the tail stays small
+  const int real_cols = (C + spc - 1) / spc;
+  const long target = (long)ctx->sm_count * 5 * 8;
+  long chunks = (target + real_cols - 1) / real_cols;
+  if (chunks > ntiles) chunks = ntiles;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  a.tiles_per_chunk = (int)((ntiles + chunks - 1) / chunks);
+  chunks = (ntiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+  dim3 grid((unsigned)ncols, (unsigned)chunks);
+
+  RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
+  switch (K) {
+    case 4:
+      score_kernel<4><<<grid, kThreads, 0, st>>>(a);
+      break;
+    case 2:
+      score_kernel<2><<<grid, kThreads, 0, st>>>(a);
+      break;
+    default:
+      score_kernel<1><<<grid, kThreads, 0, st>>>(a);
+      break;
+  }
+  RSC_CUDA(ctx, cudaGetLastError());
+  RSC_CUDA(ctx, cudaEventRecord(ctx->evk1, st));
+  ctx->stats.score_launches += 1;
+  ctx->stats.evals += (int64_t)C * ps.n;
+  ctx->stats.cands_scored += C;
+
+  fixup_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(a, d_cands, reinterpret_cast<const ex::ConeTrig*>(d_trig),
+                                                  ctx->slot_of.as<int32_t>());
+  RSC_CUDA(ctx, cudaGetLastError());
+  if (d_counts_policy) {
+    select_counts_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_cands, C, cv, ce, th.honour_enabled, d_counts_policy);
+    RSC_CUDA(ctx, cudaGetLastError());
+  }
+  return RSC_OK;
+}
+
+// after score_enqueue(want_masks=true): ctx->masks_cm = [C][ceil(m/32)] candidate-major masks
+int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st) {
+  const int K = pick_k(C);
+  const int spc = kThreads * K;
+  const int ncols = (C + spc - 1) / spc + RSC_NTYPES;
+  const int cslots = ncols * spc;
+  const int64_t words = (m + 31) / 32;
+  RSC_CUDA(ctx, ctx->masks_cm.ensure((size_t)C * words * sizeof(uint32_t)));
+  dim3 grid((unsigned)((C + 31) / 32), (unsigned)((words + 31) / 32));
+  masks_transpose_kernel<<<grid, dim3(32, 32), 0, st>>>(ctx->masks_gm.as<uint32_t>(), ctx->slot_of.as<int32_t>(),
+                                                        C, cslots, words, ctx->masks_cm.as<uint32_t>());
+  RSC_CUDA(ctx, cudaGetLastError());
+  return RSC_OK;
+}
+
+}  // namespace rsc

@@ -1,0 +1,165 @@
+"""Host-side mirror of the reference's per-shape operator API and candidate bookkeeping:
+`fit`, `scorecandidate(s)`, `refit`, `forcefitshapes`, `IterationCandidates`, `findhighestscore`
+(src/fitting.jl:15-221 and src/shapes/*.jl).  Every built-in shape routes to the CUDA library
+through the C ABI; there is no Python/NumPy implementation of the math here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib
+from .cloud import RANSACCloud
+from .confidence import ConfidenceInterval, estimatescore, isoverlap
+from .params import to_c
+from .shapes import SHAPE_KIND, ExtractedShape, FittedShape, from_cand, pack_cands
+
+
+# ---- fit (fitting.jl:30; plane.jl:33, sphere.jl:87, cylinder.jl:135, cone.jl:123) ------------
+def fit_points(pc: RANSACCloud, p, n, params) -> Tuple[List[FittedShape], np.ndarray]:
+    """Batched forcefitshapes!: p, n are (S, k, 3); returns candidates in (set, shape_types) order
+    and the source set of each."""
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    n = np.ascontiguousarray(n, dtype=np.float64)
+    assert p.shape == n.shape and p.ndim == 3 and p.shape[2] == 3, "Size must be the same."
+    S, k = p.shape[0], p.shape[1]
+    assert k > 2, "At least 3 point is needed."
+    cp = to_c(params)
+    cap = max(S * cp.n_shape_types, 1)
+    out = (_lib.rsc_cand * cap)()
+    out_set = np.zeros(cap, dtype=np.int32)
+    out_n = C.c_int32()
+    pc.ctx.check(lib.rsc_fit_points(pc.ctx.h, C.byref(cp), p.ctypes.data, n.ctypes.data, S, k, out, out_set.ctypes.data, C.byref(out_n)))
+    return [from_cand(out[i]) for i in range(out_n.value)], out_set[: out_n.value].copy()
+
+
+def fit(shape_type, p, n, pc: RANSACCloud, params) -> Optional[FittedShape]:
+    """fit(::Type{S}, p, n, pc, params): one shape type, one minimal set -> shape or None."""
+    one = dict(params)
+    one["iteration"] = dict(params["iteration"], shape_types=[shape_type])
+    shapes, _ = fit_points(pc, np.asarray(p, dtype=np.float64)[None], np.asarray(n, dtype=np.float64)[None], one)
+    return shapes[0] if shapes else None
+
+
+def fit_batch(pc: RANSACCloud, idx, params) -> Tuple[List[FittedShape], np.ndarray]:
+    """forcefitshapes! for S minimal sets given as (S, drawN) point indices into the cloud."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    S = idx.shape[0]
+    cp = to_c(params)
+    assert idx.shape[1] == cp.drawN
+    cap = max(S * cp.n_shape_types, 1)
+    out = (_lib.rsc_cand * cap)()
+    out_set = np.zeros(cap, dtype=np.int32)
+    out_n = C.c_int32()
+    pc.ctx.check(lib.rsc_fit_batch(pc.handle, C.byref(cp), idx.ctypes.data, S, out, out_set.ctypes.data, C.byref(out_n)))
+    return [from_cand(out[i]) for i in range(out_n.value)], out_set[: out_n.value].copy()
+
+
+def sample_fit(pc: RANSACCloud, params, seed: int, set0: int, S: int):
+    """samplepointcloud4! + forcefitshapes! for S minimal sets (fitting.jl:383-430, :165-173)."""
+    cp = to_c(params)
+    cap = max(S * cp.n_shape_types, 1)
+    out = (_lib.rsc_cand * cap)()
+    out_set = np.zeros(cap, dtype=np.int32)
+    out_idx = np.zeros((S, cp.drawN), dtype=np.int64)
+    out_n = C.c_int32()
+    pc.ctx.check(lib.rsc_sample_fit(pc.handle, C.byref(cp), seed, set0, S, out, out_set.ctypes.data, out_idx.ctypes.data, C.byref(out_n)))
+    return [from_cand(out[i]) for i in range(out_n.value)], out_set[: out_n.value].copy(), out_idx
+
+
+# ---- scoring (fitting.jl:45,181-190; shapes/*.jl scorecandidate) -------------------------------
+def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: int, params, want_masks=False):
+    """Raw device scoring: inlier counts (and packed masks) of candidates against subset `subsetID`
+    (0-based; -1 = whole cloud)."""
+    Cn = len(candidates)
+    counts = np.zeros(Cn, dtype=np.int32)
+    if Cn == 0:
+        return counts, None
+    if subsetID >= 0:
+        pc.upload_subset(subsetID)
+        M = len(pc.subsets[subsetID])
+    else:
+        M = pc.size
+    arr = pack_cands(candidates)
+    cp = to_c(params)
+    masks = np.zeros((Cn, (M + 31) // 32), dtype=np.uint32) if want_masks else None
+    pc.ctx.check(lib.rsc_score(pc.handle, C.byref(cp), arr, Cn, subsetID, counts.ctypes.data, masks.ctypes.data if want_masks else None))
+    return counts, masks
+
+
+def unpack_mask(row: np.ndarray, M: int) -> np.ndarray:
+    return np.unpackbits(row.view(np.uint8), bitorder="little")[:M].astype(bool)
+
+
+def scorecandidates(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: int, params):
+    """scorecandidates!: [(ConfidenceInterval, inpoints)] for all candidates in ONE launch."""
+    counts, masks = score_counts(pc, candidates, subsetID, params, want_masks=True)
+    sub = pc.subsets[subsetID]
+    out = []
+    for i in range(len(candidates)):
+        m = unpack_mask(masks[i], len(sub))
+        out.append((estimatescore(len(sub), pc.size, int(counts[i])), sub[m]))
+    return out
+
+
+def scorecandidate(pc: RANSACCloud, candidate: FittedShape, subsetID: int, params):
+    """scorecandidate(pc, candidate, subsetID, params) -> (score, inpoints)."""
+    return scorecandidates(pc, [candidate], subsetID, params)[0]
+
+
+# ---- refit (fitting.jl:57; shapes/*.jl refit) + invalidate_indexes! (fitting.jl:197) -----------
+def refit(s: FittedShape, pc: RANSACCloud, params, disable: bool = False) -> ExtractedShape:
+    cand = s.to_cand()
+    cp = to_c(params)
+    out = np.zeros(pc.size, dtype=np.int64)
+    n = C.c_int64()
+    pc.ctx.check(lib.rsc_refit_extract(pc.handle, C.byref(cp), C.byref(cand), out.ctypes.data, C.byref(n), int(disable)))
+    return ExtractedShape(s, out[: n.value].copy())
+
+
+def invalidate_indexes(pc: RANSACCloud, indexlist):
+    en = pc.isenabled
+    en[np.asarray(indexlist, dtype=np.int64) - pc.global_offset] = False
+    pc.isenabled = en
+
+
+# ---- candidate store (fitting.jl:94-158) --------------------------------------------------------
+class IterationCandidates:
+    """SoA store of (shape, score, inpoints) -- fitting.jl:94-131."""
+
+    def __init__(self):
+        self.shapes: List[FittedShape] = []
+        self.scores: List[ConfidenceInterval] = []
+        self.inpoints: List[np.ndarray] = []
+
+    def __len__(self):
+        return len(self.shapes)
+
+    def recordscore(self, shape, score, inpoints):
+        self.shapes.append(shape)
+        self.scores.append(score)
+        self.inpoints.append(inpoints)
+        return self
+
+    def deleteat(self, arg):
+        idx = sorted([arg] if np.isscalar(arg) else list(arg), reverse=True)
+        for i in idx:
+            del self.shapes[i], self.scores[i], self.inpoints[i]
+        return self
+
+
+def findhighestscore(A: IterationCandidates):
+    """fitting.jl:140-158 -> (index, overlap); index -1 when empty (0-based)."""
+    if len(A) == 0:
+        return -1, False
+    ind, highest = 0, A.scores[0].E
+    for i, sc in enumerate(A.scores):
+        if sc.E > highest:
+            highest, ind = sc.E, i
+    for i, sc in enumerate(A.scores):
+        if i != ind and isoverlap(sc, A.scores[ind]):
+            return ind, True
+    return ind, False

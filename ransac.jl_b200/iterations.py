@@ -1,0 +1,113 @@
+"""ransac(pc, params, setenabled; reset_rand): mirror of src/iterations.jl:14-162.
+
+For the four built-in shape types the whole loop runs inside the CUDA library behind one C-ABI call
+(`rsc_ransac_run`).  If `shape_types` contains a user-defined FittedShape subclass the loop runs
+here and calls that class's own `fit`/`scorecandidate`/`refit` methods -- the reference's plug-in
+contract (docs/src/newprimitive.md:12-18) -- while built-in types still score on the device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib
+from .cloud import RANSACCloud
+from .confidence import prob
+from .fitting import IterationCandidates, findhighestscore, refit, sample_fit, scorecandidates
+from .params import to_c
+from .shapes import SHAPE_KIND, ExtractedShape, from_cand
+
+
+def _all_builtin(params) -> bool:
+    return all(t in SHAPE_KIND for t in params["iteration"]["shape_types"])
+
+
+def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = False, seed: int = 1234) -> Tuple[List[ExtractedShape], float]:
+    """Run efficient RANSAC on `pc`; returns (extracted shapes, seconds).
+
+    `reset_rand=True` pins the sampler seed to 1234 like `Random.seed!(1234)` (iterations.jl:36);
+    the Philox stream is of course not Julia's."""
+    if setenabled:
+        pc.enable_all()
+    if reset_rand:
+        seed = 1234
+    if _all_builtin(params):
+        return _ransac_device(pc, params, seed)
+    return _ransac_host(pc, params, seed)
+
+
+def _ransac_device(pc, params, seed):
+    cp = to_c(params)
+    run = C.c_void_p()
+    pc.ctx.check(lib.rsc_ransac_run(pc.handle, C.byref(cp), seed, C.byref(run)))
+    try:
+        out = []
+        for i in range(lib.rsc_run_nshapes(run)):
+            cand = _lib.rsc_cand()
+            n = C.c_int64()
+            pc.ctx.check(lib.rsc_run_shape(run, i, C.byref(cand), C.byref(n)))
+            idx = np.zeros(n.value, dtype=np.int64)
+            if n.value:
+                pc.ctx.check(lib.rsc_run_inpoints(run, i, idx.ctypes.data))
+            out.append(ExtractedShape(from_cand(cand), idx))
+        secs = lib.rsc_run_seconds(run)
+    finally:
+        lib.rsc_run_destroy(run)
+    return out, int(secs * 100) / 100.0
+
+
+def _ransac_host(pc, params, seed):
+    """iterations.jl:35-162 on the host, for parameter sets with user-defined shapes."""
+    it = params["iteration"]
+    drawN, minsubsetN, prob_det, tau = it["drawN"], it["minsubsetN"], it["prob_det"], it["tau"]
+    sidx = {"lengthC": 0, "allcand": 1, "nofminset": 2}
+    builtin = [t for t in it["shape_types"] if t in SHAPE_KIND]
+    custom = [t for t in it["shape_types"] if t not in SHAPE_KIND]
+    bparams = dict(params, iteration=dict(it, shape_types=builtin))
+    t0 = time.time()
+    scored = IterationCandidates()
+    extracted: List[ExtractedShape] = []
+    cc = [0, 0, 0]
+    for k in range(1, it["itermax"] + 1):
+        if pc.count_enabled() < tau:
+            break
+        cands, csets, idx = sample_fit(pc, bparams, seed, (k - 1) * minsubsetN, minsubsetN) if builtin else ([], [], None)
+        if custom:
+            if idx is None:
+                raise NotImplementedError("user-defined shapes need at least one built-in type for sampling")
+            for row in idx:
+                if row[0] < 0:
+                    continue
+                for t in custom:
+                    f = t.fit(pc.vertices[row], pc.normals[row], pc, params)
+                    if f is not None:
+                        cands.extend(f if isinstance(f, (list, tuple)) else [f])
+        cc[1] += len(cands)
+        b = [c for c in cands if type(c) in SHAPE_KIND]
+        res = dict(zip(map(id, b), scorecandidates(pc, b, 0, params))) if b else {}
+        for c in cands:
+            sc, ip = res[id(c)] if id(c) in res else c.scorecandidate(pc, 0, params)
+            scored.recordscore(c, sc, ip)
+        cc[2] = k * minsubsetN
+        cc[0] = len(scored)
+        if len(scored) >= 1:
+            best, _ = findhighestscore(scored)
+            scr = scored.scores[best].E
+            if prob(scr, cc[sidx[it["extract_s"]]], pc.size, drawN) > prob_det:
+                shp = scored.shapes[best]
+                ex = refit(shp, pc, params, disable=True) if type(shp) in SHAPE_KIND else shp.refit(pc, params)
+                if type(shp) not in SHAPE_KIND:
+                    from .fitting import invalidate_indexes
+                    invalidate_indexes(pc, ex.inpoints)
+                extracted.append(ex)
+                scored.deleteat(best)
+                en = pc.isenabled
+                dead = [j for j in range(len(scored)) if not en[scored.inpoints[j]].all()]
+                scored.deleteat(dead)
+        if prob(tau, cc[sidx[it["terminate_s"]]], pc.size, drawN) > prob_det:
+            break
+    return extracted, int((time.time() - t0) * 100) / 100.0

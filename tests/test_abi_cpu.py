@@ -1,0 +1,113 @@
+"""CPU-side checks of the boundary: the shared library loads, exports every symbol include/rsc.h
+declares, the POD layouts match the header, and the host layer fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rsc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rsc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ransac_jl_b200 as R
+
+    syms = _declared_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(R._lib.lib, s), f"{s} declared in include/rsc.h but not exported"
+        assert s in R._lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert R._lib.lib.rsc_version() == 100
+
+
+def test_pod_layouts():
+    import ransac_jl_b200 as R
+
+    assert C.sizeof(R._lib.rsc_cand) == 64
+    assert R._lib.rsc_cand.p.offset == 8
+    assert C.sizeof(R._lib.rsc_params) == 160
+    assert C.sizeof(R._lib.rsc_stats) == 56
+
+
+def test_default_params_pod_matches_reference_defaults():
+    # test/utilitytests.jl:41-82
+    import math
+
+    import ransac_jl_b200 as R
+
+    p = R._lib.rsc_params()
+    R._lib.lib.rsc_params_default(p)
+    assert (p.drawN, p.minsubsetN, p.prob_det, p.tau, p.itermax) == (3, 15, 0.9, 900, 1000)
+    assert list(p.shape_types) == [0, 3, 2, 1] and p.n_shape_types == 4  # plane, cone, cylinder, sphere
+    assert list(p.eps) == [0.3] * 4
+    assert all(abs(a - math.radians(5)) < 1e-16 for a in p.alpha)
+    assert (p.sphere_par, p.collin_threshold, p.parallelthrdeg) == (0.02, 0.2, 1.0)
+    assert abs(p.minconeopang - math.radians(2)) < 1e-16
+    c = R.to_c(R.ransacparameters(sphere={"eps": 0.01}, iteration={"tau": 50}))
+    assert c.eps[1] == 0.01 and c.eps[0] == 0.3 and c.tau == 50
+
+
+def test_parameter_mirror_matches_reference_tests():
+    # test/utilitytests.jl:84-114
+    import math
+
+    import ransac_jl_b200 as R
+
+    p = R.ransacparameters([R.FittedSphere, R.FittedCylinder], sphere={"eps": 0.01}, cylinder={"alpha": 0.02})
+    assert p["sphere"] == {"eps": 0.01, "alpha": math.radians(5), "sphere_par": 0.02}
+    assert p["cylinder"] == {"eps": 0.3, "alpha": 0.02}
+    assert p["iteration"]["shape_types"] == [R.FittedSphere, R.FittedCylinder]
+    assert R.DEFAULT_PARAMETERS["iteration"]["shape_types"] == [R.FittedPlane, R.FittedCone, R.FittedCylinder, R.FittedSphere]
+
+
+def test_confidence_interval_mirror():
+    # test/confidenceintervals.jl:1-25
+    import ransac_jl_b200 as R
+
+    ci = R.ConfidenceInterval(1.0, 3)
+    assert (ci.E, ci.min, ci.max) == (2.0, 1.0, 3.0)
+    with pytest.raises(ValueError):
+        R.ConfidenceInterval(3, 1.0)
+    nc = R.notsoconfident(153.9, 9.7)
+    assert (nc.min, nc.max, nc.E) == (9.7, 153.9, 81.8)
+
+
+def test_iteration_candidates_store():
+    # test/fitting.jl:1-18
+    import ransac_jl_b200 as R
+
+    ic = R.IterationCandidates()
+    fp = R.FittedPlane([0.5, 0.5, 0.5], [0, 0, 1.0])
+    assert len(ic) == 0
+    ic.recordscore(fp, R.ConfidenceInterval(0, 1), [1, 2, 3, 4, 5])
+    assert len(ic) == 1 and len(ic.scores) == 1 and len(ic.inpoints) == 1
+    ic.deleteat(0)
+    assert len(ic) == 0 and len(ic.shapes) == 0
+
+
+def test_estimatescore_through_abi_matches_oracle():
+    import ransac_jl_b200 as R
+    from oracle import ransac_oracle as O
+
+    for M, N, s in [(5000, 10000, 1234), (312, 10000, 0), (1 << 19, 1 << 24, 40000), (3125000, 100000000, 777)]:
+        a, b = R.estimatescore(M, N, s), O.estimatescore(M, N, s)
+        assert (a.min, a.max, a.E) == (b.min, b.max, b.E)
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+
+    import ransac_jl_b200 as R
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(R.RscError) as e:
+        R.Context(0)
+    assert e.value.code == R._lib.RSC_E_NODEVICE

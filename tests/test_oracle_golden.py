@@ -1,0 +1,111 @@
+"""Pins the NumPy oracle to the reference's own known-answer tests.
+
+Each case restates a testset of /root/reference/test (file:line cited per test) with the
+same inputs and the same expected outcome.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ransac_oracle as O
+
+EPSI = 0.1
+ALFI = math.radians(10)
+
+
+def _defrp():
+    # test/dummyspheretest.jl:8-10
+    return O.ransacparameters(O.ransacparameters(), sphere={"eps": EPSI, "alpha": ALFI})
+
+
+def _plane_rp(base):
+    # test/dummyspheretest.jl:19
+    return O.ransacparameters(base, plane={"alpha": math.pi / 2}, common={"collin_threshold": 0.2})
+
+
+TN1 = [(0, -1, 0.0), (0, 0, -1.0), (1, 0, 0.0), (0, 1, 0.0)]
+
+
+def test_true_sphere_1():
+    # test/dummyspheretest.jl:14-22
+    tv = [(0, -1, 0.0), (0, 0, -1.0), (1, 0, 0.0), (0, 1, 0.0)]
+    fs = O.fit_sphere(tv, TN1, _defrp())
+    fp = O.fit_plane(tv, TN1, _plane_rp(_defrp()))
+    assert fs is not None and fs.kind == O.SPHERE
+    assert fp is None
+    np.testing.assert_allclose(fs.a, [0, 0, 0], atol=1e-15)
+    assert fs.s == pytest.approx(1.0, abs=1e-15)
+    assert fs.outwards is True
+
+
+def test_true_sphere_2():
+    # test/dummyspheretest.jl:24-35
+    tv = [(0, -0.99, 0.0), (0, 0, -1.0), (1.01, 0, 0.0), (0, 1, 0.0)]
+    fs1 = O.fit_sphere(tv, TN1, _defrp())
+    fs2 = O.fit_sphere(tv, TN1, O.ransacparameters(_defrp(), sphere={"eps": 0.01}))
+    fp = O.fit_plane(tv, TN1, _plane_rp(_defrp()))
+    assert fs1 is not None and fs1.kind == O.SPHERE
+    assert fs2 is None
+    assert fp is None
+
+
+def test_false_sphere_1():
+    # test/dummyspheretest.jl:37-49
+    tv = [(0, 1, 0.0), (0, 0, -1.0), (1, 0, 0.0), (0, 1, 0.0)]
+    fs1 = O.fit_sphere(tv, TN1, _defrp())
+    fs2 = O.fit_sphere(tv, TN1, O.ransacparameters(_defrp(), sphere={"eps": 10, "alpha": math.pi / 2}))
+    fp = O.fit_plane(tv, TN1, _plane_rp(_defrp()))
+    assert fs1 is None and fs2 is None and fp is None
+
+
+def test_confidence_interval():
+    # test/confidenceintervals.jl:1-10
+    ci = O.ConfidenceInterval(1.0, 3)
+    assert ci.E == 2.0 and ci.min == 1.0 and ci.max == 3.0
+    with pytest.raises(ValueError):
+        O.ConfidenceInterval(3, 1.0)
+
+
+def test_notsoconfident():
+    # test/confidenceintervals.jl:12-25
+    nc1 = O.notsoconfident(153.9, 9.7)
+    nc2 = O.notsoconfident(9.7, 153.9)
+    assert nc1.min == 9.7 and nc1.max == 153.9 and nc1.E == 81.8
+    assert (nc1.min, nc1.max, nc1.E) == (nc2.min, nc2.max, nc2.E)
+
+
+def test_default_parameters():
+    # test/utilitytests.jl:41-82
+    p = O.default_parameters()
+    it = p["iteration"]
+    assert (it["drawN"], it["minsubsetN"], it["prob_det"], it["tau"], it["itermax"]) == (3, 15, 0.9, 900, 1000)
+    assert it["extract_s"] == "nofminset" and it["terminate_s"] == "nofminset"
+    assert it["shape_types"] == [O.PLANE, O.CONE, O.CYLINDER, O.SPHERE]  # src/RANSAC.jl:94
+    assert p["common"] == {"collin_threshold": 0.2, "parallelthrdeg": 1.0}
+    assert p["plane"] == {"eps": 0.3, "alpha": math.radians(5)}
+    assert p["sphere"] == {"eps": 0.3, "alpha": math.radians(5), "sphere_par": 0.02}
+    assert p["cylinder"] == {"eps": 0.3, "alpha": math.radians(5)}
+    assert p["cone"] == {"eps": 0.3, "alpha": math.radians(5), "minconeopang": math.radians(2)}
+
+
+def test_ransacparameters_merge():
+    # test/utilitytests.jl:84-114
+    p = O.ransacparameters(O.default_parameters([O.SPHERE, O.CYLINDER]), sphere={"eps": 0.01}, cylinder={"alpha": 0.02})
+    assert p["sphere"] == {"eps": 0.01, "alpha": math.radians(5), "sphere_par": 0.02}
+    assert p["cylinder"] == {"eps": 0.3, "alpha": 0.02}
+
+
+def test_estimatescore_closed_form():
+    # E = -1 + (N+2)(sigma+1)/(M+2)  (SURVEY 8a22); interval ordered; small sizes, no overflow
+    for M, N, s in [(5000, 10000, 1234), (312, 10000, 0), (312, 10000, 312), (100, 100, 50)]:
+        ci = O.estimatescore(M, N, s)
+        assert ci.min <= ci.max
+        assert ci.E == pytest.approx(-1 + (N + 2) * (s + 1) / (M + 2), rel=1e-12)
+
+
+def test_estimatescore_int64_overflow_keeps_E():
+    # Q9: the Int64 product wraps for N >~ 1e6 but E is unaffected
+    M, N, s = 1 << 19, 1 << 24, 40000
+    ci = O.estimatescore(M, N, s)
+    assert ci.E == pytest.approx(-1 + (N + 2) * (s + 1) / (M + 2), rel=1e-12)
