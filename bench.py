@@ -195,7 +195,8 @@ def main():
     arr = R.pack_cands(cands)
     d_cands = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
     d_counts = torch.zeros(Cn, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: its handle is what the C ABI gets
+    torch.cuda.set_stream(stream)
 
     def step_resident():
         rc = lib.rsc_score_dev(pc.handle, C.byref(cp), d_cands.data_ptr(), Cn, -1, d_counts.data_ptr(), stream.cuda_stream)
