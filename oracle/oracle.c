@@ -15,7 +15,7 @@
  * The same operation order as oracle/ransac_oracle.py (tests assert bit-identical masks between
  * the two).  Build with -ffp-contract=off so that no multiply-add is fused.
  *
- * Parity status: see the header of ransac_oracle.py -- PARITY UNPINNED for compatibles*/refit and
+ * Parity status: see the header of ransac_oracle.py -- PARITY UNPINNED for the compatibles functions, refit and
  * the cylinder/cone fits (no reference test pins them; Julia is not installed here); sphere/plane
  * fit accept-reject answers are pinned by test/dummyspheretest.jl.  LinearAlgebra.rank is restated
  * with a one-sided Jacobi SVD and `\` with partial-pivot Gaussian elimination.

@@ -41,12 +41,6 @@ struct Thresh {
   uint32_t honour_enabled;  // bit t set: type t ANDs pc.isenabled into its inliers (Q4 clears SPHERE)
 };
 
-// a (candidate, point) pair whose FP32 margin fell inside the guard band
-struct AmbPair {
-  uint32_t cand;   // original candidate index
-  uint32_t point;  // position in the point set
-};
-
 // block table written by the candidate compiler: which slots/type each CTA column covers
 struct BlockTab {
   int32_t type;   // -1: empty column

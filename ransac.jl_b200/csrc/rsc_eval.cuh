@@ -107,6 +107,68 @@ __device__ __forceinline__ float eval(const float* r, float px, float py, float 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed evaluation: TWO candidates per call on sm_100's 2-wide FP32 instructions (FFMA2 / FMUL2 /
+// FADD2).  A scalar FFMA issues at half the FP32 lane rate on this chip (measured: tools/
+// fp32_peak.cu), so the tiled kernel keeps its candidates as float2 pairs; the point's scalars are
+// broadcast operands (`R.F32` in SASS) and |x| / -x are operand modifiers, i.e. free.  Each half
+// performs exactly the scalar sequence of eval<T>() (same roundings, same guard band).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 rsqrt2(float2 a) { return make_float2(rsqrt_fast(a.x), rsqrt_fast(a.y)); }
+__device__ __forceinline__ float2 max2_nan(float2 a, float2 b) {
+  return make_float2(fmax_nan(a.x, b.x), fmax_nan(a.y, b.y));
+}
+
+template <int T>
+__device__ __forceinline__ float2 eval2(const float2* r, float px, float py, float pz, float nx, float ny,
+                                        float nz, float eps, float cosa) {
+  const float2 X = bc2(px), Y = bc2(py), Z = bc2(pz), NX = bc2(nx), NY = bc2(ny), NZ = bc2(nz);
+  if constexpr (T == RSC_PLANE) {
+    const float2 d = fma2(r[0], X, fma2(r[1], Y, fma2(r[2], Z, r[3])));
+    const float2 e = add2(abs2(d), bc2(-eps));
+    const float2 nt = fma2(r[4], NX, fma2(r[5], NY, fma2(r[6], NZ, bc2(cosa))));
+    return max2_nan(e, nt);
+  } else if constexpr (T == RSC_SPHERE) {
+    const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
+    const float2 vv = fma2(vx, vx, fma2(vy, vy, mul2(vz, vz)));
+    const float2 rad = mul2(vv, rsqrt2(vv));
+    const float2 e = add2(abs2(add2(rad, neg2(r[4]))), bc2(-eps));
+    const float2 s = fma2(vx, NX, fma2(vy, NY, mul2(vz, NZ)));
+    const float2 nt = fma2(bc2(cosa), rad, neg2(s));
+    return max2_nan(e, nt);
+  } else if constexpr (T == RSC_CYLINDER) {
+    const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
+    const float2 h = fma2(r[4], vx, fma2(r[5], vy, mul2(r[6], vz)));
+    const float2 wx = fma2(neg2(r[4]), h, vx), wy = fma2(neg2(r[5]), h, vy), wz = fma2(neg2(r[6]), h, vz);
+    const float2 ww = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
+    const float2 rho = mul2(ww, rsqrt2(ww));
+    const float2 e = add2(abs2(add2(rho, neg2(r[7]))), bc2(-eps));
+    const float2 wn = fma2(wx, NX, fma2(wy, NY, mul2(wz, NZ)));
+    const float2 nt = fma2(bc2(cosa), rho, neg2(wn));
+    return max2_nan(e, nt);
+  } else {
+    const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
+    const float2 h = fma2(r[4], vx, fma2(r[5], vy, mul2(r[6], vz)));
+    const float2 wx = fma2(neg2(r[4]), h, vx), wy = fma2(neg2(r[5]), h, vy), wz = fma2(neg2(r[6]), h, vz);
+    const float2 ww = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
+    const float2 rho = mul2(ww, rsqrt2(ww));
+    const float2 d = fma2(h, r[7], neg2(mul2(rho, r[8])));
+    const float2 e = add2(abs2(d), bc2(-eps));
+    const float2 wn = fma2(wx, NX, fma2(wy, NY, mul2(wz, NZ)));
+    const float2 an = fma2(r[4], NX, fma2(r[5], NY, mul2(r[6], NZ)));
+    const float2 srho = mul2(r[7], rho);
+    const float2 q = fma2(r[8], wn, neg2(mul2(srho, an)));
+    const float2 nt = fma2(bc2(cosa), rho, neg2(q));
+    return max2_nan(e, nt);
+  }
+}
+
 // runtime-type version for the (rare) slow path
 __device__ __forceinline__ float eval_any(int type, const float* r, float px, float py, float pz,
                                           float nx, float ny, float nz, float eps, float cosa) {

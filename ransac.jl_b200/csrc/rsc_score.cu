@@ -20,6 +20,15 @@
 
 namespace rsc {
 
+// a 32-point group of one candidate whose min|margin| fell inside the FP32 guard band: the fix-up
+// kernel re-derives the reference's (float64) decision for its 32 points and corrects count/mask
+struct GroupTask {
+  uint32_t cand;   // original candidate index
+  uint32_t group;  // 32-point group index in the point set
+  uint32_t word;   // the FP32 decision bits the tiled kernel used (before enabled/valid gating)
+  uint32_t pad;
+};
+
 struct ScoreArgs {
   PointSet ps;
   Thresh th;
@@ -27,55 +36,89 @@ struct ScoreArgs {
   const int32_t* orig;     // [cslots] original candidate index, -1 for padding slots
   const BlockTab* tab;     // [gridDim.x]
   int32_t cslots;          // slot stride of rec / masks
-  int32_t tiles_per_chunk;
-  int32_t ntiles;
+  int32_t subs_per_chunk;  // 128-point sub-tiles per CTA row
+  int32_t nsubs;
   int32_t* counts_valid;   // [C] compatible real points
   int32_t* counts_enabled; // [C] compatible enabled points
   uint32_t* masks;         // nullable, group-major [n_pad/32][cslots]
-  AmbPair* wl;
+  GroupTask* wl;
   uint32_t* wl_count;
   uint32_t wl_cap;
 };
 
-// ---------------------------------------------------------------------------------------------
-// slow path: a 32-point group whose min|margin| fell inside the band.  Re-evaluates the group for
-// one slot, clears the ambiguous bits and queues those pairs for the FP64 fix-up.
-// ---------------------------------------------------------------------------------------------
-__device__ __noinline__ uint32_t resolve_group(const ScoreArgs& a, int type, int slot, uint32_t w,
-                                               const float4* sA, const float2* sB, int64_t p0) {
-  float r[kRecFields];
-#pragma unroll
-  for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
-  const float band = r[kBandField];
-  const float eps = a.th.eps[type], cosa = a.th.cosa[type];
-  const int orig = a.orig[slot];
-  for (int i = 0; i < 32; ++i) {
-    float4 A = sA[i];
-    float2 B = sB[i];
-    float m = eval_any(type, r, A.x, A.y, A.z, A.w, B.x, B.y, eps, cosa);
-    if (!(fabsf(m) > band)) {
-      w &= ~(1u << i);
-      if (orig >= 0 && p0 + i < a.ps.n) {
-        uint32_t pos = atomicAdd(a.wl_count, 1u);
-        if (pos < a.wl_cap) a.wl[pos] = AmbPair{(uint32_t)orig, (uint32_t)(p0 + i)};
-      }
-    }
-  }
-  return w;
+constexpr int kSub = 128;                       // points per warp-private sub-tile
+constexpr int kStages = 2;                      // sub-tiles in flight per warp
+constexpr int kSubFloats = 6 * kSub;            // x|y|z|nx|ny|nz rows of one sub-tile
+constexpr uint32_t kSubBytes = kSubFloats * 4;  // 3072
+
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100 PTX) ---------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
+// one lane: fetch sub-tile `sub` (6 SoA rows of 128 floats) into a warp-private stage
+__device__ __forceinline__ void issue_subtile(const PointSet& ps, int sub, float* stage, uint64_t* bar) {
+  const int64_t off = (int64_t)sub * kSub;
+  mbar_expect_tx(bar, kSubBytes);
+  bulk_g2s(stage + 0 * kSub, ps.x + off, kSub * 4, bar);
+  bulk_g2s(stage + 1 * kSub, ps.y + off, kSub * 4, bar);
+  bulk_g2s(stage + 2 * kSub, ps.z + off, kSub * 4, bar);
+  bulk_g2s(stage + 3 * kSub, ps.nx + off, kSub * 4, bar);
+  bulk_g2s(stage + 4 * kSub, ps.ny + off, kSub * 4, bar);
+  bulk_g2s(stage + 5 * kSub, ps.nz + off, kSub * 4, bar);
+}
+
+// K candidates per thread; for even K they are evaluated as K/2 packed pairs (FFMA2 path).
+// Every WARP streams the CTA row's points through its own double-buffered shared-memory stages
+// (TMA bulk copies signalled on warp-private mbarriers): there is no CTA-wide barrier in the loop.
 template <int T, int K>
-__device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float4* sA, float2* sB) {
+__device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float* wstage, uint64_t* wbar) {
   constexpr int NR = RecN<T>::n;
-  float r[K][NR];
+  constexpr bool kPacked = (K % 2 == 0);
+  constexpr int KP = kPacked ? K / 2 : 1;
+  float r[kPacked ? 1 : K][NR];  // scalar records (K odd)
+  float2 r2[KP][NR];             // packed records: .x = candidate 2j, .y = candidate 2j+1
   float band[K];
   int cntv[K], cnte[K];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const int slot = slot0 + k * kThreads + tid;
 #pragma unroll
-    for (int f = 0; f < NR; ++f) r[k][f] = a.rec[(size_t)f * a.cslots + slot];
+    for (int f = 0; f < NR; ++f) {
+      const float v = a.rec[(size_t)f * a.cslots + slot];
+      if constexpr (kPacked) {
+        if (k & 1)
+          r2[k / 2][f].y = v;
+        else
+          r2[k / 2][f].x = v;
+      } else {
+        r[k][f] = v;
+      }
+    }
     band[k] = a.rec[(size_t)kBandField * a.cslots + slot];
     cntv[k] = 0;
     cnte[k] = 0;
@@ -83,29 +126,19 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float4
   const float eps = a.th.eps[T], cosa = a.th.cosa[T];
   const bool honour = (a.th.honour_enabled >> T) & 1u;
 
-  const int tile0 = blockIdx.y * a.tiles_per_chunk;
-  const int tile1 = min(tile0 + a.tiles_per_chunk, a.ntiles);
-  for (int tile = tile0; tile < tile1; ++tile) {
-    const int64_t base = (int64_t)tile * kTile;
-    {  // stage: 6 x 128-bit loads per thread (4 consecutive points), re-packed per point
-      const int64_t i = base + 4 * tid;
-      const float4 X = __ldg(reinterpret_cast<const float4*>(a.ps.x + i));
-      const float4 Y = __ldg(reinterpret_cast<const float4*>(a.ps.y + i));
-      const float4 Z = __ldg(reinterpret_cast<const float4*>(a.ps.z + i));
-      const float4 U = __ldg(reinterpret_cast<const float4*>(a.ps.nx + i));
-      const float4 V = __ldg(reinterpret_cast<const float4*>(a.ps.ny + i));
-      const float4 W = __ldg(reinterpret_cast<const float4*>(a.ps.nz + i));
-      sA[4 * tid + 0] = make_float4(X.x, Y.x, Z.x, U.x);
-      sA[4 * tid + 1] = make_float4(X.y, Y.y, Z.y, U.y);
-      sA[4 * tid + 2] = make_float4(X.z, Y.z, Z.z, U.z);
-      sA[4 * tid + 3] = make_float4(X.w, Y.w, Z.w, U.w);
-      sB[4 * tid + 0] = make_float2(V.x, W.x);
-      sB[4 * tid + 1] = make_float2(V.y, W.y);
-      sB[4 * tid + 2] = make_float2(V.z, W.z);
-      sB[4 * tid + 3] = make_float2(V.w, W.w);
-    }
-    __syncthreads();
-    for (int g = 0; g < kGroupsPerTile; ++g) {
+  const int sub0 = blockIdx.y * a.subs_per_chunk;
+  const int nsub = min(a.subs_per_chunk, a.nsubs - sub0);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+      if (s < nsub) issue_subtile(a.ps, sub0 + s, wstage + s * kSubFloats, wbar + s);
+  }
+  for (int it = 0; it < nsub; ++it) {
+    const int st = it % kStages;
+    mbar_wait(wbar + st, (it / kStages) & 1);
+    const float* sx = wstage + st * kSubFloats;
+#pragma unroll 1
+    for (int g = 0; g < kSub / 32; ++g) {
       uint32_t mask[K];
       float mabs[K];
 #pragma unroll
@@ -113,33 +146,60 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float4
         mask[k] = 0u;
         mabs[k] = __int_as_float(0x7f800000);
       }
-      const float4* gA = sA + g * 32;
-      const float2* gB = sB + g * 32;
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const float4 A = gA[i];
-        const float2 B = gB[i];
+      const float* gx = sx + g * 32;
+#pragma unroll 1
+      for (int i4 = 0; i4 < 32; i4 += 4) {
+        // 6 broadcast 128-bit loads = 4 points
+        const float4 X = *reinterpret_cast<const float4*>(gx + i4);
+        const float4 Y = *reinterpret_cast<const float4*>(gx + kSub + i4);
+        const float4 Z = *reinterpret_cast<const float4*>(gx + 2 * kSub + i4);
+        const float4 U = *reinterpret_cast<const float4*>(gx + 3 * kSub + i4);
+        const float4 V = *reinterpret_cast<const float4*>(gx + 4 * kSub + i4);
+        const float4 W = *reinterpret_cast<const float4*>(gx + 5 * kSub + i4);
+        const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
+        const float nx[4] = {U.x, U.y, U.z, U.w}, ny[4] = {V.x, V.y, V.z, V.w}, nz[4] = {W.x, W.y, W.z, W.w};
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const float m = eval<T>(r[k], A.x, A.y, A.z, A.w, B.x, B.y, eps, cosa);
-          mask[k] = __funnelshift_l(__float_as_uint(m), mask[k], 1);  // sign bit = compatible
-          mabs[k] = fmin_nan(mabs[k], fabsf(m));
+        for (int q = 0; q < 4; ++q) {
+          if constexpr (kPacked) {
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+              const float2 m = eval2<T>(r2[j], px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
+              mask[2 * j] = __funnelshift_l(__float_as_uint(m.x), mask[2 * j], 1);  // sign bit = compatible
+              mask[2 * j + 1] = __funnelshift_l(__float_as_uint(m.y), mask[2 * j + 1], 1);
+              mabs[2 * j] = fmin_nan(mabs[2 * j], fabsf(m.x));
+              mabs[2 * j + 1] = fmin_nan(mabs[2 * j + 1], fabsf(m.y));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+              const float m = eval<T>(r[k], px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
+              mask[k] = __funnelshift_l(__float_as_uint(m), mask[k], 1);
+              mabs[k] = fmin_nan(mabs[k], fabsf(m));
+            }
+          }
         }
       }
-      const int64_t gw = (int64_t)tile * kGroupsPerTile + g;
+      const int64_t gw = (int64_t)(sub0 + it) * (kSub / 32) + g;
       const uint32_t en = __ldg(a.ps.enabled + gw);
       const uint32_t va = __ldg(a.ps.valid + gw);
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        uint32_t w = __brev(mask[k]);
+        const uint32_t w = __brev(mask[k]);
         const int slot = slot0 + k * kThreads + tid;
-        if (!(mabs[k] > band[k])) w = resolve_group(a, T, slot, w, gA, gB, base + g * 32);
+        if (!(mabs[k] > band[k])) {  // rare: hand the group to the FP64 fix-up kernel
+          const int o = a.orig[slot];
+          if (o >= 0 && va) {
+            const uint32_t pos = atomicAdd(a.wl_count, 1u);
+            if (pos < a.wl_cap) a.wl[pos] = GroupTask{(uint32_t)o, (uint32_t)gw, w, 0u};
+          }
+        }
         cntv[k] += __popc(w & va);
         cnte[k] += __popc(w & en);
         if (a.masks) a.masks[(size_t)gw * a.cslots + slot] = w & (honour ? en : va);
       }
     }
-    __syncthreads();
+    __syncwarp();
+    if (lane == 0 && it + kStages < nsub) issue_subtile(a.ps, sub0 + it + kStages, wstage + st * kSubFloats, wbar + st);
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -153,58 +213,81 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float4
 
 template <int K>
 __global__ void __launch_bounds__(kThreads) score_kernel(const __grid_constant__ ScoreArgs a) {
-  __shared__ float4 sA[kTile];
-  __shared__ float2 sB[kTile];
+  __shared__ __align__(128) float stages[kThreads / 32][kStages * kSubFloats];
+  __shared__ __align__(8) uint64_t bars[kThreads / 32][kStages];
   const BlockTab bt = a.tab[blockIdx.x];
   if (bt.type < 0) return;
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
   switch (bt.type) {
     case RSC_PLANE:
-      score_body<RSC_PLANE, K>(a, bt.slot0, sA, sB);
+      score_body<RSC_PLANE, K>(a, bt.slot0, stages[warp], bars[warp]);
       break;
     case RSC_SPHERE:
-      score_body<RSC_SPHERE, K>(a, bt.slot0, sA, sB);
+      score_body<RSC_SPHERE, K>(a, bt.slot0, stages[warp], bars[warp]);
       break;
     case RSC_CYLINDER:
-      score_body<RSC_CYLINDER, K>(a, bt.slot0, sA, sB);
+      score_body<RSC_CYLINDER, K>(a, bt.slot0, stages[warp], bars[warp]);
       break;
     default:
-      score_body<RSC_CONE, K>(a, bt.slot0, sA, sB);
+      score_body<RSC_CONE, K>(a, bt.slot0, stages[warp], bars[warp]);
       break;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// FP64 fix-up of the queued pairs (reference operation order, rsc_exact.cuh)
+// FP64 fix-up: one warp per queued 32-point group, one lane per point.  Any FP32 margin outside
+// the band has the float64 reference's sign (that is what the band bounds); inside the band the
+// pair is re-evaluated in FP64 in the reference's operation order (rsc_exact.cuh).  The difference
+// to the bits the tiled kernel used corrects the counts and the mask word.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fixup_kernel(const __grid_constant__ ScoreArgs a,
                                                     const rsc_cand* __restrict__ cands,
                                                     const ex::ConeTrig* __restrict__ trig,
                                                     const int32_t* __restrict__ slot_of) {
   const uint32_t n = min(*a.wl_count, a.wl_cap);
-  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const AmbPair pr = a.wl[e];
-    const rsc_cand c = cands[pr.cand];
-    ex::ConeTrig tr{1.0, 0.0};
-    if (c.type == RSC_CONE) {
-      if (trig) {
-        tr = trig[pr.cand];
-      } else {
-        tr.ct = cos(-c.p[6] / 2);
-        tr.st = sin(-c.p[6] / 2);
+  const int lane = threadIdx.x & 31;
+  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
+    const GroupTask tk = a.wl[e];
+    const rsc_cand c = cands[tk.cand];
+    const int slot = slot_of[tk.cand];
+    float r[kRecFields];
+#pragma unroll
+    for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
+    const uint32_t pt = tk.group * 32u + lane;
+    const float x = a.ps.x[pt], y = a.ps.y[pt], z = a.ps.z[pt];
+    const float nx = a.ps.nx[pt], ny = a.ps.ny[pt], nz = a.ps.nz[pt];
+    const float m = eval_any(c.type, r, x, y, z, nx, ny, nz, a.th.eps[c.type], a.th.cosa[c.type]);
+    bool ok = m < 0.f;
+    if (!(fabsf(m) > r[kBandField])) {
+      ex::ConeTrig tr{1.0, 0.0};
+      if (c.type == RSC_CONE) {
+        if (trig) {
+          tr = trig[tk.cand];
+        } else {
+          tr.ct = cos(-c.p[6] / 2);
+          tr.st = sin(-c.p[6] / 2);
+        }
       }
+      ok = ex::compat(c, tr, a.th, ex::V3{(double)x, (double)y, (double)z}, ex::V3{(double)nx, (double)ny, (double)nz});
     }
-    const uint32_t pt = pr.point;
-    ex::V3 p = {(double)a.ps.x[pt], (double)a.ps.y[pt], (double)a.ps.z[pt]};
-    ex::V3 nn = {(double)a.ps.nx[pt], (double)a.ps.ny[pt], (double)a.ps.nz[pt]};
-    if (!ex::compat(c, tr, a.th, p, nn)) continue;
-    const uint32_t word = pt >> 5, bit = 1u << (pt & 31);
-    const bool va = a.ps.valid[word] & bit;
-    const bool en = a.ps.enabled[word] & bit;
-    if (va) atomicAdd(a.counts_valid + pr.cand, 1);
-    if (en) atomicAdd(a.counts_enabled + pr.cand, 1);
-    if (a.masks) {
-      const bool honour = (a.th.honour_enabled >> c.type) & 1u;
-      if (honour ? en : va) atomicOr(a.masks + (size_t)word * a.cslots + slot_of[pr.cand], bit);
+    const uint32_t good = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) {
+      const uint32_t va = a.ps.valid[tk.group], en = a.ps.enabled[tk.group];
+      const int dv = __popc(good & va) - __popc(tk.word & va);
+      const int de = __popc(good & en) - __popc(tk.word & en);
+      if (dv) atomicAdd(a.counts_valid + tk.cand, dv);
+      if (de) atomicAdd(a.counts_enabled + tk.cand, de);
+      if (a.masks) {
+        const bool honour = (a.th.honour_enabled >> c.type) & 1u;
+        a.masks[(size_t)tk.group * a.cslots + slot] = good & (honour ? en : va);
+      }
     }
   }
 }
@@ -373,7 +456,7 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   const int spc = kThreads * K;
   const int ncols = (C + spc - 1) / spc + RSC_NTYPES;
   const int cslots = ncols * spc;
-  const int ntiles = (int)(ps.n_pad / kTile);
+  const int nsubs = (int)(ps.n_pad / kSub);
   const int64_t groups = ps.n_pad / 32;
 
   RSC_CUDA(ctx, ctx->rec.ensure((size_t)kRecFields * cslots * sizeof(float)));
@@ -381,7 +464,7 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   RSC_CUDA(ctx, ctx->slot_of.ensure((size_t)C * sizeof(int32_t)));
   RSC_CUDA(ctx, ctx->blktab.ensure((size_t)ncols * sizeof(BlockTab)));
   RSC_CUDA(ctx, ctx->counts.ensure((size_t)2 * C * sizeof(int32_t)));
-  RSC_CUDA(ctx, ctx->worklist.ensure(ctx->wl_cap * sizeof(AmbPair)));
+  RSC_CUDA(ctx, ctx->worklist.ensure(ctx->wl_cap * sizeof(GroupTask)));
   RSC_CUDA(ctx, ctx->wl_count.ensure(16));
   if (want_masks) RSC_CUDA(ctx, ctx->masks_gm.ensure((size_t)groups * cslots * sizeof(uint32_t)));
 
@@ -403,23 +486,23 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   a.orig = ctx->orig.as<int32_t>();
   a.tab = ctx->blktab.as<BlockTab>();
   a.cslots = cslots;
-  a.ntiles = ntiles;
+  a.nsubs = nsubs;
   a.counts_valid = cv;
   a.counts_enabled = ce;
   a.masks = want_masks ? ctx->masks_gm.as<uint32_t>() : nullptr;
-  a.wl = ctx->worklist.as<AmbPair>();
+  a.wl = ctx->worklist.as<GroupTask>();
   a.wl_count = ctx->wl_count.as<uint32_t>();
   a.wl_cap = (uint32_t)ctx->wl_cap;
 
-  // grid: columns x point chunks; aim at >= 8 waves of 5 CTAs/SM so the tail stays small
+  // grid: columns x point chunks; aim at >= 8 waves of 4 CTAs/SM so the tail stays small
   const int real_cols = (C + spc - 1) / spc;
-  const long target = (long)ctx->sm_count * 5 * 8;
+  const long target = (long)ctx->sm_count * 4 * 8;
   long chunks = (target + real_cols - 1) / real_cols;
-  if (chunks > ntiles) chunks = ntiles;
+  if (chunks > nsubs) chunks = nsubs;
   if (chunks < 1) chunks = 1;
   if (chunks > 65535) chunks = 65535;
-  a.tiles_per_chunk = (int)((ntiles + chunks - 1) / chunks);
-  chunks = (ntiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk;
+  a.subs_per_chunk = (int)((nsubs + chunks - 1) / chunks);
+  chunks = (nsubs + a.subs_per_chunk - 1) / a.subs_per_chunk;
   dim3 grid((unsigned)ncols, (unsigned)chunks);
 
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
