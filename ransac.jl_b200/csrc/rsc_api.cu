@@ -105,7 +105,7 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   rsc::DevBuf* bufs[] = {&ctx->cands,    &ctx->rec,      &ctx->orig,     &ctx->slot_of, &ctx->blktab,
-                         &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count,
+                         &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count, &ctx->pairs,
                          &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf};
   for (auto* b : bufs) b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -138,9 +138,14 @@ int32_t rsc_ctx_last_kernel(rsc_ctx* ctx, double* kernel_ms, int64_t* guard_pair
     ctx->stats.last_kernel_ms = ms;
   }
   if (guard_pairs) {
-    uint32_t n = 0;
-    if (ctx->wl_count.p) RSC_CUDA(ctx, cudaMemcpy(&n, ctx->wl_count.p, sizeof(n), cudaMemcpyDeviceToHost));
-    *guard_pairs = n;
+    uint32_t n[2] = {0, 0};
+    if (ctx->wl_count.p) RSC_CUDA(ctx, cudaMemcpy(n, ctx->wl_count.p, sizeof(n), cudaMemcpyDeviceToHost));
+    if (n[0] > ctx->wl_cap || n[1] > ctx->wl_cap) {
+      const size_t need = n[0] > n[1] ? n[0] : n[1];
+      ctx->wl_cap = need + need / 4 + 1024;  // the next call has room; this one's counts are incomplete
+      return fail(ctx, RSC_E_STATE, "guard-band queue overflowed in a *_dev call: repeat the call");
+    }
+    *guard_pairs = n[1];
   }
   return RSC_OK;
 }
@@ -184,12 +189,14 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
                        ctx->counts.as<int32_t>(), ctx->counts.as<int32_t>() + C, ctx->aux.as<double>());
     if (rc) return rc;
     RSC_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
-    uint32_t namb = 0;
+    uint32_t nq[2] = {0, 0};  // queued groups, queued pairs
     RSC_CUDA(ctx, cudaMemcpyAsync(counts, d_policy, (size_t)C * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RSC_CUDA(ctx, cudaMemcpyAsync(&namb, ctx->wl_count.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    RSC_CUDA(ctx, cudaMemcpyAsync(nq, ctx->wl_count.p, sizeof(nq), cudaMemcpyDeviceToHost, st));
     RSC_CUDA(ctx, cudaStreamSynchronize(st));
-    if ((size_t)namb > ctx->wl_cap) {  // guard-band queue overflowed: grow and redo the pass
-      ctx->wl_cap = (size_t)namb + (size_t)namb / 4 + 1024;
+    const uint32_t namb = nq[1];
+    if ((size_t)nq[0] > ctx->wl_cap || (size_t)nq[1] > ctx->wl_cap) {  // a guard-band queue overflowed: grow, redo
+      const size_t need = nq[0] > nq[1] ? nq[0] : nq[1];
+      ctx->wl_cap = need + need / 4 + 1024;
       ctx->stats.evals -= (int64_t)C * ps.n;
       ctx->stats.cands_scored -= C;
       continue;

@@ -241,54 +241,85 @@ __global__ void __launch_bounds__(kThreads) score_kernel(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------------------
-// FP64 fix-up: one warp per queued 32-point group, one lane per point.  Any FP32 margin outside
-// the band has the float64 reference's sign (that is what the band bounds); inside the band the
-// pair is re-evaluated in FP64 in the reference's operation order (rsc_exact.cuh).  The difference
-// to the bits the tiled kernel used corrects the counts and the mask word.
+// FP64 fix-up, two launches.
+//  1. fixup_scan_kernel: one warp per queued 32-point group, one lane per point.  The FP32 margin is
+//     recomputed; outside the band its sign IS the float64 reference's decision (that is what the
+//     band bounds), inside the band the (candidate, point) pair is queued.
+//  2. fixup_pair_kernel: one thread per queued pair, evaluated in FP64 in the reference's operation
+//     order (rsc_exact.cuh) -- all lanes busy, unlike a per-group FP64 branch.
+//  Both correct counts / mask bits by the difference to the bits the tiled kernel used.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) fixup_kernel(const __grid_constant__ ScoreArgs a,
-                                                    const rsc_cand* __restrict__ cands,
-                                                    const ex::ConeTrig* __restrict__ trig,
-                                                    const int32_t* __restrict__ slot_of) {
+struct AmbPair {
+  uint32_t cand_bit;  // original candidate index | (bit the tiled kernel used << 31)
+  uint32_t point;
+};
+
+__device__ __forceinline__ void apply_flip(const ScoreArgs& a, uint32_t cand, int type, int slot, uint32_t pt,
+                                           bool now_ok) {
+  const uint32_t word = pt >> 5, bit = 1u << (pt & 31);
+  const bool va = a.ps.valid[word] & bit, en = a.ps.enabled[word] & bit;
+  const int d = now_ok ? 1 : -1;
+  if (va) atomicAdd(a.counts_valid + cand, d);
+  if (en) atomicAdd(a.counts_enabled + cand, d);
+  if (a.masks) {
+    const bool honour = (a.th.honour_enabled >> type) & 1u;
+    if (honour ? en : va) atomicXor(a.masks + (size_t)word * a.cslots + slot, bit);
+  }
+}
+
+__global__ void __launch_bounds__(256) fixup_scan_kernel(const __grid_constant__ ScoreArgs a,
+                                                         const rsc_cand* __restrict__ cands,
+                                                         const int32_t* __restrict__ slot_of,
+                                                         AmbPair* __restrict__ pairs, uint32_t* __restrict__ npairs,
+                                                         uint32_t pair_cap) {
   const uint32_t n = min(*a.wl_count, a.wl_cap);
   const int lane = threadIdx.x & 31;
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
   for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
     const GroupTask tk = a.wl[e];
-    const rsc_cand c = cands[tk.cand];
+    const int type = cands[tk.cand].type;
     const int slot = slot_of[tk.cand];
     float r[kRecFields];
 #pragma unroll
     for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
     const uint32_t pt = tk.group * 32u + lane;
-    const float x = a.ps.x[pt], y = a.ps.y[pt], z = a.ps.z[pt];
-    const float nx = a.ps.nx[pt], ny = a.ps.ny[pt], nz = a.ps.nz[pt];
-    const float m = eval_any(c.type, r, x, y, z, nx, ny, nz, a.th.eps[c.type], a.th.cosa[c.type]);
-    bool ok = m < 0.f;
+    const float m = eval_any(type, r, a.ps.x[pt], a.ps.y[pt], a.ps.z[pt], a.ps.nx[pt], a.ps.ny[pt], a.ps.nz[pt],
+                             a.th.eps[type], a.th.cosa[type]);
+    const bool used = (tk.word >> lane) & 1u;
     if (!(fabsf(m) > r[kBandField])) {
-      ex::ConeTrig tr{1.0, 0.0};
-      if (c.type == RSC_CONE) {
-        if (trig) {
-          tr = trig[tk.cand];
-        } else {
-          tr.ct = cos(-c.p[6] / 2);
-          tr.st = sin(-c.p[6] / 2);
-        }
-      }
-      ok = ex::compat(c, tr, a.th, ex::V3{(double)x, (double)y, (double)z}, ex::V3{(double)nx, (double)ny, (double)nz});
+      const uint32_t pos = atomicAdd(npairs, 1u);
+      if (pos < pair_cap) pairs[pos] = AmbPair{tk.cand | ((uint32_t)used << 31), pt};
+    } else if ((m < 0.f) != used) {
+      apply_flip(a, tk.cand, type, slot, pt, m < 0.f);  // only if two FP32 evaluations straddled zero
     }
-    const uint32_t good = __ballot_sync(0xffffffffu, ok);
-    if (lane == 0) {
-      const uint32_t va = a.ps.valid[tk.group], en = a.ps.enabled[tk.group];
-      const int dv = __popc(good & va) - __popc(tk.word & va);
-      const int de = __popc(good & en) - __popc(tk.word & en);
-      if (dv) atomicAdd(a.counts_valid + tk.cand, dv);
-      if (de) atomicAdd(a.counts_enabled + tk.cand, de);
-      if (a.masks) {
-        const bool honour = (a.th.honour_enabled >> c.type) & 1u;
-        a.masks[(size_t)tk.group * a.cslots + slot] = good & (honour ? en : va);
+  }
+}
+
+__global__ void __launch_bounds__(256) fixup_pair_kernel(const __grid_constant__ ScoreArgs a,
+                                                         const rsc_cand* __restrict__ cands,
+                                                         const ex::ConeTrig* __restrict__ trig,
+                                                         const int32_t* __restrict__ slot_of,
+                                                         const AmbPair* __restrict__ pairs,
+                                                         const uint32_t* __restrict__ npairs, uint32_t pair_cap) {
+  const uint32_t n = min(*npairs, pair_cap);
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const AmbPair pr = pairs[e];
+    const uint32_t cand = pr.cand_bit & 0x7fffffffu;
+    const bool used = pr.cand_bit >> 31;
+    const rsc_cand c = cands[cand];
+    ex::ConeTrig tr{1.0, 0.0};
+    if (c.type == RSC_CONE) {
+      if (trig) {
+        tr = trig[cand];
+      } else {
+        tr.ct = cos(-c.p[6] / 2);
+        tr.st = sin(-c.p[6] / 2);
       }
     }
+    const uint32_t pt = pr.point;
+    const bool ok = ex::compat(c, tr, a.th, ex::V3{(double)a.ps.x[pt], (double)a.ps.y[pt], (double)a.ps.z[pt]},
+                               ex::V3{(double)a.ps.nx[pt], (double)a.ps.ny[pt], (double)a.ps.nz[pt]});
+    if (ok != used) apply_flip(a, cand, c.type, slot_of[cand], pt, ok);
   }
 }
 
@@ -472,7 +503,8 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   int32_t* ce = d_counts_enabled ? d_counts_enabled : ctx->counts.as<int32_t>() + C;
   RSC_CUDA(ctx, cudaMemsetAsync(cv, 0, (size_t)C * sizeof(int32_t), st));
   RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C * sizeof(int32_t), st));
-  RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.p, 0, sizeof(uint32_t), st));
+  RSC_CUDA(ctx, ctx->pairs.ensure(ctx->wl_cap * 8));
+  RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.p, 0, 2 * sizeof(uint32_t), st));
 
   compile_kernel<<<1, 1024, 0, st>>>(d_cands, C, spc, cslots, ncols, cloud->pmax, cloud->nmax,
                                      ctx->rec.as<float>(), ctx->orig.as<int32_t>(),
@@ -523,8 +555,12 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   ctx->stats.evals += (int64_t)C * ps.n;
   ctx->stats.cands_scored += C;
 
-  fixup_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(a, d_cands, reinterpret_cast<const ex::ConeTrig*>(d_trig),
-                                                  ctx->slot_of.as<int32_t>());
+  fixup_scan_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, d_cands, ctx->slot_of.as<int32_t>(), ctx->pairs.as<AmbPair>(),
+                                                       ctx->wl_count.as<uint32_t>() + 1, (uint32_t)ctx->wl_cap);
+  RSC_CUDA(ctx, cudaGetLastError());
+  fixup_pair_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, d_cands, reinterpret_cast<const ex::ConeTrig*>(d_trig),
+                                                       ctx->slot_of.as<int32_t>(), ctx->pairs.as<AmbPair>(),
+                                                       ctx->wl_count.as<uint32_t>() + 1, (uint32_t)ctx->wl_cap);
   RSC_CUDA(ctx, cudaGetLastError());
   if (d_counts_policy) {
     select_counts_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_cands, C, cv, ce, th.honour_enabled, d_counts_policy);
