@@ -83,7 +83,7 @@ struct rsc_ctx {
   rsc_stats stats{};
   // scratch of the score path
   rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, pairs, wl_count, aux;
-  rsc::DevBuf misc, misc2, idxbuf, fitbuf;
+  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf;
   size_t wl_cap = 1u << 22;  // AmbPair capacity, grows on overflow
   void* pinned = nullptr;    // small pinned staging area
   size_t pinned_cap = 0;

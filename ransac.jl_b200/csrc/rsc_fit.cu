@@ -1,16 +1,703 @@
-// rsc_fit.cu -- K1 (placeholder until the batched fit kernel lands in this file)
+// rsc_fit.cu -- K1: batched minimal-set sampling and shape fitting, one thread per minimal set.
+//
+// Replaces samplepointcloud4! (fitting.jl:383-430), forcefitshapes! (fitting.jl:165-173) and the four
+// fit methods (plane.jl:33-57, sphere.jl:29-114, cylinder.jl:34-168, cone.jl:39-128).
+//
+// The fits run in FP64 (a few kFLOP per set; the tolerance on fitted parameters is 1e-5 relative and
+// the cone apex solve can be ill conditioned) and this file is compiled with -fmad=false so that the
+// accept/reject decisions follow the plain IEEE evaluation of the reference formulas.
+// Candidates leave the kernel dense ([set][shape type] + a validity flag) and are compacted in
+// (set, shape_types) order -- the reference's candidate order, which breaks score ties (Q16).
+//
+// Sampler: every minimal set owns a Philox4x32-10 stream (key = seed, counter = (draw/2, set id)).
+// Reference semantics on the root cell (Q1): first index by rejection over all points until an
+// enabled one is hit, the others uniform over the enabled points (rank -> index by select over the
+// enabled bitmask), one re-draw on collision with the first, whole set dropped on any duplicate.
+#include <math.h>
+
+#include <vector>
+
 #include "rsc_common.cuh"
+
+namespace rsc {
+
+struct D3 {
+  double x, y, z;
+};
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator*(double s, D3 a) { return {s * a.x, s * a.y, s * a.z}; }
+__device__ __forceinline__ D3 operator-(D3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double norm(D3 a) { return sqrt(dot(a, a)); }
+__device__ __forceinline__ D3 unit(D3 a) { return (1.0 / norm(a)) * a; }  // StaticArrays: inv(norm)*a
+__device__ __forceinline__ D3 cross(D3 a, D3 b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+constexpr int kMaxK = 8;  // points per set the validators look at (minimal set + extra validators)
+
+struct FitParams {
+  double eps[RSC_NTYPES], cosa[RSC_NTYPES];
+  double cos_par;  // cosd(parallelthrdeg)
+  double sphere_par, minconeopang, collin;
+  int32_t ntypes, types[RSC_NTYPES];
+  int32_t k;
+};
+
+__device__ inline void store(rsc_cand* o, int type, int outw, D3 a, D3 b, double s) {
+  o->type = type;
+  o->outwards = outw;
+  o->p[0] = a.x, o->p[1] = a.y, o->p[2] = a.z;
+  if (type == RSC_SPHERE) {
+    o->p[3] = s, o->p[4] = 0, o->p[5] = 0, o->p[6] = 0;
+  } else {
+    o->p[3] = b.x, o->p[4] = b.y, o->p[5] = b.z, o->p[6] = s;
+  }
+}
+
+// same-side test shared by the four validators: all dots > thr -> +1, all < -thr -> -1, else 0
+__device__ inline int side(const double* d, int k, double thr) {
+  bool pos = true, neg = true;
+  for (int i = 0; i < k; ++i) {
+    pos = pos && (d[i] > thr);
+    neg = neg && (d[i] < -thr);
+  }
+  return pos ? 1 : (neg ? -1 : 0);
+}
+
+__device__ bool fit_plane(const D3* p, const D3* n, const FitParams& f, rsc_cand* out) {
+  D3 m = unit(cross(p[1] - p[0], p[2] - p[0]));
+  if (norm(m) < f.collin) return false;  // plane.jl:43 (never true: the norm is 1 or NaN, Q3)
+  double d[kMaxK];
+  for (int i = 0; i < f.k; ++i) d[i] = dot(m, unit(n[i]));
+  const int sd = side(d, f.k, f.cosa[RSC_PLANE]);
+  if (sd == 0) return false;
+  if (sd < 0) m = -1.0 * m;
+  store(out, RSC_PLANE, 1, p[0], m, 0.0);
+  return true;
+}
+
+__device__ bool fit_sphere(const D3* v, const D3* n, const FitParams& f, rsc_cand* out) {
+  const D3 n1 = unit(n[0]), n2 = unit(n[1]);
+  D3 c;
+  double R;
+  if (fabs(dot(n1, n2)) > f.cos_par) {  // parallel normals: midpoint sphere (sphere.jl:38-42)
+    c = 0.5 * (v[0] + v[1]);
+    R = norm(c - v[0]);
+  } else {
+    const D3 g = v[1] - v[0];
+    const D3 h = cross(n2, g), kk = cross(n2, n1);
+    const double nk = norm(kk), nh = norm(h);
+    if (nk < f.sphere_par || nh < f.sphere_par) {  // closest approach of the two normal lines (sphere.jl:52-61)
+      const D3 m2 = cross(n2, cross(n1, n2));
+      const D3 m1 = cross(n1, cross(n2, n1));
+      const D3 c1 = v[0] + (dot(v[1] - v[0], m2) / dot(n[0], m2)) * n[0];
+      const D3 c2 = v[1] + (dot(v[0] - v[1], m1) / dot(n[1], m1)) * n[1];
+      c = 0.5 * (c1 + c2);
+      R = (norm(v[0] - c) + norm(v[0] - c)) / 2;  // Q5: p1 twice
+    } else {
+      const double t = nh / nk;
+      c = dot(h, kk) > 0 ? v[0] + t * n1 : v[0] - t * n1;
+      R = norm(c - v[0]);
+    }
+  }
+  double d[kMaxK];
+  bool vert = true;
+  for (int i = 0; i < f.k; ++i) {
+    vert = vert && (fabs(norm(v[i] - c) - R) < f.eps[RSC_SPHERE]);
+    d[i] = dot(unit(v[i] - c), unit(n[i]));
+  }
+  if (!vert) return false;
+  const int sd = side(d, f.k, f.cosa[RSC_SPHERE]);
+  if (sd == 0) return false;
+  store(out, RSC_SPHERE, sd > 0, c, D3{0, 0, 0}, R);
+  return true;
+}
+
+// foot of w on the plane through the origin with normal a (cylinder.jl:46-59)
+__device__ __forceinline__ D3 to_plane(D3 a, D3 w) { return w + (dot(-a, w) / dot(a, a)) * a; }
+
+// first two coordinates of p in the frame (xa, ya, za), Cramer's rule (cylinder.jl:61-85)
+__device__ inline void frame2d(D3 xa, D3 ya, D3 za, D3 p, double* r) {
+  const double xx = xa.x, xy = xa.y, xz = xa.z, yx = ya.x, yy = ya.y, yz = ya.z, zx = za.x, zy = za.y, zz = za.z;
+  const double px = p.x, py = p.y, pz = p.z;
+  const double den = xz * yy * zx - xy * yz * zx - xz * yx * zy + xx * yz * zy + xy * yx * zz - xx * yy * zz;
+  const double n1 = -(pz * yy * zx) + py * yz * zx + pz * yx * zy - px * yz * zy - py * yx * zz + px * yy * zz;
+  const double n2 = pz * xy * zx - py * xz * zx - pz * xx * zy + px * xz * zy + py * xx * zz - px * xy * zz;
+  r[0] = -(n1 / den);
+  r[1] = -(n2 / den);
+}
+
+__device__ bool fit_cylinder(const D3* p, const D3* n, const FitParams& f, rsc_cand* out) {
+  if (fabs(dot(n[0], n[1])) > f.cos_par) return false;  // raw normals (Q8)
+  const D3 a = unit(cross(n[0], n[1]));
+  const D3 xa = unit(to_plane(a, p[0]));
+  const D3 ya = unit(cross(a, xa));
+  double A[2], B[2], C[2], Dd[2];
+  frame2d(xa, ya, a, to_plane(a, p[0]), A);
+  frame2d(xa, ya, a, to_plane(a, p[0] + n[0]), B);
+  frame2d(xa, ya, a, to_plane(a, p[1]), C);
+  frame2d(xa, ya, a, to_plane(a, p[1] + n[1]), Dd);
+  // intersection of the two projected normal lines (cylinder.jl:87-101)
+  const double ab[2] = {A[0] - B[0], A[1] - B[1]}, cd[2] = {C[0] - Dd[0], C[1] - Dd[1]};
+  const double d1 = A[0] * B[1] - A[1] * B[0];
+  const double d2 = C[0] * Dd[1] - C[1] * Dd[0];
+  const double d3 = ab[0] * cd[1] - ab[1] * cd[0];
+  const double i0 = (d1 * cd[0] - d2 * ab[0]) / d3, i1 = (d1 * cd[1] - d2 * ab[1]) / d3;
+  const D3 c = i0 * xa + i1 * ya;
+  double rr[2];
+  for (int i = 0; i < 2; ++i) {
+    const D3 q = p[i] - c;
+    rr[i] = norm(q - dot(a, q) * a);
+  }
+  const double R = (rr[0] + rr[1]) / 2;
+  double d[kMaxK];
+  bool vert = true;
+  for (int i = 0; i < f.k; ++i) {
+    const D3 w = (p[i] - dot(a, p[i] - c) * a) - c;
+    vert = vert && (fabs(norm(w) - R) < f.eps[RSC_CYLINDER]);
+    d[i] = dot(unit(w), n[i]);
+  }
+  if (!vert) return false;
+  const int sd = side(d, f.k, f.cosa[RSC_CYLINDER]);
+  if (sd == 0) return false;
+  store(out, RSC_CYLINDER, sd > 0, a, c, R);
+  return true;
+}
+
+// singular values of a 3 x c matrix (c = 3 or 4): one-sided Jacobi on the rows
+__device__ inline void singular_values3(const double* A, int c, double* s) {
+  double B[3][4];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 4; ++j) B[i][j] = j < c ? A[i * c + j] : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < 2; ++i)
+      for (int j = i + 1; j < 3; ++j) {
+        double aii = 0, ajj = 0, aij = 0;
+        for (int t = 0; t < 4; ++t) aii += B[i][t] * B[i][t], ajj += B[j][t] * B[j][t], aij += B[i][t] * B[j][t];
+        if (aij == 0.0) continue;
+        off = fmax(off, fabs(aij) / sqrt(aii * ajj + 1e-300));
+        const double zeta = (ajj - aii) / (2.0 * aij);
+        const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+        for (int t = 0; t < 4; ++t) {
+          const double bi = B[i][t], bj = B[j][t];
+          B[i][t] = cs * bi - sn * bj;
+          B[j][t] = sn * bi + cs * bj;
+        }
+      }
+    if (off < 1e-17) break;
+  }
+  for (int i = 0; i < 3; ++i) {
+    double q = 0;
+    for (int t = 0; t < 4; ++t) q += B[i][t] * B[i][t];
+    s[i] = sqrt(q);
+  }
+}
+
+// LinearAlgebra.rank(A) == 3 for a 3 x c matrix: all singular values > min(size)*eps*smax
+__device__ inline bool full_rank3(const double* A, int c) {
+  for (int i = 0; i < 3 * c; ++i)
+    if (!isfinite(A[i])) return false;
+  double s[3];
+  singular_values3(A, c, s);
+  const double tol = 3 * 2.220446049250313e-16 * fmax(s[0], fmax(s[1], s[2]));
+  return s[0] > tol && s[1] > tol && s[2] > tol;
+}
+
+__device__ inline bool solve3(const double* A, const double* b, double* x) {
+  double M[3][4];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) M[i][j] = A[i * 3 + j];
+    M[i][3] = b[i];
+  }
+  for (int col = 0; col < 3; ++col) {
+    int piv = col;
+    for (int r = col + 1; r < 3; ++r)
+      if (fabs(M[r][col]) > fabs(M[piv][col])) piv = r;
+    if (M[piv][col] == 0.0) return false;
+    if (piv != col)
+      for (int j = 0; j < 4; ++j) {
+        const double t = M[col][j];
+        M[col][j] = M[piv][j];
+        M[piv][j] = t;
+      }
+    for (int r = col + 1; r < 3; ++r) {
+      const double fct = M[r][col] / M[col][col];
+      for (int j = col; j < 4; ++j) M[r][j] -= fct * M[col][j];
+    }
+  }
+  for (int i = 2; i >= 0; --i) {
+    double s = M[i][3];
+    for (int j = i + 1; j < 3; ++j) s -= M[i][j] * x[j];
+    x[i] = s / M[i][i];
+  }
+  return true;
+}
+
+// project2cone (cone.jl:68-85) in the reference's own order: distance to the surface and the
+// surface normal there, through the Rodrigues matrix of the axis perpendicular to (axis, apex->p)
+__device__ inline double project2cone(D3 apex, D3 axis, double ct, double st, D3 p, D3* nrm) {
+  const D3 tp = apex - p;
+  const D3 tpn = unit(tp);
+  const D3 rot = unit(cross(axis, tpn));
+  const D3 cn = unit(cross(axis, rot));
+  const D3 nv = unit(rot);
+  const double v[3] = {nv.x, nv.y, nv.z};
+  double R[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const double o = v[i] * v[j];
+      R[i][j] = o + ct * ((i == j ? 1.0 : 0.0) - o);
+    }
+  R[0][1] -= st * v[2];
+  R[0][2] += st * v[1];
+  R[1][0] += st * v[2];
+  R[1][2] -= st * v[0];
+  R[2][0] -= st * v[1];
+  R[2][1] += st * v[0];
+  const D3 rv = {R[0][0] * cn.x + R[0][1] * cn.y + R[0][2] * cn.z, R[1][0] * cn.x + R[1][1] * cn.y + R[1][2] * cn.z,
+                 R[2][0] * cn.x + R[2][1] * cn.y + R[2][2] * cn.z};
+  const D3 cur = unit(rv);
+  *nrm = cur;
+  return dot(-cur, -tp);
+}
+
+__device__ bool fit_cone(const D3* p, const D3* n, const FitParams& f, rsc_cand* out) {
+  const double r[9] = {n[0].x, n[0].y, n[0].z, n[1].x, n[1].y, n[1].z, n[2].x, n[2].y, n[2].z};
+  if (!full_rank3(r, 3)) return false;
+  const double ds[3] = {dot(p[0], n[0]), dot(p[1], n[1]), dot(p[2], n[2])};
+  double rv[12];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) rv[i * 4 + j] = r[i * 3 + j];
+    rv[i * 4 + 3] = -1 * ds[i];
+  }
+  if (!full_rank3(rv, 4)) return false;
+  double ax3[3];
+  if (!solve3(r, ds, ax3)) return false;
+  const D3 ap = {ax3[0], ax3[1], ax3[2]};  // apex = intersection of the three tangent planes
+  D3 u[3];
+  for (int i = 0; i < 3; ++i) {
+    const D3 d = p[i] - ap;
+    const double nd = norm(d);
+    u[i] = ap + D3{d.x / nd, d.y / nd, d.z / nd};
+  }
+  D3 ax = unit(cross(u[1] - u[0], u[2] - u[0]));
+  const D3 sm = (u[0] + u[1]) + u[2];
+  const D3 mid = {sm.x / 3, sm.y / 3, sm.z / 3};
+  if (dot(ax, unit(mid - ap)) < 0) ax = -1.0 * ax;
+  double ang[3];
+  for (int i = 0; i < 3; ++i) {
+    double c = dot(unit(p[i] - ap), ax);
+    if (c == c) c = fmin(fmax(c, -1.0), 1.0);
+    ang[i] = acos(c);
+  }
+  const double op = 2 * (ang[0] + ang[1] + ang[2]) / 3;  // full opening angle (Q7)
+  // validatecone (cone.jl:87-115)
+  const double ct = cos(-op / 2), st = sin(-op / 2);
+  D3 nr[kMaxK];
+  for (int i = 0; i < f.k; ++i)
+    if (project2cone(ap, ax, ct, st, p[i], &nr[i]) > f.eps[RSC_CONE]) return false;  // signed (Q6)
+  if (op < f.minconeopang) return false;
+  double d[kMaxK];
+  for (int i = 0; i < f.k; ++i) d[i] = dot(nr[i], n[i]);
+  const int sd = side(d, f.k, f.cosa[RSC_CONE]);
+  if (sd == 0) return false;
+  store(out, RSC_CONE, sd > 0, ap, ax, op);
+  return true;
+}
+
+__device__ inline void fit_all(const D3* p, const D3* n, const FitParams& f, rsc_cand* dense, uint32_t* flags) {
+  for (int t = 0; t < f.ntypes; ++t) {
+    rsc_cand c;
+    bool ok = false;
+    switch (f.types[t]) {
+      case RSC_PLANE:
+        ok = fit_plane(p, n, f, &c);
+        break;
+      case RSC_SPHERE:
+        ok = fit_sphere(p, n, f, &c);
+        break;
+      case RSC_CYLINDER:
+        ok = fit_cylinder(p, n, f, &c);
+        break;
+      case RSC_CONE:
+        ok = fit_cone(p, n, f, &c);
+        break;
+    }
+    flags[t] = ok ? 1u : 0u;
+    if (ok) dense[t] = c;
+  }
+}
+
+// ---- Philox4x32-10 -------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                           uint32_t* o) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0, c1 = l1, c2 = n2, c3 = l0;
+    k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+  }
+  o[0] = c0, o[1] = c1, o[2] = c2, o[3] = c3;
+}
+
+struct SetStream {
+  uint32_t k0, k1, s0, s1, ndraw, blk[4];
+  __device__ SetStream(uint64_t seed, uint64_t set) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), s0((uint32_t)set), s1((uint32_t)(set >> 32)), ndraw(0) {}
+  __device__ uint64_t next() {
+    const uint32_t i = ndraw++;
+    if ((i & 1u) == 0) philox4x32(i >> 1, s0, s1, 0u, k0, k1, blk);
+    return (i & 1u) ? ((uint64_t)blk[2] | ((uint64_t)blk[3] << 32)) : ((uint64_t)blk[0] | ((uint64_t)blk[1] << 32));
+  }
+  __device__ uint64_t below(uint64_t n) { return __umul64hi(next(), n); }  // rand(1:n) - 1
+};
+
+constexpr int kSelWords = 32;  // words per rank/select block (1024 points)
+
+__global__ void block_popc_kernel(const uint32_t* __restrict__ en, int64_t words, uint32_t* __restrict__ out, int nblk) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  uint32_t s = 0;
+  for (int w = 0; w < kSelWords; ++w) {
+    const int64_t i = (int64_t)b * kSelWords + w;
+    if (i < words) s += __popc(en[i]);
+  }
+  out[b] = s;
+}
+
+// index of the j-th (0-based) enabled point
+__device__ inline int64_t select_enabled(const uint32_t* en, int64_t words, const unsigned long long* boff, int nblk,
+                                         uint64_t j) {
+  int lo = 0, hi = nblk - 1;  // last block whose offset <= j
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (boff[mid] <= j)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  uint32_t rem = (uint32_t)(j - boff[lo]);
+  for (int w = 0; w < kSelWords; ++w) {
+    const int64_t i = (int64_t)lo * kSelWords + w;
+    if (i >= words) break;
+    const uint32_t x = en[i];
+    const uint32_t c = __popc(x);
+    if (rem < c) return i * 32 + __fns(x, 0, rem + 1);
+    rem -= c;
+  }
+  return -1;
+}
+
+struct GatherSrc {
+  const float* soa;  // cloud SoA (6 x n_pad), used when idx != nullptr or sampling
+  int64_t n_pad;
+  const double* P;   // explicit coordinates S x k x 3 (used when soa == nullptr)
+  const double* N;
+};
+
+// mode 0: explicit coordinates; mode 1: explicit indices; mode 2: Philox sampling
+__global__ void __launch_bounds__(128) fit_kernel(int mode, GatherSrc src, const int64_t* __restrict__ idx_in, int S,
+                                                  FitParams f, uint64_t seed, uint64_t set0, int64_t n_points,
+                                                  const uint32_t* __restrict__ enabled, int64_t words,
+                                                  const unsigned long long* __restrict__ boff, int nblk,
+                                                  const unsigned long long* __restrict__ n_enabled,
+                                                  rsc_cand* __restrict__ dense, uint32_t* __restrict__ flags,
+                                                  int64_t* __restrict__ idx_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  D3 p[kMaxK], n[kMaxK];
+  uint32_t* fl = flags + (size_t)s * f.ntypes;
+  for (int t = 0; t < f.ntypes; ++t) fl[t] = 0;
+  int64_t id[kMaxK];
+  bool ok = true;
+  if (mode == 2) {
+    SetStream rng(seed, set0 + (uint64_t)s);
+    const uint64_t ne = *n_enabled;
+    int64_t r1 = (int64_t)rng.below((uint64_t)n_points);
+    if (ne == 0) {
+      ok = false;
+    } else {
+      while (!((enabled[r1 >> 5] >> (r1 & 31)) & 1u)) r1 = (int64_t)rng.below((uint64_t)n_points);
+    }
+    if (ok && ne < (uint64_t)f.k) ok = false;  // (false, 0): too few enabled points in the cell
+    if (ok) {
+      id[0] = r1;
+      for (int q = 1; q < f.k; ++q) {
+        int64_t c = select_enabled(enabled, words, boff, nblk, rng.below(ne));
+        if (c == id[0]) c = select_enabled(enabled, words, boff, nblk, rng.below(ne));  // "try once more"
+        id[q] = c;
+      }
+      for (int i = 1; i < f.k; ++i)
+        for (int j = 0; j < i; ++j)
+          if (id[i] == id[j]) ok = false;  // (false, 1): duplicate index
+    }
+    if (idx_out)
+      for (int q = 0; q < f.k; ++q) idx_out[(size_t)s * f.k + q] = ok ? id[q] : -1;
+  } else if (mode == 1) {
+    for (int q = 0; q < f.k; ++q) id[q] = idx_in[(size_t)s * f.k + q];
+  }
+  if (!ok) return;
+  if (mode == 0) {
+    for (int q = 0; q < f.k; ++q) {
+      const double* a = src.P + ((size_t)s * f.k + q) * 3;
+      const double* b = src.N + ((size_t)s * f.k + q) * 3;
+      p[q] = D3{a[0], a[1], a[2]};
+      n[q] = D3{b[0], b[1], b[2]};
+    }
+  } else {
+    for (int q = 0; q < f.k; ++q) {
+      const int64_t i = id[q];
+      p[q] = D3{(double)src.soa[i], (double)src.soa[src.n_pad + i], (double)src.soa[2 * src.n_pad + i]};
+      n[q] = D3{(double)src.soa[3 * src.n_pad + i], (double)src.soa[4 * src.n_pad + i], (double)src.soa[5 * src.n_pad + i]};
+    }
+  }
+  fit_all(p, n, f, dense + (size_t)s * f.ntypes, fl);
+}
+
+// order-preserving compaction of the dense candidates
+__global__ void compact_kernel(const rsc_cand* __restrict__ dense, const uint32_t* __restrict__ flags,
+                               const unsigned long long* __restrict__ offs, int total_slots, int ntypes,
+                               rsc_cand* __restrict__ out, int32_t* __restrict__ out_set) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_slots || !flags[i]) return;
+  const unsigned long long o = offs[i];
+  out[o] = dense[i];
+  if (out_set) out_set[o] = i / ntypes;
+}
+
+__global__ void scan_u32_kernel(const uint32_t* __restrict__ counts, int n, unsigned long long* __restrict__ offsets,
+                                unsigned long long* __restrict__ out_total);  // defined below
+
+int32_t make_fit_params(rsc_ctx* ctx, const rsc_params* p, int k, FitParams* f) {
+  if (!p) return fail(ctx, RSC_E_ARG, "params is null");
+  if (k < 3 || k > kMaxK) return fail(ctx, RSC_E_ARG, "fit: a set needs 3..8 points (At least 3 point is needed)");
+  if (p->n_shape_types < 0 || p->n_shape_types > RSC_NTYPES) return fail(ctx, RSC_E_ARG, "fit: bad n_shape_types");
+  for (int t = 0; t < RSC_NTYPES; ++t) {
+    f->eps[t] = p->eps[t];
+    f->cosa[t] = cos(p->alpha[t]);
+  }
+  f->cos_par = cos(p->parallelthrdeg * (M_PI / 180.0));
+  f->sphere_par = p->sphere_par;
+  f->minconeopang = p->minconeopang;
+  f->collin = p->collin_threshold;
+  f->ntypes = p->n_shape_types;
+  for (int t = 0; t < p->n_shape_types; ++t) {
+    if (p->shape_types[t] < 0 || p->shape_types[t] >= RSC_NTYPES) return fail(ctx, RSC_E_ARG, "fit: unknown shape type");
+    f->types[t] = p->shape_types[t];
+  }
+  f->k = k;
+  return RSC_OK;
+}
+
+// scratch layout inside ctx->fitbuf for S sets
+struct FitScratch {
+  rsc_cand* dense;
+  rsc_cand* out;
+  uint32_t* flags;
+  unsigned long long* offs;
+  unsigned long long* total;
+  int32_t* out_set;
+  int64_t* idx;
+};
+
+static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
+  const size_t slots = (size_t)S * (ntypes > 0 ? ntypes : 1);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  };
+  const size_t o_dense = take(slots * sizeof(rsc_cand)), o_out = take(slots * sizeof(rsc_cand));
+  const size_t o_flags = take(slots * 4), o_offs = take(slots * 8), o_total = take(8);
+  const size_t o_set = take(slots * 4), o_idx = take((size_t)S * k * 8);
+  RSC_CUDA(ctx, ctx->fitbuf.ensure(off));
+  char* b = ctx->fitbuf.as<char>();
+  fs->dense = (rsc_cand*)(b + o_dense);
+  fs->out = (rsc_cand*)(b + o_out);
+  fs->flags = (uint32_t*)(b + o_flags);
+  fs->offs = (unsigned long long*)(b + o_offs);
+  fs->total = (unsigned long long*)(b + o_total);
+  fs->out_set = (int32_t*)(b + o_set);
+  fs->idx = (int64_t*)(b + o_idx);
+  return RSC_OK;
+}
+
+// rank/select index over the enabled mask (rebuilt whenever it is needed; cheap)
+int32_t build_select_index(rsc_cloud* cloud, cudaStream_t st, unsigned long long** boff, int* nblk,
+                           unsigned long long** n_enabled) {
+  rsc_ctx* ctx = cloud->ctx;
+  const int64_t words = cloud->n_pad / 32;
+  const int nb = (int)((words + kSelWords - 1) / kSelWords);
+  RSC_CUDA(ctx, ctx->selbuf.ensure((size_t)nb * (4 + 8) + 64));
+  char* b = ctx->selbuf.as<char>();
+  unsigned long long* offs = (unsigned long long*)b;
+  unsigned long long* total = offs + nb;
+  uint32_t* cnt = (uint32_t*)(total + 1);
+  block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(cloud->enabled, words, cnt, nb);
+  RSC_CUDA(ctx, cudaGetLastError());
+  scan_u32_kernel<<<1, 1024, 0, st>>>(cnt, nb, offs, total);
+  RSC_CUDA(ctx, cudaGetLastError());
+  *boff = offs;
+  *nblk = nb;
+  *n_enabled = total;
+  return RSC_OK;
+}
+
+__global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restrict__ counts, int n,
+                                                        unsigned long long* __restrict__ offsets,
+                                                        unsigned long long* __restrict__ out_total) {
+  __shared__ unsigned long long wex[32];
+  __shared__ unsigned long long carry, chunk_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const unsigned long long v = i < n ? counts[i] : 0ull;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) wex[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const unsigned long long t = wex[lane];
+      unsigned long long ti = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o = __shfl_up_sync(0xffffffffu, ti, d);
+        if (lane >= d) ti += o;
+      }
+      wex[lane] = ti - t;
+      if (lane == 31) chunk_total = ti;
+    }
+    __syncthreads();
+    if (i < n) offsets[i] = carry + wex[warp] + (inc - v);
+    __syncthreads();
+    if (tid == 0) carry += chunk_total;
+    __syncthreads();
+  }
+  if (tid == 0) *out_total = carry;
+}
+
+// Enqueue fit (+ sampling) for S sets; leaves compacted candidates in ctx->fitbuf (FitScratch.out),
+// their count in FitScratch.total.  No synchronisation.
+int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
+                    const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
+                    FitScratch* fs) {
+  FitParams f;
+  int32_t rc = make_fit_params(ctx, params, k, &f);
+  if (rc) return rc;
+  if ((rc = carve(ctx, S, f.ntypes, k, fs))) return rc;
+  const int slots = S * f.ntypes;
+  GatherSrc src{nullptr, 0, dP, dN};
+  unsigned long long *boff = nullptr, *nen = nullptr;
+  int nblk = 0;
+  if (mode != 0) {
+    src.soa = cloud->soa;
+    src.n_pad = cloud->n_pad;
+  }
+  if (mode == 2 && (rc = build_select_index(cloud, st, &boff, &nblk, &nen))) return rc;
+  if (slots > 0) {
+    fit_kernel<<<(S + 127) / 128, 128, 0, st>>>(mode, src, d_idx, S, f, seed, set0, cloud ? cloud->n : 0,
+                                                cloud ? cloud->enabled : nullptr, cloud ? cloud->n_pad / 32 : 0, boff,
+                                                nblk, nen, fs->dense, fs->flags, mode == 2 ? fs->idx : nullptr);
+    RSC_CUDA(ctx, cudaGetLastError());
+    scan_u32_kernel<<<1, 1024, 0, st>>>(fs->flags, slots, fs->offs, fs->total);
+    RSC_CUDA(ctx, cudaGetLastError());
+    compact_kernel<<<(slots + 255) / 256, 256, 0, st>>>(fs->dense, fs->flags, fs->offs, slots, f.ntypes, fs->out, fs->out_set);
+    RSC_CUDA(ctx, cudaGetLastError());
+  } else {
+    RSC_CUDA(ctx, cudaMemsetAsync(fs->total, 0, 8, st));
+  }
+  ctx->stats.sets_drawn += S;
+  return RSC_OK;
+}
+
+static int32_t fit_finish(rsc_ctx* ctx, const FitScratch& fs, int S, int k, cudaStream_t st, rsc_cand* out,
+                          int32_t* out_set, int64_t* out_idx, int32_t* out_n) {
+  unsigned long long total = 0;
+  RSC_CUDA(ctx, cudaMemcpyAsync(&total, fs.total, 8, cudaMemcpyDeviceToHost, st));
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  *out_n = (int32_t)total;
+  if (total) {
+    if (out) RSC_CUDA(ctx, cudaMemcpyAsync(out, fs.out, (size_t)total * sizeof(rsc_cand), cudaMemcpyDeviceToHost, st));
+    if (out_set) RSC_CUDA(ctx, cudaMemcpyAsync(out_set, fs.out_set, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (out_idx) RSC_CUDA(ctx, cudaMemcpyAsync(out_idx, fs.idx, (size_t)S * k * 8, cudaMemcpyDeviceToHost, st));
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  return RSC_OK;
+}
+
+}  // namespace rsc
+
 using namespace rsc;
+
 extern "C" {
-int32_t rsc_fit_batch(rsc_cloud* cloud, const rsc_params*, const int64_t*, int32_t, rsc_cand*, int32_t*, int32_t*) {
-  return cloud ? fail(cloud->ctx, RSC_E_STATE, "rsc_fit_batch: not built yet") : RSC_E_ARG;
+
+int32_t rsc_fit_points(rsc_ctx* ctx, const rsc_params* params, const double* p, const double* n, int32_t S, int32_t k,
+                       rsc_cand* out, int32_t* out_set, int32_t* out_n) {
+  if (!ctx) return RSC_E_ARG;
+  if (!out_n || S < 0 || (S > 0 && (!p || !n || !out))) return fail(ctx, RSC_E_ARG, "fit_points: null arguments");
+  *out_n = 0;
+  if (S == 0) return RSC_OK;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const size_t bytes = (size_t)S * k * 3 * sizeof(double);
+  RSC_CUDA(ctx, ctx->misc.ensure(bytes));
+  RSC_CUDA(ctx, ctx->misc2.ensure(bytes));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, p, bytes, cudaMemcpyHostToDevice, st));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc2.p, n, bytes, cudaMemcpyHostToDevice, st));
+  FitScratch fs;
+  int32_t rc = fit_enqueue(ctx, nullptr, 0, params, k, ctx->misc.as<double>(), ctx->misc2.as<double>(), nullptr, S, 0, 0, st, &fs);
+  if (rc) return rc;
+  return fit_finish(ctx, fs, S, k, st, out, out_set, nullptr, out_n);
 }
-int32_t rsc_fit_points(rsc_ctx* ctx, const rsc_params*, const double*, const double*, int32_t, int32_t, rsc_cand*,
-                       int32_t*, int32_t*) {
-  return fail(ctx, RSC_E_STATE, "rsc_fit_points: not built yet");
+
+int32_t rsc_fit_batch(rsc_cloud* cloud, const rsc_params* params, const int64_t* idx, int32_t S, rsc_cand* out,
+                      int32_t* out_set, int32_t* out_n) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (!params || !out_n || S < 0 || (S > 0 && (!idx || !out))) return fail(ctx, RSC_E_ARG, "fit_batch: null arguments");
+  *out_n = 0;
+  if (S == 0) return RSC_OK;
+  const int k = params->drawN;
+  if (k < 3 || k > kMaxK) return fail(ctx, RSC_E_ARG, "fit_batch: drawN must be 3..8");
+  for (int64_t i = 0; i < (int64_t)S * k; ++i)
+    if (idx[i] < 0 || idx[i] >= cloud->n) return fail(ctx, RSC_E_ARG, "fit_batch: index out of range");
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  RSC_CUDA(ctx, ctx->misc.ensure((size_t)S * k * 8));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, idx, (size_t)S * k * 8, cudaMemcpyHostToDevice, st));
+  FitScratch fs;
+  int32_t rc = fit_enqueue(ctx, cloud, 1, params, k, nullptr, nullptr, ctx->misc.as<int64_t>(), S, 0, 0, st, &fs);
+  if (rc) return rc;
+  return fit_finish(ctx, fs, S, k, st, out, out_set, nullptr, out_n);
 }
-int32_t rsc_sample_fit(rsc_cloud* cloud, const rsc_params*, uint64_t, uint64_t, int32_t, rsc_cand*, int32_t*, int64_t*,
-                       int32_t*) {
-  return cloud ? fail(cloud->ctx, RSC_E_STATE, "rsc_sample_fit: not built yet") : RSC_E_ARG;
+
+int32_t rsc_sample_fit(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, uint64_t set0, int32_t S,
+                       rsc_cand* out, int32_t* out_set, int64_t* out_idx, int32_t* out_n) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (!params || !out_n || S < 0 || (S > 0 && !out)) return fail(ctx, RSC_E_ARG, "sample_fit: null arguments");
+  *out_n = 0;
+  if (S == 0) return RSC_OK;
+  const int k = params->drawN;
+  if (k < 3 || k > kMaxK) return fail(ctx, RSC_E_ARG, "sample_fit: drawN must be 3..8");
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  FitScratch fs;
+  int32_t rc = fit_enqueue(ctx, cloud, 2, params, k, nullptr, nullptr, nullptr, S, seed, set0, st, &fs);
+  if (rc) return rc;
+  return fit_finish(ctx, fs, S, k, st, out, out_set, out_idx, out_n);
 }
-}
+
+}  // extern "C"

@@ -14,6 +14,7 @@
 //   * per evaluation the kernel also tracks min|margin|; only if that falls inside the FP32 guard
 //     band is the 32-point group re-examined and the ambiguous pairs queued for FP64 (fixup_kernel).
 #include <math.h>
+#include <stdlib.h>
 
 #include "rsc_eval.cuh"
 #include "rsc_exact.cuh"
@@ -211,8 +212,8 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
   }
 }
 
-template <int K>
-__global__ void __launch_bounds__(kThreads) score_kernel(const __grid_constant__ ScoreArgs a) {
+template <int K, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) score_kernel(const __grid_constant__ ScoreArgs a) {
   __shared__ __align__(128) float stages[kThreads / 32][kStages * kSubFloats];
   __shared__ __align__(8) uint64_t bars[kThreads / 32][kStages];
   const BlockTab bt = a.tab[blockIdx.x];
@@ -528,7 +529,9 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
 
   // grid: columns x point chunks; aim at >= 8 waves of 4 CTAs/SM so the tail stays small
   const int real_cols = (C + spc - 1) / spc;
-  const long target = (long)ctx->sm_count * 4 * 8;
+  static const int waves = getenv("RSC_WAVES") ? atoi(getenv("RSC_WAVES")) : 8;
+  static const int minb = getenv("RSC_MINB") ? atoi(getenv("RSC_MINB")) : 4;
+  const long target = (long)ctx->sm_count * 4 * waves;
   long chunks = (target + real_cols - 1) / real_cols;
   if (chunks > nsubs) chunks = nsubs;
   if (chunks < 1) chunks = 1;
@@ -540,13 +543,18 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
   switch (K) {
     case 4:
-      score_kernel<4><<<grid, kThreads, 0, st>>>(a);
+      if (minb == 5)
+        score_kernel<4, 5><<<grid, kThreads, 0, st>>>(a);
+      else if (minb == 6)
+        score_kernel<4, 6><<<grid, kThreads, 0, st>>>(a);
+      else
+        score_kernel<4, 4><<<grid, kThreads, 0, st>>>(a);
       break;
     case 2:
-      score_kernel<2><<<grid, kThreads, 0, st>>>(a);
+      score_kernel<2, 4><<<grid, kThreads, 0, st>>>(a);
       break;
     default:
-      score_kernel<1><<<grid, kThreads, 0, st>>>(a);
+      score_kernel<1, 4><<<grid, kThreads, 0, st>>>(a);
       break;
   }
   RSC_CUDA(ctx, cudaGetLastError());
