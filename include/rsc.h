@@ -180,6 +180,15 @@ int32_t rsc_sample_fit(rsc_cloud* cloud, const rsc_params* params, uint64_t seed
 int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand,
                           int64_t* out_idx, int64_t* out_n, int32_t disable);
 
+/* ---- point-range sharding over the GPUs of one box (one process per GPU) ---------------------- */
+/* Every rank holds the whole cloud (sampling needs random access) but scores/refits only its range
+ * [lo, hi) -- multiples of 2048 points, hi may also be the cloud size.  The per-candidate counts and
+ * the refit's inlier-mask words are summed over the ranks by `fn` (the host enqueues an NCCL
+ * all-reduce(sum, int32) of `count` elements at d_buf on `stream`; non-zero return = failure). */
+typedef int32_t (*rsc_allreduce_fn)(void* user, void* d_buf, int64_t count, void* stream);
+int32_t rsc_ctx_set_allreduce(rsc_ctx* ctx, rsc_allreduce_fn fn, void* user);
+int32_t rsc_cloud_set_range(rsc_cloud* cloud, int64_t lo, int64_t hi);
+
 /* ---- the whole loop: ransac(pc, params; ...) iterations.jl:35-162 for built-in shapes ------- */
 int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, rsc_run** out);
 int32_t rsc_run_nshapes(const rsc_run* run);

@@ -87,6 +87,8 @@ SIGNATURES = {
     "rsc_fit_points": (C.c_int32, [_P, C.POINTER(rsc_params), _P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
     "rsc_sample_fit": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.c_uint64, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)]),
     "rsc_refit_extract": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), _P, C.POINTER(C.c_int64), C.c_int32]),
+    "rsc_ctx_set_allreduce": (C.c_int32, [_P, _P, _P]),
+    "rsc_cloud_set_range": (C.c_int32, [_P, C.c_int64, C.c_int64]),
     "rsc_ransac_run": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.POINTER(_P)]),
     "rsc_run_nshapes": (C.c_int32, [_P]),
     "rsc_run_iterations": (C.c_int32, [_P]),
@@ -107,6 +109,9 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f = getattr(lib, _name)  # AttributeError here = header/library mismatch
     _f.restype = _res
     _f.argtypes = _args
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 class RscError(RuntimeError):

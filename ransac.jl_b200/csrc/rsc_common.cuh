@@ -84,7 +84,9 @@ struct rsc_ctx {
   // scratch of the score path
   rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, pairs, wl_count, aux;
   rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf;
-  size_t wl_cap = 1u << 22;  // AmbPair capacity, grows on overflow
+  size_t wl_cap = 1u << 22;  // guard-band queue capacity (groups / pairs), grows on overflow
+  rsc_allreduce_fn allreduce = nullptr;  // sums int32 device buffers across the ranks of a sharded run
+  void* allreduce_user = nullptr;
   void* pinned = nullptr;    // small pinned staging area
   size_t pinned_cap = 0;
 };
@@ -101,6 +103,7 @@ struct rsc_cloud {
   rsc_ctx* ctx = nullptr;
   int64_t n = 0, n_pad = 0;
   int64_t global_offset = 0, n_global = 0;
+  int64_t range_lo = 0, range_hi = 0;  // this rank's point range of a replicated cloud (0,0: all)
   float* soa = nullptr;        // 6 * n_pad floats: x | y | z | nx | ny | nz
   uint32_t* enabled = nullptr; // n_pad/32 words
   uint32_t* valid = nullptr;

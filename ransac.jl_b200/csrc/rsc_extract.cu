@@ -21,12 +21,11 @@ struct ExtractArgs {
   ex::ConeTrig trig;
   float pmax, nmax;
   uint32_t* inl;           // [n_pad/32]
-  uint32_t* block_counts;  // [nblocks]
+  int64_t block0;          // first CTA-sized block of this rank's point range
 };
 
 __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_constant__ ExtractArgs a) {
   __shared__ float r[kRecFields];
-  __shared__ int wsum[kExThreads / 32];
   if (threadIdx.x == 0) {
     float t[kRecFields];
     compile_record(a.cand, a.pmax, a.nmax, t);
@@ -39,8 +38,7 @@ __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_c
   float rr[kRecFields];
 #pragma unroll
   for (int f = 0; f < kRecFields; ++f) rr[f] = r[f];
-  int cnt = 0;
-  const int64_t base = (int64_t)blockIdx.x * kExPts;
+  const int64_t base = (a.block0 + blockIdx.x) * kExPts;
 #pragma unroll 2
   for (int it = 0; it < kExPts / kExThreads; ++it) {
     const int64_t p = base + it * kExThreads + threadIdx.x;
@@ -57,18 +55,20 @@ __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_c
                         ex::V3{(double)nx, (double)ny, (double)nz});
     }
     const unsigned w = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0) {
-      a.inl[p >> 5] = w;
-      cnt += __popc(w);
-    }
+    if ((threadIdx.x & 31) == 0) a.inl[p >> 5] = w;
   }
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int s = 0;
-    for (int i = 0; i < kExThreads / 32; ++i) s += wsum[i];
-    a.block_counts[blockIdx.x] = s;
+}
+
+// inliers per CTA-sized block of the (all-reduced) inlier mask
+__global__ void block_count_kernel(const uint32_t* __restrict__ inl, int64_t words, uint32_t* __restrict__ counts, int nblocks) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  uint32_t s = 0;
+  for (int w = 0; w < kExPts / 32; ++w) {
+    const int64_t i = (int64_t)b * (kExPts / 32) + w;
+    if (i < words) s += __popc(inl[i]);
   }
+  counts[b] = s;
 }
 
 // exclusive scan of `n` counts by one CTA; total -> out_total[0]
@@ -149,12 +149,15 @@ __global__ void __launch_bounds__(kExThreads) extract_write_kernel(const uint32_
   }
 }
 
-// Enqueue steps 1+2; the caller reads the total (ctx->misc2[0]) and then calls extract_write.
+// Enqueue steps 1+2; the caller reads the total (ctx->misc2[0]) and then calls refit_write_enqueue.
+// Sharded: only this rank's point range is evaluated and the inlier-mask words are summed across
+// ranks (disjoint ranges, so the sum is the union), after which every rank holds the full mask.
 int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st) {
   rsc_ctx* ctx = cloud->ctx;
   const int64_t n_pad = cloud->n_pad;
+  const int64_t words = n_pad / 32;
   const int nblocks = (int)((n_pad + kExPts - 1) / kExPts);
-  RSC_CUDA(ctx, ctx->idxbuf.ensure((size_t)(n_pad / 32) * 4 + (size_t)nblocks * (4 + 8) + 64));
+  RSC_CUDA(ctx, ctx->idxbuf.ensure((size_t)words * 4 + (size_t)nblocks * (4 + 8) + 64));
   ExtractArgs a;
   a.ps = view_cloud(cloud);
   a.th = th;
@@ -165,14 +168,28 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
   a.nmax = cloud->nmax;
   char* b = ctx->idxbuf.as<char>();
   a.inl = reinterpret_cast<uint32_t*>(b);
-  unsigned long long* offsets = reinterpret_cast<unsigned long long*>(b + ((size_t)(n_pad / 32) * 4 + 15) / 16 * 16);
-  a.block_counts = reinterpret_cast<uint32_t*>(offsets + nblocks);
+  unsigned long long* offsets = reinterpret_cast<unsigned long long*>(b + ((size_t)words * 4 + 15) / 16 * 16);
+  uint32_t* block_counts = reinterpret_cast<uint32_t*>(offsets + nblocks);
   RSC_CUDA(ctx, ctx->misc2.ensure(64));
-  extract_mask_kernel<<<nblocks, kExThreads, 0, st>>>(a);
+  const bool sharded = ctx->allreduce && cloud->range_hi > cloud->range_lo;
+  int64_t b0 = 0, b1 = nblocks;
+  if (sharded) {
+    b0 = cloud->range_lo / kExPts;
+    b1 = (cloud->range_hi + kExPts - 1) / kExPts;
+    if (cloud->range_lo % kExPts || (cloud->range_hi % kExPts && cloud->range_hi != n_pad))
+      return fail(ctx, RSC_E_ARG, "refit: a shard range must be aligned to 2048 points");
+    RSC_CUDA(ctx, cudaMemsetAsync(a.inl, 0, (size_t)words * 4, st));
+  }
+  a.block0 = b0;
+  extract_mask_kernel<<<(unsigned)(b1 - b0), kExThreads, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
-  scan_counts_kernel<<<1, 1024, 0, st>>>(a.block_counts, nblocks, offsets, ctx->misc2.as<unsigned long long>());
+  if (sharded && ctx->allreduce(ctx->allreduce_user, a.inl, words, (void*)st))
+    return fail(ctx, RSC_E_NCCL, "refit: all-reduce callback failed");
+  block_count_kernel<<<(nblocks + 255) / 256, 256, 0, st>>>(a.inl, words, block_counts, nblocks);
   RSC_CUDA(ctx, cudaGetLastError());
-  ctx->stats.evals += cloud->n;
+  scan_counts_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, offsets, ctx->misc2.as<unsigned long long>());
+  RSC_CUDA(ctx, cudaGetLastError());
+  ctx->stats.evals += (b1 - b0) * kExPts < cloud->n ? (b1 - b0) * kExPts : cloud->n;
   return RSC_OK;
 }
 

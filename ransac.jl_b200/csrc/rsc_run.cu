@@ -1,17 +1,441 @@
-// rsc_run.cu -- the whole ransac loop (placeholder until the loop lands in this file)
+// rsc_run.cu -- the whole RANSAC loop for the built-in shapes behind one C-ABI call
+// (ransac(pc, params; ...): iterations.jl:35-162), plus K3 (score bookkeeping: findhighestscore,
+// fitting.jl:140-158) and K5 (removeinvalidshapes!, fitting.jl:209-221) on the device.
+//
+// Per iteration: K1 sample+fit (rsc_fit.cu) -> K2 score of the new candidates on subset 1
+// (rsc_score.cu; iterations.jl:95 hard-wires subset 1) -> device arg-max over the candidate store
+// -> host decides with prob() (utilities.jl:262) -> on extraction K4 refit over the whole cloud
+// (rsc_extract.cu), enabled bits cleared, store invalidated and compacted.
+//
+// K5 without stored inlier lists: every stored candidate's subset-1 inliers are enabled at the time
+// of an extraction (the reference removes any candidate with a disabled inlier at each extraction,
+// and new candidates only count enabled points), so "has a now-disabled inlier" == "is compatible
+// with one of the NEWLY disabled subset-1 points".  Those few points are gathered into a scratch
+// point set and all stored candidates are scored against it with the same K2 kernel.  Spheres,
+// whose reference scorer ignores `isenabled` (Q4), additionally die at the first extraction after
+// they were scored if they matched any already-disabled point.
+//
+// Sharding (one process per GPU): the cloud is replicated, every rank samples identically
+// (counter-based Philox) and scores only its point range; per-candidate counts and the refit's
+// inlier-mask words are summed across ranks through the all-reduce callback (NCCL on the host side).
+#include <math.h>
+#include <string.h>
+
+#include <chrono>
+#include <vector>
+
 #include "rsc_common.cuh"
-using namespace rsc;
-struct rsc_run {
-  int dummy;
+
+namespace rsc {
+
+// from rsc_fit.cu
+struct FitScratch {
+  rsc_cand* dense;
+  rsc_cand* out;
+  uint32_t* flags;
+  unsigned long long* offs;
+  unsigned long long* total;
+  int32_t* out_set;
+  int64_t* idx;
 };
+int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
+                    const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
+                    FitScratch* fs);
+__global__ void scan_u32_kernel(const uint32_t* __restrict__ counts, int n, unsigned long long* __restrict__ offsets,
+                                unsigned long long* __restrict__ out_total);
+
+// ---- K3: scores of the freshly scored candidates, arg-max over the store -------------------------
+// score = policy count; tainted = sphere whose count includes a disabled point (Q4)
+__global__ void finish_new_kernel(const rsc_cand* __restrict__ cands, int n, const int32_t* __restrict__ cv,
+                                  const int32_t* __restrict__ ce, uint32_t honour_enabled, int32_t* __restrict__ score,
+                                  uint8_t* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = cands[i].type;
+  const bool honour = (honour_enabled >> t) & 1u;
+  score[i] = honour ? ce[i] : cv[i];
+  flags[i] = (uint8_t)(1u | ((!honour && cv[i] != ce[i]) ? 2u : 0u));  // bit0 alive, bit1 tainted
+}
+
+// first index of the maximum score among alive candidates (ties: first wins, Q16)
+__global__ void __launch_bounds__(1024) argmax_kernel(const int32_t* __restrict__ score, const uint8_t* __restrict__ flags,
+                                                      int n, int64_t* __restrict__ out /*[2]: index, score*/) {
+  __shared__ long long best[32];
+  long long b = -1;  // key = score << 32 | (0x7fffffff - index): larger key = better
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (flags[i] & 1u) {
+      const long long key = ((long long)score[i] << 32) | (long long)(0x7fffffff - i);
+      b = key > b ? key : b;
+    }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const long long o = __shfl_xor_sync(0xffffffffu, b, d);
+    b = o > b ? o : b;
+  }
+  if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    b = best[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      const long long o = __shfl_xor_sync(0xffffffffu, b, d);
+      b = o > b ? o : b;
+    }
+    if (threadIdx.x == 0) {
+      if (b < 0) {
+        out[0] = -1, out[1] = 0;
+      } else {
+        out[0] = 0x7fffffff - (int)(b & 0xffffffffll);
+        out[1] = (int)(b >> 32);
+      }
+    }
+  }
+}
+
+// ---- K5 helpers -----------------------------------------------------------------------------------
+// per word of the subset mask: how many bits were cleared by the extraction
+__global__ void newly_count_kernel(const uint32_t* __restrict__ old_en, const uint32_t* __restrict__ new_en, int64_t words,
+                                   uint32_t* __restrict__ cnt) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < words) cnt[w] = __popc(old_en[w] & ~new_en[w]);
+}
+
+// gather the newly disabled subset points into a compact SoA scratch set
+__global__ void newly_gather_kernel(const uint32_t* __restrict__ old_en, const uint32_t* __restrict__ new_en, int64_t words,
+                                    const unsigned long long* __restrict__ offs, const float* __restrict__ soa, int64_t m_pad,
+                                    float* __restrict__ out, int64_t out_pad) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  uint32_t bits = old_en[w] & ~new_en[w];
+  unsigned long long o = offs[w];
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int64_t j = w * 32 + b;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) out[f * out_pad + o] = soa[f * m_pad + j];
+    ++o;
+  }
+}
+
+__global__ void fill_valid_words_kernel(uint32_t* __restrict__ valid, int64_t n, int64_t words) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  const int64_t lo = w * 32;
+  valid[w] = lo + 32 <= n ? 0xffffffffu : (lo < n ? (1u << (n - lo)) - 1u : 0u);
+}
+
+// alive &= no newly disabled compatible point; tainted spheres die; keep[] = alive as 0/1 words
+__global__ void invalidate_kernel(const int32_t* __restrict__ hit, uint8_t* __restrict__ flags, int n, int best,
+                                  uint32_t* __restrict__ keep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t f = flags[i];
+  if (i == best || hit[i] > 0 || (f & 2u)) f = 0;
+  flags[i] = f;
+  keep[i] = f & 1u;
+}
+
+__global__ void compact_store_kernel(const rsc_cand* __restrict__ c0, const int32_t* __restrict__ s0,
+                                     const uint8_t* __restrict__ f0, const uint32_t* __restrict__ keep,
+                                     const unsigned long long* __restrict__ offs, int n, rsc_cand* __restrict__ c1,
+                                     int32_t* __restrict__ s1, uint8_t* __restrict__ f1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep[i]) return;
+  const unsigned long long o = offs[i];
+  c1[o] = c0[i];
+  s1[o] = s0[i];
+  f1[o] = f0[i];
+}
+
+// the candidate store (device), ping-pong buffers for order-preserving compaction
+struct Store {
+  DevBuf cands[2], score[2], flags[2];
+  int cur = 0;
+  int n = 0;
+  size_t cap = 0;
+  cudaError_t reserve(size_t want, cudaStream_t st) {
+    if (want <= cap) return cudaSuccess;
+    size_t ncap = cap ? cap : 4096;
+    while (ncap < want) ncap *= 2;
+    for (int b = 0; b < 2; ++b) {
+      DevBuf nc, ns, nf;
+      cudaError_t e;
+      if ((e = nc.ensure(ncap * sizeof(rsc_cand))) != cudaSuccess) return e;
+      if ((e = ns.ensure(ncap * 4)) != cudaSuccess) return e;
+      if ((e = nf.ensure(ncap)) != cudaSuccess) return e;
+      if (b == cur && n) {
+        cudaMemcpyAsync(nc.p, cands[b].p, (size_t)n * sizeof(rsc_cand), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(ns.p, score[b].p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(nf.p, flags[b].p, (size_t)n, cudaMemcpyDeviceToDevice, st);
+        cudaStreamSynchronize(st);
+      }
+      cands[b].release(), score[b].release(), flags[b].release();
+      cands[b] = nc, score[b] = ns, flags[b] = nf;
+    }
+    cap = ncap;
+    return cudaSuccess;
+  }
+  void release() {
+    for (int b = 0; b < 2; ++b) cands[b].release(), score[b].release(), flags[b].release();
+  }
+};
+
+static double prob_(double n, double s, double N, double k) { return 1 - pow(1 - pow(n / N, k), s); }
+
+}  // namespace rsc
+
+using namespace rsc;
+
+struct rsc_run {
+  std::vector<rsc_cand> shapes;
+  std::vector<std::vector<int64_t>> inpoints;
+  int iterations = 0;
+  double seconds = 0.0;
+};
+
 extern "C" {
-int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params*, uint64_t, rsc_run**) {
-  return cloud ? fail(cloud->ctx, RSC_E_STATE, "rsc_ransac_run: not built yet") : RSC_E_ARG;
+
+int32_t rsc_ctx_set_allreduce(rsc_ctx* ctx, rsc_allreduce_fn fn, void* user) {
+  if (!ctx) return RSC_E_ARG;
+  ctx->allreduce = fn;
+  ctx->allreduce_user = user;
+  return RSC_OK;
 }
-int32_t rsc_run_nshapes(const rsc_run*) { return 0; }
-int32_t rsc_run_iterations(const rsc_run*) { return 0; }
-double rsc_run_seconds(const rsc_run*) { return 0.0; }
-int32_t rsc_run_shape(const rsc_run*, int32_t, rsc_cand*, int64_t*) { return RSC_E_STATE; }
-int32_t rsc_run_inpoints(const rsc_run*, int32_t, int64_t*) { return RSC_E_STATE; }
+
+int32_t rsc_cloud_set_range(rsc_cloud* cloud, int64_t lo, int64_t hi) {
+  if (!cloud) return RSC_E_ARG;
+  if (lo < 0 || hi > cloud->n_pad || lo >= hi || lo % kTile || (hi % kTile && hi != cloud->n_pad && hi != cloud->n))
+    return fail(cloud->ctx, RSC_E_ARG, "set_range: range must be non-empty and aligned to 512 points");
+  cloud->range_lo = lo;
+  cloud->range_hi = hi >= cloud->n ? cloud->n_pad : hi;
+  return RSC_OK;
+}
+
+int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc_run** out) {
+  if (!cloud || !out) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  *out = nullptr;
+  if (!p) return fail(ctx, RSC_E_ARG, "ransac_run: params is null");
+  if (p->drawN < 3 || p->drawN > 8) return fail(ctx, RSC_E_ARG, "ransac_run: drawN must be 3..8");
+  if (p->minsubsetN < 1 || p->n_shape_types < 1) return fail(ctx, RSC_E_ARG, "ransac_run: nothing to sample/fit");
+  if (p->extract_s < 0 || p->extract_s > 2 || p->terminate_s < 0 || p->terminate_s > 2)
+    return fail(ctx, RSC_E_ARG, "ransac_run: extract_s/terminate_s must be RSC_S_*");
+  if (cloud->subsets.empty() || !cloud->subsets[0].soa)
+    return fail(ctx, RSC_E_STATE, "ransac_run: subset 1 is not uploaded (rsc_cloud_set_subset(cloud, 0, ...))");
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const auto t0 = std::chrono::steady_clock::now();
+  rsc_run* run = new rsc_run();
+  Store store;
+  int32_t rc = RSC_OK;
+  const Thresh th = make_thresh(p);
+  rsc_subset& sub = cloud->subsets[0];
+  const int64_t N = cloud->n_global > 0 ? cloud->n_global : cloud->n;
+  const int S = p->minsubsetN;
+  const int maxnew = S * p->n_shape_types;
+  const bool sharded = ctx->allreduce != nullptr;
+  // this rank's slice of the subset copy (the whole of it when not sharded)
+  int64_t slo = 0, shi = sub.m_pad;
+  if (sharded && cloud->range_hi > cloud->range_lo && cloud->n_pad > 0) {
+    slo = (int64_t)((double)cloud->range_lo / cloud->n_pad * sub.m_pad) / kTile * kTile;
+    shi = cloud->range_hi >= cloud->n_pad ? sub.m_pad : (int64_t)((double)cloud->range_hi / cloud->n_pad * sub.m_pad) / kTile * kTile;
+  }
+  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta;
+  int64_t n_enabled = rsc_cloud_count_enabled(cloud);
+  int64_t counters[3] = {0, 0, 0};  // lengthC, allcand, nofminset (iterations.jl:70)
+  auto cleanup = [&]() {
+    store.release();
+    newcnt.release(), hostio.release(), olden.release(), nscratch.release(), nvalid.release(), nmeta.release();
+  };
+#define RUN_CUDA(expr)                                  \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) {                            \
+      rc = fail_cuda(ctx, _e, #expr);                   \
+      goto done;                                        \
+    }                                                   \
+  } while (0)
+
+  RUN_CUDA(newcnt.ensure((size_t)2 * maxnew * 4 + 64));
+  RUN_CUDA(hostio.ensure(64));
+
+  for (int k = 1; k <= p->itermax; ++k) {
+    if (n_enabled < p->tau) break;  // iterations.jl:75
+    run->iterations = k;
+    // ---- K1: minsubsetN minimal sets -> candidates (device, compacted in reference order) ----
+    FitScratch fs;
+    if ((rc = fit_enqueue(ctx, cloud, 2, p, p->drawN, nullptr, nullptr, nullptr, S, seed, (uint64_t)(k - 1) * S, st, &fs)))
+      goto done;
+    unsigned long long n_new_ = 0;
+    RUN_CUDA(cudaMemcpyAsync(&n_new_, fs.total, 8, cudaMemcpyDeviceToHost, st));
+    RUN_CUDA(cudaStreamSynchronize(st));
+    const int n_new = (int)n_new_;
+    counters[1] += n_new;
+    if (n_new > 0) {
+      RUN_CUDA(store.reserve((size_t)store.n + n_new, st));
+      rsc_cand* dst = store.cands[store.cur].as<rsc_cand>() + store.n;
+      RUN_CUDA(cudaMemcpyAsync(dst, fs.out, (size_t)n_new * sizeof(rsc_cand), cudaMemcpyDeviceToDevice, st));
+      // ---- K2 on subset 1 ----
+      int32_t* cv = newcnt.as<int32_t>();
+      int32_t* ce = cv + n_new;
+      PointSet ps = view_subset(&sub);
+      if (sharded) {
+        ps.x += slo, ps.y += slo, ps.z += slo, ps.nx += slo, ps.ny += slo, ps.nz += slo;
+        ps.enabled += slo / 32, ps.valid += slo / 32;
+        ps.n_pad = shi - slo;
+        ps.n = (sub.m < shi ? sub.m : shi) - slo;
+      }
+      if ((rc = score_enqueue(ctx, cloud, ps, th, dst, n_new, nullptr, false, st, cv, ce))) goto done;
+      if (sharded && (rc = ctx->allreduce(ctx->allreduce_user, cv, (int64_t)2 * n_new, (void*)st))) {
+        rc = fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce callback failed");
+        goto done;
+      }
+      finish_new_kernel<<<(n_new + 255) / 256, 256, 0, st>>>(dst, n_new, cv, ce, th.honour_enabled,
+                                                             store.score[store.cur].as<int32_t>() + store.n,
+                                                             store.flags[store.cur].as<uint8_t>() + store.n);
+      RUN_CUDA(cudaGetLastError());
+      store.n += n_new;
+    }
+    counters[2] = (int64_t)k * S;
+    counters[0] = store.n;
+    if (store.n >= 1) {
+      // ---- K3: best candidate ----
+      int64_t best[2] = {-1, 0};
+      argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store.n,
+                                        hostio.as<int64_t>());
+      RUN_CUDA(cudaGetLastError());
+      RUN_CUDA(cudaMemcpyAsync(best, hostio.p, 16, cudaMemcpyDeviceToHost, st));
+      RUN_CUDA(cudaStreamSynchronize(st));
+      if (best[0] >= 0) {
+        double E;
+        rsc_estimate_score(sub.m, N, best[1], nullptr, nullptr, &E);
+        const double s_ex = (double)counters[p->extract_s];
+        if (prob_(E, s_ex, (double)N, (double)p->drawN) > p->prob_det) {
+          // ---- K4: refit over the whole cloud, invalidate its points ----
+          rsc_cand shape;
+          RUN_CUDA(cudaMemcpyAsync(&shape, store.cands[store.cur].as<rsc_cand>() + best[0], sizeof(shape),
+                                   cudaMemcpyDeviceToHost, st));
+          RUN_CUDA(cudaStreamSynchronize(st));
+          Thresh thr = th;
+          thr.honour_enabled = 0xFu;
+          if ((rc = refit_mask_enqueue(cloud, thr, shape, st))) goto done;
+          unsigned long long total = 0;
+          RUN_CUDA(cudaMemcpyAsync(&total, ctx->misc2.p, 8, cudaMemcpyDeviceToHost, st));
+          RUN_CUDA(cudaStreamSynchronize(st));
+          // keep the subset's enabled words of before the extraction
+          const int64_t swords = sub.m_pad / 32;
+          RUN_CUDA(olden.ensure((size_t)swords * 4));
+          RUN_CUDA(cudaMemcpyAsync(olden.p, sub.enabled, (size_t)swords * 4, cudaMemcpyDeviceToDevice, st));
+          std::vector<int64_t> idx((size_t)total);
+          int64_t* d_out = nullptr;
+          if (total) {
+            RUN_CUDA(ctx->misc.ensure((size_t)total * 8));
+            d_out = ctx->misc.as<int64_t>();
+          }
+          if ((rc = refit_write_enqueue(cloud, d_out, true, st))) goto done;
+          if (total) RUN_CUDA(cudaMemcpyAsync(idx.data(), d_out, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+          RUN_CUDA(cudaStreamSynchronize(st));
+          run->shapes.push_back(shape);
+          run->inpoints.push_back(std::move(idx));
+          n_enabled -= (int64_t)total;
+          // ---- K5: drop the best and every candidate compatible with a newly disabled subset point ----
+          const int nst = store.n;
+          // scratch layout: [wcnt: swords u32][woff: swords u64][wtot u64][keep: nst u32][koff: nst u64][ktot u64]
+          const size_t o_woff = ((size_t)swords * 4 + 255) / 256 * 256;
+          const size_t o_keep = o_woff + (size_t)(swords + 1) * 8;
+          const size_t o_koff = (o_keep + (size_t)nst * 4 + 255) / 256 * 256;
+          RUN_CUDA(nmeta.ensure(o_koff + (size_t)(nst + 1) * 8));
+          uint32_t* wcnt = nmeta.as<uint32_t>();
+          unsigned long long* woff = (unsigned long long*)(nmeta.as<char>() + o_woff);
+          unsigned long long* wtot = woff + swords;
+          uint32_t* keep = (uint32_t*)(nmeta.as<char>() + o_keep);
+          unsigned long long* koff = (unsigned long long*)(nmeta.as<char>() + o_koff);
+          newly_count_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(olden.as<uint32_t>(), sub.enabled, swords, wcnt);
+          RUN_CUDA(cudaGetLastError());
+          scan_u32_kernel<<<1, 1024, 0, st>>>(wcnt, (int)swords, woff, wtot);
+          RUN_CUDA(cudaGetLastError());
+          unsigned long long nnew_dis = 0;
+          RUN_CUDA(cudaMemcpyAsync(&nnew_dis, wtot, 8, cudaMemcpyDeviceToHost, st));
+          RUN_CUDA(cudaStreamSynchronize(st));
+          int32_t* hit = nullptr;
+          RUN_CUDA(ctx->counts.ensure((size_t)3 * nst * 4));
+          hit = ctx->counts.as<int32_t>() + 2 * (size_t)nst;
+          if (nnew_dis > 0) {
+            const int64_t sp = ((int64_t)nnew_dis + kTile - 1) / kTile * kTile;
+            RUN_CUDA(nscratch.ensure((size_t)6 * sp * 4));
+            RUN_CUDA(nvalid.ensure((size_t)(sp / 32) * 4));
+            RUN_CUDA(cudaMemsetAsync(nscratch.p, 0, (size_t)6 * sp * 4, st));
+            newly_gather_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(olden.as<uint32_t>(), sub.enabled, swords, woff,
+                                                                                   sub.soa, sub.m_pad, nscratch.as<float>(), sp);
+            RUN_CUDA(cudaGetLastError());
+            fill_valid_words_kernel<<<(unsigned)((sp / 32 + 255) / 256), 256, 0, st>>>(nvalid.as<uint32_t>(), (int64_t)nnew_dis, sp / 32);
+            RUN_CUDA(cudaGetLastError());
+            PointSet ps;
+            float* b = nscratch.as<float>();
+            ps.x = b, ps.y = b + sp, ps.z = b + 2 * sp, ps.nx = b + 3 * sp, ps.ny = b + 4 * sp, ps.nz = b + 5 * sp;
+            ps.enabled = nvalid.as<uint32_t>();
+            ps.valid = nvalid.as<uint32_t>();
+            ps.n = (int64_t)nnew_dis;
+            ps.n_pad = sp;
+            // replicated on every rank (the scratch set is tiny): no all-reduce needed
+            if ((rc = score_enqueue(ctx, cloud, ps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st, hit,
+                                    ctx->counts.as<int32_t>())))
+              goto done;
+          } else {
+            RUN_CUDA(cudaMemsetAsync(hit, 0, (size_t)nst * 4, st));
+          }
+          unsigned long long* ktot = koff + nst;
+          invalidate_kernel<<<(nst + 255) / 256, 256, 0, st>>>(hit, store.flags[store.cur].as<uint8_t>(), nst, (int)best[0], keep);
+          RUN_CUDA(cudaGetLastError());
+          scan_u32_kernel<<<1, 1024, 0, st>>>(keep, nst, koff, ktot);
+          RUN_CUDA(cudaGetLastError());
+          const int nxt = store.cur ^ 1;
+          compact_store_kernel<<<(nst + 255) / 256, 256, 0, st>>>(
+              store.cands[store.cur].as<rsc_cand>(), store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(),
+              keep, koff, nst, store.cands[nxt].as<rsc_cand>(), store.score[nxt].as<int32_t>(), store.flags[nxt].as<uint8_t>());
+          RUN_CUDA(cudaGetLastError());
+          unsigned long long kept = 0;
+          RUN_CUDA(cudaMemcpyAsync(&kept, ktot, 8, cudaMemcpyDeviceToHost, st));
+          RUN_CUDA(cudaStreamSynchronize(st));
+          store.cur = nxt;
+          store.n = (int)kept;
+        }
+      }
+    }
+    // iterations.jl:151-156
+    if (prob_((double)p->tau, (double)counters[p->terminate_s], (double)N, (double)p->drawN) > p->prob_det) break;
+  }
+done:
+  cudaStreamSynchronize(st);
+  cleanup();
+  if (rc) {
+    delete run;
+    return rc;
+  }
+  run->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  *out = run;
+  return RSC_OK;
+#undef RUN_CUDA
+}
+
+int32_t rsc_run_nshapes(const rsc_run* r) { return r ? (int32_t)r->shapes.size() : 0; }
+int32_t rsc_run_iterations(const rsc_run* r) { return r ? r->iterations : 0; }
+double rsc_run_seconds(const rsc_run* r) { return r ? r->seconds : 0.0; }
+
+int32_t rsc_run_shape(const rsc_run* r, int32_t i, rsc_cand* shape, int64_t* n_inpoints) {
+  if (!r || i < 0 || (size_t)i >= r->shapes.size()) return RSC_E_ARG;
+  if (shape) *shape = r->shapes[i];
+  if (n_inpoints) *n_inpoints = (int64_t)r->inpoints[i].size();
+  return RSC_OK;
+}
+
+int32_t rsc_run_inpoints(const rsc_run* r, int32_t i, int64_t* out_idx) {
+  if (!r || i < 0 || (size_t)i >= r->shapes.size() || !out_idx) return RSC_E_ARG;
+  memcpy(out_idx, r->inpoints[i].data(), r->inpoints[i].size() * sizeof(int64_t));
+  return RSC_OK;
+}
+
 void rsc_run_destroy(rsc_run* r) { delete r; }
-}
+
+}  // extern "C"

@@ -27,7 +27,7 @@ struct GroupTask {
   uint32_t cand;   // original candidate index
   uint32_t group;  // 32-point group index in the point set
   uint32_t word;   // the FP32 decision bits the tiled kernel used (before enabled/valid gating)
-  uint32_t pad;
+  uint32_t slot_type;  // slot | (shape type << 28): saves the fix-up two dependent lookups
 };
 
 struct ScoreArgs {
@@ -191,7 +191,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
           const int o = a.orig[slot];
           if (o >= 0 && va) {
             const uint32_t pos = atomicAdd(a.wl_count, 1u);
-            if (pos < a.wl_cap) a.wl[pos] = GroupTask{(uint32_t)o, (uint32_t)gw, w, 0u};
+            if (pos < a.wl_cap) a.wl[pos] = GroupTask{(uint32_t)o, (uint32_t)gw, w, (uint32_t)slot | ((uint32_t)T << 28)};
           }
         }
         cntv[k] += __popc(w & va);
@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(256) fixup_scan_kernel(const __grid_constant__
   const uint32_t warps = gridDim.x * (blockDim.x >> 5);
   for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
     const GroupTask tk = a.wl[e];
-    const int type = cands[tk.cand].type;
-    const int slot = slot_of[tk.cand];
+    const int type = (int)(tk.slot_type >> 28);
+    const int slot = (int)(tk.slot_type & 0x0fffffffu);
     float r[kRecFields];
 #pragma unroll
     for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
@@ -529,7 +529,7 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
 
   // grid: columns x point chunks; aim at >= 8 waves of 4 CTAs/SM so the tail stays small
   const int real_cols = (C + spc - 1) / spc;
-  static const int waves = getenv("RSC_WAVES") ? atoi(getenv("RSC_WAVES")) : 8;
+  static const int waves = getenv("RSC_WAVES") ? atoi(getenv("RSC_WAVES")) : 32;
   static const int minb = getenv("RSC_MINB") ? atoi(getenv("RSC_MINB")) : 4;
   const long target = (long)ctx->sm_count * 4 * waves;
   long chunks = (target + real_cols - 1) / real_cols;
@@ -563,7 +563,7 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   ctx->stats.evals += (int64_t)C * ps.n;
   ctx->stats.cands_scored += C;
 
-  fixup_scan_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, d_cands, ctx->slot_of.as<int32_t>(), ctx->pairs.as<AmbPair>(),
+  fixup_scan_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(a, d_cands, ctx->slot_of.as<int32_t>(), ctx->pairs.as<AmbPair>(),
                                                        ctx->wl_count.as<uint32_t>() + 1, (uint32_t)ctx->wl_cap);
   RSC_CUDA(ctx, cudaGetLastError());
   fixup_pair_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a, d_cands, reinterpret_cast<const ex::ConeTrig*>(d_trig),

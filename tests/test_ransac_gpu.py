@@ -1,0 +1,103 @@
+"""End-to-end parity of the device loop (rsc_ransac_run) against the oracle's loop on the same
+Philox minimal sets: same extracted shapes in the same order, identical inlier index lists."""
+import numpy as np
+import pytest
+
+from oracle import ransac_oracle as O
+from tests.helpers import oracle_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import ransac_jl_b200 as R
+
+    return R
+
+
+def _compare_runs(R, extracted, want):
+    assert len(extracted) == len(want), ([R.strt(e.shape) for e in extracted], [O.SHAPE_NAMES[w.shape.kind] for w in want])
+    for got, w in zip(extracted, want):
+        c = got.shape.to_cand()
+        assert c.type == w.shape.kind
+        if c.type != 0:
+            assert bool(c.outwards) == w.shape.outwards
+        p = w.shape.params7()
+        np.testing.assert_allclose(np.array(c.p[:]), p, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(p).max()))
+        np.testing.assert_array_equal(got.inpoints, w.inpoints)
+
+
+def test_c1_default_parameters_matches_oracle(R):
+    """config c1: plane + sphere + cylinder, 10 k points, ransacparameters() defaults, 2 subsets"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_c1()
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 2)
+    params = R.ransacparameters()
+    extracted, secs = R.ransac(pc, params, True, seed=4321)
+    oc = O.Cloud(sc.vertices, sc.normals, [s.copy() for s in pc.subsets])
+    tr = O.RansacTrace()
+    want = O.ransac(oc, oracle_params(params), True, seed=4321, trace=tr)
+    _compare_runs(R, extracted, want)
+    kinds = sorted(R.strt(e.shape) for e in extracted)
+    assert kinds[:3] == ["cylinder", "plane", "sphere"] or len(kinds) >= 3, kinds
+    np.testing.assert_array_equal(pc.isenabled, oc.isenabled)
+    print(f"c1: {len(extracted)} shapes {kinds} in {secs} s (oracle: {tr.iterations} iterations, {tr.candidates_scored} candidates)")
+
+
+def test_noisy_scene_small_matches_oracle(R):
+    """noise + outliers, larger minsubsetN, 4 subsets, tau scaled to the cloud"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(81, 40_000, counts=(3, 1, 1, 1))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4)
+    params = R.ransacparameters(iteration={"tau": 400, "minsubsetN": 64, "itermax": 60})
+    extracted, secs = R.ransac(pc, params, True, seed=99)
+    oc = O.Cloud(sc.vertices, sc.normals, [s.copy() for s in pc.subsets])
+    want = O.ransac(oc, oracle_params(params), True, seed=99)
+    _compare_runs(R, extracted, want)
+    assert len(extracted) >= 3
+    np.testing.assert_array_equal(pc.isenabled, oc.isenabled)
+
+
+def test_resume_without_reset(R):
+    """ransac(pc, params, false) continues on the remaining points (iterations.jl:14-21)"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_c1(seed=3)
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 2)
+    params = R.ransacparameters(iteration={"itermax": 40})
+    first, _ = R.ransac(pc, params, True, seed=7)
+    left = pc.count_enabled()
+    second, _ = R.ransac(pc, params, False, seed=8)
+    assert pc.count_enabled() <= left
+    taken = np.concatenate([e.inpoints for e in first + second]) if first or second else np.zeros(0, int)
+    assert len(np.unique(taken)) == len(taken)  # no point is extracted twice
+    assert pc.count_enabled() == pc.size - len(taken)
+
+
+def test_sharded_callback_single_rank(R):
+    """the sharded code path (range + all-reduce callback) on one rank equals the plain run"""
+    import ctypes as C
+
+    from ransac_jl_b200 import scenes
+    from ransac_jl_b200._lib import ALLREDUCE_FN, lib
+
+    sc = scenes.scene_c1(seed=11)
+    params = R.ransacparameters(iteration={"itermax": 120})
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 2)
+    plain, _ = R.ransac(pc, params, True, seed=5)
+    calls = []
+    cb = ALLREDUCE_FN(lambda user, ptr, count, stream: calls.append(count) or 0)
+    pc.ctx.check(lib.rsc_ctx_set_allreduce(pc.ctx.h, C.cast(cb, C.c_void_p), None))
+    try:
+        pc.ctx.check(lib.rsc_cloud_set_range(pc.handle, 0, pc.size))
+        sharded, _ = R.ransac(pc, params, True, seed=5)
+    finally:
+        lib.rsc_ctx_set_allreduce(pc.ctx.h, None, None)
+    assert len(calls) > 0
+    assert len(plain) == len(sharded)
+    for a, b in zip(plain, sharded):
+        assert list(a.shape.to_cand().p) == list(b.shape.to_cand().p)
+        np.testing.assert_array_equal(a.inpoints, b.inpoints)

@@ -1,0 +1,73 @@
+"""CPU tests of the multi-GPU host logic: the point-range partition, and -- with two gloo ranks --
+that summing per-shard counts / disjoint inlier-mask words reproduces the unsharded result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_partition_covers_exactly_once():
+    from ransac_jl_b200.shard import ALIGN, partition
+
+    for n in (1, 2047, 2048, 2049, 10_000, 1 << 20, 10_000_000, 100_000_001):
+        for world in (1, 2, 4, 8):
+            parts = partition(n, world)
+            assert len(parts) == world
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            for (a, b), (c, d) in zip(parts, parts[1:]):
+                assert b == c and a <= b
+            for lo, hi in parts:
+                assert lo % ALIGN == 0 and (hi % ALIGN == 0 or hi == n)
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import ransac_oracle as O
+    from ransac_jl_b200 import scenes
+    from ransac_jl_b200.shard import partition
+    from tests.helpers import to_oracle_shape
+
+    sc = scenes.scene_mixed(5, n)
+    cands = scenes.perturbed_candidates(sc, 3, seed=2)
+    lo, hi = partition(n, world)[rank]
+    P, N = sc.vertices.astype(np.float64), sc.normals.astype(np.float64)
+    op = O.default_parameters()
+    # what each rank's GPU computes on its shard: counts and its slice of the inlier mask
+    local = np.array([int(O.compatibles(to_oracle_shape(c), P[lo:hi], N[lo:hi], op).sum()) for c in cands], np.int32)
+    words = np.zeros((n + 31) // 32, np.int32)
+    m = np.zeros(n, bool)
+    m[lo:hi] = O.compatibles(to_oracle_shape(cands[0]), P[lo:hi], N[lo:hi], op)
+    packed = np.packbits(m, bitorder="little")
+    words.view(np.uint8)[: len(packed)] = packed
+    t_counts, t_words = torch.from_numpy(local), torch.from_numpy(words)
+    dist.all_reduce(t_counts)  # C1: per-candidate counts
+    dist.all_reduce(t_words)  # disjoint ranges: sum == union of the mask words
+    if rank == 0:
+        whole = np.array([int(O.compatibles(to_oracle_shape(c), P, N, op).sum()) for c in cands], np.int32)
+        mask = O.compatibles(to_oracle_shape(cands[0]), P, N, op)
+        got = np.unpackbits(t_words.numpy().view(np.uint8), bitorder="little")[:n].astype(bool)
+        q.put((bool(np.array_equal(t_counts.numpy(), whole)), bool(np.array_equal(got, mask))))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_count_and_mask_reduction():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 9000, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    ok_counts, ok_mask = q.get(timeout=5)
+    assert ok_counts and ok_mask
