@@ -50,9 +50,9 @@ def test_noisy_scene_small_matches_oracle(R):
     """noise + outliers, larger minsubsetN, 4 subsets, tau scaled to the cloud"""
     from ransac_jl_b200 import scenes
 
-    sc = scenes.scene_mixed(81, 40_000, counts=(3, 1, 1, 1))
+    sc = scenes.scene_mixed(81, 40_000, noise_frac=0.002, jitter_deg=1.0, outlier_frac=0.1, counts=(3, 1, 1, 1))
     pc = R.RANSACCloud(sc.vertices, sc.normals, 4)
-    params = R.ransacparameters(iteration={"tau": 400, "minsubsetN": 64, "itermax": 60})
+    params = R.ransacparameters(iteration={"tau": 400, "minsubsetN": 128, "itermax": 120})
     extracted, secs = R.ransac(pc, params, True, seed=99)
     oc = O.Cloud(sc.vertices, sc.normals, [s.copy() for s in pc.subsets])
     want = O.ransac(oc, oracle_params(params), True, seed=99)
