@@ -105,7 +105,7 @@ def make_workload(points: int, ncands: int, rank: int):
     return sc, cands
 
 
-def cpu_baseline(sc, cands, params, budget_pts: int):
+def cpu_baseline(sc, cands, params, budget_pts: int, ncand: int = 64):
     """CPU restatement of the reference (oracle/) on a bounded sample of the same workload."""
     from oracle import ransac_oracle as O
     from tests.helpers import oracle_params, to_oracle_shape
@@ -119,7 +119,7 @@ def cpu_baseline(sc, cands, params, budget_pts: int):
     n = min(budget_pts, len(sc.vertices))
     P = sc.vertices[:n].astype(np.float64)
     N = sc.normals[:n].astype(np.float64)
-    step = max(1, len(cands) // 64)
+    step = max(1, len(cands) // ncand)
     sample = cands[::step]
     t0 = time.perf_counter()
     if have_c:
@@ -142,16 +142,16 @@ def run_reference(args, rank, world):
     import ransac_jl_b200  # noqa: F401 (host-side types only; nothing below touches the GPU)
     from ransac_jl_b200 import params as RP
 
-    pts = args.cpu_sample or (1 << 18)
+    pts = args.cpu_sample or (2 << 20)
     sc, cands = make_workload(pts, args.cands, 0)
     params = RP.ransacparameters()
     vals = []
     for i in range(args.warmup + args.steps):
-        r = cpu_baseline(sc, cands, params, pts)
+        r = cpu_baseline(sc, cands, params, pts, ncand=128)
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([x["value"] for x in vals]))
-    ms = float(np.mean([len(cands[:: max(1, len(cands) // 64)]) * pts / (x["value"] * 1e9) * 1e3 for x in vals]))
+    ms = float(np.mean([len(cands[:: max(1, len(cands) // 128)]) * pts / (x["value"] * 1e9) * 1e3 for x in vals]))
     out = {
         "impl": "reference", "metric": "candidate_point_evals_per_s", "value": v, "unit": "G evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -253,12 +253,10 @@ def main():
         counts_h = np.zeros(Cn, dtype=np.int32)
 
         def step_e2e():
-            h = C.c_void_p()
-            pc.ctx.check(lib.rsc_cloud_create(pc.ctx.h, xyz.data_ptr(), nrm.data_ptr(), n, C.byref(h)))
-            try:
-                pc.ctx.check(lib.rsc_score(h, C.byref(cp), arr, Cn, -1, counts_h.ctypes.data, None))
-            finally:
-                lib.rsc_cloud_destroy(h)
+            # the public host-buffer calls: upload this step's cloud, upload + score the candidates,
+            # read the counts back (device buffers of the cloud handle are reused, not re-allocated)
+            pc.ctx.check(lib.rsc_cloud_update(pc.handle, xyz.data_ptr(), nrm.data_ptr(), n))
+            pc.ctx.check(lib.rsc_score(pc.handle, C.byref(cp), arr, Cn, -1, counts_h.ctypes.data, None))
 
         for _ in range(max(1, min(args.warmup, 2))):
             step_e2e()
@@ -321,7 +319,8 @@ def main():
         "fp64_guard_pairs_per_step": int(guard),
     }
     if not args.no_cpu:
-        out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or (1 << 16))
+        # ~10-20 s of CPU work: 512 candidates (every 8th) x the first 8 Mi points of the same workload
+        out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or (8 << 20), ncand=512)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,208 @@
+# RANSACB200.jl -- Julia host binding of libransac_b200 (include/rsc.h) for cserteGT3/RANSAC.jl.
+#
+# UNTESTED IN THIS REPOSITORY'S CI: the build image has no Julia.  The binding mirrors, one to one,
+# the ctypes binding that the test-suite exercises (ransac.jl_b200/_lib.py); struct layouts are the
+# ones asserted in tests/test_abi_cpu.py.
+#
+# It keeps RANSAC.jl's public surface: `ransac(pc, params, setenabled)`, `RANSACCloud`, the
+# `Fitted*` types and the parameter NamedTuples are RANSAC.jl's own.  What changes is where the work
+# happens: for the four built-in shapes `fit` / `scorecandidate` / `refit` / the loop body are
+# `ccall`s into the CUDA library.  User-defined shapes keep their Julia methods (docs/src/newprimitive.md).
+module RANSACB200
+
+using RANSAC
+using RANSAC: FittedShape, FittedPlane, FittedSphere, FittedCylinder, FittedCone, ExtractedShape,
+              RANSACCloud, ConfidenceInterval
+using StaticArrays
+using Libdl
+
+const LIB = Ref{String}(get(ENV, "RANSAC_B200_LIB", "libransac_b200.so"))
+
+# ---- POD mirrors (include/rsc.h) -------------------------------------------------------------
+struct RscCand            # 64 bytes
+    type::Int32
+    outwards::Int32
+    p::NTuple{7,Float64}
+end
+
+struct RscParams          # 160 bytes
+    drawN::Int32
+    minsubsetN::Int32
+    prob_det::Float64
+    tau::Int64
+    itermax::Int32
+    extract_s::Int32
+    terminate_s::Int32
+    n_shape_types::Int32
+    shape_types::NTuple{4,Int32}
+    collin_threshold::Float64
+    parallelthrdeg::Float64
+    eps::NTuple{4,Float64}
+    alpha::NTuple{4,Float64}
+    sphere_par::Float64
+    minconeopang::Float64
+    compat_flags::UInt32
+    reserved::UInt32
+end
+
+const KIND = Dict{Any,Int32}(FittedPlane => 0, FittedSphere => 1, FittedCylinder => 2, FittedCone => 3)
+const S_SYM = Dict(:lengthC => Int32(0), :allcand => Int32(1), :nofminset => Int32(2))
+
+tocand(s::FittedPlane) = RscCand(0, 1, (s.point..., s.normal..., 0.0))
+tocand(s::FittedSphere) = RscCand(1, s.outwards, (s.center..., s.radius, 0.0, 0.0, 0.0))
+tocand(s::FittedCylinder) = RscCand(2, s.outwards, (s.axis..., s.center..., s.radius))
+tocand(s::FittedCone) = RscCand(3, s.outwards, (s.apex..., s.axis..., s.opang))
+
+function fromcand(c::RscCand)
+    p = c.p
+    v(i) = SVector{3,Float64}(p[i], p[i+1], p[i+2])
+    c.type == 0 && return FittedPlane(v(1), v(4))
+    c.type == 1 && return FittedSphere(v(1), p[4], c.outwards != 0)
+    c.type == 2 && return FittedCylinder(v(1), v(4), p[7], c.outwards != 0)
+    return FittedCone(v(1), v(4), p[7], c.outwards != 0)
+end
+
+"Flatten the nested NamedTuple of `ransacparameters` (utilities.jl:332-433) into the C POD."
+function toparams(params)
+    it = params.iteration
+    types = Int32[KIND[t] for t in it.shape_types]
+    st = ntuple(i -> i <= length(types) ? types[i] : Int32(0), 4)
+    g(name, f, d) = haskey(params, name) ? Float64(getfield(getfield(params, name), f)) : d
+    eps = (g(:plane, :ϵ, 0.3), g(:sphere, :ϵ, 0.3), g(:cylinder, :ϵ, 0.3), g(:cone, :ϵ, 0.3))
+    alp = (g(:plane, :α, deg2rad(5)), g(:sphere, :α, deg2rad(5)), g(:cylinder, :α, deg2rad(5)), g(:cone, :α, deg2rad(5)))
+    RscParams(it.drawN, it.minsubsetN, it.prob_det, it.τ, it.itermax, S_SYM[it.extract_s], S_SYM[it.terminate_s],
+              length(types), st, params.common.collin_threshold, params.common.parallelthrdeg, eps, alp,
+              g(:sphere, :sphere_par, 0.02), g(:cone, :minconeopang, deg2rad(2)), UInt32(1), UInt32(0))
+end
+
+# ---- context / cloud handles ---------------------------------------------------------------------
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+function check(rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:rsc_last_error, LIB[]), Cstring, (Ptr{Cvoid},), CTX[]))
+    error("libransac_b200 error $rc: $msg")
+end
+
+function context(device::Integer=0)
+    if CTX[] == C_NULL
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:rsc_ctx_create, LIB[]), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h)
+        rc == 0 || error("rsc_ctx_create failed ($rc): an sm_100 (B200) GPU is required, there is no CPU fallback")
+        CTX[] = h[]
+    end
+    CTX[]
+end
+
+"Device twin of a `RANSACCloud`: uploads vertices/normals (float32 SoA on the GPU) and subset 1."
+mutable struct DeviceCloud
+    h::Ptr{Cvoid}
+    pc::RANSACCloud
+    function DeviceCloud(pc::RANSACCloud)
+        ctx = context()
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        v, n = pc.vertices, pc.normals            # Vector{SVector{3,T}} is bit-compatible with T[3N]
+        GC.@preserve v n begin
+            if eltype(eltype(v)) == Float32
+                check(ccall((:rsc_cloud_create, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Ref{Ptr{Cvoid}}),
+                            ctx, pointer(v), pointer(n), pc.size, h))
+            else
+                check(ccall((:rsc_cloud_create_f64, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Ptr{Cvoid}}),
+                            ctx, pointer(v), pointer(n), pc.size, h))
+            end
+        end
+        idx = Int64.(pc.subsets[1] .- 1)          # 0-based on the C side
+        check(ccall((:rsc_cloud_set_subset, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int64), h[], 0, idx, length(idx)))
+        dc = new(h[], pc)
+        push_enabled!(dc)
+        finalizer(d -> ccall((:rsc_cloud_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), d.h), dc)
+    end
+end
+
+# pc.isenabled is a BitArray: its `chunks` are exactly the UInt64 words the C ABI expects
+push_enabled!(dc) = check(ccall((:rsc_cloud_set_enabled, LIB[]), Int32, (Ptr{Cvoid}, Ptr{UInt64}), dc.h, dc.pc.isenabled.chunks))
+pull_enabled!(dc) = check(ccall((:rsc_cloud_get_enabled, LIB[]), Int32, (Ptr{Cvoid}, Ptr{UInt64}), dc.h, dc.pc.isenabled.chunks))
+
+# ---- the operator API for built-in shapes ----------------------------------------------------------
+"`scorecandidates!` for a vector of built-in shapes: one launch, returns [(ConfidenceInterval, inpoints)]."
+function scorecandidates(dc::DeviceCloud, cands::Vector{<:FittedShape}, subsetID::Integer, params)
+    C = length(cands)
+    recs = RscCand[tocand(c) for c in cands]
+    sub = dc.pc.subsets[subsetID]
+    M = length(sub)
+    words = cld(M, 32)
+    counts = zeros(Int32, C)
+    masks = zeros(UInt32, words, C)               # column c = row c of the C layout
+    prm = Ref(toparams(params))
+    check(ccall((:rsc_score, LIB[]), Int32,
+                (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Int32, Ptr{Int32}, Ptr{UInt32}),
+                dc.h, prm, recs, C, subsetID - 1, counts, masks))
+    map(1:C) do c
+        bits = BitVector(undef, words * 32)
+        copyto!(reinterpret(UInt32, bits.chunks), 1, view(masks, :, c), 1, words)  # same LSB-first layout
+        inpoints = sub[findall(view(bits, 1:M))]
+        (RANSAC.estimatescore(M, dc.pc.size, Int(counts[c])), inpoints)
+    end
+end
+
+"`refit` + `invalidate_indexes!` (plane.jl:137-143 ... fitting.jl:197-202) on the device."
+function refit_extract!(dc::DeviceCloud, s::FittedShape, params; disable::Bool=true)
+    out = Vector{Int64}(undef, dc.pc.size)
+    n = Ref{Int64}(0)
+    prm = Ref(toparams(params))
+    cand = Ref(tocand(s))
+    check(ccall((:rsc_refit_extract, LIB[]), Int32,
+                (Ptr{Cvoid}, Ref{RscParams}, Ref{RscCand}, Ptr{Int64}, Ref{Int64}, Int32), dc.h, prm, cand, out, n, disable))
+    resize!(out, n[])
+    disable && pull_enabled!(dc)
+    ExtractedShape(s, out .+ 1)
+end
+
+"`forcefitshapes!` for S minimal sets given as a 3 x S matrix of (1-based) point indices."
+function fit_batch(dc::DeviceCloud, idx::Matrix{Int}, params)
+    S = size(idx, 2)
+    prm = Ref(toparams(params))
+    cap = S * length(params.iteration.shape_types)
+    out = Vector{RscCand}(undef, cap)
+    out_set = Vector{Int32}(undef, cap)
+    n = Ref{Int32}(0)
+    check(ccall((:rsc_fit_batch, LIB[]), Int32,
+                (Ptr{Cvoid}, Ref{RscParams}, Ptr{Int64}, Int32, Ptr{RscCand}, Ptr{Int32}, Ref{Int32}),
+                dc.h, prm, Int64.(idx .- 1), S, out, out_set, n))
+    [fromcand(out[i]) for i in 1:n[]], out_set[1:n[]] .+ 1
+end
+
+"""
+    ransac(pc, params, setenabled; reset_rand=false, seed=1234)
+
+Drop-in for `RANSAC.ransac` when every entry of `params.iteration.shape_types` is a built-in shape:
+the whole loop of iterations.jl:35-162 runs inside one `ccall`.  Otherwise falls back to
+`RANSAC.ransac` (user-defined shapes run their own Julia methods).
+"""
+function ransac(pc::RANSACCloud, params, setenabled::Bool; reset_rand=false, seed::Integer=1234)
+    all(t -> haskey(KIND, t), params.iteration.shape_types) || return RANSAC.ransac(pc, params, setenabled; reset_rand=reset_rand)
+    setenabled && fill!(pc.isenabled, true)
+    dc = DeviceCloud(pc)
+    run = Ref{Ptr{Cvoid}}(C_NULL)
+    prm = Ref(toparams(params))
+    check(ccall((:rsc_ransac_run, LIB[]), Int32, (Ptr{Cvoid}, Ref{RscParams}, UInt64, Ref{Ptr{Cvoid}}),
+                dc.h, prm, reset_rand ? 1234 : seed, run))
+    extracted = ExtractedShape[]
+    try
+        for i in 0:ccall((:rsc_run_nshapes, LIB[]), Int32, (Ptr{Cvoid},), run[])-1
+            c = Ref{RscCand}()
+            n = Ref{Int64}(0)
+            check(ccall((:rsc_run_shape, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ref{RscCand}, Ref{Int64}), run[], i, c, n))
+            idx = Vector{Int64}(undef, n[])
+            n[] > 0 && check(ccall((:rsc_run_inpoints, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}), run[], i, idx))
+            push!(extracted, ExtractedShape(fromcand(c[]), idx .+ 1))
+        end
+        secs = ccall((:rsc_run_seconds, LIB[]), Float64, (Ptr{Cvoid},), run[])
+        pull_enabled!(dc)
+        return extracted, trunc(secs, digits=2)
+    finally
+        ccall((:rsc_run_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), run[])
+    end
+end
+
+end # module

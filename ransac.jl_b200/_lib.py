@@ -72,6 +72,7 @@ SIGNATURES = {
     "rsc_cloud_create": (C.c_int32, [_P, _P, _P, C.c_int64, C.POINTER(_P)]),
     "rsc_cloud_create_f64": (C.c_int32, [_P, _P, _P, C.c_int64, C.POINTER(_P)]),
     "rsc_cloud_create_shard": (C.c_int32, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_P)]),
+    "rsc_cloud_update": (C.c_int32, [_P, _P, _P, C.c_int64]),
     "rsc_cloud_destroy": (None, [_P]),
     "rsc_cloud_size": (C.c_int64, [_P]),
     "rsc_cloud_set_subset": (C.c_int32, [_P, C.c_int32, _P, C.c_int64]),

@@ -100,6 +100,37 @@ int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st) {
   return RSC_OK;
 }
 
+// host AoS -> device SoA into the cloud's existing buffers; refreshes the guard-band scales
+template <class T>
+static int32_t cloud_upload(rsc_cloud* c, const T* xyz, const T* nrm) {
+  rsc_ctx* ctx = c->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t n = c->n;
+  const int64_t words = c->n_pad / 32;
+  const size_t bytes = (size_t)3 * n * sizeof(T);
+  RSC_CUDA(ctx, ctx->misc.ensure(bytes));
+  RSC_CUDA(ctx, ctx->misc2.ensure(bytes + 16));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, xyz, bytes, cudaMemcpyHostToDevice, st));
+  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc2.p, nrm, bytes, cudaMemcpyHostToDevice, st));
+  RSC_CUDA(ctx, ctx->wl_count.ensure(sizeof(uint32_t) * 4));
+  uint32_t* bounds = ctx->wl_count.as<uint32_t>() + 2;
+  RSC_CUDA(ctx, cudaMemsetAsync(bounds, 0, 2 * sizeof(uint32_t), st));
+  aos_to_soa_kernel<T><<<(unsigned)((c->n_pad + 255) / 256), 256, 0, st>>>(ctx->misc.as<T>(), ctx->misc2.as<T>(), n,
+                                                                            c->n_pad, c->soa, bounds);
+  RSC_CUDA(ctx, cudaGetLastError());
+  fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(c->valid, c->enabled, n, words);
+  RSC_CUDA(ctx, cudaGetLastError());
+  uint32_t hb[2];
+  RSC_CUDA(ctx, cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  float p2, n2;
+  memcpy(&p2, &hb[0], 4);
+  memcpy(&n2, &hb[1], 4);
+  c->pmax = sqrtf(p2) * 1.000001f;
+  c->nmax = sqrtf(n2) * 1.000001f;
+  return RSC_OK;
+}
+
 template <class T>
 static int32_t cloud_create_impl(rsc_ctx* ctx, const T* xyz, const T* nrm, int64_t n, int64_t global_offset,
                                  int64_t n_global, rsc_cloud** out) {
@@ -124,28 +155,11 @@ static int32_t cloud_create_impl(rsc_ctx* ctx, const T* xyz, const T* nrm, int64
     return fail_cuda(ctx, e, "cloud_create: cudaMalloc");
   }
   RSC_CUDA(ctx, cudaMemsetAsync(c->soa, 0, (size_t)6 * c->n_pad * sizeof(float), st));
-  // stage the AoS arrays in device scratch, transpose on the device
-  const size_t bytes = (size_t)3 * n * sizeof(T);
-  RSC_CUDA(ctx, ctx->misc.ensure(bytes));
-  RSC_CUDA(ctx, ctx->misc2.ensure(bytes + 16));
-  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, xyz, bytes, cudaMemcpyHostToDevice, st));
-  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc2.p, nrm, bytes, cudaMemcpyHostToDevice, st));
-  RSC_CUDA(ctx, ctx->wl_count.ensure(sizeof(uint32_t) * 4));
-  uint32_t* bounds = ctx->wl_count.as<uint32_t>() + 2;
-  RSC_CUDA(ctx, cudaMemsetAsync(bounds, 0, 2 * sizeof(uint32_t), st));
-  aos_to_soa_kernel<T><<<(unsigned)((c->n_pad + 255) / 256), 256, 0, st>>>(ctx->misc.as<T>(), ctx->misc2.as<T>(), n,
-                                                                            c->n_pad, c->soa, bounds);
-  RSC_CUDA(ctx, cudaGetLastError());
-  fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(c->valid, c->enabled, n, words);
-  RSC_CUDA(ctx, cudaGetLastError());
-  uint32_t hb[2];
-  RSC_CUDA(ctx, cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
-  RSC_CUDA(ctx, cudaStreamSynchronize(st));
-  float p2, n2;
-  memcpy(&p2, &hb[0], 4);
-  memcpy(&n2, &hb[1], 4);
-  c->pmax = sqrtf(p2) * 1.000001f;
-  c->nmax = sqrtf(n2) * 1.000001f;
+  int32_t rc = cloud_upload<T>(c, xyz, nrm);
+  if (rc) {
+    rsc_cloud_destroy(c);
+    return rc;
+  }
   *out = c;
   return RSC_OK;
 }
@@ -168,6 +182,23 @@ int32_t rsc_cloud_create_shard(rsc_ctx* ctx, const float* xyz, const float* nrm,
                                int64_t n_global, rsc_cloud** out) {
   if (global_offset < 0 || n_global < global_offset + n) return fail(ctx, RSC_E_ARG, "cloud_create_shard: bad range");
   return cloud_create_impl<float>(ctx, xyz, nrm, n, global_offset, n_global, out);
+}
+
+int32_t rsc_cloud_update(rsc_cloud* c, const float* xyz, const float* nrm, int64_t n) {
+  if (!c) return RSC_E_ARG;
+  if (!xyz || !nrm || n != c->n) return fail(c->ctx, RSC_E_ARG, "cloud_update: the cloud size cannot change");
+  RSC_CUDA(c->ctx, cudaSetDevice(c->ctx->device));
+  int32_t rc = cloud_upload<float>(c, xyz, nrm);
+  if (rc) return rc;
+  for (size_t i = 0; i < c->subsets.size(); ++i) {  // gathered subset copies follow the new coordinates
+    rsc_subset& s = c->subsets[i];
+    if (!s.soa) continue;
+    gather_subset_kernel<<<(unsigned)((s.m + 255) / 256), 256, 0, c->ctx->stream>>>(c->soa, c->n_pad, s.idx, s.m, s.m_pad, s.soa);
+    RSC_CUDA(c->ctx, cudaGetLastError());
+    RSC_CUDA(c->ctx, cudaMemcpyAsync(s.enabled, s.valid, (size_t)(s.m_pad / 32) * 4, cudaMemcpyDeviceToDevice, c->ctx->stream));
+  }
+  RSC_CUDA(c->ctx, cudaStreamSynchronize(c->ctx->stream));
+  return RSC_OK;
 }
 
 void rsc_cloud_destroy(rsc_cloud* c) {

@@ -1,0 +1,75 @@
+"""Sharded end-to-end ransac() over the GPUs of one box (torchrun, one process per GPU).
+
+Every rank builds the same seeded scene, runs the device loop with its point range + the NCCL
+all-reduce callback, and rank 0 checks the result against an unsharded run on its own GPU.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+      --master-port 29517 tools/ransac_multi.py --scene c2
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ransac_jl_b200 as R
+from ransac_jl_b200 import scenes
+from ransac_jl_b200.shard import ShardedContext
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scene", default="c2", choices=["c1", "c2", "c4", "c5small"])
+ap.add_argument("--check", type=int, default=1)
+args = ap.parse_args()
+
+rank = int(os.environ.get("RANK", 0))
+world = int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+if args.scene == "c1":
+    sc, r, it = scenes.scene_c1(), 2, {}
+elif args.scene == "c2":
+    sc, r = scenes.scene_c2(), 32
+    it = {"tau": sc.vertices.shape[0] // 100, "minsubsetN": 4096, "itermax": 200}
+elif args.scene == "c4":
+    sc, r = scenes.scene_cad(), 32
+    it = {"tau": sc.vertices.shape[0] // 1000, "minsubsetN": 8192, "itermax": 400}
+else:
+    sc, r = scenes.scene_lidar(10_000_000), 64
+    it = {"tau": sc.vertices.shape[0] // 500, "minsubsetN": 8192, "itermax": 200}
+params = R.ransacparameters(iteration=it)
+pc = R.RANSACCloud(sc.vertices, sc.normals, r, device=local)
+sh = ShardedContext(pc) if world > 1 else None
+R.ransac(pc, R.ransacparameters(iteration=dict(it, itermax=2)), True, seed=1)  # warm-up (allocations, NCCL)
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t0 = time.perf_counter()
+ex, secs = R.ransac(pc, params, True, seed=2024)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+tt = torch.tensor([dt], device="cuda")
+if world > 1:
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+ok = None
+if rank == 0 and args.check and world > 1:
+    sh.close()
+    pc2 = R.RANSACCloud(sc.vertices, sc.normals, pc.subsets, device=local)
+    ex2, _ = R.ransac(pc2, params, True, seed=2024)
+    ok = len(ex) == len(ex2) and all(
+        list(a.shape.to_cand().p) == list(b.shape.to_cand().p) and np.array_equal(a.inpoints, b.inpoints) for a, b in zip(ex, ex2))
+if rank == 0:
+    st = pc.ctx.stats()
+    print(json.dumps({"scene": args.scene, "points": int(sc.vertices.shape[0]), "n_gpus": world, "ransac_seconds": float(tt.item()),
+                      "shapes": [[R.strt(e.shape), int(len(e.inpoints))] for e in ex][:40], "n_shapes": len(ex),
+                      "points_extracted": int(sum(len(e.inpoints) for e in ex)), "evals": int(st.evals),
+                      "sets_drawn": int(st.sets_drawn), "matches_unsharded": ok}))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
