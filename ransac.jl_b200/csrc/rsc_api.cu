@@ -91,6 +91,7 @@ int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess) {
     delete ctx;
@@ -108,6 +109,8 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
                          &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count, &ctx->pairs,
                          &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf};
   for (auto* b : bufs) b->release();
+  ctx->stage[0].release(), ctx->stage[1].release();
+  cudaStreamDestroy(ctx->copy_stream);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -164,6 +167,9 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
   for (int i = 0; i < C; ++i)
     if (cands[i].type < 0 || cands[i].type >= RSC_NTYPES) return fail(ctx, RSC_E_ARG, "score: unknown shape type");
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  // a chunked upload still in flight: whole-cloud, counts-only scoring follows it chunk by chunk
+  const bool chunked = cloud->pending && subset_id < 0 && !masks;
+  if (!chunked && (rc = cloud_ready(cloud))) return rc;
   PointSet ps;
   if ((rc = pick_pointset(cloud, subset_id, &ps))) return rc;
   const Thresh th = make_thresh(params);
@@ -185,9 +191,27 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
   for (int attempt = 0; attempt < 3; ++attempt) {
     RSC_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     int32_t* d_policy = ctx->counts.as<int32_t>() + 2 * (size_t)C;
-    rc = score_enqueue(ctx, cloud, ps, th, ctx->cands.as<rsc_cand>(), C, d_policy, masks != nullptr, st,
-                       ctx->counts.as<int32_t>(), ctx->counts.as<int32_t>() + C, ctx->aux.as<double>());
-    if (rc) return rc;
+    if (chunked && attempt == 0) {
+      const int nchunks = (int)((cloud->n + cloud->chunk_pts - 1) / cloud->chunk_pts);
+      for (int i = 0; i < nchunks && !rc; ++i) {
+        const int64_t off = (int64_t)i * cloud->chunk_pts;
+        PointSet sl = ps;
+        sl.x += off, sl.y += off, sl.z += off, sl.nx += off, sl.ny += off, sl.nz += off;
+        sl.enabled += off / 32, sl.valid += off / 32;
+        sl.n = (cloud->n - off < cloud->chunk_pts) ? cloud->n - off : cloud->chunk_pts;
+        sl.n_pad = (i == nchunks - 1) ? cloud->n_pad - off : cloud->chunk_pts;
+        RSC_CUDA(ctx, cudaStreamWaitEvent(st, cloud->chunk_ev[i], 0));
+        rc = score_enqueue(ctx, cloud, sl, th, ctx->cands.as<rsc_cand>(), C, i == nchunks - 1 ? d_policy : nullptr, false, st,
+                           ctx->counts.as<int32_t>(), ctx->counts.as<int32_t>() + C, ctx->aux.as<double>(),
+                           cloud->d_bounds + 2 * i, i > 0);
+      }
+      if (rc) return rc;
+      if ((rc = cloud_ready(cloud))) return rc;
+    } else {
+      rc = score_enqueue(ctx, cloud, ps, th, ctx->cands.as<rsc_cand>(), C, d_policy, masks != nullptr, st,
+                         ctx->counts.as<int32_t>(), ctx->counts.as<int32_t>() + C, ctx->aux.as<double>());
+      if (rc) return rc;
+    }
     RSC_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
     uint32_t nq[2] = {0, 0};  // queued groups, queued pairs
     RSC_CUDA(ctx, cudaMemcpyAsync(counts, d_policy, (size_t)C * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -227,6 +251,7 @@ int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand
   if (rc) return rc;
   if (C == 0) return RSC_OK;
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((rc = cloud_ready(cloud))) return rc;
   PointSet ps;
   if ((rc = pick_pointset(cloud, subset_id, &ps))) return rc;
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -269,6 +294,7 @@ int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_
   int32_t rc = check_params(ctx, params);
   if (rc) return rc;
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((rc = cloud_ready(cloud))) return rc;
   cudaStream_t st = ctx->stream;
   Thresh th = make_thresh(params);
   th.honour_enabled = 0xFu;  // refit always works on the enabled points (e.g. sphere.jl:181-185)

@@ -8,14 +8,17 @@
 
 namespace rsc {
 
+// xyz/nrm: AoS staging of the points [off, off+cnt); soa: the whole cloud's SoA arrays
 template <class T>
-__global__ void aos_to_soa_kernel(const T* __restrict__ xyz, const T* __restrict__ nrm, int64_t n,
-                                  int64_t n_pad, float* __restrict__ soa, uint32_t* __restrict__ bounds) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void aos_to_soa_kernel(const T* __restrict__ xyz, const T* __restrict__ nrm, int64_t off, int64_t cnt,
+                                  int64_t n_pad, float* __restrict__ soa, uint32_t* __restrict__ bounds,
+                                  uint32_t* __restrict__ gbounds) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = off + j;
   float p2 = 0.f, n2 = 0.f;
-  if (i < n) {
-    const float x = (float)xyz[3 * i], y = (float)xyz[3 * i + 1], z = (float)xyz[3 * i + 2];
-    const float a = (float)nrm[3 * i], b = (float)nrm[3 * i + 1], c = (float)nrm[3 * i + 2];
+  if (j < cnt) {
+    const float x = (float)xyz[3 * j], y = (float)xyz[3 * j + 1], z = (float)xyz[3 * j + 2];
+    const float a = (float)nrm[3 * j], b = (float)nrm[3 * j + 1], c = (float)nrm[3 * j + 2];
     soa[i] = x;
     soa[n_pad + i] = y;
     soa[2 * n_pad + i] = z;
@@ -35,6 +38,8 @@ __global__ void aos_to_soa_kernel(const T* __restrict__ xyz, const T* __restrict
   if ((threadIdx.x & 31) == 0) {  // non-negative floats order like their bit patterns
     atomicMax(bounds, __float_as_uint(p2));
     atomicMax(bounds + 1, __float_as_uint(n2));
+    atomicMax(gbounds, __float_as_uint(p2));  // running maximum over the whole cloud
+    atomicMax(gbounds + 1, __float_as_uint(n2));
   }
 }
 
@@ -100,34 +105,69 @@ int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st) {
   return RSC_OK;
 }
 
-// host AoS -> device SoA into the cloud's existing buffers; refreshes the guard-band scales
+constexpr int64_t kChunkPts = 2 << 20;  // upload granularity (48 MB of float32 AoS per chunk)
+
+// host AoS -> device SoA into the cloud's existing buffers, in chunks on the copy stream:
+// H2D of chunk i+1 overlaps the transposition of chunk i and -- because the call returns as soon as
+// everything is enqueued -- whatever scoring the caller launches next (rsc_score walks the chunks
+// as their events fire).  Other entry points first wait for the upload (cloud_ready).
 template <class T>
 static int32_t cloud_upload(rsc_cloud* c, const T* xyz, const T* nrm) {
   rsc_ctx* ctx = c->ctx;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t cs = ctx->copy_stream;
   const int64_t n = c->n;
   const int64_t words = c->n_pad / 32;
-  const size_t bytes = (size_t)3 * n * sizeof(T);
-  RSC_CUDA(ctx, ctx->misc.ensure(bytes));
-  RSC_CUDA(ctx, ctx->misc2.ensure(bytes + 16));
-  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, xyz, bytes, cudaMemcpyHostToDevice, st));
-  RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc2.p, nrm, bytes, cudaMemcpyHostToDevice, st));
-  RSC_CUDA(ctx, ctx->wl_count.ensure(sizeof(uint32_t) * 4));
-  uint32_t* bounds = ctx->wl_count.as<uint32_t>() + 2;
-  RSC_CUDA(ctx, cudaMemsetAsync(bounds, 0, 2 * sizeof(uint32_t), st));
-  aos_to_soa_kernel<T><<<(unsigned)((c->n_pad + 255) / 256), 256, 0, st>>>(ctx->misc.as<T>(), ctx->misc2.as<T>(), n,
-                                                                            c->n_pad, c->soa, bounds);
+  const int nchunks = (int)((n + kChunkPts - 1) / kChunkPts);
+  // previous work on the compute stream may still read the old coordinates
+  RSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!c->d_bounds || (int)c->chunk_ev.size() < nchunks) {
+    if (c->d_bounds) cudaFree(c->d_bounds);
+    RSC_CUDA(ctx, cudaMalloc(&c->d_bounds, (size_t)(2 * nchunks + 2) * sizeof(uint32_t)));
+    while ((int)c->chunk_ev.size() < nchunks) {
+      cudaEvent_t e;
+      RSC_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      c->chunk_ev.push_back(e);
+    }
+  }
+  c->chunk_pts = kChunkPts;
+  RSC_CUDA(ctx, cudaMemsetAsync(c->d_bounds, 0, (size_t)(2 * nchunks + 2) * sizeof(uint32_t), cs));
+  fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, cs>>>(c->valid, c->enabled, n, words);
   RSC_CUDA(ctx, cudaGetLastError());
-  fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(c->valid, c->enabled, n, words);
-  RSC_CUDA(ctx, cudaGetLastError());
+  const size_t cbytes = (size_t)3 * kChunkPts * sizeof(T);
+  for (int b = 0; b < 2; ++b) RSC_CUDA(ctx, ctx->stage[b].ensure(2 * cbytes));
+  for (int i = 0; i < nchunks; ++i) {
+    const int64_t off = (int64_t)i * kChunkPts;
+    const int64_t cnt = n - off < kChunkPts ? n - off : kChunkPts;
+    T* sx = ctx->stage[i & 1].as<T>();
+    T* sn = sx + 3 * kChunkPts;
+    RSC_CUDA(ctx, cudaMemcpyAsync(sx, xyz + 3 * off, (size_t)3 * cnt * sizeof(T), cudaMemcpyHostToDevice, cs));
+    RSC_CUDA(ctx, cudaMemcpyAsync(sn, nrm + 3 * off, (size_t)3 * cnt * sizeof(T), cudaMemcpyHostToDevice, cs));
+    // bounds layout: [2i, 2i+1] this chunk, [2*nchunks, 2*nchunks+1] whole cloud
+    aos_to_soa_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(sx, sn, off, cnt, c->n_pad, c->soa,
+                                                                        c->d_bounds + 2 * i, c->d_bounds + 2 * nchunks);
+    RSC_CUDA(ctx, cudaGetLastError());
+    RSC_CUDA(ctx, cudaEventRecord(c->chunk_ev[i], cs));
+  }
+  c->pending = true;
+  return RSC_OK;
+}
+
+}  // namespace rsc
+
+namespace rsc {
+int32_t cloud_ready(rsc_cloud* c) {
+  if (!c || !c->pending) return RSC_OK;
+  rsc_ctx* ctx = c->ctx;
+  const int nchunks = (int)((c->n + c->chunk_pts - 1) / c->chunk_pts);
   uint32_t hb[2];
-  RSC_CUDA(ctx, cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
-  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  RSC_CUDA(ctx, cudaMemcpyAsync(hb, c->d_bounds + 2 * nchunks, sizeof(hb), cudaMemcpyDeviceToHost, ctx->copy_stream));
+  RSC_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   float p2, n2;
   memcpy(&p2, &hb[0], 4);
   memcpy(&n2, &hb[1], 4);
   c->pmax = sqrtf(p2) * 1.000001f;
   c->nmax = sqrtf(n2) * 1.000001f;
+  c->pending = false;
   return RSC_OK;
 }
 
@@ -155,6 +195,7 @@ static int32_t cloud_create_impl(rsc_ctx* ctx, const T* xyz, const T* nrm, int64
     return fail_cuda(ctx, e, "cloud_create: cudaMalloc");
   }
   RSC_CUDA(ctx, cudaMemsetAsync(c->soa, 0, (size_t)6 * c->n_pad * sizeof(float), st));
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
   int32_t rc = cloud_upload<T>(c, xyz, nrm);
   if (rc) {
     rsc_cloud_destroy(c);
@@ -188,8 +229,13 @@ int32_t rsc_cloud_update(rsc_cloud* c, const float* xyz, const float* nrm, int64
   if (!c) return RSC_E_ARG;
   if (!xyz || !nrm || n != c->n) return fail(c->ctx, RSC_E_ARG, "cloud_update: the cloud size cannot change");
   RSC_CUDA(c->ctx, cudaSetDevice(c->ctx->device));
-  int32_t rc = cloud_upload<float>(c, xyz, nrm);
+  int32_t rc = cloud_ready(c);  // an earlier upload may still be in flight
   if (rc) return rc;
+  if ((rc = cloud_upload<float>(c, xyz, nrm))) return rc;
+  bool has_subsets = false;
+  for (auto& s : c->subsets) has_subsets = has_subsets || s.soa;
+  if (!has_subsets) return RSC_OK;  // stays asynchronous: the next rsc_score overlaps with the upload
+  if ((rc = cloud_ready(c))) return rc;
   for (size_t i = 0; i < c->subsets.size(); ++i) {  // gathered subset copies follow the new coordinates
     rsc_subset& s = c->subsets[i];
     if (!s.soa) continue;
@@ -203,7 +249,13 @@ int32_t rsc_cloud_update(rsc_cloud* c, const float* xyz, const float* nrm, int64
 
 void rsc_cloud_destroy(rsc_cloud* c) {
   if (!c) return;
-  if (c->ctx) cudaSetDevice(c->ctx->device);
+  if (c->ctx) {
+    cudaSetDevice(c->ctx->device);
+    cudaStreamSynchronize(c->ctx->copy_stream);
+    cudaStreamSynchronize(c->ctx->stream);
+  }
+  for (auto e : c->chunk_ev) cudaEventDestroy(e);
+  if (c->d_bounds) cudaFree(c->d_bounds);
   for (auto& s : c->subsets) {
     if (s.soa) cudaFree(s.soa);
     if (s.enabled) cudaFree(s.enabled);
@@ -220,6 +272,7 @@ int64_t rsc_cloud_size(const rsc_cloud* c) { return c ? c->n : 0; }
 
 int32_t rsc_cloud_set_subset(rsc_cloud* c, int32_t subset_id, const int64_t* idx, int64_t m) {
   if (!c) return RSC_E_ARG;
+  if (int32_t rcr = cloud_ready(c)) return rcr;
   rsc_ctx* ctx = c->ctx;
   if (subset_id < 0 || subset_id > 4095 || !idx || m <= 0) return fail(ctx, RSC_E_ARG, "set_subset: bad arguments");
   for (int64_t j = 0; j < m; ++j)
@@ -258,6 +311,7 @@ int64_t rsc_cloud_subset_size(const rsc_cloud* c, int32_t subset_id) {
 
 int32_t rsc_cloud_get_enabled(rsc_cloud* c, uint64_t* words) {
   if (!c || !words) return RSC_E_ARG;
+  if (int32_t rcr = cloud_ready(c)) return rcr;
   rsc_ctx* ctx = c->ctx;
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)((c->n + 63) / 64) * 8;
@@ -268,6 +322,7 @@ int32_t rsc_cloud_get_enabled(rsc_cloud* c, uint64_t* words) {
 
 int32_t rsc_cloud_set_enabled(rsc_cloud* c, const uint64_t* words) {
   if (!c || !words) return RSC_E_ARG;
+  if (int32_t rcr = cloud_ready(c)) return rcr;
   rsc_ctx* ctx = c->ctx;
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)((c->n + 63) / 64) * 8;
@@ -283,6 +338,7 @@ int32_t rsc_cloud_set_enabled(rsc_cloud* c, const uint64_t* words) {
 
 int32_t rsc_cloud_enable_all(rsc_cloud* c) {
   if (!c) return RSC_E_ARG;
+  if (int32_t rcr = cloud_ready(c)) return rcr;
   rsc_ctx* ctx = c->ctx;
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   RSC_CUDA(ctx, cudaMemcpyAsync(c->enabled, c->valid, (size_t)(c->n_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -295,6 +351,7 @@ int32_t rsc_cloud_enable_all(rsc_cloud* c) {
 
 int64_t rsc_cloud_count_enabled(rsc_cloud* c) {
   if (!c) return -1;
+  if (cloud_ready(c)) return -1;
   rsc_ctx* ctx = c->ctx;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
   if (ctx->misc.ensure(16) != cudaSuccess) return -1;

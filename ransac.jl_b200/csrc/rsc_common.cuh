@@ -78,6 +78,8 @@ struct rsc_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host->device uploads, overlapped with scoring of earlier chunks
+  rsc::DevBuf stage[2];                // double-buffered AoS staging of one upload chunk
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   std::string err;
   rsc_stats stats{};
@@ -109,6 +111,11 @@ struct rsc_cloud {
   uint32_t* valid = nullptr;
   float pmax = 0.f;            // max |p| over the cloud (guard-band scale)
   float nmax = 1.f;            // max |n| over the cloud
+  // chunked upload in flight: chunk i is usable once chunk_ev[i] has fired on the copy stream
+  bool pending = false;
+  int64_t chunk_pts = 0;
+  std::vector<cudaEvent_t> chunk_ev;
+  uint32_t* d_bounds = nullptr;  // per chunk: max |p|^2, max |n|^2 (float bits); last pair = whole cloud
   std::vector<rsc_subset> subsets;
 };
 
@@ -160,7 +167,10 @@ Thresh make_thresh(const rsc_params* p);
 int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th,
                       const rsc_cand* d_cands, int32_t C, int32_t* d_counts_policy, bool want_masks,
                       cudaStream_t st, int32_t* d_counts_valid = nullptr,
-                      int32_t* d_counts_enabled = nullptr, const double* d_trig = nullptr);
+                      int32_t* d_counts_enabled = nullptr, const double* d_trig = nullptr,
+                      const uint32_t* d_bounds = nullptr, bool accumulate = false);
+// waits for a chunked upload to land and finalises the cloud's guard-band scales
+int32_t cloud_ready(rsc_cloud* cloud);
 // refresh the gathered enabled bits of every uploaded subset from the cloud's enabled mask
 int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st);
 

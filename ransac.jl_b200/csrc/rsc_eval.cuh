@@ -100,9 +100,9 @@ __device__ __forceinline__ float eval(const float* r, float px, float py, float 
     float e = fabsf(d) - eps;
     float wn = fmaf(wx, nx, fmaf(wy, ny, wz * nz));
     float an = fmaf(r[4], nx, fmaf(r[5], ny, r[6] * nz));
-    float srho = r[7] * rho;
-    float q = fmaf(r[8], wn, -(srho * an));
-    float nt = fmaf(cosa, rho, -q);
+    // cosa*rho - (c*wn - s*rho*an) = rho*(cosa + s*an) - c*wn
+    float t1 = fmaf(r[7], an, cosa);
+    float nt = fmaf(-r[8], wn, rho * t1);
     return fmax_nan(e, nt);
   }
 }
@@ -162,9 +162,8 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
     const float2 e = add2(abs2(d), bc2(-eps));
     const float2 wn = fma2(wx, NX, fma2(wy, NY, mul2(wz, NZ)));
     const float2 an = fma2(r[4], NX, fma2(r[5], NY, mul2(r[6], NZ)));
-    const float2 srho = mul2(r[7], rho);
-    const float2 q = fma2(r[8], wn, neg2(mul2(srho, an)));
-    const float2 nt = fma2(bc2(cosa), rho, neg2(q));
+    const float2 t1 = fma2(r[7], an, bc2(cosa));
+    const float2 nt = fma2(neg2(r[8]), wn, mul2(rho, t1));
     return max2_nan(e, nt);
   }
 }

@@ -674,6 +674,7 @@ int32_t rsc_fit_batch(rsc_cloud* cloud, const rsc_params* params, const int64_t*
   for (int64_t i = 0; i < (int64_t)S * k; ++i)
     if (idx[i] < 0 || idx[i] >= cloud->n) return fail(ctx, RSC_E_ARG, "fit_batch: index out of range");
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int32_t rcr = cloud_ready(cloud)) return rcr;
   cudaStream_t st = ctx->stream;
   RSC_CUDA(ctx, ctx->misc.ensure((size_t)S * k * 8));
   RSC_CUDA(ctx, cudaMemcpyAsync(ctx->misc.p, idx, (size_t)S * k * 8, cudaMemcpyHostToDevice, st));
@@ -693,6 +694,7 @@ int32_t rsc_sample_fit(rsc_cloud* cloud, const rsc_params* params, uint64_t seed
   const int k = params->drawN;
   if (k < 3 || k > kMaxK) return fail(ctx, RSC_E_ARG, "sample_fit: drawN must be 3..8");
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int32_t rcr = cloud_ready(cloud)) return rcr;
   cudaStream_t st = ctx->stream;
   FitScratch fs;
   int32_t rc = fit_enqueue(ctx, cloud, 2, params, k, nullptr, nullptr, nullptr, S, seed, set0, st, &fs);

@@ -224,6 +224,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   if (cloud->subsets.empty() || !cloud->subsets[0].soa)
     return fail(ctx, RSC_E_STATE, "ransac_run: subset 1 is not uploaded (rsc_cloud_set_subset(cloud, 0, ...))");
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int32_t rcr = cloud_ready(cloud)) return rcr;
   cudaStream_t st = ctx->stream;
   const auto t0 = std::chrono::steady_clock::now();
   rsc_run* run = new rsc_run();

@@ -273,25 +273,46 @@ __global__ void __launch_bounds__(256) fixup_scan_kernel(const __grid_constant__
                                                          const int32_t* __restrict__ slot_of,
                                                          AmbPair* __restrict__ pairs, uint32_t* __restrict__ npairs,
                                                          uint32_t pair_cap) {
+  // queued pairs are collected per CTA in shared memory and appended with ONE global atomic per
+  // flush (a global atomic per pair on a single counter serialises in L2: 4 M pairs took 3 ms)
+  constexpr int kBuf = 1024;
+  __shared__ AmbPair sp[kBuf];
+  __shared__ uint32_t scount, sbase;
   const uint32_t n = min(*a.wl_count, a.wl_cap);
   const int lane = threadIdx.x & 31;
-  const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
-    const GroupTask tk = a.wl[e];
-    const int type = (int)(tk.slot_type >> 28);
-    const int slot = (int)(tk.slot_type & 0x0fffffffu);
-    float r[kRecFields];
+  const uint32_t wpb = blockDim.x >> 5, warps = gridDim.x * wpb;
+  const uint32_t rounds = (n + warps - 1) / warps;
+  if (threadIdx.x == 0) scount = 0;
+  __syncthreads();
+  for (uint32_t rd = 0; rd < rounds; ++rd) {
+    const uint32_t e = rd * warps + blockIdx.x * wpb + (threadIdx.x >> 5);
+    if (e < n) {
+      const GroupTask tk = a.wl[e];
+      const int type = (int)(tk.slot_type >> 28);
+      const int slot = (int)(tk.slot_type & 0x0fffffffu);
+      float r[kRecFields];
 #pragma unroll
-    for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
-    const uint32_t pt = tk.group * 32u + lane;
-    const float m = eval_any(type, r, a.ps.x[pt], a.ps.y[pt], a.ps.z[pt], a.ps.nx[pt], a.ps.ny[pt], a.ps.nz[pt],
-                             a.th.eps[type], a.th.cosa[type]);
-    const bool used = (tk.word >> lane) & 1u;
-    if (!(fabsf(m) > r[kBandField])) {
-      const uint32_t pos = atomicAdd(npairs, 1u);
-      if (pos < pair_cap) pairs[pos] = AmbPair{tk.cand | ((uint32_t)used << 31), pt};
-    } else if ((m < 0.f) != used) {
-      apply_flip(a, tk.cand, type, slot, pt, m < 0.f);  // only if two FP32 evaluations straddled zero
+      for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
+      const uint32_t pt = tk.group * 32u + lane;
+      const float m = eval_any(type, r, a.ps.x[pt], a.ps.y[pt], a.ps.z[pt], a.ps.nx[pt], a.ps.ny[pt], a.ps.nz[pt],
+                               a.th.eps[type], a.th.cosa[type]);
+      const bool used = (tk.word >> lane) & 1u;
+      if (!(fabsf(m) > r[kBandField])) {
+        const uint32_t pos = atomicAdd(&scount, 1u);  // <= 256 per round, flushed below 768
+        sp[pos] = AmbPair{tk.cand | ((uint32_t)used << 31), pt};
+      } else if ((m < 0.f) != used) {
+        apply_flip(a, tk.cand, type, slot, pt, m < 0.f);  // only if two FP32 evaluations straddled zero
+      }
+    }
+    __syncthreads();
+    if (scount > kBuf - 256 || rd + 1 == rounds) {
+      if (threadIdx.x == 0) sbase = atomicAdd(npairs, scount);
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < scount; i += blockDim.x)
+        if (sbase + i < pair_cap) pairs[sbase + i] = sp[i];
+      __syncthreads();
+      if (threadIdx.x == 0) scount = 0;
+      __syncthreads();
     }
   }
 }
@@ -343,12 +364,17 @@ __global__ void select_counts_kernel(const rsc_cand* __restrict__ cands, int C,
 __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restrict__ cands, int C,
                                                        int spc /*slots per column*/, int cslots,
                                                        int ncols, float pmax, float nmax,
+                                                       const uint32_t* __restrict__ d_bounds,
                                                        float* __restrict__ rec, int32_t* __restrict__ orig,
                                                        int32_t* __restrict__ slot_of,
                                                        BlockTab* __restrict__ tab) {
   __shared__ int cnt[RSC_NTYPES], off[RSC_NTYPES], run[RSC_NTYPES], tot[RSC_NTYPES];
   __shared__ int wcnt[RSC_NTYPES][32], woff[RSC_NTYPES][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (d_bounds) {  // scales of the chunk being scored, still on the device (chunked upload)
+    pmax = sqrtf(__uint_as_float(d_bounds[0])) * 1.000001f;
+    nmax = sqrtf(__uint_as_float(d_bounds[1])) * 1.000001f;
+  }
   if (tid < RSC_NTYPES) {
     cnt[tid] = 0;
     run[tid] = 0;
@@ -481,7 +507,7 @@ static int pick_k(int C) { return C >= 3072 ? 4 : (C >= 768 ? 2 : 1); }
 int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th,
                       const rsc_cand* d_cands, int32_t C, int32_t* d_counts_policy, bool want_masks,
                       cudaStream_t st, int32_t* d_counts_valid, int32_t* d_counts_enabled,
-                      const double* d_trig) {
+                      const double* d_trig, const uint32_t* d_bounds, bool accumulate) {
   if (C <= 0) return RSC_OK;
   if (ps.n_pad >= ((int64_t)1 << 32)) return fail(ctx, RSC_E_ARG, "point set too large for one shard (>= 2^32)");
   const int K = pick_k(C);
@@ -502,12 +528,14 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
 
   int32_t* cv = d_counts_valid ? d_counts_valid : ctx->counts.as<int32_t>();
   int32_t* ce = d_counts_enabled ? d_counts_enabled : ctx->counts.as<int32_t>() + C;
-  RSC_CUDA(ctx, cudaMemsetAsync(cv, 0, (size_t)C * sizeof(int32_t), st));
-  RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C * sizeof(int32_t), st));
+  if (!accumulate) {
+    RSC_CUDA(ctx, cudaMemsetAsync(cv, 0, (size_t)C * sizeof(int32_t), st));
+    RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C * sizeof(int32_t), st));
+  }
   RSC_CUDA(ctx, ctx->pairs.ensure(ctx->wl_cap * 8));
   RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.p, 0, 2 * sizeof(uint32_t), st));
 
-  compile_kernel<<<1, 1024, 0, st>>>(d_cands, C, spc, cslots, ncols, cloud->pmax, cloud->nmax,
+  compile_kernel<<<1, 1024, 0, st>>>(d_cands, C, spc, cslots, ncols, cloud->pmax, cloud->nmax, d_bounds,
                                      ctx->rec.as<float>(), ctx->orig.as<int32_t>(),
                                      ctx->slot_of.as<int32_t>(), ctx->blktab.as<BlockTab>());
   RSC_CUDA(ctx, cudaGetLastError());

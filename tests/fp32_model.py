@@ -68,8 +68,8 @@ def margin32(kind, r, P, N, eps, cosa):
     d = fma(h, r[7], -(rho * r[8]))
     e = np.abs(d) - eps
     an = fma(nx, r[4], fma(ny, r[5], nz * r[6]))
-    q = fma(wn, r[8], -((r[7] * rho) * an))
-    return np.maximum(e, fma(rho, cosa, -q))
+    t1 = fma(an, r[7], cosa)
+    return np.maximum(e, fma(wn, -r[8], rho * t1))
 
 
 def margin64(kind, outw, p, P, N, eps, cosa):
