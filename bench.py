@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="override the CPU sample (points)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ransac", default="c2", choices=["none", "c2", "c4"],
+                    help="also time end-to-end ransac() on this scene (single GPU, extra JSON key)")
     return ap.parse_args()
 
 
@@ -315,15 +317,40 @@ def main():
                    "points_per_gpu": n, "candidates": Cn, "parallelism": f"point-range shards x{world}, "
                    "int32 count all-reduce (NCCL)" if world > 1 else "single GPU",
                    "l2": "inputs (403 MB of points per pass) exceed the 126 MB L2; no flush needed"},
-        "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks, "roofline": roofline,
+        "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks, "roofline": roofline,
         "fp64_guard_pairs_per_step": int(guard),
     }
+    if args.ransac != "none" and world == 1:
+        out["ransac"] = time_ransac(R, args.ransac, local)
     if not args.no_cpu:
-        # ~10-20 s of CPU work: 512 candidates (every 8th) x the first 8 Mi points of the same workload
-        out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or (8 << 20), ncand=512)
+        # ~10 s of CPU work: 512 candidates (every 8th) x all points of rank 0's shard of the same workload
+        out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or len(sc.vertices), ncand=512)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_ransac(R, which, device):
+    """End-to-end ransac(pc, params, true) wall time (host call to result on the host), best of 3."""
+    from ransac_jl_b200 import scenes
+
+    if which == "c2":
+        sc, r = scenes.scene_c2(), 32
+        it = {"tau": len(sc.vertices) // 100, "minsubsetN": 4096, "itermax": 200}
+    else:
+        sc, r = scenes.scene_cad(), 32
+        it = {"tau": len(sc.vertices) // 1000, "minsubsetN": 8192, "itermax": 400}
+    params = R.ransacparameters(iteration=it)
+    pc = R.RANSACCloud(sc.vertices, sc.normals, r, device=device)
+    R.ransac(pc, R.ransacparameters(iteration=dict(it, itermax=2)), True, seed=1)
+    best, ex = None, []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        ex, _ = R.ransac(pc, params, True, seed=2024)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"scene": which, "points": int(len(sc.vertices)), "subsets": r, "iteration": it, "seconds": best,
+            "n_shapes": len(ex), "points_extracted": int(sum(len(e.inpoints) for e in ex))}
 
 
 def _last_kernel(pc):
