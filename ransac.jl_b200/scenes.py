@@ -146,11 +146,12 @@ def make_cylinder(rng, box=100.0, rmin=3.0, rmax=10.0, lmin=20.0, lmax=60.0):
                      float(2 * math.pi * R * L), {"L": L, "h0": h0})
 
 
-def make_cone(rng, box=100.0):
+def make_cone(rng, box=100.0, hmin=25.0, hmax=45.0):
     a = _rand_unit(rng)
     apex = rng.uniform(-box / 2, box / 2, 3)
     half = math.radians(rng.uniform(10, 35))
-    h0, h1 = rng.uniform(5, 10), rng.uniform(25, 45)
+    h1 = rng.uniform(hmin, hmax)
+    h0 = h1 * rng.uniform(0.15, 0.3)
     area = math.pi * math.tan(half) / math.cos(half) * (h1 * h1 - h0 * h0)
     return Primitive("cone", FittedCone(apex, a, 2 * half, bool(rng.integers(2))), float(h1), float(area),
                      {"h0": h0, "h1": h1})
@@ -191,11 +192,14 @@ def scene_c3(n: int = 16 << 20, seed: int = 3) -> Scene:
 
 
 def scene_cad(n: int = 10_000_000, seed: int = 4, nprims: int = 200) -> Scene:
-    """c4: CAD-like, many small primitives (sizes log-uniform 1-10 % of the box), 0.5 % noise, 5 % outliers."""
+    """c4: CAD-like, 200 primitives of mixed type: 180 small ones (sizes log-uniform 1-10 % of the
+    box) on 20 larger base shapes (10-40 %), area-weighted point share, 0.5 % noise, 5 % outliers.
+    (With the reference's root-cell sampler, Q1, only the larger shapes reach the detection
+    probability; the small ones are what the octree-level sampler of SURVEY 8(f) is for.)"""
     rng = np.random.default_rng(seed)
     prims = []
     for i in range(nprims):
-        s = 100.0 * 10 ** rng.uniform(-2, -1)
+        s = 100.0 * (10 ** rng.uniform(-1, -0.4) if i < 20 else 10 ** rng.uniform(-2, -1))
         k = i % 4
         if k == 0:
             prims.append(make_plane(rng, smin=s, smax=2 * s))
@@ -204,7 +208,7 @@ def scene_cad(n: int = 10_000_000, seed: int = 4, nprims: int = 200) -> Scene:
         elif k == 2:
             prims.append(make_cylinder(rng, rmin=s / 4, rmax=s / 2, lmin=s, lmax=2 * s))
         else:
-            prims.append(make_cone(rng))
+            prims.append(make_cone(rng, hmin=s, hmax=2 * s))
     return build_scene(rng, prims, n, 0.005, 1.0, 0.05)
 
 
