@@ -320,6 +320,15 @@ def main():
         "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks, "roofline": roofline,
         "fp64_guard_pairs_per_step": int(guard),
     }
+    # K4 (refit over the whole shard, HBM bound): mask kernel time -> GB/s of algorithmic bytes
+    try:
+        ex = R.refit(cands[0], pc, params)
+        st4 = pc.ctx.stats()
+        out["refit"] = {"kernel": "rsc::extract_mask_kernel", "points": n, "inliers": int(len(ex.inpoints)),
+                        "kernel_ms": st4.refit_mask_ms, "achieved_gbs": 24.125 * n / (st4.refit_mask_ms * 1e-3) / 1e9,
+                        "peak_gbs": peaks.get("hbm_gbs"), "bound": "hbm", "algorithmic_bytes_per_point": 24.125}
+    except Exception as e:  # informational key only
+        out["refit"] = {"error": repr(e)}
     if args.ransac != "none" and world == 1:
         out["ransac"] = time_ransac(R, args.ransac, local)
     if not args.no_cpu:

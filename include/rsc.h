@@ -104,6 +104,7 @@ typedef struct rsc_stats {
   int64_t score_launches; /* launches of the tiled score kernel */
   double score_ms;        /* CUDA-event time of the last score call's kernels */
   double last_kernel_ms;  /* CUDA-event time of the last tiled score kernel launch alone */
+  double refit_mask_ms;   /* CUDA-event time of the last refit's compatibility-mask kernel (K4, HBM bound) */
 } rsc_stats;
 
 /* ---- context ----------------------------------------------------------------------- */

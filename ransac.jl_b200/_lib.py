@@ -55,6 +55,7 @@ class rsc_stats(C.Structure):
         ("score_launches", C.c_int64),
         ("score_ms", C.c_double),
         ("last_kernel_ms", C.c_double),
+        ("refit_mask_ms", C.c_double),
     ]
 
 

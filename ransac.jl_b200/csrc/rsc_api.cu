@@ -93,7 +93,8 @@ int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-      cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess) {
+      cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess ||
+      cudaEventCreate(&ctx->evr0) != cudaSuccess || cudaEventCreate(&ctx->evr1) != cudaSuccess) {
     delete ctx;
     return RSC_E_CUDA;
   }
@@ -116,6 +117,8 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
   cudaEventDestroy(ctx->ev1);
   cudaEventDestroy(ctx->evk0);
   cudaEventDestroy(ctx->evk1);
+  cudaEventDestroy(ctx->evr0);
+  cudaEventDestroy(ctx->evr1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -302,6 +305,10 @@ int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_
   unsigned long long total = 0;
   RSC_CUDA(ctx, cudaMemcpyAsync(&total, ctx->misc2.p, sizeof(total), cudaMemcpyDeviceToHost, st));
   RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->evr0, ctx->evr1) == cudaSuccess) ctx->stats.refit_mask_ms = ms;
+  }
   *out_n = (int64_t)total;
   int64_t* d_out = nullptr;
   if (out_idx && total) {

@@ -80,7 +80,7 @@ struct rsc_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // host->device uploads, overlapped with scoring of earlier chunks
   rsc::DevBuf stage[2];                // double-buffered AoS staging of one upload chunk
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   std::string err;
   rsc_stats stats{};
   // scratch of the score path

@@ -181,8 +181,10 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
     RSC_CUDA(ctx, cudaMemsetAsync(a.inl, 0, (size_t)words * 4, st));
   }
   a.block0 = b0;
+  RSC_CUDA(ctx, cudaEventRecord(ctx->evr0, st));
   extract_mask_kernel<<<(unsigned)(b1 - b0), kExThreads, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
+  RSC_CUDA(ctx, cudaEventRecord(ctx->evr1, st));
   if (sharded && ctx->allreduce(ctx->allreduce_user, a.inl, words, (void*)st))
     return fail(ctx, RSC_E_NCCL, "refit: all-reduce callback failed");
   block_count_kernel<<<(nblocks + 255) / 256, 256, 0, st>>>(a.inl, words, block_counts, nblocks);

@@ -95,7 +95,7 @@ __device__ __forceinline__ void issue_subtile(const PointSet& ps, int sub, float
 // K candidates per thread; for even K they are evaluated as K/2 packed pairs (FFMA2 path).
 // Every WARP streams the CTA row's points through its own double-buffered shared-memory stages
 // (TMA bulk copies signalled on warp-private mbarriers): there is no CTA-wide barrier in the loop.
-template <int T, int K>
+template <int T, int K, int UN>
 __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float* wstage, uint64_t* wbar) {
   constexpr int NR = RecN<T>::n;
   constexpr bool kPacked = (K % 2 == 0);
@@ -148,7 +148,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
         mabs[k] = __int_as_float(0x7f800000);
       }
       const float* gx = sx + g * 32;
-#pragma unroll 1
+#pragma unroll UN
       for (int i4 = 0; i4 < 32; i4 += 4) {
         // 6 broadcast 128-bit loads = 4 points
         const float4 X = *reinterpret_cast<const float4*>(gx + i4);
@@ -212,7 +212,7 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
   }
 }
 
-template <int K, int MINB>
+template <int K, int MINB, int U>
 __global__ void __launch_bounds__(kThreads, MINB) score_kernel(const __grid_constant__ ScoreArgs a) {
   __shared__ __align__(128) float stages[kThreads / 32][kStages * kSubFloats];
   __shared__ __align__(8) uint64_t bars[kThreads / 32][kStages];
@@ -227,16 +227,16 @@ __global__ void __launch_bounds__(kThreads, MINB) score_kernel(const __grid_cons
   __syncwarp();
   switch (bt.type) {
     case RSC_PLANE:
-      score_body<RSC_PLANE, K>(a, bt.slot0, stages[warp], bars[warp]);
+      score_body<RSC_PLANE, K, U>(a, bt.slot0, stages[warp], bars[warp]);
       break;
     case RSC_SPHERE:
-      score_body<RSC_SPHERE, K>(a, bt.slot0, stages[warp], bars[warp]);
+      score_body<RSC_SPHERE, K, U>(a, bt.slot0, stages[warp], bars[warp]);
       break;
     case RSC_CYLINDER:
-      score_body<RSC_CYLINDER, K>(a, bt.slot0, stages[warp], bars[warp]);
+      score_body<RSC_CYLINDER, K, U>(a, bt.slot0, stages[warp], bars[warp]);
       break;
     default:
-      score_body<RSC_CONE, K>(a, bt.slot0, stages[warp], bars[warp]);
+      score_body<RSC_CONE, K, U>(a, bt.slot0, stages[warp], bars[warp]);
       break;
   }
 }
@@ -559,6 +559,7 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   const int real_cols = (C + spc - 1) / spc;
   static const int waves = getenv("RSC_WAVES") ? atoi(getenv("RSC_WAVES")) : 32;
   static const int minb = getenv("RSC_MINB") ? atoi(getenv("RSC_MINB")) : 4;
+  static const int unroll = getenv("RSC_UNROLL") ? atoi(getenv("RSC_UNROLL")) : 1;
   const long target = (long)ctx->sm_count * 4 * waves;
   long chunks = (target + real_cols - 1) / real_cols;
   if (chunks > nsubs) chunks = nsubs;
@@ -571,18 +572,18 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
   switch (K) {
     case 4:
-      if (minb == 5)
-        score_kernel<4, 5><<<grid, kThreads, 0, st>>>(a);
-      else if (minb == 6)
-        score_kernel<4, 6><<<grid, kThreads, 0, st>>>(a);
+      if (unroll == 2)
+        score_kernel<4, 4, 2><<<grid, kThreads, 0, st>>>(a);
+      else if (minb == 3)
+        score_kernel<4, 3, 1><<<grid, kThreads, 0, st>>>(a);
       else
-        score_kernel<4, 4><<<grid, kThreads, 0, st>>>(a);
+        score_kernel<4, 4, 1><<<grid, kThreads, 0, st>>>(a);
       break;
     case 2:
-      score_kernel<2, 4><<<grid, kThreads, 0, st>>>(a);
+      score_kernel<2, 4, 1><<<grid, kThreads, 0, st>>>(a);
       break;
     default:
-      score_kernel<1, 4><<<grid, kThreads, 0, st>>>(a);
+      score_kernel<1, 4, 1><<<grid, kThreads, 0, st>>>(a);
       break;
   }
   RSC_CUDA(ctx, cudaGetLastError());

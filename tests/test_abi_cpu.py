@@ -33,7 +33,7 @@ def test_pod_layouts():
     assert C.sizeof(R._lib.rsc_cand) == 64
     assert R._lib.rsc_cand.p.offset == 8
     assert C.sizeof(R._lib.rsc_params) == 160
-    assert C.sizeof(R._lib.rsc_stats) == 56
+    assert C.sizeof(R._lib.rsc_stats) == 64
 
 
 def test_default_params_pod_matches_reference_defaults():
