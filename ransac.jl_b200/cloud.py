@@ -44,6 +44,7 @@ class RANSACCloud:
         device: int = 0,
         seed: int = 1234,
         shard: Optional[tuple] = None,
+        ctx: Optional[Context] = None,
     ):
         v = np.asarray(vertices)
         n = np.asarray(normals)
@@ -62,7 +63,7 @@ class RANSACCloud:
             self.subsets = makesubsets(self.size, int(subsets), np.random.default_rng(seed))
         else:
             self.subsets = [np.ascontiguousarray(s, dtype=np.int64) for s in subsets]
-        self.ctx = Context.get(device)
+        self.ctx = ctx if ctx is not None else Context.get(device)
         self._h = C.c_void_p()
         self.global_offset, self.n_global = 0, self.size
         if shard is not None:

@@ -3,6 +3,7 @@
 // rsc_extract.cu, rsc_fit.cu, rsc_cloud.cu.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -90,6 +91,10 @@ int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
   rsc_ctx* ctx = new rsc_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("RSC_WL_CAP")) {  // test hook: start with a tiny guard-band queue
+    const long v = atol(e);
+    if (v > 0) ctx->wl_cap = (size_t)v;
+  }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||

@@ -71,7 +71,8 @@ def sample_fit(pc: RANSACCloud, params, seed: int, set0: int, S: int):
 
 
 # ---- scoring (fitting.jl:45,181-190; shapes/*.jl scorecandidate) -------------------------------
-def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: int, params, want_masks=False):
+def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: int, params, want_masks=False,
+                 compat_flags=None):
     """Raw device scoring: inlier counts (and packed masks) of candidates against subset `subsetID`
     (0-based; -1 = whole cloud)."""
     Cn = len(candidates)
@@ -84,7 +85,7 @@ def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: i
     else:
         M = pc.size
     arr = pack_cands(candidates)
-    cp = to_c(params)
+    cp = to_c(params, compat_flags)
     masks = np.zeros((Cn, (M + 31) // 32), dtype=np.uint32) if want_masks else None
     pc.ctx.check(lib.rsc_score(pc.handle, C.byref(cp), arr, Cn, subsetID, counts.ctypes.data, masks.ctypes.data if want_masks else None))
     return counts, masks
