@@ -241,19 +241,22 @@ __device__ inline void compile_record(const rsc_cand& c, float pmax, float nmax,
       break;
     }
     default: {
+      // project2cone (cone.jl:68-85) only uses the DIRECTION of the axis (every cross product with
+      // it is normalised), so the closed form works on the unit axis; a zero axis matches nothing.
       double sg = c.outwards ? 1.0 : -1.0;
-      if (!finite) {
+      const double an = sqrt(c.p[3] * c.p[3] + c.p[4] * c.p[4] + c.p[5] * c.p[5]);
+      const double ia = 1.0 / an;
+      if (!finite || !(an > 0.0) || !isfinite(ia)) {
         r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 0.f, r[8] = 1.f, r[kBandField] = 1.f;
         return;
       }
       r[0] = (float)sg;
       r[1] = (float)(-sg * c.p[0]), r[2] = (float)(-sg * c.p[1]), r[3] = (float)(-sg * c.p[2]);
-      r[4] = (float)c.p[3], r[5] = (float)c.p[4], r[6] = (float)c.p[5];
+      r[4] = (float)(c.p[3] * ia), r[5] = (float)(c.p[4] * ia), r[6] = (float)(c.p[5] * ia);
       r[7] = (float)(sg * sin(0.5 * c.p[6]));
       r[8] = (float)cos(0.5 * c.p[6]);
       double cn = sqrt(c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2]);
-      double a2 = c.p[3] * c.p[3] + c.p[4] * c.p[4] + c.p[5] * c.p[5];
-      L = (P + cn + 1.0) * (a2 > 1.0 ? a2 : 1.0) * nm;
+      L = (P + cn + 1.0) * nm;
       break;
     }
   }

@@ -35,9 +35,9 @@ def record(kind, outw, p, pmax, nmax):
         a2 = float(np.dot(p[0:3], p[0:3]))
         L = (pmax + np.linalg.norm(p[3:6]) + abs(p[6]) + 1) * max(a2, 1.0) * nm
     else:
-        r = [sg, *(-sg * np.array(p[0:3])), *p[3:6], sg * math.sin(p[6] / 2), math.cos(p[6] / 2)]
-        a2 = float(np.dot(p[3:6], p[3:6]))
-        L = (pmax + np.linalg.norm(p[0:3]) + 1) * max(a2, 1.0) * nm
+        ax = np.array(p[3:6]) / np.linalg.norm(p[3:6])  # the reference's cone test only uses the axis direction
+        r = [sg, *(-sg * np.array(p[0:3])), *ax, sg * math.sin(p[6] / 2), math.cos(p[6] / 2)]
+        L = (pmax + np.linalg.norm(p[0:3]) + 1) * nm
     return [f32(x) for x in r], KAPPA[kind] * U * L
 
 
@@ -88,7 +88,7 @@ def margin64(kind, outw, p, P, N, eps, cosa):
         a, c, R = p[0:3], p[3:6], p[6]
         v = P - c; h = v @ a; w = v - h[:, None] * a; rho = np.linalg.norm(w, axis=1)
         return np.maximum(np.abs(rho - R) - eps, cosa * rho - sg * np.einsum("ij,ij->i", w, N))
-    apex, a, op = p[0:3], p[3:6], p[6]
+    apex, a, op = p[0:3], p[3:6] / np.linalg.norm(p[3:6]), p[6]
     v = P - apex; h = v @ a; w = v - h[:, None] * a; rho = np.linalg.norm(w, axis=1)
     c, s = math.cos(op / 2), math.sin(op / 2)
     d = h * s - rho * c
