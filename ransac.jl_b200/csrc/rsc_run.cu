@@ -19,6 +19,8 @@
 // (counter-based Philox) and scores only its point range; per-candidate counts and the refit's
 // inlier-mask words are summed across ranks through the all-reduce callback (NCCL on the host side).
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -245,6 +247,13 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta;
   int64_t n_enabled = rsc_cloud_count_enabled(cloud);
   int64_t counters[3] = {0, 0, 0};  // lengthC, allcand, nofminset (iterations.jl:70)
+  const bool trace = getenv("RSC_TRACE") != nullptr;
+  double t_fit = 0, t_score = 0, t_extract = 0, t_k5 = 0;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double>(b - a).count();
+  };
+
   auto cleanup = [&]() {
     store.release();
     newcnt.release(), hostio.release(), olden.release(), nscratch.release(), nvalid.release(), nmeta.release();
@@ -264,6 +273,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   for (int k = 1; k <= p->itermax; ++k) {
     if (n_enabled < p->tau) break;  // iterations.jl:75
     run->iterations = k;
+    const auto tk0 = now();
     // ---- K1: minsubsetN minimal sets -> candidates (device, compacted in reference order) ----
     FitScratch fs;
     if ((rc = fit_enqueue(ctx, cloud, 2, p, p->drawN, nullptr, nullptr, nullptr, S, seed, (uint64_t)(k - 1) * S, st, &fs)))
@@ -273,6 +283,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     RUN_CUDA(cudaStreamSynchronize(st));
     const int n_new = (int)n_new_;
     counters[1] += n_new;
+    const auto tk1 = now();
+    t_fit += secs(tk0, tk1);
     if (n_new > 0) {
       RUN_CUDA(store.reserve((size_t)store.n + n_new, st));
       rsc_cand* dst = store.cands[store.cur].as<rsc_cand>() + store.n;
@@ -308,6 +320,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
       RUN_CUDA(cudaGetLastError());
       RUN_CUDA(cudaMemcpyAsync(best, hostio.p, 16, cudaMemcpyDeviceToHost, st));
       RUN_CUDA(cudaStreamSynchronize(st));
+      const auto tk2 = now();
+      t_score += secs(tk1, tk2);
       if (best[0] >= 0) {
         double E;
         rsc_estimate_score(sub.m, N, best[1], nullptr, nullptr, &E);
@@ -340,6 +354,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           run->shapes.push_back(shape);
           run->inpoints.push_back(std::move(idx));
           n_enabled -= (int64_t)total;
+          const auto tk3 = now();
+          t_extract += secs(tk2, tk3);
           // ---- K5: drop the best and every candidate compatible with a newly disabled subset point ----
           const int nst = store.n;
           // scratch layout: [wcnt: swords u32][woff: swords u64][wtot u64][keep: nst u32][koff: nst u64][ktot u64]
@@ -401,6 +417,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           RUN_CUDA(cudaStreamSynchronize(st));
           store.cur = nxt;
           store.n = (int)kept;
+          t_k5 += secs(tk3, now());
         }
       }
     }
@@ -409,6 +426,9 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   }
 done:
   cudaStreamSynchronize(st);
+  if (trace)
+    fprintf(stderr, "[rsc_ransac_run] iterations %d shapes %zu | sample+fit %.1f ms, score+argmax %.1f ms, refit+extract %.1f ms, invalidate+compact %.1f ms\n",
+            run->iterations, run->shapes.size(), 1e3 * t_fit, 1e3 * t_score, 1e3 * t_extract, 1e3 * t_k5);
   cleanup();
   if (rc) {
     delete run;
