@@ -117,6 +117,9 @@ struct rsc_cloud {
   std::vector<cudaEvent_t> chunk_ev;
   uint32_t* d_bounds = nullptr;  // per chunk: max |p|^2, max |n|^2 (float bits); last pair = whole cloud
   std::vector<rsc_subset> subsets;
+  // rank/select index over `enabled` for the sampler (rsc_fit.cu); rebuilt lazily after any change
+  rsc::DevBuf selbuf;
+  bool sel_valid = false;
 };
 
 namespace rsc {

@@ -206,7 +206,10 @@ int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cuda
   extract_write_kernel<<<nblocks, kExThreads, 0, st>>>(inl, offsets, n_pad, cloud->global_offset, d_out,
                                                        disable ? cloud->enabled : nullptr);
   RSC_CUDA(ctx, cudaGetLastError());
-  if (disable) return refresh_subsets_enabled(cloud, st);
+  if (disable) {
+    cloud->sel_valid = false;
+    return refresh_subsets_enabled(cloud, st);
+  }
   return RSC_OK;
 }
 

@@ -309,29 +309,6 @@ __device__ bool fit_cone(const D3* p, const D3* n, const FitParams& f, rsc_cand*
   return true;
 }
 
-__device__ inline void fit_all(const D3* p, const D3* n, const FitParams& f, rsc_cand* dense, uint32_t* flags) {
-  for (int t = 0; t < f.ntypes; ++t) {
-    rsc_cand c;
-    bool ok = false;
-    switch (f.types[t]) {
-      case RSC_PLANE:
-        ok = fit_plane(p, n, f, &c);
-        break;
-      case RSC_SPHERE:
-        ok = fit_sphere(p, n, f, &c);
-        break;
-      case RSC_CYLINDER:
-        ok = fit_cylinder(p, n, f, &c);
-        break;
-      case RSC_CONE:
-        ok = fit_cone(p, n, f, &c);
-        break;
-    }
-    flags[t] = ok ? 1u : 0u;
-    if (ok) dense[t] = c;
-  }
-}
-
 // ---- Philox4x32-10 -------------------------------------------------------------------------------
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                            uint32_t* o) {
@@ -357,7 +334,7 @@ struct SetStream {
   __device__ uint64_t below(uint64_t n) { return __umul64hi(next(), n); }  // rand(1:n) - 1
 };
 
-constexpr int kSelWords = 32;  // words per rank/select block (1024 points)
+constexpr int kSelWords = 8;  // words per rank/select block (256 points): two 128-bit loads per select
 
 __global__ void block_popc_kernel(const uint32_t* __restrict__ en, int64_t words, uint32_t* __restrict__ out, int nblk) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -370,24 +347,26 @@ __global__ void block_popc_kernel(const uint32_t* __restrict__ en, int64_t words
   out[b] = s;
 }
 
-// index of the j-th (0-based) enabled point
+// index of the j-th (0-based) enabled point: binary search over the block offsets, then the
+// block's 8 mask words in two 128-bit loads (n_pad is a multiple of 512, so blocks are never ragged)
 __device__ inline int64_t select_enabled(const uint32_t* en, int64_t words, const unsigned long long* boff, int nblk,
                                          uint64_t j) {
   int lo = 0, hi = nblk - 1;  // last block whose offset <= j
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (boff[mid] <= j)
+    if (__ldg(boff + mid) <= j)
       lo = mid;
     else
       hi = mid - 1;
   }
-  uint32_t rem = (uint32_t)(j - boff[lo]);
-  for (int w = 0; w < kSelWords; ++w) {
-    const int64_t i = (int64_t)lo * kSelWords + w;
-    if (i >= words) break;
-    const uint32_t x = en[i];
-    const uint32_t c = __popc(x);
-    if (rem < c) return i * 32 + __fns(x, 0, rem + 1);
+  uint32_t rem = (uint32_t)(j - __ldg(boff + lo));
+  const uint4* wp = reinterpret_cast<const uint4*>(en + (int64_t)lo * kSelWords);
+  const uint4 A = __ldg(wp), B = __ldg(wp + 1);
+  const uint32_t w[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+#pragma unroll
+  for (int q = 0; q < kSelWords; ++q) {
+    const uint32_t c = __popc(w[q]);
+    if (rem < c) return ((int64_t)lo * kSelWords + q) * 32 + __fns(w[q], 0, rem + 1);
     rem -= c;
   }
   return -1;
@@ -400,63 +379,86 @@ struct GatherSrc {
   const double* N;
 };
 
-// mode 0: explicit coordinates; mode 1: explicit indices; mode 2: Philox sampling
-__global__ void __launch_bounds__(128) fit_kernel(int mode, GatherSrc src, const int64_t* __restrict__ idx_in, int S,
-                                                  FitParams f, uint64_t seed, uint64_t set0, int64_t n_points,
-                                                  const uint32_t* __restrict__ enabled, int64_t words,
-                                                  const unsigned long long* __restrict__ boff, int nblk,
-                                                  const unsigned long long* __restrict__ n_enabled,
-                                                  rsc_cand* __restrict__ dense, uint32_t* __restrict__ flags,
-                                                  int64_t* __restrict__ idx_out) {
+// samplepointcloud4! on the root cell: one thread per minimal set, writes its k indices (-1 = failed)
+__global__ void __launch_bounds__(128) sample_kernel(int S, int k, uint64_t seed, uint64_t set0, int64_t n_points,
+                                                     const uint32_t* __restrict__ enabled, int64_t words,
+                                                     const unsigned long long* __restrict__ boff, int nblk,
+                                                     const unsigned long long* __restrict__ n_enabled,
+                                                     int64_t* __restrict__ idx_out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
-  D3 p[kMaxK], n[kMaxK];
-  uint32_t* fl = flags + (size_t)s * f.ntypes;
-  for (int t = 0; t < f.ntypes; ++t) fl[t] = 0;
   int64_t id[kMaxK];
   bool ok = true;
-  if (mode == 2) {
-    SetStream rng(seed, set0 + (uint64_t)s);
-    const uint64_t ne = *n_enabled;
-    int64_t r1 = (int64_t)rng.below((uint64_t)n_points);
-    if (ne == 0) {
-      ok = false;
-    } else {
-      while (!((enabled[r1 >> 5] >> (r1 & 31)) & 1u)) r1 = (int64_t)rng.below((uint64_t)n_points);
-    }
-    if (ok && ne < (uint64_t)f.k) ok = false;  // (false, 0): too few enabled points in the cell
-    if (ok) {
-      id[0] = r1;
-      for (int q = 1; q < f.k; ++q) {
-        int64_t c = select_enabled(enabled, words, boff, nblk, rng.below(ne));
-        if (c == id[0]) c = select_enabled(enabled, words, boff, nblk, rng.below(ne));  // "try once more"
-        id[q] = c;
-      }
-      for (int i = 1; i < f.k; ++i)
-        for (int j = 0; j < i; ++j)
-          if (id[i] == id[j]) ok = false;  // (false, 1): duplicate index
-    }
-    if (idx_out)
-      for (int q = 0; q < f.k; ++q) idx_out[(size_t)s * f.k + q] = ok ? id[q] : -1;
-  } else if (mode == 1) {
-    for (int q = 0; q < f.k; ++q) id[q] = idx_in[(size_t)s * f.k + q];
+  SetStream rng(seed, set0 + (uint64_t)s);
+  const uint64_t ne = *n_enabled;
+  int64_t r1 = (int64_t)rng.below((uint64_t)n_points);
+  if (ne == 0) {
+    ok = false;
+  } else {
+    while (!((__ldg(enabled + (r1 >> 5)) >> (r1 & 31)) & 1u)) r1 = (int64_t)rng.below((uint64_t)n_points);
   }
-  if (!ok) return;
-  if (mode == 0) {
+  if (ok && ne < (uint64_t)k) ok = false;  // (false, 0): too few enabled points in the cell
+  if (ok) {
+    id[0] = r1;
+    for (int q = 1; q < k; ++q) {
+      int64_t c = select_enabled(enabled, words, boff, nblk, rng.below(ne));
+      if (c == id[0]) c = select_enabled(enabled, words, boff, nblk, rng.below(ne));  // "try once more"
+      id[q] = c;
+    }
+    for (int i = 1; i < k; ++i)
+      for (int j = 0; j < i; ++j)
+        if (id[i] == id[j]) ok = false;  // (false, 1): duplicate index
+  }
+  for (int q = 0; q < k; ++q) idx_out[(size_t)s * k + q] = ok ? id[q] : -1;
+}
+
+// one thread per (minimal set, shape type): blockIdx.y = position in shape_types, so a warp runs
+// one fit routine.  Points come from explicit coordinates (src.soa == nullptr) or from the cloud
+// by index; sets whose first index is negative (failed samples) yield nothing.
+__global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* __restrict__ idx, int S, FitParams f,
+                                                  rsc_cand* __restrict__ dense, uint32_t* __restrict__ flags) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.y;
+  if (s >= S) return;
+  const size_t slot = (size_t)s * f.ntypes + t;
+  flags[slot] = 0;
+  D3 p[kMaxK], n[kMaxK];
+  if (src.soa) {
+    if (idx[(size_t)s * f.k] < 0) return;
+    for (int q = 0; q < f.k; ++q) {
+      const int64_t i = idx[(size_t)s * f.k + q];
+      p[q] = D3{(double)__ldg(src.soa + i), (double)__ldg(src.soa + src.n_pad + i), (double)__ldg(src.soa + 2 * src.n_pad + i)};
+      n[q] = D3{(double)__ldg(src.soa + 3 * src.n_pad + i), (double)__ldg(src.soa + 4 * src.n_pad + i),
+                (double)__ldg(src.soa + 5 * src.n_pad + i)};
+    }
+  } else {
     for (int q = 0; q < f.k; ++q) {
       const double* a = src.P + ((size_t)s * f.k + q) * 3;
       const double* b = src.N + ((size_t)s * f.k + q) * 3;
       p[q] = D3{a[0], a[1], a[2]};
       n[q] = D3{b[0], b[1], b[2]};
     }
-  } else {
-    for (int q = 0; q < f.k; ++q) {
-      const int64_t i = id[q];
-      p[q] = D3{(double)src.soa[i], (double)src.soa[src.n_pad + i], (double)src.soa[2 * src.n_pad + i]};
-      n[q] = D3{(double)src.soa[3 * src.n_pad + i], (double)src.soa[4 * src.n_pad + i], (double)src.soa[5 * src.n_pad + i]};
-    }
   }
-  fit_all(p, n, f, dense + (size_t)s * f.ntypes, fl);
+  rsc_cand c;
+  bool ok = false;
+  switch (f.types[t]) {
+    case RSC_PLANE:
+      ok = fit_plane(p, n, f, &c);
+      break;
+    case RSC_SPHERE:
+      ok = fit_sphere(p, n, f, &c);
+      break;
+    case RSC_CYLINDER:
+      ok = fit_cylinder(p, n, f, &c);
+      break;
+    case RSC_CONE:
+      ok = fit_cone(p, n, f, &c);
+      break;
+  }
+  if (ok) {
+    dense[slot] = c;
+    flags[slot] = 1u;
+  }
 }
 
 // order-preserving compaction of the dense candidates
@@ -528,21 +530,24 @@ static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
   return RSC_OK;
 }
 
-// rank/select index over the enabled mask (rebuilt whenever it is needed; cheap)
+// rank/select index over the enabled mask; cached on the cloud until the mask changes
 int32_t build_select_index(rsc_cloud* cloud, cudaStream_t st, unsigned long long** boff, int* nblk,
                            unsigned long long** n_enabled) {
   rsc_ctx* ctx = cloud->ctx;
   const int64_t words = cloud->n_pad / 32;
   const int nb = (int)((words + kSelWords - 1) / kSelWords);
-  RSC_CUDA(ctx, ctx->selbuf.ensure((size_t)nb * (4 + 8) + 64));
-  char* b = ctx->selbuf.as<char>();
+  RSC_CUDA(ctx, cloud->selbuf.ensure((size_t)nb * (4 + 8) + 64));
+  char* b = cloud->selbuf.as<char>();
   unsigned long long* offs = (unsigned long long*)b;
   unsigned long long* total = offs + nb;
   uint32_t* cnt = (uint32_t*)(total + 1);
-  block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(cloud->enabled, words, cnt, nb);
-  RSC_CUDA(ctx, cudaGetLastError());
-  scan_u32_kernel<<<1, 1024, 0, st>>>(cnt, nb, offs, total);
-  RSC_CUDA(ctx, cudaGetLastError());
+  if (!cloud->sel_valid) {
+    block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(cloud->enabled, words, cnt, nb);
+    RSC_CUDA(ctx, cudaGetLastError());
+    scan_u32_kernel<<<1, 1024, 0, st>>>(cnt, nb, offs, total);
+    RSC_CUDA(ctx, cudaGetLastError());
+    cloud->sel_valid = true;
+  }
   *boff = offs;
   *nblk = nb;
   *n_enabled = total;
@@ -607,9 +612,14 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
   }
   if (mode == 2 && (rc = build_select_index(cloud, st, &boff, &nblk, &nen))) return rc;
   if (slots > 0) {
-    fit_kernel<<<(S + 127) / 128, 128, 0, st>>>(mode, src, d_idx, S, f, seed, set0, cloud ? cloud->n : 0,
-                                                cloud ? cloud->enabled : nullptr, cloud ? cloud->n_pad / 32 : 0, boff,
-                                                nblk, nen, fs->dense, fs->flags, mode == 2 ? fs->idx : nullptr);
+    const int64_t* use_idx = d_idx;
+    if (mode == 2) {
+      sample_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, k, seed, set0, cloud->n, cloud->enabled, cloud->n_pad / 32, boff, nblk,
+                                                     nen, fs->idx);
+      RSC_CUDA(ctx, cudaGetLastError());
+      use_idx = fs->idx;
+    }
+    fit_kernel<<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->flags);
     RSC_CUDA(ctx, cudaGetLastError());
     scan_u32_kernel<<<1, 1024, 0, st>>>(fs->flags, slots, fs->offs, fs->total);
     RSC_CUDA(ctx, cudaGetLastError());
