@@ -99,10 +99,17 @@ int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
       cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
       cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess ||
-      cudaEventCreate(&ctx->evr0) != cudaSuccess || cudaEventCreate(&ctx->evr1) != cudaSuccess) {
+      cudaEventCreate(&ctx->evr0) != cudaSuccess || cudaEventCreate(&ctx->evr1) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
     delete ctx;
     return RSC_E_CUDA;
   }
+  for (int i = 0; i < 3; ++i)
+    if (cudaStreamCreateWithFlags(&ctx->sfork[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete ctx;
+      return RSC_E_CUDA;
+    }
   *out = ctx;
   return RSC_OK;
 }
@@ -117,6 +124,11 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
   for (auto* b : bufs) b->release();
   ctx->stage[0].release(), ctx->stage[1].release();
   cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < 3; ++i) {
+    if (ctx->sfork[i]) cudaStreamSynchronize(ctx->sfork[i]), cudaStreamDestroy(ctx->sfork[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);

@@ -81,6 +81,9 @@ struct rsc_ctx {
   cudaStream_t copy_stream = nullptr;  // host->device uploads, overlapped with scoring of earlier chunks
   rsc::DevBuf stage[2];                // double-buffered AoS staging of one upload chunk
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
+  cudaStream_t sfork[3] = {nullptr, nullptr, nullptr};  // the per-type score kernels of one call run side by side
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  int last_cslots = 0;                 // slot stride of the last compiled candidate records / masks
   std::string err;
   rsc_stats stats{};
   // scratch of the score path

@@ -12,6 +12,16 @@
 //   cone     h = a.v, w = v - a h, rho = |w|, (c,s) = cos/sin(opang/2):
 //            dist = h s - rho c;   +-(c (w.n) - s rho (a.n)) > cos(alpha) rho
 // The outwards sign is folded into the record (sg = +-1 multiplies v), so a warp never branches.
+//
+// Operation count (FP32-pipe instructions per evaluation: plane 7, sphere 12, cylinder 18, cone 23):
+//   * sphere/cylinder: d = r - R comes out of ONE fma(vv, rsqrt(vv), -R); the angle term re-uses it,
+//     cos(alpha) r - s = cos(alpha) d - (s - cos(alpha) R), with -cos(alpha) R folded into the record
+//     as the start value of the s chain;
+//   * cone: both tests are divided by c = cos(opang/2) > 0 (sign-preserving):
+//     dist/c = h tan - rho,   margin/c = rho (cos(alpha)/c + tan (a.n)) - w.n,
+//     so the record carries tan, eps/c and cos(alpha)/c and the margin (and its guard band) are in
+//     units of 1/c.  Cones with c < 1/16 (opening angle > 172.8 deg) get an infinite band: every pair
+//     of theirs is decided by the FP64 path.
 #pragma once
 #include "rsc_common.cuh"
 
@@ -48,15 +58,15 @@ struct RecN<RSC_PLANE> {
 };
 template <>
 struct RecN<RSC_SPHERE> {
-  static constexpr int n = 5;
+  static constexpr int n = 6;
 };
 template <>
 struct RecN<RSC_CYLINDER> {
-  static constexpr int n = 8;
+  static constexpr int n = 9;
 };
 template <>
 struct RecN<RSC_CONE> {
-  static constexpr int n = 9;
+  static constexpr int n = 10;
 };
 
 // r: the used fields of the record (registers).  p = (x,y,z), n = (nx,ny,nz).
@@ -70,39 +80,38 @@ __device__ __forceinline__ float eval(const float* r, float px, float py, float 
     float nt = fmaf(r[4], nx, fmaf(r[5], ny, fmaf(r[6], nz, cosa)));
     return fmax_nan(e, nt);
   } else if constexpr (T == RSC_SPHERE) {
-    // r0 = sg, r1..3 = -sg*center, r4 = R
+    // r0 = sg, r1..3 = -sg*center, r4 = -R, r5 = -cos(alpha)*R
     float vx = fmaf(r[0], px, r[1]), vy = fmaf(r[0], py, r[2]), vz = fmaf(r[0], pz, r[3]);
     float vv = fmaf(vx, vx, fmaf(vy, vy, vz * vz));
-    float rad = vv * rsqrt_fast(vv);
-    float e = fabsf(rad - r[4]) - eps;
-    float s = fmaf(vx, nx, fmaf(vy, ny, vz * nz));
-    float nt = fmaf(cosa, rad, -s);
+    float d = fmaf(vv, rsqrt_fast(vv), r[4]);
+    float e = fabsf(d) - eps;
+    float s = fmaf(vx, nx, fmaf(vy, ny, fmaf(vz, nz, r[5])));
+    float nt = fmaf(cosa, d, -s);
     return fmax_nan(e, nt);
   } else if constexpr (T == RSC_CYLINDER) {
-    // r0 = sg, r1..3 = -sg*center, r4..6 = axis, r7 = R
+    // r0 = sg, r1..3 = -sg*center, r4..6 = axis, r7 = -R, r8 = -cos(alpha)*R
     float vx = fmaf(r[0], px, r[1]), vy = fmaf(r[0], py, r[2]), vz = fmaf(r[0], pz, r[3]);
     float h = fmaf(r[4], vx, fmaf(r[5], vy, r[6] * vz));
     float wx = fmaf(-r[4], h, vx), wy = fmaf(-r[5], h, vy), wz = fmaf(-r[6], h, vz);
     float ww = fmaf(wx, wx, fmaf(wy, wy, wz * wz));
-    float rho = ww * rsqrt_fast(ww);
-    float e = fabsf(rho - r[7]) - eps;
-    float wn = fmaf(wx, nx, fmaf(wy, ny, wz * nz));
-    float nt = fmaf(cosa, rho, -wn);
+    float d = fmaf(ww, rsqrt_fast(ww), r[7]);
+    float e = fabsf(d) - eps;
+    float wn = fmaf(wx, nx, fmaf(wy, ny, fmaf(wz, nz, r[8])));
+    float nt = fmaf(cosa, d, -wn);
     return fmax_nan(e, nt);
   } else {
-    // r0 = sg, r1..3 = -sg*apex, r4..6 = axis, r7 = sg*sin(opang/2), r8 = cos(opang/2)
+    // r0 = sg, r1..3 = -sg*apex, r4..6 = axis, r7 = sg*tan(opang/2), r8 = -eps/c, r9 = cos(alpha)/c
     float vx = fmaf(r[0], px, r[1]), vy = fmaf(r[0], py, r[2]), vz = fmaf(r[0], pz, r[3]);
     float h = fmaf(r[4], vx, fmaf(r[5], vy, r[6] * vz));
     float wx = fmaf(-r[4], h, vx), wy = fmaf(-r[5], h, vy), wz = fmaf(-r[6], h, vz);
     float ww = fmaf(wx, wx, fmaf(wy, wy, wz * wz));
     float rho = ww * rsqrt_fast(ww);
-    float d = fmaf(h, r[7], -(rho * r[8]));
-    float e = fabsf(d) - eps;
+    float d = fmaf(h, r[7], -rho);
+    float e = fabsf(d) + r[8];
     float wn = fmaf(wx, nx, fmaf(wy, ny, wz * nz));
     float an = fmaf(r[4], nx, fmaf(r[5], ny, r[6] * nz));
-    // cosa*rho - (c*wn - s*rho*an) = rho*(cosa + s*an) - c*wn
-    float t1 = fmaf(r[7], an, cosa);
-    float nt = fmaf(-r[8], wn, rho * t1);
+    float t1 = fmaf(r[7], an, r[9]);
+    float nt = fmaf(rho, t1, -wn);
     return fmax_nan(e, nt);
   }
 }
@@ -137,20 +146,20 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
   } else if constexpr (T == RSC_SPHERE) {
     const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
     const float2 vv = fma2(vx, vx, fma2(vy, vy, mul2(vz, vz)));
-    const float2 rad = mul2(vv, rsqrt2(vv));
-    const float2 e = add2(abs2(add2(rad, neg2(r[4]))), bc2(-eps));
-    const float2 s = fma2(vx, NX, fma2(vy, NY, mul2(vz, NZ)));
-    const float2 nt = fma2(bc2(cosa), rad, neg2(s));
+    const float2 d = fma2(vv, rsqrt2(vv), r[4]);
+    const float2 e = add2(abs2(d), bc2(-eps));
+    const float2 s = fma2(vx, NX, fma2(vy, NY, fma2(vz, NZ, r[5])));
+    const float2 nt = fma2(bc2(cosa), d, neg2(s));
     return max2_nan(e, nt);
   } else if constexpr (T == RSC_CYLINDER) {
     const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
     const float2 h = fma2(r[4], vx, fma2(r[5], vy, mul2(r[6], vz)));
     const float2 wx = fma2(neg2(r[4]), h, vx), wy = fma2(neg2(r[5]), h, vy), wz = fma2(neg2(r[6]), h, vz);
     const float2 ww = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
-    const float2 rho = mul2(ww, rsqrt2(ww));
-    const float2 e = add2(abs2(add2(rho, neg2(r[7]))), bc2(-eps));
-    const float2 wn = fma2(wx, NX, fma2(wy, NY, mul2(wz, NZ)));
-    const float2 nt = fma2(bc2(cosa), rho, neg2(wn));
+    const float2 d = fma2(ww, rsqrt2(ww), r[7]);
+    const float2 e = add2(abs2(d), bc2(-eps));
+    const float2 wn = fma2(wx, NX, fma2(wy, NY, fma2(wz, NZ, r[8])));
+    const float2 nt = fma2(bc2(cosa), d, neg2(wn));
     return max2_nan(e, nt);
   } else {
     const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
@@ -158,12 +167,12 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
     const float2 wx = fma2(neg2(r[4]), h, vx), wy = fma2(neg2(r[5]), h, vy), wz = fma2(neg2(r[6]), h, vz);
     const float2 ww = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
     const float2 rho = mul2(ww, rsqrt2(ww));
-    const float2 d = fma2(h, r[7], neg2(mul2(rho, r[8])));
-    const float2 e = add2(abs2(d), bc2(-eps));
+    const float2 d = fma2(h, r[7], neg2(rho));
+    const float2 e = add2(abs2(d), r[8]);
     const float2 wn = fma2(wx, NX, fma2(wy, NY, mul2(wz, NZ)));
     const float2 an = fma2(r[4], NX, fma2(r[5], NY, mul2(r[6], NZ)));
-    const float2 t1 = fma2(r[7], an, bc2(cosa));
-    const float2 nt = fma2(neg2(r[8]), wn, mul2(rho, t1));
+    const float2 t1 = fma2(r[7], an, r[9]);
+    const float2 nt = fma2(rho, t1, neg2(wn));
     return max2_nan(e, nt);
   }
 }
@@ -187,7 +196,7 @@ __device__ __forceinline__ float eval_any(int type, const float* r, float px, fl
 // over the cloud, the scale of every intermediate and therefore of the rounding error.
 // A candidate with a non-finite parameter can match nothing in the reference (NaN compares
 // false); it gets a record that is far from everything so that no NaN reaches the tiled kernel.
-__device__ inline void compile_record(const rsc_cand& c, float pmax, float nmax, float* r /*[12]*/) {
+__device__ inline void compile_record(const rsc_cand& c, const Thresh& th, float pmax, float nmax, float* r /*[12]*/) {
   const double u = 5.9604644775390625e-08;  // 2^-24
   for (int i = 0; i < kRecFields; ++i) r[i] = 0.f;
   bool finite = true;
@@ -215,12 +224,13 @@ __device__ inline void compile_record(const rsc_cand& c, float pmax, float nmax,
     case RSC_SPHERE: {
       double sg = c.outwards ? 1.0 : -1.0;
       if (!finite) {
-        r[0] = 1.f, r[1] = 1e15f, r[4] = 1e30f, r[kBandField] = 1.f;
+        r[0] = 1.f, r[1] = 1e15f, r[4] = -1e30f, r[kBandField] = 1.f;
         return;
       }
       r[0] = (float)sg;
       r[1] = (float)(-sg * c.p[0]), r[2] = (float)(-sg * c.p[1]), r[3] = (float)(-sg * c.p[2]);
-      r[4] = (float)c.p[3];
+      r[4] = (float)(-c.p[3]);
+      r[5] = (float)(-th.cosa_d[RSC_SPHERE] * c.p[3]);
       double cn = sqrt(c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2]);
       L = (P + cn + fabs(c.p[3]) + 1.0) * nm;
       break;
@@ -228,13 +238,14 @@ __device__ inline void compile_record(const rsc_cand& c, float pmax, float nmax,
     case RSC_CYLINDER: {
       double sg = c.outwards ? 1.0 : -1.0;
       if (!finite) {
-        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 1e30f, r[kBandField] = 1.f;
+        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = -1e30f, r[kBandField] = 1.f;
         return;
       }
       r[0] = (float)sg;
       r[1] = (float)(-sg * c.p[3]), r[2] = (float)(-sg * c.p[4]), r[3] = (float)(-sg * c.p[5]);
       r[4] = (float)c.p[0], r[5] = (float)c.p[1], r[6] = (float)c.p[2];
-      r[7] = (float)c.p[6];
+      r[7] = (float)(-c.p[6]);
+      r[8] = (float)(-th.cosa_d[RSC_CYLINDER] * c.p[6]);
       double cn = sqrt(c.p[3] * c.p[3] + c.p[4] * c.p[4] + c.p[5] * c.p[5]);
       double a2 = c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2];
       L = (P + cn + fabs(c.p[6]) + 1.0) * (a2 > 1.0 ? a2 : 1.0) * nm;
@@ -246,17 +257,23 @@ __device__ inline void compile_record(const rsc_cand& c, float pmax, float nmax,
       double sg = c.outwards ? 1.0 : -1.0;
       const double an = sqrt(c.p[3] * c.p[3] + c.p[4] * c.p[4] + c.p[5] * c.p[5]);
       const double ia = 1.0 / an;
-      if (!finite || !(an > 0.0) || !isfinite(ia)) {
-        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 0.f, r[8] = 1.f, r[kBandField] = 1.f;
+      const double ch = cos(0.5 * c.p[6]), sh = sin(0.5 * c.p[6]);
+      const bool flat = !(ch >= 1.0 / 16.0);  // opening angle > 172.8 deg (or NaN): decided in FP64
+      if (!finite || !(an > 0.0) || !isfinite(ia) || flat) {
+        // far from everything; a flat cone additionally gets an infinite band (every pair -> FP64)
+        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 0.f, r[8] = 0.f, r[9] = 1.f;
+        r[kBandField] = (finite && an > 0.0 && isfinite(ia)) ? __int_as_float(0x7f800000) : 1.f;
         return;
       }
+      const double ic = 1.0 / ch;
       r[0] = (float)sg;
       r[1] = (float)(-sg * c.p[0]), r[2] = (float)(-sg * c.p[1]), r[3] = (float)(-sg * c.p[2]);
       r[4] = (float)(c.p[3] * ia), r[5] = (float)(c.p[4] * ia), r[6] = (float)(c.p[5] * ia);
-      r[7] = (float)(sg * sin(0.5 * c.p[6]));
-      r[8] = (float)cos(0.5 * c.p[6]);
+      r[7] = (float)(sg * sh * ic);
+      r[8] = (float)(-th.eps_d[RSC_CONE] * ic);
+      r[9] = (float)(th.cosa_d[RSC_CONE] * ic);
       double cn = sqrt(c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2]);
-      L = (P + cn + 1.0) * nm;
+      L = (P + cn + 1.0) * nm * ic;  // the margin is in units of 1/c
       break;
     }
   }

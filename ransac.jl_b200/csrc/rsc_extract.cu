@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_c
   __shared__ float r[kRecFields];
   if (threadIdx.x == 0) {
     float t[kRecFields];
-    compile_record(a.cand, a.pmax, a.nmax, t);
+    compile_record(a.cand, a.th, a.pmax, a.nmax, t);
     for (int f = 0; f < kRecFields; ++f) r[f] = t[f];
   }
   __syncthreads();

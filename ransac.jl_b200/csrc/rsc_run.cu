@@ -396,8 +396,9 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
             ps.n = (int64_t)nnew_dis;
             ps.n_pad = sp;
             // replicated on every rank (the scratch set is tiny): no all-reduce needed
-            if ((rc = score_enqueue(ctx, cloud, ps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st, hit,
-                                    ctx->counts.as<int32_t>())))
+            // enabled == valid on the scratch set: the enabled-gated count (kept for every type) is the hit count
+            if ((rc = score_enqueue(ctx, cloud, ps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st,
+                                    ctx->counts.as<int32_t>(), hit)))
               goto done;
           } else {
             RUN_CUDA(cudaMemsetAsync(hit, 0, (size_t)nst * 4, st));

@@ -95,7 +95,11 @@ __device__ __forceinline__ void issue_subtile(const PointSet& ps, int sub, float
 // K candidates per thread; for even K they are evaluated as K/2 packed pairs (FFMA2 path).
 // Every WARP streams the CTA row's points through its own double-buffered shared-memory stages
 // (TMA bulk copies signalled on warp-private mbarriers): there is no CTA-wide barrier in the loop.
-template <int T, int K, int UN>
+//
+// Mask words are built MSB-first (the sign bit of each margin is funnel-shifted in from the right),
+// so the first point of a 32-point group ends at bit 31: counts use the bit-reversed enabled/valid
+// words, and only the words that leave the thread (mask store, fix-up queue) are reversed back.
+template <int T, int K, int U, bool MASKS>
 __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float* wstage, uint64_t* wbar) {
   constexpr int NR = RecN<T>::n;
   constexpr bool kPacked = (K % 2 == 0);
@@ -103,14 +107,14 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
   float r[kPacked ? 1 : K][NR];  // scalar records (K odd)
   float2 r2[KP][NR];             // packed records: .x = candidate 2j, .y = candidate 2j+1
   float band[K];
-  int cntv[K], cnte[K];
+  int cnte[K], cntv[K];
   const int tid = threadIdx.x, lane = tid & 31;
+  const float* recp = a.rec + slot0 + tid;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
-    const int slot = slot0 + k * kThreads + tid;
 #pragma unroll
     for (int f = 0; f < NR; ++f) {
-      const float v = a.rec[(size_t)f * a.cslots + slot];
+      const float v = recp[(size_t)f * a.cslots + k * kThreads];
       if constexpr (kPacked) {
         if (k & 1)
           r2[k / 2][f].y = v;
@@ -120,15 +124,20 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
         r[k][f] = v;
       }
     }
-    band[k] = a.rec[(size_t)kBandField * a.cslots + slot];
-    cntv[k] = 0;
+    band[k] = recp[(size_t)kBandField * a.cslots + k * kThreads];
     cnte[k] = 0;
+    cntv[k] = 0;
   }
   const float eps = a.th.eps[T], cosa = a.th.cosa[T];
+  // honour: the type ANDs pc.isenabled into its inliers; otherwise (sphere, Q4) the policy count is
+  // the validity-gated one and the enabled-gated count is kept beside it (the loop's "tainted" flag)
   const bool honour = (a.th.honour_enabled >> T) & 1u;
 
   const int sub0 = blockIdx.y * a.subs_per_chunk;
   const int nsub = min(a.subs_per_chunk, a.nsubs - sub0);
+  const uint32_t* enp = a.ps.enabled + (size_t)sub0 * (kSub / 32);
+  const uint32_t* vap = a.ps.valid + (size_t)sub0 * (kSub / 32);
+  uint32_t* maskp = MASKS ? a.masks + (size_t)sub0 * (kSub / 32) * a.cslots + slot0 + tid : nullptr;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s)
@@ -148,17 +157,17 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
         mabs[k] = __int_as_float(0x7f800000);
       }
       const float* gx = sx + g * 32;
-#pragma unroll UN
+#pragma unroll U
       for (int i4 = 0; i4 < 32; i4 += 4) {
         // 6 broadcast 128-bit loads = 4 points
         const float4 X = *reinterpret_cast<const float4*>(gx + i4);
         const float4 Y = *reinterpret_cast<const float4*>(gx + kSub + i4);
         const float4 Z = *reinterpret_cast<const float4*>(gx + 2 * kSub + i4);
-        const float4 U = *reinterpret_cast<const float4*>(gx + 3 * kSub + i4);
+        const float4 U4 = *reinterpret_cast<const float4*>(gx + 3 * kSub + i4);
         const float4 V = *reinterpret_cast<const float4*>(gx + 4 * kSub + i4);
         const float4 W = *reinterpret_cast<const float4*>(gx + 5 * kSub + i4);
         const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
-        const float nx[4] = {U.x, U.y, U.z, U.w}, ny[4] = {V.x, V.y, V.z, V.w}, nz[4] = {W.x, W.y, W.z, W.w};
+        const float nx[4] = {U4.x, U4.y, U4.z, U4.w}, ny[4] = {V.x, V.y, V.z, V.w}, nz[4] = {W.x, W.y, W.z, W.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if constexpr (kPacked) {
@@ -180,23 +189,37 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
           }
         }
       }
-      const int64_t gw = (int64_t)(sub0 + it) * (kSub / 32) + g;
-      const uint32_t en = __ldg(a.ps.enabled + gw);
-      const uint32_t va = __ldg(a.ps.valid + gw);
+      // ---- group epilogue: counts (+ mask words); the guard-band queue is the rare path ----
+      const int gi = it * (kSub / 32) + g;
+      const uint32_t en = __ldg(enp + gi);
+      const uint32_t va = __ldg(vap + gi);
+      const uint32_t ben = __brev(en), bva = __brev(va);
+      bool amb = false;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const uint32_t w = __brev(mask[k]);
-        const int slot = slot0 + k * kThreads + tid;
-        if (!(mabs[k] > band[k])) {  // rare: hand the group to the FP64 fix-up kernel
+        amb |= !(mabs[k] > band[k]);
+        cnte[k] += __popc(mask[k] & ben);
+      }
+      if (!honour) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) cntv[k] += __popc(mask[k] & bva);
+      }
+      if constexpr (MASKS) {
+        const uint32_t gate = honour ? en : va;
+#pragma unroll
+        for (int k = 0; k < K; ++k) maskp[(size_t)gi * a.cslots + k * kThreads] = __brev(mask[k]) & gate;
+      }
+      if (amb && va) {  // rare: hand the group(s) to the FP64 fix-up kernels
+        const int64_t gw = (int64_t)sub0 * (kSub / 32) + gi;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          if (mabs[k] > band[k]) continue;
+          const int slot = slot0 + k * kThreads + tid;
           const int o = a.orig[slot];
-          if (o >= 0 && va) {
-            const uint32_t pos = atomicAdd(a.wl_count, 1u);
-            if (pos < a.wl_cap) a.wl[pos] = GroupTask{(uint32_t)o, (uint32_t)gw, w, (uint32_t)slot | ((uint32_t)T << 28)};
-          }
+          if (o < 0) continue;
+          const uint32_t pos = atomicAdd(a.wl_count, 1u);
+          if (pos < a.wl_cap) a.wl[pos] = GroupTask{(uint32_t)o, (uint32_t)gw, __brev(mask[k]), (uint32_t)slot | ((uint32_t)T << 28)};
         }
-        cntv[k] += __popc(w & va);
-        cnte[k] += __popc(w & en);
-        if (a.masks) a.masks[(size_t)gw * a.cslots + slot] = w & (honour ? en : va);
       }
     }
     __syncwarp();
@@ -206,18 +229,22 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
   for (int k = 0; k < K; ++k) {
     const int o = a.orig[slot0 + k * kThreads + tid];
     if (o >= 0) {
-      if (cntv[k]) atomicAdd(a.counts_valid + o, cntv[k]);
       if (cnte[k]) atomicAdd(a.counts_enabled + o, cnte[k]);
+      if (!honour && cntv[k]) atomicAdd(a.counts_valid + o, cntv[k]);
     }
   }
 }
 
-template <int K, int MINB, int U>
+// One kernel per shape type (and per tiling): register allocation, occupancy and the number of
+// candidates per thread are chosen per type.  The grid spans ALL columns of the block table; CTAs of
+// another type's columns leave at once (the host does not know the per-type candidate counts: the
+// candidates may live on the device only).
+template <int T, int K, int MINB, int U, bool MASKS>
 __global__ void __launch_bounds__(kThreads, MINB) score_kernel(const __grid_constant__ ScoreArgs a) {
   __shared__ __align__(128) float stages[kThreads / 32][kStages * kSubFloats];
   __shared__ __align__(8) uint64_t bars[kThreads / 32][kStages];
   const BlockTab bt = a.tab[blockIdx.x];
-  if (bt.type < 0) return;
+  if (bt.type != T) return;
   const int warp = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
@@ -225,20 +252,7 @@ __global__ void __launch_bounds__(kThreads, MINB) score_kernel(const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  switch (bt.type) {
-    case RSC_PLANE:
-      score_body<RSC_PLANE, K, U>(a, bt.slot0, stages[warp], bars[warp]);
-      break;
-    case RSC_SPHERE:
-      score_body<RSC_SPHERE, K, U>(a, bt.slot0, stages[warp], bars[warp]);
-      break;
-    case RSC_CYLINDER:
-      score_body<RSC_CYLINDER, K, U>(a, bt.slot0, stages[warp], bars[warp]);
-      break;
-    default:
-      score_body<RSC_CONE, K, U>(a, bt.slot0, stages[warp], bars[warp]);
-      break;
-  }
+  score_body<T, K, U, MASKS>(a, bt.slot0, stages[warp], bars[warp]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -361,8 +375,12 @@ __global__ void select_counts_kernel(const rsc_cand* __restrict__ cands, int C,
 // One CTA; slots are assigned stably (candidate order within a type is kept).
 // Column order is cone, cylinder, sphere, plane: the most expensive columns are scheduled first.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restrict__ cands, int C,
-                                                       int spc /*slots per column*/, int cslots,
+struct ColSlots {
+  int v[RSC_NTYPES];  // slots per CTA column (= 128 x candidates per thread) of each type
+};
+
+__global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restrict__ cands, int C, const Thresh th,
+                                                       const ColSlots spcs, int cslots,
                                                        int ncols, float pmax, float nmax,
                                                        const uint32_t* __restrict__ d_bounds,
                                                        float* __restrict__ rec, int32_t* __restrict__ orig,
@@ -391,6 +409,7 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
     for (int oi = 0; oi < RSC_NTYPES; ++oi) {
       const int t = order[oi];
       off[t] = s;
+      const int spc = spcs.v[t];
       const int nb = (cnt[t] + spc - 1) / spc;
       for (int b = 0; b < nb && col < ncols; ++b) tab[col++] = BlockTab{t, s + b * spc};
       s += nb * spc;
@@ -432,7 +451,7 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
       if (t >= 0) {
         const int slot = off[t] + run[t] + woff[t][warp] + myrank;
         float r[kRecFields];
-        compile_record(cands[i], pmax, nmax, r);
+        compile_record(cands[i], th, pmax, nmax, r);
 #pragma unroll
         for (int f = 0; f < kRecFields; ++f) rec[(size_t)f * cslots + slot] = r[f];
         orig[slot] = i;
@@ -449,6 +468,7 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
   for (int t = 0; t < RSC_NTYPES; ++t) {
     const int n = cnt[t];
     if (n == 0) continue;
+    const int spc = spcs.v[t];
     const int padded = ((n + spc - 1) / spc) * spc;
     const int src = off[t] + n - 1;
     for (int s = n + tid; s < padded; s += blockDim.x) {
@@ -502,7 +522,74 @@ Thresh make_thresh(const rsc_params* p) {
   return th;
 }
 
-static int pick_k(int C) { return C >= 3072 ? 4 : (C >= 768 ? 2 : 1); }
+// ---- tiling table -----------------------------------------------------------------------------
+// (K candidates per thread, CTAs per SM, points unrolled x4) per shape type.  The defaults were
+// picked on a B200 with tools/tune_score.py; RSC_CFG_<PLANE|SPHERE|CYLINDER|CONE>="K,MINB,U"
+// overrides one type (tuning hook, read on every call).
+using ScoreFn = void (*)(const ScoreArgs);
+struct Tiling {
+  int K, minb, U;
+  ScoreFn fn[RSC_NTYPES];       // counts only
+  ScoreFn fn_masks[RSC_NTYPES]; // counts + packed inlier bitmasks
+};
+#define RSC_TILING(K, MINB, U)                                                                          \
+  Tiling {                                                                                              \
+    K, MINB, U,                                                                                         \
+        {score_kernel<RSC_PLANE, K, MINB, U, false>, score_kernel<RSC_SPHERE, K, MINB, U, false>,       \
+         score_kernel<RSC_CYLINDER, K, MINB, U, false>, score_kernel<RSC_CONE, K, MINB, U, false>},     \
+    {                                                                                                   \
+      score_kernel<RSC_PLANE, K, MINB, U, true>, score_kernel<RSC_SPHERE, K, MINB, U, true>,            \
+          score_kernel<RSC_CYLINDER, K, MINB, U, true>, score_kernel<RSC_CONE, K, MINB, U, true>        \
+    }                                                                                                   \
+  }
+static const Tiling kTilings[] = {
+    RSC_TILING(1, 4, 1), RSC_TILING(2, 4, 1), RSC_TILING(2, 8, 1), RSC_TILING(4, 3, 1), RSC_TILING(4, 4, 1),
+    RSC_TILING(4, 5, 1), RSC_TILING(4, 6, 1), RSC_TILING(4, 4, 2), RSC_TILING(8, 2, 1), RSC_TILING(8, 3, 1),
+};
+static const Tiling* find_tiling(int K, int minb, int U) {
+  for (const Tiling& t : kTilings)
+    if (t.K == K && t.minb == minb && t.U == U) return &t;
+  return nullptr;
+}
+
+// K by problem size: few candidates -> fewer per thread, so that there are columns to spread over
+static int cap_k(int C) { return C >= 3072 ? 8 : (C >= 768 ? 2 : 1); }
+
+static const Tiling* pick_tiling(int type, int C) {
+  static const char* names[RSC_NTYPES] = {"RSC_CFG_PLANE", "RSC_CFG_SPHERE", "RSC_CFG_CYLINDER", "RSC_CFG_CONE"};
+  static const int dflt[RSC_NTYPES][3] = {{4, 4, 1}, {4, 4, 1}, {4, 4, 1}, {4, 4, 1}};
+  int K = dflt[type][0], minb = dflt[type][1], U = dflt[type][2];
+  if (const char* e = getenv(names[type])) {
+    int a = 0, b = 0, c = 0;
+    if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && find_tiling(a, b, c)) K = a, minb = b, U = c;
+  }
+  const int kc = cap_k(C);
+  if (K > kc) {
+    K = kc;
+    minb = 4, U = 1;
+  }
+  return find_tiling(K, minb, U);
+}
+
+// layout of the compiled records for C candidates: per-type slots per column, total slot stride
+struct SlotLayout {
+  const Tiling* til[RSC_NTYPES];
+  ColSlots spcs;
+  int ncols, cslots;
+};
+static SlotLayout slot_layout(int C) {
+  SlotLayout L;
+  int min_spc = 1 << 30, sum_spc = 0;
+  for (int t = 0; t < RSC_NTYPES; ++t) {
+    L.til[t] = pick_tiling(t, C);
+    L.spcs.v[t] = kThreads * L.til[t]->K;
+    min_spc = min(min_spc, L.spcs.v[t]);
+    sum_spc += L.spcs.v[t];
+  }
+  L.ncols = (C + min_spc - 1) / min_spc + RSC_NTYPES;
+  L.cslots = ((C + sum_spc + 127) / 128) * 128;  // sum over types of ceil(cnt_t / spc_t) * spc_t <= C + sum spc_t
+  return L;
+}
 
 int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th,
                       const rsc_cand* d_cands, int32_t C, int32_t* d_counts_policy, bool want_masks,
@@ -510,10 +597,9 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
                       const double* d_trig, const uint32_t* d_bounds, bool accumulate) {
   if (C <= 0) return RSC_OK;
   if (ps.n_pad >= ((int64_t)1 << 32)) return fail(ctx, RSC_E_ARG, "point set too large for one shard (>= 2^32)");
-  const int K = pick_k(C);
-  const int spc = kThreads * K;
-  const int ncols = (C + spc - 1) / spc + RSC_NTYPES;
-  const int cslots = ncols * spc;
+  const SlotLayout L = slot_layout(C);
+  const int ncols = L.ncols, cslots = L.cslots;
+  ctx->last_cslots = cslots;
   const int nsubs = (int)(ps.n_pad / kSub);
   const int64_t groups = ps.n_pad / 32;
 
@@ -535,7 +621,7 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   RSC_CUDA(ctx, ctx->pairs.ensure(ctx->wl_cap * 8));
   RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.p, 0, 2 * sizeof(uint32_t), st));
 
-  compile_kernel<<<1, 1024, 0, st>>>(d_cands, C, spc, cslots, ncols, cloud->pmax, cloud->nmax, d_bounds,
+  compile_kernel<<<1, 1024, 0, st>>>(d_cands, C, th, L.spcs, cslots, ncols, cloud->pmax, cloud->nmax, d_bounds,
                                      ctx->rec.as<float>(), ctx->orig.as<int32_t>(),
                                      ctx->slot_of.as<int32_t>(), ctx->blktab.as<BlockTab>());
   RSC_CUDA(ctx, cudaGetLastError());
@@ -555,36 +641,38 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   a.wl_count = ctx->wl_count.as<uint32_t>();
   a.wl_cap = (uint32_t)ctx->wl_cap;
 
-  // grid: columns x point chunks; aim at >= 8 waves of 4 CTAs/SM so the tail stays small
-  const int real_cols = (C + spc - 1) / spc;
-  static const int waves = getenv("RSC_WAVES") ? atoi(getenv("RSC_WAVES")) : 32;
-  static const int minb = getenv("RSC_MINB") ? atoi(getenv("RSC_MINB")) : 4;
-  static const int unroll = getenv("RSC_UNROLL") ? atoi(getenv("RSC_UNROLL")) : 1;
+  // grid: columns x point chunks; aim at `waves` waves of resident CTAs so the tail stays small.
+  // The four per-type kernels are independent; on large problems they run on four streams (forked
+  // from and joined back into `st`) so that one kernel's tail is filled by the next one's CTAs.
+  const int waves = getenv("RSC_WAVES") ? atoi(getenv("RSC_WAVES")) : 32;
+  const int est_cols = (C + kThreads * 4 - 1) / (kThreads * 4);
   const long target = (long)ctx->sm_count * 4 * waves;
-  long chunks = (target + real_cols - 1) / real_cols;
+  long chunks = (target + est_cols - 1) / est_cols;
   if (chunks > nsubs) chunks = nsubs;
   if (chunks < 1) chunks = 1;
   if (chunks > 65535) chunks = 65535;
   a.subs_per_chunk = (int)((nsubs + chunks - 1) / chunks);
   chunks = (nsubs + a.subs_per_chunk - 1) / a.subs_per_chunk;
   dim3 grid((unsigned)ncols, (unsigned)chunks);
+  const bool fork = (double)C * (double)ps.n_pad >= 1e9 && !getenv("RSC_NOFORK");
 
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
-  switch (K) {
-    case 4:
-      if (unroll == 2)
-        score_kernel<4, 4, 2><<<grid, kThreads, 0, st>>>(a);
-      else if (minb == 3)
-        score_kernel<4, 3, 1><<<grid, kThreads, 0, st>>>(a);
-      else
-        score_kernel<4, 4, 1><<<grid, kThreads, 0, st>>>(a);
-      break;
-    case 2:
-      score_kernel<2, 4, 1><<<grid, kThreads, 0, st>>>(a);
-      break;
-    default:
-      score_kernel<1, 4, 1><<<grid, kThreads, 0, st>>>(a);
-      break;
+  if (fork) RSC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+  // most expensive type first
+  const int order[RSC_NTYPES] = {RSC_CONE, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
+  for (int oi = 0; oi < RSC_NTYPES; ++oi) {
+    const int t = order[oi];
+    cudaStream_t s = st;
+    if (fork && oi > 0) {
+      s = ctx->sfork[oi - 1];
+      RSC_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_fork, 0));
+    }
+    (want_masks ? L.til[t]->fn_masks[t] : L.til[t]->fn[t])<<<grid, kThreads, 0, s>>>(a);
+    RSC_CUDA(ctx, cudaGetLastError());
+    if (fork && oi > 0) {
+      RSC_CUDA(ctx, cudaEventRecord(ctx->ev_join[oi - 1], s));
+      RSC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[oi - 1], 0));
+    }
   }
   RSC_CUDA(ctx, cudaGetLastError());
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk1, st));
@@ -608,10 +696,7 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
 
 // after score_enqueue(want_masks=true): ctx->masks_cm = [C][ceil(m/32)] candidate-major masks
 int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st) {
-  const int K = pick_k(C);
-  const int spc = kThreads * K;
-  const int ncols = (C + spc - 1) / spc + RSC_NTYPES;
-  const int cslots = ncols * spc;
+  const int cslots = ctx->last_cslots;
   const int64_t words = (m + 31) / 32;
   RSC_CUDA(ctx, ctx->masks_cm.ensure((size_t)C * words * sizeof(uint32_t)));
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((words + 31) / 32));

@@ -19,26 +19,30 @@ def rsqrt(x):
     return (r * (1 + 2.2 * U * np.sign(np.sin(np.arange(len(x)) * 12.9898)))).astype(f32)
 
 
-def record(kind, outw, p, pmax, nmax):
-    """(fields, band) like rsc::compile_record"""
+def record(kind, outw, p, pmax, nmax, eps=0.3, cosa=math.cos(math.radians(5))):
+    """(fields, band, scale) like rsc::compile_record; the kernel's margin is scale x the plain margin"""
     nm = max(1.0, nmax)
     sg = 1.0 if outw else -1.0
+    scale = 1.0
     if kind == 0:
         m = np.array(p[3:6]); mn = np.linalg.norm(m); o = m / mn; oq = float(o @ p[0:3])
         r = [*o, -oq, *(-m)]
         L = (pmax + abs(oq) + 1) * max(mn, 1.0) * nm
     elif kind == 1:
-        r = [sg, *(-sg * np.array(p[0:3])), p[3]]
+        r = [sg, *(-sg * np.array(p[0:3])), -p[3], -cosa * p[3]]
         L = (pmax + np.linalg.norm(p[0:3]) + abs(p[3]) + 1) * nm
     elif kind == 2:
-        r = [sg, *(-sg * np.array(p[3:6])), *p[0:3], p[6]]
+        r = [sg, *(-sg * np.array(p[3:6])), *p[0:3], -p[6], -cosa * p[6]]
         a2 = float(np.dot(p[0:3], p[0:3]))
         L = (pmax + np.linalg.norm(p[3:6]) + abs(p[6]) + 1) * max(a2, 1.0) * nm
     else:
         ax = np.array(p[3:6]) / np.linalg.norm(p[3:6])  # the reference's cone test only uses the axis direction
-        r = [sg, *(-sg * np.array(p[0:3])), *ax, sg * math.sin(p[6] / 2), math.cos(p[6] / 2)]
-        L = (pmax + np.linalg.norm(p[0:3]) + 1) * nm
-    return [f32(x) for x in r], KAPPA[kind] * U * L
+        ch, sh = math.cos(p[6] / 2), math.sin(p[6] / 2)
+        assert ch >= 1 / 16, "flat cones are decided in FP64 (infinite band)"
+        scale = 1.0 / ch
+        r = [sg, *(-sg * np.array(p[0:3])), *ax, sg * sh / ch, -eps / ch, cosa / ch]
+        L = (pmax + np.linalg.norm(p[0:3]) + 1) * nm / ch
+    return [f32(x) for x in r], KAPPA[kind] * U * L, scale
 
 
 def margin32(kind, r, P, N, eps, cosa):
@@ -53,23 +57,25 @@ def margin32(kind, r, P, N, eps, cosa):
     vx, vy, vz = fma(px, r[0], r[1]), fma(py, r[0], r[2]), fma(pz, r[0], r[3])
     if kind == 1:
         vv = fma(vx, vx, fma(vy, vy, vz * vz))
-        rad = vv * rsqrt(vv)
-        e = np.abs(rad - r[4]) - eps
-        s = fma(vx, nx, fma(vy, ny, vz * nz))
-        return np.maximum(e, fma(rad, cosa, -s))
+        d = fma(vv, rsqrt(vv), r[4])
+        e = np.abs(d) - eps
+        s = fma(vx, nx, fma(vy, ny, fma(vz, nz, r[5])))
+        return np.maximum(e, fma(d, cosa, -s))
     h = fma(vx, r[4], fma(vy, r[5], vz * r[6]))
     wx, wy, wz = fma(h, -r[4], vx), fma(h, -r[5], vy), fma(h, -r[6], vz)
     ww = fma(wx, wx, fma(wy, wy, wz * wz))
+    if kind == 2:
+        d = fma(ww, rsqrt(ww), r[7])
+        e = np.abs(d) - eps
+        wn = fma(wx, nx, fma(wy, ny, fma(wz, nz, r[8])))
+        return np.maximum(e, fma(d, cosa, -wn))
     rho = ww * rsqrt(ww)
     wn = fma(wx, nx, fma(wy, ny, wz * nz))
-    if kind == 2:
-        e = np.abs(rho - r[7]) - eps
-        return np.maximum(e, fma(rho, cosa, -wn))
-    d = fma(h, r[7], -(rho * r[8]))
-    e = np.abs(d) - eps
+    d = fma(h, r[7], -rho)
+    e = np.abs(d) + r[8]
     an = fma(nx, r[4], fma(ny, r[5], nz * r[6]))
-    t1 = fma(an, r[7], cosa)
-    return np.maximum(e, fma(wn, -r[8], rho * t1))
+    t1 = fma(an, r[7], r[9])
+    return np.maximum(e, fma(rho, t1, -wn))
 
 
 def margin64(kind, outw, p, P, N, eps, cosa):

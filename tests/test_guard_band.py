@@ -24,9 +24,9 @@ def test_fp32_error_within_band():
     worst = {}
     for sh in cands:
         kind, outw, p = _cand_params(sh)
-        r, band = M.record(kind, outw, p, pmax, nmax)
+        r, band, scale = M.record(kind, outw, p, pmax, nmax, eps, cosa)
         m32 = M.margin32(kind, r, P, N, eps, cosa).astype(np.float64)
-        m64 = M.margin64(kind, outw, p, P, N, eps, cosa)
+        m64 = M.margin64(kind, outw, p, P, N, eps, cosa) * scale
         ok = np.isfinite(m32) & np.isfinite(m64)
         ratio = float((np.abs(m32 - m64)[ok] / band).max())
         worst[kind] = max(worst.get(kind, 0.0), ratio)
@@ -56,8 +56,8 @@ def test_fp32_far_candidates_within_band():
             else:
                 p = [*far, *(-far / np.linalg.norm(far) * 0.9 + a * 0.1), 0.3]
                 ax = np.array(p[3:6]); p[3:6] = list(ax / np.linalg.norm(ax))
-            r, band = M.record(kind, True, p, pmax, 1.0)
+            r, band, scale = M.record(kind, True, p, pmax, 1.0, eps, cosa)
             m32 = M.margin32(kind, r, P, N, eps, cosa).astype(np.float64)
-            m64 = M.margin64(kind, True, p, P, N, eps, cosa)
+            m64 = M.margin64(kind, True, p, P, N, eps, cosa) * scale
             ok = np.isfinite(m32) & np.isfinite(m64)
             assert (np.abs(m32 - m64)[ok] / band).max() < 0.5, kind

@@ -182,3 +182,32 @@ def test_fit_four_point_sets_and_type_subsets(R):
             c = sh.to_cand()
             assert c.type == t and bool(c.outwards) == outw
             assert np.abs(np.array(c.p[:]) - p).max() <= 1e-5 * max(1.0, np.abs(p).max())
+
+
+def test_wide_and_flat_cones(R):
+    """the tiled kernel evaluates cones divided by cos(opang/2); cones wider than 172.8 deg (and
+    opang >= 180 deg, where that cosine is <= 0) are routed to the FP64 path wholesale.  Counts,
+    masks and refit lists must still be the reference's."""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(105, 20_000)
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 1)
+    params = R.ransacparameters()
+    rng = np.random.default_rng(8)
+    P, N = sc.vertices.astype(np.float64), sc.normals.astype(np.float64)
+    cands = []
+    for deg in (120.0, 160.0, 170.0, 172.0, 173.5, 178.0, 179.99, 180.0, 185.0, 270.0):
+        for outw in (True, False):
+            a = rng.normal(size=3)
+            a /= np.linalg.norm(a)
+            apex = P[rng.integers(len(P))] - a * rng.uniform(0.0, 3.0)
+            cands.append(R.FittedCone(apex, a, math.radians(deg), outw))
+    counts, masks = R.score_counts(pc, cands, -1, params, want_masks=True)
+    want, wmask = _oracle_counts(cands, P, N, oracle_params(params))
+    np.testing.assert_array_equal(counts, want)
+    for i in range(len(cands)):
+        np.testing.assert_array_equal(R.unpack_mask(masks[i], pc.size), wmask[i])
+    assert want.sum() > 0
+    for i in (0, 9, 13):
+        ex = R.refit(cands[i], pc, params)
+        np.testing.assert_array_equal(ex.inpoints, np.flatnonzero(wmask[i]))
