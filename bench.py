@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_EVAL = {"plane": 13, "sphere": 16, "cylinder": 27, "cone": 38}
 MIX_FLOPS = 23.5
+NCU_TRAFFIC_BYTES = 1.706e9  # measured, see profiles/r1d_score_kernels_ncu.json
 
 
 def parse():
@@ -300,10 +301,13 @@ def main():
     ach = MIX_FLOPS * Cn * n / (kernel_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the four score kernels of one step, from the
+        # `ncu --set full` capture profiles/r1d_score_kernels_ncu.json (same command, 16 Mi points)
+        "traffic": NCU_TRAFFIC_BYTES if (Cn == 4096 and n == (16 << 20)) else None,
         "peak_source": f"derived: {nsm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry; "
                        "the path uses no tensor cores and is not HBM bound)",
-        "kernel": "rsc::score_kernel<4>", "kernel_ms": kernel_ms,
+        "kernel": "rsc::score_kernel<T,K,MINB,U,MASKS> x4 (one launch per shape type, side by side on four streams; "
+                  "kernel_ms = CUDA events around the four launches)", "kernel_ms": kernel_ms,
         "algorithmic_flops_per_eval": MIX_FLOPS,
         "hbm_gbs_algorithmic": (Cn / 512) * 24.125 * n / (kernel_ms * 1e-3) / 1e9,
         "hbm_peak_gbs": peaks.get("hbm_gbs"),
@@ -317,14 +321,15 @@ def main():
                    "points_per_gpu": n, "candidates": Cn, "parallelism": f"point-range shards x{world}, "
                    "int32 count all-reduce (NCCL)" if world > 1 else "single GPU",
                    "l2": "inputs (403 MB of points per pass) exceed the 126 MB L2; no flush needed"},
-        "e2e": e2e, "gpu_launches": 5 * args.steps, "clocks": clocks, "roofline": roofline,
+        # per step: compile_kernel, 4 x score_kernel, fixup_scan_kernel, fixup_pair_kernel, select_counts_kernel
+        "e2e": e2e, "gpu_launches": 8 * args.steps, "clocks": clocks, "roofline": roofline,
         "fp64_guard_pairs_per_step": int(guard),
     }
     # K4 (refit over the whole shard, HBM bound): mask kernel time -> GB/s of algorithmic bytes
     try:
         ex = R.refit(cands[0], pc, params)
         st4 = pc.ctx.stats()
-        out["refit"] = {"kernel": "rsc::extract_mask_kernel", "points": n, "inliers": int(len(ex.inpoints)),
+        out["refit"] = {"kernel": "rsc::extract_mask_kernel<T>", "points": n, "inliers": int(len(ex.inpoints)),
                         "kernel_ms": st4.refit_mask_ms, "achieved_gbs": 24.125 * n / (st4.refit_mask_ms * 1e-3) / 1e9,
                         "peak_gbs": peaks.get("hbm_gbs"), "bound": "hbm", "algorithmic_bytes_per_point": 24.125}
     except Exception as e:  # informational key only

@@ -134,15 +134,17 @@ __device__ __forceinline__ float2 max2_nan(float2 a, float2 b) {
   return make_float2(fmax_nan(a.x, b.x), fmax_nan(a.y, b.y));
 }
 
+// the two terms of the margin: returns the distance term e, stores the angle term nt
 template <int T>
-__device__ __forceinline__ float2 eval2(const float2* r, float px, float py, float pz, float nx, float ny,
-                                        float nz, float eps, float cosa) {
+__device__ __forceinline__ float2 eval2_terms(const float2* r, float px, float py, float pz, float nx, float ny,
+                                              float nz, float eps, float cosa, float2* nt_out) {
   const float2 X = bc2(px), Y = bc2(py), Z = bc2(pz), NX = bc2(nx), NY = bc2(ny), NZ = bc2(nz);
   if constexpr (T == RSC_PLANE) {
     const float2 d = fma2(r[0], X, fma2(r[1], Y, fma2(r[2], Z, r[3])));
     const float2 e = add2(abs2(d), bc2(-eps));
     const float2 nt = fma2(r[4], NX, fma2(r[5], NY, fma2(r[6], NZ, bc2(cosa))));
-    return max2_nan(e, nt);
+    *nt_out = nt;
+    return e;
   } else if constexpr (T == RSC_SPHERE) {
     const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
     const float2 vv = fma2(vx, vx, fma2(vy, vy, mul2(vz, vz)));
@@ -150,7 +152,8 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
     const float2 e = add2(abs2(d), bc2(-eps));
     const float2 s = fma2(vx, NX, fma2(vy, NY, fma2(vz, NZ, r[5])));
     const float2 nt = fma2(bc2(cosa), d, neg2(s));
-    return max2_nan(e, nt);
+    *nt_out = nt;
+    return e;
   } else if constexpr (T == RSC_CYLINDER) {
     const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
     const float2 h = fma2(r[4], vx, fma2(r[5], vy, mul2(r[6], vz)));
@@ -160,7 +163,8 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
     const float2 e = add2(abs2(d), bc2(-eps));
     const float2 wn = fma2(wx, NX, fma2(wy, NY, fma2(wz, NZ, r[8])));
     const float2 nt = fma2(bc2(cosa), d, neg2(wn));
-    return max2_nan(e, nt);
+    *nt_out = nt;
+    return e;
   } else {
     const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
     const float2 h = fma2(r[4], vx, fma2(r[5], vy, mul2(r[6], vz)));
@@ -173,8 +177,18 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
     const float2 an = fma2(r[4], NX, fma2(r[5], NY, mul2(r[6], NZ)));
     const float2 t1 = fma2(r[7], an, r[9]);
     const float2 nt = fma2(rho, t1, neg2(wn));
-    return max2_nan(e, nt);
+    *nt_out = nt;
+    return e;
   }
+}
+
+// margin of a candidate pair = max(distance term, angle term), NaN-propagating
+template <int T>
+__device__ __forceinline__ float2 eval2(const float2* r, float px, float py, float pz, float nx, float ny,
+                                        float nz, float eps, float cosa) {
+  float2 nt;
+  const float2 e = eval2_terms<T>(r, px, py, pz, nx, ny, nz, eps, cosa, &nt);
+  return max2_nan(e, nt);
 }
 
 // runtime-type version for the (rare) slow path

@@ -1,11 +1,17 @@
 // rsc_extract.cu -- K4: refit + invalidate_indexes! for one shape over the whole cloud shard
 // (plane.jl:137-143, sphere.jl:179-190, cylinder.jl:228-234, cone.jl:176-182, fitting.jl:197-202).
 //
-// One thread per point, HBM bound (24 B/point + 1/8 B of enabled mask).  Three launches:
-//   1. extract_mask_kernel   compatibility (FP32, FP64 inside the guard band) AND enabled ->
-//                            inlier bitmask word per warp + inlier count per CTA
-//   2. scan_counts_kernel    exclusive scan of the CTA counts (one CTA)
-//   3. extract_write_kernel  ascending global indices by stream compaction; clears enabled bits
+// HBM bound (24 B/point + 1/8 B of enabled mask).  Launches:
+//   1. extract_mask_kernel<T>  four points per thread (128-bit loads of the six SoA rows, skipped for
+//                              disabled points), FP32 margin -> inlier bitmask words; points whose
+//                              margin is inside the guard band are queued
+//   2. extract_fix_kernel      the queued points in FP64, in the reference's operation order
+//                              (rsc_exact.cuh); patches their mask bits.  If the queue overflowed
+//                              (flat cones: every point is "ambiguous") it re-scans the whole range.
+//   3. block_count_kernel, scan_counts_kernel   exclusive scan of the per-CTA inlier counts
+//   4. extract_write_kernel    ascending global indices by stream compaction; clears enabled bits
+#include <stdlib.h>
+
 #include "rsc_eval.cuh"
 #include "rsc_exact.cuh"
 
@@ -20,10 +26,15 @@ struct ExtractArgs {
   rsc_cand cand;
   ex::ConeTrig trig;
   float pmax, nmax;
-  uint32_t* inl;           // [n_pad/32]
-  int64_t block0;          // first CTA-sized block of this rank's point range
+  uint32_t* inl;    // [n_pad/32]
+  int64_t block0;   // first CTA-sized block of this rank's point range
+  int64_t nblocks;  // blocks of the range
+  uint32_t* queue;  // local indices of points inside the guard band
+  uint32_t* qn;     // queue fill
+  uint32_t qcap;
 };
 
+template <int T>
 __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_constant__ ExtractArgs a) {
   __shared__ float r[kRecFields];
   if (threadIdx.x == 0) {
@@ -32,30 +43,94 @@ __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_c
     for (int f = 0; f < kRecFields; ++f) r[f] = t[f];
   }
   __syncthreads();
-  const int type = a.cand.type;
   const float band = r[kBandField];
-  const float eps = a.th.eps[type], cosa = a.th.cosa[type];
+  const float eps = a.th.eps[T], cosa = a.th.cosa[T];
+  float rr[RecN<T>::n];
+#pragma unroll
+  for (int f = 0; f < RecN<T>::n; ++f) rr[f] = r[f];
+  const int64_t base = (a.block0 + blockIdx.x) * kExPts;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int it = 0; it < kExPts / (kExThreads * 4); ++it) {
+    const int64_t p = base + ((int64_t)it * kExThreads + threadIdx.x) * 4;  // n_pad is a multiple of 512
+    uint32_t okb = 0;
+    if (p < a.ps.n_pad) {
+      const uint32_t nib = (__ldg(a.ps.enabled + (p >> 5)) >> (p & 31)) & 0xFu;
+      if (nib) {
+        const float4 X = __ldg(reinterpret_cast<const float4*>(a.ps.x + p));
+        const float4 Y = __ldg(reinterpret_cast<const float4*>(a.ps.y + p));
+        const float4 Z = __ldg(reinterpret_cast<const float4*>(a.ps.z + p));
+        const float4 U = __ldg(reinterpret_cast<const float4*>(a.ps.nx + p));
+        const float4 V = __ldg(reinterpret_cast<const float4*>(a.ps.ny + p));
+        const float4 W = __ldg(reinterpret_cast<const float4*>(a.ps.nz + p));
+        const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
+        const float nx[4] = {U.x, U.y, U.z, U.w}, ny[4] = {V.x, V.y, V.z, V.w}, nz[4] = {W.x, W.y, W.z, W.w};
+        uint32_t amb = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float m = eval<T>(rr, px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
+          okb |= (m < 0.f ? 1u : 0u) << q;
+          amb |= (!(fabsf(m) > band) ? 1u : 0u) << q;
+        }
+        okb &= nib;
+        amb &= nib;
+        if (amb) {  // rare
+          const uint32_t cnt = __popc(amb);
+          uint32_t pos = atomicAdd(a.qn, cnt);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if ((amb >> q) & 1u) {
+              if (pos < a.qcap) a.queue[pos] = (uint32_t)(p + q);
+              ++pos;
+            }
+        }
+      }
+    }
+    uint32_t v = okb << ((lane & 7) * 4);
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    v |= __shfl_xor_sync(0xffffffffu, v, 4);
+    if ((lane & 7) == 0 && p < a.ps.n_pad) a.inl[p >> 5] = v;
+  }
+}
+
+// FP64 decisions for the queued points (or, after a queue overflow, for every enabled point of the
+// range whose FP32 margin is inside the band)
+__global__ void __launch_bounds__(256) extract_fix_kernel(const __grid_constant__ ExtractArgs a) {
+  const uint32_t n = *a.qn;
+  const int type = a.cand.type;
+  auto decide = [&](uint32_t pt) {
+    const bool ok = ex::compat(a.cand, a.trig, a.th,
+                               ex::V3{(double)a.ps.x[pt], (double)a.ps.y[pt], (double)a.ps.z[pt]},
+                               ex::V3{(double)a.ps.nx[pt], (double)a.ps.ny[pt], (double)a.ps.nz[pt]});
+    const uint32_t bit = 1u << (pt & 31);
+    if (ok)
+      atomicOr(a.inl + (pt >> 5), bit);
+    else
+      atomicAnd(a.inl + (pt >> 5), ~bit);
+  };
+  if (n <= a.qcap) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) decide(a.queue[e]);
+    return;
+  }
+  __shared__ float r[kRecFields];
+  if (threadIdx.x == 0) {
+    float t[kRecFields];
+    compile_record(a.cand, a.th, a.pmax, a.nmax, t);
+    for (int f = 0; f < kRecFields; ++f) r[f] = t[f];
+  }
+  __syncthreads();
   float rr[kRecFields];
 #pragma unroll
   for (int f = 0; f < kRecFields; ++f) rr[f] = r[f];
-  const int64_t base = (a.block0 + blockIdx.x) * kExPts;
-#pragma unroll 2
-  for (int it = 0; it < kExPts / kExThreads; ++it) {
-    const int64_t p = base + it * kExThreads + threadIdx.x;
-    if (p >= a.ps.n_pad) break;  // n_pad is a multiple of 512: whole warps leave together
-    const uint32_t en = __ldg(a.ps.enabled + (p >> 5));
-    bool ok = false;
-    if ((en >> (p & 31)) & 1u) {
-      const float x = __ldg(a.ps.x + p), y = __ldg(a.ps.y + p), z = __ldg(a.ps.z + p);
-      const float nx = __ldg(a.ps.nx + p), ny = __ldg(a.ps.ny + p), nz = __ldg(a.ps.nz + p);
-      const float m = eval_any(type, rr, x, y, z, nx, ny, nz, eps, cosa);
-      ok = m < 0.f;
-      if (!(fabsf(m) > band))
-        ok = ex::compat(a.cand, a.trig, a.th, ex::V3{(double)x, (double)y, (double)z},
-                        ex::V3{(double)nx, (double)ny, (double)nz});
-    }
-    const unsigned w = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0) a.inl[p >> 5] = w;
+  const int64_t lo = a.block0 * kExPts;
+  int64_t hi = (a.block0 + a.nblocks) * kExPts;
+  if (hi > a.ps.n_pad) hi = a.ps.n_pad;
+  for (int64_t p = lo + blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += (int64_t)gridDim.x * blockDim.x) {
+    if (!((a.ps.enabled[p >> 5] >> (p & 31)) & 1u)) continue;
+    const float m = eval_any(type, rr, a.ps.x[p], a.ps.y[p], a.ps.z[p], a.ps.nx[p], a.ps.ny[p], a.ps.nz[p], a.th.eps[type],
+                             a.th.cosa[type]);
+    if (!(fabsf(m) > rr[kBandField])) decide((uint32_t)p);
   }
 }
 
@@ -181,10 +256,39 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
     RSC_CUDA(ctx, cudaMemsetAsync(a.inl, 0, (size_t)words * 4, st));
   }
   a.block0 = b0;
+  a.nblocks = b1 - b0;
+  size_t qcap = (size_t)1 << 20;
+  if (const char* e = getenv("RSC_EXQ_CAP")) {  // test hook: force the queue-overflow path
+    const long v = atol(e);
+    if (v > 0) qcap = (size_t)v;
+  }
+  RSC_CUDA(ctx, ctx->exq.ensure(qcap * 4 + 16));
+  a.qn = ctx->exq.as<uint32_t>();
+  a.queue = a.qn + 4;
+  a.qcap = (uint32_t)qcap;
+  RSC_CUDA(ctx, cudaMemsetAsync(a.qn, 0, 4, st));
+  const unsigned grid = (unsigned)(b1 - b0);
   RSC_CUDA(ctx, cudaEventRecord(ctx->evr0, st));
-  extract_mask_kernel<<<(unsigned)(b1 - b0), kExThreads, 0, st>>>(a);
+  switch (cand.type) {
+    case RSC_PLANE:
+      extract_mask_kernel<RSC_PLANE><<<grid, kExThreads, 0, st>>>(a);
+      break;
+    case RSC_SPHERE:
+      extract_mask_kernel<RSC_SPHERE><<<grid, kExThreads, 0, st>>>(a);
+      break;
+    case RSC_CYLINDER:
+      extract_mask_kernel<RSC_CYLINDER><<<grid, kExThreads, 0, st>>>(a);
+      break;
+    case RSC_CONE:
+      extract_mask_kernel<RSC_CONE><<<grid, kExThreads, 0, st>>>(a);
+      break;
+    default:
+      return fail(ctx, RSC_E_ARG, "refit: unknown shape type");
+  }
   RSC_CUDA(ctx, cudaGetLastError());
   RSC_CUDA(ctx, cudaEventRecord(ctx->evr1, st));
+  extract_fix_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a);
+  RSC_CUDA(ctx, cudaGetLastError());
   if (sharded && ctx->allreduce(ctx->allreduce_user, a.inl, words, (void*)st))
     return fail(ctx, RSC_E_NCCL, "refit: all-reduce callback failed");
   block_count_kernel<<<(nblocks + 255) / 256, 256, 0, st>>>(a.inl, words, block_counts, nblocks);

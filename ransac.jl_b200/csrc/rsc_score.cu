@@ -80,16 +80,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-// one lane: fetch sub-tile `sub` (6 SoA rows of 128 floats) into a warp-private stage
-__device__ __forceinline__ void issue_subtile(const PointSet& ps, int sub, float* stage, uint64_t* bar) {
-  const int64_t off = (int64_t)sub * kSub;
+// one lane: fetch one sub-tile (6 SoA rows of 128 floats, `stride` floats apart) into a warp-private stage
+__device__ __forceinline__ void issue_subtile(const float* src, int64_t stride, float* stage, uint64_t* bar) {
   mbar_expect_tx(bar, kSubBytes);
-  bulk_g2s(stage + 0 * kSub, ps.x + off, kSub * 4, bar);
-  bulk_g2s(stage + 1 * kSub, ps.y + off, kSub * 4, bar);
-  bulk_g2s(stage + 2 * kSub, ps.z + off, kSub * 4, bar);
-  bulk_g2s(stage + 3 * kSub, ps.nx + off, kSub * 4, bar);
-  bulk_g2s(stage + 4 * kSub, ps.ny + off, kSub * 4, bar);
-  bulk_g2s(stage + 5 * kSub, ps.nz + off, kSub * 4, bar);
+#pragma unroll
+  for (int f = 0; f < 6; ++f) bulk_g2s(stage + f * kSub, src + f * stride, kSub * 4, bar);
 }
 
 // K candidates per thread; for even K they are evaluated as K/2 packed pairs (FFMA2 path).
@@ -138,11 +133,78 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
   const uint32_t* enp = a.ps.enabled + (size_t)sub0 * (kSub / 32);
   const uint32_t* vap = a.ps.valid + (size_t)sub0 * (kSub / 32);
   uint32_t* maskp = MASKS ? a.masks + (size_t)sub0 * (kSub / 32) * a.cslots + slot0 + tid : nullptr;
+  const int64_t stride = a.ps.y - a.ps.x;  // the six SoA rows are equally spaced (host-checked)
+  const float* src0 = a.ps.x + (int64_t)sub0 * kSub;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s)
-      if (s < nsub) issue_subtile(a.ps, sub0 + s, wstage + s * kSubFloats, wbar + s);
+      if (s < nsub) issue_subtile(src0 + s * kSub, stride, wstage + s * kSubFloats, wbar + s);
   }
+
+  // four points (6 broadcast 128-bit loads) against the thread's K candidates
+  auto body4 = [&](const float* gp, uint32_t (&mask)[K], float (&mabs)[K]) {
+    const float4 X = *reinterpret_cast<const float4*>(gp);
+    const float4 Y = *reinterpret_cast<const float4*>(gp + kSub);
+    const float4 Z = *reinterpret_cast<const float4*>(gp + 2 * kSub);
+    const float4 U4 = *reinterpret_cast<const float4*>(gp + 3 * kSub);
+    const float4 V = *reinterpret_cast<const float4*>(gp + 4 * kSub);
+    const float4 W = *reinterpret_cast<const float4*>(gp + 5 * kSub);
+    const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
+    const float nx[4] = {U4.x, U4.y, U4.z, U4.w}, ny[4] = {V.x, V.y, V.z, V.w}, nz[4] = {W.x, W.y, W.z, W.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if constexpr (kPacked) {
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+          const float2 m = eval2<T>(r2[j], px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
+          mask[2 * j] = __funnelshift_l(__float_as_uint(m.x), mask[2 * j], 1);  // sign bit = compatible
+          mask[2 * j + 1] = __funnelshift_l(__float_as_uint(m.y), mask[2 * j + 1], 1);
+          mabs[2 * j] = fmin_nan(mabs[2 * j], fabsf(m.x));
+          mabs[2 * j + 1] = fmin_nan(mabs[2 * j + 1], fabsf(m.y));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const float m = eval<T>(r[k], px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
+          mask[k] = __funnelshift_l(__float_as_uint(m), mask[k], 1);
+          mabs[k] = fmin_nan(mabs[k], fabsf(m));
+        }
+      }
+    }
+  };
+
+  // group epilogue: counts (+ mask words); the guard-band queue is the rare path
+  auto epilogue = [&](const uint32_t (&mask)[K], const float (&mabs)[K], int gi, uint32_t en, uint32_t va) {
+    const uint32_t ben = __brev(en), bva = __brev(va);
+    bool amb = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      amb |= !(mabs[k] > band[k]);
+      cnte[k] += __popc(mask[k] & ben);
+    }
+    if (!honour) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) cntv[k] += __popc(mask[k] & bva);
+    }
+    if constexpr (MASKS) {
+      const uint32_t gate = honour ? en : va;
+#pragma unroll
+      for (int k = 0; k < K; ++k) maskp[(size_t)gi * a.cslots + k * kThreads] = __brev(mask[k]) & gate;
+    }
+    if (amb && va) {  // rare: hand the group(s) to the FP64 fix-up kernels
+      const int64_t gw = (int64_t)sub0 * (kSub / 32) + gi;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (mabs[k] > band[k]) continue;
+        const int slot = slot0 + k * kThreads + tid;
+        const int o = a.orig[slot];
+        if (o < 0) continue;
+        const uint32_t pos = atomicAdd(a.wl_count, 1u);
+        if (pos < a.wl_cap) a.wl[pos] = GroupTask{(uint32_t)o, (uint32_t)gw, __brev(mask[k]), (uint32_t)slot | ((uint32_t)T << 28)};
+      }
+    }
+  };
+
   for (int it = 0; it < nsub; ++it) {
     const int st = it % kStages;
     mbar_wait(wbar + st, (it / kStages) & 1);
@@ -158,72 +220,12 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
       }
       const float* gx = sx + g * 32;
 #pragma unroll U
-      for (int i4 = 0; i4 < 32; i4 += 4) {
-        // 6 broadcast 128-bit loads = 4 points
-        const float4 X = *reinterpret_cast<const float4*>(gx + i4);
-        const float4 Y = *reinterpret_cast<const float4*>(gx + kSub + i4);
-        const float4 Z = *reinterpret_cast<const float4*>(gx + 2 * kSub + i4);
-        const float4 U4 = *reinterpret_cast<const float4*>(gx + 3 * kSub + i4);
-        const float4 V = *reinterpret_cast<const float4*>(gx + 4 * kSub + i4);
-        const float4 W = *reinterpret_cast<const float4*>(gx + 5 * kSub + i4);
-        const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
-        const float nx[4] = {U4.x, U4.y, U4.z, U4.w}, ny[4] = {V.x, V.y, V.z, V.w}, nz[4] = {W.x, W.y, W.z, W.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if constexpr (kPacked) {
-#pragma unroll
-            for (int j = 0; j < KP; ++j) {
-              const float2 m = eval2<T>(r2[j], px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
-              mask[2 * j] = __funnelshift_l(__float_as_uint(m.x), mask[2 * j], 1);  // sign bit = compatible
-              mask[2 * j + 1] = __funnelshift_l(__float_as_uint(m.y), mask[2 * j + 1], 1);
-              mabs[2 * j] = fmin_nan(mabs[2 * j], fabsf(m.x));
-              mabs[2 * j + 1] = fmin_nan(mabs[2 * j + 1], fabsf(m.y));
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-              const float m = eval<T>(r[k], px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
-              mask[k] = __funnelshift_l(__float_as_uint(m), mask[k], 1);
-              mabs[k] = fmin_nan(mabs[k], fabsf(m));
-            }
-          }
-        }
-      }
-      // ---- group epilogue: counts (+ mask words); the guard-band queue is the rare path ----
+      for (int i4 = 0; i4 < 32; i4 += 4) body4(gx + i4, mask, mabs);
       const int gi = it * (kSub / 32) + g;
-      const uint32_t en = __ldg(enp + gi);
-      const uint32_t va = __ldg(vap + gi);
-      const uint32_t ben = __brev(en), bva = __brev(va);
-      bool amb = false;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        amb |= !(mabs[k] > band[k]);
-        cnte[k] += __popc(mask[k] & ben);
-      }
-      if (!honour) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) cntv[k] += __popc(mask[k] & bva);
-      }
-      if constexpr (MASKS) {
-        const uint32_t gate = honour ? en : va;
-#pragma unroll
-        for (int k = 0; k < K; ++k) maskp[(size_t)gi * a.cslots + k * kThreads] = __brev(mask[k]) & gate;
-      }
-      if (amb && va) {  // rare: hand the group(s) to the FP64 fix-up kernels
-        const int64_t gw = (int64_t)sub0 * (kSub / 32) + gi;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          if (mabs[k] > band[k]) continue;
-          const int slot = slot0 + k * kThreads + tid;
-          const int o = a.orig[slot];
-          if (o < 0) continue;
-          const uint32_t pos = atomicAdd(a.wl_count, 1u);
-          if (pos < a.wl_cap) a.wl[pos] = GroupTask{(uint32_t)o, (uint32_t)gw, __brev(mask[k]), (uint32_t)slot | ((uint32_t)T << 28)};
-        }
-      }
+      epilogue(mask, mabs, gi, __ldg(enp + gi), __ldg(vap + gi));
     }
     __syncwarp();
-    if (lane == 0 && it + kStages < nsub) issue_subtile(a.ps, sub0 + it + kStages, wstage + st * kSubFloats, wbar + st);
+    if (lane == 0 && it + kStages < nsub) issue_subtile(src0 + (it + kStages) * kSub, stride, wstage + st * kSubFloats, wbar + st);
   }
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -543,8 +545,7 @@ struct Tiling {
     }                                                                                                   \
   }
 static const Tiling kTilings[] = {
-    RSC_TILING(1, 4, 1), RSC_TILING(2, 4, 1), RSC_TILING(2, 8, 1), RSC_TILING(4, 3, 1), RSC_TILING(4, 4, 1),
-    RSC_TILING(4, 5, 1), RSC_TILING(4, 6, 1), RSC_TILING(4, 4, 2), RSC_TILING(8, 2, 1), RSC_TILING(8, 3, 1),
+    RSC_TILING(1, 4, 1), RSC_TILING(2, 4, 1), RSC_TILING(4, 3, 1), RSC_TILING(4, 4, 1), RSC_TILING(8, 2, 1),
 };
 static const Tiling* find_tiling(int K, int minb, int U) {
   for (const Tiling& t : kTilings)
@@ -557,7 +558,7 @@ static int cap_k(int C) { return C >= 3072 ? 8 : (C >= 768 ? 2 : 1); }
 
 static const Tiling* pick_tiling(int type, int C) {
   static const char* names[RSC_NTYPES] = {"RSC_CFG_PLANE", "RSC_CFG_SPHERE", "RSC_CFG_CYLINDER", "RSC_CFG_CONE"};
-  static const int dflt[RSC_NTYPES][3] = {{4, 4, 1}, {4, 4, 1}, {4, 4, 1}, {4, 4, 1}};
+  static const int dflt[RSC_NTYPES][3] = {{4, 4, 1}, {4, 4, 1}, {4, 3, 1}, {4, 3, 1}};  // plane, sphere, cylinder, cone
   int K = dflt[type][0], minb = dflt[type][1], U = dflt[type][2];
   if (const char* e = getenv(names[type])) {
     int a = 0, b = 0, c = 0;
@@ -597,6 +598,11 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
                       const double* d_trig, const uint32_t* d_bounds, bool accumulate) {
   if (C <= 0) return RSC_OK;
   if (ps.n_pad >= ((int64_t)1 << 32)) return fail(ctx, RSC_E_ARG, "point set too large for one shard (>= 2^32)");
+  {
+    const int64_t sd = ps.y - ps.x;
+    if (ps.z - ps.y != sd || ps.nx - ps.z != sd || ps.ny - ps.nx != sd || ps.nz - ps.ny != sd)
+      return fail(ctx, RSC_E_ARG, "score: the six SoA rows of the point set must be equally spaced");
+  }
   const SlotLayout L = slot_layout(C);
   const int ncols = L.ncols, cslots = L.cslots;
   ctx->last_cslots = cslots;

@@ -211,3 +211,26 @@ def test_wide_and_flat_cones(R):
     for i in (0, 9, 13):
         ex = R.refit(cands[i], pc, params)
         np.testing.assert_array_equal(ex.inpoints, np.flatnonzero(wmask[i]))
+
+
+def test_refit_guard_queue_overflow(R, monkeypatch):
+    """refit queues the points inside the FP32 guard band for FP64; with a tiny queue the fix-up
+    kernel must fall back to re-scanning the range and still return the reference's list"""
+    from ransac_jl_b200 import scenes
+
+    monkeypatch.setenv("RSC_EXQ_CAP", "8")
+    sc = scenes.scene_mixed(106, 50_000)
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 1)
+    rng = np.random.default_rng(5)
+    en = rng.random(pc.size) > 0.3
+    pc.isenabled = en
+    params = R.ransacparameters()
+    P, N = sc.vertices.astype(np.float64), sc.normals.astype(np.float64)
+    a = np.array([0.0, 0.0, 1.0])
+    flat = R.FittedCone(P[10] - a * 0.5, a, math.radians(176.0), True)  # infinite band: every enabled point queues
+    cands = [p.shape for p in sc.primitives][:6] + [flat]
+    want, wmask = _oracle_counts(cands, P, N, oracle_params(params), enabled=en)
+    for i, sh in enumerate(cands):
+        ex = R.refit(sh, pc, params)
+        m = wmask[i] & en
+        np.testing.assert_array_equal(ex.inpoints, np.flatnonzero(m))
