@@ -32,22 +32,23 @@ struct ExtractArgs {
   uint32_t* queue;  // local indices of points inside the guard band
   uint32_t* qn;     // queue fill
   uint32_t qcap;
+  float* rec;       // [kRecFields] compiled record of the shape
 };
+
+// the shape's FP32 record, compiled once (FP64 sqrt/sin/cos on one thread) ahead of the streaming kernel
+__global__ void extract_compile_kernel(const __grid_constant__ ExtractArgs a) {
+  float t[kRecFields];
+  compile_record(a.cand, a.th, a.pmax, a.nmax, t);
+  for (int f = 0; f < kRecFields; ++f) a.rec[f] = t[f];
+}
 
 template <int T>
 __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_constant__ ExtractArgs a) {
-  __shared__ float r[kRecFields];
-  if (threadIdx.x == 0) {
-    float t[kRecFields];
-    compile_record(a.cand, a.th, a.pmax, a.nmax, t);
-    for (int f = 0; f < kRecFields; ++f) r[f] = t[f];
-  }
-  __syncthreads();
-  const float band = r[kBandField];
+  const float band = __ldg(a.rec + kBandField);
   const float eps = a.th.eps[T], cosa = a.th.cosa[T];
   float rr[RecN<T>::n];
 #pragma unroll
-  for (int f = 0; f < RecN<T>::n; ++f) rr[f] = r[f];
+  for (int f = 0; f < RecN<T>::n; ++f) rr[f] = __ldg(a.rec + f);
   const int64_t base = (a.block0 + blockIdx.x) * kExPts;
   const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -113,16 +114,9 @@ __global__ void __launch_bounds__(256) extract_fix_kernel(const __grid_constant_
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) decide(a.queue[e]);
     return;
   }
-  __shared__ float r[kRecFields];
-  if (threadIdx.x == 0) {
-    float t[kRecFields];
-    compile_record(a.cand, a.th, a.pmax, a.nmax, t);
-    for (int f = 0; f < kRecFields; ++f) r[f] = t[f];
-  }
-  __syncthreads();
   float rr[kRecFields];
 #pragma unroll
-  for (int f = 0; f < kRecFields; ++f) rr[f] = r[f];
+  for (int f = 0; f < kRecFields; ++f) rr[f] = a.rec[f];
   const int64_t lo = a.block0 * kExPts;
   int64_t hi = (a.block0 + a.nblocks) * kExPts;
   if (hi > a.ps.n_pad) hi = a.ps.n_pad;
@@ -262,12 +256,15 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
     const long v = atol(e);
     if (v > 0) qcap = (size_t)v;
   }
-  RSC_CUDA(ctx, ctx->exq.ensure(qcap * 4 + 16));
+  RSC_CUDA(ctx, ctx->exq.ensure(qcap * 4 + 16 + kRecFields * 4));
   a.qn = ctx->exq.as<uint32_t>();
-  a.queue = a.qn + 4;
+  a.rec = reinterpret_cast<float*>(a.qn + 4);
+  a.queue = a.qn + 4 + kRecFields;
   a.qcap = (uint32_t)qcap;
   RSC_CUDA(ctx, cudaMemsetAsync(a.qn, 0, 4, st));
   const unsigned grid = (unsigned)(b1 - b0);
+  extract_compile_kernel<<<1, 1, 0, st>>>(a);
+  RSC_CUDA(ctx, cudaGetLastError());
   RSC_CUDA(ctx, cudaEventRecord(ctx->evr0, st));
   switch (cand.type) {
     case RSC_PLANE:

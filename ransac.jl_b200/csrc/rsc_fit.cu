@@ -188,7 +188,7 @@ __device__ inline void singular_values3(const double* A, int c, double* s) {
           B[j][t] = sn * bi + cs * bj;
         }
       }
-    if (off < 1e-17) break;
+    if (off <= 2.220446049250313e-16) break;  // every pair orthogonal to working precision (de Rijk's criterion)
   }
   for (int i = 0; i < 3; ++i) {
     double q = 0;
@@ -267,14 +267,25 @@ __device__ inline double project2cone(D3 apex, D3 axis, double ct, double st, D3
 
 __device__ bool fit_cone(const D3* p, const D3* n, const FitParams& f, rsc_cand* out) {
   const double r[9] = {n[0].x, n[0].y, n[0].z, n[1].x, n[1].y, n[1].z, n[2].x, n[2].y, n[2].z};
-  if (!full_rank3(r, 3)) return false;
   const double ds[3] = {dot(p[0], n[0]), dot(p[1], n[1]), dot(p[2], n[2])};
-  double rv[12];
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) rv[i * 4 + j] = r[i * 3 + j];
-    rv[i * 4 + 3] = -1 * ds[i];
+  // rank(r) == 3 && rank([r | -d]) == 3 (cone.jl:44,48).  Shortcut that cannot disagree with the SVD:
+  // sigma_min(r) = |det| / (s1 s2) >= 2 |det| / |r|_F^2, the augmented matrix has sigma_min >= that of r,
+  // and both tolerances are <= 3 eps |[r | -d]|_F.  Only when the bound is within a factor 1e4 of the
+  // tolerance (numerically singular normals) are the singular values computed.
+  const double det = r[0] * (r[4] * r[8] - r[5] * r[7]) - r[1] * (r[3] * r[8] - r[5] * r[6]) + r[2] * (r[3] * r[7] - r[4] * r[6]);
+  double fr = 0.0;
+  for (int i = 0; i < 9; ++i) fr += r[i] * r[i];
+  const double fa = fr + ds[0] * ds[0] + ds[1] * ds[1] + ds[2] * ds[2];
+  const bool clearly_full = 2.0 * fabs(det) > 1e4 * (3 * 2.220446049250313e-16) * sqrt(fa) * fr;  // false on NaN/Inf
+  if (!clearly_full) {
+    if (!full_rank3(r, 3)) return false;
+    double rv[12];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) rv[i * 4 + j] = r[i * 3 + j];
+      rv[i * 4 + 3] = -1 * ds[i];
+    }
+    if (!full_rank3(rv, 4)) return false;
   }
-  if (!full_rank3(rv, 4)) return false;
   double ax3[3];
   if (!solve3(r, ds, ax3)) return false;
   const D3 ap = {ax3[0], ax3[1], ax3[2]};  // apex = intersection of the three tangent planes
@@ -554,18 +565,26 @@ int32_t build_select_index(rsc_cloud* cloud, cudaStream_t st, unsigned long long
   return RSC_OK;
 }
 
+// exclusive scan of n counts by ONE CTA (n is small: flags of a batch, block counts of a mask);
+// every thread takes 8 consecutive elements per pass, so 8192 elements cost one block-wide scan
 __global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restrict__ counts, int n,
                                                         unsigned long long* __restrict__ offsets,
                                                         unsigned long long* __restrict__ out_total) {
+  constexpr int E = 8;
   __shared__ unsigned long long wex[32];
   __shared__ unsigned long long carry, chunk_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + tid;
-    const unsigned long long v = i < n ? counts[i] : 0ull;
-    unsigned long long inc = v;
+  for (int base = 0; base < n; base += 1024 * E) {
+    const int i0 = base + tid * E;
+    uint32_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) v[e] = (i0 + e < n) ? counts[i0 + e] : 0u;
+    unsigned long long s = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) s += v[e];
+    unsigned long long inc = s;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
@@ -585,7 +604,12 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restri
       if (lane == 31) chunk_total = ti;
     }
     __syncthreads();
-    if (i < n) offsets[i] = carry + wex[warp] + (inc - v);
+    unsigned long long run = carry + wex[warp] + (inc - s);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      if (i0 + e < n) offsets[i0 + e] = run;
+      run += v[e];
+    }
     __syncthreads();
     if (tid == 0) carry += chunk_total;
     __syncthreads();

@@ -189,11 +189,22 @@ static double prob_(double n, double s, double N, double k) { return 1 - pow(1 -
 
 using namespace rsc;
 
+// Result of one run.  The inlier index lists stay in device memory (one arena, disjoint lists, in
+// extraction order) until the caller fetches them with rsc_run_inpoints: no per-extraction host
+// buffer, no device->host traffic inside the loop.
 struct rsc_run {
   std::vector<rsc_cand> shapes;
-  std::vector<std::vector<int64_t>> inpoints;
+  std::vector<int64_t> off{0};  // off[i]..off[i+1]: list of shape i inside d_idx
+  int64_t* d_idx = nullptr;
+  int device = 0;
   int iterations = 0;
   double seconds = 0.0;
+  ~rsc_run() {
+    if (d_idx) {
+      cudaSetDevice(device);
+      cudaFree(d_idx);
+    }
+  }
 };
 
 extern "C" {
@@ -248,7 +259,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   int64_t n_enabled = rsc_cloud_count_enabled(cloud);
   int64_t counters[3] = {0, 0, 0};  // lengthC, allcand, nofminset (iterations.jl:70)
   const bool trace = getenv("RSC_TRACE") != nullptr;
-  double t_fit = 0, t_score = 0, t_extract = 0, t_k5 = 0;
+  double t_fit = 0, t_score = 0, t_extract = 0, t_k5 = 0, t_exa = 0, t_exb = 0;
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
     return std::chrono::duration<double>(b - a).count();
@@ -269,6 +280,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
 
   RUN_CUDA(newcnt.ensure((size_t)2 * maxnew * 4 + 64));
   RUN_CUDA(hostio.ensure(64));
+  run->device = ctx->device;
+  RUN_CUDA(cudaMalloc(&run->d_idx, (size_t)(n_enabled > 0 ? n_enabled : 1) * sizeof(int64_t)));  // every point is extracted at most once
 
   for (int k = 1; k <= p->itermax; ++k) {
     if (n_enabled < p->tau) break;  // iterations.jl:75
@@ -332,27 +345,23 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           RUN_CUDA(cudaMemcpyAsync(&shape, store.cands[store.cur].as<rsc_cand>() + best[0], sizeof(shape),
                                    cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaStreamSynchronize(st));
+          const auto tka = now();
+          t_exa += secs(tk2, tka);
           Thresh thr = th;
           thr.honour_enabled = 0xFu;
           if ((rc = refit_mask_enqueue(cloud, thr, shape, st))) goto done;
           unsigned long long total = 0;
           RUN_CUDA(cudaMemcpyAsync(&total, ctx->misc2.p, 8, cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaStreamSynchronize(st));
+          t_exb += secs(tka, now());
           // keep the subset's enabled words of before the extraction
           const int64_t swords = sub.m_pad / 32;
           RUN_CUDA(olden.ensure((size_t)swords * 4));
           RUN_CUDA(cudaMemcpyAsync(olden.p, sub.enabled, (size_t)swords * 4, cudaMemcpyDeviceToDevice, st));
-          std::vector<int64_t> idx((size_t)total);
-          int64_t* d_out = nullptr;
-          if (total) {
-            RUN_CUDA(ctx->misc.ensure((size_t)total * 8));
-            d_out = ctx->misc.as<int64_t>();
-          }
-          if ((rc = refit_write_enqueue(cloud, d_out, true, st))) goto done;
-          if (total) RUN_CUDA(cudaMemcpyAsync(idx.data(), d_out, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
-          RUN_CUDA(cudaStreamSynchronize(st));
+          int64_t* d_out = run->d_idx + run->off.back();
+          if ((rc = refit_write_enqueue(cloud, total ? d_out : nullptr, true, st))) goto done;
           run->shapes.push_back(shape);
-          run->inpoints.push_back(std::move(idx));
+          run->off.push_back(run->off.back() + (int64_t)total);
           n_enabled -= (int64_t)total;
           const auto tk3 = now();
           t_extract += secs(tk2, tk3);
@@ -428,8 +437,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
 done:
   cudaStreamSynchronize(st);
   if (trace)
-    fprintf(stderr, "[rsc_ransac_run] iterations %d shapes %zu | sample+fit %.1f ms, score+argmax %.1f ms, refit+extract %.1f ms, invalidate+compact %.1f ms\n",
-            run->iterations, run->shapes.size(), 1e3 * t_fit, 1e3 * t_score, 1e3 * t_extract, 1e3 * t_k5);
+    fprintf(stderr, "[rsc_ransac_run] iterations %d shapes %zu | sample+fit %.1f ms, score+argmax %.1f ms, refit+extract %.1f ms (shape fetch %.1f, mask+count %.1f), invalidate+compact %.1f ms\n",
+            run->iterations, run->shapes.size(), 1e3 * t_fit, 1e3 * t_score, 1e3 * t_extract, 1e3 * t_exa, 1e3 * t_exb, 1e3 * t_k5);
   cleanup();
   if (rc) {
     delete run;
@@ -448,14 +457,17 @@ double rsc_run_seconds(const rsc_run* r) { return r ? r->seconds : 0.0; }
 int32_t rsc_run_shape(const rsc_run* r, int32_t i, rsc_cand* shape, int64_t* n_inpoints) {
   if (!r || i < 0 || (size_t)i >= r->shapes.size()) return RSC_E_ARG;
   if (shape) *shape = r->shapes[i];
-  if (n_inpoints) *n_inpoints = (int64_t)r->inpoints[i].size();
+  if (n_inpoints) *n_inpoints = r->off[i + 1] - r->off[i];
   return RSC_OK;
 }
 
 int32_t rsc_run_inpoints(const rsc_run* r, int32_t i, int64_t* out_idx) {
   if (!r || i < 0 || (size_t)i >= r->shapes.size() || !out_idx) return RSC_E_ARG;
-  memcpy(out_idx, r->inpoints[i].data(), r->inpoints[i].size() * sizeof(int64_t));
-  return RSC_OK;
+  const int64_t n = r->off[i + 1] - r->off[i];
+  if (n == 0) return RSC_OK;
+  if (cudaSetDevice(r->device) != cudaSuccess) return RSC_E_CUDA;
+  return cudaMemcpy(out_idx, r->d_idx + r->off[i], (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost) == cudaSuccess ? RSC_OK
+                                                                                                                        : RSC_E_CUDA;
 }
 
 void rsc_run_destroy(rsc_run* r) { delete r; }

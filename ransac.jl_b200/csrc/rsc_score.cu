@@ -660,7 +660,8 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   a.subs_per_chunk = (int)((nsubs + chunks - 1) / chunks);
   chunks = (nsubs + a.subs_per_chunk - 1) / a.subs_per_chunk;
   dim3 grid((unsigned)ncols, (unsigned)chunks);
-  const bool fork = (double)C * (double)ps.n_pad >= 1e9 && !getenv("RSC_NOFORK");
+  // (worth the fork/join events from ~1e7 evaluations on: four short kernels overlap instead of queueing)
+  const bool fork = (double)C * (double)ps.n_pad >= 1e7 && !getenv("RSC_NOFORK");
 
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
   if (fork) RSC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));

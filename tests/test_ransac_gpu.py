@@ -101,3 +101,19 @@ def test_sharded_callback_single_rank(R):
     for a, b in zip(plain, sharded):
         assert list(a.shape.to_cand().p) == list(b.shape.to_cand().p)
         np.testing.assert_array_equal(a.inpoints, b.inpoints)
+
+
+def test_large_cloud_matches_oracle(R):
+    """300 k points (the sampler's rank/select index spans more than one scan pass), 8 subsets,
+    256 minimal sets per iteration: shapes, inlier lists and the final isenabled equal the oracle's"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(83, 300_000, noise_frac=0.002, jitter_deg=1.0, outlier_frac=0.1, counts=(3, 1, 1, 1))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 8)
+    params = R.ransacparameters(iteration={"tau": 3000, "minsubsetN": 256, "itermax": 40})
+    extracted, secs = R.ransac(pc, params, True, seed=99)
+    oc = O.Cloud(sc.vertices, sc.normals, [s.copy() for s in pc.subsets])
+    want = O.ransac(oc, oracle_params(params), True, seed=99)
+    _compare_runs(R, extracted, want)
+    assert len(extracted) >= 3
+    np.testing.assert_array_equal(pc.isenabled, oc.isenabled)
