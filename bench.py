@@ -336,7 +336,7 @@ def main():
         out["refit"] = {"error": repr(e)}
     if args.ransac != "none" and world == 1:
         out["ransac"] = time_ransac(R, args.ransac, local)
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         # ~10 s of CPU work: 512 candidates (every 8th) x all points of rank 0's shard of the same workload
         out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or len(sc.vertices), ncand=512)
     print(json.dumps(out))

@@ -104,7 +104,7 @@ int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
     delete ctx;
     return RSC_E_CUDA;
   }
-  for (int i = 0; i < 3; ++i)
+  for (int i = 0; i < 4; ++i)
     if (cudaStreamCreateWithFlags(&ctx->sfork[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
       delete ctx;
@@ -124,7 +124,7 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
   for (auto* b : bufs) b->release();
   ctx->stage[0].release(), ctx->stage[1].release();
   cudaStreamDestroy(ctx->copy_stream);
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < 4; ++i) {
     if (ctx->sfork[i]) cudaStreamSynchronize(ctx->sfork[i]), cudaStreamDestroy(ctx->sfork[i]);
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }

@@ -16,6 +16,11 @@ constexpr int kTile = 512;         // points staged in shared memory per tile
 constexpr int kGroupsPerTile = kTile / 32;
 constexpr int kRecFields = 12;     // floats per compiled candidate record (SoA over slots)
 constexpr int kBandField = 11;     // record field holding the FP32 guard band
+// Column (kernel) types of the tiled scorer: the four public shape types plus wide cones (opening
+// angle > 120 deg), which are evaluated in a form scaled by 1/sin(opang/2) instead of 1/cos(opang/2).
+constexpr int kColTypes = 5;
+constexpr int kConeWide = 4;
+__host__ __device__ constexpr int public_type(int col_type) { return col_type == kConeWide ? RSC_CONE : col_type; }
 
 // SoA float32 view of a set of points resident in HBM (the whole cloud shard or a gathered subset).
 // All arrays have n_pad (multiple of kTile) elements; padding points are zero with enabled=valid=0.
@@ -81,8 +86,8 @@ struct rsc_ctx {
   cudaStream_t copy_stream = nullptr;  // host->device uploads, overlapped with scoring of earlier chunks
   rsc::DevBuf stage[2];                // double-buffered AoS staging of one upload chunk
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
-  cudaStream_t sfork[3] = {nullptr, nullptr, nullptr};  // the per-type score kernels of one call run side by side
-  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t sfork[4] = {nullptr, nullptr, nullptr, nullptr};  // the per-type score kernels of one call run side by side
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   int last_cslots = 0;                 // slot stride of the last compiled candidate records / masks
   std::string err;
   rsc_stats stats{};

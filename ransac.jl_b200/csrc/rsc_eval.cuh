@@ -20,8 +20,10 @@
 //   * cone: both tests are divided by c = cos(opang/2) > 0 (sign-preserving):
 //     dist/c = h tan - rho,   margin/c = rho (cos(alpha)/c + tan (a.n)) - w.n,
 //     so the record carries tan, eps/c and cos(alpha)/c and the margin (and its guard band) are in
-//     units of 1/c.  Cones with c < 1/16 (opening angle > 172.8 deg) get an infinite band: every pair
-//     of theirs is decided by the FP64 path.
+//     units of 1/c.  Cones wider than 120 degrees (c < 1/2; fits on near-planar patches produce them)
+//     form their own column type kConeWide, scaled by s = sin(opang/2) instead (24 ops):
+//     dist/s = h - rho cot,   margin/s = rho (cos(alpha)/s + a.n) - cot (w.n);
+//     only opening angles beyond ~352.8 deg (s < 1/16) fall back to an infinite band = all-FP64.
 #pragma once
 #include "rsc_common.cuh"
 
@@ -29,7 +31,13 @@ namespace rsc {
 
 // error-bound multipliers (units of 2^-24 * magnitude), calibrated in tests/test_guard_band.py
 __host__ __device__ constexpr float kappa(int type) {
-  return type == RSC_PLANE ? 8.f : type == RSC_SPHERE ? 16.f : type == RSC_CYLINDER ? 16.f : 20.f;
+  return type == RSC_PLANE ? 8.f : type == RSC_SPHERE ? 16.f : type == RSC_CYLINDER ? 16.f : 20.f;  // both cone forms: 20
+}
+
+// column type of a candidate: its public type, except cones wider than 120 degrees (cos(opang/2) < 1/2)
+__host__ __device__ inline int col_type(const rsc_cand& c) {
+  if (c.type != RSC_CONE) return c.type;
+  return cos(0.5 * c.p[6]) >= 0.5 ? RSC_CONE : kConeWide;  // NaN opang -> kConeWide (its record is "far")
 }
 
 __device__ __forceinline__ float fmax_nan(float a, float b) {
@@ -68,6 +76,10 @@ template <>
 struct RecN<RSC_CONE> {
   static constexpr int n = 10;
 };
+template <>
+struct RecN<kConeWide> {
+  static constexpr int n = 11;
+};
 
 // r: the used fields of the record (registers).  p = (x,y,z), n = (nx,ny,nz).
 template <int T>
@@ -98,6 +110,21 @@ __device__ __forceinline__ float eval(const float* r, float px, float py, float 
     float e = fabsf(d) - eps;
     float wn = fmaf(wx, nx, fmaf(wy, ny, fmaf(wz, nz, r[8])));
     float nt = fmaf(cosa, d, -wn);
+    return fmax_nan(e, nt);
+  } else if constexpr (T == kConeWide) {
+    // r0 = sg, r1..3 = -sg*apex, r4..6 = axis, r7 = sg*cot(opang/2), r8 = -eps/s, r9 = cos(alpha)/s, r10 = cot
+    float vx = fmaf(r[0], px, r[1]), vy = fmaf(r[0], py, r[2]), vz = fmaf(r[0], pz, r[3]);
+    float h = fmaf(r[4], vx, fmaf(r[5], vy, r[6] * vz));
+    float wx = fmaf(-r[4], h, vx), wy = fmaf(-r[5], h, vy), wz = fmaf(-r[6], h, vz);
+    float ww = fmaf(wx, wx, fmaf(wy, wy, wz * wz));
+    float rho = ww * rsqrt_fast(ww);
+    float d = fmaf(-rho, r[7], h);
+    float e = fabsf(d) + r[8];
+    float wn = fmaf(wx, nx, fmaf(wy, ny, wz * nz));
+    float an = fmaf(r[4], nx, fmaf(r[5], ny, r[6] * nz));
+    float t1 = fmaf(r[0], an, r[9]);
+    float cw = r[10] * wn;
+    float nt = fmaf(rho, t1, -cw);
     return fmax_nan(e, nt);
   } else {
     // r0 = sg, r1..3 = -sg*apex, r4..6 = axis, r7 = sg*tan(opang/2), r8 = -eps/c, r9 = cos(alpha)/c
@@ -165,6 +192,21 @@ __device__ __forceinline__ float2 eval2_terms(const float2* r, float px, float p
     const float2 nt = fma2(bc2(cosa), d, neg2(wn));
     *nt_out = nt;
     return e;
+  } else if constexpr (T == kConeWide) {
+    const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
+    const float2 h = fma2(r[4], vx, fma2(r[5], vy, mul2(r[6], vz)));
+    const float2 wx = fma2(neg2(r[4]), h, vx), wy = fma2(neg2(r[5]), h, vy), wz = fma2(neg2(r[6]), h, vz);
+    const float2 ww = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
+    const float2 rho = mul2(ww, rsqrt2(ww));
+    const float2 d = fma2(neg2(rho), r[7], h);
+    const float2 e = add2(abs2(d), r[8]);
+    const float2 wn = fma2(wx, NX, fma2(wy, NY, mul2(wz, NZ)));
+    const float2 an = fma2(r[4], NX, fma2(r[5], NY, mul2(r[6], NZ)));
+    const float2 t1 = fma2(r[0], an, r[9]);
+    const float2 cw = mul2(r[10], wn);
+    const float2 nt = fma2(rho, t1, neg2(cw));
+    *nt_out = nt;
+    return e;
   } else {
     const float2 vx = fma2(r[0], X, r[1]), vy = fma2(r[0], Y, r[2]), vz = fma2(r[0], Z, r[3]);
     const float2 h = fma2(r[4], vx, fma2(r[5], vy, mul2(r[6], vz)));
@@ -191,7 +233,7 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
   return max2_nan(e, nt);
 }
 
-// runtime-type version for the (rare) slow path
+// runtime-type version for the (rare) slow path; `type` is a COLUMN type (col_type())
 __device__ __forceinline__ float eval_any(int type, const float* r, float px, float py, float pz,
                                           float nx, float ny, float nz, float eps, float cosa) {
   switch (type) {
@@ -201,6 +243,8 @@ __device__ __forceinline__ float eval_any(int type, const float* r, float px, fl
       return eval<RSC_SPHERE>(r, px, py, pz, nx, ny, nz, eps, cosa);
     case RSC_CYLINDER:
       return eval<RSC_CYLINDER>(r, px, py, pz, nx, ny, nz, eps, cosa);
+    case kConeWide:
+      return eval<kConeWide>(r, px, py, pz, nx, ny, nz, eps, cosa);
     default:
       return eval<RSC_CONE>(r, px, py, pz, nx, ny, nz, eps, cosa);
   }
@@ -210,7 +254,8 @@ __device__ __forceinline__ float eval_any(int type, const float* r, float px, fl
 // over the cloud, the scale of every intermediate and therefore of the rounding error.
 // A candidate with a non-finite parameter can match nothing in the reference (NaN compares
 // false); it gets a record that is far from everything so that no NaN reaches the tiled kernel.
-__device__ inline void compile_record(const rsc_cand& c, const Thresh& th, float pmax, float nmax, float* r /*[12]*/) {
+// `col` = col_type(c) as decided by the caller (the kernel that evaluates the record must use the same form).
+__device__ inline void compile_record(const rsc_cand& c, int col, const Thresh& th, float pmax, float nmax, float* r /*[12]*/) {
   const double u = 5.9604644775390625e-08;  // 2^-24
   for (int i = 0; i < kRecFields; ++i) r[i] = 0.f;
   bool finite = true;
@@ -272,22 +317,24 @@ __device__ inline void compile_record(const rsc_cand& c, const Thresh& th, float
       const double an = sqrt(c.p[3] * c.p[3] + c.p[4] * c.p[4] + c.p[5] * c.p[5]);
       const double ia = 1.0 / an;
       const double ch = cos(0.5 * c.p[6]), sh = sin(0.5 * c.p[6]);
-      const bool flat = !(ch >= 1.0 / 16.0);  // opening angle > 172.8 deg (or NaN): decided in FP64
-      if (!finite || !(an > 0.0) || !isfinite(ia) || flat) {
-        // far from everything; a flat cone additionally gets an infinite band (every pair -> FP64)
-        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 0.f, r[8] = 0.f, r[9] = 1.f;
+      const bool wide = (col == kConeWide);
+      const bool needle = wide && !(sh >= 1.0 / 16.0);  // opening angle beyond ~352.8 deg (or NaN): FP64 decides
+      if (!finite || !(an > 0.0) || !isfinite(ia) || needle) {
+        // far from everything; a finite "needle" additionally gets an infinite band (every pair -> FP64)
+        r[0] = 1.f, r[2] = 1e15f, r[4] = 1.f, r[7] = 0.f, r[8] = 0.f, r[9] = 1.f, r[10] = 0.f;
         r[kBandField] = (finite && an > 0.0 && isfinite(ia)) ? __int_as_float(0x7f800000) : 1.f;
         return;
       }
-      const double ic = 1.0 / ch;
+      const double sc = wide ? 1.0 / sh : 1.0 / ch;  // the margin is in units of 1/c (1/s for wide cones)
       r[0] = (float)sg;
       r[1] = (float)(-sg * c.p[0]), r[2] = (float)(-sg * c.p[1]), r[3] = (float)(-sg * c.p[2]);
       r[4] = (float)(c.p[3] * ia), r[5] = (float)(c.p[4] * ia), r[6] = (float)(c.p[5] * ia);
-      r[7] = (float)(sg * sh * ic);
-      r[8] = (float)(-th.eps_d[RSC_CONE] * ic);
-      r[9] = (float)(th.cosa_d[RSC_CONE] * ic);
+      r[7] = (float)(wide ? sg * ch * sc : sg * sh * sc);
+      r[8] = (float)(-th.eps_d[RSC_CONE] * sc);
+      r[9] = (float)(th.cosa_d[RSC_CONE] * sc);
+      r[10] = (float)(wide ? ch * sc : 0.0);
       double cn = sqrt(c.p[0] * c.p[0] + c.p[1] * c.p[1] + c.p[2] * c.p[2]);
-      L = (P + cn + 1.0) * nm * ic;  // the margin is in units of 1/c
+      L = (P + cn + 1.0) * nm * sc;
       break;
     }
   }

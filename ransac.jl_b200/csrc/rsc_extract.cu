@@ -33,19 +33,20 @@ struct ExtractArgs {
   uint32_t* qn;     // queue fill
   uint32_t qcap;
   float* rec;       // [kRecFields] compiled record of the shape
+  int col;          // column type (col_type(cand), decided on the host)
 };
 
 // the shape's FP32 record, compiled once (FP64 sqrt/sin/cos on one thread) ahead of the streaming kernel
 __global__ void extract_compile_kernel(const __grid_constant__ ExtractArgs a) {
   float t[kRecFields];
-  compile_record(a.cand, a.th, a.pmax, a.nmax, t);
+  compile_record(a.cand, a.col, a.th, a.pmax, a.nmax, t);
   for (int f = 0; f < kRecFields; ++f) a.rec[f] = t[f];
 }
 
 template <int T>
 __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_constant__ ExtractArgs a) {
   const float band = __ldg(a.rec + kBandField);
-  const float eps = a.th.eps[T], cosa = a.th.cosa[T];
+  const float eps = a.th.eps[public_type(T)], cosa = a.th.cosa[public_type(T)];
   float rr[RecN<T>::n];
 #pragma unroll
   for (int f = 0; f < RecN<T>::n; ++f) rr[f] = __ldg(a.rec + f);
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kExThreads) extract_mask_kernel(const __grid_c
 // range whose FP32 margin is inside the band)
 __global__ void __launch_bounds__(256) extract_fix_kernel(const __grid_constant__ ExtractArgs a) {
   const uint32_t n = *a.qn;
-  const int type = a.cand.type;
+  const int type = a.cand.type;  // public type: thresholds
   auto decide = [&](uint32_t pt) {
     const bool ok = ex::compat(a.cand, a.trig, a.th,
                                ex::V3{(double)a.ps.x[pt], (double)a.ps.y[pt], (double)a.ps.z[pt]},
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) extract_fix_kernel(const __grid_constant_
   if (hi > a.ps.n_pad) hi = a.ps.n_pad;
   for (int64_t p = lo + blockIdx.x * blockDim.x + threadIdx.x; p < hi; p += (int64_t)gridDim.x * blockDim.x) {
     if (!((a.ps.enabled[p >> 5] >> (p & 31)) & 1u)) continue;
-    const float m = eval_any(type, rr, a.ps.x[p], a.ps.y[p], a.ps.z[p], a.ps.nx[p], a.ps.ny[p], a.ps.nz[p], a.th.eps[type],
+    const float m = eval_any(a.col, rr, a.ps.x[p], a.ps.y[p], a.ps.z[p], a.ps.nx[p], a.ps.ny[p], a.ps.nz[p], a.th.eps[type],
                              a.th.cosa[type]);
     if (!(fabsf(m) > rr[kBandField])) decide((uint32_t)p);
   }
@@ -263,12 +264,17 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
   a.qcap = (uint32_t)qcap;
   RSC_CUDA(ctx, cudaMemsetAsync(a.qn, 0, 4, st));
   const unsigned grid = (unsigned)(b1 - b0);
+  if (cand.type < 0 || cand.type >= RSC_NTYPES) return fail(ctx, RSC_E_ARG, "refit: unknown shape type");
+  a.col = col_type(cand);
   extract_compile_kernel<<<1, 1, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
   RSC_CUDA(ctx, cudaEventRecord(ctx->evr0, st));
-  switch (cand.type) {
+  switch (a.col) {
     case RSC_PLANE:
       extract_mask_kernel<RSC_PLANE><<<grid, kExThreads, 0, st>>>(a);
+      break;
+    case kConeWide:
+      extract_mask_kernel<kConeWide><<<grid, kExThreads, 0, st>>>(a);
       break;
     case RSC_SPHERE:
       extract_mask_kernel<RSC_SPHERE><<<grid, kExThreads, 0, st>>>(a);

@@ -192,6 +192,23 @@ using namespace rsc;
 // Result of one run.  The inlier index lists stay in device memory (one arena, disjoint lists, in
 // extraction order) until the caller fetches them with rsc_run_inpoints: no per-extraction host
 // buffer, no device->host traffic inside the loop.
+// 1 if either guard-band queue (groups, pairs) of the last score call overflowed
+__global__ void queue_overflow_kernel(const uint32_t* __restrict__ wl_count, uint32_t cap, int32_t* __restrict__ out) {
+  *out = (wl_count[0] > cap || wl_count[1] > cap) ? 1 : 0;
+}
+
+// after an overflow: size the queues for what the last call wanted (+25 %); the buffers themselves
+// are re-allocated by the next score_enqueue
+static int32_t grow_guard_queue(rsc_ctx* ctx) {
+  uint32_t n[2] = {0, 0};
+  if (cudaMemcpy(n, ctx->wl_count.p, sizeof(n), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return fail(ctx, RSC_E_CUDA, "ransac_run: reading the guard-band queue fill failed");
+  const size_t need = (size_t)(n[0] > n[1] ? n[0] : n[1]);
+  if (need > ctx->wl_cap) ctx->wl_cap = need + need / 4 + 1024;
+  else ctx->wl_cap = ctx->wl_cap * 2;  // another rank overflowed: keep the sizes moving together
+  return RSC_OK;
+}
+
 struct rsc_run {
   std::vector<rsc_cand> shapes;
   std::vector<int64_t> off{0};  // off[i]..off[i+1]: list of shape i inside d_idx
@@ -298,41 +315,58 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     counters[1] += n_new;
     const auto tk1 = now();
     t_fit += secs(tk0, tk1);
-    if (n_new > 0) {
-      RUN_CUDA(store.reserve((size_t)store.n + n_new, st));
-      rsc_cand* dst = store.cands[store.cur].as<rsc_cand>() + store.n;
-      RUN_CUDA(cudaMemcpyAsync(dst, fs.out, (size_t)n_new * sizeof(rsc_cand), cudaMemcpyDeviceToDevice, st));
-      // ---- K2 on subset 1 ----
-      int32_t* cv = newcnt.as<int32_t>();
-      int32_t* ce = cv + n_new;
-      PointSet ps = view_subset(&sub);
-      if (sharded) {
-        ps.x += slo, ps.y += slo, ps.z += slo, ps.nx += slo, ps.ny += slo, ps.nz += slo;
-        ps.enabled += slo / 32, ps.valid += slo / 32;
-        ps.n_pad = shi - slo;
-        ps.n = (sub.m < shi ? sub.m : shi) - slo;
+    // ---- K2 on subset 1 + K3 ----  (repeated with a larger guard-band queue if that overflowed:
+    // dropped queue entries would leave FP32 decisions in the counts)
+    const int store_n0 = store.n;
+    int64_t best[2] = {-1, 0};
+    for (int attempt = 0;; ++attempt) {
+      store.n = store_n0;
+      int32_t ovf = 0;
+      if (n_new > 0) {
+        RUN_CUDA(store.reserve((size_t)store.n + n_new, st));
+        rsc_cand* dst = store.cands[store.cur].as<rsc_cand>() + store.n;
+        RUN_CUDA(cudaMemcpyAsync(dst, fs.out, (size_t)n_new * sizeof(rsc_cand), cudaMemcpyDeviceToDevice, st));
+        int32_t* cv = newcnt.as<int32_t>();
+        int32_t* ce = cv + n_new;
+        PointSet ps = view_subset(&sub);
+        if (sharded) {
+          ps.x += slo, ps.y += slo, ps.z += slo, ps.nx += slo, ps.ny += slo, ps.nz += slo;
+          ps.enabled += slo / 32, ps.valid += slo / 32;
+          ps.n_pad = shi - slo;
+          ps.n = (sub.m < shi ? sub.m : shi) - slo;
+        }
+        if ((rc = score_enqueue(ctx, cloud, ps, th, dst, n_new, nullptr, false, st, cv, ce))) goto done;
+        // overflow flag rides behind the counts, so that a sharded run decides to repeat collectively
+        queue_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, cv + 2 * n_new);
+        RUN_CUDA(cudaGetLastError());
+        if (sharded && (rc = ctx->allreduce(ctx->allreduce_user, cv, (int64_t)2 * n_new + 1, (void*)st))) {
+          rc = fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce callback failed");
+          goto done;
+        }
+        finish_new_kernel<<<(n_new + 255) / 256, 256, 0, st>>>(dst, n_new, cv, ce, th.honour_enabled,
+                                                               store.score[store.cur].as<int32_t>() + store.n,
+                                                               store.flags[store.cur].as<uint8_t>() + store.n);
+        RUN_CUDA(cudaGetLastError());
+        RUN_CUDA(cudaMemcpyAsync(&ovf, cv + 2 * n_new, 4, cudaMemcpyDeviceToHost, st));
+        store.n += n_new;
       }
-      if ((rc = score_enqueue(ctx, cloud, ps, th, dst, n_new, nullptr, false, st, cv, ce))) goto done;
-      if (sharded && (rc = ctx->allreduce(ctx->allreduce_user, cv, (int64_t)2 * n_new, (void*)st))) {
-        rc = fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce callback failed");
+      if (store.n >= 1) {
+        argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store.n,
+                                          hostio.as<int64_t>());
+        RUN_CUDA(cudaGetLastError());
+        RUN_CUDA(cudaMemcpyAsync(best, hostio.p, 16, cudaMemcpyDeviceToHost, st));
+      }
+      RUN_CUDA(cudaStreamSynchronize(st));
+      if (ovf == 0) break;
+      if (attempt >= 4) {
+        rc = fail(ctx, RSC_E_STATE, "ransac_run: guard-band queue kept overflowing");
         goto done;
       }
-      finish_new_kernel<<<(n_new + 255) / 256, 256, 0, st>>>(dst, n_new, cv, ce, th.honour_enabled,
-                                                             store.score[store.cur].as<int32_t>() + store.n,
-                                                             store.flags[store.cur].as<uint8_t>() + store.n);
-      RUN_CUDA(cudaGetLastError());
-      store.n += n_new;
+      if ((rc = grow_guard_queue(ctx))) goto done;
     }
     counters[2] = (int64_t)k * S;
     counters[0] = store.n;
     if (store.n >= 1) {
-      // ---- K3: best candidate ----
-      int64_t best[2] = {-1, 0};
-      argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store.n,
-                                        hostio.as<int64_t>());
-      RUN_CUDA(cudaGetLastError());
-      RUN_CUDA(cudaMemcpyAsync(best, hostio.p, 16, cudaMemcpyDeviceToHost, st));
-      RUN_CUDA(cudaStreamSynchronize(st));
       const auto tk2 = now();
       t_score += secs(tk1, tk2);
       if (best[0] >= 0) {
@@ -387,6 +421,9 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           int32_t* hit = nullptr;
           RUN_CUDA(ctx->counts.ensure((size_t)3 * nst * 4));
           hit = ctx->counts.as<int32_t>() + 2 * (size_t)nst;
+          unsigned long long kept = 0;
+          int nxt = store.cur ^ 1;
+          for (int attempt = 0;; ++attempt) {  // repeated if the guard-band queue overflowed
           if (nnew_dis > 0) {
             const int64_t sp = ((int64_t)nnew_dis + kTile - 1) / kTile * kTile;
             RUN_CUDA(nscratch.ensure((size_t)6 * sp * 4));
@@ -417,14 +454,22 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           RUN_CUDA(cudaGetLastError());
           scan_u32_kernel<<<1, 1024, 0, st>>>(keep, nst, koff, ktot);
           RUN_CUDA(cudaGetLastError());
-          const int nxt = store.cur ^ 1;
+          nxt = store.cur ^ 1;
           compact_store_kernel<<<(nst + 255) / 256, 256, 0, st>>>(
               store.cands[store.cur].as<rsc_cand>(), store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(),
               keep, koff, nst, store.cands[nxt].as<rsc_cand>(), store.score[nxt].as<int32_t>(), store.flags[nxt].as<uint8_t>());
           RUN_CUDA(cudaGetLastError());
-          unsigned long long kept = 0;
+          uint32_t wln[2] = {0, 0};
+          if (nnew_dis > 0) RUN_CUDA(cudaMemcpyAsync(wln, ctx->wl_count.p, 8, cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaMemcpyAsync(&kept, ktot, 8, cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaStreamSynchronize(st));
+          if (wln[0] <= ctx->wl_cap && wln[1] <= ctx->wl_cap) break;
+          if (attempt >= 4) {
+            rc = fail(ctx, RSC_E_STATE, "ransac_run: guard-band queue kept overflowing");
+            goto done;
+          }
+          if ((rc = grow_guard_queue(ctx))) goto done;
+          }
           store.cur = nxt;
           store.n = (int)kept;
           t_k5 += secs(tk3, now());

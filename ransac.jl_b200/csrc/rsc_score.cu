@@ -123,10 +123,11 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
     cnte[k] = 0;
     cntv[k] = 0;
   }
-  const float eps = a.th.eps[T], cosa = a.th.cosa[T];
+  constexpr int PT = public_type(T);
+  const float eps = a.th.eps[PT], cosa = a.th.cosa[PT];
   // honour: the type ANDs pc.isenabled into its inliers; otherwise (sphere, Q4) the policy count is
   // the validity-gated one and the enabled-gated count is kept beside it (the loop's "tainted" flag)
-  const bool honour = (a.th.honour_enabled >> T) & 1u;
+  const bool honour = (a.th.honour_enabled >> PT) & 1u;
 
   const int sub0 = blockIdx.y * a.subs_per_chunk;
   const int nsub = min(a.subs_per_chunk, a.nsubs - sub0);
@@ -304,13 +305,14 @@ __global__ void __launch_bounds__(256) fixup_scan_kernel(const __grid_constant__
     const uint32_t e = rd * warps + blockIdx.x * wpb + (threadIdx.x >> 5);
     if (e < n) {
       const GroupTask tk = a.wl[e];
-      const int type = (int)(tk.slot_type >> 28);
+      const int col = (int)(tk.slot_type >> 28);  // column type: selects the evaluation form
+      const int type = public_type(col);
       const int slot = (int)(tk.slot_type & 0x0fffffffu);
       float r[kRecFields];
 #pragma unroll
       for (int f = 0; f < kRecFields; ++f) r[f] = a.rec[(size_t)f * a.cslots + slot];
       const uint32_t pt = tk.group * 32u + lane;
-      const float m = eval_any(type, r, a.ps.x[pt], a.ps.y[pt], a.ps.z[pt], a.ps.nx[pt], a.ps.ny[pt], a.ps.nz[pt],
+      const float m = eval_any(col, r, a.ps.x[pt], a.ps.y[pt], a.ps.z[pt], a.ps.nx[pt], a.ps.ny[pt], a.ps.nz[pt],
                                a.th.eps[type], a.th.cosa[type]);
       const bool used = (tk.word >> lane) & 1u;
       if (!(fabsf(m) > r[kBandField])) {
@@ -378,7 +380,7 @@ __global__ void select_counts_kernel(const rsc_cand* __restrict__ cands, int C,
 // Column order is cone, cylinder, sphere, plane: the most expensive columns are scheduled first.
 // ---------------------------------------------------------------------------------------------
 struct ColSlots {
-  int v[RSC_NTYPES];  // slots per CTA column (= 128 x candidates per thread) of each type
+  int v[kColTypes];  // slots per CTA column (= 128 x candidates per thread) of each column type
 };
 
 __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restrict__ cands, int C, const Thresh th,
@@ -388,27 +390,27 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
                                                        float* __restrict__ rec, int32_t* __restrict__ orig,
                                                        int32_t* __restrict__ slot_of,
                                                        BlockTab* __restrict__ tab) {
-  __shared__ int cnt[RSC_NTYPES], off[RSC_NTYPES], run[RSC_NTYPES], tot[RSC_NTYPES];
-  __shared__ int wcnt[RSC_NTYPES][32], woff[RSC_NTYPES][32];
+  __shared__ int cnt[kColTypes], off[kColTypes], run[kColTypes], tot[kColTypes];
+  __shared__ int wcnt[kColTypes][32], woff[kColTypes][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (d_bounds) {  // scales of the chunk being scored, still on the device (chunked upload)
     pmax = sqrtf(__uint_as_float(d_bounds[0])) * 1.000001f;
     nmax = sqrtf(__uint_as_float(d_bounds[1])) * 1.000001f;
   }
-  if (tid < RSC_NTYPES) {
+  if (tid < kColTypes) {
     cnt[tid] = 0;
     run[tid] = 0;
   }
   __syncthreads();
   for (int i = tid; i < C; i += blockDim.x) {
     const int t = cands[i].type;
-    if (t >= 0 && t < RSC_NTYPES) atomicAdd(&cnt[t], 1);
+    if (t >= 0 && t < RSC_NTYPES) atomicAdd(&cnt[col_type(cands[i])], 1);
   }
   __syncthreads();
   if (tid == 0) {
-    const int order[RSC_NTYPES] = {RSC_CONE, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
+    const int order[kColTypes] = {kConeWide, RSC_CONE, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
     int s = 0, col = 0;
-    for (int oi = 0; oi < RSC_NTYPES; ++oi) {
+    for (int oi = 0; oi < kColTypes; ++oi) {
       const int t = order[oi];
       off[t] = s;
       const int spc = spcs.v[t];
@@ -424,11 +426,11 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
     int t = -1;
     if (i < C) {
       t = cands[i].type;
-      if (t < 0 || t >= RSC_NTYPES) t = -1;
+      t = (t < 0 || t >= RSC_NTYPES) ? -1 : col_type(cands[i]);
     }
     int myrank = 0;
 #pragma unroll
-    for (int tt = 0; tt < RSC_NTYPES; ++tt) {
+    for (int tt = 0; tt < kColTypes; ++tt) {
       const unsigned b = __ballot_sync(0xffffffffu, t == tt);
       if (t == tt) myrank = __popc(b & ((1u << lane) - 1u));
       if (lane == 0) wcnt[tt][warp] = __popc(b);
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
     __syncthreads();
     if (warp == 0) {
 #pragma unroll
-      for (int tt = 0; tt < RSC_NTYPES; ++tt) {
+      for (int tt = 0; tt < kColTypes; ++tt) {
         const int v = wcnt[tt][lane];
         int inc = v;
 #pragma unroll
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
       if (t >= 0) {
         const int slot = off[t] + run[t] + woff[t][warp] + myrank;
         float r[kRecFields];
-        compile_record(cands[i], th, pmax, nmax, r);
+        compile_record(cands[i], t, th, pmax, nmax, r);
 #pragma unroll
         for (int f = 0; f < kRecFields; ++f) rec[(size_t)f * cslots + slot] = r[f];
         orig[slot] = i;
@@ -463,11 +465,11 @@ __global__ void __launch_bounds__(1024) compile_kernel(const rsc_cand* __restric
       }
     }
     __syncthreads();
-    if (tid < RSC_NTYPES) run[tid] += tot[tid];
+    if (tid < kColTypes) run[tid] += tot[tid];
     __syncthreads();
   }
   // padding slots replicate the last real candidate of their type (orig = -1: results dropped)
-  for (int t = 0; t < RSC_NTYPES; ++t) {
+  for (int t = 0; t < kColTypes; ++t) {
     const int n = cnt[t];
     if (n == 0) continue;
     const int spc = spcs.v[t];
@@ -531,17 +533,19 @@ Thresh make_thresh(const rsc_params* p) {
 using ScoreFn = void (*)(const ScoreArgs);
 struct Tiling {
   int K, minb, U;
-  ScoreFn fn[RSC_NTYPES];       // counts only
-  ScoreFn fn_masks[RSC_NTYPES]; // counts + packed inlier bitmasks
+  ScoreFn fn[kColTypes];       // counts only
+  ScoreFn fn_masks[kColTypes]; // counts + packed inlier bitmasks
 };
 #define RSC_TILING(K, MINB, U)                                                                          \
   Tiling {                                                                                              \
     K, MINB, U,                                                                                         \
         {score_kernel<RSC_PLANE, K, MINB, U, false>, score_kernel<RSC_SPHERE, K, MINB, U, false>,       \
-         score_kernel<RSC_CYLINDER, K, MINB, U, false>, score_kernel<RSC_CONE, K, MINB, U, false>},     \
+         score_kernel<RSC_CYLINDER, K, MINB, U, false>, score_kernel<RSC_CONE, K, MINB, U, false>,      \
+         score_kernel<kConeWide, K, MINB, U, false>},                                                   \
     {                                                                                                   \
       score_kernel<RSC_PLANE, K, MINB, U, true>, score_kernel<RSC_SPHERE, K, MINB, U, true>,            \
-          score_kernel<RSC_CYLINDER, K, MINB, U, true>, score_kernel<RSC_CONE, K, MINB, U, true>        \
+          score_kernel<RSC_CYLINDER, K, MINB, U, true>, score_kernel<RSC_CONE, K, MINB, U, true>,       \
+          score_kernel<kConeWide, K, MINB, U, true>                                                     \
     }                                                                                                   \
   }
 static const Tiling kTilings[] = {
@@ -557,8 +561,8 @@ static const Tiling* find_tiling(int K, int minb, int U) {
 static int cap_k(int C) { return C >= 3072 ? 8 : (C >= 768 ? 2 : 1); }
 
 static const Tiling* pick_tiling(int type, int C) {
-  static const char* names[RSC_NTYPES] = {"RSC_CFG_PLANE", "RSC_CFG_SPHERE", "RSC_CFG_CYLINDER", "RSC_CFG_CONE"};
-  static const int dflt[RSC_NTYPES][3] = {{4, 4, 1}, {4, 4, 1}, {4, 3, 1}, {4, 3, 1}};  // plane, sphere, cylinder, cone
+  static const char* names[kColTypes] = {"RSC_CFG_PLANE", "RSC_CFG_SPHERE", "RSC_CFG_CYLINDER", "RSC_CFG_CONE", "RSC_CFG_CONE"};
+  static const int dflt[kColTypes][3] = {{4, 4, 1}, {4, 4, 1}, {4, 3, 1}, {4, 3, 1}, {4, 3, 1}};  // plane, sphere, cylinder, cone, wide cone
   int K = dflt[type][0], minb = dflt[type][1], U = dflt[type][2];
   if (const char* e = getenv(names[type])) {
     int a = 0, b = 0, c = 0;
@@ -574,20 +578,20 @@ static const Tiling* pick_tiling(int type, int C) {
 
 // layout of the compiled records for C candidates: per-type slots per column, total slot stride
 struct SlotLayout {
-  const Tiling* til[RSC_NTYPES];
+  const Tiling* til[kColTypes];
   ColSlots spcs;
   int ncols, cslots;
 };
 static SlotLayout slot_layout(int C) {
   SlotLayout L;
   int min_spc = 1 << 30, sum_spc = 0;
-  for (int t = 0; t < RSC_NTYPES; ++t) {
+  for (int t = 0; t < kColTypes; ++t) {
     L.til[t] = pick_tiling(t, C);
     L.spcs.v[t] = kThreads * L.til[t]->K;
     min_spc = min(min_spc, L.spcs.v[t]);
     sum_spc += L.spcs.v[t];
   }
-  L.ncols = (C + min_spc - 1) / min_spc + RSC_NTYPES;
+  L.ncols = (C + min_spc - 1) / min_spc + kColTypes;
   L.cslots = ((C + sum_spc + 127) / 128) * 128;  // sum over types of ceil(cnt_t / spc_t) * spc_t <= C + sum spc_t
   return L;
 }
@@ -666,8 +670,8 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
   if (fork) RSC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
   // most expensive type first
-  const int order[RSC_NTYPES] = {RSC_CONE, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
-  for (int oi = 0; oi < RSC_NTYPES; ++oi) {
+  const int order[kColTypes] = {RSC_CONE, kConeWide, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
+  for (int oi = 0; oi < kColTypes; ++oi) {
     const int t = order[oi];
     cudaStream_t s = st;
     if (fork && oi > 0) {

@@ -212,13 +212,32 @@ def scene_cad(n: int = 10_000_000, seed: int = 4, nprims: int = 200) -> Scene:
     return build_scene(rng, prims, n, 0.005, 1.0, 0.05)
 
 
-def scene_lidar(n: int = 100_000_000, seed: int = 5) -> Scene:
-    """c5: LiDAR-like, 8 large planes (60 %), 30 cylinders (10 %), 30 % outliers."""
+LIDAR_CHUNK = 12_500_000
+
+
+def lidar_primitives(seed: int = 5):
     rng = np.random.default_rng(seed)
     prims = [make_plane(rng, box=100.0, smin=80.0, smax=100.0) for _ in range(8)]
     prims += [make_cylinder(rng, rmin=0.3, rmax=1.0, lmin=5.0, lmax=15.0) for _ in range(30)]
     w = [0.6 / 8] * 8 + [0.1 / 30] * 30
-    return build_scene(rng, prims, n, 0.002, 2.0, 0.3, weights=w)
+    return prims, w
+
+
+def scene_lidar_chunk(i: int, n_chunk: int, seed: int = 5) -> Scene:
+    """points [i*LIDAR_CHUNK, i*LIDAR_CHUNK + n_chunk) of the c5 scene: every chunk is an independent
+    shuffled draw from the same primitives (so ranks can generate chunks side by side)"""
+    prims, w = lidar_primitives(seed)
+    return build_scene(np.random.default_rng([seed, 1000 + i]), prims, n_chunk, 0.002, 2.0, 0.3, weights=w)
+
+
+def scene_lidar(n: int = 100_000_000, seed: int = 5) -> Scene:
+    """c5: LiDAR-like, 8 large planes (60 %), 30 cylinders (10 %), 30 % outliers; generated in
+    chunks of 12.5 M points."""
+    parts = []
+    for i, lo in enumerate(range(0, n, LIDAR_CHUNK)):
+        parts.append(scene_lidar_chunk(i, min(LIDAR_CHUNK, n - lo), seed))
+    return Scene(np.concatenate([p.vertices for p in parts]), np.concatenate([p.normals for p in parts]),
+                 np.concatenate([p.labels for p in parts]), parts[0].primitives)
 
 
 def perturbed_candidates(scene: Scene, per_type: int, seed: int = 7, pos=0.3, ang_deg=1.5, rel=0.01):

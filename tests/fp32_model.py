@@ -38,10 +38,15 @@ def record(kind, outw, p, pmax, nmax, eps=0.3, cosa=math.cos(math.radians(5))):
     else:
         ax = np.array(p[3:6]) / np.linalg.norm(p[3:6])  # the reference's cone test only uses the axis direction
         ch, sh = math.cos(p[6] / 2), math.sin(p[6] / 2)
-        assert ch >= 1 / 16, "flat cones are decided in FP64 (infinite band)"
-        scale = 1.0 / ch
-        r = [sg, *(-sg * np.array(p[0:3])), *ax, sg * sh / ch, -eps / ch, cosa / ch]
-        L = (pmax + np.linalg.norm(p[0:3]) + 1) * nm / ch
+        apex = np.array(p[0:3])
+        if ch >= 0.5:  # column type RSC_CONE: margin in units of 1/cos(opang/2)
+            scale = 1.0 / ch
+            r = [sg, *(-sg * apex), *ax, sg * sh * scale, -eps * scale, cosa * scale]
+        else:  # column type kConeWide: margin in units of 1/sin(opang/2)
+            assert sh >= 1 / 16, "needle cones are decided in FP64 (infinite band)"
+            scale = 1.0 / sh
+            r = [sg, *(-sg * apex), *ax, sg * ch * scale, -eps * scale, cosa * scale, ch * scale]
+        L = (pmax + np.linalg.norm(apex) + 1) * nm * scale
     return [f32(x) for x in r], KAPPA[kind] * U * L, scale
 
 
@@ -71,6 +76,13 @@ def margin32(kind, r, P, N, eps, cosa):
         return np.maximum(e, fma(d, cosa, -wn))
     rho = ww * rsqrt(ww)
     wn = fma(wx, nx, fma(wy, ny, wz * nz))
+    if len(r) == 11:  # wide cone
+        d = fma(-rho, r[7], h)
+        e = np.abs(d) + r[8]
+        an = fma(nx, r[4], fma(ny, r[5], nz * r[6]))
+        t1 = fma(an, r[0], r[9])
+        cw = (r[10] * wn).astype(f32)
+        return np.maximum(e, fma(rho, t1, -cw))
     d = fma(h, r[7], -rho)
     e = np.abs(d) + r[8]
     an = fma(nx, r[4], fma(ny, r[5], nz * r[6]))

@@ -61,3 +61,26 @@ def test_fp32_far_candidates_within_band():
             m64 = M.margin64(kind, True, p, P, N, eps, cosa) * scale
             ok = np.isfinite(m32) & np.isfinite(m64)
             assert (np.abs(m32 - m64)[ok] / band).max() < 0.5, kind
+
+
+def test_fp32_wide_cones_within_band():
+    """cones wider than 120 degrees use the 1/sin(opang/2)-scaled form (column type kConeWide)"""
+    rng = np.random.default_rng(4)
+    sc = S.scene_mixed(13, 30_000)
+    P, N = sc.vertices, sc.normals
+    pmax = float(np.sqrt((P.astype(np.float64) ** 2).sum(1)).max())
+    eps, cosa = 0.3, math.cos(math.radians(5))
+    worst = 0.0
+    for deg in (100.0, 119.0, 121.0, 150.0, 175.0, 179.9, 180.0, 185.0, 270.0, 340.0):
+        for outw in (True, False):
+            a = rng.normal(size=3); a /= np.linalg.norm(a)
+            apex = P[rng.integers(len(P))].astype(np.float64) - a * rng.uniform(0, 3)
+            p = [*apex, *a, math.radians(deg)]
+            r, band, scale = M.record(3, outw, p, pmax, 1.0, eps, cosa)
+            assert (len(r) == 11) == (deg > 120.0)
+            m32 = M.margin32(3, r, P, N, eps, cosa).astype(np.float64)
+            m64 = M.margin64(3, outw, p, P, N, eps, cosa) * scale
+            ok = np.isfinite(m32) & np.isfinite(m64)
+            worst = max(worst, float((np.abs(m32 - m64)[ok] / band).max()))
+    print("wide cones: max |m32-m64|/band", worst)
+    assert worst < 0.5

@@ -117,3 +117,28 @@ def test_large_cloud_matches_oracle(R):
     _compare_runs(R, extracted, want)
     assert len(extracted) >= 3
     np.testing.assert_array_equal(pc.isenabled, oc.isenabled)
+
+
+def test_tiny_guard_queue_and_wide_cones_match_oracle(R):
+    """a plane-dominated scene (three-point cone fits on planar patches give near-180-degree cones,
+    the kConeWide column type) run on a context whose guard-band queue starts with 32 entries: the
+    loop must notice every overflow, grow the queue and repeat, and still equal the oracle"""
+    import os
+
+    from ransac_jl_b200 import scenes
+
+    os.environ["RSC_WL_CAP"] = "32"
+    try:
+        ctx = R.Context(0)
+    finally:
+        del os.environ["RSC_WL_CAP"]
+    sc = scenes.scene_mixed(85, 60_000, noise_frac=0.003, jitter_deg=2.0, outlier_frac=0.2, counts=(4, 1, 0, 0))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4, ctx=ctx)
+    params = R.ransacparameters(iteration={"tau": 600, "minsubsetN": 256, "itermax": 60})
+    extracted, secs = R.ransac(pc, params, True, seed=7)
+    oc = O.Cloud(sc.vertices, sc.normals, [s.copy() for s in pc.subsets])
+    tr = O.RansacTrace()
+    want = O.ransac(oc, oracle_params(params), True, seed=7, trace=tr)
+    _compare_runs(R, extracted, want)
+    assert len(extracted) >= 3
+    np.testing.assert_array_equal(pc.isenabled, oc.isenabled)

@@ -21,7 +21,8 @@ from ransac_jl_b200 import scenes
 from ransac_jl_b200.shard import ShardedContext
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--scene", default="c2", choices=["c1", "c2", "c4", "c5small"])
+ap.add_argument("--scene", default="c2", choices=["c1", "c2", "c4", "c5small", "c5"])
+ap.add_argument("--points", type=int, default=100_000_000, help="c5: cloud size")
 ap.add_argument("--check", type=int, default=1)
 args = ap.parse_args()
 
@@ -40,9 +41,30 @@ elif args.scene == "c2":
 elif args.scene == "c4":
     sc, r = scenes.scene_cad(), 32
     it = {"tau": sc.vertices.shape[0] // 1000, "minsubsetN": 8192, "itermax": 400}
-else:
+elif args.scene == "c5small":
     sc, r = scenes.scene_lidar(10_000_000), 64
     it = {"tau": sc.vertices.shape[0] // 500, "minsubsetN": 8192, "itermax": 200}
+else:
+    # c5: the ranks generate the 12.5 M-point chunks of the scene side by side into /dev/shm, then
+    # every rank maps all of them (the cloud is replicated; scoring/refit are sharded by point range)
+    n, ch = args.points, scenes.LIDAR_CHUNK
+    nch = (n + ch - 1) // ch
+    tag = f"/dev/shm/rsc_c5_{n}"
+    for i in range(rank, nch, world):
+        part = scenes.scene_lidar_chunk(i, min(ch, n - i * ch))
+        np.save(f"{tag}_v{i}.npy", part.vertices)
+        np.save(f"{tag}_n{i}.npy", part.normals)
+    if world > 1:
+        dist.barrier()
+    V = np.concatenate([np.load(f"{tag}_v{i}.npy", mmap_mode="r") for i in range(nch)])
+    Nn = np.concatenate([np.load(f"{tag}_n{i}.npy", mmap_mode="r") for i in range(nch)])
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        for i in range(nch):
+            os.remove(f"{tag}_v{i}.npy"), os.remove(f"{tag}_n{i}.npy")
+    sc, r = scenes.Scene(V, Nn, None, scenes.lidar_primitives()[0]), 64
+    it = {"tau": n // 500, "minsubsetN": 8192, "itermax": 200}
 params = R.ransacparameters(iteration=it)
 pc = R.RANSACCloud(sc.vertices, sc.normals, r, device=local)
 sh = ShardedContext(pc) if world > 1 else None
