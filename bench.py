@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_EVAL = {"plane": 13, "sphere": 16, "cylinder": 27, "cone": 38}
 MIX_FLOPS = 23.5
-NCU_TRAFFIC_BYTES = 1.706e9  # measured, see profiles/r1d_score_kernels_ncu.json
+NCU_TRAFFIC_BYTES = 1.702e9  # measured: profiles/r1e_kernels_ncu_full.json (4 x ~408 MB read + 72 MB of fix-up queue writes)
 
 
 def parse():
@@ -302,7 +302,7 @@ def main():
     roofline = {
         "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of the four score kernels of one step, from the
-        # `ncu --set full` capture profiles/r1d_score_kernels_ncu.json (same command, 16 Mi points)
+        # `ncu --set full` capture profiles/r1e_kernels_ncu_full.json (same command, 16 Mi points)
         "traffic": NCU_TRAFFIC_BYTES if (Cn == 4096 and n == (16 << 20)) else None,
         "peak_source": f"derived: {nsm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry; "
                        "the path uses no tensor cores and is not HBM bound)",
