@@ -199,6 +199,8 @@ int32_t rsc_run_nshapes(const rsc_run* run);
 int32_t rsc_run_iterations(const rsc_run* run);
 double rsc_run_seconds(const rsc_run* run);
 int32_t rsc_run_shape(const rsc_run* run, int32_t i, rsc_cand* shape, int64_t* n_inpoints);
+/* The inlier index lists of a run stay in device memory until they are asked for: this call copies
+ * list i (ascending 0-based global indices, n_inpoints of rsc_run_shape) into the caller's buffer. */
 int32_t rsc_run_inpoints(const rsc_run* run, int32_t i, int64_t* out_idx);
 void rsc_run_destroy(rsc_run* run);
 
