@@ -47,6 +47,11 @@ extern "C" {
 /* compat_flags: reference behaviours that can be switched off (SURVEY.md 8a' quirk numbers) */
 #define RSC_COMPAT_SPHERE_IGNORES_ENABLED 1u /* Q4: sphere.jl:121,131 */
 #define RSC_COMPAT_DEFAULT (RSC_COMPAT_SPHERE_IGNORES_ENABLED)
+/* extension switch (off by default): draw minimal sets with the level-weighted octree-cell sampler the
+ * reference is written for (fitting.jl:383-430, octree.jl:198-205) instead of from the root cell, which
+ * is what its shipped code always does (Q1: levelweight/levelscore swapped, octree.jl:82-84).
+ * Needs rsc_cloud_build_cells. */
+#define RSC_SAMPLER_OCTREE 2u
 
 /* which counter plays `s` in prob(n,s,N,k): utilities.jl:297-300 */
 #define RSC_S_LENGTHC 0
@@ -193,11 +198,28 @@ typedef int32_t (*rsc_allreduce_fn)(void* user, void* d_buf, int64_t count, void
 int32_t rsc_ctx_set_allreduce(rsc_ctx* ctx, rsc_allreduce_fn fn, void* user);
 int32_t rsc_cloud_set_range(rsc_cloud* cloud, int64_t lo, int64_t hi);
 
+/* ---- flattened octree + level-weighted cell sampler (extension) -------------
+ * Replaces the RegionTrees octree (octree.jl:158-244) by Morton-sorted cells: level 1 = the bounding
+ * box, every level halves each axis, a cell "splits" while it holds more than 8 points
+ * (octree.jl:163-165).  nlevels <= 11.  rsc_sample_fit_cells is rsc_sample_fit with the cell of a
+ * level drawn from `levelweight` (restricted to the levels above the first point's leaf);
+ * out_level[S] receives the level of every set.  rsc_update_levelweight is octree.jl:198-205. */
+int32_t rsc_cloud_build_cells(rsc_cloud* cloud, int32_t nlevels);
+int32_t rsc_cloud_cells_levels(const rsc_cloud* cloud);
+int32_t rsc_cloud_get_cells(rsc_cloud* cloud, uint32_t* codes_sorted, uint32_t* perm, uint8_t* leafdepth);
+int32_t rsc_sample_fit_cells(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, uint64_t set0, int32_t S,
+                             const double* levelweight, int32_t nlevels, rsc_cand* out, int32_t* out_set,
+                             int64_t* out_idx, int32_t* out_level, int32_t* out_n);
+void rsc_level_cumsum(const double* levelweight, int32_t nlevels, double* cum);
+void rsc_update_levelweight(double* levelweight, const double* levelscore, int32_t nlevels);
+
 /* ---- the whole loop: ransac(pc, params; ...) iterations.jl:35-162 for built-in shapes ------- */
 int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, rsc_run** out);
 int32_t rsc_run_nshapes(const rsc_run* run);
 int32_t rsc_run_iterations(const rsc_run* run);
 double rsc_run_seconds(const rsc_run* run);
+/* cell sampler runs: final level weights and accumulated level scores; returns the number of levels (0: root-cell run) */
+int32_t rsc_run_levelweight(const rsc_run* run, double* levelweight, double* levelscore);
 int32_t rsc_run_shape(const rsc_run* run, int32_t i, rsc_cand* shape, int64_t* n_inpoints);
 /* The inlier index lists of a run stay in device memory until they are asked for: this call copies
  * list i (ascending 0-based global indices, n_inpoints of rsc_run_shape) into the caller's buffer. */

@@ -730,6 +730,126 @@ def sample_minimal_set(pc: Cloud, drawN: int, stream: SetStream, enabled_idx: Op
 
 
 # --------------------------------------------------------------------------------------
+# Flattened octree + level-weighted cell sampler.  NOT the shipped reference's
+# behaviour: there `levelweight`/`levelscore` are swapped at construction (Q1, octree.jl:82-84), every
+# minimal set comes from the root cell and the octree never matters.  This restates what the code is
+# written to do (octree.jl:158-244, fitting.jl:383-430, octree.jl:198-205) on a Morton-ordered grid
+# hierarchy, and is the definition the device sampler is tested against:
+#   * root cell = bounding box of the cloud, every level halves each axis (like child_boundary,
+#     octree.jl:169); level 1 = root, level l uses the top l-1 bits per axis of the quantised
+#     coordinates q = floor((x - lo) / (hi - lo) * 2^D), D = nlevels - 1 (clamped to 2^D - 1);
+#   * a cell is split while it holds more than 8 points (OctreeRefinery(8), octree.jl:163-165,241):
+#     leafdepth(p) = first level at which p's cell holds <= 8 points, capped at nlevels;
+#   * enabled points of a cell are enumerated in Morton order (ties: original index).
+# --------------------------------------------------------------------------------------
+
+
+def morton3(q: np.ndarray, D: int) -> np.ndarray:
+    """interleave the D low bits of q[:,0], q[:,1], q[:,2] (x is the most significant of each triple)"""
+    code = np.zeros(len(q), np.int64)
+    for b in range(D - 1, -1, -1):
+        code = (code << 3) | (((q[:, 0] >> b) & 1) << 2) | (((q[:, 1] >> b) & 1) << 1) | ((q[:, 2] >> b) & 1)
+    return code
+
+
+class MortonOctree:
+    def __init__(self, vertices, nlevels: int):
+        assert 1 <= nlevels <= 11
+        V = np.asarray(vertices, dtype=F)
+        self.nlevels = nlevels
+        D = self.D = nlevels - 1
+        lo, hi = V.min(0), V.max(0)
+        w = hi - lo
+        w[w == 0] = 1.0
+        q = np.floor((V - lo) / w * float(1 << D)).astype(np.int64)
+        q = np.clip(q, 0, (1 << D) - 1)
+        code = morton3(q, D)
+        self.perm = np.argsort(code, kind="stable").astype(np.int64)  # sorted position -> point index
+        self.codes = code[self.perm]
+        self.inv = np.empty_like(self.perm)
+        self.inv[self.perm] = np.arange(len(V))
+        self.leafdepth = np.full(len(V), nlevels, np.int32)  # per point (original index)
+        undecided = np.ones(len(V), bool)
+        for l in range(1, nlevels + 1):
+            a, b = self._ranges(code, l)
+            small = undecided & ((b - a) <= 8)
+            self.leafdepth[small] = l
+            undecided &= ~small
+
+    def _ranges(self, code, level):
+        shift = 3 * (self.D - (level - 1))
+        pre = code >> shift
+        a = np.searchsorted(self.codes >> shift, pre, side="left")
+        b = np.searchsorted(self.codes >> shift, pre, side="right")
+        return a, b
+
+    def cell_range(self, point: int, level: int):
+        """[a, b) in Morton order of the level-`level` cell containing `point`"""
+        shift = 3 * (self.D - (level - 1))
+        pre = self.codes[self.inv[point]] >> shift
+        sc = self.codes >> shift
+        return int(np.searchsorted(sc, pre, side="left")), int(np.searchsorted(sc, pre, side="right"))
+
+
+def level_cumsum(levelweight) -> np.ndarray:
+    """cum[j-1] = levelweight[1] + ... + levelweight[j], summed left to right in float64"""
+    out, c = [], 0.0
+    for x in levelweight:
+        c += float(x)
+        out.append(c)
+    return np.array(out)
+
+
+def draw_level(u64: int, cum: np.ndarray, leafdepth: int) -> int:
+    """Level of the cell the other k-1 points come from: drawn from the level distribution restricted
+    to 1..leafdepth (docs/src/ransac.md:80-82 -- the shipped code takes argmax(levelweight[1:leafdepth])
+    instead, fitting.jl:401, which never leaves level 1).  1-based."""
+    target = (float(u64) * 2.0 ** -64) * float(cum[leafdepth - 1])
+    for l in range(1, leafdepth + 1):
+        if cum[l - 1] > target:
+            return l
+    return leafdepth
+
+
+def sample_minimal_set_octree(pc: "Cloud", oct: MortonOctree, drawN: int, stream: SetStream, cum, en_sorted: np.ndarray):
+    """samplepointcloud4! (fitting.jl:383-430) on the flattened octree.  `en_sorted` = isenabled in
+    Morton order, `cum` = level_cumsum(levelweight).  Returns (ok, level, idx)."""
+    N = pc.size
+    r1 = stream.rand_below(N)
+    while not pc.isenabled[r1]:
+        r1 = stream.rand_below(N)
+    level = draw_level(stream.next_u64(), cum, int(oct.leafdepth[r1]))
+    a, b = oct.cell_range(r1, level)
+    pos = np.flatnonzero(en_sorted[a:b]) + a
+    ne = len(pos)
+    idx = np.zeros(drawN, np.int64)
+    if ne < drawN:
+        return False, level, idx
+    idx[0] = r1
+    for k in range(1, drawN):
+        nexti = stream.rand_below(ne)
+        if idx[0] == oct.perm[pos[nexti]]:
+            nexti = stream.rand_below(ne)
+        idx[k] = oct.perm[pos[nexti]]
+    for i in range(1, drawN):
+        for j in range(i):
+            if idx[i] == idx[j]:
+                return False, level, idx
+    return True, level, idx
+
+
+def updatelevelweight(levelweight: np.ndarray, levelscore: np.ndarray, x: float = 0.9) -> np.ndarray:
+    """octree.jl:198-205; unchanged while no level has a score yet (w == 0 would give NaN)."""
+    P, sg = levelweight, levelscore
+    w = 0.0
+    for i in range(len(P)):
+        w += sg[i] / P[i]
+    if not w > 0.0:
+        return P.copy()
+    return np.array([x * sg[i] / (w * P[i]) + (1 - x) / len(P) for i in range(len(P))])
+
+
+# --------------------------------------------------------------------------------------
 # the loop (iterations.jl:35-162)
 # --------------------------------------------------------------------------------------
 
@@ -747,6 +867,7 @@ class RansacTrace:
     candidates_scored: int = 0
     evals: int = 0
     extracted_at: List[int] = field(default_factory=list)
+    levelweight: Optional[np.ndarray] = None
 
 
 def forcefit(p, n, params) -> List[Shape]:
@@ -766,6 +887,7 @@ def ransac(
     seed: int = 1234,
     minimal_sets: Optional[Callable[[int, int], Optional[np.ndarray]]] = None,
     trace: Optional[RansacTrace] = None,
+    octree: Optional[MortonOctree] = None,
 ) -> List[Extracted]:
     """iterations.jl:14-21 + :35-162.
 
@@ -785,30 +907,57 @@ def ransac(
     extracted: List[Extracted] = []
     cc = [0, 0, 0]
     tr = trace if trace is not None else RansacTrace()
+    if octree is not None:  # level-weighted cell sampler (8(f)-1); un-swapped initial values (octree.jl:82-83)
+        levelweight = np.full(octree.nlevels, 1.0 / octree.nlevels)
+        levelscore = np.zeros(octree.nlevels)
     for k in range(1, itermax + 1):
         if int(pc.isenabled.sum()) < tau:
             break
         tr.iterations = k
         cands: List[Shape] = []
+        levels: List[int] = []
         en_idx = np.flatnonzero(pc.isenabled)
+        if octree is not None:
+            cum = level_cumsum(levelweight)
+            en_sorted = pc.isenabled[octree.perm]
         for i in range(minsubsetN):
             if minimal_sets is not None:
                 sd = minimal_sets(k, i)
                 if sd is None:
                     continue
+            elif octree is not None:
+                ok, lvl, sd = sample_minimal_set_octree(pc, octree, drawN, SetStream(seed, (k - 1) * minsubsetN + i), cum, en_sorted)
+                if not ok:
+                    continue
+                fitted = forcefit(pc.vertices[sd], pc.normals[sd], params)
+                cands.extend(fitted)
+                levels.extend([lvl] * len(fitted))
+                continue
             else:
                 ok, _, sd = sample_minimal_set(pc, drawN, SetStream(seed, (k - 1) * minsubsetN + i), en_idx)
                 if not ok:
                     continue
             cands.extend(forcefit(pc.vertices[sd], pc.normals[sd], params))
         cc[1] += len(cands)
-        for c in cands:  # scorecandidates! (fitting.jl:181-190), subset 1 only (Q10)
+        lv_n = np.zeros(octree.nlevels if octree is not None else 0, np.int64)
+        lv_s = np.zeros_like(lv_n)
+        for ci, c in enumerate(cands):  # scorecandidates! (fitting.jl:181-190), subset 1 only (Q10)
             sc, ip = scorecandidate(pc, c, 0, params)
             shapes.append(c)
             scores.append(sc)
             inpts.append(ip)
             tr.candidates_scored += 1
             tr.evals += len(pc.subsets[0])
+            if octree is not None:
+                lv_n[levels[ci] - 1] += 1
+                lv_s[levels[ci] - 1] += len(ip)
+        if octree is not None:
+            # levelscore[level] += E(sc) (fitting.jl:184), summed in closed form per level:
+            # sum of E = -n + (N+2)/(M+2) * (sum of sigma + n)
+            M1, Nn = len(pc.subsets[0]), pc.size
+            for l in range(octree.nlevels):
+                if lv_n[l]:
+                    levelscore[l] += (-float(lv_n[l])) + (float(Nn + 2) / float(M1 + 2)) * float(lv_s[l] + lv_n[l])
         cc[2] = k * minsubsetN
         tr.sets_drawn = cc[2]
         cc[0] = len(shapes)
@@ -827,6 +976,9 @@ def ransac(
                 shapes = [shapes[j] for j in keep]
                 scores = [scores[j] for j in keep]
                 inpts = [inpts[j] for j in keep]
+        if octree is not None:
+            levelweight = updatelevelweight(levelweight, levelscore)  # iterations.jl:148
+            tr.levelweight = levelweight.copy()
         s = cc[sidx[it["terminate_s"]]]
         if prob(tau, s, pc.size, drawN) > prob_det:
             break

@@ -18,6 +18,7 @@ from .fitting import (
     invalidate_indexes,
     refit,
     sample_fit,
+    sample_fit_cells,
     score_counts,
     scorecandidate,
     scorecandidates,

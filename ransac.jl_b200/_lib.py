@@ -88,6 +88,13 @@ SIGNATURES = {
     "rsc_fit_batch": (C.c_int32, [_P, C.POINTER(rsc_params), _P, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
     "rsc_fit_points": (C.c_int32, [_P, C.POINTER(rsc_params), _P, _P, C.c_int32, C.c_int32, _P, _P, C.POINTER(C.c_int32)]),
     "rsc_sample_fit": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.c_uint64, C.c_int32, _P, _P, _P, C.POINTER(C.c_int32)]),
+    "rsc_cloud_build_cells": (C.c_int32, [_P, C.c_int32]),
+    "rsc_cloud_cells_levels": (C.c_int32, [_P]),
+    "rsc_cloud_get_cells": (C.c_int32, [_P, _P, _P, _P]),
+    "rsc_sample_fit_cells": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.c_uint64, C.c_int32, _P, C.c_int32, _P, _P, _P, _P,
+                                         C.POINTER(C.c_int32)]),
+    "rsc_level_cumsum": (None, [_P, C.c_int32, _P]),
+    "rsc_update_levelweight": (None, [_P, _P, C.c_int32]),
     "rsc_refit_extract": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), _P, C.POINTER(C.c_int64), C.c_int32]),
     "rsc_ctx_set_allreduce": (C.c_int32, [_P, _P, _P]),
     "rsc_cloud_set_range": (C.c_int32, [_P, C.c_int64, C.c_int64]),
@@ -95,6 +102,7 @@ SIGNATURES = {
     "rsc_run_nshapes": (C.c_int32, [_P]),
     "rsc_run_iterations": (C.c_int32, [_P]),
     "rsc_run_seconds": (C.c_double, [_P]),
+    "rsc_run_levelweight": (C.c_int32, [_P, _P, _P]),
     "rsc_run_shape": (C.c_int32, [_P, C.c_int32, C.POINTER(rsc_cand), C.POINTER(C.c_int64)]),
     "rsc_run_inpoints": (C.c_int32, [_P, C.c_int32, _P]),
     "rsc_run_destroy": (None, [_P]),
@@ -112,6 +120,8 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f.restype = _res
     _f.argtypes = _args
 
+
+RSC_SAMPLER_OCTREE = 2  # compat_flags: level-weighted octree-cell sampler (extension, include/rsc.h)
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 

@@ -95,6 +95,22 @@ class RANSACCloud:
         self.ctx.check(lib.rsc_cloud_set_subset(self._h, subset_id, s.ctypes.data, len(s)))
         self._uploaded.add(subset_id)
 
+    # -- flattened octree (extension) --------------------------------------
+    def build_cells(self, nlevels: int = 8):
+        """Morton-ordered octree cells for the level-weighted sampler (replaces RegionTrees,
+        octree.jl:158-244): level 1 = bounding box, every level halves each axis."""
+        self.ctx.check(lib.rsc_cloud_build_cells(self._h, int(nlevels)))
+        self.nlevels = int(nlevels)
+        return self
+
+    def get_cells(self):
+        """(sorted Morton codes, sorted position -> point index, leafdepth per point)"""
+        codes = np.zeros(self.size, np.uint32)
+        perm = np.zeros(self.size, np.uint32)
+        ld = np.zeros(self.size, np.uint8)
+        self.ctx.check(lib.rsc_cloud_get_cells(self._h, codes.ctypes.data, perm.ctypes.data, ld.ctypes.data))
+        return codes, perm, ld
+
     # -- pc.isenabled -------------------------------------------------------------------
     @property
     def isenabled(self) -> np.ndarray:

@@ -149,7 +149,8 @@ static int32_t cloud_upload(rsc_cloud* c, const T* xyz, const T* nrm) {
     RSC_CUDA(ctx, cudaEventRecord(c->chunk_ev[i], cs));
   }
   c->pending = true;
-  c->sel_valid = false;
+  c->enabled_changed();
+  if (c->cells.nlevels) cells_release(c);  // the octree was built for the old coordinates
   return RSC_OK;
 }
 
@@ -256,6 +257,7 @@ void rsc_cloud_destroy(rsc_cloud* c) {
     cudaStreamSynchronize(c->ctx->stream);
   }
   c->selbuf.release();
+  cells_release(c);
   for (auto e : c->chunk_ev) cudaEventDestroy(e);
   if (c->d_bounds) cudaFree(c->d_bounds);
   for (auto& s : c->subsets) {
@@ -329,7 +331,7 @@ int32_t rsc_cloud_set_enabled(rsc_cloud* c, const uint64_t* words) {
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)((c->n + 63) / 64) * 8;
   const int64_t w = c->n_pad / 32;
-  c->sel_valid = false;
+  c->enabled_changed();
   RSC_CUDA(ctx, cudaMemcpyAsync(c->enabled, words, bytes, cudaMemcpyHostToDevice, ctx->stream));
   and_words_kernel<<<(unsigned)((w + 255) / 256), 256, 0, ctx->stream>>>(c->enabled, c->valid, w);
   RSC_CUDA(ctx, cudaGetLastError());
@@ -344,7 +346,7 @@ int32_t rsc_cloud_enable_all(rsc_cloud* c) {
   if (int32_t rcr = cloud_ready(c)) return rcr;
   rsc_ctx* ctx = c->ctx;
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
-  c->sel_valid = false;
+  c->enabled_changed();
   RSC_CUDA(ctx, cudaMemcpyAsync(c->enabled, c->valid, (size_t)(c->n_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   for (auto& s : c->subsets)
     if (s.soa)

@@ -109,6 +109,20 @@ struct rsc_subset {
   int64_t* idx = nullptr;      // m local point indices (device)
 };
 
+// flattened octree of a cloud (rsc_octree.cu): Morton-sorted codes, cells = contiguous code ranges
+struct rsc_cells {
+  int nlevels = 0;               // 0: not built
+  uint32_t* codes = nullptr;     // [n] sorted Morton codes (3 (nlevels-1) bits)
+  uint32_t* perm = nullptr;      // [n] sorted position -> point index
+  uint32_t* inv = nullptr;       // [n] point index -> sorted position
+  uint8_t* leafdepth = nullptr;  // [n] by point index: first level whose cell holds <= 8 points
+  uint32_t* en_sorted = nullptr; // [n_pad/32] pc.isenabled in Morton order
+  bool en_valid = false;         // en_sorted matches the cloud's enabled mask
+  rsc::DevBuf selbuf;            // rank/select index over en_sorted
+  bool sel_valid = false;
+  double lo[3] = {0, 0, 0}, w[3] = {1, 1, 1};  // bounding box used for the quantisation
+};
+
 struct rsc_cloud {
   rsc_ctx* ctx = nullptr;
   int64_t n = 0, n_pad = 0;
@@ -128,9 +142,19 @@ struct rsc_cloud {
   // rank/select index over `enabled` for the sampler (rsc_fit.cu); rebuilt lazily after any change
   rsc::DevBuf selbuf;
   bool sel_valid = false;
+  rsc_cells cells;
+  // every change of `enabled` goes through here: the cached sampler indices are rebuilt lazily
+  void enabled_changed() {
+    sel_valid = false;
+    cells.en_valid = false;
+    cells.sel_valid = false;
+  }
 };
 
 namespace rsc {
+
+int32_t cells_refresh_enabled(rsc_cloud* cloud, cudaStream_t st);
+void cells_release(rsc_cloud* cloud);
 
 inline PointSet view_cloud(const rsc_cloud* c) {
   PointSet ps;
@@ -190,6 +214,20 @@ int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_
 }  // namespace rsc
 
 namespace rsc {
+// scratch of one sample/fit batch inside ctx->fitbuf (rsc_fit.cu)
+struct FitScratch {
+  rsc_cand* dense;
+  rsc_cand* out;
+  uint32_t* flags;
+  unsigned long long* offs;
+  unsigned long long* total;
+  int32_t* out_set;
+  int64_t* idx;
+  int32_t* level;  // per set: octree level its cell came from (cell sampler only)
+};
+int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
+                    const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
+                    FitScratch* fs, const double* cum = nullptr);
 int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st);
 int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st);
 }  // namespace rsc

@@ -314,7 +314,7 @@ int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cuda
                                                        disable ? cloud->enabled : nullptr);
   RSC_CUDA(ctx, cudaGetLastError());
   if (disable) {
-    cloud->sel_valid = false;
+    cloud->enabled_changed();
     return refresh_subsets_enabled(cloud, st);
   }
   return RSC_OK;

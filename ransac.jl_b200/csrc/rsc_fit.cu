@@ -423,6 +423,92 @@ __global__ void __launch_bounds__(128) sample_kernel(int S, int k, uint64_t seed
   for (int q = 0; q < k; ++q) idx_out[(size_t)s * k + q] = ok ? id[q] : -1;
 }
 
+// ---- level-weighted cell sampler on the flattened octree (rsc_octree.cu) ----------
+struct CellsView {
+  const uint32_t* codes;      // sorted Morton codes
+  const uint32_t* perm;       // sorted position -> point index
+  const uint32_t* inv;        // point index -> sorted position
+  const uint8_t* leafdepth;   // by point index
+  const uint32_t* en_sorted;  // isenabled in Morton order
+  const unsigned long long* boff;  // rank blocks over en_sorted
+  int nblk;
+  int nlevels;
+  double cum[11];             // cumulative level weights (host, float64, left to right)
+};
+
+// enabled points among sorted positions [0, p)
+__device__ __forceinline__ uint64_t rank_sorted(const CellsView& c, int64_t p, int64_t words) {
+  const int64_t blk = p / (kSelWords * 32);
+  if (blk >= c.nblk) return __ldg(c.boff + c.nblk);  // p == n_pad: the total (stored behind the offsets)
+  uint64_t r = __ldg(c.boff + blk);
+  const int64_t w0 = blk * kSelWords, wp = p >> 5;
+  for (int64_t w = w0; w < wp; ++w) r += __popc(__ldg(c.en_sorted + w));
+  if (p & 31) r += __popc(__ldg(c.en_sorted + wp) & ((1u << (p & 31)) - 1u));
+  return r;
+}
+
+__device__ __forceinline__ int64_t lower_bound_code(const uint32_t* __restrict__ codes, int64_t lo, int64_t hi, uint64_t key) {
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((uint64_t)__ldg(codes + mid) < key)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  return lo;
+}
+
+// samplepointcloud4! (fitting.jl:383-430) with the cell of a drawn octree level: one thread per set.
+// The level is DRAWN from the level distribution restricted to 1..leafdepth(r1) (docs/src/ransac.md:
+// 80-82); the shipped code takes the argmax (fitting.jl:401), which never leaves level 1.
+__global__ void __launch_bounds__(128) sample_cells_kernel(int S, int k, uint64_t seed, uint64_t set0, int64_t n_points,
+                                                           const uint32_t* __restrict__ enabled, int64_t words, CellsView c,
+                                                           int64_t* __restrict__ idx_out, int32_t* __restrict__ level_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  int64_t id[kMaxK];
+  bool ok = true;
+  int level = 0;
+  SetStream rng(seed, set0 + (uint64_t)s);
+  const uint64_t ne_all = __ldg(c.boff + c.nblk);
+  if (ne_all == 0) {
+    ok = false;
+  } else {
+    int64_t r1 = (int64_t)rng.below((uint64_t)n_points);
+    while (!((__ldg(enabled + (r1 >> 5)) >> (r1 & 31)) & 1u)) r1 = (int64_t)rng.below((uint64_t)n_points);
+    const int ld = c.leafdepth[r1];
+    // level: smallest l with cum[l] > u * cum[ld]  (u = 64 random bits as a fraction)
+    const double target = __dmul_rn(__dmul_rn((double)rng.next(), 5.421010862427522e-20 /* 2^-64 */), c.cum[ld - 1]);
+    level = ld;
+    for (int l = 1; l <= ld; ++l)
+      if (c.cum[l - 1] > target) {
+        level = l;
+        break;
+      }
+    const int shift = 3 * ((c.nlevels - 1) - (level - 1));
+    const uint32_t code = __ldg(c.codes + __ldg(c.inv + r1));
+    const uint64_t lo_key = (uint64_t)(code >> shift) << shift;
+    const int64_t a = lower_bound_code(c.codes, 0, n_points, lo_key);
+    const int64_t b = lower_bound_code(c.codes, a, n_points, lo_key + ((uint64_t)1 << shift));
+    const uint64_t ra = rank_sorted(c, a, words);
+    const uint64_t ne = rank_sorted(c, b, words) - ra;
+    if (ne < (uint64_t)k) ok = false;  // (false, 0): too few enabled points in the cell
+    if (ok) {
+      id[0] = r1;
+      for (int q = 1; q < k; ++q) {
+        int64_t p = (int64_t)__ldg(c.perm + select_enabled(c.en_sorted, words, c.boff, c.nblk, ra + rng.below(ne)));
+        if (p == id[0]) p = (int64_t)__ldg(c.perm + select_enabled(c.en_sorted, words, c.boff, c.nblk, ra + rng.below(ne)));
+        id[q] = p;
+      }
+      for (int i = 1; i < k; ++i)
+        for (int j = 0; j < i; ++j)
+          if (id[i] == id[j]) ok = false;  // (false, 1): duplicate index
+    }
+  }
+  for (int q = 0; q < k; ++q) idx_out[(size_t)s * k + q] = ok ? id[q] : -1;
+  level_out[s] = level;
+}
+
 // one thread per (minimal set, shape type): blockIdx.y = position in shape_types, so a warp runs
 // one fit routine.  Points come from explicit coordinates (src.soa == nullptr) or from the cloud
 // by index; sets whose first index is negative (failed samples) yield nothing.
@@ -507,17 +593,6 @@ int32_t make_fit_params(rsc_ctx* ctx, const rsc_params* p, int k, FitParams* f) 
   return RSC_OK;
 }
 
-// scratch layout inside ctx->fitbuf for S sets
-struct FitScratch {
-  rsc_cand* dense;
-  rsc_cand* out;
-  uint32_t* flags;
-  unsigned long long* offs;
-  unsigned long long* total;
-  int32_t* out_set;
-  int64_t* idx;
-};
-
 static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
   const size_t slots = (size_t)S * (ntypes > 0 ? ntypes : 1);
   size_t off = 0;
@@ -528,7 +603,7 @@ static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
   };
   const size_t o_dense = take(slots * sizeof(rsc_cand)), o_out = take(slots * sizeof(rsc_cand));
   const size_t o_flags = take(slots * 4), o_offs = take(slots * 8), o_total = take(8);
-  const size_t o_set = take(slots * 4), o_idx = take((size_t)S * k * 8);
+  const size_t o_set = take(slots * 4), o_idx = take((size_t)S * k * 8), o_level = take((size_t)S * 4);
   RSC_CUDA(ctx, ctx->fitbuf.ensure(off));
   char* b = ctx->fitbuf.as<char>();
   fs->dense = (rsc_cand*)(b + o_dense);
@@ -538,6 +613,7 @@ static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
   fs->total = (unsigned long long*)(b + o_total);
   fs->out_set = (int32_t*)(b + o_set);
   fs->idx = (int64_t*)(b + o_idx);
+  fs->level = (int32_t*)(b + o_level);
   return RSC_OK;
 }
 
@@ -567,6 +643,31 @@ int32_t build_select_index(rsc_cloud* cloud, cudaStream_t st, unsigned long long
 
 // exclusive scan of n counts by ONE CTA (n is small: flags of a batch, block counts of a mask);
 // every thread takes 8 consecutive elements per pass, so 8192 elements cost one block-wide scan
+// the same index over isenabled in Morton order (cell sampler); refreshed lazily after every change
+int32_t build_cells_index(rsc_cloud* cloud, cudaStream_t st, const double* cum, CellsView* v) {
+  rsc_ctx* ctx = cloud->ctx;
+  rsc_cells& c = cloud->cells;
+  if (c.nlevels == 0) return fail(ctx, RSC_E_STATE, "cell sampler: rsc_cloud_build_cells has not been called");
+  if (int32_t rc = cells_refresh_enabled(cloud, st)) return rc;
+  const int64_t words = cloud->n_pad / 32;
+  const int nb = (int)((words + kSelWords - 1) / kSelWords);
+  RSC_CUDA(ctx, c.selbuf.ensure((size_t)nb * (4 + 8) + 64));
+  unsigned long long* offs = c.selbuf.as<unsigned long long>();
+  unsigned long long* total = offs + nb;
+  uint32_t* cnt = (uint32_t*)(total + 1);
+  if (!c.sel_valid) {
+    block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(c.en_sorted, words, cnt, nb);
+    RSC_CUDA(ctx, cudaGetLastError());
+    scan_u32_kernel<<<1, 1024, 0, st>>>(cnt, nb, offs, total);
+    RSC_CUDA(ctx, cudaGetLastError());
+    c.sel_valid = true;
+  }
+  v->codes = c.codes, v->perm = c.perm, v->inv = c.inv, v->leafdepth = c.leafdepth, v->en_sorted = c.en_sorted;
+  v->boff = offs, v->nblk = nb, v->nlevels = c.nlevels;
+  for (int l = 0; l < 11; ++l) v->cum[l] = l < c.nlevels ? cum[l] : 0.0;
+  return RSC_OK;
+}
+
 __global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restrict__ counts, int n,
                                                         unsigned long long* __restrict__ offsets,
                                                         unsigned long long* __restrict__ out_total) {
@@ -619,9 +720,11 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restri
 
 // Enqueue fit (+ sampling) for S sets; leaves compacted candidates in ctx->fitbuf (FitScratch.out),
 // their count in FitScratch.total.  No synchronisation.
+// mode 0: explicit coordinates, 1: explicit indices, 2: root-cell sampler (the reference's behaviour,
+// Q1), 3: level-weighted cell sampler on the flattened octree (`cum` = cumulative level weights)
 int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
                     const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
-                    FitScratch* fs) {
+                    FitScratch* fs, const double* cum) {
   FitParams f;
   int32_t rc = make_fit_params(ctx, params, k, &f);
   if (rc) return rc;
@@ -635,9 +738,16 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
     src.n_pad = cloud->n_pad;
   }
   if (mode == 2 && (rc = build_select_index(cloud, st, &boff, &nblk, &nen))) return rc;
+  CellsView cv;
+  if (mode == 3 && (rc = build_cells_index(cloud, st, cum, &cv))) return rc;
   if (slots > 0) {
     const int64_t* use_idx = d_idx;
-    if (mode == 2) {
+    if (mode == 3) {
+      sample_cells_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, k, seed, set0, cloud->n, cloud->enabled, cloud->n_pad / 32, cv,
+                                                           fs->idx, fs->level);
+      RSC_CUDA(ctx, cudaGetLastError());
+      use_idx = fs->idx;
+    } else if (mode == 2) {
       sample_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, k, seed, set0, cloud->n, cloud->enabled, cloud->n_pad / 32, boff, nblk,
                                                      nen, fs->idx);
       RSC_CUDA(ctx, cudaGetLastError());
@@ -676,6 +786,8 @@ static int32_t fit_finish(rsc_ctx* ctx, const FitScratch& fs, int S, int k, cuda
 using namespace rsc;
 
 extern "C" {
+
+void rsc_level_cumsum(const double* levelweight, int32_t nlevels, double* cum);
 
 int32_t rsc_fit_points(rsc_ctx* ctx, const rsc_params* params, const double* p, const double* n, int32_t S, int32_t k,
                        rsc_cand* out, int32_t* out_set, int32_t* out_n) {
@@ -734,6 +846,47 @@ int32_t rsc_sample_fit(rsc_cloud* cloud, const rsc_params* params, uint64_t seed
   int32_t rc = fit_enqueue(ctx, cloud, 2, params, k, nullptr, nullptr, nullptr, S, seed, set0, st, &fs);
   if (rc) return rc;
   return fit_finish(ctx, fs, S, k, st, out, out_set, out_idx, out_n);
+}
+
+int32_t rsc_sample_fit_cells(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, uint64_t set0, int32_t S,
+                             const double* levelweight, int32_t nlevels, rsc_cand* out, int32_t* out_set, int64_t* out_idx,
+                             int32_t* out_level, int32_t* out_n) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (!params || !out_n || !levelweight || S < 0 || (S > 0 && !out)) return fail(ctx, RSC_E_ARG, "sample_fit_cells: null arguments");
+  *out_n = 0;
+  if (S == 0) return RSC_OK;
+  if (nlevels != cloud->cells.nlevels) return fail(ctx, RSC_E_ARG, "sample_fit_cells: nlevels differs from rsc_cloud_build_cells");
+  const int k = params->drawN;
+  if (k < 3 || k > kMaxK) return fail(ctx, RSC_E_ARG, "sample_fit_cells: drawN must be 3..8");
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (int32_t rcr = cloud_ready(cloud)) return rcr;
+  cudaStream_t st = ctx->stream;
+  double cum[11];
+  rsc_level_cumsum(levelweight, nlevels, cum);
+  FitScratch fs;
+  int32_t rc = fit_enqueue(ctx, cloud, 3, params, k, nullptr, nullptr, nullptr, S, seed, set0, st, &fs, cum);
+  if (rc) return rc;
+  if (out_level) RSC_CUDA(ctx, cudaMemcpyAsync(out_level, fs.level, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+  return fit_finish(ctx, fs, S, k, st, out, out_set, out_idx, out_n);
+}
+
+void rsc_level_cumsum(const double* levelweight, int32_t nlevels, double* cum) {
+  double c = 0.0;
+  for (int l = 0; l < nlevels && l < 11; ++l) {
+    c += levelweight[l];
+    cum[l] = c;
+  }
+}
+
+/* octree.jl:198-205 (x = 9/10); the weights stay unchanged while no level has a score (w = 0 would give NaN) */
+void rsc_update_levelweight(double* levelweight, const double* levelscore, int32_t nlevels) {
+  double w = 0.0;
+  for (int i = 0; i < nlevels; ++i) w += levelscore[i] / levelweight[i];
+  if (!(w > 0.0)) return;
+  double nw[11];
+  for (int i = 0; i < nlevels && i < 11; ++i) nw[i] = 0.9 * levelscore[i] / (w * levelweight[i]) + (1 - 0.9) / nlevels;
+  for (int i = 0; i < nlevels && i < 11; ++i) levelweight[i] = nw[i];
 }
 
 }  // extern "C"

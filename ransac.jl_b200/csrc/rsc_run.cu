@@ -31,18 +31,10 @@
 namespace rsc {
 
 // from rsc_fit.cu
-struct FitScratch {
-  rsc_cand* dense;
-  rsc_cand* out;
-  uint32_t* flags;
-  unsigned long long* offs;
-  unsigned long long* total;
-  int32_t* out_set;
-  int64_t* idx;
-};
-int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
-                    const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
-                    FitScratch* fs);
+}  // namespace rsc
+extern "C" void rsc_level_cumsum(const double* levelweight, int32_t nlevels, double* cum);
+extern "C" void rsc_update_levelweight(double* levelweight, const double* levelscore, int32_t nlevels);
+namespace rsc {
 __global__ void scan_u32_kernel(const uint32_t* __restrict__ counts, int n, unsigned long long* __restrict__ offsets,
                                 unsigned long long* __restrict__ out_total);
 
@@ -192,6 +184,18 @@ using namespace rsc;
 // Result of one run.  The inlier index lists stay in device memory (one arena, disjoint lists, in
 // extraction order) until the caller fetches them with rsc_run_inpoints: no per-extraction host
 // buffer, no device->host traffic inside the loop.
+// per octree level: number of new candidates and the sum of their scores (fitting.jl:184 adds E(score)
+// per candidate; E is affine in the count, so the host adds the closed form of the sum)
+__global__ void level_stats_kernel(const int32_t* __restrict__ out_set, const int32_t* __restrict__ set_level,
+                                   const int32_t* __restrict__ score, int n, long long* __restrict__ lv /*[2][11]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = set_level[out_set[i]] - 1;
+  if (l < 0 || l >= 11) return;
+  atomicAdd((unsigned long long*)(lv + l), 1ull);
+  atomicAdd((unsigned long long*)(lv + 11 + l), (unsigned long long)score[i]);
+}
+
 // 1 if either guard-band queue (groups, pairs) of the last score call overflowed
 __global__ void queue_overflow_kernel(const uint32_t* __restrict__ wl_count, uint32_t cap, int32_t* __restrict__ out) {
   *out = (wl_count[0] > cap || wl_count[1] > cap) ? 1 : 0;
@@ -216,6 +220,8 @@ struct rsc_run {
   int device = 0;
   int iterations = 0;
   double seconds = 0.0;
+  int nlevels = 0;  // cell sampler: final level weights / accumulated level scores
+  double levelweight[11] = {0}, levelscore[11] = {0};
   ~rsc_run() {
     if (d_idx) {
       cudaSetDevice(device);
@@ -272,7 +278,9 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     slo = (int64_t)((double)cloud->range_lo / cloud->n_pad * sub.m_pad) / kTile * kTile;
     shi = cloud->range_hi >= cloud->n_pad ? sub.m_pad : (int64_t)((double)cloud->range_hi / cloud->n_pad * sub.m_pad) / kTile * kTile;
   }
-  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta;
+  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf;
+  const bool cells_mode = (p->compat_flags & RSC_SAMPLER_OCTREE) != 0;
+  const int nlv = cloud->cells.nlevels;
   int64_t n_enabled = rsc_cloud_count_enabled(cloud);
   int64_t counters[3] = {0, 0, 0};  // lengthC, allcand, nofminset (iterations.jl:70)
   const bool trace = getenv("RSC_TRACE") != nullptr;
@@ -285,6 +293,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   auto cleanup = [&]() {
     store.release();
     newcnt.release(), hostio.release(), olden.release(), nscratch.release(), nvalid.release(), nmeta.release();
+    lvbuf.release();
   };
 #define RUN_CUDA(expr)                                  \
   do {                                                  \
@@ -300,13 +309,27 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   run->device = ctx->device;
   RUN_CUDA(cudaMalloc(&run->d_idx, (size_t)(n_enabled > 0 ? n_enabled : 1) * sizeof(int64_t)));  // every point is extracted at most once
 
+  // level-weighted cell sampler (extension): un-swapped initial values (octree.jl:82-83)
+  if (cells_mode) {
+    if (nlv == 0) {
+      rc = fail(ctx, RSC_E_STATE, "ransac_run: RSC_SAMPLER_OCTREE needs rsc_cloud_build_cells first");
+      goto done;
+    }
+    run->nlevels = nlv;
+    for (int l = 0; l < nlv; ++l) run->levelweight[l] = 1.0 / nlv, run->levelscore[l] = 0.0;
+    RUN_CUDA(lvbuf.ensure(2 * 11 * 8));
+  }
+
   for (int k = 1; k <= p->itermax; ++k) {
     if (n_enabled < p->tau) break;  // iterations.jl:75
     run->iterations = k;
     const auto tk0 = now();
     // ---- K1: minsubsetN minimal sets -> candidates (device, compacted in reference order) ----
     FitScratch fs;
-    if ((rc = fit_enqueue(ctx, cloud, 2, p, p->drawN, nullptr, nullptr, nullptr, S, seed, (uint64_t)(k - 1) * S, st, &fs)))
+    double cum[11];
+    if (cells_mode) rsc_level_cumsum(run->levelweight, nlv, cum);
+    if ((rc = fit_enqueue(ctx, cloud, cells_mode ? 3 : 2, p, p->drawN, nullptr, nullptr, nullptr, S, seed, (uint64_t)(k - 1) * S, st,
+                          &fs, cells_mode ? cum : nullptr)))
       goto done;
     unsigned long long n_new_ = 0;
     RUN_CUDA(cudaMemcpyAsync(&n_new_, fs.total, 8, cudaMemcpyDeviceToHost, st));
@@ -319,6 +342,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     // dropped queue entries would leave FP32 decisions in the counts)
     const int store_n0 = store.n;
     int64_t best[2] = {-1, 0};
+    long long lv_host[22] = {0};
     for (int attempt = 0;; ++attempt) {
       store.n = store_n0;
       int32_t ovf = 0;
@@ -348,6 +372,13 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
                                                                store.flags[store.cur].as<uint8_t>() + store.n);
         RUN_CUDA(cudaGetLastError());
         RUN_CUDA(cudaMemcpyAsync(&ovf, cv + 2 * n_new, 4, cudaMemcpyDeviceToHost, st));
+        if (cells_mode) {
+          RUN_CUDA(cudaMemsetAsync(lvbuf.p, 0, 2 * 11 * 8, st));
+          level_stats_kernel<<<(n_new + 255) / 256, 256, 0, st>>>(fs.out_set, fs.level, store.score[store.cur].as<int32_t>() + store.n,
+                                                                  n_new, lvbuf.as<long long>());
+          RUN_CUDA(cudaGetLastError());
+          RUN_CUDA(cudaMemcpyAsync(lv_host, lvbuf.p, 2 * 11 * 8, cudaMemcpyDeviceToHost, st));
+        }
         store.n += n_new;
       }
       if (store.n >= 1) {
@@ -366,6 +397,11 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     }
     counters[2] = (int64_t)k * S;
     counters[0] = store.n;
+    if (cells_mode && n_new > 0) {  // levelscore[level] += sum of E = -n + (N+2)/(M+2) (sum sigma + n)
+      for (int l = 0; l < nlv; ++l)
+        if (lv_host[l])
+          run->levelscore[l] += (-(double)lv_host[l]) + ((double)(N + 2) / (double)(sub.m + 2)) * (double)(lv_host[11 + l] + lv_host[l]);
+    }
     if (store.n >= 1) {
       const auto tk2 = now();
       t_score += secs(tk1, tk2);
@@ -476,6 +512,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
         }
       }
     }
+    if (cells_mode) rsc_update_levelweight(run->levelweight, run->levelscore, nlv);  // iterations.jl:148
     // iterations.jl:151-156
     if (prob_((double)p->tau, (double)counters[p->terminate_s], (double)N, (double)p->drawN) > p->prob_det) break;
   }
@@ -498,6 +535,15 @@ done:
 int32_t rsc_run_nshapes(const rsc_run* r) { return r ? (int32_t)r->shapes.size() : 0; }
 int32_t rsc_run_iterations(const rsc_run* r) { return r ? r->iterations : 0; }
 double rsc_run_seconds(const rsc_run* r) { return r ? r->seconds : 0.0; }
+
+int32_t rsc_run_levelweight(const rsc_run* r, double* levelweight, double* levelscore) {
+  if (!r) return 0;
+  for (int l = 0; l < r->nlevels; ++l) {
+    if (levelweight) levelweight[l] = r->levelweight[l];
+    if (levelscore) levelscore[l] = r->levelscore[l];
+  }
+  return r->nlevels;
+}
 
 int32_t rsc_run_shape(const rsc_run* r, int32_t i, rsc_cand* shape, int64_t* n_inpoints) {
   if (!r || i < 0 || (size_t)i >= r->shapes.size()) return RSC_E_ARG;

@@ -70,6 +70,22 @@ def sample_fit(pc: RANSACCloud, params, seed: int, set0: int, S: int):
     return [from_cand(out[i]) for i in range(out_n.value)], out_set[: out_n.value].copy(), out_idx
 
 
+def sample_fit_cells(pc: RANSACCloud, params, seed: int, set0: int, S: int, levelweight):
+    """samplepointcloud4! with the level-weighted octree-cell sampler (pc.build_cells first) +
+    forcefitshapes!.  Returns (shapes, set of each shape, indices (S, drawN), level of each set)."""
+    cp = to_c(params)
+    lw = np.ascontiguousarray(levelweight, dtype=np.float64)
+    cap = max(S * cp.n_shape_types, 1)
+    out = (_lib.rsc_cand * cap)()
+    out_set = np.zeros(cap, dtype=np.int32)
+    out_idx = np.zeros((S, cp.drawN), dtype=np.int64)
+    out_level = np.zeros(S, dtype=np.int32)
+    out_n = C.c_int32()
+    pc.ctx.check(lib.rsc_sample_fit_cells(pc.handle, C.byref(cp), seed, set0, S, lw.ctypes.data, len(lw), out, out_set.ctypes.data,
+                                          out_idx.ctypes.data, out_level.ctypes.data, C.byref(out_n)))
+    return [from_cand(out[i]) for i in range(out_n.value)], out_set[: out_n.value].copy(), out_idx, out_level
+
+
 # ---- scoring (fitting.jl:45,181-190; shapes/*.jl scorecandidate) -------------------------------
 def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: int, params, want_masks=False,
                  compat_flags=None):

@@ -26,22 +26,32 @@ def _all_builtin(params) -> bool:
     return all(t in SHAPE_KIND for t in params["iteration"]["shape_types"])
 
 
-def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = False, seed: int = 1234) -> Tuple[List[ExtractedShape], float]:
+def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = False, seed: int = 1234,
+           sampler: str = "root") -> Tuple[List[ExtractedShape], float]:
     """Run efficient RANSAC on `pc`; returns (extracted shapes, seconds).
 
     `reset_rand=True` pins the sampler seed to 1234 like `Random.seed!(1234)` (iterations.jl:36);
-    the Philox stream is of course not Julia's."""
+    the Philox stream is of course not Julia's.  `sampler="octree"` (extension, needs
+    `pc.build_cells()`) draws the minimal sets from level-weighted octree cells -- what the reference
+    is written for -- instead of from the root cell, which is what its shipped code does (Q1); the
+    final level weights are left in `pc.levelweight`."""
     if setenabled:
         pc.enable_all()
     if reset_rand:
         seed = 1234
     if _all_builtin(params):
-        return _ransac_device(pc, params, seed)
+        return _ransac_device(pc, params, seed, sampler)
+    if sampler != "root":
+        raise ValueError("the octree sampler is only available for the built-in shape types (device loop)")
     return _ransac_host(pc, params, seed)
 
 
-def _ransac_device(pc, params, seed):
+def _ransac_device(pc, params, seed, sampler="root"):
     cp = to_c(params)
+    if sampler == "octree":
+        cp.compat_flags |= _lib.RSC_SAMPLER_OCTREE
+    elif sampler != "root":
+        raise ValueError("sampler must be 'root' or 'octree'")
     run = C.c_void_p()
     pc.ctx.check(lib.rsc_ransac_run(pc.handle, C.byref(cp), seed, C.byref(run)))
     try:
@@ -55,6 +65,10 @@ def _ransac_device(pc, params, seed):
                 pc.ctx.check(lib.rsc_run_inpoints(run, i, idx.ctypes.data))
             out.append(ExtractedShape(from_cand(cand), idx))
         secs = lib.rsc_run_seconds(run)
+        lw, ls = np.zeros(11), np.zeros(11)
+        nl = lib.rsc_run_levelweight(run, lw.ctypes.data, ls.ctypes.data)
+        if nl:
+            pc.levelweight, pc.levelscore = lw[:nl].copy(), ls[:nl].copy()
     finally:
         lib.rsc_run_destroy(run)
     return out, int(secs * 100) / 100.0
