@@ -24,6 +24,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scene", default="c2", choices=["c1", "c2", "c4", "c5small", "c5"])
 ap.add_argument("--points", type=int, default=100_000_000, help="c5: cloud size")
 ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--sampler", default="root", choices=["root", "octree"])
+ap.add_argument("--levels", type=int, default=8, help="octree levels of the cell sampler")
+ap.add_argument("--itermax", type=int, default=0)
 args = ap.parse_args()
 
 rank = int(os.environ.get("RANK", 0))
@@ -65,15 +68,23 @@ else:
             os.remove(f"{tag}_v{i}.npy"), os.remove(f"{tag}_n{i}.npy")
     sc, r = scenes.Scene(V, Nn, None, scenes.lidar_primitives()[0]), 64
     it = {"tau": n // 500, "minsubsetN": 8192, "itermax": 200}
+if args.itermax:
+    it["itermax"] = args.itermax
 params = R.ransacparameters(iteration=it)
 pc = R.RANSACCloud(sc.vertices, sc.normals, r, device=local)
+t_cells = None
+if args.sampler == "octree":
+    torch.cuda.synchronize()
+    tc = time.perf_counter()
+    pc.build_cells(args.levels)
+    t_cells = time.perf_counter() - tc
 sh = ShardedContext(pc) if world > 1 else None
-R.ransac(pc, R.ransacparameters(iteration=dict(it, itermax=2)), True, seed=1)  # warm-up (allocations, NCCL)
+R.ransac(pc, R.ransacparameters(iteration=dict(it, itermax=2)), True, seed=1, sampler=args.sampler)  # warm-up (allocations, NCCL)
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-ex, secs = R.ransac(pc, params, True, seed=2024)
+ex, secs = R.ransac(pc, params, True, seed=2024, sampler=args.sampler)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 tt = torch.tensor([dt], device="cuda")
@@ -83,7 +94,9 @@ ok = None
 if rank == 0 and args.check and world > 1:
     sh.close()
     pc2 = R.RANSACCloud(sc.vertices, sc.normals, pc.subsets, device=local)
-    ex2, _ = R.ransac(pc2, params, True, seed=2024)
+    if args.sampler == "octree":
+        pc2.build_cells(args.levels)
+    ex2, _ = R.ransac(pc2, params, True, seed=2024, sampler=args.sampler)
     ok = len(ex) == len(ex2) and all(
         list(a.shape.to_cand().p) == list(b.shape.to_cand().p) and np.array_equal(a.inpoints, b.inpoints) for a, b in zip(ex, ex2))
 if rank == 0:
@@ -91,7 +104,9 @@ if rank == 0:
     print(json.dumps({"scene": args.scene, "points": int(sc.vertices.shape[0]), "n_gpus": world, "ransac_seconds": float(tt.item()),
                       "shapes": [[R.strt(e.shape), int(len(e.inpoints))] for e in ex][:40], "n_shapes": len(ex),
                       "points_extracted": int(sum(len(e.inpoints) for e in ex)), "evals": int(st.evals),
-                      "sets_drawn": int(st.sets_drawn), "matches_unsharded": ok}))
+                      "sets_drawn": int(st.sets_drawn), "matches_unsharded": ok, "sampler": args.sampler,
+                      "build_cells_seconds": t_cells,
+                      "levelweight": [round(float(x), 4) for x in getattr(pc, "levelweight", [])]}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()
