@@ -173,18 +173,29 @@ function fit_batch(dc::DeviceCloud, idx::Matrix{Int}, params)
 end
 
 """
-    ransac(pc, params, setenabled; reset_rand=false, seed=1234)
+    ransac(pc, params, setenabled; reset_rand=false, seed=1234, sampler=:root, octree_levels=8)
 
 Drop-in for `RANSAC.ransac` when every entry of `params.iteration.shape_types` is a built-in shape:
 the whole loop of iterations.jl:35-162 runs inside one `ccall`.  Otherwise falls back to
 `RANSAC.ransac` (user-defined shapes run their own Julia methods).
+
+`sampler=:octree` (extension) draws the minimal sets from level-weighted octree cells -- what
+samplepointcloud4!/updatelevelweight are written for -- instead of from the root cell, which is what
+the shipped package always does (levelweight/levelscore are swapped in the constructor, octree.jl:82-84).
+The final weights/scores are written back to `pc.levelweight` / `pc.levelscore` when their length fits.
 """
-function ransac(pc::RANSACCloud, params, setenabled::Bool; reset_rand=false, seed::Integer=1234)
+function ransac(pc::RANSACCloud, params, setenabled::Bool; reset_rand=false, seed::Integer=1234, sampler::Symbol=:root,
+                octree_levels::Integer=8)
     all(t -> haskey(KIND, t), params.iteration.shape_types) || return RANSAC.ransac(pc, params, setenabled; reset_rand=reset_rand)
     setenabled && fill!(pc.isenabled, true)
     dc = DeviceCloud(pc)
     run = Ref{Ptr{Cvoid}}(C_NULL)
-    prm = Ref(toparams(params))
+    p0 = toparams(params)
+    if sampler == :octree
+        check(ccall((:rsc_cloud_build_cells, LIB[]), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
+        p0 = RscParams((f === :compat_flags ? (p0.compat_flags | UInt32(2)) : getfield(p0, f) for f in fieldnames(RscParams))...)  # RSC_SAMPLER_OCTREE
+    end
+    prm = Ref(p0)
     check(ccall((:rsc_ransac_run, LIB[]), Int32, (Ptr{Cvoid}, Ref{RscParams}, UInt64, Ref{Ptr{Cvoid}}),
                 dc.h, prm, reset_rand ? 1234 : seed, run))
     extracted = ExtractedShape[]
@@ -198,6 +209,11 @@ function ransac(pc::RANSACCloud, params, setenabled::Bool; reset_rand=false, see
             push!(extracted, ExtractedShape(fromcand(c[]), idx .+ 1))
         end
         secs = ccall((:rsc_run_seconds, LIB[]), Float64, (Ptr{Cvoid},), run[])
+        lw = zeros(Float64, 11); ls = zeros(Float64, 11)
+        nl = ccall((:rsc_run_levelweight, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), run[], lw, ls)
+        if nl > 0 && length(pc.levelweight) == nl
+            pc.levelweight .= lw[1:nl]; pc.levelscore .= ls[1:nl]
+        end
         pull_enabled!(dc)
         return extracted, trunc(secs, digits=2)
     finally
