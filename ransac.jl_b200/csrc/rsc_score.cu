@@ -258,6 +258,41 @@ __global__ void __launch_bounds__(kThreads, MINB) score_kernel(const __grid_cons
   score_body<T, K, U, MASKS>(a, bt.slot0, stages[warp], bars[warp]);
 }
 
+// All column types in ONE launch (runtime switch per CTA column): for small batches (the device loop
+// scores a few hundred new candidates per iteration) five launches plus fork/join events cost more
+// host time than the kernels run.  Registers = the maximum over the types, fine at K <= 2.
+template <int K, int MINB, bool MASKS>
+__global__ void __launch_bounds__(kThreads, MINB) score_kernel_any(const __grid_constant__ ScoreArgs a) {
+  __shared__ __align__(128) float stages[kThreads / 32][kStages * kSubFloats];
+  __shared__ __align__(8) uint64_t bars[kThreads / 32][kStages];
+  const BlockTab bt = a.tab[blockIdx.x];
+  if (bt.type < 0) return;
+  const int warp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&bars[warp][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  switch (bt.type) {
+    case RSC_PLANE:
+      score_body<RSC_PLANE, K, 1, MASKS>(a, bt.slot0, stages[warp], bars[warp]);
+      break;
+    case RSC_SPHERE:
+      score_body<RSC_SPHERE, K, 1, MASKS>(a, bt.slot0, stages[warp], bars[warp]);
+      break;
+    case RSC_CYLINDER:
+      score_body<RSC_CYLINDER, K, 1, MASKS>(a, bt.slot0, stages[warp], bars[warp]);
+      break;
+    case RSC_CONE:
+      score_body<RSC_CONE, K, 1, MASKS>(a, bt.slot0, stages[warp], bars[warp]);
+      break;
+    default:
+      score_body<kConeWide, K, 1, MASKS>(a, bt.slot0, stages[warp], bars[warp]);
+      break;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // FP64 fix-up, two launches.
 //  1. fixup_scan_kernel: one warp per queued 32-point group, one lane per point.  The FP32 margin is
@@ -664,25 +699,45 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
   a.subs_per_chunk = (int)((nsubs + chunks - 1) / chunks);
   chunks = (nsubs + a.subs_per_chunk - 1) / a.subs_per_chunk;
   dim3 grid((unsigned)ncols, (unsigned)chunks);
-  // (worth the fork/join events from ~1e7 evaluations on: four short kernels overlap instead of queueing)
-  const bool fork = (double)C * (double)ps.n_pad >= 1e7 && !getenv("RSC_NOFORK");
+  // (below ~1e9 evaluations the fused single-launch kernel or plain sequential launches are cheaper)
+  static const double fork_min = getenv("RSC_FORK_MIN") ? atof(getenv("RSC_FORK_MIN")) : 1e9;
+  const bool fork = (double)C * (double)ps.n_pad >= fork_min && !getenv("RSC_NOFORK");
 
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
-  if (fork) RSC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-  // most expensive type first
-  const int order[kColTypes] = {RSC_CONE, kConeWide, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
-  for (int oi = 0; oi < kColTypes; ++oi) {
-    const int t = order[oi];
-    cudaStream_t s = st;
-    if (fork && oi > 0) {
-      s = ctx->sfork[oi - 1];
-      RSC_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_fork, 0));
+  // small batches with one tiling for every type: a single launch with a per-column type switch
+  const int K0 = L.til[0]->K;
+  bool uniform_k = K0 <= 2;
+  for (int t = 1; t < kColTypes; ++t) uniform_k = uniform_k && L.til[t]->K == K0;
+  if (!fork && uniform_k && !getenv("RSC_NOFUSE")) {
+    if (K0 == 1) {
+      if (want_masks)
+        score_kernel_any<1, 4, true><<<grid, kThreads, 0, st>>>(a);
+      else
+        score_kernel_any<1, 4, false><<<grid, kThreads, 0, st>>>(a);
+    } else {
+      if (want_masks)
+        score_kernel_any<2, 4, true><<<grid, kThreads, 0, st>>>(a);
+      else
+        score_kernel_any<2, 4, false><<<grid, kThreads, 0, st>>>(a);
     }
-    (want_masks ? L.til[t]->fn_masks[t] : L.til[t]->fn[t])<<<grid, kThreads, 0, s>>>(a);
     RSC_CUDA(ctx, cudaGetLastError());
-    if (fork && oi > 0) {
-      RSC_CUDA(ctx, cudaEventRecord(ctx->ev_join[oi - 1], s));
-      RSC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[oi - 1], 0));
+  } else {
+    if (fork) RSC_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    // most expensive type first
+    const int order[kColTypes] = {RSC_CONE, kConeWide, RSC_CYLINDER, RSC_SPHERE, RSC_PLANE};
+    for (int oi = 0; oi < kColTypes; ++oi) {
+      const int t = order[oi];
+      cudaStream_t s = st;
+      if (fork && oi > 0) {
+        s = ctx->sfork[oi - 1];
+        RSC_CUDA(ctx, cudaStreamWaitEvent(s, ctx->ev_fork, 0));
+      }
+      (want_masks ? L.til[t]->fn_masks[t] : L.til[t]->fn[t])<<<grid, kThreads, 0, s>>>(a);
+      RSC_CUDA(ctx, cudaGetLastError());
+      if (fork && oi > 0) {
+        RSC_CUDA(ctx, cudaEventRecord(ctx->ev_join[oi - 1], s));
+        RSC_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[oi - 1], 0));
+      }
     }
   }
   RSC_CUDA(ctx, cudaGetLastError());
