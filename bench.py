@@ -45,8 +45,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="override the CPU sample (points)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--ransac", default="c2", choices=["none", "c2", "c4"],
-                    help="also time end-to-end ransac() on this scene (single GPU, extra JSON key)")
+    ap.add_argument("--ransac", default="c4", choices=["none", "c2", "c4"],
+                    help="also time end-to-end ransac() on this scene (single GPU, extra JSON key); c4 = the "
+                         "10 M-point CAD-like scene BASELINE.json's second headline is quoted on")
     return ap.parse_args()
 
 

@@ -167,7 +167,7 @@ int32_t rsc_cloud_build_cells(rsc_cloud* cloud, int32_t nlevels) {
   if (!cloud) return RSC_E_ARG;
   rsc_ctx* ctx = cloud->ctx;
   if (nlevels < 1 || nlevels > 11) return fail(ctx, RSC_E_ARG, "build_cells: nlevels must be 1..11 (30-bit Morton codes)");
-  if (cloud->n <= 0 || cloud->n >= ((int64_t)1 << 32)) return fail(ctx, RSC_E_ARG, "build_cells: cloud size");
+  if (cloud->n <= 0 || cloud->n >= ((int64_t)1 << 31)) return fail(ctx, RSC_E_ARG, "build_cells: cloud size must be below 2^31 points per shard");
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (int32_t rcr = cloud_ready(cloud)) return rcr;
   cudaStream_t st = ctx->stream;

@@ -234,3 +234,41 @@ def test_refit_guard_queue_overflow(R, monkeypatch):
         ex = R.refit(sh, pc, params)
         m = wmask[i] & en
         np.testing.assert_array_equal(ex.inpoints, np.flatnonzero(m))
+
+
+def test_update_coordinates_drops_cells_and_rescoring_follows(R):
+    """rsc_cloud_update replaces the coordinates in place: scoring must see the new points, the
+    flattened octree built for the old ones must be gone (the sampler refuses until it is rebuilt)"""
+    import ctypes as C
+
+    from ransac_jl_b200 import scenes
+    from ransac_jl_b200._lib import lib
+
+    a = scenes.scene_mixed(107, 30_000)
+    b = scenes.scene_mixed(108, 30_000)
+    pc = R.RANSACCloud(a.vertices, a.normals, 1).build_cells(6)
+    params = R.ransacparameters()
+    cands = [p.shape for p in b.primitives]
+    assert lib.rsc_cloud_cells_levels(pc.handle) == 6
+    pc.ctx.check(lib.rsc_cloud_update(pc.handle, b.vertices.ctypes.data, b.normals.ctypes.data, pc.size))
+    counts, _ = R.score_counts(pc, cands, -1, params)
+    want, _ = _oracle_counts(cands, b.vertices.astype(np.float64), b.normals.astype(np.float64), oracle_params(params))
+    np.testing.assert_array_equal(counts, want)
+    assert lib.rsc_cloud_cells_levels(pc.handle) == 0
+    with pytest.raises(R.RscError):
+        R.sample_fit_cells(pc, params, 1, 0, 16, np.full(6, 1 / 6))
+
+
+def test_many_candidates_multi_column_masks(R):
+    """20 000 candidates (several CTA columns per type, K = 4 tiling) with masks on a small cloud"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(109, 4_000)
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 1)
+    params = R.ransacparameters()
+    cands = scenes.perturbed_candidates(sc, 5000, seed=13)
+    counts, masks = R.score_counts(pc, cands, -1, params, want_masks=True)
+    want, wmask = _oracle_counts(cands, sc.vertices.astype(np.float64), sc.normals.astype(np.float64), oracle_params(params))
+    np.testing.assert_array_equal(counts, want)
+    for i in range(0, len(cands), 211):
+        np.testing.assert_array_equal(R.unpack_mask(masks[i], pc.size), wmask[i])
