@@ -26,6 +26,8 @@
 #include <chrono>
 #include <vector>
 
+#include <algorithm>
+
 #include "rsc_common.cuh"
 
 namespace rsc {
@@ -196,6 +198,52 @@ __global__ void level_stats_kernel(const int32_t* __restrict__ out_set, const in
   atomicAdd((unsigned long long*)(lv + 11 + l), (unsigned long long)score[i]);
 }
 
+// The loop runs `nb` iterations speculatively as one batch (same Philox set ids as nb separate
+// iterations).  seg[j] = first compacted candidate that belongs to iteration j of the batch
+// (candidates are in set order), seg[nb] = their number.
+__global__ void seg_bounds_kernel(const int32_t* __restrict__ out_set, const unsigned long long* __restrict__ total, int S, int nb,
+                                  int32_t* __restrict__ seg) {
+  const int j = threadIdx.x;
+  if (j > nb) return;
+  const int n = (int)*total;
+  int lo = 0, hi = n;
+  const int key = j * S;  // first set of iteration j
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (out_set[mid] < key)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  seg[j] = (j == nb) ? n : lo;
+}
+
+// per batch iteration: arg-max key (score << 32 | 0x7fffffff - store index; -1 if empty) over its new candidates
+__global__ void __launch_bounds__(256) seg_argmax_kernel(const int32_t* __restrict__ score, const uint8_t* __restrict__ flags,
+                                                         const int32_t* __restrict__ seg, int store_n0, long long* __restrict__ keys) {
+  __shared__ long long best[8];
+  const int j = blockIdx.x;
+  long long b = -1;
+  for (int i = seg[j] + threadIdx.x; i < seg[j + 1]; i += blockDim.x) {
+    const int g = store_n0 + i;
+    if (flags[g] & 1u) {
+      const long long key = ((long long)score[g] << 32) | (long long)(0x7fffffff - g);
+      b = key > b ? key : b;
+    }
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const long long o = __shfl_xor_sync(0xffffffffu, b, d);
+    b = o > b ? o : b;
+  }
+  if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) b = best[w] > b ? best[w] : b;
+    keys[j] = b;
+  }
+}
+
 // 1 if either guard-band queue (groups, pairs) of the last score call overflowed
 __global__ void queue_overflow_kernel(const uint32_t* __restrict__ wl_count, uint32_t cap, int32_t* __restrict__ out) {
   *out = (wl_count[0] > cap || wl_count[1] > cap) ? 1 : 0;
@@ -281,6 +329,9 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf;
   const bool cells_mode = (p->compat_flags & RSC_SAMPLER_OCTREE) != 0;
   const int nlv = cloud->cells.nlevels;
+  const int Bmax = cells_mode ? 1 : (getenv("RSC_BATCH") ? std::max(1, std::min(16, atoi(getenv("RSC_BATCH")))) : 16);
+  int B = 1;  // iterations per speculative batch
+  bool terminated = false;
   int64_t n_enabled = rsc_cloud_count_enabled(cloud);
   int64_t counters[3] = {0, 0, 0};  // lengthC, allcand, nofminset (iterations.jl:70)
   const bool trace = getenv("RSC_TRACE") != nullptr;
@@ -320,28 +371,42 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     RUN_CUDA(lvbuf.ensure(2 * 11 * 8));
   }
 
-  for (int k = 1; k <= p->itermax; ++k) {
+  // Iterations are run in speculative batches of nb: as long as nothing is extracted the enabled mask
+  // does not change, so iterations k..k+nb-1 can sample, fit and score together (one K2 launch over
+  // all their candidates, one or two host syncs per batch instead of per iteration).  The host then
+  // walks the batch iteration by iteration with exactly the reference's bookkeeping and cuts it at
+  // the first extraction or at termination; the later iterations of a cut batch are discarded and
+  // redone (their sets sampled a stale mask).  The cell sampler updates its level weights every
+  // iteration (iterations.jl:148), so it runs with nb = 1.
+  RUN_CUDA(newcnt.ensure((size_t)2 * maxnew * Bmax * 4 + 64));
+  RUN_CUDA(hostio.ensure(64 + (size_t)(Bmax + 2) * 8 + (size_t)(Bmax + 2) * 4));
+  for (int k = 1; k <= p->itermax && !terminated;) {
     if (n_enabled < p->tau) break;  // iterations.jl:75
-    run->iterations = k;
+    const int nb = std::min(B, p->itermax - k + 1);
     const auto tk0 = now();
-    // ---- K1: minsubsetN minimal sets -> candidates (device, compacted in reference order) ----
+    // ---- K1: nb * minsubsetN minimal sets -> candidates (device, compacted in reference order) ----
     FitScratch fs;
     double cum[11];
     if (cells_mode) rsc_level_cumsum(run->levelweight, nlv, cum);
-    if ((rc = fit_enqueue(ctx, cloud, cells_mode ? 3 : 2, p, p->drawN, nullptr, nullptr, nullptr, S, seed, (uint64_t)(k - 1) * S, st,
-                          &fs, cells_mode ? cum : nullptr)))
+    if ((rc = fit_enqueue(ctx, cloud, cells_mode ? 3 : 2, p, p->drawN, nullptr, nullptr, nullptr, S * nb, seed, (uint64_t)(k - 1) * S,
+                          st, &fs, cells_mode ? cum : nullptr)))
       goto done;
-    unsigned long long n_new_ = 0;
-    RUN_CUDA(cudaMemcpyAsync(&n_new_, fs.total, 8, cudaMemcpyDeviceToHost, st));
+    long long* d_keys = hostio.as<long long>() + 8;         // [nb] segment arg-max keys
+    int32_t* d_seg = (int32_t*)(d_keys + Bmax + 2);           // [nb + 1] segment bounds
+    int32_t seg_h[18] = {0};
+    seg_bounds_kernel<<<1, 32, 0, st>>>(fs.out_set, fs.total, S, nb, d_seg);
+    RUN_CUDA(cudaGetLastError());
+    RUN_CUDA(cudaMemcpyAsync(seg_h, d_seg, (size_t)(nb + 1) * 4, cudaMemcpyDeviceToHost, st));
     RUN_CUDA(cudaStreamSynchronize(st));
-    const int n_new = (int)n_new_;
-    counters[1] += n_new;
+    const int n_new = seg_h[nb];
     const auto tk1 = now();
     t_fit += secs(tk0, tk1);
     // ---- K2 on subset 1 + K3 ----  (repeated with a larger guard-band queue if that overflowed:
     // dropped queue entries would leave FP32 decisions in the counts)
     const int store_n0 = store.n;
     int64_t best[2] = {-1, 0};
+    long long seg_keys[18];
+    for (int j = 0; j < 18; ++j) seg_keys[j] = -1;
     long long lv_host[22] = {0};
     for (int attempt = 0;; ++attempt) {
       store.n = store_n0;
@@ -381,11 +446,17 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
         }
         store.n += n_new;
       }
-      if (store.n >= 1) {
-        argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store.n,
+      if (store_n0 >= 1) {  // best of the candidates stored before this batch
+        argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0,
                                           hostio.as<int64_t>());
         RUN_CUDA(cudaGetLastError());
         RUN_CUDA(cudaMemcpyAsync(best, hostio.p, 16, cudaMemcpyDeviceToHost, st));
+      }
+      if (n_new > 0) {  // and of every iteration's new candidates
+        seg_argmax_kernel<<<nb, 256, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), d_seg,
+                                               store_n0, d_keys);
+        RUN_CUDA(cudaGetLastError());
+        RUN_CUDA(cudaMemcpyAsync(seg_keys, d_keys, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
       }
       RUN_CUDA(cudaStreamSynchronize(st));
       if (ovf == 0) break;
@@ -395,28 +466,42 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
       }
       if ((rc = grow_guard_queue(ctx))) goto done;
     }
-    counters[2] = (int64_t)k * S;
+    const auto tk2 = now();
+    t_score += secs(tk1, tk2);
+    // ---- walk the iterations of the batch with the reference's bookkeeping ----
+    long long bestkey = (store_n0 >= 1 && best[0] >= 0) ? (((long long)best[1] << 32) | (long long)(0x7fffffff - best[0])) : -1;
+    bool extracted_now = false;
+    int used = 0;
+    for (int j = 0; j < nb && !extracted_now && !terminated; ++j) {
+    const int kk = k + j;
+    run->iterations = kk;
+    used = j + 1;
+    counters[1] += seg_h[j + 1] - seg_h[j];
+    store.n = store_n0 + seg_h[j + 1];
+    counters[2] = (int64_t)kk * S;
     counters[0] = store.n;
     if (cells_mode && n_new > 0) {  // levelscore[level] += sum of E = -n + (N+2)/(M+2) (sum sigma + n)
       for (int l = 0; l < nlv; ++l)
         if (lv_host[l])
           run->levelscore[l] += (-(double)lv_host[l]) + ((double)(N + 2) / (double)(sub.m + 2)) * (double)(lv_host[11 + l] + lv_host[l]);
     }
+    if (seg_keys[j] > bestkey) bestkey = seg_keys[j];  // first maximum wins: the key carries the store index
+    best[0] = bestkey >= 0 ? (int64_t)(0x7fffffff - (bestkey & 0xffffffffll)) : -1;
+    best[1] = bestkey >= 0 ? (int64_t)(bestkey >> 32) : 0;
     if (store.n >= 1) {
-      const auto tk2 = now();
-      t_score += secs(tk1, tk2);
       if (best[0] >= 0) {
         double E;
         rsc_estimate_score(sub.m, N, best[1], nullptr, nullptr, &E);
         const double s_ex = (double)counters[p->extract_s];
         if (prob_(E, s_ex, (double)N, (double)p->drawN) > p->prob_det) {
           // ---- K4: refit over the whole cloud, invalidate its points ----
+          const auto tkx = now();
           rsc_cand shape;
           RUN_CUDA(cudaMemcpyAsync(&shape, store.cands[store.cur].as<rsc_cand>() + best[0], sizeof(shape),
                                    cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaStreamSynchronize(st));
           const auto tka = now();
-          t_exa += secs(tk2, tka);
+          t_exa += secs(tkx, tka);
           Thresh thr = th;
           thr.honour_enabled = 0xFu;
           if ((rc = refit_mask_enqueue(cloud, thr, shape, st))) goto done;
@@ -434,7 +519,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           run->off.push_back(run->off.back() + (int64_t)total);
           n_enabled -= (int64_t)total;
           const auto tk3 = now();
-          t_extract += secs(tk2, tk3);
+          t_extract += secs(tkx, tk3);
           // ---- K5: drop the best and every candidate compatible with a newly disabled subset point ----
           const int nst = store.n;
           // scratch layout: [wcnt: swords u32][woff: swords u64][wtot u64][keep: nst u32][koff: nst u64][ktot u64]
@@ -509,12 +594,17 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           store.cur = nxt;
           store.n = (int)kept;
           t_k5 += secs(tk3, now());
+          extracted_now = true;  // the rest of the batch sampled the mask of before this extraction
         }
       }
     }
     if (cells_mode) rsc_update_levelweight(run->levelweight, run->levelscore, nlv);  // iterations.jl:148
     // iterations.jl:151-156
-    if (prob_((double)p->tau, (double)counters[p->terminate_s], (double)N, (double)p->drawN) > p->prob_det) break;
+    if (prob_((double)p->tau, (double)counters[p->terminate_s], (double)N, (double)p->drawN) > p->prob_det) terminated = true;
+    }  // iterations of the batch
+    k += used;
+    B = extracted_now ? 2 : std::min(2 * B, Bmax);
+    if (B > Bmax) B = Bmax;
   }
 done:
   cudaStreamSynchronize(st);
