@@ -228,6 +228,7 @@ struct FitScratch {
 int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
                     const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
                     FitScratch* fs, const double* cum = nullptr);
+int32_t fit_reserve(rsc_ctx* ctx, const rsc_params* params, int S);
 int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st);
 int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st);
 }  // namespace rsc

@@ -720,6 +720,12 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restri
 
 // Enqueue fit (+ sampling) for S sets; leaves compacted candidates in ctx->fitbuf (FitScratch.out),
 // their count in FitScratch.total.  No synchronisation.
+// size the scratch for batches of up to S sets once (the device loop grows its batches while it runs)
+int32_t fit_reserve(rsc_ctx* ctx, const rsc_params* params, int S) {
+  FitScratch fs;
+  return carve(ctx, S, params->n_shape_types, params->drawN, &fs);
+}
+
 // mode 0: explicit coordinates, 1: explicit indices, 2: root-cell sampler (the reference's behaviour,
 // Q1), 3: level-weighted cell sampler on the flattened octree (`cum` = cumulative level weights)
 int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,

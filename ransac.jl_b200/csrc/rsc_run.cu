@@ -380,6 +380,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   // iteration (iterations.jl:148), so it runs with nb = 1.
   RUN_CUDA(newcnt.ensure((size_t)2 * maxnew * Bmax * 4 + 64));
   RUN_CUDA(hostio.ensure(64 + (size_t)(Bmax + 2) * 8 + (size_t)(Bmax + 2) * 4));
+  if ((rc = fit_reserve(ctx, p, S * Bmax))) goto done;
+  RUN_CUDA(store.reserve((size_t)maxnew * Bmax, st));  // room for the first batches without re-allocations
   for (int k = 1; k <= p->itermax && !terminated;) {
     if (n_enabled < p->tau) break;  // iterations.jl:75
     const int nb = std::min(B, p->itermax - k + 1);
