@@ -120,7 +120,7 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   rsc::DevBuf* bufs[] = {&ctx->cands,    &ctx->rec,      &ctx->orig,     &ctx->slot_of, &ctx->blktab,
                          &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count, &ctx->pairs,
-                         &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf, &ctx->exq};
+                         &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf, &ctx->exq, &ctx->scanbuf};
   for (auto* b : bufs) b->release();
   ctx->stage[0].release(), ctx->stage[1].release();
   cudaStreamDestroy(ctx->copy_stream);

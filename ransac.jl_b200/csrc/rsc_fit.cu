@@ -631,8 +631,7 @@ int32_t build_select_index(rsc_cloud* cloud, cudaStream_t st, unsigned long long
   if (!cloud->sel_valid) {
     block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(cloud->enabled, words, cnt, nb);
     RSC_CUDA(ctx, cudaGetLastError());
-    scan_u32_kernel<<<1, 1024, 0, st>>>(cnt, nb, offs, total);
-    RSC_CUDA(ctx, cudaGetLastError());
+    if (int32_t rcs = scan_u32(ctx, cnt, nb, offs, total, st)) return rcs;
     cloud->sel_valid = true;
   }
   *boff = offs;
@@ -658,8 +657,7 @@ int32_t build_cells_index(rsc_cloud* cloud, cudaStream_t st, const double* cum, 
   if (!c.sel_valid) {
     block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(c.en_sorted, words, cnt, nb);
     RSC_CUDA(ctx, cudaGetLastError());
-    scan_u32_kernel<<<1, 1024, 0, st>>>(cnt, nb, offs, total);
-    RSC_CUDA(ctx, cudaGetLastError());
+    if (int32_t rcs = scan_u32(ctx, cnt, nb, offs, total, st)) return rcs;
     c.sel_valid = true;
   }
   v->codes = c.codes, v->perm = c.perm, v->inv = c.inv, v->leafdepth = c.leafdepth, v->en_sorted = c.en_sorted;
@@ -718,6 +716,90 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restri
   if (tid == 0) *out_total = carry;
 }
 
+// ---- exclusive scan of n uint32 counts into 64-bit offsets (+ total), any n -------------------
+// Up to 32 Ki elements one CTA does it; beyond that: per-CTA sums of 8 Ki-element tiles, a one-CTA scan
+// of the tile sums, and a second pass in which every CTA scans its own tile on top of its offset.
+constexpr int kScanTile = 8192;
+
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(const uint32_t* __restrict__ counts, int n, uint32_t* __restrict__ sums) {
+  __shared__ uint32_t ws[32];
+  const int base = blockIdx.x * kScanTile;
+  uint32_t s = 0;
+#pragma unroll
+  for (int e = 0; e < kScanTile / 1024; ++e) {
+    const int i = base + e * 1024 + threadIdx.x;
+    if (i < n) s += counts[i];
+  }
+  s = __reduce_add_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = __reduce_add_sync(0xffffffffu, ws[threadIdx.x]);
+    if (threadIdx.x == 0) sums[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) scan_tile_apply_kernel(const uint32_t* __restrict__ counts, int n,
+                                                               const unsigned long long* __restrict__ tile_off,
+                                                               unsigned long long* __restrict__ offsets) {
+  constexpr int E = kScanTile / 1024;
+  __shared__ unsigned long long wex[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * kScanTile + tid * E;
+  uint32_t v[E];
+  unsigned long long s = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    v[e] = (i0 + e < n) ? counts[i0 + e] : 0u;
+    s += v[e];
+  }
+  unsigned long long inc = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) wex[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long t = wex[lane];
+    unsigned long long ti = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(0xffffffffu, ti, d);
+      if (lane >= d) ti += o;
+    }
+    wex[lane] = ti - t;
+  }
+  __syncthreads();
+  unsigned long long run = tile_off[blockIdx.x] + wex[warp] + (inc - s);
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (i0 + e < n) offsets[i0 + e] = run;
+    run += v[e];
+  }
+}
+
+int32_t scan_u32(rsc_ctx* ctx, const uint32_t* counts, int n, unsigned long long* offsets, unsigned long long* total,
+                 cudaStream_t st) {
+  if (n <= 4 * kScanTile) {
+    scan_u32_kernel<<<1, 1024, 0, st>>>(counts, n, offsets, total);
+    RSC_CUDA(ctx, cudaGetLastError());
+    return RSC_OK;
+  }
+  const int tiles = (n + kScanTile - 1) / kScanTile;
+  RSC_CUDA(ctx, ctx->scanbuf.ensure((size_t)tiles * (4 + 8) + 64));
+  unsigned long long* toff = ctx->scanbuf.as<unsigned long long>();
+  uint32_t* tsum = (uint32_t*)(toff + tiles + 1);
+  scan_tile_sums_kernel<<<tiles, 1024, 0, st>>>(counts, n, tsum);
+  RSC_CUDA(ctx, cudaGetLastError());
+  scan_u32_kernel<<<1, 1024, 0, st>>>(tsum, tiles, toff, total);
+  RSC_CUDA(ctx, cudaGetLastError());
+  scan_tile_apply_kernel<<<tiles, 1024, 0, st>>>(counts, n, toff, offsets);
+  RSC_CUDA(ctx, cudaGetLastError());
+  return RSC_OK;
+}
+
 // Enqueue fit (+ sampling) for S sets; leaves compacted candidates in ctx->fitbuf (FitScratch.out),
 // their count in FitScratch.total.  No synchronisation.
 // size the scratch for batches of up to S sets once (the device loop grows its batches while it runs)
@@ -761,8 +843,7 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
     }
     fit_kernel<<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->flags);
     RSC_CUDA(ctx, cudaGetLastError());
-    scan_u32_kernel<<<1, 1024, 0, st>>>(fs->flags, slots, fs->offs, fs->total);
-    RSC_CUDA(ctx, cudaGetLastError());
+    if ((rc = scan_u32(ctx, fs->flags, slots, fs->offs, fs->total, st))) return rc;
     compact_kernel<<<(slots + 255) / 256, 256, 0, st>>>(fs->dense, fs->flags, fs->offs, slots, f.ntypes, fs->out, fs->out_set);
     RSC_CUDA(ctx, cudaGetLastError());
   } else {

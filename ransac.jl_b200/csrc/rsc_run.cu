@@ -536,8 +536,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           unsigned long long* koff = (unsigned long long*)(nmeta.as<char>() + o_koff);
           newly_count_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(olden.as<uint32_t>(), sub.enabled, swords, wcnt);
           RUN_CUDA(cudaGetLastError());
-          scan_u32_kernel<<<1, 1024, 0, st>>>(wcnt, (int)swords, woff, wtot);
-          RUN_CUDA(cudaGetLastError());
+          if ((rc = scan_u32(ctx, wcnt, (int)swords, woff, wtot, st))) goto done;
           unsigned long long nnew_dis = 0;
           RUN_CUDA(cudaMemcpyAsync(&nnew_dis, wtot, 8, cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaStreamSynchronize(st));
@@ -575,8 +574,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           unsigned long long* ktot = koff + nst;
           invalidate_kernel<<<(nst + 255) / 256, 256, 0, st>>>(hit, store.flags[store.cur].as<uint8_t>(), nst, (int)best[0], keep);
           RUN_CUDA(cudaGetLastError());
-          scan_u32_kernel<<<1, 1024, 0, st>>>(keep, nst, koff, ktot);
-          RUN_CUDA(cudaGetLastError());
+          if ((rc = scan_u32(ctx, keep, nst, koff, ktot, st))) goto done;
           nxt = store.cur ^ 1;
           compact_store_kernel<<<(nst + 255) / 256, 256, 0, st>>>(
               store.cands[store.cur].as<rsc_cand>(), store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(),
