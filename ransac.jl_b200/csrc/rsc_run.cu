@@ -330,6 +330,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   const bool cells_mode = (p->compat_flags & RSC_SAMPLER_OCTREE) != 0;
   const int nlv = cloud->cells.nlevels;
   const int Bmax = cells_mode ? 1 : (getenv("RSC_BATCH") ? std::max(1, std::min(16, atoi(getenv("RSC_BATCH")))) : 16);
+  const int Bmin = getenv("RSC_BATCH_MIN") ? std::max(1, atoi(getenv("RSC_BATCH_MIN"))) : 8;  // batch size after an extraction (swept on c2/c4: 8-16 best)
   int B = 1;  // iterations per speculative batch
   bool terminated = false;
   int64_t n_enabled = rsc_cloud_count_enabled(cloud);
@@ -603,7 +604,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     if (prob_((double)p->tau, (double)counters[p->terminate_s], (double)N, (double)p->drawN) > p->prob_det) terminated = true;
     }  // iterations of the batch
     k += used;
-    B = extracted_now ? 2 : std::min(2 * B, Bmax);
+    B = extracted_now ? std::min(Bmin, Bmax) : std::min(2 * B, Bmax);
     if (B > Bmax) B = Bmax;
   }
 done:

@@ -60,7 +60,7 @@ def _ransac_device(pc, params, seed, sampler="root"):
             cand = _lib.rsc_cand()
             n = C.c_int64()
             pc.ctx.check(lib.rsc_run_shape(run, i, C.byref(cand), C.byref(n)))
-            idx = np.zeros(n.value, dtype=np.int64)
+            idx = np.empty(n.value, dtype=np.int64)  # filled by rsc_run_inpoints (device -> host)
             if n.value:
                 pc.ctx.check(lib.rsc_run_inpoints(run, i, idx.ctypes.data))
             out.append(ExtractedShape(from_cand(cand), idx))
@@ -71,6 +71,7 @@ def _ransac_device(pc, params, seed, sampler="root"):
             pc.levelweight, pc.levelscore = lw[:nl].copy(), ls[:nl].copy()
     finally:
         lib.rsc_run_destroy(run)
+    pc.last_run_seconds = secs  # unrounded device-loop time (the return value is truncated like the reference's)
     return out, int(secs * 100) / 100.0
 
 
