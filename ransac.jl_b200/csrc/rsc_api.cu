@@ -122,6 +122,7 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
                          &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count, &ctx->pairs,
                          &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf, &ctx->exq, &ctx->scanbuf};
   for (auto* b : bufs) b->release();
+  rsc::loop_scratch_free(ctx);
   ctx->stage[0].release(), ctx->stage[1].release();
   cudaStreamDestroy(ctx->copy_stream);
   for (int i = 0; i < 4; ++i) {

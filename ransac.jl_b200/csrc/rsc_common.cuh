@@ -88,6 +88,7 @@ struct rsc_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evr0 = nullptr, evr1 = nullptr;
   cudaStream_t sfork[4] = {nullptr, nullptr, nullptr, nullptr};  // the per-type score kernels of one call run side by side
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* loop_scratch = nullptr;        // rsc::LoopScratch of rsc_ransac_run, kept between runs (rsc_run.cu)
   int last_cslots = 0;                 // slot stride of the last compiled candidate records / masks
   std::string err;
   rsc_stats stats{};
@@ -228,6 +229,7 @@ struct FitScratch {
 int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
                     const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
                     FitScratch* fs, const double* cum = nullptr);
+void loop_scratch_free(rsc_ctx* ctx);
 int32_t fit_reserve(rsc_ctx* ctx, const rsc_params* params, int S);
 // exclusive scan of n uint32 counts into 64-bit offsets (+ total) on `st` (rsc_fit.cu)
 int32_t scan_u32(rsc_ctx* ctx, const uint32_t* counts, int n, unsigned long long* offsets, unsigned long long* total,

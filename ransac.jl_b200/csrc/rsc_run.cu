@@ -177,6 +177,23 @@ struct Store {
   }
 };
 
+// scratch of the device loop, kept on the context between runs (allocating and freeing ~100 MB of
+// device buffers per run cost 10-25 ms of a 40 ms loop)
+struct LoopScratch {
+  Store store;
+  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf;
+};
+
+void loop_scratch_free(rsc_ctx* ctx) {
+  LoopScratch* ls = static_cast<LoopScratch*>(ctx->loop_scratch);
+  if (!ls) return;
+  ls->store.release();
+  ls->newcnt.release(), ls->hostio.release(), ls->olden.release(), ls->nscratch.release(), ls->nvalid.release(), ls->nmeta.release();
+  ls->lvbuf.release();
+  delete ls;
+  ctx->loop_scratch = nullptr;
+}
+
 static double prob_(double n, double s, double N, double k) { return 1 - pow(1 - pow(n / N, k), s); }
 
 }  // namespace rsc
@@ -312,7 +329,10 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   cudaStream_t st = ctx->stream;
   const auto t0 = std::chrono::steady_clock::now();
   rsc_run* run = new rsc_run();
-  Store store;
+  if (!ctx->loop_scratch) ctx->loop_scratch = new LoopScratch();
+  LoopScratch& ls = *static_cast<LoopScratch*>(ctx->loop_scratch);
+  Store& store = ls.store;
+  store.n = 0, store.cur = 0;
   int32_t rc = RSC_OK;
   const Thresh th = make_thresh(p);
   rsc_subset& sub = cloud->subsets[0];
@@ -326,7 +346,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     slo = (int64_t)((double)cloud->range_lo / cloud->n_pad * sub.m_pad) / kTile * kTile;
     shi = cloud->range_hi >= cloud->n_pad ? sub.m_pad : (int64_t)((double)cloud->range_hi / cloud->n_pad * sub.m_pad) / kTile * kTile;
   }
-  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf;
+  DevBuf &newcnt = ls.newcnt, &hostio = ls.hostio, &olden = ls.olden, &nscratch = ls.nscratch, &nvalid = ls.nvalid, &nmeta = ls.nmeta,
+         &lvbuf = ls.lvbuf;
   const bool cells_mode = (p->compat_flags & RSC_SAMPLER_OCTREE) != 0;
   const int nlv = cloud->cells.nlevels;
   const int Bmax = cells_mode ? 1 : (getenv("RSC_BATCH") ? std::max(1, std::min(16, atoi(getenv("RSC_BATCH")))) : 16);
@@ -342,11 +363,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     return std::chrono::duration<double>(b - a).count();
   };
 
-  auto cleanup = [&]() {
-    store.release();
-    newcnt.release(), hostio.release(), olden.release(), nscratch.release(), nvalid.release(), nmeta.release();
-    lvbuf.release();
-  };
+  auto cleanup = [&]() {};  // the scratch stays on the context (loop_scratch_free at rsc_ctx_destroy)
 #define RUN_CUDA(expr)                                  \
   do {                                                  \
     cudaError_t _e = (expr);                            \
