@@ -101,7 +101,8 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
   constexpr int KP = kPacked ? K / 2 : 1;
   // U = 3: pair-major source order (all four points of a pair, then the next pair).  ptxas schedules the
   // block itself, but from this order it finds 1-5 % better operand reuse than from point-major (U = 1);
-  // a lockstep order (every formula step for the four points back to back) was measured and is no better.
+  // a lockstep order (every formula step for the four points back to back) and eight points per pair
+  // were measured and are no better.
   constexpr bool kOrderJQ = (U == 3);
   float r[kPacked ? 1 : K][NR];  // scalar records (K odd)
   float2 r2[KP][NR];             // packed records: .x = candidate 2j, .y = candidate 2j+1
