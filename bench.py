@@ -335,6 +335,12 @@ def main():
                         "peak_gbs": peaks.get("hbm_gbs"), "bound": "hbm", "algorithmic_bytes_per_point": 24.125}
     except Exception as e:  # informational key only
         out["refit"] = {"error": repr(e)}
+    # counts + packed bitmasks variant, device resident: 4096 x 4 Mi points -> 2 GiB of masks
+    if world == 1:
+        try:
+            out["masks_variant"] = time_masks_variant(R, lib, C, torch, sc, cands, params, local, dev)
+        except Exception as e:  # informational key only
+            out["masks_variant"] = {"error": repr(e)}
     if args.ransac != "none" and world == 1:
         out["ransac"] = time_ransac(R, args.ransac, local)
     if not args.no_cpu and world == 1:
@@ -343,6 +349,37 @@ def main():
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_masks_variant(R, lib, C, torch, sc, cands, params, local, dev, npts=4 << 20):
+    """rsc_score_dev_masks: counts + candidate-major inlier bitmasks written to device memory."""
+    n = min(npts, len(sc.vertices))
+    pc = R.RANSACCloud(sc.vertices[:n], sc.normals[:n], [np.zeros(0, np.int64)], device=local)
+    cp = R.to_c(params)
+    Cn = len(cands)
+    arr = R.pack_cands(cands)
+    d_cands = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    d_counts = torch.zeros(Cn, dtype=torch.int32, device=dev)
+    words = (n + 31) // 32
+    d_masks = torch.empty((Cn, words), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    best = None
+    for it in range(4):
+        ev[0].record()
+        pc.ctx.check(lib.rsc_score_dev_masks(pc.handle, C.byref(cp), d_cands.data_ptr(), Cn, -1, d_counts.data_ptr(),
+                                             d_masks.data_ptr(), st.cuda_stream))
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1])
+        best = ms if best is None or ms < best else best
+    # popcount of the masks must equal the counts (sample of candidates)
+    sel = list(range(0, Cn, 257))
+    pop = [int(np.unpackbits(d_masks[i].cpu().numpy().view(np.uint8)).sum()) for i in sel]
+    ok = pop == [int(d_counts[i].item()) for i in sel]
+    pc.close()
+    return {"points": n, "candidates": Cn, "ms_per_step": best, "G_evals_s": Cn * n / best / 1e6, "mask_bytes": int(Cn * words * 4),
+            "popcount_equals_counts": bool(ok)}
 
 
 def time_ransac(R, which, device):

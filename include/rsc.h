@@ -160,6 +160,10 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
  * (NULL = the context stream) and returns without synchronising. */
 int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,
                       int32_t subset_id, int32_t* d_counts, void* stream);
+/* same, plus the packed inlier bitmasks, candidate-major [C][ceil(m/32)] uint32 words (LSB = first point of the
+ * set; gated like the counts), written to DEVICE memory -- the counts+masks variant without a host round trip. */
+int32_t rsc_score_dev_masks(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,
+                            int32_t subset_id, int32_t* d_counts, uint32_t* d_masks, void* stream);
 /* estimatescore (confidenceintervals.jl:53-74), Int64 wrap-around included (Q9). */
 void rsc_estimate_score(int64_t subset_len, int64_t cloud_len, int64_t count, double* out_min,
                         double* out_max, double* out_E);

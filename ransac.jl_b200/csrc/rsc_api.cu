@@ -279,6 +279,23 @@ int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand
   return score_enqueue(ctx, cloud, ps, make_thresh(params), d_cands, C, d_counts, false, st);
 }
 
+int32_t rsc_score_dev_masks(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,
+                            int32_t subset_id, int32_t* d_counts, uint32_t* d_masks, void* stream) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (C < 0 || (C > 0 && (!d_cands || !d_counts || !d_masks))) return fail(ctx, RSC_E_ARG, "score_dev_masks: null device pointers");
+  int32_t rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (C == 0) return RSC_OK;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((rc = cloud_ready(cloud))) return rc;
+  PointSet ps;
+  if ((rc = pick_pointset(cloud, subset_id, &ps))) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  if ((rc = score_enqueue(ctx, cloud, ps, make_thresh(params), d_cands, C, d_counts, true, st))) return rc;
+  return masks_to_candidate_major(ctx, C, ps.n, st, d_masks);
+}
+
 static inline int64_t wrapmul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
 
 void rsc_estimate_score(int64_t subset_len, int64_t cloud_len, int64_t count, double* out_min, double* out_max,

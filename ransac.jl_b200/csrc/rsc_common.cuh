@@ -210,7 +210,8 @@ int32_t cloud_ready(rsc_cloud* cloud);
 // refresh the gathered enabled bits of every uploaded subset from the cloud's enabled mask
 int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st);
 
-int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st);
+// group-major masks of the last score_enqueue(want_masks) -> candidate-major [C][ceil(m/32)] (d_out, or ctx->masks_cm)
+int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st, uint32_t* d_out = nullptr);
 
 }  // namespace rsc
 

@@ -782,13 +782,16 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
 }
 
 // after score_enqueue(want_masks=true): ctx->masks_cm = [C][ceil(m/32)] candidate-major masks
-int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st) {
+int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st, uint32_t* d_out) {
   const int cslots = ctx->last_cslots;
   const int64_t words = (m + 31) / 32;
-  RSC_CUDA(ctx, ctx->masks_cm.ensure((size_t)C * words * sizeof(uint32_t)));
+  if (!d_out) {
+    RSC_CUDA(ctx, ctx->masks_cm.ensure((size_t)C * words * sizeof(uint32_t)));
+    d_out = ctx->masks_cm.as<uint32_t>();
+  }
   dim3 grid((unsigned)((C + 31) / 32), (unsigned)((words + 31) / 32));
   masks_transpose_kernel<<<grid, dim3(32, 32), 0, st>>>(ctx->masks_gm.as<uint32_t>(), ctx->slot_of.as<int32_t>(),
-                                                        C, cslots, words, ctx->masks_cm.as<uint32_t>());
+                                                        C, cslots, words, d_out);
   RSC_CUDA(ctx, cudaGetLastError());
   return RSC_OK;
 }

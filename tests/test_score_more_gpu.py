@@ -272,3 +272,34 @@ def test_many_candidates_multi_column_masks(R):
     np.testing.assert_array_equal(counts, want)
     for i in range(0, len(cands), 211):
         np.testing.assert_array_equal(R.unpack_mask(masks[i], pc.size), wmask[i])
+
+
+def test_score_dev_masks_device_pointers(R):
+    """rsc_score_dev_masks: candidates, counts and candidate-major masks all in device memory"""
+    import ctypes as C
+
+    import torch
+
+    from ransac_jl_b200 import scenes
+    from ransac_jl_b200._lib import lib
+
+    sc = scenes.scene_mixed(110, 20_001)  # ragged: not a multiple of 32
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 2)
+    en = np.random.default_rng(1).random(pc.size) > 0.3
+    pc.isenabled = en
+    params = R.ransacparameters()
+    cands = [p.shape for p in sc.primitives] + scenes.perturbed_candidates(sc, 40, seed=3)
+    cp = R.to_c(params)
+    dev = torch.device("cuda", 0)
+    d_cands = torch.frombuffer(bytearray(bytes(R.pack_cands(cands))), dtype=torch.uint8).to(dev)
+    for subset in (-1, 0):
+        m = pc.size if subset < 0 else len(pc.subsets[0])
+        words = (m + 31) // 32
+        d_counts = torch.zeros(len(cands), dtype=torch.int32, device=dev)
+        d_masks = torch.zeros((len(cands), words), dtype=torch.int32, device=dev)
+        pc.ctx.check(lib.rsc_score_dev_masks(pc.handle, C.byref(cp), d_cands.data_ptr(), len(cands), subset, d_counts.data_ptr(),
+                                             d_masks.data_ptr(), None))
+        torch.cuda.synchronize()
+        counts, masks = R.score_counts(pc, cands, subset, params, want_masks=True)  # host-buffer path
+        np.testing.assert_array_equal(d_counts.cpu().numpy(), counts)
+        np.testing.assert_array_equal(d_masks.cpu().numpy().view(np.uint32), np.asarray(masks).reshape(len(cands), words))
