@@ -127,14 +127,20 @@ def cpu_baseline(sc, cands, params, budget_pts: int, ncand: int = 64):
     sample = cands[::step]
     t0 = time.perf_counter()
     if have_c:
-        cores = c_oracle.score_counts(sample, P, N, op)[1]
+        cores = c_oracle.score_counts(sample, P, N, op, nthreads=os.cpu_count() or 1)[1]  # all host threads, explicitly
     else:
         cores = 1
         for sh in sample:
             O.compatibles(to_oracle_shape(sh), P, N, op)
     dt = time.perf_counter() - t0
     ev = len(sample) * n
-    return {"value": ev / dt / 1e9, "unit": "G evals/s", "cores": cores, "kind": "port",
+    single = None
+    if have_c:  # the reference is single-threaded: the same code on ONE thread, on 1/16 of the points
+        n1 = max(1, n // 16)
+        t1 = time.perf_counter()
+        c_oracle.score_counts(sample, P[:n1], N[:n1], op, nthreads=1)
+        single = len(sample) * n1 / (time.perf_counter() - t1) / 1e9
+    return {"value": ev / dt / 1e9, "unit": "G evals/s", "cores": cores, "kind": "port", "single_thread_value": single,
             "sample": f"{len(sample)} candidates (every {step}th, all four types) x first {n} points of the workload; "
                       f"{'C (OpenMP)' if have_c else 'NumPy'} float64 restatement of RANSAC.jl compatibles*, {dt:.2f} s"}
 
