@@ -7,6 +7,11 @@
 // -> host decides with prob() (utilities.jl:262) -> on extraction K4 refit over the whole cloud
 // (rsc_extract.cu), enabled bits cleared, store invalidated and compacted.
 //
+// Iterations run in SPECULATIVE BATCHES of up to 16: as long as nothing is extracted the enabled mask
+// is unchanged, so the iterations of a batch sample (same Philox set ids as separate iterations), fit
+// and score together; the host then walks the batch with the reference's bookkeeping, iteration by
+// iteration, and cuts it at the first extraction or at termination (see the loop below).
+//
 // K5 without stored inlier lists: every stored candidate's subset-1 inliers are enabled at the time
 // of an extraction (the reference removes any candidate with a disabled inlier at each extraction,
 // and new candidates only count enabled points), so "has a now-disabled inlier" == "is compatible
@@ -23,10 +28,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <vector>
-
-#include <algorithm>
 
 #include "rsc_common.cuh"
 

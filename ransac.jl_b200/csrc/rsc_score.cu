@@ -4,15 +4,21 @@
 // Replaces scorecandidates!/scorecandidate/compatibles* (fitting.jl:181-190, plane.jl:61-130,
 // sphere.jl:118-172, cylinder.jl:172-221, cone.jl:132-167).
 //
-// Mapping (B200-first, the path is FP32-ALU bound):
-//   * candidates are register resident: every thread owns K compiled candidates of ONE shape type
-//     (a CTA column = 128*K "slots" of one type, so no warp ever diverges on the type);
-//   * points stream HBM (SoA, 128-bit loads) -> shared memory (re-packed as {x,y,z,nx},{ny,nz}) and
-//     are read back as warp-wide BROADCAST loads: 2 LDS per point feed K*32 evaluations per warp;
-//   * the inlier bit of each evaluation is shifted into a per-candidate register (one 32-bit mask
-//     word per 32 points), so counting is one POPC per 32 evaluations and bitmasks come for free;
-//   * per evaluation the kernel also tracks min|margin|; only if that falls inside the FP32 guard
-//     band is the 32-point group re-examined and the ambiguous pairs queued for FP64 (fixup_kernel).
+// Mapping (B200-first, the path is FP32-issue bound):
+//   * candidates are register resident: every thread owns K compiled candidates of ONE column type
+//     (plane, sphere, cylinder, cone, wide cone; a CTA column = 128*K "slots" of one type, one kernel
+//     per type, so no warp ever diverges on the type), evaluated as K/2 packed pairs (FFMA2);
+//   * points stream HBM (SoA rows) -> warp-private shared-memory stages by TMA bulk copies
+//     (cp.async.bulk + mbarrier, no CTA barrier in the loop) and are read back as warp-wide BROADCAST
+//     128-bit loads: 6 LDS per 4 points feed K*32*4 evaluations per warp;
+//   * the inlier bit of each evaluation (sign of its margin) is funnel-shifted into a per-candidate
+//     register (one 32-bit mask word per 32 points), so counting is one POPC per 32 evaluations and
+//     bitmasks come for free;
+//   * per evaluation the kernel also tracks min|margin|; a 32-point group whose minimum falls inside
+//     the FP32 guard band is queued, re-scanned (fixup_scan_kernel) and its ambiguous pairs are
+//     decided in FP64 in the reference's operation order (fixup_pair_kernel).
+// DESIGN.md section 3 has the measurements behind these choices and the register-bank analysis of
+// what bounds the kernel.
 #include <math.h>
 #include <stdlib.h>
 
