@@ -25,6 +25,7 @@ from .fitting import (
     unpack_mask,
 )
 from .iterations import ransac
+from .jsonyaml import dict2nt, exportJSON, readconfig, toDict
 from .params import (
     DEFAULT_PARAMETERS,
     DEFAULT_SHAPE_DICT,
