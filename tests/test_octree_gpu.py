@@ -102,3 +102,13 @@ def test_loop_with_cell_sampler_matches_oracle(R):
     pc2 = R.RANSACCloud(sc.vertices, sc.normals, pc.subsets)
     b, _ = R.ransac(pc2, params, True, seed=11)
     assert [len(x.inpoints) for x in a] == [len(x.inpoints) for x in b]
+
+
+def test_reference_grid_leaf_depth(R):
+    # test/octree.jl:116-139 on the device structure: 6^3 grid, every leaf at depth 3
+    ps = (np.array([[i, j, k] for i in range(6) for j in range(6) for k in range(6)], float) / 3).astype(np.float32)
+    for nlevels in (3, 6):
+        pc = R.RANSACCloud(ps, ps, 1).build_cells(nlevels)
+        _, perm, ld = pc.get_cells()
+        assert (ld == 3).all()
+        np.testing.assert_array_equal(perm.astype(np.int64), O.MortonOctree(ps, nlevels).perm)

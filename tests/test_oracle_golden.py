@@ -109,3 +109,18 @@ def test_estimatescore_int64_overflow_keeps_E():
     M, N, s = 1 << 19, 1 << 24, 40000
     ci = O.estimatescore(M, N, s)
     assert ci.E == pytest.approx(-1 + (N + 2) * (s + 1) / (M + 2), rel=1e-12)
+
+
+def test_octree_depth_on_the_reference_grid():
+    # test/octree.jl:116-139: 6^3 grid with spacing 1/3 -> every leaf has depth 3, the tree has depth 3,
+    # getnthcell(leaf, 2) / (leaf, 1) are the parent / the root.  Restated on the flattened octree.
+    ps = np.array([[i, j, k] for i in range(6) for j in range(6) for k in range(6)], float) / 3
+    for nlevels in (3, 5, 8):
+        oc = O.MortonOctree(ps, nlevels)
+        assert (oc.leafdepth == 3).all()  # findleaf(pc.octree, ps[117]).data.depth == 3; octreedepth == 3
+        a3, b3 = oc.cell_range(116, 3)  # ps[117] is 1-based
+        a2, b2 = oc.cell_range(116, 2)
+        a1, b1 = oc.cell_range(116, 1)
+        assert (a1, b1) == (0, 216) and b2 - a2 == 27 and 1 <= b3 - a3 <= 8
+        assert a1 <= a2 <= a3 and b3 <= b2 <= b1  # leaf within parent within root
+        assert set(oc.perm[a3:b3]) <= set(oc.perm[a2:b2])
