@@ -349,8 +349,8 @@ def main():
         "traffic": NCU_TRAFFIC_BYTES if (Cn == 4096 and n == (16 << 20)) else None,
         "peak_source": f"derived: {nsm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry; "
                        "the path uses no tensor cores and is not HBM bound)",
-        "kernel": "rsc::score_kernel<T,K,MINB,U,MASKS> x4 (one launch per shape type, side by side on four streams; "
-                  "kernel_ms = CUDA events around the four launches)", "kernel_ms": kernel_ms,
+        "kernel": "rsc::score_kernel<T,K,MINB,U,MASKS> x5 (one launch per column type: plane, sphere, cylinder, cone, wide cone; "
+                  "side by side on forked streams; kernel_ms = CUDA events around the launches)", "kernel_ms": kernel_ms,
         "algorithmic_flops_per_eval": MIX_FLOPS,
         "hbm_gbs_algorithmic": (Cn / 512) * 24.125 * n / (kernel_ms * 1e-3) / 1e9,
         "hbm_peak_gbs": peaks.get("hbm_gbs"),
@@ -364,8 +364,9 @@ def main():
                    "points_per_gpu": n, "candidates": Cn, "parallelism": f"point-range shards x{world}, "
                    "int32 count all-reduce (NCCL)" if world > 1 else "single GPU",
                    "l2": "inputs (403 MB of points per pass) exceed the 126 MB L2; no flush needed"},
-        # per step: compile_kernel, 4 x score_kernel, fixup_scan_kernel, fixup_pair_kernel, select_counts_kernel
-        "e2e": e2e, "gpu_launches": 8 * args.steps, "clocks": clocks, "roofline": roofline,
+        # per step: compile_kernel, 5 x score_kernel (plane, sphere, cylinder, cone, wide cone), fixup_scan_kernel,
+        # fixup_pair_kernel, select_counts_kernel
+        "e2e": e2e, "gpu_launches": 9 * args.steps, "clocks": clocks, "roofline": roofline,
         "fp64_guard_pairs_per_step": int(guard),
     }
     # K4 (refit over the whole shard, HBM bound): mask kernel time -> GB/s of algorithmic bytes
