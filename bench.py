@@ -87,9 +87,18 @@ class ClockSampler:
             import pynvml as nv
 
             nv.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+            ent = vis[self.index] if self.index < len(vis) else str(self.index)
+            if ent.isdigit():
+                h = nv.nvmlDeviceGetHandleByIndex(int(ent))
+            elif ent.startswith("GPU-"):
+                h = nv.nvmlDeviceGetHandleByUUID(ent)
+            else:  # by PCI bus id of the CUDA device, robust against any other enumeration
+                import torch
+
+                bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+                h = nv.nvmlDeviceGetHandleByIndex(next(i for i in range(nv.nvmlDeviceGetCount())
+                                                       if nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(i)).bus == bus))
             self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             self.source = "nvml, 10 ms period"
             self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
