@@ -65,6 +65,7 @@ class ClockSampler:
         self._stop = threading.Event()
         self.t = None
         self.source = None
+        self.period = float(os.environ.get("BENCH_CLOCK_PERIOD_MS", "10")) / 1e3
 
     def _nvml_loop(self, nv, h):
         while not self._stop.is_set():
@@ -80,9 +81,11 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(self.period)
 
     def start(self):
+        if self.period <= 0:
+            return
         try:
             import pynvml as nv
 
@@ -100,7 +103,7 @@ class ClockSampler:
                 h = nv.nvmlDeviceGetHandleByIndex(next(i for i in range(nv.nvmlDeviceGetCount())
                                                        if nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(i)).bus == bus))
             self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            self.source = "nvml, 10 ms period"
+            self.source = f"nvml, {self.period * 1e3:.0f} ms period"
             self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
             self.t.start()
             return
