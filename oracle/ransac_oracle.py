@@ -443,7 +443,8 @@ def project2cone(sh: Shape, pts):
         # rodriguesrad(rot_ax, -opang/2): utilities.jl:61-64 -> :19-24 -> :32-43
         nv = normalize3(rot_ax)
         th = -opang / 2
-        ct, st = math.cos(th), math.sin(th)
+        # (Julia's cos(Inf) throws a DomainError; a non-finite opening angle is treated as NaN = matches nothing)
+        ct, st = float(np.cos(th)), float(np.sin(th))
         eye = np.eye(3)
         outer = nv[:, :, None] * nv[:, None, :]
         R = outer + ct * (eye[None] - outer)

@@ -41,3 +41,43 @@ def near_threshold_report(sh, pts, nrm, params, idx):
     eps, cosa = params[name]["eps"], math.cos(params[name]["alpha"])
     m = M.margin64(c.type, bool(c.outwards), list(c.p), np.asarray(pts)[idx], np.asarray(nrm)[idx], eps, cosa)
     return np.abs(m) / max(eps, 1e-300)
+
+
+def adversarial_case(seed: int = 12345, n: int = 4000):
+    """Oracle shapes + float64 points/normals that stress the scorers: every shape type, wide/flat
+    cones, non-unit axes and normals, huge and tiny radii, points on axes / at centres, zero normals,
+    NaN / Inf / zero-axis candidates.  Coordinates are float32-representable (the device stores float32)."""
+    import math
+
+    rng = np.random.default_rng(seed)
+    P = rng.normal(size=(n, 3)) * rng.choice([0.1, 1.0, 30.0], size=(n, 1))
+    N = rng.normal(size=(n, 3))
+    N /= np.linalg.norm(N, axis=1, keepdims=True)
+    N[:50] *= rng.uniform(0.2, 3.0, (50, 1))  # non-unit normals (Q15)
+    N[50:60] = 0.0                            # zero normals
+    shapes = []
+    for i in range(160):
+        kind = i % 4
+        a = rng.normal(size=3)
+        if i % 5:
+            a /= np.linalg.norm(a)            # otherwise a non-unit axis / plane normal (Q18)
+        q = P[rng.integers(n)] + rng.normal(size=3) * rng.choice([0.0, 0.05, 1.0])
+        outw = bool(rng.integers(2))
+        if kind == 0:
+            p7 = [*q, *a, 0.0]
+        elif kind == 1:
+            p7 = [*q, float(rng.choice([1e-3, 0.5, 3.0, 200.0])), 0, 0, 0]
+        elif kind == 2:
+            p7 = [*a, *q, float(rng.choice([1e-3, 0.5, 3.0, 200.0]))]
+        else:
+            p7 = [*q, *a, math.radians(float(rng.choice([1.0, 20.0, 90.0, 121.0, 179.0, 180.0, 200.0, 355.0])))]
+        shapes.append(O.shape_from_params7(kind, outw, p7))
+    # points exactly at a centre / on an axis (Q17), candidates with NaN / Inf parameters
+    P[100] = shapes[1].params7()[0:3]
+    P[101] = np.asarray(shapes[3].params7()[0:3]) + 2.0 * np.asarray(shapes[3].params7()[3:6])
+    shapes.append(O.shape_from_params7(1, True, [np.nan, 0, 0, 1.0, 0, 0, 0]))
+    shapes.append(O.shape_from_params7(3, True, [0, 0, 0, 0, 0, 1.0, np.inf]))
+    shapes.append(O.shape_from_params7(2, False, [0, 0, 0, 1.0, 2.0, 3.0, 1.0]))  # zero axis
+    P = P.astype(np.float32).astype(np.float64)
+    N = N.astype(np.float32).astype(np.float64)
+    return shapes, P, N

@@ -83,3 +83,21 @@ def test_known_answers_through_c():
     pl = O.ransacparameters(O.default_parameters([O.PLANE]), plane={"alpha": math.pi / 2})
     for tv in (tv1, tv2, tv3):
         assert len(CO.fit_points(tv[None], tn[None], pl)[0]) == 0
+
+
+def test_random_and_degenerate_candidates_agree_between_the_two_oracles():
+    """adversarial inputs: random shapes of every type (wide/flat cones, non-unit axes and normals,
+    huge and tiny radii), points on axes / at centres / with zero normals, NaN parameters -- the two
+    independent restatements (NumPy, C) must still give the same masks"""
+    from tests.helpers import adversarial_case
+
+    shapes, P, N = adversarial_case()
+    op = O.default_parameters()
+    counts, _, masks = CO.score_counts(shapes, P, N, op, want_masks=True)
+    nonzero = 0
+    for i, sh in enumerate(shapes):
+        with np.errstate(all="ignore"):
+            want = O.compatibles(sh, P, N, op)
+        assert np.array_equal(masks[i], want), (i, sh.kind, int(want.sum()), int(masks[i].sum()))
+        nonzero += int(want.any())
+    assert nonzero > 20

@@ -303,3 +303,30 @@ def test_score_dev_masks_device_pointers(R):
         counts, masks = R.score_counts(pc, cands, subset, params, want_masks=True)  # host-buffer path
         np.testing.assert_array_equal(d_counts.cpu().numpy(), counts)
         np.testing.assert_array_equal(d_masks.cpu().numpy().view(np.uint32), np.asarray(masks).reshape(len(cands), words))
+
+
+def test_adversarial_candidates_match_oracle(R):
+    """tests.helpers.adversarial_case: every shape type with wide/flat cones, non-unit axes/normals, tiny and
+    huge radii, points on axes and at centres, zero normals, NaN/Inf/zero-axis candidates -- counts, masks
+    and refit lists must be the oracle's, bit for bit"""
+    from ransac_jl_b200 import _lib
+    from ransac_jl_b200.shapes import from_cand
+    from tests.helpers import adversarial_case
+
+    oshapes, P, N = adversarial_case()
+    cands = []
+    for sh in oshapes:
+        c = _lib.rsc_cand(type=int(sh.kind), outwards=int(bool(sh.outwards)))
+        for i, v in enumerate(sh.params7()):
+            c.p[i] = float(v)
+        cands.append(from_cand(c))
+    pc = R.RANSACCloud(P.astype(np.float32), N.astype(np.float32), 1)
+    params = R.ransacparameters()
+    op = oracle_params(params)
+    counts, masks = R.score_counts(pc, cands, -1, params, want_masks=True)
+    want, _, wmask = CO.score_counts(oshapes, P, N, op, want_masks=True)
+    np.testing.assert_array_equal(counts, want)
+    for i in range(len(cands)):
+        np.testing.assert_array_equal(R.unpack_mask(masks[i], pc.size), wmask[i], err_msg=f"candidate {i} kind {oshapes[i].kind}")
+    for i in range(0, len(cands), 7):
+        np.testing.assert_array_equal(R.refit(cands[i], pc, params).inpoints, np.flatnonzero(wmask[i]))
