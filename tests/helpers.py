@@ -81,3 +81,47 @@ def adversarial_case(seed: int = 12345, n: int = 4000):
     P = P.astype(np.float32).astype(np.float64)
     N = N.astype(np.float32).astype(np.float64)
     return shapes, P, N
+
+
+def degenerate_sets(seed: int = 777):
+    """Minimal sets (S, 3, 3) points + normals that stress the fits: collinear points (Q3), coincident
+    points, parallel / anti-parallel / zero normals, near-singular normal triples for the cone's rank
+    test, tiny and huge scales, plus ordinary sets from a sphere, a cylinder and a cone for contrast."""
+    rng = np.random.default_rng(seed)
+    Ps, Ns = [], []
+
+    def add(p, n):
+        Ps.append(np.asarray(p, float)), Ns.append(np.asarray(n, float))
+
+    e = np.eye(3)
+    for s in (1e-3, 1.0, 1e3):
+        add([[0, 0, 0], [s, 0, 0], [2 * s, 0, 0]], [e[2], e[2], e[2]])                # collinear, equal normals
+        add([[0, 0, 0], [0, 0, 0], [s, s, 0]], [e[2], e[2], e[2]])                    # coincident points
+        add([[0, 0, 0], [s, 0, 0], [0, s, 0]], [e[2], e[2], e[2]])                    # a clean plane
+        add([[0, 0, 0], [s, 0, 0], [0, s, 0]], [e[2], -e[2], e[2]])                   # anti-parallel normal
+        add([[0, 0, 0], [s, 0, 0], [0, s, 0]], [e[2], e[2], [0, 0, 0]])               # zero normal
+        add([[s, 0, 0], [0, s, 0], [0, 0, s]], [e[0], e[1], e[2]])                    # sphere of radius s
+        add([[s, 0, 0], [0, s, 0], [0, 0, s]], [-e[0], -e[1], -e[2]])                 # ... inward
+        add([[s, 0, 0], [0, s, 0], [-s, 0, 5 * s]], [e[0], e[1], -e[0]])              # cylinder around z
+        add([[s, 0, 0], [0, s, 0], [-s, 0, 5 * s]], [2 * e[0], 0.5 * e[1], -3 * e[0]])  # ... raw normals (Q8)
+    for _ in range(40):  # cones: apex at a random place, random half angle, points on the surface
+        apex, ax = rng.normal(size=3) * 5, rng.normal(size=3)
+        ax /= np.linalg.norm(ax)
+        half = rng.uniform(0.05, 1.4)
+        u = np.cross(ax, rng.normal(size=3)); u /= np.linalg.norm(u)
+        v = np.cross(ax, u)
+        p, n = [], []
+        for _k in range(3):
+            t, ph = rng.uniform(0.5, 5.0), rng.uniform(0, 2 * np.pi)
+            rad = np.cos(ph) * u + np.sin(ph) * v
+            p.append(apex + t * (np.cos(half) * ax + np.sin(half) * rad))
+            n.append(np.cos(half) * rad - np.sin(half) * ax)
+        add(p, n)
+    for _ in range(40):  # nearly coplanar normals: the cone's rank(r) == 3 decision sits near its tolerance
+        a, b = rng.normal(size=3), rng.normal(size=3)
+        a /= np.linalg.norm(a); b /= np.linalg.norm(b)
+        c = 0.6 * a + 0.4 * b + rng.normal(size=3) * float(rng.choice([0.0, 1e-17, 1e-15, 1e-12, 1e-8, 1e-3]))
+        add(rng.normal(size=(3, 3)) * 3, [a, b, c])
+    for _ in range(60):  # random sets
+        add(rng.normal(size=(3, 3)) * 10, rng.normal(size=(3, 3)))
+    return np.stack(Ps), np.stack(Ns)

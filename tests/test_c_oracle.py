@@ -101,3 +101,22 @@ def test_random_and_degenerate_candidates_agree_between_the_two_oracles():
         assert np.array_equal(masks[i], want), (i, sh.kind, int(want.sum()), int(masks[i].sum()))
         nonzero += int(want.any())
     assert nonzero > 20
+
+
+def test_degenerate_minimal_sets_agree_between_the_two_oracles():
+    """collinear / coincident points, parallel, anti-parallel and zero normals, near-singular cone normal
+    triples (rank() decisions at their tolerance), scales 1e-3..1e3: same accept/reject, same parameters"""
+    from tests.helpers import degenerate_sets
+
+    P, N = degenerate_sets()
+    op = O.default_parameters()
+    got, gset = CO.fit_points(P, N, op)
+    want = []
+    with np.errstate(all="ignore"):
+        for s in range(len(P)):
+            want += [(s, sh) for sh in O.forcefit(P[s], N[s], op)]
+    assert [(int(s), t) for (t, _, _), s in zip(got, gset)] == [(s, sh.kind) for s, sh in want]
+    assert len(want) > 40
+    for (t, outw, p), (_, sh) in zip(got, want):
+        assert t == 0 or bool(outw) == bool(sh.outwards)
+        np.testing.assert_allclose(np.asarray(p)[:7], sh.params7(), rtol=1e-9, atol=1e-9 * max(1.0, np.abs(sh.params7()).max()))

@@ -158,3 +158,22 @@ def test_sampler_too_few_enabled(R):
     pc.isenabled = en
     shapes, sets, idx = R.sample_fit(pc, R.ransacparameters(), 1, 0, 64)
     assert len(shapes) == 0 and (idx == -1).all()
+
+
+def test_degenerate_minimal_sets_match_oracle(R):
+    """tests.helpers.degenerate_sets through rsc_fit_points: collinear / coincident points, parallel and zero
+    normals, near-singular cone normal triples (the rank shortcut must agree with the SVD), three scales"""
+    from oracle import c_oracle as CO
+    from tests.helpers import degenerate_sets, oracle_params
+
+    P, N = degenerate_sets()
+    params = R.ransacparameters()
+    pc = R.RANSACCloud(np.zeros((4, 3), np.float32), np.ones((4, 3), np.float32), 1)
+    shapes, sets = R.fit_points(pc, P, N, params)
+    want, wset = CO.fit_points(P, N, oracle_params(params))
+    assert [(int(s), sh.to_cand().type) for s, sh in zip(sets, shapes)] == [(int(s), t) for (t, _, _), s in zip(want, wset)]
+    for sh, (t, outw, p) in zip(shapes, want):
+        c = sh.to_cand()
+        assert t == 0 or bool(c.outwards) == bool(outw)
+        p = np.asarray(p)[:7]
+        np.testing.assert_allclose(np.array(c.p[:7]), p, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(p).max()))
