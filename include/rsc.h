@@ -133,7 +133,8 @@ int32_t rsc_cloud_create_f64(rsc_ctx* ctx, const double* xyz, const double* nrm,
 int32_t rsc_cloud_create_shard(rsc_ctx* ctx, const float* xyz, const float* nrm, int64_t n,
                                int64_t global_offset, int64_t n_global, rsc_cloud** out);
 /* Re-upload new coordinates (same n) into the device buffers of an existing cloud: all points
- * enabled again, subset copies re-gathered.  A re-scan of the same scene, no re-allocation. */
+ * enabled again, subset copies re-gathered, the flattened octree (rsc_cloud_build_cells) dropped.
+ * A re-scan of the same scene, no re-allocation. */
 int32_t rsc_cloud_update(rsc_cloud* cloud, const float* xyz, const float* nrm, int64_t n);
 void rsc_cloud_destroy(rsc_cloud* cloud);
 int64_t rsc_cloud_size(const rsc_cloud* cloud);
