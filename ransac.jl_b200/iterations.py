@@ -103,7 +103,7 @@ def _ransac_host(pc, params, seed):
                         cands.extend(f if isinstance(f, (list, tuple)) else [f])
         cc[1] += len(cands)
         b = [c for c in cands if type(c) in SHAPE_KIND]
-        res = dict(zip(map(id, b), scorecandidates(pc, b, 0, params))) if b else {}
+        res = dict(zip(map(id, b), scorecandidates(pc, b, 0, bparams))) if b else {}
         for c in cands:
             sc, ip = res[id(c)] if id(c) in res else c.scorecandidate(pc, 0, params)
             scored.recordscore(c, sc, ip)
@@ -114,7 +114,7 @@ def _ransac_host(pc, params, seed):
             scr = scored.scores[best].E
             if prob(scr, cc[sidx[it["extract_s"]]], pc.size, drawN) > prob_det:
                 shp = scored.shapes[best]
-                ex = refit(shp, pc, params, disable=True) if type(shp) in SHAPE_KIND else shp.refit(pc, params)
+                ex = refit(shp, pc, bparams, disable=True) if type(shp) in SHAPE_KIND else shp.refit(pc, params)
                 if type(shp) not in SHAPE_KIND:
                     from .fitting import invalidate_indexes
                     invalidate_indexes(pc, ex.inpoints)

@@ -25,7 +25,12 @@ def defaultshapeparameters(shape_type) -> dict:
         return {"cylinder": {"eps": 0.3, "alpha": math.radians(5)}}
     if shape_type is FittedCone:
         return {"cone": {"eps": 0.3, "alpha": math.radians(5), "minconeopang": math.radians(2)}}
-    raise TypeError(f"no default parameters for {shape_type!r}")
+    # user-defined shapes bring their own method, like `defaultshapeparameters(::Type{MyShape})` in the
+    # reference (docs/src/newprimitive.md:12-18, fitting.jl:15)
+    own = getattr(shape_type, "defaultshapeparameters", None)
+    if callable(own):
+        return dict(own())
+    raise TypeError(f"no default parameters for {shape_type!r}: define a static `defaultshapeparameters()` on the class")
 
 
 def defaultiterationparameters(shape_types) -> dict:
