@@ -587,6 +587,49 @@ def estimatescore(S1length: int, Plength: int, sigma: int) -> ConfidenceInterval
     return notsoconfident(-1 - gmin, -1 - gmax)
 
 
+def estimatescore_f64(Slength: int, Plength: int, sigma: int) -> ConfidenceInterval:
+    """confidenceintervals.jl:53-74 with the products taken in float64, left to right (no Int64 wrap, Q9):
+    the interval the formula means.  Used by progressive scoring, whose decisions read
+    min/max; the reference's loop only ever reads E, which the wrap does not touch."""
+    Np, x, n = float(-2 - Slength), float(-2 - Plength), float(-1 - sigma)
+    sq_ = ((x * n) * (Np - x)) * (Np - n) / (Np - 1.0)
+    sq = 0.0 if sq_ < 0 else math.sqrt(sq_)
+    return notsoconfident(-1 - (x * n + sq) / Np, -1 - (x * n - sq) / Np)
+
+
+def refine_progressive(pc: "Cloud", params, shapes, scores, evaluated, trace=None) -> None:
+    """Progressive subset scoring (iterations.jl:110 "TODO: refine if best.overlap",
+    docs/src/ransac.md:137-141, Schnabel et al. 2007 sec. 4.5.1).  `evaluated[i] = [j, sigma, M]`:
+    candidate i has been scored on subsets 1..j, with sigma compatible points among their M points.
+    While the interval of the best candidate (largest E, first wins) overlaps another one (isoverlap,
+    confidenceintervals.jl:29-36), the least-evaluated candidates among the best and its overlappers are
+    scored on their next subset and their interval is re-estimated from the union (sigma, M summed).
+    Stops when the best stands alone or those candidates have used every subset."""
+    r = len(pc.subsets)
+    while len(shapes) > 1:
+        best, overlap = findhighestscore(scores)
+        if not overlap:
+            return
+        group = [i for i in range(len(scores)) if i == best or isoverlap(scores[i], scores[best])]
+        lmin = min(evaluated[i][0] for i in group)
+        if lmin >= r:
+            return
+        for i in group:
+            if evaluated[i][0] != lmin:
+                continue
+            sub = pc.subsets[lmin]  # 0-based id of subset lmin+1
+            cp = compatibles(shapes[i], pc.vertices[sub], pc.normals[sub], params)
+            if shapes[i].kind != SPHERE:  # same per-type policy as scorecandidate (Q4)
+                cp = cp & pc.isenabled[sub]
+            evaluated[i][0] += 1
+            evaluated[i][1] += int(cp.sum())
+            evaluated[i][2] += len(sub)
+            scores[i] = estimatescore_f64(evaluated[i][2], pc.size, evaluated[i][1])
+            if trace is not None:
+                trace.evals += len(sub)
+                trace.refined += 1
+
+
 def prob(n, s, N, k):
     """utilities.jl:262."""
     return 1 - (1 - (n / N) ** k) ** s
@@ -869,6 +912,7 @@ class RansacTrace:
     evals: int = 0
     extracted_at: List[int] = field(default_factory=list)
     levelweight: Optional[np.ndarray] = None
+    refined: int = 0  # progressive scoring: (candidate, subset) evaluations beyond subset 1
 
 
 def forcefit(p, n, params) -> List[Shape]:
@@ -889,8 +933,12 @@ def ransac(
     minimal_sets: Optional[Callable[[int, int], Optional[np.ndarray]]] = None,
     trace: Optional[RansacTrace] = None,
     octree: Optional[MortonOctree] = None,
+    progressive: bool = False,
 ) -> List[Extracted]:
     """iterations.jl:14-21 + :35-162.
+
+    `progressive=True` (extension) refines overlapping scores on further subsets before
+    the extraction test (refine_progressive); intervals are then the float64 ones (estimatescore_f64).
 
     `minimal_sets(k, i)` may supply the index triple of minimal set i of iteration k (or None
     for a failed sample); by default the Philox sampler above is used with set_id =
@@ -905,6 +953,7 @@ def ransac(
     shapes: List[Shape] = []
     scores: List[ConfidenceInterval] = []
     inpts: List[np.ndarray] = []
+    evaluated: List[list] = []  # progressive scoring state per stored candidate
     extracted: List[Extracted] = []
     cc = [0, 0, 0]
     tr = trace if trace is not None else RansacTrace()
@@ -944,9 +993,12 @@ def ransac(
         lv_s = np.zeros_like(lv_n)
         for ci, c in enumerate(cands):  # scorecandidates! (fitting.jl:181-190), subset 1 only (Q10)
             sc, ip = scorecandidate(pc, c, 0, params)
+            if progressive:
+                sc = estimatescore_f64(len(pc.subsets[0]), pc.size, len(ip))
             shapes.append(c)
             scores.append(sc)
             inpts.append(ip)
+            evaluated.append([1, len(ip), len(pc.subsets[0])])
             tr.candidates_scored += 1
             tr.evals += len(pc.subsets[0])
             if octree is not None:
@@ -963,6 +1015,8 @@ def ransac(
         tr.sets_drawn = cc[2]
         cc[0] = len(shapes)
         if len(shapes) >= 1:
+            if progressive:
+                refine_progressive(pc, params, shapes, scores, evaluated, tr)
             best, _ = findhighestscore(scores)
             scr = scores[best].E
             s = cc[sidx[it["extract_s"]]]
@@ -972,11 +1026,12 @@ def ransac(
                 pc.isenabled[ip] = False
                 extracted.append(Extracted(shapes[best], ip))
                 tr.extracted_at.append(k)
-                del shapes[best], scores[best], inpts[best]
+                del shapes[best], scores[best], inpts[best], evaluated[best]
                 keep = [j for j in range(len(shapes)) if pc.isenabled[inpts[j]].all()]
                 shapes = [shapes[j] for j in keep]
                 scores = [scores[j] for j in keep]
                 inpts = [inpts[j] for j in keep]
+                evaluated = [evaluated[j] for j in keep]
         if octree is not None:
             levelweight = updatelevelweight(levelweight, levelscore)  # iterations.jl:148
             tr.levelweight = levelweight.copy()

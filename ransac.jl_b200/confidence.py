@@ -58,6 +58,18 @@ def estimatescore(S1length: int, Plength: int, sigmaS1: int) -> ConfidenceInterv
     return ci
 
 
+def estimatescore_f64(Slength: int, Plength: int, sigma: int) -> ConfidenceInterval:
+    """The interval confidenceintervals.jl:53-74 means: products in float64, left to right, without the
+    reference's Int64 wrap-around (Q9).  Progressive scoring decides on min/max, which the
+    wrap corrupts for N >~ 1e6; the reference's own loop only reads E, which it does not."""
+    import math
+
+    Np, x, n = float(-2 - Slength), float(-2 - Plength), float(-1 - sigma)
+    sq_ = ((x * n) * (Np - x)) * (Np - n) / (Np - 1.0)
+    sq = 0.0 if sq_ < 0 else math.sqrt(sq_)
+    return notsoconfident(-1 - (x * n + sq) / Np, -1 - (x * n - sq) / Np)
+
+
 def prob(n, s, N, k):
     """utilities.jl:262."""
     return 1 - (1 - (n / N) ** k) ** s

@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib
 from ._lib import lib
 from .cloud import RANSACCloud
-from .confidence import ConfidenceInterval, estimatescore, isoverlap
+from .confidence import ConfidenceInterval, estimatescore, estimatescore_f64, isoverlap
 from .params import to_c
 from .shapes import SHAPE_KIND, ExtractedShape, FittedShape, from_cand, pack_cands
 
@@ -151,21 +151,52 @@ class IterationCandidates:
         self.shapes: List[FittedShape] = []
         self.scores: List[ConfidenceInterval] = []
         self.inpoints: List[np.ndarray] = []
+        # progressive scoring (extension): [subsets evaluated, compatible points among them, their size]
+        self.evaluated: List[list] = []
 
     def __len__(self):
         return len(self.shapes)
 
-    def recordscore(self, shape, score, inpoints):
+    def recordscore(self, shape, score, inpoints, subset_size: int = -1):
         self.shapes.append(shape)
         self.scores.append(score)
         self.inpoints.append(inpoints)
+        self.evaluated.append([1, len(inpoints), subset_size])
         return self
 
     def deleteat(self, arg):
         idx = sorted([arg] if np.isscalar(arg) else list(arg), reverse=True)
         for i in idx:
-            del self.shapes[i], self.scores[i], self.inpoints[i]
+            del self.shapes[i], self.scores[i], self.inpoints[i], self.evaluated[i]
         return self
+
+
+def refine_progressive(pc: RANSACCloud, A: IterationCandidates, params) -> int:
+    """Progressive subset scoring -- what iterations.jl:110 leaves as "TODO: refine if best.overlap"
+    (docs/src/ransac.md:137-141; Schnabel et al. 2007, sec. 4.5.1).  While the interval of the best
+    candidate overlaps another one (`isoverlap`), the least-evaluated candidates among the best and its
+    overlappers are scored on their next subset -- one `rsc_score` launch per round, counts only -- and
+    re-estimated from the union of the subsets seen so far.  Returns the number
+    of (candidate, subset) evaluations made."""
+    r, done = len(pc.subsets), 0
+    while len(A) > 1:
+        best, overlap = findhighestscore(A)
+        if not overlap:
+            break
+        group = [i for i in range(len(A)) if i == best or isoverlap(A.scores[i], A.scores[best])]
+        lmin = min(A.evaluated[i][0] for i in group)
+        if lmin >= r:
+            break
+        todo = [i for i in group if A.evaluated[i][0] == lmin]
+        dev = [i for i in todo if type(A.shapes[i]) in SHAPE_KIND]
+        counts = dict(zip(dev, score_counts(pc, [A.shapes[i] for i in dev], lmin, params)[0])) if dev else {}
+        for i in todo:  # user-defined shapes score themselves (docs/src/newprimitive.md:16)
+            c = counts[i] if i in counts else len(A.shapes[i].scorecandidate(pc, lmin, params)[1])
+            ev = A.evaluated[i]
+            ev[0], ev[1], ev[2] = ev[0] + 1, ev[1] + int(c), ev[2] + len(pc.subsets[lmin])
+            A.scores[i] = estimatescore_f64(ev[2], pc.size, ev[1])
+        done += len(todo)
+    return done
 
 
 def findhighestscore(A: IterationCandidates):

@@ -16,8 +16,8 @@ import numpy as np
 from . import _lib
 from ._lib import lib
 from .cloud import RANSACCloud
-from .confidence import prob
-from .fitting import IterationCandidates, findhighestscore, refit, sample_fit, scorecandidates
+from .confidence import estimatescore_f64, prob
+from .fitting import IterationCandidates, findhighestscore, refine_progressive, refit, sample_fit, scorecandidates
 from .params import to_c
 from .shapes import SHAPE_KIND, ExtractedShape, from_cand
 
@@ -27,23 +27,26 @@ def _all_builtin(params) -> bool:
 
 
 def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = False, seed: int = 1234,
-           sampler: str = "root") -> Tuple[List[ExtractedShape], float]:
+           sampler: str = "root", progressive: bool = False) -> Tuple[List[ExtractedShape], float]:
     """Run efficient RANSAC on `pc`; returns (extracted shapes, seconds).
 
     `reset_rand=True` pins the sampler seed to 1234 like `Random.seed!(1234)` (iterations.jl:36);
     the Philox stream is of course not Julia's.  `sampler="octree"` (extension, needs
     `pc.build_cells()`) draws the minimal sets from level-weighted octree cells -- what the reference
     is written for -- instead of from the root cell, which is what its shipped code does (Q1); the
-    final level weights are left in `pc.levelweight`."""
+    final level weights are left in `pc.levelweight`.  `progressive=True` (extension) refines
+    overlapping scores on further subsets before each extraction test (`fitting.refine_progressive`,
+    the reference's "TODO: refine if best.overlap", iterations.jl:110); it runs the host loop over the
+    per-call C ABI and leaves the number of extra (candidate, subset) evaluations in `pc.last_refined`."""
     if setenabled:
         pc.enable_all()
     if reset_rand:
         seed = 1234
-    if _all_builtin(params):
+    if _all_builtin(params) and not progressive:
         return _ransac_device(pc, params, seed, sampler)
     if sampler != "root":
-        raise ValueError("the octree sampler is only available for the built-in shape types (device loop)")
-    return _ransac_host(pc, params, seed)
+        raise ValueError("the octree sampler is only available in the device loop (built-in shape types, not progressive)")
+    return _ransac_host(pc, params, seed, progressive)
 
 
 def _ransac_device(pc, params, seed, sampler="root"):
@@ -75,8 +78,9 @@ def _ransac_device(pc, params, seed, sampler="root"):
     return out, int(secs * 100) / 100.0
 
 
-def _ransac_host(pc, params, seed):
-    """iterations.jl:35-162 on the host, for parameter sets with user-defined shapes."""
+def _ransac_host(pc, params, seed, progressive=False):
+    """iterations.jl:35-162 on the host, for parameter sets with user-defined shapes and for
+    progressive scoring."""
     it = params["iteration"]
     drawN, minsubsetN, prob_det, tau = it["drawN"], it["minsubsetN"], it["prob_det"], it["tau"]
     sidx = {"lengthC": 0, "allcand": 1, "nofminset": 2}
@@ -87,6 +91,8 @@ def _ransac_host(pc, params, seed):
     scored = IterationCandidates()
     extracted: List[ExtractedShape] = []
     cc = [0, 0, 0]
+    M1 = len(pc.subsets[0])
+    pc.last_refined = 0
     for k in range(1, it["itermax"] + 1):
         if pc.count_enabled() < tau:
             break
@@ -106,10 +112,14 @@ def _ransac_host(pc, params, seed):
         res = dict(zip(map(id, b), scorecandidates(pc, b, 0, bparams))) if b else {}
         for c in cands:
             sc, ip = res[id(c)] if id(c) in res else c.scorecandidate(pc, 0, params)
-            scored.recordscore(c, sc, ip)
+            if progressive:
+                sc = estimatescore_f64(M1, pc.size, len(ip))
+            scored.recordscore(c, sc, ip, M1)
         cc[2] = k * minsubsetN
         cc[0] = len(scored)
         if len(scored) >= 1:
+            if progressive:
+                pc.last_refined += refine_progressive(pc, scored, bparams)
             best, _ = findhighestscore(scored)
             scr = scored.scores[best].E
             if prob(scr, cc[sidx[it["extract_s"]]], pc.size, drawN) > prob_det:
