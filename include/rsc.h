@@ -52,6 +52,10 @@ extern "C" {
  * is what its shipped code always does (Q1: levelweight/levelscore swapped, octree.jl:82-84).
  * Needs rsc_cloud_build_cells. */
 #define RSC_SAMPLER_OCTREE 2u
+/* extension switch (off by default): rsc_ransac_run refits the best candidate by least squares to the
+ * compatible points within 3 eps (rsc_refit_lsq) before it extracts it -- the paper's refit, which the
+ * reference leaves out (docs/src/ransac.md:163-169). */
+#define RSC_REFIT_LSQ 8u
 
 /* which counter plays `s` in prob(n,s,N,k): utilities.jl:297-300 */
 #define RSC_S_LENGTHC 0
@@ -127,7 +131,12 @@ int32_t rsc_ctx_last_kernel(rsc_ctx* ctx, double* kernel_ms, int64_t* guard_pair
 /* ---- cloud: RANSACCloud (octree.jl:37-59, ctors :78-138) ------------------------------ */
 /* xyz/nrm are AoS (N x 3), bit-compatible with Vector{SVector{3,Float32}}; stored on device as
  * SoA float32.  `_f64` down-converts Vector{SVector{3,Float64}}.  `_shard` uploads the point range
- * [global_offset, global_offset+n) of a cloud of n_global points (one shard per GPU/process). */
+ * [global_offset, global_offset+n) of a cloud of n_global points (one shard per GPU/process).
+ * The upload is enqueued in 2 Mi-point chunks and the call returns; the next call on the cloud waits
+ * for it (rsc_score on the whole cloud even follows it chunk by chunk).  From pageable arrays (a
+ * Julia Vector, a NumPy array) CUDA has staged the data when the call returns and the host arrays
+ * are not needed any more; PAGE-LOCKED arrays are read by DMA after the return and must stay valid
+ * and unchanged until the next call on this cloud has returned. */
 int32_t rsc_cloud_create(rsc_ctx* ctx, const float* xyz, const float* nrm, int64_t n, rsc_cloud** out);
 int32_t rsc_cloud_create_f64(rsc_ctx* ctx, const double* xyz, const double* nrm, int64_t n, rsc_cloud** out);
 int32_t rsc_cloud_create_shard(rsc_ctx* ctx, const float* xyz, const float* nrm, int64_t n,
@@ -193,6 +202,17 @@ int32_t rsc_sample_fit(rsc_cloud* cloud, const rsc_params* params, uint64_t seed
  * enabled bits (and those of the uploaded subsets). */
 int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand,
                           int64_t* out_idx, int64_t* out_n, int32_t disable);
+/* Extension (the reference's refit keeps the candidate unchanged, docs/src/ransac.md:
+ * 163-169): least-squares refit of `cand` to the enabled points compatible with it inside band * eps
+ * (the paper uses band = 3).  The point set is selected once, with the exact float64 decisions of
+ * rsc_refit_extract; planes get the total-least-squares plane, the other shapes a Levenberg-Marquardt
+ * minimisation of the squared point-to-surface distances (normal equations accumulated on the device
+ * in float64, one streaming pass per step).  *out = refined shape (= *cand if fewer than 2 x #parameters
+ * points are selected or the minimisation fails), *n_used = selected points, *rms = root mean square
+ * distance after the refit (NaN if unchanged); n_used and rms may be NULL.  Nothing is disabled:
+ * call rsc_refit_extract with *out afterwards. */
+int32_t rsc_refit_lsq(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand, double band,
+                      rsc_cand* out, int64_t* n_used, double* rms);
 
 /* ---- point-range sharding over the GPUs of one box (one process per GPU) ---------------------- */
 /* Every rank holds the whole cloud (sampling needs random access) but scores/refits only its range

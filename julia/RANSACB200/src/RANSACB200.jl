@@ -158,6 +158,23 @@ function refit_extract!(dc::DeviceCloud, s::FittedShape, params; disable::Bool=t
     ExtractedShape(s, out .+ 1)
 end
 
+"""
+Extension: least-squares refit of `s` to the enabled points compatible with it inside `band` * eps (the
+paper's refit, which RANSAC.jl leaves out: docs/src/ransac.md:163-169).  Returns
+`(refined shape, points used, rms distance)`; follow it with `refit_extract!`.
+"""
+function refit_lsq(dc::DeviceCloud, s::FittedShape, params; band::Float64=3.0)
+    prm = Ref(toparams(params))
+    cand = Ref(tocand(s))
+    out = Ref(tocand(s))
+    n = Ref{Int64}(0)
+    rms = Ref{Float64}(NaN)
+    check(ccall((:rsc_refit_lsq, LIB[]), Int32,
+                (Ptr{Cvoid}, Ref{RscParams}, Ref{RscCand}, Float64, Ref{RscCand}, Ref{Int64}, Ref{Float64}),
+                dc.h, prm, cand, band, out, n, rms))
+    fromcand(out[]), n[], rms[]
+end
+
 "`forcefitshapes!` for S minimal sets given as a 3 x S matrix of (1-based) point indices."
 function fit_batch(dc::DeviceCloud, idx::Matrix{Int}, params)
     S = size(idx, 2)

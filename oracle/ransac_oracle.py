@@ -699,6 +699,195 @@ def findhighestscore(scores: Sequence[ConfidenceInterval]) -> Tuple[int, bool]:
 
 
 # --------------------------------------------------------------------------------------
+# least-squares refit (extension).  The reference's refit keeps the candidate as it
+# is ("In our implementation least-square fitting is not used", docs/src/ransac.md:163-169); the
+# paper refits it to all compatible points within 3 eps before the extraction.  Definition shared
+# with the CUDA library (rsc_lsq.cu): the point set is selected ONCE with the candidate
+# (compatibles* with eps scaled by `band`, enabled points only); planes get the total-least-squares
+# plane of that set (centroid + smallest-eigenvalue direction of the scatter matrix), the other
+# shapes a Levenberg-Marquardt minimisation of the sum of squared point-to-surface distances.
+# --------------------------------------------------------------------------------------
+
+LSQ_NPAR = {PLANE: 3, SPHERE: 4, CYLINDER: 7, CONE: 7}
+LSQ_MAXIT = 12
+LSQ_REL = 1e-12
+
+
+def lsq_pack(sh: Shape) -> np.ndarray:
+    if sh.kind == PLANE:
+        return np.array([*sh.a, *sh.b], F)
+    if sh.kind == SPHERE:
+        return np.array([*sh.a, sh.s], F)
+    if sh.kind == CYLINDER:  # axis, center, radius
+        return np.array([*sh.a, *sh.b, sh.s], F)
+    return np.array([*sh.a, *sh.b, sh.s / 2], F)  # apex, axis, HALF opening angle
+
+
+def lsq_unpack(kind: int, outwards: bool, x: np.ndarray) -> Shape:
+    if kind == PLANE:
+        return Shape(PLANE, x[0:3].copy(), x[3:6].copy(), 0.0, True)
+    if kind == SPHERE:
+        return Shape(SPHERE, x[0:3].copy(), np.zeros(3), float(x[3]), outwards)
+    if kind == CYLINDER:
+        return Shape(CYLINDER, x[0:3].copy(), x[3:6].copy(), float(x[6]), outwards)
+    return Shape(CONE, x[0:3].copy(), x[3:6].copy(), float(2 * x[6]), outwards)
+
+
+def lsq_normalise(kind: int, x: np.ndarray) -> np.ndarray:
+    """bring a stepped parameter vector back to the reference's conventions: unit axis; cylinder
+    centre on the plane through the origin perpendicular to the axis (cylinder.jl:114)"""
+    x = x.copy()
+    if kind == CYLINDER:
+        a = x[0:3] / math.sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2])
+        c = x[3:6]
+        x[0:3] = a
+        x[3:6] = c - a * (a[0] * c[0] + a[1] * c[1] + a[2] * c[2])
+    elif kind == CONE:
+        x[3:6] = x[3:6] / math.sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5])
+    return x
+
+
+def lsq_residual_jacobian(kind: int, x: np.ndarray, P: np.ndarray):
+    """residual r (n,) and Jacobian J (n, npar) of the signed point-to-surface distance"""
+    if kind == PLANE:  # moments about the old point: "J" = v, "r" = 1 (A = sum v v^T, g = sum v, cost = n)
+        v = P - x[0:3]
+        return np.ones(len(P)), v
+    if kind == SPHERE:
+        v = P - x[0:3]
+        rho = np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2])
+        u = v / rho[:, None]
+        return rho - x[3], np.c_[-u, -np.ones(len(P))]
+    if kind == CYLINDER:
+        a, c, R = x[0:3], x[3:6], x[6]
+        v = P - c
+        h = v[:, 0] * a[0] + v[:, 1] * a[1] + v[:, 2] * a[2]
+        w = v - h[:, None] * a
+        rho = np.sqrt(w[:, 0] * w[:, 0] + w[:, 1] * w[:, 1] + w[:, 2] * w[:, 2])
+        wh = w / rho[:, None]
+        return rho - R, np.c_[-h[:, None] * wh, -wh, -np.ones(len(P))]
+    ap, a, th = x[0:3], x[3:6], x[6]
+    sn, cs = math.sin(th), math.cos(th)
+    v = P - ap
+    h = v[:, 0] * a[0] + v[:, 1] * a[1] + v[:, 2] * a[2]
+    w = v - h[:, None] * a
+    rho = np.sqrt(w[:, 0] * w[:, 0] + w[:, 1] * w[:, 1] + w[:, 2] * w[:, 2])
+    wh = w / rho[:, None]
+    dv = sn * a[None, :] - cs * wh  # d r / d v
+    return h * sn - rho * cs, np.c_[-dv, sn * v + (cs * h)[:, None] * wh, h * cs + rho * sn]
+
+
+def lsq_accumulate(kind: int, x: np.ndarray, P: np.ndarray):
+    """normal equations of one pass: A = J^T J, g = J^T r, cost = r^T r (points with a non-finite
+    residual or Jacobian -- on the axis, at the centre -- are left out)"""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r, J = lsq_residual_jacobian(kind, x, P)
+    ok = np.isfinite(r) & np.isfinite(J).all(axis=1)
+    r, J = r[ok], J[ok]
+    return J.T @ J, J.T @ r, float(r @ r)
+
+
+def lsq_cholesky_solve(A: np.ndarray, b: np.ndarray) -> Optional[np.ndarray]:
+    """solve A x = b for a symmetric positive definite A (None if a pivot is not positive)"""
+    n = len(b)
+    L = np.zeros((n, n))
+    for j in range(n):
+        d = A[j, j] - sum(L[j, k] * L[j, k] for k in range(j))
+        if not (d > 0) or not math.isfinite(d):
+            return None
+        L[j, j] = math.sqrt(d)
+        for i in range(j + 1, n):
+            L[i, j] = (A[i, j] - sum(L[i, k] * L[j, k] for k in range(j))) / L[j, j]
+    y = np.zeros(n)
+    for i in range(n):
+        y[i] = (b[i] - sum(L[i, k] * y[k] for k in range(i))) / L[i, i]
+    xs = np.zeros(n)
+    for i in reversed(range(n)):
+        xs[i] = (y[i] - sum(L[k, i] * xs[k] for k in range(i + 1, n))) / L[i, i]
+    return xs
+
+
+def lsq_smallest_eigvec3(M: np.ndarray) -> np.ndarray:
+    """eigenvector of the smallest eigenvalue of a symmetric 3x3 matrix: cyclic Jacobi, fixed sweep
+    order (0,1), (0,2), (1,2), 30 sweeps at most"""
+    A = M.astype(F).copy()
+    V = np.eye(3)
+    for _ in range(30):
+        off = abs(A[0, 1]) + abs(A[0, 2]) + abs(A[1, 2])
+        if off <= 1e-300 or off <= 1e-17 * (abs(A[0, 0]) + abs(A[1, 1]) + abs(A[2, 2])):
+            break
+        for p_, q_ in ((0, 1), (0, 2), (1, 2)):
+            if A[p_, q_] == 0.0:
+                continue
+            tau = (A[q_, q_] - A[p_, p_]) / (2 * A[p_, q_])
+            t = (1.0 if tau >= 0 else -1.0) / (abs(tau) + math.sqrt(1 + tau * tau))
+            c = 1 / math.sqrt(1 + t * t)
+            s_ = t * c
+            Jm = np.eye(3)
+            Jm[p_, p_] = Jm[q_, q_] = c
+            Jm[p_, q_], Jm[q_, p_] = s_, -s_
+            A = Jm.T @ A @ Jm
+            V = V @ Jm
+    k = int(np.argmin([A[0, 0], A[1, 1], A[2, 2]]))
+    return V[:, k].copy()
+
+
+def lsq_select(sh: Shape, pc: "Cloud", params, band: float = 3.0) -> np.ndarray:
+    """indices of the enabled points compatible with `sh` inside band * eps (and alpha)"""
+    name = SHAPE_NAMES[sh.kind]
+    p3 = {k: dict(v) for k, v in params.items()}
+    p3[name]["eps"] = params[name]["eps"] * band
+    en = np.flatnonzero(pc.isenabled)
+    return en[compatibles(sh, pc.vertices[en], pc.normals[en], p3)]
+
+
+def lsq_refine(sh: Shape, pc: "Cloud", params, band: float = 3.0):
+    """-> (refined shape, number of points used, rms distance).  The candidate is returned unchanged
+    if fewer than 2 * npar points are selected or the minimisation leaves the finite numbers."""
+    sel = lsq_select(sh, pc, params, band)
+    npar = LSQ_NPAR[sh.kind]
+    n = len(sel)
+    if n < 2 * npar:
+        return sh, n, float("nan")
+    P = pc.vertices[sel]
+    x = lsq_pack(sh)
+    if sh.kind == PLANE:
+        A, g, cnt = lsq_accumulate(PLANE, x, P)
+        mean = g / cnt
+        M = A - cnt * np.outer(mean, mean)
+        nv = lsq_smallest_eigvec3(M)
+        nv = nv / math.sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2])
+        if nv[0] * x[3] + nv[1] * x[4] + nv[2] * x[5] < 0:
+            nv = -nv
+        out = np.array([*(x[0:3] + mean), *nv])
+        if not np.isfinite(out).all():
+            return sh, n, float("nan")
+        rms = math.sqrt(max(0.0, float(nv @ M @ nv)) / cnt)
+        return lsq_unpack(PLANE, True, out), n, rms
+    x = lsq_normalise(sh.kind, x)
+    A, g, cost = lsq_accumulate(sh.kind, x, P)
+    lam = 1e-3
+    for _ in range(LSQ_MAXIT):
+        D = A + lam * np.diag(np.diag(A)) + 1e-12 * np.trace(A) / npar * np.eye(npar)
+        d = lsq_cholesky_solve(D, -g)
+        if d is None or not np.isfinite(d).all():
+            lam *= 10
+            continue
+        x1 = lsq_normalise(sh.kind, x + d)
+        A1, g1, cost1 = lsq_accumulate(sh.kind, x1, P)
+        if math.isfinite(cost1) and cost1 <= cost:
+            rel = (cost - cost1) / max(cost, 1e-300)
+            x, A, g, cost = x1, A1, g1, cost1
+            lam = max(lam / 10, 1e-9)
+            if rel < LSQ_REL:
+                break
+        else:
+            lam *= 10
+    if not np.isfinite(x).all():
+        return sh, n, float("nan")
+    return lsq_unpack(sh.kind, sh.outwards, x), n, math.sqrt(cost / n)
+
+
+# --------------------------------------------------------------------------------------
 # Philox4x32-10 (Salmon et al., SC'11) -- the stream the CUDA sampler uses, so that the
 # oracle and the device draw identical minimal sets (the reference's own RNG stream is
 # Julia-version dependent, Q19, and therefore not part of the parity contract).
@@ -934,11 +1123,13 @@ def ransac(
     trace: Optional[RansacTrace] = None,
     octree: Optional[MortonOctree] = None,
     progressive: bool = False,
+    lsq: bool = False,
 ) -> List[Extracted]:
     """iterations.jl:14-21 + :35-162.
 
     `progressive=True` (extension) refines overlapping scores on further subsets before
     the extraction test (refine_progressive); intervals are then the float64 ones (estimatescore_f64).
+    `lsq=True` (extension) refits the best candidate by least squares before extracting it.
 
     `minimal_sets(k, i)` may supply the index triple of minimal set i of iteration k (or None
     for a failed sample); by default the Philox sampler above is used with set_id =
@@ -1021,6 +1212,8 @@ def ransac(
             scr = scores[best].E
             s = cc[sidx[it["extract_s"]]]
             if prob(scr, s, pc.size, drawN) > prob_det:
+                if lsq:
+                    shapes[best] = lsq_refine(shapes[best], pc, params)[0]
                 ip = refit(shapes[best], pc, params)
                 tr.evals += int(pc.isenabled.sum())
                 pc.isenabled[ip] = False

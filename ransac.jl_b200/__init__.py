@@ -8,7 +8,7 @@ an sm_100 device.  There is no CPU fallback anywhere in this package.
 from . import _lib
 from ._lib import Context, RscError
 from .cloud import RANSACCloud, makesubsets
-from .confidence import ConfidenceInterval, E, estimatescore, isoverlap, notsoconfident, prob
+from .confidence import ConfidenceInterval, E, estimatescore, estimatescore_f64, isoverlap, notsoconfident, prob
 from .fitting import (
     IterationCandidates,
     findhighestscore,
@@ -16,6 +16,8 @@ from .fitting import (
     fit_batch,
     fit_points,
     invalidate_indexes,
+    lsq_refit,
+    refine_progressive,
     refit,
     sample_fit,
     sample_fit_cells,

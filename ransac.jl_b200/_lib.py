@@ -97,6 +97,8 @@ SIGNATURES = {
     "rsc_level_cumsum": (None, [_P, C.c_int32, _P]),
     "rsc_update_levelweight": (None, [_P, _P, C.c_int32]),
     "rsc_refit_extract": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), _P, C.POINTER(C.c_int64), C.c_int32]),
+    "rsc_refit_lsq": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), C.c_double, C.POINTER(rsc_cand),
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rsc_ctx_set_allreduce": (C.c_int32, [_P, _P, _P]),
     "rsc_cloud_set_range": (C.c_int32, [_P, C.c_int64, C.c_int64]),
     "rsc_ransac_run": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.POINTER(_P)]),
@@ -122,6 +124,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f.argtypes = _args
 
 
+RSC_REFIT_LSQ = 8  # compat_flags: least-squares refit before each extraction (extension, include/rsc.h)
 RSC_SAMPLER_OCTREE = 2  # compat_flags: level-weighted octree-cell sampler (extension, include/rsc.h)
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)

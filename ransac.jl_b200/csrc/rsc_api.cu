@@ -101,13 +101,13 @@ int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
       cudaEventCreate(&ctx->evk0) != cudaSuccess || cudaEventCreate(&ctx->evk1) != cudaSuccess ||
       cudaEventCreate(&ctx->evr0) != cudaSuccess || cudaEventCreate(&ctx->evr1) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
-    delete ctx;
+    rsc_ctx_destroy(ctx);  // releases whatever was created (handles start out null)
     return RSC_E_CUDA;
   }
   for (int i = 0; i < 4; ++i)
     if (cudaStreamCreateWithFlags(&ctx->sfork[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
-      delete ctx;
+      rsc_ctx_destroy(ctx);
       return RSC_E_CUDA;
     }
   *out = ctx;
@@ -117,27 +117,24 @@ int32_t rsc_ctx_create(int32_t device, rsc_ctx** out) {
 void rsc_ctx_destroy(rsc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   rsc::DevBuf* bufs[] = {&ctx->cands,    &ctx->rec,      &ctx->orig,     &ctx->slot_of, &ctx->blktab,
                          &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count, &ctx->pairs,
-                         &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf, &ctx->exq, &ctx->scanbuf};
+                         &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf, &ctx->exq, &ctx->scanbuf, &ctx->lsqbuf};
   for (auto* b : bufs) b->release();
   rsc::loop_scratch_free(ctx);
   ctx->stage[0].release(), ctx->stage[1].release();
-  cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (int i = 0; i < 4; ++i) {
     if (ctx->sfork[i]) cudaStreamSynchronize(ctx->sfork[i]), cudaStreamDestroy(ctx->sfork[i]);
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  cudaEventDestroy(ctx->ev0);
-  cudaEventDestroy(ctx->ev1);
-  cudaEventDestroy(ctx->evk0);
-  cudaEventDestroy(ctx->evk1);
-  cudaEventDestroy(ctx->evr0);
-  cudaEventDestroy(ctx->evr1);
-  cudaStreamDestroy(ctx->stream);
+  for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->evk0, ctx->evk1, ctx->evr0, ctx->evr1})
+    if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();  // a failed create leaves nothing sticky behind
   delete ctx;
 }
 

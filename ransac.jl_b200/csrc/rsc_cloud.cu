@@ -292,10 +292,15 @@ int32_t rsc_cloud_set_subset(rsc_cloud* c, int32_t subset_id, const int64_t* idx
   s.m_pad = (m + kTile - 1) / kTile * kTile;
   const int64_t words = s.m_pad / 32;
   cudaStream_t st = ctx->stream;
-  RSC_CUDA(ctx, cudaMalloc(&s.soa, (size_t)6 * s.m_pad * sizeof(float)));
-  RSC_CUDA(ctx, cudaMalloc(&s.enabled, (size_t)words * 4));
-  RSC_CUDA(ctx, cudaMalloc(&s.valid, (size_t)words * 4));
-  RSC_CUDA(ctx, cudaMalloc(&s.idx, (size_t)m * sizeof(int64_t)));
+  cudaError_t e;
+  if ((e = cudaMalloc(&s.soa, (size_t)6 * s.m_pad * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&s.enabled, (size_t)words * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&s.valid, (size_t)words * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&s.idx, (size_t)m * sizeof(int64_t))) != cudaSuccess) {
+    cudaFree(s.soa), cudaFree(s.enabled), cudaFree(s.valid), cudaFree(s.idx);  // cudaFree(nullptr) is a no-op
+    s = rsc_subset();  // not uploaded
+    return fail_cuda(ctx, e, "set_subset: cudaMalloc");
+  }
   RSC_CUDA(ctx, cudaMemsetAsync(s.soa, 0, (size_t)6 * s.m_pad * sizeof(float), st));
   RSC_CUDA(ctx, cudaMemcpyAsync(s.idx, idx, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   gather_subset_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(c->soa, c->n_pad, s.idx, m, s.m_pad, s.soa);

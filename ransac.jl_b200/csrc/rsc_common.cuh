@@ -94,7 +94,7 @@ struct rsc_ctx {
   rsc_stats stats{};
   // scratch of the score path
   rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, pairs, wl_count, aux;
-  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf;
+  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf;
   size_t wl_cap = 1u << 22;  // guard-band queue capacity (groups / pairs), grows on overflow
   rsc_allreduce_fn allreduce = nullptr;  // sums int32 device buffers across the ranks of a sharded run
   void* allreduce_user = nullptr;
@@ -237,4 +237,7 @@ int32_t scan_u32(rsc_ctx* ctx, const uint32_t* counts, int n, unsigned long long
                  cudaStream_t st);
 int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st);
 int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st);
+// least-squares refit of *cand in place (rsc_lsq.cu); synchronises `st`
+int32_t lsq_refine(rsc_cloud* cloud, const rsc_params* params, double band, rsc_cand* cand, int64_t* n_used, double* rms,
+                   cudaStream_t st);
 }  // namespace rsc

@@ -526,6 +526,9 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           RUN_CUDA(cudaStreamSynchronize(st));
           const auto tka = now();
           t_exa += secs(tkx, tka);
+          if (p->compat_flags & RSC_REFIT_LSQ) {  // extension: the paper's least-squares refit within 3 eps
+            if ((rc = lsq_refine(cloud, p, 3.0, &shape, nullptr, nullptr, st))) goto done;
+          }
           Thresh thr = th;
           thr.honour_enabled = 0xFu;
           if ((rc = refit_mask_enqueue(cloud, thr, shape, st))) goto done;

@@ -137,6 +137,17 @@ def refit(s: FittedShape, pc: RANSACCloud, params, disable: bool = False) -> Ext
     return ExtractedShape(s, out[: n.value].copy())
 
 
+def lsq_refit(s: FittedShape, pc: RANSACCloud, params, band: float = 3.0):
+    """Extension: least-squares refit of `s` to the enabled points compatible with it
+    inside band * eps -- the refit of the paper, which the reference leaves out
+    (docs/src/ransac.md:163-169).  Returns (refined shape, points used, rms distance)."""
+    cand, out = s.to_cand(), _lib.rsc_cand()
+    cp = to_c(params)
+    n, rms = C.c_int64(), C.c_double()
+    pc.ctx.check(lib.rsc_refit_lsq(pc.handle, C.byref(cp), C.byref(cand), float(band), C.byref(out), C.byref(n), C.byref(rms)))
+    return from_cand(out), n.value, rms.value
+
+
 def invalidate_indexes(pc: RANSACCloud, indexlist):
     en = pc.isenabled
     en[np.asarray(indexlist, dtype=np.int64) - pc.global_offset] = False

@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import lib
 from .cloud import RANSACCloud
 from .confidence import estimatescore_f64, prob
-from .fitting import IterationCandidates, findhighestscore, refine_progressive, refit, sample_fit, scorecandidates
+from .fitting import IterationCandidates, findhighestscore, lsq_refit, refine_progressive, refit, sample_fit, scorecandidates
 from .params import to_c
 from .shapes import SHAPE_KIND, ExtractedShape, from_cand
 
@@ -27,7 +27,7 @@ def _all_builtin(params) -> bool:
 
 
 def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = False, seed: int = 1234,
-           sampler: str = "root", progressive: bool = False) -> Tuple[List[ExtractedShape], float]:
+           sampler: str = "root", progressive: bool = False, lsq: bool = False) -> Tuple[List[ExtractedShape], float]:
     """Run efficient RANSAC on `pc`; returns (extracted shapes, seconds).
 
     `reset_rand=True` pins the sampler seed to 1234 like `Random.seed!(1234)` (iterations.jl:36);
@@ -37,20 +37,24 @@ def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = 
     final level weights are left in `pc.levelweight`.  `progressive=True` (extension) refines
     overlapping scores on further subsets before each extraction test (`fitting.refine_progressive`,
     the reference's "TODO: refine if best.overlap", iterations.jl:110); it runs the host loop over the
-    per-call C ABI and leaves the number of extra (candidate, subset) evaluations in `pc.last_refined`."""
+    per-call C ABI and leaves the number of extra (candidate, subset) evaluations in `pc.last_refined`.
+    `lsq=True` (extension) refits the best candidate by least squares to the compatible points within
+    3 eps before it is extracted (`fitting.lsq_refit`; the paper's refit, docs/src/ransac.md:163-169)."""
     if setenabled:
         pc.enable_all()
     if reset_rand:
         seed = 1234
     if _all_builtin(params) and not progressive:
-        return _ransac_device(pc, params, seed, sampler)
+        return _ransac_device(pc, params, seed, sampler, lsq)
     if sampler != "root":
         raise ValueError("the octree sampler is only available in the device loop (built-in shape types, not progressive)")
-    return _ransac_host(pc, params, seed, progressive)
+    return _ransac_host(pc, params, seed, progressive, lsq)
 
 
-def _ransac_device(pc, params, seed, sampler="root"):
+def _ransac_device(pc, params, seed, sampler="root", lsq=False):
     cp = to_c(params)
+    if lsq:
+        cp.compat_flags |= _lib.RSC_REFIT_LSQ
     if sampler == "octree":
         cp.compat_flags |= _lib.RSC_SAMPLER_OCTREE
     elif sampler != "root":
@@ -78,7 +82,7 @@ def _ransac_device(pc, params, seed, sampler="root"):
     return out, int(secs * 100) / 100.0
 
 
-def _ransac_host(pc, params, seed, progressive=False):
+def _ransac_host(pc, params, seed, progressive=False, lsq=False):
     """iterations.jl:35-162 on the host, for parameter sets with user-defined shapes and for
     progressive scoring."""
     it = params["iteration"]
@@ -124,6 +128,8 @@ def _ransac_host(pc, params, seed, progressive=False):
             scr = scored.scores[best].E
             if prob(scr, cc[sidx[it["extract_s"]]], pc.size, drawN) > prob_det:
                 shp = scored.shapes[best]
+                if lsq and type(shp) in SHAPE_KIND:
+                    shp = lsq_refit(shp, pc, bparams)[0]
                 ex = refit(shp, pc, bparams, disable=True) if type(shp) in SHAPE_KIND else shp.refit(pc, params)
                 if type(shp) not in SHAPE_KIND:
                     from .fitting import invalidate_indexes

@@ -1,0 +1,183 @@
+"""Least-squares refit before the extraction (extension; the reference keeps the candidate
+unchanged, docs/src/ransac.md:163-169).  CPU: the oracle's definition recovers known shapes from noisy
+samples.  GPU: rsc_refit_lsq (normal equations accumulated on the device) agrees with the oracle within
+1e-5 relative, and the device loop with RSC_REFIT_LSQ extracts the oracle's shapes and inlier lists."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ransac_oracle as O
+from tests.helpers import oracle_params, to_oracle_shape
+
+
+def _unit(v):
+    v = np.asarray(v, float)
+    return v / np.linalg.norm(v)
+
+
+def noisy_cases(seed=1, n=4000, extra_outliers=500):
+    """[(name, perturbed start shape, true parameter dict, float32 points, normals, sigma)]"""
+    rng = np.random.default_rng(seed)
+    cases = []
+
+    def finish(V, N):
+        out = rng.uniform(-12, 12, (extra_outliers, 3))
+        on = rng.normal(size=(extra_outliers, 3))
+        on /= np.linalg.norm(on, axis=1, keepdims=True)
+        V = np.r_[V, out].astype(np.float32).astype(np.float64)
+        N = np.r_[N, on].astype(np.float32).astype(np.float64)
+        return V, N
+
+    # plane z = 0.5 x tilted
+    nrm = _unit([0.2, -0.1, 1.0])
+    e1 = _unit(np.cross(nrm, [1, 0, 0]))
+    e2 = np.cross(nrm, e1)
+    uv = rng.uniform(-6, 6, (n, 2))
+    V = np.array([1.0, 2.0, 3.0]) + uv[:, :1] * e1 + uv[:, 1:] * e2 + rng.normal(0, 0.05, (n, 1)) * nrm
+    V, N = finish(V, np.tile(nrm, (n, 1)))
+    start = O.Shape(O.PLANE, np.array([1.0, 2.0, 3.1]), _unit(nrm + [0.01, 0.015, 0.0]))
+    cases.append(("plane", start, {"normal": nrm, "point": np.array([1.0, 2.0, 3.0])}, V, N, 0.05))
+    # sphere
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    V = np.array([1.0, 2.0, 3.0]) + (5 + rng.normal(0, 0.05, n))[:, None] * d
+    V, N = finish(V, d)
+    start = O.Shape(O.SPHERE, np.array([1.1, 2.05, 2.9]), np.zeros(3), 5.08, True)
+    cases.append(("sphere", start, {"center": np.array([1.0, 2.0, 3.0]), "radius": 5.0}, V, N, 0.05))
+    # cylinder (inwards-pointing normals: outwards = False)
+    ax = _unit([0.1, 0.2, 1.0])
+    e1 = _unit(np.cross(ax, [1, 0, 0]))
+    e2 = np.cross(ax, e1)
+    c0 = np.array([2.0, 0, 0])
+    c0 = c0 - ax * (ax @ c0)
+    th = rng.uniform(0, 2 * np.pi, n)
+    z = rng.uniform(-5, 5, n)
+    rad = 2 + rng.normal(0, 0.03, n)
+    rd = np.cos(th)[:, None] * e1 + np.sin(th)[:, None] * e2
+    V = c0 + z[:, None] * ax + rad[:, None] * rd
+    V, N = finish(V, -rd)
+    a1 = _unit(ax + [0.01, -0.01, 0.0])
+    c1 = c0 + [0.05, 0.03, 0]
+    start = O.Shape(O.CYLINDER, a1, c1 - a1 * (a1 @ c1), 2.06, False)
+    cases.append(("cylinder", start, {"axis": ax, "center": c0, "radius": 2.0}, V, N, 0.03))
+    # cone, apex at (1,1,-2), axis z, half angle 20 deg
+    ha = math.radians(20)
+    h = rng.uniform(2, 10, n)
+    th = rng.uniform(0, 2 * np.pi, n)
+    rho = h * math.tan(ha)
+    nr = np.c_[np.cos(th) * math.cos(ha), np.sin(th) * math.cos(ha), -math.sin(ha) * np.ones(n)]
+    V = np.array([1.0, 1.0, -2.0]) + np.c_[rho * np.cos(th), rho * np.sin(th), h] + rng.normal(0, 0.03, n)[:, None] * nr
+    V, N = finish(V, nr)
+    start = O.Shape(O.CONE, np.array([1.05, 0.95, -1.9]), _unit([0.01, 0.0, 1.0]), 2 * ha + 0.01, True)
+    cases.append(("cone", start, {"apex": np.array([1.0, 1.0, -2.0]), "axis": np.array([0, 0, 1.0]), "opang": 2 * ha}, V, N, 0.03))
+    return cases
+
+
+def test_oracle_lsq_recovers_the_shapes():
+    P = O.default_parameters()
+    for name, start, truth, V, N, sigma in noisy_cases():
+        pc = O.Cloud(V, N, [np.arange(len(V))])
+        before = int(O.compatibles(start, V, N, P).sum())
+        ref, used, rms = O.lsq_refine(start, pc, P)
+        after = int(O.compatibles(ref, V, N, P).sum())
+        assert used > 3500 and 0.7 * sigma < rms < 1.3 * sigma, (name, used, rms)
+        assert after >= before, (name, before, after)
+        if name == "plane":
+            assert abs(ref.b @ truth["normal"]) > 1 - 1e-6 and abs((ref.a - truth["point"]) @ truth["normal"]) < 0.01
+        elif name == "sphere":
+            assert np.abs(ref.a - truth["center"]).max() < 0.01 and abs(ref.s - 5) < 0.01
+        elif name == "cylinder":
+            assert abs(ref.a @ truth["axis"]) > 1 - 1e-6 and np.abs(ref.b - truth["center"]).max() < 0.01 and abs(ref.s - 2) < 0.01
+            assert abs(ref.a @ ref.b) < 1e-12 and ref.outwards is False  # conventions kept
+        else:
+            assert abs(ref.b @ truth["axis"]) > 1 - 1e-6 and np.abs(ref.a - truth["apex"]).max() < 0.03 and abs(ref.s - truth["opang"]) < 0.003
+
+
+def test_oracle_lsq_keeps_the_candidate_without_support():
+    P = O.default_parameters()
+    V = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    N = np.tile([0, 0, 1.0], (3, 1))
+    pc = O.Cloud(V, N, [np.arange(3)])
+    sh = O.Shape(O.SPHERE, np.array([0.0, 0, -5]), np.zeros(3), 5.0, True)
+    ref, used, rms = O.lsq_refine(sh, pc, P)
+    assert ref is sh and used < 8 and rms != rms
+
+
+def test_lsq_helpers():
+    rng = np.random.default_rng(0)
+    for n in (3, 4, 7):
+        B = rng.normal(size=(n + 3, n))
+        A = B.T @ B
+        b = rng.normal(size=n)
+        np.testing.assert_allclose(O.lsq_cholesky_solve(A, b), np.linalg.solve(A, b), rtol=1e-9)
+    assert O.lsq_cholesky_solve(np.array([[1.0, 2], [2, 1]]), np.ones(2)) is None
+    for _ in range(20):
+        B = rng.normal(size=(3, 3))
+        M = B @ B.T
+        v = O.lsq_smallest_eigvec3(M)
+        w, U = np.linalg.eigh(M)
+        assert abs(abs(v @ U[:, 0]) - 1) < 1e-9
+
+
+@pytest.mark.gpu
+def test_device_lsq_matches_oracle():
+    import ransac_jl_b200 as R
+
+    P = R.ransacparameters()
+    OP = oracle_params(P)
+    for name, start, truth, V, N, sigma in noisy_cases():
+        pc = R.RANSACCloud(V.astype(np.float32), N.astype(np.float32), 1)
+        en = np.ones(len(V), bool)
+        en[::7] = False  # disabled points must not be used
+        pc.isenabled = en
+        oc = O.Cloud(V, N, [np.arange(len(V))], en.copy())
+        shp = R.from_cand(R._lib.rsc_cand(start.kind, int(start.outwards), (R._lib.C.c_double * 7)(*start.params7())))
+        got, used, rms = R.lsq_refit(shp, pc, P)
+        want, wused, wrms = O.lsq_refine(start, oc, OP)
+        assert used == wused, name
+        g, w = np.array(got.to_cand().p[:7]), want.params7()
+        np.testing.assert_allclose(g, w, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(w).max()), err_msg=name)
+        assert abs(rms - wrms) <= 1e-6 * wrms, name
+        assert bool(got.to_cand().outwards) == want.outwards or start.kind == O.PLANE
+        np.testing.assert_array_equal(pc.isenabled, en)  # nothing is disabled by the refit
+        # too little support: unchanged
+        far = O.Shape(O.SPHERE, np.array([500.0, 0, 0]), np.zeros(3), 1.0, True)
+        fshp = R.from_cand(R._lib.rsc_cand(far.kind, 1, (R._lib.C.c_double * 7)(*far.params7())))
+        same, n0, r0 = R.lsq_refit(fshp, pc, P)
+        assert n0 == 0 and r0 != r0 and np.array_equal(np.array(same.to_cand().p[:4]), far.params7()[:4])
+
+
+@pytest.mark.gpu
+def test_device_loop_with_lsq_matches_oracle():
+    import ransac_jl_b200 as R
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(86, 30_000, noise_frac=0.004, jitter_deg=1.5, outlier_frac=0.15, counts=(2, 1, 1, 1))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4)
+    params = R.ransacparameters(iteration={"tau": 300, "minsubsetN": 64, "itermax": 40})
+    extracted, _ = R.ransac(pc, params, True, seed=21, lsq=True)
+    oc = O.Cloud(sc.vertices.astype(np.float64), sc.normals.astype(np.float64), [s.copy() for s in pc.subsets])
+    want = O.ransac(oc, oracle_params(params), True, seed=21, lsq=True)
+    plain = O.ransac(O.Cloud(sc.vertices.astype(np.float64), sc.normals.astype(np.float64), [s.copy() for s in pc.subsets]),
+                     oracle_params(params), True, seed=21)
+    assert len(extracted) == len(want) >= 3
+    for got, w in zip(extracted, want):
+        c = got.shape.to_cand()
+        assert c.type == w.shape.kind
+        p = w.shape.params7()
+        np.testing.assert_allclose(np.array(c.p[:7]), p, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(p).max()))
+        # the refined parameters agree to ~1e-10, but a point within that of a threshold may flip: allow a handful
+        a, b = set(got.inpoints.tolist()), set(w.inpoints.tolist())
+        assert len(a ^ b) <= 2, len(a ^ b)
+    # the least-squares refit collects at least as many points for the first shape as the plain refit
+    assert len(want[0].inpoints) >= len(plain[0].inpoints)
+    # host loop (per-call ABI: rsc_refit_lsq + rsc_refit_extract) == device loop
+    from ransac_jl_b200 import iterations as IT
+
+    pc.enable_all()
+    host, _ = IT._ransac_host(pc, params, 21, lsq=True)
+    assert len(host) == len(extracted)
+    for a, b in zip(host, extracted):
+        np.testing.assert_allclose(np.array(a.shape.to_cand().p[:7]), np.array(b.shape.to_cand().p[:7]), rtol=1e-12, atol=1e-300)
+        np.testing.assert_array_equal(a.inpoints, b.inpoints)
