@@ -56,6 +56,13 @@ extern "C" {
  * compatible points within 3 eps (rsc_refit_lsq) before it extracts it -- the paper's refit, which the
  * reference leaves out (docs/src/ransac.md:163-169). */
 #define RSC_REFIT_LSQ 8u
+/* extension switch (off by default): progressive subset scoring inside rsc_ransac_run -- what the
+ * reference leaves as "TODO: refine if best.overlap" (iterations.jl:110; docs/src/ransac.md:137-141).
+ * While the confidence interval of the best candidate overlaps another one (isoverlap,
+ * confidenceintervals.jl:29-36) the least-evaluated candidates among the best and its overlappers are
+ * scored on their next subset and re-estimated from the union; intervals are the float64 ones (no
+ * Int64 wrap, Q9).  Needs every subset uploaded with rsc_cloud_set_subset. */
+#define RSC_SCORE_PROGRESSIVE 16u
 
 /* which counter plays `s` in prob(n,s,N,k): utilities.jl:297-300 */
 #define RSC_S_LENGTHC 0
@@ -242,6 +249,7 @@ void rsc_update_levelweight(double* levelweight, const double* levelscore, int32
 int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* params, uint64_t seed, rsc_run** out);
 int32_t rsc_run_nshapes(const rsc_run* run);
 int32_t rsc_run_iterations(const rsc_run* run);
+int64_t rsc_run_refined(const rsc_run* run); /* RSC_SCORE_PROGRESSIVE: (candidate, subset) evaluations beyond subset 1 */
 double rsc_run_seconds(const rsc_run* run);
 /* cell sampler runs: final level weights and accumulated level scores; returns the number of levels (0: root-cell run) */
 int32_t rsc_run_levelweight(const rsc_run* run, double* levelweight, double* levelscore);

@@ -104,6 +104,7 @@ SIGNATURES = {
     "rsc_ransac_run": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.POINTER(_P)]),
     "rsc_run_nshapes": (C.c_int32, [_P]),
     "rsc_run_iterations": (C.c_int32, [_P]),
+    "rsc_run_refined": (C.c_int64, [_P]),
     "rsc_run_seconds": (C.c_double, [_P]),
     "rsc_run_levelweight": (C.c_int32, [_P, _P, _P]),
     "rsc_run_shape": (C.c_int32, [_P, C.c_int32, C.POINTER(rsc_cand), C.POINTER(C.c_int64)]),
@@ -124,6 +125,7 @@ for _name, (_res, _args) in SIGNATURES.items():
     _f.argtypes = _args
 
 
+RSC_SCORE_PROGRESSIVE = 16  # compat_flags: progressive subset scoring in rsc_ransac_run (extension)
 RSC_REFIT_LSQ = 8  # compat_flags: least-squares refit before each extraction (extension, include/rsc.h)
 RSC_SAMPLER_OCTREE = 2  # compat_flags: level-weighted octree-cell sampler (extension, include/rsc.h)
 

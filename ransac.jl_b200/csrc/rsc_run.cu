@@ -148,6 +148,60 @@ __global__ void compact_store_kernel(const rsc_cand* __restrict__ c0, const int3
   f1[o] = f0[i];
 }
 
+// ---- progressive subset scoring (extension; iterations.jl:110 "TODO: refine if best.overlap") ----
+__global__ void gather_cands_kernel(const rsc_cand* __restrict__ store, const int32_t* __restrict__ idx, int n,
+                                    rsc_cand* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = store[idx[i]];
+}
+
+// Host mirror of the store's scores while refining: candidate i has been scored on subsets 1..lvl[i],
+// sigma[i] compatible points among their M[i] points; interval from the union, in float64 without the
+// reference's Int64 wrap (Q9) -- same operation order as oracle/ransac_oracle.py::estimatescore_f64.
+struct ProgMirror {
+  std::vector<int64_t> sigma, M;
+  std::vector<int32_t> lvl;
+  std::vector<double> lo, hi, E;
+  size_t size() const { return E.size(); }
+  void clear() { sigma.clear(), M.clear(), lvl.clear(), lo.clear(), hi.clear(), E.clear(); }
+  static void interval(int64_t m, int64_t N, int64_t sg, double* lo, double* hi, double* E) {
+    const double Np = (double)(-2 - m), x = (double)(-2 - N), n = (double)(-1 - sg);
+    const double xn = x * n;
+    const double sq_ = (xn * (Np - x)) * (Np - n) / (Np - 1.0);
+    const double sq = sq_ < 0 ? 0.0 : sqrt(sq_);
+    const double a = -1 - (xn + sq) / Np, b = -1 - (xn - sq) / Np;
+    *lo = a < b ? a : b;
+    *hi = a < b ? b : a;
+    *E = (*lo + *hi) / 2;
+  }
+  void push(int64_t sg, int64_t m, int64_t N) {
+    double a, b, e;
+    interval(m, N, sg, &a, &b, &e);
+    sigma.push_back(sg), M.push_back(m), lvl.push_back(1), lo.push_back(a), hi.push_back(b), E.push_back(e);
+  }
+  void add(size_t i, int64_t sg, int64_t m, int64_t N) {
+    sigma[i] += sg, M[i] += m, lvl[i] += 1;
+    interval(M[i], N, sigma[i], &lo[i], &hi[i], &E[i]);
+  }
+  int best() const {  // findhighestscore (fitting.jl:140-150): strict >, first wins
+    if (E.empty()) return -1;
+    int ind = 0;
+    for (size_t i = 1; i < E.size(); ++i)
+      if (E[i] > E[ind]) ind = (int)i;
+    return ind;
+  }
+  bool overlap(size_t i, size_t j) const {  // isoverlap (confidenceintervals.jl:29-36)
+    if (lo[i] == lo[j]) return true;
+    return lo[i] < lo[j] ? lo[j] <= hi[i] : lo[i] <= hi[j];
+  }
+  void compact(const std::vector<uint32_t>& keep) {
+    size_t o = 0;
+    for (size_t i = 0; i < E.size(); ++i)
+      if (keep[i]) sigma[o] = sigma[i], M[o] = M[i], lvl[o] = lvl[i], lo[o] = lo[i], hi[o] = hi[i], E[o] = E[i], ++o;
+    sigma.resize(o), M.resize(o), lvl.resize(o), lo.resize(o), hi.resize(o), E.resize(o);
+  }
+};
+
 // the candidate store (device), ping-pong buffers for order-preserving compaction
 struct Store {
   DevBuf cands[2], score[2], flags[2];
@@ -185,7 +239,7 @@ struct Store {
 // device buffers per run cost 10-25 ms of a 40 ms loop)
 struct LoopScratch {
   Store store;
-  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf;
+  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf, prog;
 };
 
 void loop_scratch_free(rsc_ctx* ctx) {
@@ -193,7 +247,7 @@ void loop_scratch_free(rsc_ctx* ctx) {
   if (!ls) return;
   ls->store.release();
   ls->newcnt.release(), ls->hostio.release(), ls->olden.release(), ls->nscratch.release(), ls->nvalid.release(), ls->nmeta.release();
-  ls->lvbuf.release();
+  ls->lvbuf.release(), ls->prog.release();
   delete ls;
   ctx->loop_scratch = nullptr;
 }
@@ -288,6 +342,7 @@ struct rsc_run {
   int64_t* d_idx = nullptr;
   int device = 0;
   int iterations = 0;
+  int64_t refined = 0;  // progressive scoring: (candidate, subset) evaluations beyond subset 1
   double seconds = 0.0;
   int nlevels = 0;  // cell sampler: final level weights / accumulated level scores
   double levelweight[11] = {0}, levelscore[11] = {0};
@@ -352,6 +407,51 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   }
   DevBuf &newcnt = ls.newcnt, &hostio = ls.hostio, &olden = ls.olden, &nscratch = ls.nscratch, &nvalid = ls.nvalid, &nmeta = ls.nmeta,
          &lvbuf = ls.lvbuf;
+  const bool prog = (p->compat_flags & RSC_SCORE_PROGRESSIVE) != 0;
+  const int nsub = (int)cloud->subsets.size();
+  ProgMirror mirror;
+  std::vector<int32_t> newscore, todo, todo_counts;
+  std::vector<uint32_t> keep_h;
+  // a rank's slice of a gathered subset copy: the same fraction of it as the rank's range of the cloud
+  auto subset_view = [&](rsc_subset& sb) {
+    PointSet v = view_subset(&sb);
+    if (sharded && cloud->range_hi > cloud->range_lo && cloud->n_pad > 0) {
+      const int64_t lo = (int64_t)((double)cloud->range_lo / cloud->n_pad * sb.m_pad) / kTile * kTile;
+      const int64_t hi = cloud->range_hi >= cloud->n_pad ? sb.m_pad : (int64_t)((double)cloud->range_hi / cloud->n_pad * sb.m_pad) / kTile * kTile;
+      v.x += lo, v.y += lo, v.z += lo, v.nx += lo, v.ny += lo, v.nz += lo;
+      v.enabled += lo / 32, v.valid += lo / 32;
+      v.n_pad = hi - lo;
+      v.n = (sb.m < hi ? sb.m : hi) - lo;
+    }
+    return v;
+  };
+  // progressive scoring: policy counts of the store candidates `todo` on subset `sj` (0-based) -> todo_counts
+  auto score_selected = [&](int sj) -> int32_t {
+    const int n = (int)todo.size();
+    todo_counts.assign(n, 0);
+    const size_t o_c = ((size_t)n * 4 + 255) / 256 * 256, o_k = o_c + ((size_t)n * sizeof(rsc_cand) + 255) / 256 * 256;
+    if (ls.prog.ensure(o_k + (size_t)(n + 1) * 4) != cudaSuccess) return fail(ctx, RSC_E_NOMEM, "ransac_run: progressive scratch");
+    int32_t* d_idx = ls.prog.as<int32_t>();
+    rsc_cand* d_c = (rsc_cand*)(ls.prog.as<char>() + o_c);
+    int32_t* d_cnt = (int32_t*)(ls.prog.as<char>() + o_k);
+    if (cudaMemcpyAsync(d_idx, todo.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return fail(ctx, RSC_E_CUDA, "ransac_run: progressive upload");
+    gather_cands_kernel<<<(n + 255) / 256, 256, 0, st>>>(store.cands[store.cur].as<rsc_cand>(), d_idx, n, d_c);
+    for (int attempt = 0;; ++attempt) {
+      int32_t r2 = score_enqueue(ctx, cloud, subset_view(cloud->subsets[sj]), th, d_c, n, d_cnt, false, st);
+      if (r2) return r2;
+      queue_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, d_cnt + n);
+      if (sharded && ctx->allreduce(ctx->allreduce_user, d_cnt, (int64_t)n + 1, (void*)st))
+        return fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce callback failed");
+      int32_t ovf = 0;
+      if (cudaMemcpyAsync(todo_counts.data(), d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+          cudaMemcpyAsync(&ovf, d_cnt + n, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        return fail(ctx, RSC_E_CUDA, "ransac_run: progressive scoring failed");
+      if (ovf == 0) return RSC_OK;
+      if (attempt >= 4) return fail(ctx, RSC_E_STATE, "ransac_run: guard-band queue kept overflowing");
+      if ((r2 = grow_guard_queue(ctx))) return r2;
+    }
+  };
   const bool cells_mode = (p->compat_flags & RSC_SAMPLER_OCTREE) != 0;
   const int nlv = cloud->cells.nlevels;
   const int Bmax = cells_mode ? 1 : (getenv("RSC_BATCH") ? std::max(1, std::min(16, atoi(getenv("RSC_BATCH")))) : 16);
@@ -392,6 +492,13 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     for (int l = 0; l < nlv; ++l) run->levelweight[l] = 1.0 / nlv, run->levelscore[l] = 0.0;
     RUN_CUDA(lvbuf.ensure(2 * 11 * 8));
   }
+
+  if (prog)
+    for (int j = 0; j < nsub; ++j)
+      if (!cloud->subsets[j].soa) {
+        rc = fail(ctx, RSC_E_STATE, "ransac_run: RSC_SCORE_PROGRESSIVE needs every subset uploaded (rsc_cloud_set_subset)");
+        goto done;
+      }
 
   // Iterations are run in speculative batches of nb: as long as nothing is extracted the enabled mask
   // does not change, so iterations k..k+nb-1 can sample, fit and score together (one K2 launch over
@@ -482,6 +589,11 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
         RUN_CUDA(cudaGetLastError());
         RUN_CUDA(cudaMemcpyAsync(seg_keys, d_keys, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
       }
+      if (prog && n_new > 0) {
+        newscore.resize(n_new);
+        RUN_CUDA(cudaMemcpyAsync(newscore.data(), store.score[store.cur].as<int32_t>() + store_n0, (size_t)n_new * 4,
+                                 cudaMemcpyDeviceToHost, st));
+      }
       RUN_CUDA(cudaStreamSynchronize(st));
       if (ovf == 0) break;
       if (attempt >= 4) {
@@ -512,10 +624,37 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     if (seg_keys[j] > bestkey) bestkey = seg_keys[j];  // first maximum wins: the key carries the store index
     best[0] = bestkey >= 0 ? (int64_t)(0x7fffffff - (bestkey & 0xffffffffll)) : -1;
     best[1] = bestkey >= 0 ? (int64_t)(bestkey >> 32) : 0;
+    if (prog) {
+      // refine while the best interval overlaps another one: the least-evaluated candidates among the best
+      // and its overlappers are scored on their next subset (one K2 launch per round), re-estimated
+      // from the union; stops when the best stands alone or those candidates have seen every subset
+      for (int i = seg_h[j]; i < seg_h[j + 1]; ++i) mirror.push(newscore[i], sub.m, N);
+      while (mirror.size() > 1) {
+        const int b = mirror.best();
+        int lmin = 1 << 30;
+        bool any = false;
+        for (size_t i = 0; i < mirror.size(); ++i)
+          if ((int)i == b || mirror.overlap(i, b)) {
+            any = any || (int)i != b;
+            lmin = mirror.lvl[i] < lmin ? mirror.lvl[i] : lmin;
+          }
+        if (!any || lmin >= nsub) break;
+        todo.clear();
+        for (size_t i = 0; i < mirror.size(); ++i)
+          if (((int)i == b || mirror.overlap(i, b)) && mirror.lvl[i] == lmin) todo.push_back((int32_t)i);
+        if ((rc = score_selected(lmin))) goto done;
+        for (size_t t = 0; t < todo.size(); ++t) mirror.add(todo[t], todo_counts[t], cloud->subsets[lmin].m, N);
+        run->refined += (int64_t)todo.size();
+      }
+      best[0] = mirror.best();
+    }
     if (store.n >= 1) {
       if (best[0] >= 0) {
         double E;
-        rsc_estimate_score(sub.m, N, best[1], nullptr, nullptr, &E);
+        if (prog)
+          E = mirror.E[best[0]];
+        else
+          rsc_estimate_score(sub.m, N, best[1], nullptr, nullptr, &E);
         const double s_ex = (double)counters[p->extract_s];
         if (prob_(E, s_ex, (double)N, (double)p->drawN) > p->prob_det) {
           // ---- K4: refit over the whole cloud, invalidate its points ----
@@ -616,6 +755,12 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           }
           if ((rc = grow_guard_queue(ctx))) goto done;
           }
+          if (prog) {
+            keep_h.resize(nst);
+            RUN_CUDA(cudaMemcpyAsync(keep_h.data(), keep, (size_t)nst * 4, cudaMemcpyDeviceToHost, st));
+            RUN_CUDA(cudaStreamSynchronize(st));
+            mirror.compact(keep_h);
+          }
           store.cur = nxt;
           store.n = (int)kept;
           t_k5 += secs(tk3, now());
@@ -649,6 +794,7 @@ done:
 
 int32_t rsc_run_nshapes(const rsc_run* r) { return r ? (int32_t)r->shapes.size() : 0; }
 int32_t rsc_run_iterations(const rsc_run* r) { return r ? r->iterations : 0; }
+int64_t rsc_run_refined(const rsc_run* r) { return r ? r->refined : 0; }
 double rsc_run_seconds(const rsc_run* r) { return r ? r->seconds : 0.0; }
 
 int32_t rsc_run_levelweight(const rsc_run* r, double* levelweight, double* levelscore) {

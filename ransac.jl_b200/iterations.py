@@ -36,23 +36,27 @@ def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = 
     is written for -- instead of from the root cell, which is what its shipped code does (Q1); the
     final level weights are left in `pc.levelweight`.  `progressive=True` (extension) refines
     overlapping scores on further subsets before each extraction test (`fitting.refine_progressive`,
-    the reference's "TODO: refine if best.overlap", iterations.jl:110); it runs the host loop over the
-    per-call C ABI and leaves the number of extra (candidate, subset) evaluations in `pc.last_refined`.
+    the reference's "TODO: refine if best.overlap", iterations.jl:110; `RSC_SCORE_PROGRESSIVE` in the
+    device loop) and leaves the number of extra (candidate, subset) evaluations in `pc.last_refined`.
     `lsq=True` (extension) refits the best candidate by least squares to the compatible points within
     3 eps before it is extracted (`fitting.lsq_refit`; the paper's refit, docs/src/ransac.md:163-169)."""
     if setenabled:
         pc.enable_all()
     if reset_rand:
         seed = 1234
-    if _all_builtin(params) and not progressive:
-        return _ransac_device(pc, params, seed, sampler, lsq)
+    if _all_builtin(params):
+        return _ransac_device(pc, params, seed, sampler, lsq, progressive)
     if sampler != "root":
-        raise ValueError("the octree sampler is only available in the device loop (built-in shape types, not progressive)")
+        raise ValueError("the octree sampler is only available in the device loop (built-in shape types)")
     return _ransac_host(pc, params, seed, progressive, lsq)
 
 
-def _ransac_device(pc, params, seed, sampler="root", lsq=False):
+def _ransac_device(pc, params, seed, sampler="root", lsq=False, progressive=False):
     cp = to_c(params)
+    if progressive:
+        for j in range(len(pc.subsets)):  # the refinement scores on the subsets 2..r too
+            pc.upload_subset(j)
+        cp.compat_flags |= _lib.RSC_SCORE_PROGRESSIVE
     if lsq:
         cp.compat_flags |= _lib.RSC_REFIT_LSQ
     if sampler == "octree":
@@ -72,6 +76,7 @@ def _ransac_device(pc, params, seed, sampler="root", lsq=False):
                 pc.ctx.check(lib.rsc_run_inpoints(run, i, idx.ctypes.data))
             out.append(ExtractedShape(from_cand(cand), idx))
         secs = lib.rsc_run_seconds(run)
+        pc.last_refined = int(lib.rsc_run_refined(run))
         lw, ls = np.zeros(11), np.zeros(11)
         nl = lib.rsc_run_levelweight(run, lw.ctypes.data, ls.ctypes.data)
         if nl:
