@@ -77,8 +77,11 @@ def test_resume_without_reset(R):
     assert pc.count_enabled() == pc.size - len(taken)
 
 
-def test_sharded_callback_single_rank(R):
-    """the sharded code path (range + all-reduce callback) on one rank equals the plain run"""
+@pytest.mark.parametrize("opts", [{}, {"progressive": True}, {"lsq": True}], ids=["plain", "progressive", "lsq"])
+def test_sharded_callback_single_rank(R, opts):
+    """the sharded code path (range + all-reduce callback) on one rank equals the plain run, also with
+    the extensions switched on (progressive scoring slices every subset copy, the least-squares refit
+    all-reduces its selection mask)"""
     import ctypes as C
 
     from ransac_jl_b200 import scenes
@@ -87,16 +90,18 @@ def test_sharded_callback_single_rank(R):
     sc = scenes.scene_c1(seed=11)
     params = R.ransacparameters(iteration={"itermax": 120})
     pc = R.RANSACCloud(sc.vertices, sc.normals, 2)
-    plain, _ = R.ransac(pc, params, True, seed=5)
+    plain, _ = R.ransac(pc, params, True, seed=5, **opts)
+    refined = getattr(pc, "last_refined", 0)
     calls = []
     cb = ALLREDUCE_FN(lambda user, ptr, count, stream: calls.append(count) or 0)
     pc.ctx.check(lib.rsc_ctx_set_allreduce(pc.ctx.h, C.cast(cb, C.c_void_p), None))
     try:
         pc.ctx.check(lib.rsc_cloud_set_range(pc.handle, 0, pc.size))
-        sharded, _ = R.ransac(pc, params, True, seed=5)
+        sharded, _ = R.ransac(pc, params, True, seed=5, **opts)
     finally:
         lib.rsc_ctx_set_allreduce(pc.ctx.h, None, None)
     assert len(calls) > 0
+    assert pc.last_refined == refined and (refined > 0 or "progressive" not in opts)
     assert len(plain) == len(sharded)
     for a, b in zip(plain, sharded):
         assert list(a.shape.to_cand().p) == list(b.shape.to_cand().p)
