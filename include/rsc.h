@@ -173,6 +173,15 @@ int64_t rsc_cloud_count_enabled(rsc_cloud* cloud);
  *                order (bit j%32 of word j/32 = point j): inpoints = subset[mask]. */
 int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C,
                   int32_t subset_id, int32_t* counts, uint32_t* masks);
+/* Extension: the same counts as rsc_score(cloud, params, cands, C, -1, counts, NULL) -- whole cloud,
+ * counts only -- without evaluating the pairs that cannot match.  Needs rsc_cloud_build_cells (Morton
+ * order): every 512-point tile of the Morton-ordered cloud has a bounding sphere (c, r); the distance
+ * functions of compatibles* are 1-Lipschitz in the point, so |dist(c)| > eps + r proves that no point
+ * of the tile is compatible and the (candidate, tile) pair is skipped.  The surviving pairs go through
+ * the same FP32 forms, guard band and float64 decisions as rsc_score: the counts are identical.
+ * Optional outs: (candidate, tile) pairs in total / surviving the test, CUDA-event time of the kernel. */
+int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C,
+                         int32_t* counts, int64_t* pairs_total, int64_t* pairs_survived, double* kernel_ms);
 /* device-pointer variant: d_cands/d_counts live on the context's device; enqueues on `stream`
  * (NULL = the context stream) and returns without synchronising. */
 int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,

@@ -22,6 +22,7 @@ from .fitting import (
     sample_fit,
     sample_fit_cells,
     score_counts,
+    score_counts_culled,
     scorecandidate,
     scorecandidates,
     unpack_mask,

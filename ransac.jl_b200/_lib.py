@@ -97,6 +97,8 @@ SIGNATURES = {
     "rsc_level_cumsum": (None, [_P, C.c_int32, _P]),
     "rsc_update_levelweight": (None, [_P, _P, C.c_int32]),
     "rsc_refit_extract": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), _P, C.POINTER(C.c_int64), C.c_int32]),
+    "rsc_score_culled": (C.c_int32, [_P, C.POINTER(rsc_params), _P, C.c_int32, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                     C.POINTER(C.c_double)]),
     "rsc_refit_lsq": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), C.c_double, C.POINTER(rsc_cand),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rsc_ctx_set_allreduce": (C.c_int32, [_P, _P, _P]),

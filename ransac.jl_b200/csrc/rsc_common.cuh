@@ -94,7 +94,7 @@ struct rsc_ctx {
   rsc_stats stats{};
   // scratch of the score path
   rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, pairs, wl_count, aux;
-  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf;
+  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf, cullbuf;
   size_t wl_cap = 1u << 22;  // guard-band queue capacity (groups / pairs), grows on overflow
   rsc_allreduce_fn allreduce = nullptr;  // sums int32 device buffers across the ranks of a sharded run
   void* allreduce_user = nullptr;
@@ -118,6 +118,8 @@ struct rsc_cells {
   uint32_t* inv = nullptr;       // [n] point index -> sorted position
   uint8_t* leafdepth = nullptr;  // [n] by point index: first level whose cell holds <= 8 points
   uint32_t* en_sorted = nullptr; // [n_pad/32] pc.isenabled in Morton order
+  float* msoa = nullptr;         // [6 n_pad] Morton-ordered SoA copy of the cloud (rsc_cull.cu, built on first use)
+  void* tiles = nullptr;         // [n_pad/512] float4 bounding sphere of every 512-point tile of msoa
   bool en_valid = false;         // en_sorted matches the cloud's enabled mask
   rsc::DevBuf selbuf;            // rank/select index over en_sorted
   bool sel_valid = false;

@@ -153,6 +153,8 @@ void cells_release(rsc_cloud* cloud) {
   if (c.inv) cudaFree(c.inv);
   if (c.leafdepth) cudaFree(c.leafdepth);
   if (c.en_sorted) cudaFree(c.en_sorted);
+  if (c.msoa) cudaFree(c.msoa);
+  if (c.tiles) cudaFree(c.tiles);
   c.selbuf.release();
   c = rsc_cells();
 }

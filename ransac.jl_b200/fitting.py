@@ -107,6 +107,22 @@ def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: i
     return counts, masks
 
 
+def score_counts_culled(pc: RANSACCloud, candidates: Sequence[FittedShape], params):
+    """Extension: the counts of `score_counts(pc, candidates, -1, params)` (whole cloud) without
+    evaluating the (candidate, 512-point Morton tile) pairs that provably hold no compatible point
+    (`rsc_score_culled`; needs `pc.build_cells()`).  Returns (counts, info) with info = pairs_total,
+    pairs_survived, kernel_ms."""
+    Cn = len(candidates)
+    counts = np.zeros(Cn, dtype=np.int32)
+    if Cn == 0:
+        return counts, {"pairs_total": 0, "pairs_survived": 0, "kernel_ms": 0.0}
+    arr = pack_cands(candidates)
+    cp = to_c(params)
+    tot, sur, ms = C.c_int64(), C.c_int64(), C.c_double()
+    pc.ctx.check(lib.rsc_score_culled(pc.handle, C.byref(cp), arr, Cn, counts.ctypes.data, C.byref(tot), C.byref(sur), C.byref(ms)))
+    return counts, {"pairs_total": tot.value, "pairs_survived": sur.value, "kernel_ms": ms.value}
+
+
 def unpack_mask(row: np.ndarray, M: int) -> np.ndarray:
     return np.unpackbits(row.view(np.uint8), bitorder="little")[:M].astype(bool)
 

@@ -1,0 +1,76 @@
+"""Morton-tile culling (rsc_score_culled): the counts must be the dense path's, which are the oracle's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def R():
+    import ransac_jl_b200 as R
+
+    return R
+
+
+def test_culled_counts_equal_dense_counts_on_a_noisy_scene(R):
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(91, 300_000, noise_frac=0.004, jitter_deg=1.5, outlier_frac=0.2, counts=(3, 2, 2, 2))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 1)
+    cands = scenes.perturbed_candidates(sc, 160, seed=7)
+    params = R.ransacparameters()
+    with pytest.raises(R.RscError):
+        R.score_counts_culled(pc, cands, params)  # needs the Morton order
+    pc.build_cells(9)
+    en = np.ones(pc.size, bool)
+    en[np.random.default_rng(3).random(pc.size) < 0.3] = False
+    pc.isenabled = en
+    dense, _ = R.score_counts(pc, cands, -1, params)
+    got, info = R.score_counts_culled(pc, cands, params)
+    np.testing.assert_array_equal(got, dense)
+    assert info["pairs_total"] == len(cands) * ((pc.size + 511) // 512)
+    assert 0 < info["pairs_survived"] < 0.6 * info["pairs_total"], info
+    # spheres ignore isenabled (Q4) unless the quirk is switched off: both policies agree with the dense path
+    pc.enable_all()
+    dense2, _ = R.score_counts(pc, cands, -1, params)
+    got2, _ = R.score_counts_culled(pc, cands, params)
+    np.testing.assert_array_equal(got2, dense2)
+    assert (dense2 >= dense).all() and dense2.sum() > dense.sum()
+
+
+def test_culled_counts_on_adversarial_candidates(R):
+    """non-unit axes and normals, wide / flat / needle cones, NaN / Inf / zero-axis candidates, points on axes"""
+    from ransac_jl_b200 import _lib
+    from ransac_jl_b200.shapes import from_cand
+    from tests.helpers import adversarial_case
+
+    oshapes, P, N = adversarial_case()
+    cands = []
+    for sh in oshapes:
+        c = _lib.rsc_cand(type=int(sh.kind), outwards=int(bool(sh.outwards)))
+        for i, v in enumerate(sh.params7()):
+            c.p[i] = float(v)
+        cands.append(from_cand(c))
+    pc = R.RANSACCloud(P.astype(np.float32), N.astype(np.float32), 1)
+    pc.build_cells(6)
+    params = R.ransacparameters()
+    dense, _ = R.score_counts(pc, cands, -1, params)
+    got, _ = R.score_counts_culled(pc, cands, params)
+    np.testing.assert_array_equal(got, dense)
+
+
+def test_culled_ragged_sizes_and_thresholds(R):
+    from ransac_jl_b200 import scenes
+
+    for n in (1, 511, 513, 5000):
+        sc = scenes.scene_mixed(17 + n, max(n, 64), noise_frac=0.003, jitter_deg=1.0, outlier_frac=0.1, counts=(1, 1, 1, 1))
+        V, N = sc.vertices[:n], sc.normals[:n]
+        pc = R.RANSACCloud(V, N, 1)
+        pc.build_cells(5)
+        cands = scenes.perturbed_candidates(sc, 12, seed=5)
+        for eps, alpha in ((0.3, np.deg2rad(5)), (1.5, np.deg2rad(20)), (0.01, np.deg2rad(1))):
+            params = R.ransacparameters(plane={"eps": eps, "alpha": alpha}, sphere={"eps": eps, "alpha": alpha},
+                                        cylinder={"eps": eps, "alpha": alpha}, cone={"eps": eps, "alpha": alpha})
+            dense, _ = R.score_counts(pc, cands, -1, params)
+            got, _ = R.score_counts_culled(pc, cands, params)
+            np.testing.assert_array_equal(got, dense, err_msg=f"n={n} eps={eps}")
