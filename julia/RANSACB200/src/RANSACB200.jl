@@ -190,7 +190,8 @@ function fit_batch(dc::DeviceCloud, idx::Matrix{Int}, params)
 end
 
 """
-    ransac(pc, params, setenabled; reset_rand=false, seed=1234, sampler=:root, octree_levels=8)
+    ransac(pc, params, setenabled; reset_rand=false, seed=1234, sampler=:root, octree_levels=8,
+           progressive=false, lsq=false)
 
 Drop-in for `RANSAC.ransac` when every entry of `params.iteration.shape_types` is a built-in shape:
 the whole loop of iterations.jl:35-162 runs inside one `ccall`.  Otherwise falls back to
@@ -200,9 +201,13 @@ the whole loop of iterations.jl:35-162 runs inside one `ccall`.  Otherwise falls
 samplepointcloud4!/updatelevelweight are written for -- instead of from the root cell, which is what
 the shipped package always does (levelweight/levelscore are swapped in the constructor, octree.jl:82-84).
 The final weights/scores are written back to `pc.levelweight` / `pc.levelscore` when their length fits.
+`progressive=true` (extension) refines overlapping confidence intervals on the subsets 2..r before each
+extraction test -- the "TODO: refine if best.overlap" of iterations.jl:110; `lsq=true` (extension) refits
+the best candidate by least squares to the compatible points within 3 eps before extracting it
+(docs/src/ransac.md:163-169).
 """
 function ransac(pc::RANSACCloud, params, setenabled::Bool; reset_rand=false, seed::Integer=1234, sampler::Symbol=:root,
-                octree_levels::Integer=8)
+                octree_levels::Integer=8, progressive::Bool=false, lsq::Bool=false)
     all(t -> haskey(KIND, t), params.iteration.shape_types) || return RANSAC.ransac(pc, params, setenabled; reset_rand=reset_rand)
     setenabled && fill!(pc.isenabled, true)
     dc = DeviceCloud(pc)
@@ -212,6 +217,15 @@ function ransac(pc::RANSACCloud, params, setenabled::Bool; reset_rand=false, see
         check(ccall((:rsc_cloud_build_cells, LIB[]), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
         p0 = RscParams((f === :compat_flags ? (p0.compat_flags | UInt32(2)) : getfield(p0, f) for f in fieldnames(RscParams))...)  # RSC_SAMPLER_OCTREE
     end
+    withflag(p, bit) = RscParams((f === :compat_flags ? (p.compat_flags | UInt32(bit)) : getfield(p, f) for f in fieldnames(RscParams))...)
+    if progressive   # RSC_SCORE_PROGRESSIVE: every subset must be on the device (subset 1 already is)
+        for j in 2:length(pc.subsets)
+            idx = Int64.(pc.subsets[j] .- 1)
+            check(ccall((:rsc_cloud_set_subset, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int64), dc.h, j - 1, idx, length(idx)))
+        end
+        p0 = withflag(p0, 16)
+    end
+    lsq && (p0 = withflag(p0, 8))   # RSC_REFIT_LSQ
     prm = Ref(p0)
     check(ccall((:rsc_ransac_run, LIB[]), Int32, (Ptr{Cvoid}, Ref{RscParams}, UInt64, Ref{Ptr{Cvoid}}),
                 dc.h, prm, reset_rand ? 1234 : seed, run))
