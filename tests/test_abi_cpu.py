@@ -111,3 +111,52 @@ def test_fails_loudly_without_gpu():
     with pytest.raises(R.RscError) as e:
         R.Context(0)
     assert e.value.code == R._lib.RSC_E_NODEVICE
+
+
+def test_header_flags_match_the_python_mirror():
+    import re
+
+    import ransac_jl_b200 as R
+
+    src = open(os.path.join(ROOT, "include", "rsc.h")).read()
+    defs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(RSC_[A-Z_]+)\s+\(?(-?\d+)u?\)?", src)}
+    assert defs["RSC_COMPAT_SPHERE_IGNORES_ENABLED"] == R._lib.RSC_COMPAT_SPHERE_IGNORES_ENABLED == 1
+    assert defs["RSC_SAMPLER_OCTREE"] == R._lib.RSC_SAMPLER_OCTREE == 2
+    assert defs["RSC_REFIT_LSQ"] == R._lib.RSC_REFIT_LSQ == 8
+    assert defs["RSC_SCORE_PROGRESSIVE"] == R._lib.RSC_SCORE_PROGRESSIVE == 16
+    flags = [defs[k] for k in ("RSC_COMPAT_SPHERE_IGNORES_ENABLED", "RSC_SAMPLER_OCTREE", "RSC_REFIT_LSQ", "RSC_SCORE_PROGRESSIVE")]
+    assert len(set(flags)) == 4 and all(f & (f - 1) == 0 for f in flags)  # distinct single bits
+
+
+def test_estimatescore_f64_mirror_matches_oracle():
+    import ransac_jl_b200 as R
+    from oracle import ransac_oracle as O
+
+    for M, N, s in [(5000, 10000, 1234), (312, 10000, 0), (1 << 19, 1 << 24, 40000), (3125000, 100000000, 777), (7, 9, 7)]:
+        a, b = R.estimatescore_f64(M, N, s), O.estimatescore_f64(M, N, s)
+        assert (a.min, a.max, a.E) == (b.min, b.max, b.E)
+        assert a.min <= a.E <= a.max
+
+
+def test_user_defined_shape_brings_its_own_default_parameters():
+    # fitting.jl:15 / docs/src/newprimitive.md:12-18
+    from dataclasses import dataclass
+
+    import ransac_jl_b200 as R
+
+    @dataclass
+    class Torus(R.FittedShape):
+        r: float = 1.0
+
+        @staticmethod
+        def defaultshapeparameters():
+            return {"torus": {"eps": 0.1}}
+
+    p = R.ransacparameters([R.FittedPlane, Torus])
+    assert p["torus"] == {"eps": 0.1} and "plane" in p and "sphere" not in p
+
+    class Nothing(R.FittedShape):
+        pass
+
+    with pytest.raises(TypeError):
+        R.ransacparameters([Nothing])
