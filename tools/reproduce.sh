@@ -40,3 +40,9 @@ for t in fp32_peak pipe_mix2 loop_bench loop_bench2; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Iinclude -Iransac.jl_b200/csrc -o tools/$t tools/$t.cu
   tools/$t > gpurun_out/$t.jsonl
 done
+
+# extensions (profiles/r1g_*): least-squares refit on c4, progressive + lsq sharded over 2 GPUs, culled scoring
+for l in 0 1; do RSC_TRACE=1 python tools/ransac_multi.py --scene c4 --lsq $l > gpurun_out/c4_lsq$l.json; done
+$TR --nproc-per-node 2 --master-port 29517 tools/ransac_multi.py --scene c2 --progressive 1 --lsq 1 > gpurun_out/c2_2gpu_prog_lsq.json
+python tools/cull_estimate.py --points 4194304 --tile 512 --per-type 32 --levels 12     # CPU only
+python -m pytest tests/_cull_gpu_pending.py -q && python tools/cull_bench.py > gpurun_out/cull_bench.json
