@@ -431,6 +431,40 @@ def _clamp(x):
     return min(max(x, -1.0), 1.0)
 
 
+def crossprodtensor(v) -> np.ndarray:
+    """utilities.jl:50-54."""
+    return np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+
+
+def pluscrossprod(A: np.ndarray, value, v) -> np.ndarray:
+    """pluscrossprod! (utilities.jl:32-43), in place; A is (..., 3, 3), v is (..., 3), value a scalar."""
+    A[..., 0, 1] -= value * v[..., 2]
+    A[..., 0, 2] += value * v[..., 1]
+    A[..., 1, 0] += value * v[..., 2]
+    A[..., 1, 2] -= value * v[..., 0]
+    A[..., 2, 0] -= value * v[..., 1]
+    A[..., 2, 1] += value * v[..., 0]
+    return A
+
+
+def rodrigues(nv: np.ndarray, ct: float, st: float) -> np.ndarray:
+    """rodrigues(nv, theta) (utilities.jl:6-11,19-24) for a batch of unit axes nv (n,3), given
+    cos(theta), sin(theta): nv nv' + cos (I - nv nv'), then pluscrossprod!(R, sin, nv)."""
+    outer = nv[..., :, None] * nv[..., None, :]
+    R = outer + ct * (np.eye(3) - outer)
+    return pluscrossprod(R, st, nv)
+
+
+def push2candidatesandlevels(candidates: list, candidate, levels: list, current_level) -> None:
+    """utilities.jl:473-481: a fit may return one candidate or an array of candidates."""
+    if isinstance(candidate, (list, tuple)):
+        candidates.extend(candidate)
+        levels.extend([current_level] * len(candidate))
+    else:
+        candidates.append(candidate)
+        levels.append(current_level)
+
+
 def project2cone(sh: Shape, pts):
     """cone.jl:68-85, vectorised over points; returns (dist, normal)."""
     apex, axis, opang = sh.a, sh.b, sh.s
@@ -445,15 +479,7 @@ def project2cone(sh: Shape, pts):
         th = -opang / 2
         # (Julia's cos(Inf) throws a DomainError; a non-finite opening angle is treated as NaN = matches nothing)
         ct, st = float(np.cos(th)), float(np.sin(th))
-        eye = np.eye(3)
-        outer = nv[:, :, None] * nv[:, None, :]
-        R = outer + ct * (eye[None] - outer)
-        R[:, 0, 1] -= st * nv[:, 2]
-        R[:, 0, 2] += st * nv[:, 1]
-        R[:, 1, 0] += st * nv[:, 2]
-        R[:, 1, 2] -= st * nv[:, 0]
-        R[:, 2, 0] -= st * nv[:, 1]
-        R[:, 2, 1] += st * nv[:, 0]
+        R = rodrigues(nv, ct, st)
         rv = np.stack(
             [
                 R[:, i, 0] * comp_n[:, 0] + R[:, i, 1] * comp_n[:, 1] + R[:, i, 2] * comp_n[:, 2]
@@ -1170,9 +1196,8 @@ def ransac(
                 ok, lvl, sd = sample_minimal_set_octree(pc, octree, drawN, SetStream(seed, (k - 1) * minsubsetN + i), cum, en_sorted)
                 if not ok:
                     continue
-                fitted = forcefit(pc.vertices[sd], pc.normals[sd], params)
-                cands.extend(fitted)
-                levels.extend([lvl] * len(fitted))
+                for fitted in forcefit(pc.vertices[sd], pc.normals[sd], params):  # fitting.jl:165-173
+                    push2candidatesandlevels(cands, fitted, levels, lvl)
                 continue
             else:
                 ok, _, sd = sample_minimal_set(pc, drawN, SetStream(seed, (k - 1) * minsubsetN + i), en_idx)

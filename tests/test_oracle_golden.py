@@ -124,3 +124,36 @@ def test_octree_depth_on_the_reference_grid():
         assert (a1, b1) == (0, 216) and b2 - a2 == 27 and 1 <= b3 - a3 <= 8
         assert a1 <= a2 <= a3 and b3 <= b2 <= b1  # leaf within parent within root
         assert set(oc.perm[a3:b3]) <= set(oc.perm[a2:b2])
+
+
+def test_cross_product_tensor_and_rodrigues():
+    """test/utilitytests.jl:115-133 ("cross prod"): pluscrossprod!(A, value, v) == A + value * crossprodtensor(v),
+    exactly; plus the defining properties of the rotation the cone projection builds from them"""
+    import math
+
+    rng = np.random.default_rng(0)
+    A = rng.random((3, 3))
+    val = math.radians(15)
+    vec = rng.random(3)
+    vec /= np.linalg.norm(vec)
+    assert np.array_equal(A + math.sin(val) * O.crossprodtensor(vec), O.pluscrossprod(A.copy(), math.sin(val), vec))
+    assert np.array_equal(A + O.crossprodtensor(vec), O.pluscrossprod(A.copy(), 1, vec))
+    assert np.array_equal(A, O.pluscrossprod(A.copy(), 0, vec))
+    # rodrigues (utilities.jl:6-11): a rotation about vec by val
+    R = O.rodrigues(vec[None, :], math.cos(val), math.sin(val))[0]
+    np.testing.assert_allclose(R @ R.T, np.eye(3), atol=1e-15)
+    np.testing.assert_allclose(R @ vec, vec, atol=1e-15)
+    assert abs(np.trace(R) - (1 + 2 * math.cos(val))) < 1e-15 and abs(np.linalg.det(R) - 1) < 1e-15
+    perp = np.cross(vec, [1.0, 0, 0])
+    perp /= np.linalg.norm(perp)
+    assert np.dot(np.cross(perp, R @ perp), vec) > 0  # right-handed about vec
+
+
+def test_push2candidatesandlevels():
+    """test/utilitytests.jl:135-151"""
+    fp = O.Shape(O.PLANE, np.array([0.5, 0.5, 0.5]), np.array([0.0, 0, 1]))
+    candidates, levels = [], []
+    O.push2candidatesandlevels(candidates, fp, levels, 3)
+    assert len(candidates) == 1 and len(levels) == 1
+    O.push2candidatesandlevels(candidates, [fp, fp], levels, 0)
+    assert len(candidates) == 3 and levels == [3, 0, 0]
