@@ -1003,6 +1003,19 @@ def sample_minimal_set(pc: Cloud, drawN: int, stream: SetStream, enabled_idx: Op
 # --------------------------------------------------------------------------------------
 
 
+def iswithinrectangle(vmin, vmax, p) -> bool:
+    """octree.jl:187-196: membership test of the reference's octree refinement -- "bottom/left" (the low
+    faces) is outside, "top/right" (the high faces) is inside.  (The flattened Morton octree below
+    quantises with floor(), i.e. low faces inside: points exactly on a division plane may land in the
+    neighbouring cell -- one of the reasons its sampling is an extension, not a parity claim.)"""
+    for i in range(3):
+        if not (vmin[i] < p[i]):
+            return False
+        if not (vmax[i] >= p[i]):
+            return False
+    return True
+
+
 def morton3(q: np.ndarray, D: int) -> np.ndarray:
     """interleave the D low bits of q[:,0], q[:,1], q[:,2] (x is the most significant of each triple)"""
     code = np.zeros(len(q), np.int64)

@@ -157,3 +157,18 @@ def test_push2candidatesandlevels():
     assert len(candidates) == 1 and len(levels) == 1
     O.push2candidatesandlevels(candidates, [fp, fp], levels, 0)
     assert len(candidates) == 3 and levels == [3, 0, 0]
+
+
+def test_iswithinrectangle():
+    """test/octree.jl:10-114 on the unit box: corner points, edge / face midpoints, inside and outside points"""
+    lo, hi = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+    inside = [(1, 1, 1), (1, .5, 1), (.5, 1, 1), (1, 1, .5), (.5, .5, 1), (.5, 1, .5), (1, .5, .5),
+              (.5, .5, .1), (.5, .1, .5), (.1, .5, .5), (.5, .5, .9), (.5, .9, .5), (.9, .5, .5)]
+    outside = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (0, 1, 1),
+               (.5, 0, 0), (.5, 0, 1), (0, .5, 0), (0, .5, 1), (1, .5, 0), (.5, 1, 0), (1, 0, .5), (0, 0, .5), (0, 1, .5),
+               (.5, .5, 0), (.5, 0, .5), (0, .5, .5),
+               (.5, .5, -.1), (.5, -.1, .5), (-.1, .5, .5), (.5, .5, 1.1), (.5, 1.1, .5), (1.1, .5, .5)]
+    for p in inside:
+        assert O.iswithinrectangle(lo, hi, p) is True, p
+    for p in outside:
+        assert O.iswithinrectangle(lo, hi, p) is False, p
