@@ -1003,6 +1003,21 @@ def sample_minimal_set(pc: Cloud, drawN: int, stream: SetStream, enabled_idx: Op
 # --------------------------------------------------------------------------------------
 
 
+def findAABB(points):
+    """utilities.jl:125-136: axis-aligned bounding box (min corner, max corner) of a point list; the
+    octree's root box (octree.jl:239).  NaN coordinates never replace a bound, like the reference's
+    `>` / `<` comparisons."""
+    P = np.asarray(points, dtype=F)
+    mn, mx = P[0].copy(), P[0].copy()
+    for j in range(P.shape[1]):
+        col = P[:, j]
+        col = col[col == col]
+        if len(col):
+            mn[j] = min(mn[j], col.min()) if mn[j] == mn[j] else mn[j]
+            mx[j] = max(mx[j], col.max()) if mx[j] == mx[j] else mx[j]
+    return mn, mx
+
+
 def iswithinrectangle(vmin, vmax, p) -> bool:
     """octree.jl:187-196: membership test of the reference's octree refinement -- "bottom/left" (the low
     faces) is outside, "top/right" (the high faces) is inside.  (The flattened Morton octree below
@@ -1030,7 +1045,7 @@ class MortonOctree:
         V = np.asarray(vertices, dtype=F)
         self.nlevels = nlevels
         D = self.D = nlevels - 1
-        lo, hi = V.min(0), V.max(0)
+        lo, hi = findAABB(V)  # octree.jl:239
         w = hi - lo
         w[w == 0] = 1.0
         q = np.floor((V - lo) / w * float(1 << D)).astype(np.int64)

@@ -172,3 +172,12 @@ def test_iswithinrectangle():
         assert O.iswithinrectangle(lo, hi, p) is True, p
     for p in outside:
         assert O.iswithinrectangle(lo, hi, p) is False, p
+
+
+def test_findAABB():
+    """test/utilitytests.jl:5-27: 30 random points in the unit cube/square plus the two extreme corners"""
+    rng = np.random.default_rng(1)
+    for dim in (3, 2):
+        pts = list(rng.random((30, dim))) + [np.full(dim, -1.0), np.full(dim, 2.0)]
+        mn, mx = O.findAABB(pts)
+        assert np.array_equal(mn, np.full(dim, -1.0)) and np.array_equal(mx, np.full(dim, 2.0))
