@@ -38,6 +38,7 @@ from .params import (
     defaultparameters,
     defaultshapeparameters,
     ransacparameters,
+    setfloattype,
     to_c,
 )
 from .shapes import (

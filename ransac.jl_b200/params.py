@@ -85,6 +85,23 @@ def ransacparameters(p=None, **kwargs) -> dict:
     return new
 
 
+def setfloattype(nt: dict, T) -> dict:
+    """setfloattype(nt, T) (utilities.jl:488-504): convert every real, non-integer number of a nested
+    parameter dict to the float type `T` (np.float32 / np.float64 / float); integers, strings and
+    everything else pass through.  Used with `RANSACCloud(...; force_eltype=T)`."""
+    import numbers
+
+    out = {}
+    for k, v in nt.items():
+        if isinstance(v, dict):
+            out[k] = setfloattype(v, T)
+        elif isinstance(v, numbers.Real) and not isinstance(v, (numbers.Integral, bool)):
+            out[k] = T(v)
+        else:
+            out[k] = v
+    return out
+
+
 def to_c(params: dict, compat_flags: Optional[int] = None) -> _lib.rsc_params:
     """Flatten the nested parameters into the C-ABI POD (include/rsc.h, rsc_params)."""
     c = _lib.rsc_params()

@@ -160,3 +160,27 @@ def test_user_defined_shape_brings_its_own_default_parameters():
 
     with pytest.raises(TypeError):
         R.ransacparameters([Nothing])
+
+
+def test_setfloattype():
+    # test/utilitytests.jl:153-189
+    import ransac_jl_b200 as R
+
+    nta = {"alpha": 1.0, "somepar": "key1", "intpar": 1}
+    ntb = {"alpha": 1, "otherpar": np.float32(0.145), "str": "str"}
+    nt = {"alpha": 9, "eps": 0.1, "gamma": np.float32(0.01), "shapea": nta, "shapeb": ntb}
+    f32 = R.setfloattype(nt, np.float32)
+    assert f32["alpha"] == 9 and isinstance(f32["alpha"], int)
+    assert isinstance(f32["eps"], np.float32) and np.isclose(f32["eps"], np.float32(0.1))
+    assert isinstance(f32["gamma"], np.float32) and np.isclose(f32["gamma"], np.float32(0.01))
+    assert isinstance(f32["shapea"]["alpha"], np.float32) and f32["shapea"]["somepar"] == "key1"
+    assert f32["shapea"]["intpar"] == 1 and isinstance(f32["shapea"]["intpar"], int)
+    assert f32["shapeb"]["alpha"] == 1 and isinstance(f32["shapeb"]["alpha"], int)
+    assert isinstance(f32["shapeb"]["otherpar"], np.float32) and f32["shapeb"]["str"] == "str"
+    f64 = R.setfloattype(f32, np.float64)
+    rt = float(np.sqrt(np.finfo(np.float32).eps))
+    assert f64["alpha"] == 9 and isinstance(f64["eps"], np.float64) and np.isclose(f64["eps"], 0.1, rtol=rt)
+    assert isinstance(f64["gamma"], np.float64) and np.isclose(f64["gamma"], 0.01, rtol=rt)
+    assert isinstance(f64["shapea"]["alpha"], np.float64) and f64["shapea"]["intpar"] == 1
+    assert isinstance(f64["shapeb"]["otherpar"], np.float64) and np.isclose(f64["shapeb"]["otherpar"], 0.145, rtol=rt)
+    assert f64["shapeb"]["str"] == "str"
