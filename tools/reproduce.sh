@@ -45,4 +45,4 @@ done
 for l in 0 1; do RSC_TRACE=1 python tools/ransac_multi.py --scene c4 --lsq $l > gpurun_out/c4_lsq$l.json; done
 $TR --nproc-per-node 2 --master-port 29517 tools/ransac_multi.py --scene c2 --progressive 1 --lsq 1 > gpurun_out/c2_2gpu_prog_lsq.json
 python tools/cull_estimate.py --points 4194304 --tile 512 --per-type 32 --levels 12     # CPU only
-python -m pytest tests/_cull_gpu_pending.py -q && python tools/cull_bench.py > gpurun_out/cull_bench.json
+python -m pytest tests/test_cull_gpu.py -q && python tools/cull_bench.py > gpurun_out/cull_bench.json
