@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cands", type=int, default=4096)
     ap.add_argument("--cpu-sample", type=int, default=0, help="override the CPU sample (points)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cull", action="store_true", help="skip the informational culled-scoring leg")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--ransac", default="c4", choices=["none", "c2", "c4"],
                     help="also time end-to-end ransac() on this scene (single GPU, extra JSON key); c4 = the "
@@ -403,9 +404,33 @@ def main():
     if not args.no_cpu and world == 1:
         # ~10 s of CPU work: 512 candidates (every 8th) x all points of rank 0's shard of the same workload
         out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or len(sc.vertices), ncand=512)
+    # informational, last (nothing measured above depends on it): the same counts through Morton-tile culling
+    # (rsc_score_culled).  Never the headline: the reference evaluates every pair.
+    if world == 1 and not args.no_cull:
+        try:
+            out["culled_variant"] = time_culled_variant(R, pc, cands, params)
+        except Exception as e:
+            out["culled_variant"] = {"error": repr(e)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_culled_variant(R, pc, cands, params, reps=3):
+    """rsc_score_culled on the resident cloud of the headline workload; counts checked against the dense path."""
+    pc.build_cells(11)
+    dense, _ = R.score_counts(pc, cands, -1, params)
+    got, info = R.score_counts_culled(pc, cands, params)  # builds the Morton copy + tile spheres
+    ms = []
+    for _ in range(reps):
+        got, info = R.score_counts_culled(pc, cands, params)
+        ms.append(info["kernel_ms"])
+    evals = len(cands) * pc.size
+    return {"kernel": "rsc::cull_score_kernel", "kernel_ms": min(ms), "equal_counts": bool(np.array_equal(got, dense)),
+            "pairs_total": info["pairs_total"], "pairs_survived": info["pairs_survived"],
+            "surviving_fraction": info["pairs_survived"] / max(1, info["pairs_total"]),
+            "G_evals_s_reference_equivalent": evals / (min(ms) * 1e-3) / 1e9,
+            "note": "skips (candidate, 512-point Morton tile) pairs that provably hold no compatible point; same counts"}
 
 
 def time_masks_variant(R, lib, C, torch, sc, cands, params, local, dev, npts=4 << 20):
