@@ -13,9 +13,11 @@
 // (the candidate's compiled FP32 record, one 48-byte load) and stages the survivors' records in shared
 // memory; NARROW PHASE: all threads loop over the survivors (warp-uniform), evaluate their 4 points
 // with the same eval<T>() forms and guard band as the dense kernel, decide in-band pairs in FP64 in the
-// reference's operation order on the spot (rsc_exact.cuh), and add the warp's count with one REDUX + atomic.
+// reference's operation order -- queued through a per-CTA staging buffer for cull_fix_kernel, one thread per
+// pair (rsc_exact.cuh) -- and add the warp's count with one REDUX + atomic.
 // Counts only (masks would come out in Morton order), whole cloud only.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -42,7 +44,13 @@ struct CullArgs {
   int32_t* cv;  // [C] compatible real points
   int32_t* ce;  // [C] compatible enabled points
   unsigned long long* stats;  // [0] surviving (candidate, tile) pairs, [1] pairs decided in FP64
+  uint2* queue;               // in-band pairs (candidate, Morton position) waiting for their float64 decision
+  uint32_t qcap;
+  uint32_t* qn;               // entries appended (may exceed qcap: the excess was decided inline)
+  int inline_fp64;            // != 0: no queue, every in-band pair is decided on the spot (RSC_CULL_INLINE=1)
 };
+
+constexpr int kCullSQ = 1024;  // per-CTA staging of queued pairs (one global atomic per flush, not per pair)
 
 __global__ void cull_compile_kernel(const rsc_cand* __restrict__ cands, int C, Thresh th, float pmax, float nmax,
                                     float* __restrict__ rec, uint8_t* __restrict__ col) {
@@ -150,9 +158,33 @@ struct CullPoints {
   uint32_t valid, enabled;  // bit q: point q of this thread
 };
 
+// the FP64 decision of one in-band pair; kept out of line so that its registers (and code) do not
+// weigh on the FP32 loop -- the kernel's occupancy is set by the narrow phase, not by this path
+__device__ __noinline__ uint32_t cull_exact(const rsc_cand* __restrict__ cp, const double* __restrict__ trig, const Thresh* th,
+                                            float px, float py, float pz, float nx, float ny, float nz) {
+  const rsc_cand c = *cp;
+  const ex::ConeTrig tr = {trig[0], trig[1]};
+  const ex::V3 p = {(double)px, (double)py, (double)pz};
+  const ex::V3 n = {(double)nx, (double)ny, (double)nz};
+  return ex::compat(c, tr, *th, p, n) ? 1u : 0u;
+}
+
+// float64 decision of one queued pair, added to the counts (the FP32 pass counted nothing for it)
+__device__ __forceinline__ void cull_fix_one(const CullArgs& a, uint2 e) {
+  const uint32_t cand = e.x;
+  const int64_t j = (int64_t)e.y;
+  const float* X = a.msoa;
+  const uint32_t ok = cull_exact(a.cands + cand, a.trig + 2 * cand, &a.th, X[j], X[a.n_pad + j], X[2 * a.n_pad + j], X[3 * a.n_pad + j],
+                                 X[4 * a.n_pad + j], X[5 * a.n_pad + j]);
+  if (ok) {
+    atomicAdd(a.cv + cand, 1);
+    if ((a.en[j >> 5] >> (j & 31)) & 1u) atomicAdd(a.ce + cand, 1);
+  }
+}
+
 template <int T>
 __device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __restrict__ sr, int cand, const CullPoints& P, int& cv,
-                                            int& ce, int& nexact) {
+                                            int& ce, int& nexact, uint32_t jbase, uint2* sq, uint32_t* sqn) {
   float r[RecN<T>::n];
 #pragma unroll
   for (int i = 0; i < RecN<T>::n; ++i) r[i] = sr[i];
@@ -170,27 +202,48 @@ __device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __re
     amb |= (sure ? 0u : 1u) << q;
   }
   amb &= P.valid;  // padding points count for nothing
-  if (amb) {       // inside the FP32 guard band: the reference's float64 decision
-    const rsc_cand c = a.cands[cand];
-    const ex::ConeTrig tr = {a.trig[2 * cand], a.trig[2 * cand + 1]};
+  if (amb) {       // inside the FP32 guard band: queued for the reference's float64 decision
 #pragma unroll
     for (int q = 0; q < kCullPts; ++q)
       if ((amb >> q) & 1u) {
-        const ex::V3 p = {(double)P.px[q], (double)P.py[q], (double)P.pz[q]};
-        const ex::V3 n = {(double)P.nx[q], (double)P.ny[q], (double)P.nz[q]};
-        const uint32_t ok = ex::compat(c, tr, a.th, p, n) ? 1u : 0u;
-        cv += (int)ok;
-        ce += (int)(ok & (P.enabled >> q));
-        ++nexact;
+        const uint32_t slot = a.inline_fp64 ? (uint32_t)kCullSQ : atomicAdd(sqn, 1u);
+        if (slot < (uint32_t)kCullSQ) {
+          sq[slot] = make_uint2((uint32_t)cand, jbase + (uint32_t)(q * kCullThreads));
+        } else {  // staging full (e.g. a needle cone: every pair is in-band): decide on the spot
+          const uint32_t ok = cull_exact(a.cands + cand, a.trig + 2 * cand, &a.th, P.px[q], P.py[q], P.pz[q], P.nx[q], P.ny[q], P.nz[q]);
+          cv += (int)ok;
+          ce += (int)(ok & (P.enabled >> q));
+          ++nexact;
+        }
       }
   }
 }
 
-__global__ void __launch_bounds__(kCullThreads) cull_score_kernel(const __grid_constant__ CullArgs a) {
+__global__ void __launch_bounds__(kCullThreads, 4) cull_score_kernel(const __grid_constant__ CullArgs a) {
   __shared__ __align__(16) float srec[kCullThreads][kRecFields];
   __shared__ uint8_t scol[kCullThreads];
   __shared__ uint32_t surv[kCullThreads / 32];
+  __shared__ uint2 sq[kCullSQ];
+  __shared__ uint32_t sqn, sbase;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) sqn = 0;
+  __syncthreads();
+  // append the staged pairs to the global queue (entries beyond its capacity are decided here)
+  auto flush = [&]() {
+    const uint32_t cnt = sqn < (uint32_t)kCullSQ ? sqn : (uint32_t)kCullSQ;
+    if (tid == 0) sbase = atomicAdd(a.qn, cnt);
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += kCullThreads) {
+      const uint32_t g = sbase + i;
+      if (g < a.qcap)
+        a.queue[g] = sq[i];
+      else
+        cull_fix_one(a, sq[i]);
+    }
+    __syncthreads();
+    if (tid == 0) sqn = 0;
+    __syncthreads();
+  };
   unsigned long long n_surv = 0;
   int n_exact = 0;
   const float* X = a.msoa;
@@ -208,6 +261,7 @@ __global__ void __launch_bounds__(kCullThreads) cull_score_kernel(const __grid_c
     }
     P.enabled &= P.valid;
     const float4 ts = a.tiles[tile];
+    const uint32_t jbase = (uint32_t)(base + tid);
     for (int c0 = 0; c0 < a.C; c0 += kCullThreads) {
       // ---- broad phase: one candidate per thread against the tile sphere ----
       const int ci = c0 + tid;
@@ -242,19 +296,19 @@ __global__ void __launch_bounds__(kCullThreads) cull_score_kernel(const __grid_c
           int cv = 0, ce = 0;
           switch (scol[s]) {
             case RSC_PLANE:
-              cull_narrow<RSC_PLANE>(a, srec[s], cand, P, cv, ce, n_exact);
+              cull_narrow<RSC_PLANE>(a, srec[s], cand, P, cv, ce, n_exact, jbase, sq, &sqn);
               break;
             case RSC_SPHERE:
-              cull_narrow<RSC_SPHERE>(a, srec[s], cand, P, cv, ce, n_exact);
+              cull_narrow<RSC_SPHERE>(a, srec[s], cand, P, cv, ce, n_exact, jbase, sq, &sqn);
               break;
             case RSC_CYLINDER:
-              cull_narrow<RSC_CYLINDER>(a, srec[s], cand, P, cv, ce, n_exact);
+              cull_narrow<RSC_CYLINDER>(a, srec[s], cand, P, cv, ce, n_exact, jbase, sq, &sqn);
               break;
             case kConeWide:
-              cull_narrow<kConeWide>(a, srec[s], cand, P, cv, ce, n_exact);
+              cull_narrow<kConeWide>(a, srec[s], cand, P, cv, ce, n_exact, jbase, sq, &sqn);
               break;
             default:
-              cull_narrow<RSC_CONE>(a, srec[s], cand, P, cv, ce, n_exact);
+              cull_narrow<RSC_CONE>(a, srec[s], cand, P, cv, ce, n_exact, jbase, sq, &sqn);
               break;
           }
           cv = __reduce_add_sync(0xffffffffu, cv);
@@ -266,11 +320,20 @@ __global__ void __launch_bounds__(kCullThreads) cull_score_kernel(const __grid_c
         }
       }
       __syncthreads();  // the next chunk overwrites srec / surv
+      if (sqn > (uint32_t)kCullSQ / 2) flush();  // uniform: every thread reads the same sqn after the barrier
     }
   }
+  if (sqn) flush();
   n_exact = __reduce_add_sync(0xffffffffu, n_exact);
   if (lane == 0 && n_exact) atomicAdd(a.stats + 1, (unsigned long long)n_exact);
   if (tid == 0 && n_surv) atomicAdd(a.stats, n_surv);
+}
+
+// float64 decisions of the queued pairs: one thread per pair, all lanes busy
+__global__ void __launch_bounds__(256) cull_fix_kernel(const __grid_constant__ CullArgs a) {
+  const uint32_t n = *a.qn < a.qcap ? *a.qn : a.qcap;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cull_fix_one(a, a.queue[i]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.stats + 1, (unsigned long long)*a.qn);
 }
 
 __global__ void cull_policy_kernel(const rsc_cand* __restrict__ cands, int C, const int32_t* __restrict__ cv,
@@ -335,8 +398,11 @@ extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, 
   const size_t o_cv = o_rec + (size_t)C * kRecFields * sizeof(float);
   const size_t o_stats = o_cv + (size_t)3 * C * sizeof(int32_t);
   const size_t o_stats_al = (o_stats + 15) / 16 * 16;
-  const size_t o_col = o_stats_al + 16;
-  RSC_CUDA(ctx, ctx->cullbuf.ensure(o_col + (size_t)C));
+  const size_t o_col = o_stats_al + 32;  // stats[2], qn
+  int64_t qcap = (int64_t)C * cloud->n / 4096;
+  qcap = qcap < (1 << 16) ? (1 << 16) : qcap > (8 << 20) ? (8 << 20) : qcap;
+  const size_t o_queue = (o_col + (size_t)C + 15) / 16 * 16;
+  RSC_CUDA(ctx, ctx->cullbuf.ensure(o_queue + (size_t)qcap * sizeof(uint2)));
   char* b = ctx->cullbuf.as<char>();
   rsc_cand* d_c = reinterpret_cast<rsc_cand*>(b);
   double* d_trig = reinterpret_cast<double*>(b + o_trig);
@@ -347,7 +413,7 @@ extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, 
   RSC_CUDA(ctx, cudaMemcpyAsync(d_c, cands, (size_t)C * sizeof(rsc_cand), cudaMemcpyHostToDevice, st));
   RSC_CUDA(ctx, cudaMemcpyAsync(d_trig, trig.data(), (size_t)2 * C * sizeof(double), cudaMemcpyHostToDevice, st));
   RSC_CUDA(ctx, cudaMemsetAsync(d_cv, 0, (size_t)3 * C * sizeof(int32_t), st));
-  RSC_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, st));
+  RSC_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 32, st));
   cull_compile_kernel<<<(C + 127) / 128, 128, 0, st>>>(d_c, C, th, cloud->pmax, cloud->nmax, d_rec, d_col);
   RSC_CUDA(ctx, cudaGetLastError());
   CullArgs a;
@@ -361,9 +427,17 @@ extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, 
   a.C = C;
   a.cv = d_cv, a.ce = d_cv + C;
   a.stats = d_stats;
+  a.qn = reinterpret_cast<uint32_t*>(d_stats + 2);
+  a.queue = reinterpret_cast<uint2*>(b + o_queue);
+  a.qcap = (uint32_t)qcap;
+  // in-band pairs: decided on the spot (default, the variant validated on the GPU first) or queued for
+  // cull_fix_kernel (RSC_CULL_INLINE=0)
+  a.inline_fp64 = getenv("RSC_CULL_INLINE") ? atoi(getenv("RSC_CULL_INLINE")) : 1;
   const int grid = a.ntiles < ctx->sm_count * 8 ? a.ntiles : ctx->sm_count * 8;
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
   cull_score_kernel<<<grid, kCullThreads, 0, st>>>(a);
+  RSC_CUDA(ctx, cudaGetLastError());
+  cull_fix_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk1, st));
   cull_policy_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_c, C, a.cv, a.ce, th.honour_enabled, d_cv + 2 * (size_t)C);
