@@ -430,9 +430,9 @@ extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, 
   a.qn = reinterpret_cast<uint32_t*>(d_stats + 2);
   a.queue = reinterpret_cast<uint2*>(b + o_queue);
   a.qcap = (uint32_t)qcap;
-  // in-band pairs: decided on the spot (default, the variant validated on the GPU first) or queued for
-  // cull_fix_kernel (RSC_CULL_INLINE=0)
-  a.inline_fp64 = getenv("RSC_CULL_INLINE") ? atoi(getenv("RSC_CULL_INLINE")) : 1;
+  // in-band pairs: queued for cull_fix_kernel (default; 12.2 ms on c3) or decided on the spot
+  // (RSC_CULL_INLINE=1; 13.5 ms) -- both validated against the dense path (tests/test_cull_gpu.py)
+  a.inline_fp64 = getenv("RSC_CULL_INLINE") ? atoi(getenv("RSC_CULL_INLINE")) : 0;
   const int grid = a.ntiles < ctx->sm_count * 8 ? a.ntiles : ctx->sm_count * 8;
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
   cull_score_kernel<<<grid, kCullThreads, 0, st>>>(a);
