@@ -159,6 +159,24 @@ function refit_extract!(dc::DeviceCloud, s::FittedShape, params; disable::Bool=t
 end
 
 """
+Extension: whole-cloud inlier counts of `cands` -- the counts `scorecandidate` would give on the whole
+cloud -- skipping the (candidate, 512-point Morton tile) pairs that provably hold no compatible point
+(`rsc_score_culled`).  Builds the Morton order on first use.  Returns `(counts, pairs_total, pairs_survived)`.
+"""
+function score_culled(dc::DeviceCloud, cands::Vector{<:FittedShape}, params; octree_levels::Integer=11)
+    check(ccall((:rsc_cloud_cells_levels, LIB[]), Int32, (Ptr{Cvoid},), dc.h) > 0 ? Int32(0) :
+          ccall((:rsc_cloud_build_cells, LIB[]), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
+    prm = Ref(toparams(params))
+    arr = [tocand(c) for c in cands]
+    counts = Vector{Int32}(undef, length(arr))
+    tot = Ref{Int64}(0); sur = Ref{Int64}(0); ms = Ref{Float64}(0.0)
+    check(ccall((:rsc_score_culled, LIB[]), Int32,
+                (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Ptr{Int32}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
+                dc.h, prm, arr, length(arr), counts, tot, sur, ms))
+    Int.(counts), tot[], sur[]
+end
+
+"""
 Extension: least-squares refit of `s` to the enabled points compatible with it inside `band` * eps (the
 paper's refit, which RANSAC.jl leaves out: docs/src/ransac.md:163-169).  Returns
 `(refined shape, points used, rms distance)`; follow it with `refit_extract!`.

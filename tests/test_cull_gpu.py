@@ -1,4 +1,6 @@
-"""Morton-tile culling (rsc_score_culled): the counts must be the dense path's, which are the oracle's."""
+"""Morton-tile culling (rsc_score_culled): the counts must be the dense path's, which are the oracle's.
+Both ways of deciding the in-band pairs are covered: queued for cull_fix_kernel (default) and inline
+(RSC_CULL_INLINE=1, read by the library on every call)."""
 import numpy as np
 import pytest
 
@@ -12,8 +14,11 @@ def R():
     return R
 
 
-def test_culled_counts_equal_dense_counts_on_a_noisy_scene(R):
+@pytest.mark.parametrize("inline", ["0", "1"], ids=["queued", "inline"])
+def test_culled_counts_equal_dense_counts_on_a_noisy_scene(R, monkeypatch, inline):
     from ransac_jl_b200 import scenes
+
+    monkeypatch.setenv("RSC_CULL_INLINE", inline)
 
     sc = scenes.scene_mixed(91, 300_000, noise_frac=0.004, jitter_deg=1.5, outlier_frac=0.2, counts=(3, 2, 2, 2))
     pc = R.RANSACCloud(sc.vertices, sc.normals, 1)
@@ -38,12 +43,14 @@ def test_culled_counts_equal_dense_counts_on_a_noisy_scene(R):
     assert (dense2 >= dense).all() and dense2.sum() > dense.sum()
 
 
-def test_culled_counts_on_adversarial_candidates(R):
+@pytest.mark.parametrize("inline", ["0", "1"], ids=["queued", "inline"])
+def test_culled_counts_on_adversarial_candidates(R, monkeypatch, inline):
     """non-unit axes and normals, wide / flat / needle cones, NaN / Inf / zero-axis candidates, points on axes"""
     from ransac_jl_b200 import _lib
     from ransac_jl_b200.shapes import from_cand
     from tests.helpers import adversarial_case
 
+    monkeypatch.setenv("RSC_CULL_INLINE", inline)
     oshapes, P, N = adversarial_case()
     cands = []
     for sh in oshapes:
