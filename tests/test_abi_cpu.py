@@ -184,3 +184,31 @@ def test_setfloattype():
     assert isinstance(f64["shapea"]["alpha"], np.float64) and f64["shapea"]["intpar"] == 1
     assert isinstance(f64["shapeb"]["otherpar"], np.float64) and np.isclose(f64["shapeb"]["otherpar"], 0.145, rtol=rt)
     assert f64["shapeb"]["str"] == "str"
+
+
+def test_null_handles_are_rejected_without_touching_the_device():
+    """every entry point that takes a cloud/context/run returns an error (or a neutral value) for NULL:
+    no exception or crash crosses the boundary, and none of this needs a GPU"""
+    import ransac_jl_b200 as R
+
+    L = R._lib.lib
+    p = R._lib.rsc_params()
+    L.rsc_params_default(p)
+    cand = R._lib.rsc_cand()
+    n64, dbl = C.c_int64(), C.c_double()
+    E_ARG = -1
+    assert L.rsc_score(None, C.byref(p), None, 0, -1, None, None) == E_ARG
+    assert L.rsc_score_culled(None, C.byref(p), None, 0, None, None, None, None) == E_ARG
+    assert L.rsc_refit_extract(None, C.byref(p), C.byref(cand), None, C.byref(n64), 0) == E_ARG
+    assert L.rsc_refit_lsq(None, C.byref(p), C.byref(cand), 3.0, C.byref(cand), C.byref(n64), C.byref(dbl)) == E_ARG
+    assert L.rsc_cloud_build_cells(None, 8) == E_ARG
+    assert L.rsc_cloud_set_subset(None, 0, None, 0) == E_ARG
+    assert L.rsc_cloud_enable_all(None) == E_ARG
+    run = C.c_void_p()
+    assert L.rsc_ransac_run(None, C.byref(p), 1, C.byref(run)) == E_ARG and not run.value
+    assert L.rsc_run_nshapes(None) == 0 and L.rsc_run_iterations(None) == 0 and L.rsc_run_refined(None) == 0
+    assert L.rsc_cloud_size(None) == 0 and L.rsc_cloud_count_enabled(None) == -1
+    L.rsc_cloud_destroy(None)
+    L.rsc_ctx_destroy(None)
+    L.rsc_run_destroy(None)
+    assert L.rsc_last_error(None) is not None
