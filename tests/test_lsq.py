@@ -181,3 +181,48 @@ def test_device_loop_with_lsq_matches_oracle():
     for a, b in zip(host, extracted):
         np.testing.assert_allclose(np.array(a.shape.to_cand().p[:7]), np.array(b.shape.to_cand().p[:7]), rtol=1e-12, atol=1e-300)
         np.testing.assert_array_equal(a.inpoints, b.inpoints)
+
+
+def test_oracle_lsq_random_poses():
+    """random spheres and cylinders, noisy samples of a partial surface, perturbed starts: the refit lands on
+    the true parameters and never increases the rms distance of its point set"""
+    rng = np.random.default_rng(42)
+    P = O.default_parameters()
+    for trial in range(12):
+        n = 1500
+        if trial % 2 == 0:
+            c, R0 = rng.uniform(-20, 20, 3), rng.uniform(2, 15)
+            d = rng.normal(size=(n, 3))
+            d[:, 2] = np.abs(d[:, 2])  # half sphere
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            V = c + (R0 + rng.normal(0, 0.02, n))[:, None] * d
+            N = d
+            start = O.Shape(O.SPHERE, c + rng.normal(0, 0.05, 3), np.zeros(3), R0 + 0.05, True)
+        else:
+            ax = _unit(rng.normal(size=3))
+            e1 = _unit(np.cross(ax, [0.3, 0.5, 0.8]))
+            e2 = np.cross(ax, e1)
+            c = rng.uniform(-10, 10, 3)
+            c = c - ax * (ax @ c)
+            R0 = rng.uniform(1, 6)
+            th = rng.uniform(0, 1.5 * np.pi, n)  # three quarters of the circumference
+            rd = np.cos(th)[:, None] * e1 + np.sin(th)[:, None] * e2
+            V = c + rng.uniform(-8, 8, n)[:, None] * ax + (R0 + rng.normal(0, 0.02, n))[:, None] * rd
+            N = rd
+            a1 = _unit(ax + rng.normal(0, 0.004, 3))
+            c1 = c + rng.normal(0, 0.03, 3)
+            start = O.Shape(O.CYLINDER, a1, c1 - a1 * (a1 @ c1), R0 + 0.04, True)
+        V = V.astype(np.float32).astype(np.float64)
+        pc = O.Cloud(V, N, [np.arange(n)])
+        sel = O.lsq_select(start, pc, P)
+        x0 = O.lsq_normalise(start.kind, O.lsq_pack(start))
+        cost0 = O.lsq_accumulate(start.kind, x0, V[sel])[2]
+        ref, used, rms = O.lsq_refine(start, pc, P)
+        assert used == len(sel) > 1000
+        assert rms <= math.sqrt(cost0 / used) + 1e-12
+        assert 0.015 < rms < 0.03, (trial, rms)
+        assert abs(ref.s - R0) < 0.01, (trial, ref.s, R0)
+        if start.kind == O.SPHERE:
+            assert np.abs(ref.a - c).max() < 0.02
+        else:
+            assert abs(ref.a @ ax) > 1 - 1e-5 and np.abs(ref.b - c).max() < 0.03 and abs(ref.a @ ref.b) < 1e-10
