@@ -5,7 +5,6 @@ reference (Q9) is reproduced by the shipped library, not re-derived in Python.""
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
 
 from . import _lib
 

@@ -7,7 +7,7 @@ them into the `rsc_params` POD that crosses the C ABI.
 from __future__ import annotations
 
 import math
-from typing import Optional, Sequence
+from typing import Optional
 
 from . import _lib
 from .shapes import FittedCone, FittedCylinder, FittedPlane, FittedSphere, SHAPE_KIND

@@ -3,8 +3,8 @@
 (src/fitting.jl:81-84), with the conversion to/from the 64-byte C-ABI candidate record."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import List, Sequence
+from dataclasses import dataclass
+from typing import Sequence
 
 import numpy as np
 
