@@ -108,3 +108,63 @@ def fit_points(P, N, op):
     m = lib.orc_fit_points(P.ctypes.data_as(C.c_void_p), N.ctypes.data_as(C.c_void_p), C.c_int(S), C.c_int(k), C.byref(prm), out,
                            out_set.ctypes.data_as(C.c_void_p))
     return [(out[i].type, bool(out[i].outwards), np.array(out[i].p[:])) for i in range(m)], out_set[:m].copy()
+
+
+class orc_iter(C.Structure):
+    _fields_ = [("drawN", C.c_int32), ("minsubsetN", C.c_int32), ("itermax", C.c_int32), ("extract_s", C.c_int32),
+                ("terminate_s", C.c_int32), ("reserved", C.c_int32), ("tau", C.c_int64), ("prob_det", C.c_double)]
+
+
+_S = {"lengthC": 0, "allcand": 1, "nofminset": 2}
+
+
+def estimate_score(s1len: int, plen: int, sigma: int):
+    """estimatescore (confidenceintervals.jl:53-74) with Int64 wrap-around -> (min, max, E)"""
+    lib = _load()
+    a, b, e = C.c_double(), C.c_double(), C.c_double()
+    lib.orc_estimate_score(C.c_int64(s1len), C.c_int64(plen), C.c_int64(sigma), C.byref(a), C.byref(b), C.byref(e))
+    return a.value, b.value, e.value
+
+
+def ransac(P, N, subset1, op, seed, enabled=None, nthreads=0):
+    """The whole loop (iterations.jl:35-162) in C on the Philox minimal sets of the NumPy oracle.
+
+    P, N: (n, 3) float64; subset1: pc.subsets[0] (0-based global indices); enabled: bool (n,) or None
+    (= ransac(pc, params, true)).  Returns (shapes, enabled_after, info): shapes = list of
+    (type, outwards, p[7], inpoints int64 ascending), info = dict(iterations, cands_scored, evals,
+    extracted_at, seconds=(sample+fit, score, refit+bookkeeping), threads)."""
+    lib = _load()
+    lib.orc_ransac.restype = C.c_void_p
+    lib.orc_run_shape.restype = C.c_int64
+    lib.orc_run_cands_scored.restype = C.c_int64
+    lib.orc_run_evals.restype = C.c_int64
+    P = np.ascontiguousarray(P, dtype=np.float64)
+    N = np.ascontiguousarray(N, dtype=np.float64)
+    sub = np.ascontiguousarray(subset1, dtype=np.int64)
+    n = len(P)
+    en = np.ones(n, np.uint8) if enabled is None else np.ascontiguousarray(enabled, dtype=np.uint8).copy()
+    prm = to_params(op)
+    i = op["iteration"]
+    it = orc_iter(int(i["drawN"]), int(i["minsubsetN"]), int(i["itermax"]), _S[i["extract_s"]], _S[i["terminate_s"]], 0,
+                  int(i["tau"]), float(i["prob_det"]))
+    run = C.c_void_p(lib.orc_ransac(P.ctypes.data_as(C.c_void_p), N.ctypes.data_as(C.c_void_p), C.c_int64(n),
+                                    sub.ctypes.data_as(C.c_void_p), C.c_int64(len(sub)), en.ctypes.data_as(C.c_void_p),
+                                    C.byref(prm), C.byref(it), C.c_uint64(seed), C.c_int(nthreads)))
+    try:
+        shapes, at = [], []
+        for k in range(lib.orc_run_nshapes(run)):
+            c, a = orc_cand(), C.c_int32()
+            ln = lib.orc_run_shape(run, k, C.byref(c), C.byref(a))
+            idx = np.empty(ln, np.int64)
+            if ln:
+                lib.orc_run_inpoints(run, k, idx.ctypes.data_as(C.c_void_p))
+            shapes.append((c.type, bool(c.outwards), np.array(c.p[:]), idx))
+            at.append(a.value)
+        secs = (C.c_double * 3)()
+        lib.orc_run_seconds(run, secs)
+        info = {"iterations": lib.orc_run_iterations(run), "cands_scored": lib.orc_run_cands_scored(run),
+                "evals": lib.orc_run_evals(run), "extracted_at": at, "seconds": tuple(secs),
+                "threads": nthreads if nthreads > 0 else lib.orc_max_threads()}
+    finally:
+        lib.orc_run_free(run)
+    return shapes, en.astype(bool), info

@@ -408,6 +408,32 @@ static int fit_cone(const v3* p, const v3* n, int k, const orc_params* prm, orc_
   return 1;
 }
 
+/* forcefitshapes! for ONE minimal set (fitting.jl:165-173): candidates in shape_types order; returns how many */
+static int fit_set(const v3* p, const v3* n, int k, const orc_params* prm, orc_cand* out) {
+  int m = 0;
+  for (int t = 0; t < prm->n_shape_types; ++t) {
+    orc_cand c;
+    memset(&c, 0, sizeof(c));
+    int ok = 0;
+    switch (prm->shape_types[t]) {
+      case 0:
+        ok = fit_plane(p, n, k, prm, &c);
+        break;
+      case 1:
+        ok = fit_sphere(p, n, k, prm, &c);
+        break;
+      case 2:
+        ok = fit_cylinder(p, n, k, prm, &c);
+        break;
+      case 3:
+        ok = fit_cone(p, n, k, prm, &c);
+        break;
+    }
+    if (ok) out[m++] = c;
+  }
+  return m;
+}
+
 /*
  * forcefitshapes! for S minimal sets: P, N = S x k x 3 doubles.  Candidates are written compacted in
  * (set, shape_types) order; out_set[i] = source set.  Returns the number of candidates.
@@ -423,29 +449,12 @@ int orc_fit_points(const double* P, const double* N, int S, int k, const orc_par
       p[i] = (v3){pp[0], pp[1], pp[2]};
       n[i] = (v3){nn[0], nn[1], nn[2]};
     }
-    for (int t = 0; t < prm->n_shape_types; ++t) {
-      orc_cand c;
-      memset(&c, 0, sizeof(c));
-      int ok = 0;
-      switch (prm->shape_types[t]) {
-        case 0:
-          ok = fit_plane(p, n, k, prm, &c);
-          break;
-        case 1:
-          ok = fit_sphere(p, n, k, prm, &c);
-          break;
-        case 2:
-          ok = fit_cylinder(p, n, k, prm, &c);
-          break;
-        case 3:
-          ok = fit_cone(p, n, k, prm, &c);
-          break;
-      }
-      if (ok) {
-        out[m] = c;
-        out_set[m] = s;
-        ++m;
-      }
+    orc_cand c[4];
+    int got = fit_set(p, n, k, prm, c);
+    for (int j = 0; j < got; ++j) {
+      out[m] = c[j];
+      out_set[m] = s;
+      ++m;
     }
   }
   return m;
@@ -457,4 +466,324 @@ int orc_max_threads(void) {
 #else
   return 1;
 #endif
+}
+
+/* =====================================================================================
+ * The loop: ransac(pc, params) -- src/iterations.jl:35-162, with
+ *   samplepointcloud4!      src/fitting.jl:383-430 (root cell only: Q1, octree.jl:82-84)
+ *   forcefitshapes!         src/fitting.jl:165-173
+ *   scorecandidates!        src/fitting.jl:181-190 (subset 1 only: iterations.jl:95)
+ *   scorecandidate x4       plane.jl:61-71, sphere.jl:118-135 (Q4: ignores isenabled),
+ *                           cylinder.jl:172-186, cone.jl:155-167
+ *   findhighestscore        src/fitting.jl:140-150 (strict >, first maximum wins)
+ *   estimatescore           src/confidenceintervals.jl:53-74 (Int64 products wrap: Q9)
+ *   prob / chooseS          src/utilities.jl:262, :297-300
+ *   refit x4                plane.jl:137-143, sphere.jl:179-190, cylinder.jl:228-234, cone.jl:176-182
+ *   invalidate_indexes!     src/fitting.jl:197-202
+ *   removeinvalidshapes!    src/fitting.jl:209-221 (stored inlier lists, literally)
+ * Julia's random stream is version dependent (Q19) and not part of the contract: the minimal set
+ * `(k-1)*minsubsetN + i` draws from a Philox4x32-10 stream keyed by the seed, exactly like
+ * oracle/ransac_oracle.py::SetStream / sample_minimal_set (tests assert C loop == NumPy loop).
+ * OpenMP only parallelises over independent sets / (candidate, point) pairs; every result is
+ * assembled in the reference's sequential order.
+ * ===================================================================================== */
+
+typedef struct {
+  int32_t drawN, minsubsetN, itermax, extract_s, terminate_s, reserved;
+  int64_t tau;
+  double prob_det;
+} orc_iter;
+
+typedef struct orc_run {
+  int nshapes, cap;
+  orc_cand* shapes;
+  int64_t* len;
+  int64_t** idx;
+  int32_t* extracted_at;
+  int iterations;
+  int64_t cands_scored, evals;
+  double seconds_sample_fit, seconds_score, seconds_extract;
+} orc_run;
+
+/* ---- Philox4x32-10 set streams (ransac_oracle.py:927-960) ---- */
+static void philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0, c1 = n1, c2 = n2, c3 = n3;
+    k0 += 0x9E3779B9u, k1 += 0xBB67AE85u;
+  }
+  out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+
+typedef struct {
+  uint32_t key[2];
+  uint64_t set_id;
+  uint32_t ndraw;
+  uint32_t blk[4];
+} set_stream;
+
+static uint64_t stream_u64(set_stream* s) {
+  const uint32_t i = s->ndraw++;
+  if ((i & 1u) == 0) {
+    uint32_t ctr[4] = {i / 2, (uint32_t)s->set_id, (uint32_t)(s->set_id >> 32), 0};
+    philox4x32(ctr, s->key, s->blk);
+    return (uint64_t)s->blk[0] | ((uint64_t)s->blk[1] << 32);
+  }
+  return (uint64_t)s->blk[2] | ((uint64_t)s->blk[3] << 32);
+}
+
+static int64_t rand_below(set_stream* s, int64_t n) { return (int64_t)(((unsigned __int128)stream_u64(s) * (unsigned __int128)(uint64_t)n) >> 64); }
+
+/* samplepointcloud4! on the root cell; returns 1 and idx[drawN] on success */
+static int sample_set(int64_t n, const uint8_t* enabled, const int64_t* en_idx, int64_t ne, int drawN, uint64_t seed, uint64_t set_id,
+                      int64_t* idx) {
+  set_stream st = {{(uint32_t)seed, (uint32_t)(seed >> 32)}, set_id, 0, {0, 0, 0, 0}};
+  if (ne == 0) return 0; /* the reference would spin forever; the tau test keeps it from getting here */
+  int64_t r1 = rand_below(&st, n);
+  while (!enabled[r1]) r1 = rand_below(&st, n);
+  if (ne < drawN) return 0;
+  idx[0] = r1;
+  for (int k = 1; k < drawN; ++k) {
+    int64_t nexti = rand_below(&st, ne);
+    if (idx[0] == en_idx[nexti]) nexti = rand_below(&st, ne); /* "try oncemore", fitting.jl:417-420 */
+    idx[k] = en_idx[nexti];
+  }
+  for (int i = 1; i < drawN; ++i) /* allisdifferent, utilities.jl:285-295 */
+    for (int j = 0; j < i; ++j)
+      if (idx[i] == idx[j]) return 0;
+  return 1;
+}
+
+/* estimatescore with Julia's Int64 arithmetic (products wrap, Q9); E = (min+max)/2 */
+static int64_t wrap_mul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
+void orc_estimate_score(int64_t s1len, int64_t plen, int64_t sigma, double* omin, double* omax, double* oE) {
+  const int64_t N = -2 - s1len, x = -2 - plen, n = -1 - sigma;
+  const int64_t xn = wrap_mul(x, n);
+  const int64_t prod = wrap_mul(wrap_mul(xn, N - x), N - n);
+  const double sq_ = (double)prod / (double)(N - 1);
+  const double sq = sq_ < 0 ? 0.0 : sqrt(sq_);
+  const double gmin = ((double)xn + sq) / (double)N, gmax = ((double)xn - sq) / (double)N;
+  const double a = -1 - gmin, b = -1 - gmax;
+  const double lo = a < b ? a : b, hi = a < b ? b : a; /* notsoconfident */
+  if (omin) *omin = lo;
+  if (omax) *omax = hi;
+  if (oE) *oE = (lo + hi) / 2;
+}
+
+static double prob_(double n, double s, double N, double k) { return 1 - pow(1 - pow(n / N, k), s); }
+
+static double now_s(void) {
+#ifdef _OPENMP
+  return omp_get_wtime();
+#else
+  return 0.0;
+#endif
+}
+
+typedef struct {
+  orc_cand c;
+  double E;
+  int32_t* in; /* inpoints: global indices in subset order */
+  int64_t nin;
+} stored;
+
+/*
+ * P, N: n x 3 float64; subset1: m global indices (pc.subsets[1]); enabled: n bytes, in/out
+ * (ransac(pc, params, setenabled): the caller sets them to 1 for setenabled = true).
+ */
+orc_run* orc_ransac(const double* P, const double* Nrm, int64_t n, const int64_t* subset1, int64_t m, uint8_t* enabled,
+                    const orc_params* prm, const orc_iter* it, uint64_t seed, int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+  orc_run* run = (orc_run*)calloc(1, sizeof(orc_run));
+  const int drawN = it->drawN, S = it->minsubsetN, nt = prm->n_shape_types;
+  if (drawN < 2 || drawN > 8 || n >= 2147483647LL) return run;
+  double thr[4];
+  for (int t = 0; t < 4; ++t) thr[t] = cos(prm->alpha[t]);
+  int64_t n_enabled = 0;
+  for (int64_t i = 0; i < n; ++i) n_enabled += enabled[i] != 0;
+  int64_t* en_idx = (int64_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(int64_t));
+  int64_t ne = 0;
+  int en_dirty = 1;
+  stored* store = NULL;
+  int64_t nstore = 0, capstore = 0;
+  orc_cand* newc = (orc_cand*)malloc((size_t)S * nt * sizeof(orc_cand));
+  int32_t* newn = (int32_t*)malloc((size_t)S * sizeof(int32_t));
+  const int CB = 256; /* candidates scored per block (bounds the byte-mask scratch) */
+  uint8_t* mk = (uint8_t*)malloc((size_t)CB * (size_t)(m > 0 ? m : 1));
+  uint8_t* rmask = (uint8_t*)malloc((size_t)(n > 0 ? n : 1));
+  int64_t cc[3] = {0, 0, 0}; /* lengthC, allcand, nofminset: iterations.jl:70 */
+
+  for (int k = 1; k <= it->itermax; ++k) {
+    if (n_enabled < it->tau) break; /* iterations.jl:75 */
+    run->iterations = k;
+    double t0 = now_s();
+    if (en_dirty) {
+      ne = 0;
+      for (int64_t i = 0; i < n; ++i)
+        if (enabled[i]) en_idx[ne++] = i;
+      en_dirty = 0;
+    }
+    /* ---- minsubsetN minimal sets -> candidates in (set, shape_types) order ---- */
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < S; ++i) {
+      int64_t sd[8];
+      newn[i] = 0;
+      if (!sample_set(n, enabled, en_idx, ne, drawN, seed, (uint64_t)(k - 1) * (uint64_t)S + (uint64_t)i, sd)) continue;
+      v3 p[8], nn[8];
+      for (int j = 0; j < drawN; ++j) {
+        p[j] = (v3){P[3 * sd[j]], P[3 * sd[j] + 1], P[3 * sd[j] + 2]};
+        nn[j] = (v3){Nrm[3 * sd[j]], Nrm[3 * sd[j] + 1], Nrm[3 * sd[j] + 2]};
+      }
+      newn[i] = fit_set(p, nn, drawN, prm, newc + (size_t)i * nt);
+    }
+    int64_t ncand = 0;
+    for (int i = 0; i < S; ++i) {
+      for (int j = 0; j < newn[i]; ++j) newc[ncand + j] = newc[(size_t)i * nt + j]; /* ncand <= i*nt: in-place compaction */
+      ncand += newn[i];
+    }
+    cc[1] += ncand; /* iterations.jl:94 */
+    double t1 = now_s();
+    run->seconds_sample_fit += t1 - t0;
+    /* ---- scorecandidates! on subset 1 ---- */
+    if (nstore + ncand > capstore) {
+      capstore = (nstore + ncand) * 2 + 64;
+      store = (stored*)realloc(store, (size_t)capstore * sizeof(stored));
+    }
+    for (int64_t c0 = 0; c0 < ncand; c0 += CB) {
+      const int nb = (int)(ncand - c0 < CB ? ncand - c0 : CB);
+      const int64_t chunk = 8192, nch = (m + chunk - 1) / chunk;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+      for (int c = 0; c < nb; ++c)
+        for (int64_t ch = 0; ch < nch; ++ch) {
+          const orc_cand* cd = &newc[c0 + c];
+          const double ct = cos(-cd->p[6] / 2), st = sin(-cd->p[6] / 2);
+          const int honour = !(cd->type == 1 && prm->sphere_ignores_enabled);
+          const int64_t hi = (ch + 1) * chunk < m ? (ch + 1) * chunk : m;
+          uint8_t* row = mk + (size_t)c * (size_t)m;
+          for (int64_t j = ch * chunk; j < hi; ++j) {
+            const int64_t g = subset1[j];
+            v3 p = {P[3 * g], P[3 * g + 1], P[3 * g + 2]}, nn = {Nrm[3 * g], Nrm[3 * g + 1], Nrm[3 * g + 2]};
+            int ok = compat_any(cd, ct, st, p, nn, prm->eps, thr);
+            if (honour) ok = ok && enabled[g];
+            row[j] = (uint8_t)ok;
+          }
+        }
+#pragma omp parallel for schedule(dynamic, 1)
+      for (int c = 0; c < nb; ++c) {
+        const uint8_t* row = mk + (size_t)c * (size_t)m;
+        int64_t cnt = 0;
+        for (int64_t j = 0; j < m; ++j) cnt += row[j];
+        stored* sp = &store[nstore + c];
+        sp->c = newc[c0 + c];
+        sp->nin = cnt;
+        sp->in = (int32_t*)malloc((size_t)(cnt > 0 ? cnt : 1) * sizeof(int32_t));
+        int64_t o = 0;
+        for (int64_t j = 0; j < m; ++j)
+          if (row[j]) sp->in[o++] = (int32_t)subset1[j];
+        orc_estimate_score(m, n, cnt, NULL, NULL, &sp->E);
+      }
+      nstore += nb;
+    }
+    run->cands_scored += ncand;
+    run->evals += ncand * m;
+    cc[2] = (int64_t)k * S; /* iterations.jl:99 */
+    cc[0] = nstore;         /* iterations.jl:102 */
+    double t2 = now_s();
+    run->seconds_score += t2 - t1;
+    if (nstore >= 1) {
+      int64_t best = 0; /* findhighestscore: strict >, first wins */
+      double highest = store[0].E;
+      for (int64_t i = 0; i < nstore; ++i)
+        if (store[i].E > highest) highest = store[i].E, best = i;
+      const double s_ex = (double)cc[it->extract_s];
+      if (prob_(highest, s_ex, (double)n, (double)drawN) > it->prob_det) {
+        /* ---- refit over the enabled points of the whole cloud, invalidate_indexes! ---- */
+        const orc_cand bc = store[best].c;
+        const double ct = cos(-bc.p[6] / 2), st = sin(-bc.p[6] / 2);
+        int64_t total = 0;
+#pragma omp parallel for schedule(static) reduction(+ : total)
+        for (int64_t i = 0; i < n; ++i) {
+          int ok = 0;
+          if (enabled[i]) {
+            v3 p = {P[3 * i], P[3 * i + 1], P[3 * i + 2]}, nn = {Nrm[3 * i], Nrm[3 * i + 1], Nrm[3 * i + 2]};
+            ok = compat_any(&bc, ct, st, p, nn, prm->eps, thr);
+          }
+          rmask[i] = (uint8_t)ok;
+          total += ok;
+        }
+        if (run->nshapes == run->cap) {
+          run->cap = run->cap ? 2 * run->cap : 16;
+          run->shapes = (orc_cand*)realloc(run->shapes, (size_t)run->cap * sizeof(orc_cand));
+          run->len = (int64_t*)realloc(run->len, (size_t)run->cap * sizeof(int64_t));
+          run->idx = (int64_t**)realloc(run->idx, (size_t)run->cap * sizeof(int64_t*));
+          run->extracted_at = (int32_t*)realloc(run->extracted_at, (size_t)run->cap * sizeof(int32_t));
+        }
+        int64_t* list = (int64_t*)malloc((size_t)(total > 0 ? total : 1) * sizeof(int64_t));
+        int64_t o = 0;
+        for (int64_t i = 0; i < n; ++i)
+          if (rmask[i]) list[o++] = i, enabled[i] = 0;
+        n_enabled -= total;
+        en_dirty = 1;
+        run->shapes[run->nshapes] = bc, run->len[run->nshapes] = total, run->idx[run->nshapes] = list;
+        run->extracted_at[run->nshapes] = k;
+        ++run->nshapes;
+        run->evals += ne;
+        /* deleteat!(scoredshapes, best) + removeinvalidshapes! */
+        uint8_t* dead = (uint8_t*)calloc((size_t)nstore, 1);
+        dead[best] = 1;
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int64_t i = 0; i < nstore; ++i) {
+          if (i == best) continue;
+          const stored* sp = &store[i];
+          for (int64_t j = 0; j < sp->nin; ++j)
+            if (!enabled[sp->in[j]]) {
+              dead[i] = 1;
+              break;
+            }
+        }
+        int64_t w = 0;
+        for (int64_t i = 0; i < nstore; ++i) {
+          if (dead[i])
+            free(store[i].in);
+          else
+            store[w++] = store[i];
+        }
+        nstore = w;
+        free(dead);
+      }
+    }
+    run->seconds_extract += now_s() - t2;
+    /* iterations.jl:151-156 */
+    if (prob_((double)it->tau, (double)cc[it->terminate_s], (double)n, (double)drawN) > it->prob_det) break;
+  }
+  for (int64_t i = 0; i < nstore; ++i) free(store[i].in);
+  free(store), free(newc), free(newn), free(mk), free(rmask), free(en_idx);
+  return run;
+}
+
+int orc_run_nshapes(const orc_run* r) { return r->nshapes; }
+int orc_run_iterations(const orc_run* r) { return r->iterations; }
+int64_t orc_run_cands_scored(const orc_run* r) { return r->cands_scored; }
+int64_t orc_run_evals(const orc_run* r) { return r->evals; }
+void orc_run_seconds(const orc_run* r, double* out3) {
+  out3[0] = r->seconds_sample_fit, out3[1] = r->seconds_score, out3[2] = r->seconds_extract;
+}
+int64_t orc_run_shape(const orc_run* r, int i, orc_cand* out, int32_t* extracted_at) {
+  if (i < 0 || i >= r->nshapes) return -1;
+  if (out) *out = r->shapes[i];
+  if (extracted_at) *extracted_at = r->extracted_at[i];
+  return r->len[i];
+}
+void orc_run_inpoints(const orc_run* r, int i, int64_t* out) {
+  if (i < 0 || i >= r->nshapes) return;
+  memcpy(out, r->idx[i], (size_t)r->len[i] * sizeof(int64_t));
+}
+void orc_run_free(orc_run* r) {
+  if (!r) return;
+  for (int i = 0; i < r->nshapes; ++i) free(r->idx[i]);
+  free(r->shapes), free(r->len), free(r->idx), free(r->extracted_at), free(r);
 }
