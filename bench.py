@@ -176,11 +176,10 @@ def cpu_baseline(sc, cands, params, budget_pts: int, ncand: int = 64):
     sample = cands[::step]
     t0 = time.perf_counter()
     if have_c:
-        cores = c_oracle.score_counts(sample, P, N, op, nthreads=os.cpu_count() or 1)[1]  # all host threads, explicitly
+        counts, cores = c_oracle.score_counts(sample, P, N, op, nthreads=os.cpu_count() or 1)  # all host threads, explicitly
     else:
         cores = 1
-        for sh in sample:
-            O.compatibles(to_oracle_shape(sh), P, N, op)
+        counts = np.array([int(O.compatibles(to_oracle_shape(sh), P, N, op).sum()) for sh in sample], np.int32)
     dt = time.perf_counter() - t0
     ev = len(sample) * n
     single = None
@@ -189,7 +188,8 @@ def cpu_baseline(sc, cands, params, budget_pts: int, ncand: int = 64):
         t1 = time.perf_counter()
         c_oracle.score_counts(sample, P[:n1], N[:n1], op, nthreads=1)
         single = len(sample) * n1 / (time.perf_counter() - t1) / 1e9
-    return {"value": ev / dt / 1e9, "unit": "G evals/s", "cores": cores, "kind": "port", "single_thread_value": single,
+    return {"_counts": counts, "_step": step, "_n": n,
+            "value": ev / dt / 1e9, "unit": "G evals/s", "cores": cores, "kind": "port", "single_thread_value": single,
             "sample": f"{len(sample)} candidates (every {step}th, all four types) x first {n} points of the workload; "
                       f"{'C (OpenMP)' if have_c else 'NumPy'} float64 restatement of RANSAC.jl compatibles*, {dt:.2f} s"}
 
@@ -207,6 +207,7 @@ def run_reference(args, rank, world):
     vals = []
     for i in range(args.warmup + args.steps):
         r = cpu_baseline(sc, cands, params, pts, ncand=128)
+        r = {k: v for k, v in r.items() if not k.startswith("_")}
         if i >= args.warmup:
             vals.append(r)
     v = float(np.mean([x["value"] for x in vals]))
@@ -403,7 +404,15 @@ def main():
         out["ransac"] = time_ransac(R, args.ransac, local)
     if not args.no_cpu and world == 1:
         # ~10 s of CPU work: 512 candidates (every 8th) x all points of rank 0's shard of the same workload
-        out["cpu_baseline"] = cpu_baseline(sc, cands, params, args.cpu_sample or len(sc.vertices), ncand=512)
+        cb = cpu_baseline(sc, cands, params, args.cpu_sample or len(sc.vertices), ncand=512)
+        # the oracle's counts of those candidates against the device's, on the same points: parity at the
+        # full c3 size (the device counted all 4096 candidates over all points in the timed steps above)
+        if cb["_n"] == n:
+            want, got = np.asarray(cb["_counts"]), counts_host[:: cb["_step"]]
+            out["parity_checked"] = {"cands": int(len(want)), "points": int(n), "mismatches": int((want != got).sum()),
+                                     "max_abs_count_diff": int(np.abs(want.astype(np.int64) - got).max()),
+                                     "checker": "oracle/oracle.c::orc_score (float64 restatement of compatibles*)"}
+        out["cpu_baseline"] = {k: v for k, v in cb.items() if not k.startswith("_")}
     # informational, last (nothing measured above depends on it): the same counts through Morton-tile culling
     # (rsc_score_culled).  Never the headline: the reference evaluates every pair.
     if world == 1 and not args.no_cull:

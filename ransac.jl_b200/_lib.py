@@ -120,11 +120,36 @@ if not os.path.exists(LIB_PATH):
         "(make -C ransac.jl_b200/csrc). There is no CPU fallback."
     )
 
-lib = C.CDLL(LIB_PATH)
-for _name, (_res, _args) in SIGNATURES.items():
-    _f = getattr(lib, _name)  # AttributeError here = header/library mismatch
-    _f.restype = _res
-    _f.argtypes = _args
+
+
+class _LazyLib:
+    """libransac_b200.so, dlopen-ed on first use.  Importing the package (host-side types, parameters,
+    scene generators) must not map the CUDA library: bench.py's `--impl reference` arm and the CPU
+    oracle tools import those without touching the product.  A missing library is still an import-time
+    error (above), and the first call fails loudly if it cannot be loaded."""
+
+    _cdll = None
+
+    def _load(self):
+        if _LazyLib._cdll is None:
+            cdll = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                f = getattr(cdll, name)  # AttributeError here = header/library mismatch
+                f.restype = res
+                f.argtypes = args
+            _LazyLib._cdll = cdll
+        return _LazyLib._cdll
+
+    def __getattr__(self, name):
+        return getattr(self._load(), name)
+
+
+lib = _LazyLib()
+
+
+def loaded() -> bool:
+    """True once libransac_b200.so has been mapped into this process."""
+    return _LazyLib._cdll is not None
 
 
 RSC_SCORE_PROGRESSIVE = 16  # compat_flags: progressive subset scoring in rsc_ransac_run (extension)

@@ -43,6 +43,13 @@ static int32_t pick_pointset(rsc_cloud* cloud, int32_t subset_id, PointSet* ps) 
   return RSC_OK;
 }
 
+// chunked scoring: every per-chunk score_enqueue resets the guard-band queue fill, so a chunk's overflow
+// is latched here (wl_count[2] = largest fill that exceeded the capacity) before the next chunk runs
+__global__ void latch_overflow_kernel(uint32_t* __restrict__ wl_count, uint32_t cap) {
+  const uint32_t m = wl_count[0] > wl_count[1] ? wl_count[0] : wl_count[1];
+  if (m > cap && m > wl_count[2]) wl_count[2] = m;
+}
+
 }  // namespace rsc
 
 using namespace rsc;
@@ -211,6 +218,8 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
     int32_t* d_policy = ctx->counts.as<int32_t>() + 2 * (size_t)C;
     if (chunked && attempt == 0) {
       const int nchunks = (int)((cloud->n + cloud->chunk_pts - 1) / cloud->chunk_pts);
+      RSC_CUDA(ctx, ctx->wl_count.ensure(16));
+      RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.as<uint32_t>() + 2, 0, sizeof(uint32_t), st));
       for (int i = 0; i < nchunks && !rc; ++i) {
         const int64_t off = (int64_t)i * cloud->chunk_pts;
         PointSet sl = ps;
@@ -222,6 +231,10 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
         rc = score_enqueue(ctx, cloud, sl, th, ctx->cands.as<rsc_cand>(), C, i == nchunks - 1 ? d_policy : nullptr, false, st,
                            ctx->counts.as<int32_t>(), ctx->counts.as<int32_t>() + C, ctx->aux.as<double>(),
                            cloud->d_bounds + 2 * i, i > 0);
+        if (!rc) {
+          latch_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap);
+          RSC_CUDA(ctx, cudaGetLastError());
+        }
       }
       if (rc) return rc;
       if ((rc = cloud_ready(cloud))) return rc;
@@ -231,13 +244,15 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
       if (rc) return rc;
     }
     RSC_CUDA(ctx, cudaEventRecord(ctx->ev1, st));
-    uint32_t nq[2] = {0, 0};  // queued groups, queued pairs
+    uint32_t nq[3] = {0, 0, 0};  // queued groups, queued pairs, latched overflow of an earlier chunk
+    const bool latched = chunked && attempt == 0;
     RSC_CUDA(ctx, cudaMemcpyAsync(counts, d_policy, (size_t)C * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RSC_CUDA(ctx, cudaMemcpyAsync(nq, ctx->wl_count.p, sizeof(nq), cudaMemcpyDeviceToHost, st));
+    RSC_CUDA(ctx, cudaMemcpyAsync(nq, ctx->wl_count.p, (latched ? 3 : 2) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     RSC_CUDA(ctx, cudaStreamSynchronize(st));
     const uint32_t namb = nq[1];
-    if ((size_t)nq[0] > ctx->wl_cap || (size_t)nq[1] > ctx->wl_cap) {  // a guard-band queue overflowed: grow, redo
-      const size_t need = nq[0] > nq[1] ? nq[0] : nq[1];
+    if ((size_t)nq[0] > ctx->wl_cap || (size_t)nq[1] > ctx->wl_cap || nq[2] != 0) {  // a guard-band queue overflowed: grow, redo
+      size_t need = nq[0] > nq[1] ? nq[0] : nq[1];
+      if (nq[2] > need) need = nq[2];
       ctx->wl_cap = need + need / 4 + 1024;
       ctx->stats.evals -= (int64_t)C * ps.n;
       ctx->stats.cands_scored -= C;

@@ -130,7 +130,8 @@ struct rsc_cloud {
   rsc_ctx* ctx = nullptr;
   int64_t n = 0, n_pad = 0;
   int64_t global_offset = 0, n_global = 0;
-  int64_t range_lo = 0, range_hi = 0;  // this rank's point range of a replicated cloud (0,0: all)
+  int64_t range_lo = 0, range_hi = 0;  // this rank's point range of a replicated cloud
+  bool range_set = false;              // false: the whole cloud; true with lo == hi: an empty rank (joins every all-reduce with zeros)
   float* soa = nullptr;        // 6 * n_pad floats: x | y | z | nx | ny | nz
   uint32_t* enabled = nullptr; // n_pad/32 words
   uint32_t* valid = nullptr;

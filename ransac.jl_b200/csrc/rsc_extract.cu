@@ -241,13 +241,12 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
   unsigned long long* offsets = reinterpret_cast<unsigned long long*>(b + ((size_t)words * 4 + 15) / 16 * 16);
   uint32_t* block_counts = reinterpret_cast<uint32_t*>(offsets + nblocks);
   RSC_CUDA(ctx, ctx->misc2.ensure(64));
-  const bool sharded = ctx->allreduce && cloud->range_hi > cloud->range_lo;
+  const bool sharded = ctx->allreduce && cloud->range_set;
   int64_t b0 = 0, b1 = nblocks;
   if (sharded) {
     b0 = cloud->range_lo / kExPts;
     b1 = (cloud->range_hi + kExPts - 1) / kExPts;
-    if (cloud->range_lo % kExPts || (cloud->range_hi % kExPts && cloud->range_hi != n_pad))
-      return fail(ctx, RSC_E_ARG, "refit: a shard range must be aligned to 2048 points");
+    if (b1 < b0) b1 = b0;  // an empty rank (range_lo == range_hi == n_pad) evaluates nothing
     RSC_CUDA(ctx, cudaMemsetAsync(a.inl, 0, (size_t)words * 4, st));
   }
   a.block0 = b0;
@@ -269,7 +268,10 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
   extract_compile_kernel<<<1, 1, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
   RSC_CUDA(ctx, cudaEventRecord(ctx->evr0, st));
+  if (grid == 0) a.col = -2;  // empty rank: no mask kernel, it only joins the all-reduce below
   switch (a.col) {
+    case -2:
+      break;
     case RSC_PLANE:
       extract_mask_kernel<RSC_PLANE><<<grid, kExThreads, 0, st>>>(a);
       break;

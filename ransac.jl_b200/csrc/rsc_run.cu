@@ -365,10 +365,12 @@ int32_t rsc_ctx_set_allreduce(rsc_ctx* ctx, rsc_allreduce_fn fn, void* user) {
 
 int32_t rsc_cloud_set_range(rsc_cloud* cloud, int64_t lo, int64_t hi) {
   if (!cloud) return RSC_E_ARG;
-  if (lo < 0 || hi > cloud->n_pad || lo >= hi || lo % kTile || (hi % kTile && hi != cloud->n_pad && hi != cloud->n))
-    return fail(cloud->ctx, RSC_E_ARG, "set_range: range must be non-empty and aligned to 512 points");
-  cloud->range_lo = lo;
+  // 2048 = points per refit CTA (rsc_extract.cu); lo == hi is an empty rank (clouds smaller than 2048 x ranks)
+  if (lo < 0 || hi > cloud->n_pad || lo > hi || (lo % 2048 && lo != cloud->n) || (hi % 2048 && hi != cloud->n_pad && hi != cloud->n))
+    return fail(cloud->ctx, RSC_E_ARG, "set_range: range bounds must be multiples of 2048 points (or the cloud size)");
+  cloud->range_lo = lo >= cloud->n ? cloud->n_pad : lo;
   cloud->range_hi = hi >= cloud->n ? cloud->n_pad : hi;
+  cloud->range_set = true;
   return RSC_OK;
 }
 
@@ -401,7 +403,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   const bool sharded = ctx->allreduce != nullptr;
   // this rank's slice of the subset copy (the whole of it when not sharded)
   int64_t slo = 0, shi = sub.m_pad;
-  if (sharded && cloud->range_hi > cloud->range_lo && cloud->n_pad > 0) {
+  if (sharded && cloud->range_set && cloud->n_pad > 0) {
     slo = (int64_t)((double)cloud->range_lo / cloud->n_pad * sub.m_pad) / kTile * kTile;
     shi = cloud->range_hi >= cloud->n_pad ? sub.m_pad : (int64_t)((double)cloud->range_hi / cloud->n_pad * sub.m_pad) / kTile * kTile;
   }
@@ -415,13 +417,13 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   // a rank's slice of a gathered subset copy: the same fraction of it as the rank's range of the cloud
   auto subset_view = [&](rsc_subset& sb) {
     PointSet v = view_subset(&sb);
-    if (sharded && cloud->range_hi > cloud->range_lo && cloud->n_pad > 0) {
+    if (sharded && cloud->range_set && cloud->n_pad > 0) {
       const int64_t lo = (int64_t)((double)cloud->range_lo / cloud->n_pad * sb.m_pad) / kTile * kTile;
       const int64_t hi = cloud->range_hi >= cloud->n_pad ? sb.m_pad : (int64_t)((double)cloud->range_hi / cloud->n_pad * sb.m_pad) / kTile * kTile;
       v.x += lo, v.y += lo, v.z += lo, v.nx += lo, v.ny += lo, v.nz += lo;
       v.enabled += lo / 32, v.valid += lo / 32;
       v.n_pad = hi - lo;
-      v.n = (sb.m < hi ? sb.m : hi) - lo;
+      v.n = std::max<int64_t>(0, (sb.m < hi ? sb.m : hi) - lo);
     }
     return v;
   };
@@ -553,7 +555,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           ps.x += slo, ps.y += slo, ps.z += slo, ps.nx += slo, ps.ny += slo, ps.nz += slo;
           ps.enabled += slo / 32, ps.valid += slo / 32;
           ps.n_pad = shi - slo;
-          ps.n = (sub.m < shi ? sub.m : shi) - slo;
+          ps.n = std::max<int64_t>(0, (sub.m < shi ? sub.m : shi) - slo);
         }
         if ((rc = score_enqueue(ctx, cloud, ps, th, dst, n_new, nullptr, false, st, cv, ce))) goto done;
         // overflow flag rides behind the counts, so that a sharded run decides to repeat collectively

@@ -663,6 +663,19 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
                       cudaStream_t st, int32_t* d_counts_valid, int32_t* d_counts_enabled,
                       const double* d_trig, const uint32_t* d_bounds, bool accumulate) {
   if (C <= 0) return RSC_OK;
+  if (ps.n_pad <= 0) {  // an empty slice (a rank without points of this set): zero counts, empty queues
+    RSC_CUDA(ctx, ctx->counts.ensure((size_t)2 * C * sizeof(int32_t)));
+    RSC_CUDA(ctx, ctx->wl_count.ensure(16));
+    int32_t* cv0 = d_counts_valid ? d_counts_valid : ctx->counts.as<int32_t>();
+    int32_t* ce0 = d_counts_enabled ? d_counts_enabled : ctx->counts.as<int32_t>() + C;
+    if (!accumulate) {
+      RSC_CUDA(ctx, cudaMemsetAsync(cv0, 0, (size_t)C * sizeof(int32_t), st));
+      RSC_CUDA(ctx, cudaMemsetAsync(ce0, 0, (size_t)C * sizeof(int32_t), st));
+    }
+    RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.p, 0, 2 * sizeof(uint32_t), st));
+    if (d_counts_policy) RSC_CUDA(ctx, cudaMemsetAsync(d_counts_policy, 0, (size_t)C * sizeof(int32_t), st));
+    return RSC_OK;
+  }
   if (ps.n_pad >= ((int64_t)1 << 32)) return fail(ctx, RSC_E_ARG, "point set too large for one shard (>= 2^32)");
   {
     const int64_t sd = ps.y - ps.x;
