@@ -46,9 +46,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="skip the informational culled-scoring leg")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--ransac", default="c4", choices=["none", "c2", "c4"],
-                    help="also time end-to-end ransac() on this scene (single GPU, extra JSON key); c4 = the "
-                         "10 M-point CAD-like scene BASELINE.json's second headline is quoted on")
+    ap.add_argument("--ransac", default="c4,c5",
+                    help="comma list of scenes (c2, c4, c5; 'none') on which end-to-end ransac() is also timed, at every N "
+                         "(sharded storage + the library's NCCL at N > 1; extra JSON key `ransac`): c4 = the 10 M-point "
+                         "CAD-like scene BASELINE.json's second headline is quoted on, c5 = the 100 M-point LiDAR-like scan")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaled c3 leg at N > 1")
     return ap.parse_args()
 
 
@@ -243,6 +245,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1:  # the library's own NCCL communicator: torch.distributed only carries its 128-byte id
+        from ransac_jl_b200 import shard
+
+        shard.init_comm(R.Context.get(local))
 
     sc, cands = make_workload(args.points, args.cands, rank)
     params = R.ransacparameters()
@@ -258,11 +264,12 @@ def main():
     stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: its handle is what the C ABI gets
     torch.cuda.set_stream(stream)
 
-    def step_resident():
-        rc = lib.rsc_score_dev(pc.handle, C.byref(cp), d_cands.data_ptr(), Cn, -1, d_counts.data_ptr(), stream.cuda_stream)
+    def step_resident(cloud=None):
+        cloud = cloud or pc
+        rc = lib.rsc_score_dev(cloud.handle, C.byref(cp), d_cands.data_ptr(), Cn, -1, d_counts.data_ptr(), stream.cuda_stream)
         pc.ctx.check(rc)
-        if world > 1:
-            dist.all_reduce(d_counts)
+        if world > 1:  # ncclAllReduce(int32, sum) of the per-candidate counts, enqueued by the library on the same stream
+            pc.ctx.check(lib.rsc_ctx_allreduce(pc.ctx.h, d_counts.data_ptr(), Cn, stream.cuda_stream))
 
     if world > 1:
         dist.barrier()  # first barrier = lazy NCCL set-up: keep it out of the neighbourhood of the timed region
@@ -344,6 +351,54 @@ def main():
                "h2d_bytes_per_step": int(2 * n * 12 + Cn * 64 + Cn * 16), "d2h_bytes_per_step": int(Cn * 4 + 4),
                "ms_per_step": dt / args.steps * 1e3}
 
+    # ---- strong-scaled c3 ("shards N/G per GPU"): the SAME total of points, 1/N of them per GPU ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        n_s = (n // world) // 2048 * 2048
+        pcs = R.RANSACCloud(sc.vertices[:n_s], sc.normals[:n_s], [np.zeros(0, np.int64)], device=local)
+        for _ in range(args.warmup):
+            step_resident(pcs)
+        torch.cuda.synchronize()
+        dist.barrier()
+        s_a, s_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_a.record()
+        for _ in range(args.steps):
+            step_resident(pcs)
+        s_b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ts = torch.tensor([s_a.elapsed_time(s_b)], device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ms_s = float(ts.item()) / args.steps
+        ks = []
+        for _ in range(3):
+            step_resident(pcs)
+            ks.append(_last_kernel(pcs)[0])
+        strong = {"scaling": "strong", "points_total": int(n_s * world), "points_per_gpu": int(n_s), "candidates": Cn,
+                  "ms_per_step": ms_s, "value": float(Cn) * n_s * world / (ms_s * 1e-3) / 1e9, "unit": "G evals/s",
+                  "score_kernels_ms": float(np.mean(ks)),
+                  "note": "same step as the headline (rsc_score_dev + the library's ncclAllReduce of the counts), "
+                          "max over ranks; compare with the 1-GPU headline value for the strong-scaling efficiency"}
+        pcs.close()
+
+    # ---- end-to-end ransac() at this N (all ranks take part) ----
+    ransac_out = None
+    scenes_req = [s for s in args.ransac.split(",") if s and s != "none"]
+    if scenes_req:
+        # free the microbenchmark's device buffers first (c5 needs 2.4 GB per replica at N = 1)
+        keep_for_rank0 = (sc, cands)
+        from tools import ransac_e2e
+
+        ransac_out = {}
+        for which in scenes_req:
+            try:
+                ransac_out[which] = ransac_e2e.run(which, rank, world, local, dist if world > 1 else None,
+                                                   cpu_loop=not args.no_cpu)
+            except Exception as e:  # informational keys: never lose the headline line
+                ransac_out[which] = {"error": repr(e)}
+                if world > 1:
+                    break  # the ranks may no longer be in step
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -400,8 +455,10 @@ def main():
             out["masks_variant"] = time_masks_variant(R, lib, C, torch, sc, cands, params, local, dev)
         except Exception as e:  # informational key only
             out["masks_variant"] = {"error": repr(e)}
-    if args.ransac != "none" and world == 1:
-        out["ransac"] = time_ransac(R, args.ransac, local)
+    if strong is not None:
+        out["strong"] = strong
+    if ransac_out is not None:
+        out["ransac"] = ransac_out
     if not args.no_cpu and world == 1:
         # ~10 s of CPU work: 512 candidates (every 8th) x all points of rank 0's shard of the same workload
         cb = cpu_baseline(sc, cands, params, args.cpu_sample or len(sc.vertices), ncand=512)
@@ -471,31 +528,6 @@ def time_masks_variant(R, lib, C, torch, sc, cands, params, local, dev, npts=4 <
     pc.close()
     return {"points": n, "candidates": Cn, "ms_per_step": best, "G_evals_s": Cn * n / best / 1e6, "mask_bytes": int(Cn * words * 4),
             "popcount_equals_counts": bool(ok)}
-
-
-def time_ransac(R, which, device):
-    """End-to-end ransac(pc, params, true) wall time (host call to result on the host), best of 3."""
-    from ransac_jl_b200 import scenes
-
-    if which == "c2":
-        sc, r = scenes.scene_c2(), 32
-        it = {"tau": len(sc.vertices) // 100, "minsubsetN": 4096, "itermax": 200}
-    else:
-        sc, r = scenes.scene_cad(), 32
-        it = {"tau": len(sc.vertices) // 1000, "minsubsetN": 8192, "itermax": 400}
-    params = R.ransacparameters(iteration=it)
-    pc = R.RANSACCloud(sc.vertices, sc.normals, r, device=device)
-    R.ransac(pc, R.ransacparameters(iteration=dict(it, itermax=2)), True, seed=1)
-    best, ex, loop = None, [], None
-    for rep in range(3):
-        t0 = time.perf_counter()
-        ex, _ = R.ransac(pc, params, True, seed=2024)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, loop = dt, getattr(pc, "last_run_seconds", None)
-    return {"scene": which, "points": int(len(sc.vertices)), "subsets": r, "iteration": it, "seconds": best,
-            "device_loop_seconds": loop,
-            "n_shapes": len(ex), "points_extracted": int(sum(len(e.inpoints) for e in ex))}
 
 
 def _last_kernel(pc):

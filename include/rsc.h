@@ -92,7 +92,7 @@ typedef struct rsc_cand {
  * eps/alpha are indexed by RSC_PLANE..RSC_CONE.
  */
 typedef struct rsc_params {
-  int32_t drawN;       /* iteration.drawN (only 3 is supported by the built-in fits) */
+  int32_t drawN;       /* iteration.drawN: 3..8 (the fits use the first three points, the rest only validate) */
   int32_t minsubsetN;  /* iteration.minsubsetN */
   double prob_det;     /* iteration.prob_det */
   int64_t tau;         /* iteration.tau */
@@ -137,8 +137,11 @@ int32_t rsc_ctx_last_kernel(rsc_ctx* ctx, double* kernel_ms, int64_t* guard_pair
 
 /* ---- cloud: RANSACCloud (octree.jl:37-59, ctors :78-138) ------------------------------ */
 /* xyz/nrm are AoS (N x 3), bit-compatible with Vector{SVector{3,Float32}}; stored on device as
- * SoA float32.  `_f64` down-converts Vector{SVector{3,Float64}}.  `_shard` uploads the point range
- * [global_offset, global_offset+n) of a cloud of n_global points (one shard per GPU/process).
+ * SoA float32.  `_f64` down-converts Vector{SVector{3,Float64}} (the device computes on the float32
+ * roundings: decisions are the float64 ones OF THE ROUNDED coordinates).  `_shard` uploads the point
+ * range [global_offset, global_offset+n) of a cloud of n_global points (one shard per GPU/process,
+ * sharded storage): global_offset must be a multiple of 2048 and n a multiple of 2048 unless the range
+ * ends the cloud; indices the library returns or takes (subsets, inlier lists) are GLOBAL.
  * The upload is enqueued in 2 Mi-point chunks and the call returns; the next call on the cloud waits
  * for it (rsc_score on the whole cloud even follows it chunk by chunk).  From pageable arrays (a
  * Julia Vector, a NumPy array) CUDA has staged the data when the call returns and the host arrays
@@ -156,6 +159,8 @@ void rsc_cloud_destroy(rsc_cloud* cloud);
 int64_t rsc_cloud_size(const rsc_cloud* cloud);
 /* pc.subsets (octree.jl:129-135): `idx` holds subset `subset_id`'s local point indices in subset
  * order; the device keeps a gathered contiguous copy so that scoring streams it linearly. */
+/* On a shard (rsc_cloud_create_shard) `idx` holds the GLOBAL indices of the whole subset (the same array
+ * on every rank); the rank keeps the entries of its own range, in subset order. */
 int32_t rsc_cloud_set_subset(rsc_cloud* cloud, int32_t subset_id, const int64_t* idx, int64_t m);
 int64_t rsc_cloud_subset_size(const rsc_cloud* cloud, int32_t subset_id);
 /* pc.isenabled in BitArray.chunks layout: ceil(n/64) UInt64 words, bit i%64 of word i/64 */
@@ -230,13 +235,37 @@ int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_
 int32_t rsc_refit_lsq(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand, double band,
                       rsc_cand* out, int64_t* n_used, double* rms);
 
-/* ---- point-range sharding over the GPUs of one box (one process per GPU) ---------------------- */
-/* Every rank holds the whole cloud (sampling needs random access) but scores/refits only its range
- * [lo, hi) -- multiples of 2048 points, hi may also be the cloud size.  The per-candidate counts and
- * the refit's inlier-mask words are summed over the ranks by `fn` (the host enqueues an NCCL
- * all-reduce(sum, int32) of `count` elements at d_buf on `stream`; non-zero return = failure). */
+/* ---- point-range sharding over the GPUs of one box (one process per GPU) ----------------------
+ * The path shards by point range: every rank scores/refits the points it owns and the
+ * per-candidate counts are summed with an int32 all-reduce.  Two layouts:
+ *   (1) SHARDED STORAGE (the default for multi-GPU runs): every rank uploads only its own range with
+ *       rsc_cloud_create_shard -- 24 B/point and the host->device copy scale with 1/ranks.  The enabled
+ *       mask of the WHOLE cloud (1 bit/point) is replicated so that every rank draws the same Philox
+ *       minimal sets; the 3 x 24 B of coordinates a set needs are gathered from their owners with one
+ *       all-reduce per batch of sets; subset copies, refit, inlier lists and K5 stay local to the range.
+ *       Needs a communicator (rsc_ctx_comm_init or rsc_ctx_set_allreduce).  rsc_ransac_run supports the
+ *       reference behaviour in this layout (not the extension switches).
+ *   (2) REPLICATED STORAGE: every rank holds the whole cloud (rsc_cloud_create) and is given a range
+ *       with rsc_cloud_set_range; also works with the extension switches.
+ * The all-reduce is NCCL inside the library (rsc_ctx_comm_init: libnccl.so.2 is dlopen-ed, so the
+ * library itself loads without NCCL) or a host callback (rsc_ctx_set_allreduce). */
+#define RSC_UNIQUE_ID_BYTES 128
+/* rank 0: ncclGetUniqueId into out[128]; the host passes the bytes to the other ranks (MPI, sockets, ...) */
+int32_t rsc_comm_unique_id(void* out);
+/* every rank: ncclCommInitRank on the context's device; all later sharded calls on this context
+ * all-reduce on the context stream with ncclAllReduce(int32, sum).  Collective. */
+int32_t rsc_ctx_comm_init(rsc_ctx* ctx, const void* unique_id, int32_t rank, int32_t nranks);
+int32_t rsc_ctx_comm_destroy(rsc_ctx* ctx);
+/* sums `count` int32 elements at DEVICE pointer d_buf over the ranks (in place) with the context's
+ * communicator or callback, enqueued on `stream` (NULL = the context stream); no synchronisation.  This is
+ * what follows rsc_score_dev on a shard: per-candidate counts of the ranks' point ranges -> counts of the cloud. */
+int32_t rsc_ctx_allreduce(rsc_ctx* ctx, int32_t* d_buf, int64_t count, void* stream);
+/* alternative: the host sums `count` int32 elements at device pointer d_buf over the ranks, enqueued on
+ * `stream` (non-zero return = failure) */
 typedef int32_t (*rsc_allreduce_fn)(void* user, void* d_buf, int64_t count, void* stream);
 int32_t rsc_ctx_set_allreduce(rsc_ctx* ctx, rsc_allreduce_fn fn, void* user);
+/* layout (2): this rank's range [lo, hi) of a replicated cloud -- multiples of 2048 points (hi may also
+ * be the cloud size); lo == hi is an empty rank, which still joins every all-reduce */
 int32_t rsc_cloud_set_range(rsc_cloud* cloud, int64_t lo, int64_t hi);
 
 /* ---- flattened octree + level-weighted cell sampler (extension) -------------
@@ -263,6 +292,11 @@ double rsc_run_seconds(const rsc_run* run);
 /* cell sampler runs: final level weights and accumulated level scores; returns the number of levels (0: root-cell run) */
 int32_t rsc_run_levelweight(const rsc_run* run, double* levelweight, double* levelscore);
 int32_t rsc_run_shape(const rsc_run* run, int32_t i, rsc_cand* shape, int64_t* n_inpoints);
+/* sharded storage: n_inpoints above counts the indices THIS rank holds (its range's part of the list;
+ * concatenated in rank order the parts are the ascending global list); this is the size of the whole list */
+int64_t rsc_run_shape_total(const rsc_run* run, int32_t i);
+/* host synchronisations (cudaStreamSynchronize) the loop needed, and speculative batches it ran */
+int32_t rsc_run_syncs(const rsc_run* run, int32_t* batches);
 /* The inlier index lists of a run stay in device memory until they are asked for: this call copies
  * list i (ascending 0-based global indices, n_inpoints of rsc_run_shape) into the caller's buffer. */
 int32_t rsc_run_inpoints(const rsc_run* run, int32_t i, int64_t* out_idx);

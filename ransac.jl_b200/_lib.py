@@ -102,6 +102,12 @@ SIGNATURES = {
     "rsc_refit_lsq": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), C.c_double, C.POINTER(rsc_cand),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rsc_ctx_set_allreduce": (C.c_int32, [_P, _P, _P]),
+    "rsc_comm_unique_id": (C.c_int32, [_P]),
+    "rsc_ctx_comm_init": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
+    "rsc_ctx_comm_destroy": (C.c_int32, [_P]),
+    "rsc_ctx_allreduce": (C.c_int32, [_P, _P, C.c_int64, _P]),
+    "rsc_run_shape_total": (C.c_int64, [_P, C.c_int32]),
+    "rsc_run_syncs": (C.c_int32, [_P, C.POINTER(C.c_int32)]),
     "rsc_cloud_set_range": (C.c_int32, [_P, C.c_int64, C.c_int64]),
     "rsc_ransac_run": (C.c_int32, [_P, C.POINTER(rsc_params), C.c_uint64, C.POINTER(_P)]),
     "rsc_run_nshapes": (C.c_int32, [_P]),

@@ -60,11 +60,13 @@ class RANSACCloud:
         self.normals = np.ascontiguousarray(n.astype(v.dtype, copy=False))
         self.size = int(v.shape[0])
         if isinstance(subsets, (int, np.integer)):
-            self.subsets = makesubsets(self.size, int(subsets), np.random.default_rng(seed))
+            # a shard draws the subsets of the WHOLE cloud (global indices, the same on every rank)
+            self.subsets = makesubsets(self.size if shard is None else int(shard[1]), int(subsets), np.random.default_rng(seed))
         else:
             self.subsets = [np.ascontiguousarray(s, dtype=np.int64) for s in subsets]
         self.ctx = ctx if ctx is not None else Context.get(device)
         self._h = C.c_void_p()
+        self.is_shard = False
         self.global_offset, self.n_global = 0, self.size
         if shard is not None:
             self.global_offset, self.n_global = int(shard[0]), int(shard[1])
@@ -74,6 +76,7 @@ class RANSACCloud:
             rc = lib.rsc_cloud_create_shard(
                 self.ctx.h, self.vertices.ctypes.data, self.normals.ctypes.data, self.size,
                 self.global_offset, self.n_global, C.byref(self._h))
+            self.is_shard = self.n_global > self.size
         elif self.vertices.dtype == np.float32:
             rc = lib.rsc_cloud_create(self.ctx.h, self.vertices.ctypes.data, self.normals.ctypes.data, self.size, C.byref(self._h))
         else:

@@ -93,6 +93,59 @@ __global__ void popc_words_kernel(const uint32_t* __restrict__ w, int64_t words,
   if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
+__global__ void andnot_words_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ m, int64_t words) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < words) dst[w] &= ~m[w];
+}
+
+// ---- sharded storage: the replicated whole-cloud enabled mask ---------------------------------------
+// Ranges are disjoint and start at multiples of 2048 points, so every rank's local words land in their own
+// slots of a zeroed whole-cloud buffer and an int32 sum over the ranks is the union.
+static int32_t shard_exchange(rsc_cloud* c, const uint32_t* local_words, const int32_t* d_extra_in, int n_extra, cudaStream_t st,
+                              uint32_t** out) {
+  rsc_ctx* ctx = c->ctx;
+  if (!ctx->allreduce) return fail(ctx, RSC_E_STATE, "sharded storage needs a communicator (rsc_ctx_comm_init or rsc_ctx_set_allreduce)");
+  RSC_CUDA(ctx, ctx->shardbuf.ensure((size_t)(c->g_words + n_extra + 4) * 4));
+  uint32_t* tmp = ctx->shardbuf.as<uint32_t>();
+  RSC_CUDA(ctx, cudaMemsetAsync(tmp, 0, (size_t)(c->g_words + n_extra) * 4, st));
+  RSC_CUDA(ctx, cudaMemcpyAsync(tmp + c->global_offset / 32, local_words, (size_t)(c->n_pad / 32) * 4, cudaMemcpyDeviceToDevice, st));
+  if (n_extra) RSC_CUDA(ctx, cudaMemcpyAsync(tmp + c->g_words, d_extra_in, (size_t)n_extra * 4, cudaMemcpyDeviceToDevice, st));
+  if (ctx->allreduce(ctx->allreduce_user, tmp, c->g_words + n_extra, (void*)st)) return fail(ctx, RSC_E_NCCL, "sharded storage: all-reduce failed");
+  *out = tmp;
+  return RSC_OK;
+}
+
+int32_t shard_sync_enabled(rsc_cloud* c, cudaStream_t st) {
+  uint32_t* tmp = nullptr;
+  if (int32_t rc = shard_exchange(c, c->enabled, nullptr, 0, st, &tmp)) return rc;
+  RSC_CUDA(c->ctx, cudaMemcpyAsync(c->g_enabled, tmp, (size_t)c->g_words * 4, cudaMemcpyDeviceToDevice, st));
+  c->enabled_changed();
+  return RSC_OK;
+}
+
+int32_t shard_clear_enabled(rsc_cloud* c, const uint32_t* inl_local, const int32_t* d_extra_in, int n_extra, int32_t* d_extra_out,
+                            cudaStream_t st) {
+  uint32_t* tmp = nullptr;
+  if (int32_t rc = shard_exchange(c, inl_local, d_extra_in, n_extra, st, &tmp)) return rc;
+  andnot_words_kernel<<<(unsigned)((c->g_words + 255) / 256), 256, 0, st>>>(c->g_enabled, tmp, c->g_words);
+  RSC_CUDA(c->ctx, cudaGetLastError());
+  if (n_extra) RSC_CUDA(c->ctx, cudaMemcpyAsync(d_extra_out, tmp + c->g_words, (size_t)n_extra * 4, cudaMemcpyDeviceToDevice, st));
+  c->enabled_changed();
+  return RSC_OK;
+}
+
+// set bits of a mask (synchronises the context stream); -1 on failure
+int64_t count_mask_bits(rsc_ctx* ctx, const uint32_t* words, int64_t nwords) {
+  if (ctx->misc.ensure(16) != cudaSuccess) return -1;
+  unsigned long long* d = ctx->misc.as<unsigned long long>();
+  cudaMemsetAsync(d, 0, 8, ctx->stream);
+  popc_words_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(words, nwords, d);
+  unsigned long long h = 0;
+  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+  return (int64_t)h;
+}
+
 int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st) {
   rsc_ctx* ctx = cloud->ctx;
   for (auto& s : cloud->subsets) {
@@ -180,6 +233,9 @@ static int32_t cloud_create_impl(rsc_ctx* ctx, const T* xyz, const T* nrm, int64
   *out = nullptr;
   if (!xyz || !nrm || n <= 0) return fail(ctx, RSC_E_ARG, "cloud_create: empty cloud or null arrays");
   if (n >= ((int64_t)1 << 32) - kTile) return fail(ctx, RSC_E_ARG, "cloud_create: shard too large (>= 2^32 points)");
+  const bool shard = n_global > n;
+  if (shard && (global_offset % 2048 || (n % 2048 && global_offset + n != n_global)))
+    return fail(ctx, RSC_E_ARG, "cloud_create_shard: a range must start at a multiple of 2048 points and hold a multiple of 2048 points unless it ends the cloud");
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   rsc_cloud* c = new rsc_cloud();
   c->ctx = ctx;
@@ -197,6 +253,14 @@ static int32_t cloud_create_impl(rsc_ctx* ctx, const T* xyz, const T* nrm, int64
     return fail_cuda(ctx, e, "cloud_create: cudaMalloc");
   }
   RSC_CUDA(ctx, cudaMemsetAsync(c->soa, 0, (size_t)6 * c->n_pad * sizeof(float), st));
+  if (shard) {  // replicated whole-cloud enabled mask, all points enabled (like every rank's local mask)
+    c->g_words = (n_global + kTile - 1) / kTile * (kTile / 32);
+    if ((e = cudaMalloc(&c->g_enabled, (size_t)c->g_words * 4)) != cudaSuccess) {
+      rsc_cloud_destroy(c);
+      return fail_cuda(ctx, e, "cloud_create_shard: cudaMalloc");
+    }
+    fill_valid_kernel<<<(unsigned)((c->g_words + 255) / 256), 256, 0, st>>>(c->g_enabled, nullptr, n_global, c->g_words);
+  }
   RSC_CUDA(ctx, cudaStreamSynchronize(st));
   int32_t rc = cloud_upload<T>(c, xyz, nrm);
   if (rc) {
@@ -241,8 +305,10 @@ int32_t rsc_cloud_update(rsc_cloud* c, const float* xyz, const float* nrm, int64
   for (size_t i = 0; i < c->subsets.size(); ++i) {  // gathered subset copies follow the new coordinates
     rsc_subset& s = c->subsets[i];
     if (!s.soa) continue;
-    gather_subset_kernel<<<(unsigned)((s.m + 255) / 256), 256, 0, c->ctx->stream>>>(c->soa, c->n_pad, s.idx, s.m, s.m_pad, s.soa);
-    RSC_CUDA(c->ctx, cudaGetLastError());
+    if (s.m > 0) {
+      gather_subset_kernel<<<(unsigned)((s.m + 255) / 256), 256, 0, c->ctx->stream>>>(c->soa, c->n_pad, s.idx, s.m, s.m_pad, s.soa);
+      RSC_CUDA(c->ctx, cudaGetLastError());
+    }
     RSC_CUDA(c->ctx, cudaMemcpyAsync(s.enabled, s.valid, (size_t)(s.m_pad / 32) * 4, cudaMemcpyDeviceToDevice, c->ctx->stream));
   }
   RSC_CUDA(c->ctx, cudaStreamSynchronize(c->ctx->stream));
@@ -267,6 +333,7 @@ void rsc_cloud_destroy(rsc_cloud* c) {
     if (s.idx) cudaFree(s.idx);
   }
   if (c->soa) cudaFree(c->soa);
+  if (c->g_enabled) cudaFree(c->g_enabled);
   if (c->enabled) cudaFree(c->enabled);
   if (c->valid) cudaFree(c->valid);
   delete c;
@@ -279,8 +346,19 @@ int32_t rsc_cloud_set_subset(rsc_cloud* c, int32_t subset_id, const int64_t* idx
   if (int32_t rcr = cloud_ready(c)) return rcr;
   rsc_ctx* ctx = c->ctx;
   if (subset_id < 0 || subset_id > 4095 || !idx || m <= 0) return fail(ctx, RSC_E_ARG, "set_subset: bad arguments");
-  for (int64_t j = 0; j < m; ++j)
-    if (idx[j] < 0 || idx[j] >= c->n) return fail(ctx, RSC_E_ARG, "set_subset: index out of range");
+  const int64_t m_global = m;
+  std::vector<int64_t> local;  // shard: the entries of this rank's range, as local indices, in subset order
+  if (c->is_shard()) {
+    for (int64_t j = 0; j < m; ++j) {
+      if (idx[j] < 0 || idx[j] >= c->n_global) return fail(ctx, RSC_E_ARG, "set_subset: index out of range");
+      if (idx[j] >= c->global_offset && idx[j] < c->global_offset + c->n) local.push_back(idx[j] - c->global_offset);
+    }
+    idx = local.data();
+    m = (int64_t)local.size();
+  } else {
+    for (int64_t j = 0; j < m; ++j)
+      if (idx[j] < 0 || idx[j] >= c->n) return fail(ctx, RSC_E_ARG, "set_subset: index out of range");
+  }
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   if ((size_t)subset_id >= c->subsets.size()) c->subsets.resize(subset_id + 1);
   rsc_subset& s = c->subsets[subset_id];
@@ -289,22 +367,26 @@ int32_t rsc_cloud_set_subset(rsc_cloud* c, int32_t subset_id, const int64_t* idx
     s = rsc_subset();
   }
   s.m = m;
+  s.m_global = m_global;
   s.m_pad = (m + kTile - 1) / kTile * kTile;
+  if (s.m_pad == 0) s.m_pad = kTile;  // a rank may own no point of the subset: one all-padding tile
   const int64_t words = s.m_pad / 32;
   cudaStream_t st = ctx->stream;
   cudaError_t e;
   if ((e = cudaMalloc(&s.soa, (size_t)6 * s.m_pad * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&s.enabled, (size_t)words * 4)) != cudaSuccess ||
       (e = cudaMalloc(&s.valid, (size_t)words * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&s.idx, (size_t)m * sizeof(int64_t))) != cudaSuccess) {
+      (e = cudaMalloc(&s.idx, (size_t)(m > 0 ? m : 1) * sizeof(int64_t))) != cudaSuccess) {
     cudaFree(s.soa), cudaFree(s.enabled), cudaFree(s.valid), cudaFree(s.idx);  // cudaFree(nullptr) is a no-op
     s = rsc_subset();  // not uploaded
     return fail_cuda(ctx, e, "set_subset: cudaMalloc");
   }
   RSC_CUDA(ctx, cudaMemsetAsync(s.soa, 0, (size_t)6 * s.m_pad * sizeof(float), st));
-  RSC_CUDA(ctx, cudaMemcpyAsync(s.idx, idx, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  gather_subset_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(c->soa, c->n_pad, s.idx, m, s.m_pad, s.soa);
-  RSC_CUDA(ctx, cudaGetLastError());
+  if (m > 0) {
+    RSC_CUDA(ctx, cudaMemcpyAsync(s.idx, idx, (size_t)m * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    gather_subset_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(c->soa, c->n_pad, s.idx, m, s.m_pad, s.soa);
+    RSC_CUDA(ctx, cudaGetLastError());
+  }
   fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(s.valid, nullptr, m, words);
   RSC_CUDA(ctx, cudaGetLastError());
   gather_enabled_kernel<<<(unsigned)((words * 32 + 255) / 256), 256, 0, st>>>(c->enabled, s.idx, m, words, s.enabled);
@@ -353,6 +435,10 @@ int32_t rsc_cloud_enable_all(rsc_cloud* c) {
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   c->enabled_changed();
   RSC_CUDA(ctx, cudaMemcpyAsync(c->enabled, c->valid, (size_t)(c->n_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (c->is_shard()) {  // every rank enables all of its points: so does the replicated mask
+    fill_valid_kernel<<<(unsigned)((c->g_words + 255) / 256), 256, 0, ctx->stream>>>(c->g_enabled, nullptr, c->n_global, c->g_words);
+    RSC_CUDA(ctx, cudaGetLastError());
+  }
   for (auto& s : c->subsets)
     if (s.soa)
       RSC_CUDA(ctx, cudaMemcpyAsync(s.enabled, s.valid, (size_t)(s.m_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -365,14 +451,7 @@ int64_t rsc_cloud_count_enabled(rsc_cloud* c) {
   if (cloud_ready(c)) return -1;
   rsc_ctx* ctx = c->ctx;
   if (cudaSetDevice(ctx->device) != cudaSuccess) return -1;
-  if (ctx->misc.ensure(16) != cudaSuccess) return -1;
-  unsigned long long* d = ctx->misc.as<unsigned long long>();
-  cudaMemsetAsync(d, 0, 8, ctx->stream);
-  popc_words_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(c->enabled, c->n_pad / 32, d);
-  unsigned long long h = 0;
-  cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
-  if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
-  return (int64_t)h;
+  return count_mask_bits(ctx, c->enabled, c->n_pad / 32);
 }
 
 }  // extern "C"

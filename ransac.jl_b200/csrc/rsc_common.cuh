@@ -94,16 +94,20 @@ struct rsc_ctx {
   rsc_stats stats{};
   // scratch of the score path
   rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, pairs, wl_count, aux;
-  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf, cullbuf;
+  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf, cullbuf, shardbuf, gselbuf;
   size_t wl_cap = 1u << 22;  // guard-band queue capacity (groups / pairs), grows on overflow
   rsc_allreduce_fn allreduce = nullptr;  // sums int32 device buffers across the ranks of a sharded run
   void* allreduce_user = nullptr;
+  void* comm = nullptr;                  // ncclComm_t of rsc_ctx_comm_init (rsc_comm.cu); allreduce then points into the library
+  int rank = 0, nranks = 1;
+  int64_t allreduce_calls = 0, allreduce_bytes = 0;
   void* pinned = nullptr;    // small pinned staging area
   size_t pinned_cap = 0;
 };
 
 struct rsc_subset {
   int64_t m = 0, m_pad = 0;
+  int64_t m_global = 0;        // size of the whole subset (= m unless the cloud is a shard: then m counts this rank's entries)
   float* soa = nullptr;        // 6 * m_pad floats
   uint32_t* enabled = nullptr; // m_pad/32 words
   uint32_t* valid = nullptr;
@@ -146,6 +150,12 @@ struct rsc_cloud {
   // rank/select index over `enabled` for the sampler (rsc_fit.cu); rebuilt lazily after any change
   rsc::DevBuf selbuf;
   bool sel_valid = false;
+  // sharded storage (rsc_cloud_create_shard with n_global > n): isenabled of the WHOLE cloud, replicated on
+  // every rank (1 bit/point) so that all ranks draw the same minimal sets; kept equal by all-reducing
+  // the cleared words after every extraction.  g_words is a multiple of 16 (512 points).
+  uint32_t* g_enabled = nullptr;
+  int64_t g_words = 0;
+  bool is_shard() const { return g_enabled != nullptr; }
   rsc_cells cells;
   // every change of `enabled` goes through here: the cached sampler indices are rebuilt lazily
   void enabled_changed() {
@@ -229,10 +239,22 @@ struct FitScratch {
   int32_t* out_set;
   int64_t* idx;
   int32_t* level;  // per set: octree level its cell came from (cell sampler only)
+  float* gath;     // sharded storage: [S][k][6] coordinates + normals of the drawn points, gathered from their owners
 };
 int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
                     const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
                     FitScratch* fs, const double* cum = nullptr);
+int64_t count_mask_bits(rsc_ctx* ctx, const uint32_t* words, int64_t nwords);
+// sharded storage: (re)build the replicated whole-cloud enabled mask from the ranks' local masks (collective)
+int32_t shard_sync_enabled(rsc_cloud* cloud, cudaStream_t st);
+// sharded storage, after an extraction: clear the bits of the ranks' local inlier-mask words `inl_local`
+// (n_pad/32 words) in the replicated mask; the int32 behind the words carries `extra` values summed over
+// the ranks too (returned in d_extra_out[0..n_extra), device) -- collective
+int32_t shard_clear_enabled(rsc_cloud* cloud, const uint32_t* inl_local, const int32_t* d_extra_in, int n_extra,
+                            int32_t* d_extra_out, cudaStream_t st);
+// the two loops behind rsc_ransac_run (rsc_loop.cu: reference behaviour, decisions on the device;
+// rsc_run.cu: the extension switches, host-walked)
+int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc_run* run);
 void loop_scratch_free(rsc_ctx* ctx);
 int32_t fit_reserve(rsc_ctx* ctx, const rsc_params* params, int S);
 // exclusive scan of n uint32 counts into 64-bit offsets (+ total) on `st` (rsc_fit.cu)

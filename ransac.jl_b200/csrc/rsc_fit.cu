@@ -388,7 +388,20 @@ struct GatherSrc {
   int64_t n_pad;
   const double* P;   // explicit coordinates S x k x 3 (used when soa == nullptr)
   const double* N;
+  const float* G;    // sharded storage: [S][k][6] float32 x y z nx ny nz gathered from the owning ranks
 };
+
+// sharded storage: every rank writes the bit patterns of the drawn points it owns (zeros for the others);
+// an int32 sum over the ranks then leaves every set's coordinates on every rank, bit for bit
+__global__ void gather_owned_kernel(const int64_t* __restrict__ idx, int64_t nidx, const float* __restrict__ soa, int64_t n_pad,
+                                    int64_t goff, int64_t n_local, float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nidx) return;
+  const int64_t g = idx[j] - goff;
+  const bool mine = idx[j] >= 0 && g >= 0 && g < n_local;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) out[j * 6 + f] = mine ? __ldg(soa + f * n_pad + g) : 0.f;
+}
 
 // samplepointcloud4! on the root cell: one thread per minimal set, writes its k indices (-1 = failed)
 __global__ void __launch_bounds__(128) sample_kernel(int S, int k, uint64_t seed, uint64_t set0, int64_t n_points,
@@ -520,7 +533,14 @@ __global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* 
   const size_t slot = (size_t)s * f.ntypes + t;
   flags[slot] = 0;
   D3 p[kMaxK], n[kMaxK];
-  if (src.soa) {
+  if (src.G) {
+    if (idx[(size_t)s * f.k] < 0) return;
+    for (int q = 0; q < f.k; ++q) {
+      const float* g = src.G + ((size_t)s * f.k + q) * 6;
+      p[q] = D3{(double)g[0], (double)g[1], (double)g[2]};
+      n[q] = D3{(double)g[3], (double)g[4], (double)g[5]};
+    }
+  } else if (src.soa) {
     if (idx[(size_t)s * f.k] < 0) return;
     for (int q = 0; q < f.k; ++q) {
       const int64_t i = idx[(size_t)s * f.k + q];
@@ -604,6 +624,7 @@ static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
   const size_t o_dense = take(slots * sizeof(rsc_cand)), o_out = take(slots * sizeof(rsc_cand));
   const size_t o_flags = take(slots * 4), o_offs = take(slots * 8), o_total = take(8);
   const size_t o_set = take(slots * 4), o_idx = take((size_t)S * k * 8), o_level = take((size_t)S * 4);
+  const size_t o_gath = take((size_t)S * k * 6 * 4);
   RSC_CUDA(ctx, ctx->fitbuf.ensure(off));
   char* b = ctx->fitbuf.as<char>();
   fs->dense = (rsc_cand*)(b + o_dense);
@@ -614,6 +635,7 @@ static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
   fs->out_set = (int32_t*)(b + o_set);
   fs->idx = (int64_t*)(b + o_idx);
   fs->level = (int32_t*)(b + o_level);
+  fs->gath = (float*)(b + o_gath);
   return RSC_OK;
 }
 
@@ -621,7 +643,9 @@ static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
 int32_t build_select_index(rsc_cloud* cloud, cudaStream_t st, unsigned long long** boff, int* nblk,
                            unsigned long long** n_enabled) {
   rsc_ctx* ctx = cloud->ctx;
-  const int64_t words = cloud->n_pad / 32;
+  // a shard samples from the replicated whole-cloud mask (same sets on every rank)
+  const uint32_t* mask = cloud->is_shard() ? cloud->g_enabled : cloud->enabled;
+  const int64_t words = cloud->is_shard() ? cloud->g_words : cloud->n_pad / 32;
   const int nb = (int)((words + kSelWords - 1) / kSelWords);
   RSC_CUDA(ctx, cloud->selbuf.ensure((size_t)nb * (4 + 8) + 64));
   char* b = cloud->selbuf.as<char>();
@@ -629,7 +653,7 @@ int32_t build_select_index(rsc_cloud* cloud, cudaStream_t st, unsigned long long
   unsigned long long* total = offs + nb;
   uint32_t* cnt = (uint32_t*)(total + 1);
   if (!cloud->sel_valid) {
-    block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(cloud->enabled, words, cnt, nb);
+    block_popc_kernel<<<(nb + 255) / 256, 256, 0, st>>>(mask, words, cnt, nb);
     RSC_CUDA(ctx, cudaGetLastError());
     if (int32_t rcs = scan_u32(ctx, cnt, nb, offs, total, st)) return rcs;
     cloud->sel_valid = true;
@@ -818,7 +842,9 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
   if (rc) return rc;
   if ((rc = carve(ctx, S, f.ntypes, k, fs))) return rc;
   const int slots = S * f.ntypes;
-  GatherSrc src{nullptr, 0, dP, dN};
+  GatherSrc src{nullptr, 0, dP, dN, nullptr};
+  const bool shard = cloud && cloud->is_shard();
+  if (shard && mode != 2) return fail(ctx, RSC_E_STATE, "fit: a shard (sharded storage) only supports the root-cell sampler of rsc_ransac_run");
   unsigned long long *boff = nullptr, *nen = nullptr;
   int nblk = 0;
   if (mode != 0) {
@@ -834,6 +860,19 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
       sample_cells_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, k, seed, set0, cloud->n, cloud->enabled, cloud->n_pad / 32, cv,
                                                            fs->idx, fs->level);
       RSC_CUDA(ctx, cudaGetLastError());
+      use_idx = fs->idx;
+    } else if (mode == 2 && shard) {
+      // sharded storage: global indices from the replicated mask, coordinates gathered from their owners
+      sample_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, k, seed, set0, cloud->n_global, cloud->g_enabled, cloud->g_words, boff, nblk,
+                                                     nen, fs->idx);
+      RSC_CUDA(ctx, cudaGetLastError());
+      const int64_t nidx = (int64_t)S * k;
+      gather_owned_kernel<<<(unsigned)((nidx + 255) / 256), 256, 0, st>>>(fs->idx, nidx, cloud->soa, cloud->n_pad, cloud->global_offset,
+                                                                           cloud->n, fs->gath);
+      RSC_CUDA(ctx, cudaGetLastError());
+      if (!ctx->allreduce || ctx->allreduce(ctx->allreduce_user, fs->gath, nidx * 6, (void*)st))
+        return fail(ctx, RSC_E_NCCL, "fit: gathering the minimal sets' coordinates (all-reduce) failed");
+      src.G = fs->gath;
       use_idx = fs->idx;
     } else if (mode == 2) {
       sample_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, k, seed, set0, cloud->n, cloud->enabled, cloud->n_pad / 32, boff, nblk,

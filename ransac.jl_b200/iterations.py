@@ -74,8 +74,15 @@ def _ransac_device(pc, params, seed, sampler="root", lsq=False, progressive=Fals
             idx = np.empty(n.value, dtype=np.int64)  # filled by rsc_run_inpoints (device -> host)
             if n.value:
                 pc.ctx.check(lib.rsc_run_inpoints(run, i, idx.ctypes.data))
-            out.append(ExtractedShape(from_cand(cand), idx))
+            ex = ExtractedShape(from_cand(cand), idx)
+            # sharded storage: `inpoints` is this rank's part of the list (shard.gather_extracted joins them)
+            ex.total = int(lib.rsc_run_shape_total(run, i))
+            out.append(ex)
         secs = lib.rsc_run_seconds(run)
+        nbatch = C.c_int32()
+        pc.last_run_syncs = int(lib.rsc_run_syncs(run, C.byref(nbatch)))
+        pc.last_run_batches = int(nbatch.value)
+        pc.last_run_iterations = int(lib.rsc_run_iterations(run))
         pc.last_refined = int(lib.rsc_run_refined(run))
         lw, ls = np.zeros(11), np.zeros(11)
         nl = lib.rsc_run_levelweight(run, lw.ctypes.data, ls.ctypes.data)

@@ -1,14 +1,20 @@
-"""Point-range sharding over the GPUs of one box: one process per GPU (torch.distributed, NCCL).
+"""Point-range sharding over the GPUs of one box: one process per GPU (include/rsc.h, "point-range
+sharding").
 
-Every rank holds the whole cloud (the sampler needs random access and all ranks draw the same
-Philox minimal sets), scores and refits only its own point range, and the per-candidate counts and
-inlier-mask words are summed with an NCCL all-reduce that the C library triggers through a callback
-(`rsc_ctx_set_allreduce`).  The same partition is used by bench.py for the scoring microbenchmark.
+`ShardedCloud` is the sharded-storage layout: every rank uploads only its own point range
+(`partition`), the library keeps the whole cloud's enabled mask replicated, draws identical Philox
+minimal sets on every rank and gathers their coordinates from the owning ranks; per-candidate counts,
+K5 hits and the cleared enabled words are summed with NCCL **inside the library**
+(`rsc_ctx_comm_init`; torch.distributed only carries the 128-byte NCCL id from rank 0 to the others).
+`ShardedContext` is the older replicated-storage layout (whole cloud on every rank + a range per rank),
+which also supports the extension switches; it can use the library's NCCL too or a host callback.
 """
 from __future__ import annotations
 
 import ctypes as C
 from typing import List, Tuple
+
+import numpy as np
 
 from . import _lib
 from ._lib import lib
@@ -28,6 +34,31 @@ def partition(n: int, world: int, align: int = ALIGN) -> List[Tuple[int, int]]:
     return out
 
 
+def init_comm(ctx, group=None) -> None:
+    """NCCL communicator of the library on `ctx` (one per process): rank 0 draws the NCCL unique id,
+    torch.distributed broadcasts its 128 bytes, every rank calls rsc_ctx_comm_init (collective)."""
+    import torch.distributed as dist
+
+    if getattr(ctx, "_comm", False):
+        return
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ident = [None]
+    if rank == 0:
+        buf = (C.c_uint8 * 128)()
+        ctx.check(lib.rsc_comm_unique_id(buf))
+        ident = [bytes(buf)]
+    dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    buf = (C.c_uint8 * 128).from_buffer_copy(ident[0])
+    ctx.check(lib.rsc_ctx_comm_init(ctx.h, buf, rank, world))
+    ctx._comm = True
+
+
+def close_comm(ctx) -> None:
+    if getattr(ctx, "_comm", False):
+        lib.rsc_ctx_comm_destroy(ctx.h)
+        ctx._comm = False
+
+
 class _DevInt32:
     """__cuda_array_interface__ view of a raw device pointer (int32[n])."""
 
@@ -35,10 +66,29 @@ class _DevInt32:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 3}
 
 
-class ShardedContext:
-    """Installs the NCCL all-reduce callback on a context and the rank's point range on a cloud."""
+def ShardedCloud(vertices_local, normals_local, subsets, rank_range: Tuple[int, int], n_global: int, device: int = 0,
+                 group=None, comm: str = "nccl"):
+    """Sharded storage: a RANSACCloud over this rank's range [lo, hi) of a cloud of n_global points.
+    `subsets` = the whole cloud's subsets (global indices, the same on every rank); `comm` = "nccl" (the
+    library's own communicator) or "callback" (torch.distributed through rsc_ctx_set_allreduce)."""
+    from .cloud import RANSACCloud
 
-    def __init__(self, pc, group=None):
+    lo, hi = rank_range
+    assert len(vertices_local) == hi - lo
+    pc = RANSACCloud(vertices_local, normals_local, subsets, device=device, shard=(lo, n_global))
+    if comm == "nccl":
+        init_comm(pc.ctx, group)
+    else:
+        pc._sharded = ShardedContext(pc, group, set_range=False, comm=comm)
+    return pc
+
+
+class ShardedContext:
+    """Replicated storage: installs an all-reduce (host callback into torch.distributed, or the library's
+    NCCL with comm="nccl") on a context and the rank's point range on a cloud.  comm="host" stages the
+    callback through host memory (any torch.distributed backend, e.g. gloo: ranks may then share a GPU)."""
+
+    def __init__(self, pc, group=None, set_range: bool = True, comm: str = "callback"):
         import torch
         import torch.distributed as dist
 
@@ -46,23 +96,48 @@ class ShardedContext:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.range = partition(pc.size, self.world)[self.rank]
-        ext = torch.cuda.ExternalStream(pc.ctx.stream, device=torch.device("cuda", pc.ctx.device))
+        self.comm = comm
+        if comm == "nccl":
+            init_comm(pc.ctx, group)
+        else:
+            ext = torch.cuda.ExternalStream(pc.ctx.stream, device=torch.device("cuda", pc.ctx.device))
+            host_staged = comm == "host"  # e.g. a gloo group: several ranks may then share one GPU (tests)
 
-        def _allreduce(user, ptr, count, stream):
-            try:
-                t = torch.as_tensor(_DevInt32(ptr, count), device=torch.device("cuda", pc.ctx.device))
-                with torch.cuda.stream(ext):
-                    dist.all_reduce(t, group=group)
-                return 0
-            except Exception as e:  # never let an exception cross the C boundary
-                print(f"[rsc] all-reduce callback failed: {e!r}")
-                return 1
+            def _allreduce(user, ptr, count, stream):
+                try:
+                    t = torch.as_tensor(_DevInt32(ptr, count), device=torch.device("cuda", pc.ctx.device))
+                    with torch.cuda.stream(ext):
+                        if host_staged:
+                            h = t.cpu()
+                            dist.all_reduce(h, group=group)
+                            t.copy_(h)
+                        else:
+                            dist.all_reduce(t, group=group)
+                    return 0
+                except Exception as e:  # never let an exception cross the C boundary
+                    print(f"[rsc] all-reduce callback failed: {e!r}")
+                    return 1
 
-        self._cb = _lib.ALLREDUCE_FN(_allreduce)  # keep alive
-        pc.ctx.check(lib.rsc_ctx_set_allreduce(pc.ctx.h, C.cast(self._cb, C.c_void_p), None))
-        lo, hi = self.range
-        if hi > lo:
+            self._cb = _lib.ALLREDUCE_FN(_allreduce)  # keep alive
+            pc.ctx.check(lib.rsc_ctx_set_allreduce(pc.ctx.h, C.cast(self._cb, C.c_void_p), None))
+        if set_range:
+            lo, hi = self.range  # an empty range (lo == hi) is a rank that only joins the all-reduces
             pc.ctx.check(lib.rsc_cloud_set_range(pc.handle, lo, hi))
 
     def close(self):
-        lib.rsc_ctx_set_allreduce(self.pc.ctx.h, None, None)
+        if self.comm == "nccl":
+            close_comm(self.pc.ctx)
+        else:
+            lib.rsc_ctx_set_allreduce(self.pc.ctx.h, None, None)
+
+
+def gather_extracted(extracted, group=None):
+    """Sharded storage leaves every shape's inlier list distributed (each rank holds the ascending
+    indices of its range): concatenate the parts in rank order on every rank (torch.distributed)."""
+    import torch.distributed as dist
+
+    from .shapes import ExtractedShape
+
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, [e.inpoints for e in extracted], group=group)
+    return [ExtractedShape(e.shape, np.concatenate([p[i] for p in parts])) for i, e in enumerate(extracted)]
