@@ -195,6 +195,16 @@ int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand
  * set; gated like the counts), written to DEVICE memory -- the counts+masks variant without a host round trip. */
 int32_t rsc_score_dev_masks(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,
                             int32_t subset_id, int32_t* d_counts, uint32_t* d_masks, void* stream);
+/* Audit hook for the exactness argument: the FP32 MARGINS the tiled kernels compute
+ * for C candidates x the points [point0, point0+npoints) of the whole cloud -- the packed FFMA2 evaluation
+ * of score_kernel with the hardware's MUFU.RSQ and contraction -- candidate-major into margins[C][npoints];
+ * bands[C] = each candidate's guard band (a pair is decided in FP32 only if |margin| > band), col_types[C] =
+ * the evaluation form (0..3, 4 = wide cone: the margin is in units of 1/cos or 1/sin of the half angle),
+ * *packed_vs_scalar_diffs = pairs on which the packed and the scalar evaluation differ in any bit.
+ * tests/test_guard_band_gpu.py checks |margin - float64 margin| < band / 2 on 10^8 pairs.  All outs but
+ * margins are nullable. */
+int32_t rsc_debug_margins(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int64_t point0,
+                          int64_t npoints, float* margins, float* bands, int32_t* col_types, int64_t* packed_vs_scalar_diffs);
 /* estimatescore (confidenceintervals.jl:53-74), Int64 wrap-around included (Q9). */
 void rsc_estimate_score(int64_t subset_len, int64_t cloud_len, int64_t count, double* out_min,
                         double* out_max, double* out_E);

@@ -78,6 +78,8 @@ end
 # ---- context / cloud handles ---------------------------------------------------------------------
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
 
+version() = ccall((:rsc_version, LIB[]), Int32, ())
+
 function check(rc)
     rc == 0 && return
     msg = unsafe_string(ccall((:rsc_last_error, LIB[]), Cstring, (Ptr{Cvoid},), CTX[]))
@@ -206,6 +208,63 @@ function fit_batch(dc::DeviceCloud, idx::Matrix{Int}, params)
                 dc.h, prm, Int64.(idx .- 1), S, out, out_set, n))
     [fromcand(out[i]) for i in 1:n[]], out_set[1:n[]] .+ 1
 end
+
+"""
+    loop_with_sets(pc, params, sets)
+
+RANSAC.jl's loop (iterations.jl:35-162) with the device doing the work of `forcefitshapes!`,
+`scorecandidates!` and `refit` through the per-call ABI, on minimal sets given explicitly (`sets[k][i]` =
+0-based index triple of set i of iteration k, or `nothing`): the form in which a run is comparable with
+the package itself set for set (julia/make_golden.jl, test/runtests.jl).  Returns
+`(extracted, extracted_at, iterations)`.
+"""
+function loop_with_sets(pc::RANSACCloud, params, sets)
+    it = params.iteration
+    dc = DeviceCloud(pc)
+    shapes = FittedShape[]; scores = ConfidenceInterval[]; inpts = Vector{Int}[]
+    extracted = ExtractedShape[]; extracted_at = Int[]
+    cc = [0, 0, 0]
+    iterations = 0
+    for k in 1:it.itermax
+        count(pc.isenabled) < it.τ && break
+        iterations = k
+        trip = [Int.(sets[k][i]) .+ 1 for i in 1:it.minsubsetN if k <= length(sets) && sets[k][i] !== nothing]
+        cands = isempty(trip) ? FittedShape[] : fit_batch(dc, hcat(trip...), params)[1]
+        cc[2] += length(cands)
+        if !isempty(cands)
+            for (c, (sc, ip)) in zip(cands, scorecandidates(dc, collect(FittedShape, cands), 1, params))
+                push!(shapes, c); push!(scores, sc); push!(inpts, ip)
+            end
+        end
+        cc[3] = k * it.minsubsetN
+        cc[1] = length(shapes)
+        if !isempty(shapes)
+            best = RANSAC.findhighestscore(RANSAC.IterationCandidates(shapes, scores, inpts))
+            scr = RANSAC.E(scores[best.index])
+            if RANSAC.prob(scr, RANSAC.chooseS(cc, it.extract_s), pc.size, it.drawN) > it.prob_det
+                ex = refit_extract!(dc, shapes[best.index], params)       # also clears pc.isenabled
+                push!(extracted, ex); push!(extracted_at, k)
+                deleteat!(shapes, best.index); deleteat!(scores, best.index); deleteat!(inpts, best.index)
+                dead = [j for j in eachindex(inpts) if !all(pc.isenabled[inpts[j]])]
+                deleteat!(shapes, dead); deleteat!(scores, dead); deleteat!(inpts, dead)
+            end
+        end
+        RANSAC.prob(it.τ, RANSAC.chooseS(cc, it.terminate_s), pc.size, it.drawN) > it.prob_det && break
+    end
+    extracted, extracted_at, iterations
+end
+
+# ---- one process per GPU: sharded storage (include/rsc.h "point-range sharding") ---------------------
+"rank 0: the 128-byte NCCL id to hand to the other ranks (MPI.jl bcast, a socket, a file)"
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    rc = ccall((:rsc_comm_unique_id, LIB[]), Int32, (Ptr{UInt8},), id)
+    rc == 0 || error("rsc_comm_unique_id failed ($rc): libnccl.so.2 not loadable?")
+    id
+end
+"every rank: NCCL communicator inside the library (collective)"
+comm_init(id::Vector{UInt8}, rank::Integer, nranks::Integer) =
+    check(ccall((:rsc_ctx_comm_init, LIB[]), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), context(), id, rank, nranks))
 
 """
     ransac(pc, params, setenabled; reset_rand=false, seed=1234, sampler=:root, octree_levels=8,

@@ -309,6 +309,44 @@ int32_t rsc_score_dev_masks(rsc_cloud* cloud, const rsc_params* params, const rs
   return masks_to_candidate_major(ctx, C, ps.n, st, d_masks);
 }
 
+// Audit of the FP32 guard band on the real hardware: the margins the tiled kernels compute.
+int32_t rsc_debug_margins(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int64_t point0,
+                          int64_t npoints, float* margins, float* bands, int32_t* col_types, int64_t* packed_vs_scalar_diffs) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (C <= 0 || C > 65535 || !cands || !margins || npoints <= 0 || point0 < 0 || point0 + npoints > cloud->n)
+    return fail(ctx, RSC_E_ARG, "debug_margins: bad arguments (1 <= C <= 65535, point range inside the cloud)");
+  int32_t rc = check_params(ctx, params);
+  if (rc) return rc;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((rc = cloud_ready(cloud))) return rc;
+  cudaStream_t st = ctx->stream;
+  const size_t o_rec = ((size_t)C * sizeof(rsc_cand) + 255) / 256 * 256, o_col = o_rec + ((size_t)C * kRecFields * 4 + 255) / 256 * 256;
+  const size_t o_diff = o_col + ((size_t)C * 4 + 255) / 256 * 256, o_out = o_diff + 256;
+  RSC_CUDA(ctx, ctx->cullbuf.ensure(o_out + (size_t)C * npoints * 4));
+  char* b = ctx->cullbuf.as<char>();
+  rsc_cand* d_c = (rsc_cand*)b;
+  float* d_rec = (float*)(b + o_rec);
+  int32_t* d_col = (int32_t*)(b + o_col);
+  unsigned long long* d_diff = (unsigned long long*)(b + o_diff);
+  float* d_out = (float*)(b + o_out);
+  RSC_CUDA(ctx, cudaMemcpyAsync(d_c, cands, (size_t)C * sizeof(rsc_cand), cudaMemcpyHostToDevice, st));
+  RSC_CUDA(ctx, cudaMemsetAsync(d_diff, 0, 8, st));
+  if ((rc = audit_margins(ctx, cloud, view_cloud(cloud), make_thresh(params), d_c, C, point0, npoints, d_out, d_rec, d_col, d_diff, st)))
+    return rc;
+  RSC_CUDA(ctx, cudaMemcpyAsync(margins, d_out, (size_t)C * npoints * 4, cudaMemcpyDeviceToHost, st));
+  std::vector<float> rec((size_t)C * kRecFields);
+  RSC_CUDA(ctx, cudaMemcpyAsync(rec.data(), d_rec, rec.size() * 4, cudaMemcpyDeviceToHost, st));
+  if (col_types) RSC_CUDA(ctx, cudaMemcpyAsync(col_types, d_col, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+  unsigned long long diffs = 0;
+  RSC_CUDA(ctx, cudaMemcpyAsync(&diffs, d_diff, 8, cudaMemcpyDeviceToHost, st));
+  RSC_CUDA(ctx, cudaStreamSynchronize(st));
+  if (bands)
+    for (int i = 0; i < C; ++i) bands[i] = rec[(size_t)i * kRecFields + kBandField];
+  if (packed_vs_scalar_diffs) *packed_vs_scalar_diffs = (int64_t)diffs;
+  return RSC_OK;
+}
+
 static inline int64_t wrapmul(int64_t a, int64_t b) { return (int64_t)((uint64_t)a * (uint64_t)b); }
 
 void rsc_estimate_score(int64_t subset_len, int64_t cloud_len, int64_t count, double* out_min, double* out_max,

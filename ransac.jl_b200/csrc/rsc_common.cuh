@@ -218,6 +218,8 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
                       cudaStream_t st, int32_t* d_counts_valid = nullptr,
                       int32_t* d_counts_enabled = nullptr, const double* d_trig = nullptr,
                       const uint32_t* d_bounds = nullptr, bool accumulate = false);
+int32_t audit_margins(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th, const rsc_cand* d_cands, int32_t C,
+                      int64_t p0, int64_t np, float* d_out, float* d_rec, int32_t* d_cols, unsigned long long* d_diffs, cudaStream_t st);
 // waits for a chunked upload to land and finalises the cloud's guard-band scales
 int32_t cloud_ready(rsc_cloud* cloud);
 // refresh the gathered enabled bits of every uploaded subset from the cloud's enabled mask

@@ -103,14 +103,16 @@ __device__ __forceinline__ void issue_subtile(const float* src, int64_t stride, 
 template <int T, int K, int U, bool MASKS>
 __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float* wstage, uint64_t* wbar) {
   constexpr int NR = RecN<T>::n;
-  constexpr bool kPacked = (K % 2 == 0);
+  // U = 5 / 6: SCALAR evaluation (one FFMA per candidate and point; 5 = point-major, 6 = candidate-major source
+  // order) -- three 32-bit sources per instruction instead of the packed forms' 64/32/64-bit, see DESIGN.md 3
+  constexpr bool kPacked = (K % 2 == 0) && U < 5;
   constexpr int KP = kPacked ? K / 2 : 1;
   // U = 3: pair-major source order (all four points of a pair, then the next pair).  ptxas schedules the
   // block itself, but from this order it finds 1-5 % better operand reuse than from point-major (U = 1);
   // a lockstep order (every formula step for the four points back to back) and eight points per pair
   // were measured and are no better.
   constexpr bool kOrderJQ = (U == 3);
-  float r[kPacked ? 1 : K][NR];  // scalar records (K odd)
+  float r[kPacked ? 1 : K][NR];  // scalar records (K odd, or the scalar tilings)
   float2 r2[KP][NR];             // packed records: .x = candidate 2j, .y = candidate 2j+1
   float band[K];
   int cnte[K], cntv[K];
@@ -175,6 +177,20 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
           mask[2 * j + 1] = __funnelshift_l(__float_as_uint(m[q].y), mask[2 * j + 1], 1);
           mabs[2 * j] = fmin_nan(mabs[2 * j], fabsf(m[q].x));
           mabs[2 * j + 1] = fmin_nan(mabs[2 * j + 1], fabsf(m[q].y));
+        }
+      }
+      return;
+    }
+    if constexpr (!kPacked && U == 6) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m[q] = eval<T>(r[k], px[q], py[q], pz[q], nx[q], ny[q], nz[q], eps, cosa);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          mask[k] = __funnelshift_l(__float_as_uint(m[q]), mask[k], 1);
+          mabs[k] = fmin_nan(mabs[k], fabsf(m[q]));
         }
       }
       return;
@@ -612,6 +628,7 @@ struct Tiling {
   }
 static const Tiling kTilings[] = {
     RSC_TILING(1, 4, 1), RSC_TILING(2, 4, 1), RSC_TILING(4, 3, 1), RSC_TILING(4, 4, 1), RSC_TILING(8, 2, 1), RSC_TILING(4, 4, 3), RSC_TILING(4, 3, 3),
+    RSC_TILING(4, 4, 5), RSC_TILING(4, 3, 5), RSC_TILING(4, 4, 6), RSC_TILING(4, 3, 6), RSC_TILING(8, 2, 5),
 };
 static const Tiling* find_tiling(int K, int minb, int U) {
   for (const Tiling& t : kTilings)
@@ -797,6 +814,76 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
     select_counts_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_cands, C, cv, ce, th.honour_enabled, d_counts_policy);
     RSC_CUDA(ctx, cudaGetLastError());
   }
+  return RSC_OK;
+}
+
+// ---- audit of the guard band on the real hardware (rsc_debug_margins) --------------------------------
+__global__ void audit_compile_kernel(const rsc_cand* __restrict__ cands, int C, const Thresh th, float pmax, float nmax,
+                                     float* __restrict__ rec /*[C][kRecFields]*/, int32_t* __restrict__ cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C) return;
+  const int col = (cands[i].type < 0 || cands[i].type >= RSC_NTYPES) ? RSC_PLANE : col_type(cands[i]);
+  float r[kRecFields];
+  compile_record(cands[i], col, th, pmax, nmax, r);
+  for (int f = 0; f < kRecFields; ++f) rec[(size_t)i * kRecFields + f] = r[f];
+  cols[i] = col;
+}
+
+// margins through the PACKED evaluation (eval2<T>, both halves hold the candidate: what score_kernel
+// executes) and through the scalar one (eval<T>: the fix-up scan and K4); `diffs` counts pairs on which
+// the two differ in any bit
+template <int T>
+__device__ __forceinline__ float audit_one(const float* r, float px, float py, float pz, float nx, float ny, float nz, float eps,
+                                           float cosa, unsigned long long* diffs) {
+  float2 r2[RecN<T>::n];
+#pragma unroll
+  for (int f = 0; f < RecN<T>::n; ++f) r2[f] = make_float2(r[f], r[f]);
+  const float2 m2 = eval2<T>(r2, px, py, pz, nx, ny, nz, eps, cosa);
+  const float m1 = eval<T>(r, px, py, pz, nx, ny, nz, eps, cosa);
+  if (__float_as_uint(m2.x) != __float_as_uint(m1) || __float_as_uint(m2.y) != __float_as_uint(m1)) atomicAdd(diffs, 1ull);
+  return m2.x;
+}
+
+__global__ void __launch_bounds__(256) audit_margin_kernel(PointSet ps, Thresh th, const float* __restrict__ rec,
+                                                           const int32_t* __restrict__ cols, int64_t p0, int64_t np,
+                                                           float* __restrict__ out, unsigned long long* __restrict__ diffs) {
+  const int c = blockIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= np) return;
+  float r[kRecFields];
+#pragma unroll
+  for (int f = 0; f < kRecFields; ++f) r[f] = rec[(size_t)c * kRecFields + f];
+  const int col = cols[c], pt = public_type(col);
+  const int64_t i = p0 + j;
+  const float px = ps.x[i], py = ps.y[i], pz = ps.z[i], nx = ps.nx[i], ny = ps.ny[i], nz = ps.nz[i];
+  const float eps = th.eps[pt], cosa = th.cosa[pt];
+  float m;
+  switch (col) {
+    case RSC_PLANE:
+      m = audit_one<RSC_PLANE>(r, px, py, pz, nx, ny, nz, eps, cosa, diffs);
+      break;
+    case RSC_SPHERE:
+      m = audit_one<RSC_SPHERE>(r, px, py, pz, nx, ny, nz, eps, cosa, diffs);
+      break;
+    case RSC_CYLINDER:
+      m = audit_one<RSC_CYLINDER>(r, px, py, pz, nx, ny, nz, eps, cosa, diffs);
+      break;
+    case kConeWide:
+      m = audit_one<kConeWide>(r, px, py, pz, nx, ny, nz, eps, cosa, diffs);
+      break;
+    default:
+      m = audit_one<RSC_CONE>(r, px, py, pz, nx, ny, nz, eps, cosa, diffs);
+      break;
+  }
+  out[(size_t)c * np + j] = m;
+}
+
+int32_t audit_margins(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th, const rsc_cand* d_cands, int32_t C,
+                      int64_t p0, int64_t np, float* d_out, float* d_rec, int32_t* d_cols, unsigned long long* d_diffs, cudaStream_t st) {
+  audit_compile_kernel<<<(C + 127) / 128, 128, 0, st>>>(d_cands, C, th, cloud->pmax, cloud->nmax, d_rec, d_cols);
+  RSC_CUDA(ctx, cudaGetLastError());
+  audit_margin_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)C), 256, 0, st>>>(ps, th, d_rec, d_cols, p0, np, d_out, d_diffs);
+  RSC_CUDA(ctx, cudaGetLastError());
   return RSC_OK;
 }
 

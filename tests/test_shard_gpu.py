@@ -51,11 +51,11 @@ def _worker(rank, world, port, which, layout, q):
         ex, _ = R.ransac(pc, params, True, seed=seed)
         assert all(len(e.inpoints) == 0 or (e.inpoints.min() >= lo and e.inpoints.max() < hi) for e in ex)
         local_en = pc.isenabled
+        totals = [e.total for e in ex]
         ex = shard.gather_extracted(ex)
         parts = [None] * world
         dist.all_gather_object(parts, local_en)
         enabled = np.concatenate(parts)
-        totals = [e.total for e in ex]
     else:
         pc = R.RANSACCloud(sc.vertices, sc.normals, subsets)
         sh = shard.ShardedContext(pc, comm="host")
@@ -82,10 +82,21 @@ def test_two_ranks_one_gpu_match_c_oracle(which, layout):
     procs = [ctx.Process(target=_worker, args=(rk, 2, port, which, layout, q)) for rk in range(2)]
     for p in procs:
         p.start()
-    got, enabled, totals, syncs, batches = q.get(timeout=600)
+    import queue as _queue
+
+    res = None
+    for _ in range(120):  # a crashed worker must not leave the test waiting for the queue
+        try:
+            res = q.get(timeout=5)
+            break
+        except _queue.Empty:
+            if any(p.exitcode not in (None, 0) for p in procs):
+                break
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
+    assert res is not None
+    got, enabled, totals, syncs, batches = res
     sc, r, itp, seed = _scene(which)
     subsets = R.makesubsets(len(sc.vertices), r, np.random.default_rng(1234))
     want, en, info = c_oracle.ransac(sc.vertices, sc.normals, subsets[0], oracle_params(R.ransacparameters(iteration=itp)), seed)

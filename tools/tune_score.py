@@ -16,7 +16,7 @@ from ransac_jl_b200 import scenes
 from ransac_jl_b200._lib import lib
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 8 << 20
-CFGS = ["4,4,1", "4,3,1", "4,4,3", "4,3,3", "8,2,1"]
+CFGS = (os.environ.get("TUNE_CFGS") or "4,4,1;4,3,1;4,4,3;4,3,3;8,2,1;4,4,5;4,3,5;4,4,6;4,3,6;8,2,5").split(";")
 TYPES = ["PLANE", "SPHERE", "CYLINDER", "CONE"]
 FLOPS = {"PLANE": 13, "SPHERE": 16, "CYLINDER": 27, "CONE": 38}
 
