@@ -135,11 +135,44 @@ __global__ void newly_mask_kernel(uint32_t* __restrict__ old_en, const uint32_t*
   if (w < words) old_en[w] &= ~new_en[w];
 }
 
+// K5, gathered form: the newly disabled subset points (old & ~new) into a compact SoA scratch set of
+// `cap` points (the host sizes it by the extracted candidate's subset score, an upper bound of their
+// number); *over = 1 if they do not fit (then the host repeats K5 in the masked form)
+__global__ void newly_gather_capped_kernel(const uint32_t* __restrict__ old_en, const uint32_t* __restrict__ new_en, int64_t words,
+                                           const unsigned long long* __restrict__ offs, const unsigned long long* __restrict__ total,
+                                           const float* __restrict__ soa, int64_t m_pad, float* __restrict__ out, int64_t cap,
+                                           int32_t* __restrict__ over) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w == 0) *over = (*total > (unsigned long long)cap) ? 1 : 0;
+  if (w >= words) return;
+  uint32_t bits = old_en[w] & ~new_en[w];
+  unsigned long long o = offs[w];
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int64_t j = w * 32 + b;
+    if (o < (unsigned long long)cap) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) out[f * cap + o] = soa[f * m_pad + j];
+    }
+    ++o;
+  }
+}
+
+// valid (= enabled) words of the scratch set: the first *n points are real
+__global__ void fill_valid_dev_kernel(uint32_t* __restrict__ valid, const unsigned long long* __restrict__ n, int64_t words) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  const long long nn = (long long)*n, lo = w * 32;
+  valid[w] = lo + 32 <= nn ? 0xffffffffu : (lo < nn ? (1u << (nn - lo)) - 1u : 0u);
+}
+
 __global__ void k5_pack_kernel(LoopDev* __restrict__ d, const unsigned long long* __restrict__ ktot, const int32_t* __restrict__ ovf,
-                               const unsigned long long* __restrict__ total_local, K5Host* __restrict__ out) {
+                               const int32_t* __restrict__ over, const unsigned long long* __restrict__ total_local,
+                               K5Host* __restrict__ out) {
   out->kept = *ktot;
   out->total_local = *total_local;
-  out->ovf = *ovf;
+  out->ovf = (*ovf ? 1 : 0) + (*over ? 2 : 0);  // bit 0: guard-band queue overflow, bit 1: scratch set too small (any rank)
   out->tot_global = d->tot_global[0];
 }
 
@@ -318,11 +351,55 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
         if ((rc = shard_clear_enabled(cloud, ctx->idxbuf.as<uint32_t>(), dev->tot_global, 1, dev->tot_global, st))) return rc;
       }
       // ---- K5: drop the best and every candidate compatible with a newly disabled subset point ----
+      // Gathered form: the newly disabled points of this rank's subset slice go into a compact scratch
+      // set.  Their number is only known on the device, but it cannot exceed the candidate's subset
+      // score (every one of them was a compatible, enabled subset point when the candidate was scored;
+      // the enabled set only shrinks), which the host has from the decision record: that sizes the
+      // launch without a round trip.  Masked form (the least-squares refit moves the shape, so the bound
+      // does not hold; also the fallback): score against the whole slice under the mask old & ~new.
       const int nst = store.n;
-      newly_mask_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(ls.olden.as<uint32_t>(), sub.enabled, swords);
-      RUN_CUDA(cudaGetLastError());
+      bool masked = (p->compat_flags & RSC_REFIT_LSQ) != 0 || getenv("RSC_K5_MASKED") != nullptr;
       PointSet dps = sps;
-      dps.enabled = ls.olden.as<uint32_t>() + sps_word0;
+      // hit counts [nst] + two flags that ride with them through the all-reduce: guard-band queue overflow,
+      // scratch set too small
+      RUN_CUDA(ctx->counts.ensure(((size_t)3 * nst + 8) * 4));
+      int32_t* hit = ctx->counts.as<int32_t>() + 2 * (size_t)nst;
+      int32_t* d_over = hit + nst + 1;
+      RUN_CUDA(cudaMemsetAsync(d_over, 0, 4, st));
+      const int64_t sl_words = sps.n_pad / 32;
+      if (!masked && sl_words > 0) {
+        const int64_t cap = ((int64_t)std::max(rec.best_score, 1) + kTile - 1) / kTile * kTile;
+        const size_t o_woff = ((size_t)sl_words * 4 + 255) / 256 * 256;
+        RUN_CUDA(ls.prog.ensure(o_woff + (size_t)(sl_words + 2) * 8 + 64));
+        uint32_t* wcnt = ls.prog.as<uint32_t>();
+        unsigned long long* woff = (unsigned long long*)(ls.prog.as<char>() + o_woff);
+        unsigned long long* wtot = woff + sl_words;
+        const uint32_t* old_sl = ls.olden.as<uint32_t>() + sps_word0;
+        newly_count_kernel<<<(unsigned)((sl_words + 255) / 256), 256, 0, st>>>(old_sl, sps.enabled, sl_words, wcnt);
+        RUN_CUDA(cudaGetLastError());
+        if ((rc = scan_u32(ctx, wcnt, (int)sl_words, woff, wtot, st))) return rc;
+        RUN_CUDA(ls.nscratch.ensure((size_t)6 * cap * 4));
+        RUN_CUDA(ls.nvalid.ensure((size_t)(cap / 32) * 4));
+        RUN_CUDA(cudaMemsetAsync(ls.nscratch.p, 0, (size_t)6 * cap * 4, st));
+        newly_gather_capped_kernel<<<(unsigned)((sl_words + 255) / 256), 256, 0, st>>>(old_sl, sps.enabled, sl_words, woff, wtot, sps.x,
+                                                                                      sps.y - sps.x, ls.nscratch.as<float>(), cap, d_over);
+        RUN_CUDA(cudaGetLastError());
+        fill_valid_dev_kernel<<<(unsigned)((cap / 32 + 255) / 256), 256, 0, st>>>(ls.nvalid.as<uint32_t>(), wtot, cap / 32);
+        RUN_CUDA(cudaGetLastError());
+        float* b = ls.nscratch.as<float>();
+        dps.x = b, dps.y = b + cap, dps.z = b + 2 * cap, dps.nx = b + 3 * cap, dps.ny = b + 4 * cap, dps.nz = b + 5 * cap;
+        dps.enabled = dps.valid = ls.nvalid.as<uint32_t>();
+        dps.n = dps.n_pad = cap;
+      }
+      auto mask_form = [&]() -> cudaError_t {
+        newly_mask_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(ls.olden.as<uint32_t>(), sub.enabled, swords);
+        dps = sps;
+        dps.enabled = ls.olden.as<uint32_t>() + sps_word0;
+        masked = true;
+        cudaMemsetAsync(d_over, 0, 4, st);
+        return cudaGetLastError();
+      };
+      if (masked) RUN_CUDA(mask_form());
       const size_t o_koff = ((size_t)nst * 4 + 255) / 256 * 256;
       RUN_CUDA(ls.nmeta.ensure(o_koff + (size_t)(nst + 1) * 8));
       uint32_t* keep = ls.nmeta.as<uint32_t>();
@@ -330,15 +407,13 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
       unsigned long long* ktot = koff + nst;
       int nxt = store.cur ^ 1;
       for (int attempt = 0;; ++attempt) {
-        RUN_CUDA(ctx->counts.ensure(((size_t)3 * nst + 4) * 4));
-        int32_t* hit = ctx->counts.as<int32_t>() + 2 * (size_t)nst;
-        // enabled-gated counts under the mask of the newly disabled points = hits
+        // enabled-gated counts over the newly disabled points = hits
         if ((rc = score_enqueue(ctx, cloud, dps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st,
                                 ctx->counts.as<int32_t>(), hit)))
           return rc;
         queue_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, hit + nst);
         RUN_CUDA(cudaGetLastError());
-        if (coll && ctx->allreduce(ctx->allreduce_user, hit, (int64_t)nst + 1, (void*)st))
+        if (coll && ctx->allreduce(ctx->allreduce_user, hit, (int64_t)nst + 2, (void*)st))
           return fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce of the K5 hits failed");
         invalidate_kernel<<<(nst + 255) / 256, 256, 0, st>>>(hit, store.flags[store.cur].as<uint8_t>(), nst, rec.best_idx, keep);
         RUN_CUDA(cudaGetLastError());
@@ -347,11 +422,15 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
             store.cands[store.cur].as<rsc_cand>(), store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), keep,
             koff, nst, store.cands[nxt].as<rsc_cand>(), store.score[nxt].as<int32_t>(), store.flags[nxt].as<uint8_t>());
         RUN_CUDA(cudaGetLastError());
-        k5_pack_kernel<<<1, 1, 0, st>>>(dev, ktot, hit + nst, ctx->misc2.as<unsigned long long>(), dk5);
+        k5_pack_kernel<<<1, 1, 0, st>>>(dev, ktot, hit + nst, d_over, ctx->misc2.as<unsigned long long>(), dk5);
         RUN_CUDA(cudaGetLastError());
         RUN_CUDA(cudaMemcpyAsync(&hio->k5, dk5, sizeof(K5Host), cudaMemcpyDeviceToHost, st));
         RUN_CUDA(sync());
         if (!hio->k5.ovf) break;
+        if (hio->k5.ovf & 2) {  // (not expected) more newly disabled points than the bound: masked form
+          RUN_CUDA(mask_form());
+          continue;
+        }
         // invalidate_kernel marked flags of this attempt: they only ever go from alive to dead on hits that
         // can only grow with the complete counts, so repeating on the same flags is safe
         if (attempt >= 4) return fail(ctx, RSC_E_STATE, "ransac_run: guard-band queue kept overflowing");
