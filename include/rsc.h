@@ -205,6 +205,11 @@ int32_t rsc_score_dev_masks(rsc_cloud* cloud, const rsc_params* params, const rs
  * margins are nullable. */
 int32_t rsc_debug_margins(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int64_t point0,
                           int64_t npoints, float* margins, float* bands, int32_t* col_types, int64_t* packed_vs_scalar_diffs);
+/* Measurement hook for K4 (HBM bound): average duration (ms) of the refit's compatibility-mask kernel over
+ * `reps` back-to-back launches between ONE CUDA-event pair (an event pair around a single ~70 us launch
+ * over-reads it by the event latency).  Nothing is extracted or disabled. */
+int32_t rsc_debug_refit_mask_ms(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand, int32_t reps,
+                                double* ms_per_launch, int64_t* n_inliers);
 /* estimatescore (confidenceintervals.jl:53-74), Int64 wrap-around included (Q9). */
 void rsc_estimate_score(int64_t subset_len, int64_t cloud_len, int64_t count, double* out_min,
                         double* out_max, double* out_E);

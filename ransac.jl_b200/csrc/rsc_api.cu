@@ -309,6 +309,30 @@ int32_t rsc_score_dev_masks(rsc_cloud* cloud, const rsc_params* params, const rs
   return masks_to_candidate_major(ctx, C, ps.n, st, d_masks);
 }
 
+// Measurement hook: average duration of K4's mask kernel over `reps` back-to-back launches (one CUDA-event pair)
+int32_t rsc_debug_refit_mask_ms(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand, int32_t reps, double* ms_per_launch,
+                                int64_t* n_inliers) {
+  if (!cloud) return RSC_E_ARG;
+  rsc_ctx* ctx = cloud->ctx;
+  if (!cand || !ms_per_launch || reps < 2 || reps > 1000) return fail(ctx, RSC_E_ARG, "debug_refit_mask_ms: bad arguments (2 <= reps <= 1000)");
+  if (cand->type < 0 || cand->type >= RSC_NTYPES) return fail(ctx, RSC_E_ARG, "debug_refit_mask_ms: unknown shape type");
+  int32_t rc = check_params(ctx, params);
+  if (rc) return rc;
+  RSC_CUDA(ctx, cudaSetDevice(ctx->device));
+  if ((rc = cloud_ready(cloud))) return rc;
+  Thresh th = make_thresh(params);
+  th.honour_enabled = 0xFu;
+  if ((rc = refit_mask_enqueue(cloud, th, *cand, ctx->stream, reps))) return rc;
+  unsigned long long total = 0;
+  RSC_CUDA(ctx, cudaMemcpyAsync(&total, ctx->misc2.p, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+  RSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  RSC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->evr0, ctx->evr1));
+  *ms_per_launch = (double)ms / reps;
+  if (n_inliers) *n_inliers = (int64_t)total;
+  return RSC_OK;
+}
+
 // Audit of the FP32 guard band on the real hardware: the margins the tiled kernels compute.
 int32_t rsc_debug_margins(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int64_t point0,
                           int64_t npoints, float* margins, float* bands, int32_t* col_types, int64_t* packed_vs_scalar_diffs) {

@@ -262,7 +262,9 @@ int32_t fit_reserve(rsc_ctx* ctx, const rsc_params* params, int S);
 // exclusive scan of n uint32 counts into 64-bit offsets (+ total) on `st` (rsc_fit.cu)
 int32_t scan_u32(rsc_ctx* ctx, const uint32_t* counts, int n, unsigned long long* offsets, unsigned long long* total,
                  cudaStream_t st);
-int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st);
+// timed_reps > 1 (measurement only): the mask kernel runs that many times back to back between the evr0/evr1
+// events before the real pass, so that its duration is not an event pair around one ~70 us launch
+int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st, int timed_reps = 1);
 int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st);
 // least-squares refit of *cand in place (rsc_lsq.cu); synchronises `st`
 int32_t lsq_refine(rsc_cloud* cloud, const rsc_params* params, double band, rsc_cand* cand, int64_t* n_used, double* rms,
