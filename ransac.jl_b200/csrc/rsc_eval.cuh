@@ -233,6 +233,139 @@ __device__ __forceinline__ float2 eval2(const float2* r, float px, float py, flo
   return max2_nan(e, nt);
 }
 
+// Lockstep evaluation of FOUR points against one candidate pair: every formula step is written for the four
+// points back to back, so that consecutive packed instructions share their candidate operand (the operand-
+// reuse cache then serves it and the instruction reads at most two even and two odd registers: 2 issue
+// cycles instead of 3, see tools/sass_model.py).  Same operations, same roundings as eval2<T>().
+template <int T>
+__device__ __forceinline__ void eval2x4(const float2* r, const float* px, const float* py, const float* pz, const float* nx,
+                                        const float* ny, const float* nz, float eps, float cosa, float2* m) {
+#define RSC_Q for (int q = 0; q < 4; ++q)
+  if constexpr (T == RSC_PLANE) {
+    float2 d[4], nt[4];
+#pragma unroll
+    RSC_Q d[q] = fma2(r[2], bc2(pz[q]), r[3]);
+#pragma unroll
+    RSC_Q d[q] = fma2(r[1], bc2(py[q]), d[q]);
+#pragma unroll
+    RSC_Q d[q] = fma2(r[0], bc2(px[q]), d[q]);
+#pragma unroll
+    RSC_Q nt[q] = fma2(r[6], bc2(nz[q]), bc2(cosa));
+#pragma unroll
+    RSC_Q nt[q] = fma2(r[5], bc2(ny[q]), nt[q]);
+#pragma unroll
+    RSC_Q nt[q] = fma2(r[4], bc2(nx[q]), nt[q]);
+#pragma unroll
+    RSC_Q d[q] = add2(abs2(d[q]), bc2(-eps));
+#pragma unroll
+    RSC_Q m[q] = max2_nan(d[q], nt[q]);
+  } else {
+    float2 vx[4], vy[4], vz[4];
+#pragma unroll
+    RSC_Q vx[q] = fma2(r[0], bc2(px[q]), r[1]);
+#pragma unroll
+    RSC_Q vy[q] = fma2(r[0], bc2(py[q]), r[2]);
+#pragma unroll
+    RSC_Q vz[q] = fma2(r[0], bc2(pz[q]), r[3]);
+    if constexpr (T == RSC_SPHERE) {
+      float2 vv[4], s[4];
+#pragma unroll
+      RSC_Q vv[q] = mul2(vz[q], vz[q]);
+#pragma unroll
+      RSC_Q vv[q] = fma2(vy[q], vy[q], vv[q]);
+#pragma unroll
+      RSC_Q vv[q] = fma2(vx[q], vx[q], vv[q]);
+#pragma unroll
+      RSC_Q s[q] = fma2(vz[q], bc2(nz[q]), r[5]);
+#pragma unroll
+      RSC_Q s[q] = fma2(vy[q], bc2(ny[q]), s[q]);
+#pragma unroll
+      RSC_Q s[q] = fma2(vx[q], bc2(nx[q]), s[q]);
+#pragma unroll
+      RSC_Q vv[q] = fma2(vv[q], rsqrt2(vv[q]), r[4]);  // d
+#pragma unroll
+      RSC_Q s[q] = fma2(bc2(cosa), vv[q], neg2(s[q]));  // nt
+#pragma unroll
+      RSC_Q vv[q] = add2(abs2(vv[q]), bc2(-eps));
+#pragma unroll
+      RSC_Q m[q] = max2_nan(vv[q], s[q]);
+    } else {
+      float2 h[4], ww[4];
+#pragma unroll
+      RSC_Q h[q] = mul2(r[6], vz[q]);
+#pragma unroll
+      RSC_Q h[q] = fma2(r[5], vy[q], h[q]);
+#pragma unroll
+      RSC_Q h[q] = fma2(r[4], vx[q], h[q]);
+#pragma unroll
+      RSC_Q vx[q] = fma2(neg2(r[4]), h[q], vx[q]);  // w
+#pragma unroll
+      RSC_Q vy[q] = fma2(neg2(r[5]), h[q], vy[q]);
+#pragma unroll
+      RSC_Q vz[q] = fma2(neg2(r[6]), h[q], vz[q]);
+#pragma unroll
+      RSC_Q ww[q] = mul2(vz[q], vz[q]);
+#pragma unroll
+      RSC_Q ww[q] = fma2(vy[q], vy[q], ww[q]);
+#pragma unroll
+      RSC_Q ww[q] = fma2(vx[q], vx[q], ww[q]);
+      if constexpr (T == RSC_CYLINDER) {
+        float2 wn[4];
+#pragma unroll
+        RSC_Q wn[q] = fma2(vz[q], bc2(nz[q]), r[8]);
+#pragma unroll
+        RSC_Q wn[q] = fma2(vy[q], bc2(ny[q]), wn[q]);
+#pragma unroll
+        RSC_Q wn[q] = fma2(vx[q], bc2(nx[q]), wn[q]);
+#pragma unroll
+        RSC_Q ww[q] = fma2(ww[q], rsqrt2(ww[q]), r[7]);  // d
+#pragma unroll
+        RSC_Q wn[q] = fma2(bc2(cosa), ww[q], neg2(wn[q]));  // nt
+#pragma unroll
+        RSC_Q ww[q] = add2(abs2(ww[q]), bc2(-eps));
+#pragma unroll
+        RSC_Q m[q] = max2_nan(ww[q], wn[q]);
+      } else {
+        float2 wn[4], an[4];
+#pragma unroll
+        RSC_Q an[q] = mul2(r[6], bc2(nz[q]));
+#pragma unroll
+        RSC_Q an[q] = fma2(r[5], bc2(ny[q]), an[q]);
+#pragma unroll
+        RSC_Q an[q] = fma2(r[4], bc2(nx[q]), an[q]);
+#pragma unroll
+        RSC_Q wn[q] = mul2(vz[q], bc2(nz[q]));
+#pragma unroll
+        RSC_Q wn[q] = fma2(vy[q], bc2(ny[q]), wn[q]);
+#pragma unroll
+        RSC_Q wn[q] = fma2(vx[q], bc2(nx[q]), wn[q]);
+#pragma unroll
+        RSC_Q ww[q] = mul2(ww[q], rsqrt2(ww[q]));  // rho
+        if constexpr (T == kConeWide) {
+#pragma unroll
+          RSC_Q h[q] = fma2(neg2(ww[q]), r[7], h[q]);  // d
+#pragma unroll
+          RSC_Q an[q] = fma2(r[0], an[q], r[9]);  // t1
+#pragma unroll
+          RSC_Q wn[q] = mul2(r[10], wn[q]);  // cw
+        } else {
+#pragma unroll
+          RSC_Q h[q] = fma2(h[q], r[7], neg2(ww[q]));  // d
+#pragma unroll
+          RSC_Q an[q] = fma2(r[7], an[q], r[9]);  // t1
+        }
+#pragma unroll
+        RSC_Q h[q] = add2(abs2(h[q]), r[8]);  // e
+#pragma unroll
+        RSC_Q an[q] = fma2(ww[q], an[q], neg2(wn[q]));  // nt
+#pragma unroll
+        RSC_Q m[q] = max2_nan(h[q], an[q]);
+      }
+    }
+  }
+#undef RSC_Q
+}
+
 // runtime-type version for the (rare) slow path; `type` is a COLUMN type (col_type())
 __device__ __forceinline__ float eval_any(int type, const float* r, float px, float py, float pz,
                                           float nx, float ny, float nz, float eps, float cosa) {

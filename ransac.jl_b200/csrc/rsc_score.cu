@@ -165,6 +165,21 @@ __device__ __forceinline__ void score_body(const ScoreArgs& a, int slot0, float*
     const float4 W = *reinterpret_cast<const float4*>(gp + 5 * kSub);
     const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
     const float nx[4] = {U4.x, U4.y, U4.z, U4.w}, ny[4] = {V.x, V.y, V.z, V.w}, nz[4] = {W.x, W.y, W.z, W.w};
+    if constexpr (kPacked && U == 4) {  // lockstep over the four points (eval2x4)
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        float2 m[4];
+        eval2x4<T>(r2[j], px, py, pz, nx, ny, nz, eps, cosa, m);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          mask[2 * j] = __funnelshift_l(__float_as_uint(m[q].x), mask[2 * j], 1);
+          mask[2 * j + 1] = __funnelshift_l(__float_as_uint(m[q].y), mask[2 * j + 1], 1);
+          mabs[2 * j] = fmin_nan(mabs[2 * j], fabsf(m[q].x));
+          mabs[2 * j + 1] = fmin_nan(mabs[2 * j + 1], fabsf(m[q].y));
+        }
+      }
+      return;
+    }
     if constexpr (kPacked && kOrderJQ) {
 #pragma unroll
       for (int j = 0; j < KP; ++j) {
@@ -626,10 +641,14 @@ struct Tiling {
           score_kernel<kConeWide, K, MINB, U, true>                                                     \
     }                                                                                                   \
   }
+#ifdef RSC_EXP_K  // quick single-tiling builds for tools/sass_model.py: nvcc -DRSC_EXP_K=4 -DRSC_EXP_MINB=3 -DRSC_EXP_U=4
+static const Tiling kTilings[] = {RSC_TILING(1, 4, 1), RSC_TILING(RSC_EXP_K, RSC_EXP_MINB, RSC_EXP_U)};
+#else
 static const Tiling kTilings[] = {
     RSC_TILING(1, 4, 1), RSC_TILING(2, 4, 1), RSC_TILING(4, 3, 1), RSC_TILING(4, 4, 1), RSC_TILING(8, 2, 1), RSC_TILING(4, 4, 3), RSC_TILING(4, 3, 3),
     RSC_TILING(4, 4, 5), RSC_TILING(4, 3, 5), RSC_TILING(4, 4, 6), RSC_TILING(4, 3, 6), RSC_TILING(8, 2, 5),
 };
+#endif
 static const Tiling* find_tiling(int K, int minb, int U) {
   for (const Tiling& t : kTilings)
     if (t.K == K && t.minb == minb && t.U == U) return &t;
