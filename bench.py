@@ -31,7 +31,19 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_EVAL = {"plane": 13, "sphere": 16, "cylinder": 27, "cone": 38}
 MIX_FLOPS = 23.5
-NCU_TRAFFIC_BYTES = 1.702e9  # measured: profiles/r1e_kernels_ncu_full.json (4 x ~408 MB read + 72 MB of fix-up queue writes)
+NCU_FULL = "profiles/r2f_kernels_ncu_full.json"  # the committed `ncu --set full` capture roofline.traffic is read from
+
+
+def ncu_traffic(cands: int, points: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the score kernels of one step, from the committed ncu
+    capture of the same command -- only if that capture is of THIS configuration; None otherwise."""
+    try:
+        d = json.load(open(os.path.join(ROOT, NCU_FULL)))
+        if d["config"]["candidates"] == cands and d["config"]["points"] == points:
+            return float(d["traffic_bytes_per_step"])
+    except Exception:
+        pass
+    return None
 
 
 def parse():
@@ -415,9 +427,9 @@ def main():
     ach = MIX_FLOPS * Cn * n / (kernel_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of the four score kernels of one step, from the
-        # `ncu --set full` capture profiles/r1e_kernels_ncu_full.json (same command, 16 Mi points)
-        "traffic": NCU_TRAFFIC_BYTES if (Cn == 4096 and n == (16 << 20)) else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the score kernels of one step, read from the committed
+        # `ncu --set full` capture (same command and configuration; null for any other configuration)
+        "traffic": ncu_traffic(Cn, n), "traffic_source": NCU_FULL, "algorithmic_bytes": 4 * 24.125 * n,
         "peak_source": f"derived: {nsm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry; "
                        "the path uses no tensor cores and is not HBM bound)",
         "kernel": "rsc::score_kernel<T,K,MINB,U,MASKS> x5 (one launch per column type: plane, sphere, cylinder, cone, wide cone; "

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -94,7 +95,7 @@ struct rsc_ctx {
   rsc_stats stats{};
   // scratch of the score path
   rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, pairs, wl_count, aux;
-  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf, cullbuf, shardbuf, gselbuf;
+  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf, cullbuf, shardbuf, gselbuf, smallbuf;
   size_t wl_cap = 1u << 22;  // guard-band queue capacity (groups / pairs), grows on overflow
   rsc_allreduce_fn allreduce = nullptr;  // sums int32 device buffers across the ranks of a sharded run
   void* allreduce_user = nullptr;
@@ -218,6 +219,10 @@ int32_t score_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
                       cudaStream_t st, int32_t* d_counts_valid = nullptr,
                       int32_t* d_counts_enabled = nullptr, const double* d_trig = nullptr,
                       const uint32_t* d_bounds = nullptr, bool accumulate = false);
+// K2 for small candidate batches (rsc_small.cu): thread = point, candidates from shared memory, FP64 decisions
+// inline; the candidate count may live on the device (d_count), c_cap bounds it.  Zeroes d_cv / d_ce [c_cap].
+int32_t score_small_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th, const rsc_cand* d_cands,
+                            int32_t c_cap, const unsigned long long* d_count, int32_t* d_cv, int32_t* d_ce, cudaStream_t st);
 int32_t audit_margins(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const Thresh& th, const rsc_cand* d_cands, int32_t C,
                       int64_t p0, int64_t np, float* d_out, float* d_rec, int32_t* d_cols, unsigned long long* d_diffs, cudaStream_t st);
 // waits for a chunked upload to land and finalises the cloud's guard-band scales

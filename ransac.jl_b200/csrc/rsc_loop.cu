@@ -54,7 +54,8 @@ struct DecideParams {
 struct BatchRec {  // device -> host, once per batch
   long long counters[3];
   int32_t used, extract, terminated, iterations;
-  int32_t best_idx, best_score, store_n, ovf;
+  int32_t best_idx, best_score, store_n, ovf;  // ovf: 1 = a guard-band queue overflowed, 2 = more new candidates than the launch was sized for
+  int32_t n_new, pad;
   rsc_cand best;
 };
 
@@ -91,9 +92,12 @@ __device__ double prob_dev(double n, double s, double N, double k) { return 1 - 
 
 // K3: the bookkeeping of one batch, iteration by iteration (one thread: the walk is sequential by nature)
 __global__ void decide_kernel(LoopDev* __restrict__ d, const int32_t* __restrict__ ovf, int store_n0, int nb, int k0, DecideParams q,
-                              const rsc_cand* __restrict__ cands) {
+                              const rsc_cand* __restrict__ cands, int cap_new) {
   BatchRec r;
-  r.ovf = ovf ? *ovf : 0;
+  r.ovf = ovf ? (*ovf ? 1 : 0) : 0;
+  r.n_new = d->seg[nb];
+  r.pad = 0;
+  if (cap_new >= 0 && r.n_new > cap_new) r.ovf = 2;  // the sync-free launch was sized for fewer candidates: the host repeats K2
   r.used = 0, r.extract = 0, r.terminated = 0, r.iterations = k0 - 1, r.best_idx = -1, r.best_score = 0, r.store_n = store_n0;
   for (int i = 0; i < 3; ++i) r.counters[i] = d->counters[i];
   if (r.ovf) {  // a guard-band queue overflowed on some rank: the counts are incomplete, the host repeats K2
@@ -127,6 +131,27 @@ __global__ void decide_kernel(LoopDev* __restrict__ d, const int32_t* __restrict
   }
   for (int i = 0; i < 3; ++i) d->counters[i] = r.counters[i];
   d->rec = r;
+}
+
+// the sync-free batch path: the number of new candidates stays on the device (the fit's compaction total)
+__global__ void append_new_kernel(const rsc_cand* __restrict__ src, const unsigned long long* __restrict__ total, int cap,
+                                  rsc_cand* __restrict__ dst) {
+  const int n = (int)min(*total, (unsigned long long)cap);
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * 4; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+__global__ void finish_new_dev_kernel(const rsc_cand* __restrict__ cands, const unsigned long long* __restrict__ total, int cap,
+                                      const int32_t* __restrict__ cv, const int32_t* __restrict__ ce, uint32_t honour_enabled,
+                                      int32_t* __restrict__ score, uint8_t* __restrict__ flags) {
+  const int n = (int)min(*total, (unsigned long long)cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = cands[i].type;
+    const bool honour = (honour_enabled >> t) & 1u;
+    score[i] = honour ? ce[i] : cv[i];
+    flags[i] = (uint8_t)(1u | ((!honour && cv[i] != ce[i]) ? 2u : 0u));
+  }
 }
 
 // K5: mask of the subset points the extraction just disabled, in place: old &= ~new
@@ -210,6 +235,11 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
     sps.n = std::max<int64_t>(0, (sub.m < hi ? sub.m : hi) - lo);
   }
   const int64_t sps_word0 = sps.enabled - sub.enabled;
+  // small-batch scorer (rsc_small.cu) limits: beyond them the tiled kernel is the faster one
+  const bool use_small = getenv("RSC_NO_SMALL") == nullptr;
+  constexpr int kSmallMaxCands = 1024;
+  constexpr double kSmallMaxEvals = 2.0e9;
+  long long rate_seen = -1;  // largest number of new candidates per iteration seen so far (-1: no batch yet)
   const int Bmax = getenv("RSC_BATCH") ? std::max(1, std::min(kMaxBatch, atoi(getenv("RSC_BATCH")))) : 16;
   const int Bmin = getenv("RSC_BATCH_MIN") ? std::max(1, std::min(Bmax, atoi(getenv("RSC_BATCH_MIN")))) : std::min(8, Bmax);
   int B = 1;
@@ -280,14 +310,61 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
     if ((rc = fit_enqueue(ctx, cloud, 2, p, p->drawN, nullptr, nullptr, nullptr, S * nb, seed, (uint64_t)(k - 1) * S, st, &fs))) return rc;
     seg_bounds_kernel<<<1, 96, 0, st>>>(fs.out_set, fs.total, S, nb, dev->seg);
     RUN_CUDA(cudaGetLastError());
-    RUN_CUDA(cudaMemcpyAsync(hio->seg, dev->seg, (size_t)(nb + 1) * 4, cudaMemcpyDeviceToHost, st));
-    RUN_CUDA(sync());
-    const int n_new = hio->seg[nb];
+    const int store_n0 = store.n;
+    // ---- sync-free path: K2 for a small batch, sized by a PREDICTION of the number of new candidates ----
+    // (4 x the largest per-iteration yield seen so far; the true number stays on the device.  If more turn up,
+    // decide_kernel says so and the batch is scored again the classic way.)
+    int cap_new = -1;
+    if (use_small && rate_seen >= 0) {
+      const long long want = std::max<long long>(128, 4ll * rate_seen * nb + 64);
+      const long long cap = std::min<long long>((want + 127) / 128 * 128, (long long)maxnew * nb);
+      if (cap <= kSmallMaxCands && (double)cap * (double)std::max<int64_t>(sps.n_pad, 1) <= kSmallMaxEvals) cap_new = (int)cap;
+    }
+    bool scored = false;
+    if (cap_new > 0) {
+      RUN_CUDA(store.reserve((size_t)store_n0 + cap_new, st));
+      RUN_CUDA(ls.newcnt.ensure((size_t)2 * cap_new * 4 + 64));
+      rsc_cand* dst = store.cands[store.cur].as<rsc_cand>() + store_n0;
+      int32_t* cv = ls.newcnt.as<int32_t>();
+      int32_t* ce = cv + cap_new;
+      append_new_kernel<<<std::max(1, std::min(cap_new * 4 / 256, 64)), 256, 0, st>>>(fs.out, fs.total, cap_new, dst);
+      RUN_CUDA(cudaGetLastError());
+      if ((rc = score_small_enqueue(ctx, cloud, sps, th, dst, cap_new, fs.total, cv, ce, st))) return rc;
+      if (coll && ctx->allreduce(ctx->allreduce_user, cv, (int64_t)2 * cap_new, (void*)st))
+        return fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce of the counts failed");
+      finish_new_dev_kernel<<<std::max(1, std::min(cap_new / 256, 64)), 256, 0, st>>>(
+          dst, fs.total, cap_new, cv, ce, th.honour_enabled, store.score[store.cur].as<int32_t>() + store_n0,
+          store.flags[store.cur].as<uint8_t>() + store_n0);
+      RUN_CUDA(cudaGetLastError());
+      seg_argmax_kernel<<<nb, 256, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), dev->seg, store_n0,
+                                             dev->seg_keys);
+      RUN_CUDA(cudaGetLastError());
+      if (store_n0 >= 1) {
+        argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0, dev->oldbest);
+        RUN_CUDA(cudaGetLastError());
+      }
+      decide_kernel<<<1, 1, 0, st>>>(dev, nullptr, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), cap_new);
+      RUN_CUDA(cudaGetLastError());
+      RUN_CUDA(cudaMemcpyAsync(&hio->rec, &dev->rec, sizeof(BatchRec), cudaMemcpyDeviceToHost, st));
+      RUN_CUDA(sync());
+      scored = hio->rec.ovf == 0;
+      if (scored) ctx->stats.evals += (int64_t)hio->rec.n_new * sps.n, ctx->stats.cands_scored += hio->rec.n_new;
+    }
+    int n_new = 0;
+    if (scored) {
+      n_new = hio->rec.n_new;
+    } else if (cap_new > 0) {
+      n_new = hio->rec.n_new;  // known from the record of the undersized attempt
+    } else {
+      RUN_CUDA(cudaMemcpyAsync(hio->seg, dev->seg, (size_t)(nb + 1) * 4, cudaMemcpyDeviceToHost, st));
+      RUN_CUDA(sync());
+      n_new = hio->seg[nb];
+    }
+    rate_seen = std::max<long long>(rate_seen, (n_new + nb - 1) / nb);
     const auto tk1 = now();
     t_fit += secs(tk0, tk1);
-    // ---- K2 on subset 1 + K3 (repeated with a larger guard-band queue if that overflowed) ----
-    const int store_n0 = store.n;
-    for (int attempt = 0;; ++attempt) {
+    // ---- classic path: K2 (tiled) on subset 1 + K3 (repeated with a larger guard-band queue if that overflowed) ----
+    for (int attempt = 0; !scored; ++attempt) {
       const int32_t* d_ovf = nullptr;
       if (n_new > 0) {
         RUN_CUDA(store.reserve((size_t)store_n0 + n_new, st));
@@ -317,7 +394,7 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
                                           dev->oldbest);
         RUN_CUDA(cudaGetLastError());
       }
-      decide_kernel<<<1, 1, 0, st>>>(dev, d_ovf, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>());
+      decide_kernel<<<1, 1, 0, st>>>(dev, d_ovf, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), -1);
       RUN_CUDA(cudaGetLastError());
       RUN_CUDA(cudaMemcpyAsync(&hio->rec, &dev->rec, sizeof(BatchRec), cudaMemcpyDeviceToHost, st));
       RUN_CUDA(sync());
@@ -408,11 +485,18 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
       int nxt = store.cur ^ 1;
       for (int attempt = 0;; ++attempt) {
         // enabled-gated counts over the newly disabled points = hits
-        if ((rc = score_enqueue(ctx, cloud, dps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st,
-                                ctx->counts.as<int32_t>(), hit)))
-          return rc;
-        queue_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, hit + nst);
-        RUN_CUDA(cudaGetLastError());
+        if (use_small && nst <= kSmallMaxCands && (double)nst * (double)std::max<int64_t>(dps.n_pad, 1) <= kSmallMaxEvals) {
+          if ((rc = score_small_enqueue(ctx, cloud, dps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr,
+                                        ctx->counts.as<int32_t>(), hit, st)))
+            return rc;
+          RUN_CUDA(cudaMemsetAsync(hit + nst, 0, 4, st));  // no guard-band queue on this path
+        } else {
+          if ((rc = score_enqueue(ctx, cloud, dps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st,
+                                  ctx->counts.as<int32_t>(), hit)))
+            return rc;
+          queue_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, hit + nst);
+          RUN_CUDA(cudaGetLastError());
+        }
         if (coll && ctx->allreduce(ctx->allreduce_user, hit, (int64_t)nst + 2, (void*)st))
           return fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce of the K5 hits failed");
         invalidate_kernel<<<(nst + 255) / 256, 256, 0, st>>>(hit, store.flags[store.cur].as<uint8_t>(), nst, rec.best_idx, keep);
