@@ -57,8 +57,9 @@ __device__ inline void store(rsc_cand* o, int type, int outw, D3 a, D3 b, double
 }
 
 // same-side test shared by the four validators: all dots > thr -> +1, all < -thr -> -1, else 0
-__device__ inline int side(const double* d, int k, double thr) {
+__device__ __forceinline__ int side(const double* d, int k, double thr) {
   bool pos = true, neg = true;
+#pragma unroll
   for (int i = 0; i < k; ++i) {
     pos = pos && (d[i] > thr);
     neg = neg && (d[i] < -thr);
@@ -66,19 +67,25 @@ __device__ inline int side(const double* d, int k, double thr) {
   return pos ? 1 : (neg ? -1 : 0);
 }
 
+template <int KK>
 __device__ bool fit_plane(const D3* p, const D3* n, const FitParams& f, rsc_cand* out) {
+  constexpr int KA = KK ? KK : kMaxK;
+  const int kk = KK ? KK : f.k;
   D3 m = unit(cross(p[1] - p[0], p[2] - p[0]));
   if (norm(m) < f.collin) return false;  // plane.jl:43 (never true: the norm is 1 or NaN, Q3)
-  double d[kMaxK];
-  for (int i = 0; i < f.k; ++i) d[i] = dot(m, unit(n[i]));
-  const int sd = side(d, f.k, f.cosa[RSC_PLANE]);
+  double d[KA];
+  _Pragma("unroll") for (int i = 0; i < kk; ++i) d[i] = dot(m, unit(n[i]));
+  const int sd = side(d, kk, f.cosa[RSC_PLANE]);
   if (sd == 0) return false;
   if (sd < 0) m = -1.0 * m;
   store(out, RSC_PLANE, 1, p[0], m, 0.0);
   return true;
 }
 
+template <int KK>
 __device__ bool fit_sphere(const D3* v, const D3* n, const FitParams& f, rsc_cand* out) {
+  constexpr int KA = KK ? KK : kMaxK;
+  const int kk = KK ? KK : f.k;
   const D3 n1 = unit(n[0]), n2 = unit(n[1]);
   D3 c;
   double R;
@@ -102,14 +109,14 @@ __device__ bool fit_sphere(const D3* v, const D3* n, const FitParams& f, rsc_can
       R = norm(c - v[0]);
     }
   }
-  double d[kMaxK];
+  double d[KA];
   bool vert = true;
-  for (int i = 0; i < f.k; ++i) {
+  _Pragma("unroll") for (int i = 0; i < kk; ++i) {
     vert = vert && (fabs(norm(v[i] - c) - R) < f.eps[RSC_SPHERE]);
     d[i] = dot(unit(v[i] - c), unit(n[i]));
   }
   if (!vert) return false;
-  const int sd = side(d, f.k, f.cosa[RSC_SPHERE]);
+  const int sd = side(d, kk, f.cosa[RSC_SPHERE]);
   if (sd == 0) return false;
   store(out, RSC_SPHERE, sd > 0, c, D3{0, 0, 0}, R);
   return true;
@@ -129,7 +136,10 @@ __device__ inline void frame2d(D3 xa, D3 ya, D3 za, D3 p, double* r) {
   r[1] = -(n2 / den);
 }
 
+template <int KK>
 __device__ bool fit_cylinder(const D3* p, const D3* n, const FitParams& f, rsc_cand* out) {
+  constexpr int KA = KK ? KK : kMaxK;
+  const int kk = KK ? KK : f.k;
   if (fabs(dot(n[0], n[1])) > f.cos_par) return false;  // raw normals (Q8)
   const D3 a = unit(cross(n[0], n[1]));
   const D3 xa = unit(to_plane(a, p[0]));
@@ -152,15 +162,15 @@ __device__ bool fit_cylinder(const D3* p, const D3* n, const FitParams& f, rsc_c
     rr[i] = norm(q - dot(a, q) * a);
   }
   const double R = (rr[0] + rr[1]) / 2;
-  double d[kMaxK];
+  double d[KA];
   bool vert = true;
-  for (int i = 0; i < f.k; ++i) {
+  _Pragma("unroll") for (int i = 0; i < kk; ++i) {
     const D3 w = (p[i] - dot(a, p[i] - c) * a) - c;
     vert = vert && (fabs(norm(w) - R) < f.eps[RSC_CYLINDER]);
     d[i] = dot(unit(w), n[i]);
   }
   if (!vert) return false;
-  const int sd = side(d, f.k, f.cosa[RSC_CYLINDER]);
+  const int sd = side(d, kk, f.cosa[RSC_CYLINDER]);
   if (sd == 0) return false;
   store(out, RSC_CYLINDER, sd > 0, a, c, R);
   return true;
@@ -265,7 +275,10 @@ __device__ inline double project2cone(D3 apex, D3 axis, double ct, double st, D3
   return dot(-cur, -tp);
 }
 
+template <int KK>
 __device__ bool fit_cone(const D3* p, const D3* n, const FitParams& f, rsc_cand* out) {
+  constexpr int KA = KK ? KK : kMaxK;
+  const int kk = KK ? KK : f.k;
   const double r[9] = {n[0].x, n[0].y, n[0].z, n[1].x, n[1].y, n[1].z, n[2].x, n[2].y, n[2].z};
   const double ds[3] = {dot(p[0], n[0]), dot(p[1], n[1]), dot(p[2], n[2])};
   // rank(r) == 3 && rank([r | -d]) == 3 (cone.jl:44,48).  Shortcut that cannot disagree with the SVD:
@@ -308,13 +321,13 @@ __device__ bool fit_cone(const D3* p, const D3* n, const FitParams& f, rsc_cand*
   const double op = 2 * (ang[0] + ang[1] + ang[2]) / 3;  // full opening angle (Q7)
   // validatecone (cone.jl:87-115)
   const double ct = cos(-op / 2), st = sin(-op / 2);
-  D3 nr[kMaxK];
-  for (int i = 0; i < f.k; ++i)
+  D3 nr[KA];
+  _Pragma("unroll") for (int i = 0; i < kk; ++i)
     if (project2cone(ap, ax, ct, st, p[i], &nr[i]) > f.eps[RSC_CONE]) return false;  // signed (Q6)
   if (op < f.minconeopang) return false;
-  double d[kMaxK];
-  for (int i = 0; i < f.k; ++i) d[i] = dot(nr[i], n[i]);
-  const int sd = side(d, f.k, f.cosa[RSC_CONE]);
+  double d[KA];
+  _Pragma("unroll") for (int i = 0; i < kk; ++i) d[i] = dot(nr[i], n[i]);
+  const int sd = side(d, kk, f.cosa[RSC_CONE]);
   if (sd == 0) return false;
   store(out, RSC_CONE, sd > 0, ap, ax, op);
   return true;
@@ -525,33 +538,37 @@ __global__ void __launch_bounds__(128) sample_cells_kernel(int S, int k, uint64_
 // one thread per (minimal set, shape type): blockIdx.y = position in shape_types, so a warp runs
 // one fit routine.  Points come from explicit coordinates (src.soa == nullptr) or from the cloud
 // by index; sets whose first index is negative (failed samples) yield nothing.
+// KK = 3: the minimal set of the reference's default drawN, everything in registers; KK = 0: f.k points (3..8)
+template <int KK>
 __global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* __restrict__ idx, int S, FitParams f,
                                                   rsc_cand* __restrict__ dense, uint32_t* __restrict__ flags) {
+  constexpr int KA = KK ? KK : kMaxK;
+  const int fk = KK ? KK : f.k;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
   if (s >= S) return;
   const size_t slot = (size_t)s * f.ntypes + t;
   flags[slot] = 0;
-  D3 p[kMaxK], n[kMaxK];
+  D3 p[KA], n[KA];
   if (src.G) {
-    if (idx[(size_t)s * f.k] < 0) return;
-    for (int q = 0; q < f.k; ++q) {
-      const float* g = src.G + ((size_t)s * f.k + q) * 6;
+    if (idx[(size_t)s * fk] < 0) return;
+    _Pragma("unroll") for (int q = 0; q < fk; ++q) {
+      const float* g = src.G + ((size_t)s * fk + q) * 6;
       p[q] = D3{(double)g[0], (double)g[1], (double)g[2]};
       n[q] = D3{(double)g[3], (double)g[4], (double)g[5]};
     }
   } else if (src.soa) {
-    if (idx[(size_t)s * f.k] < 0) return;
-    for (int q = 0; q < f.k; ++q) {
-      const int64_t i = idx[(size_t)s * f.k + q];
+    if (idx[(size_t)s * fk] < 0) return;
+    _Pragma("unroll") for (int q = 0; q < fk; ++q) {
+      const int64_t i = idx[(size_t)s * fk + q];
       p[q] = D3{(double)__ldg(src.soa + i), (double)__ldg(src.soa + src.n_pad + i), (double)__ldg(src.soa + 2 * src.n_pad + i)};
       n[q] = D3{(double)__ldg(src.soa + 3 * src.n_pad + i), (double)__ldg(src.soa + 4 * src.n_pad + i),
                 (double)__ldg(src.soa + 5 * src.n_pad + i)};
     }
   } else {
-    for (int q = 0; q < f.k; ++q) {
-      const double* a = src.P + ((size_t)s * f.k + q) * 3;
-      const double* b = src.N + ((size_t)s * f.k + q) * 3;
+    _Pragma("unroll") for (int q = 0; q < fk; ++q) {
+      const double* a = src.P + ((size_t)s * fk + q) * 3;
+      const double* b = src.N + ((size_t)s * fk + q) * 3;
       p[q] = D3{a[0], a[1], a[2]};
       n[q] = D3{b[0], b[1], b[2]};
     }
@@ -560,16 +577,16 @@ __global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* 
   bool ok = false;
   switch (f.types[t]) {
     case RSC_PLANE:
-      ok = fit_plane(p, n, f, &c);
+      ok = fit_plane<KK>(p, n, f, &c);
       break;
     case RSC_SPHERE:
-      ok = fit_sphere(p, n, f, &c);
+      ok = fit_sphere<KK>(p, n, f, &c);
       break;
     case RSC_CYLINDER:
-      ok = fit_cylinder(p, n, f, &c);
+      ok = fit_cylinder<KK>(p, n, f, &c);
       break;
     case RSC_CONE:
-      ok = fit_cone(p, n, f, &c);
+      ok = fit_cone<KK>(p, n, f, &c);
       break;
   }
   if (ok) {
@@ -880,7 +897,10 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
       RSC_CUDA(ctx, cudaGetLastError());
       use_idx = fs->idx;
     }
-    fit_kernel<<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->flags);
+    if (k == 3)
+      fit_kernel<3><<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->flags);
+    else
+      fit_kernel<0><<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->flags);
     RSC_CUDA(ctx, cudaGetLastError());
     if ((rc = scan_u32(ctx, fs->flags, slots, fs->offs, fs->total, st))) return rc;
     compact_kernel<<<(slots + 255) / 256, 256, 0, st>>>(fs->dense, fs->flags, fs->offs, slots, f.ntypes, fs->out, fs->out_set);

@@ -90,44 +90,68 @@ __device__ double estimate_E(long long M, long long N, long long count) {
 
 __device__ double prob_dev(double n, double s, double N, double k) { return 1 - pow(1 - pow(n / N, k), s); }  // utilities.jl:262
 
-// K3: the bookkeeping of one batch, iteration by iteration (one thread: the walk is sequential by nature)
-__global__ void decide_kernel(LoopDev* __restrict__ d, const int32_t* __restrict__ ovf, int store_n0, int nb, int k0, DecideParams q,
-                              const rsc_cand* __restrict__ cands, int cap_new) {
+// K3: the bookkeeping of one batch.  The walk over the batch's iterations is sequential by nature (cut at the
+// first extraction / termination), but what it compares is not: thread j evaluates iteration j's counters,
+// running best (a prefix maximum of the per-iteration arg-max keys), estimatescore, and the two prob() tests
+// (four FP64 pow calls); thread 0 then takes the first iteration that extracts or terminates.
+__global__ void __launch_bounds__(kMaxBatch) decide_kernel(LoopDev* __restrict__ d, const int32_t* __restrict__ ovf, int store_n0,
+                                                           int nb, int k0, DecideParams q, const rsc_cand* __restrict__ cands,
+                                                           int cap_new) {
+  __shared__ long long s_key[kMaxBatch];
+  __shared__ int s_ext[kMaxBatch], s_term[kMaxBatch];
+  const int j = threadIdx.x;
+  const int over = ovf ? (*ovf ? 1 : 0) : 0;
+  const int n_new = d->seg[nb];
+  const bool redo = over || (cap_new >= 0 && n_new > cap_new);
+  if (j < nb && !redo) {
+    long long key = (store_n0 >= 1 && d->oldbest[0] >= 0) ? ((d->oldbest[1] << 32) | (long long)(0x7fffffff - d->oldbest[0])) : -1;
+    for (int i = 0; i <= j; ++i)
+      if (d->seg_keys[i] > key) key = d->seg_keys[i];  // strict >: the first maximum wins (the key carries the store index)
+    const long long c0 = store_n0 + d->seg[j + 1];                 // iterations.jl:102
+    const long long c1 = d->counters[1] + d->seg[j + 1];           // iterations.jl:94 (accumulated over the batch)
+    const long long c2 = (long long)(k0 + j) * q.S;                // iterations.jl:99
+    const long long cc[3] = {c0, c1, c2};
+    int ext = 0;
+    if (c0 >= 1 && key >= 0) {
+      const double E = estimate_E(q.M, q.N, (long long)(key >> 32));
+      ext = prob_dev(E, (double)cc[q.extract_s], (double)q.N, (double)q.drawN) > q.prob_det;  // iterations.jl:113
+    }
+    s_key[j] = key;
+    s_ext[j] = ext;
+    s_term[j] = prob_dev((double)q.tau, (double)cc[q.terminate_s], (double)q.N, (double)q.drawN) > q.prob_det;  // iterations.jl:151-156
+  }
+  __syncthreads();
+  if (j != 0) return;
   BatchRec r;
-  r.ovf = ovf ? (*ovf ? 1 : 0) : 0;
-  r.n_new = d->seg[nb];
+  r.ovf = over ? 1 : ((cap_new >= 0 && n_new > cap_new) ? 2 : 0);  // 2: the sync-free launch was sized for fewer candidates
+  r.n_new = n_new;
   r.pad = 0;
-  if (cap_new >= 0 && r.n_new > cap_new) r.ovf = 2;  // the sync-free launch was sized for fewer candidates: the host repeats K2
   r.used = 0, r.extract = 0, r.terminated = 0, r.iterations = k0 - 1, r.best_idx = -1, r.best_score = 0, r.store_n = store_n0;
   for (int i = 0; i < 3; ++i) r.counters[i] = d->counters[i];
-  if (r.ovf) {  // a guard-band queue overflowed on some rank: the counts are incomplete, the host repeats K2
+  if (redo) {  // the counts are incomplete (queue overflow on some rank) or some candidates were not scored: the host repeats K2
     d->rec = r;
     return;
   }
-  long long bestkey = (store_n0 >= 1 && d->oldbest[0] >= 0) ? ((d->oldbest[1] << 32) | (long long)(0x7fffffff - d->oldbest[0])) : -1;
-  for (int j = 0; j < nb; ++j) {
-    const int kk = k0 + j;
-    r.iterations = kk;
-    r.used = j + 1;
-    r.counters[1] += d->seg[j + 1] - d->seg[j];  // iterations.jl:94
-    r.store_n = store_n0 + d->seg[j + 1];
-    r.counters[2] = (long long)kk * q.S;         // iterations.jl:99
-    r.counters[0] = r.store_n;                   // iterations.jl:102
-    if (d->seg_keys[j] > bestkey) bestkey = d->seg_keys[j];  // strict >: the first maximum wins (the key carries the index)
-    if (r.store_n >= 1 && bestkey >= 0) {
-      const int idx = 0x7fffffff - (int)(bestkey & 0xffffffffll);
-      const int score = (int)(bestkey >> 32);
-      const double E = estimate_E(q.M, q.N, score);
-      if (prob_dev(E, (double)r.counters[q.extract_s], (double)q.N, (double)q.drawN) > q.prob_det) {  // iterations.jl:113
-        r.extract = 1;
-        r.best_idx = idx;
-        r.best_score = score;
-        r.best = cands[idx];
-      }
+  int last = nb - 1;
+  for (int i = 0; i < nb; ++i)
+    if (s_ext[i] || s_term[i]) {
+      last = i;
+      break;
     }
-    if (prob_dev((double)q.tau, (double)r.counters[q.terminate_s], (double)q.N, (double)q.drawN) > q.prob_det)
-      r.terminated = 1;  // iterations.jl:151-156
-    if (r.extract || r.terminated) break;
+  if (nb > 0) {
+    r.used = last + 1;
+    r.iterations = k0 + last;
+    r.store_n = store_n0 + d->seg[last + 1];
+    r.counters[0] = r.store_n;
+    r.counters[1] = d->counters[1] + d->seg[last + 1];
+    r.counters[2] = (long long)(k0 + last) * q.S;
+    r.extract = s_ext[last];
+    r.terminated = s_term[last];
+    if (r.extract) {
+      r.best_idx = 0x7fffffff - (int)(s_key[last] & 0xffffffffll);
+      r.best_score = (int)(s_key[last] >> 32);
+      r.best = cands[r.best_idx];
+    }
   }
   for (int i = 0; i < 3; ++i) d->counters[i] = r.counters[i];
   d->rec = r;
@@ -343,7 +367,7 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
         argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0, dev->oldbest);
         RUN_CUDA(cudaGetLastError());
       }
-      decide_kernel<<<1, 1, 0, st>>>(dev, nullptr, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), cap_new);
+      decide_kernel<<<1, kMaxBatch, 0, st>>>(dev, nullptr, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), cap_new);
       RUN_CUDA(cudaGetLastError());
       RUN_CUDA(cudaMemcpyAsync(&hio->rec, &dev->rec, sizeof(BatchRec), cudaMemcpyDeviceToHost, st));
       RUN_CUDA(sync());
@@ -394,7 +418,7 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
                                           dev->oldbest);
         RUN_CUDA(cudaGetLastError());
       }
-      decide_kernel<<<1, 1, 0, st>>>(dev, d_ovf, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), -1);
+      decide_kernel<<<1, kMaxBatch, 0, st>>>(dev, d_ovf, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), -1);
       RUN_CUDA(cudaGetLastError());
       RUN_CUDA(cudaMemcpyAsync(&hio->rec, &dev->rec, sizeof(BatchRec), cudaMemcpyDeviceToHost, st));
       RUN_CUDA(sync());
