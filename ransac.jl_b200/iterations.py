@@ -116,13 +116,20 @@ def _ransac_host(pc, params, seed, progressive=False, lsq=False):
         if custom:
             if idx is None:
                 raise NotImplementedError("user-defined shapes need at least one built-in type for sampling")
-            for row in idx:
+            # forcefitshapes! (fitting.jl:165-173) appends per minimal set in shape_types order: merge the device's
+            # built-in candidates with the user's by (set, position in shape_types) -- findhighestscore is
+            # "first maximum wins", so the order decides ties
+            pos = {t: i for i, t in enumerate(it["shape_types"])}
+            keyed = [((int(s), pos[type(c)]), c) for c, s in zip(cands, csets)]
+            for si, row in enumerate(idx):
                 if row[0] < 0:
                     continue
                 for t in custom:
                     f = t.fit(pc.vertices[row], pc.normals[row], pc, params)
                     if f is not None:
-                        cands.extend(f if isinstance(f, (list, tuple)) else [f])
+                        keyed.extend(((si, pos[t]), c) for c in (f if isinstance(f, (list, tuple)) else [f]))
+            keyed.sort(key=lambda kc: kc[0])  # stable
+            cands = [c for _, c in keyed]
         cc[1] += len(cands)
         b = [c for c in cands if type(c) in SHAPE_KIND]
         res = dict(zip(map(id, b), scorecandidates(pc, b, 0, bparams))) if b else {}
@@ -143,14 +150,15 @@ def _ransac_host(pc, params, seed, progressive=False, lsq=False):
                 if lsq and type(shp) in SHAPE_KIND:
                     shp = lsq_refit(shp, pc, bparams)[0]
                 ex = refit(shp, pc, bparams, disable=True) if type(shp) in SHAPE_KIND else shp.refit(pc, params)
-                if type(shp) not in SHAPE_KIND:
-                    from .fitting import invalidate_indexes
-                    invalidate_indexes(pc, ex.inpoints)
-                extracted.append(ex)
-                scored.deleteat(best)
-                en = pc.isenabled
-                dead = [j for j in range(len(scored)) if not en[scored.inpoints[j]].all()]
-                scored.deleteat(dead)
+                if ex is not None:  # a user's refit may return nothing: the reference then skips the extraction (iterations.jl:130)
+                    if type(shp) not in SHAPE_KIND:
+                        from .fitting import invalidate_indexes
+                        invalidate_indexes(pc, ex.inpoints)
+                    extracted.append(ex)
+                    scored.deleteat(best)
+                    en = pc.isenabled
+                    dead = [j for j in range(len(scored)) if not en[scored.inpoints[j]].all()]
+                    scored.deleteat(dead)
         if prob(tau, cc[sidx[it["terminate_s"]]], pc.size, drawN) > prob_det:
             break
     return extracted, int((time.time() - t0) * 100) / 100.0
