@@ -425,6 +425,12 @@ def main():
     nsm = torch.cuda.get_device_properties(local).multi_processor_count
     fp32_peak = nsm * 128 * 2 * sm_max * 1e6 / 1e12
     ach = MIX_FLOPS * Cn * n / (kernel_ms * 1e-3) / 1e12
+    fma_chain = None  # measured FP32 peak of this very GPU: scalar FFMA chains (tools/fp32_peak.cu, ~1 s)
+    try:
+        pk = subprocess.run([os.path.join(ROOT, "tools", "fp32_peak")], capture_output=True, text=True, timeout=120)  # rank 0 = device 0
+        fma_chain = float(json.loads(pk.stdout.strip().splitlines()[-1])["ffma_scalar_tflops"])
+    except Exception:
+        pass
     roofline = {
         "bound": "fp32", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach / fp32_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of the score kernels of one step, read from the committed
@@ -432,6 +438,7 @@ def main():
         "traffic": ncu_traffic(Cn, n), "traffic_source": NCU_FULL, "algorithmic_bytes": 4 * 24.125 * n,
         "peak_source": f"derived: {nsm} SMs x 128 FP32 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP32 entry; "
                        "the path uses no tensor cores and is not HBM bound)",
+        "peak_measured_fma_chain": fma_chain, "frac_of_measured_fma_chain": (ach / fma_chain) if fma_chain else None,
         "kernel": "rsc::score_kernel<T,K,MINB,U,MASKS> x5 (one launch per column type: plane, sphere, cylinder, cone, wide cone; "
                   "side by side on forked streams; kernel_ms = CUDA events around the launches)", "kernel_ms": kernel_ms,
         "algorithmic_flops_per_eval": MIX_FLOPS,
