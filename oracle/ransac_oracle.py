@@ -1031,6 +1031,216 @@ def iswithinrectangle(vmin, vmax, p) -> bool:
     return True
 
 
+# --------------------------------------------------------------------------------------
+# Parameter-space bitmap + largest connected component (second half).
+# The reference carries this as DEAD code (src/parameterspacebitmap.jl is not included by RANSAC.jl,
+# its test file test/parameterspacebitmap.jl is commented out in runtests.jl, and `label_components`
+# comes from ImageMorphology, which is not a dependency): docs/src/ransac.md:106-112 lists "part of the
+# largest connected component in the parameter space bitmap" as the third compatibility criterion and
+# says it is not considered.  Restated literally below (bitmapparameters, largestconncomp) and pinned to
+# the two known-answer test sets of test/parameterspacebitmap.jl; the extension the CUDA library
+# implements (shape_parameters2d + bitmap_filter, rsc_bitmap.cu) follows.
+# --------------------------------------------------------------------------------------
+
+
+def arbitrary_orthogonal(vec) -> np.ndarray:
+    """utilities.jl:84-92: a vector orthogonal to `vec` (cross product with the unit vector of its smallest component)."""
+    v = normalize3(_v(vec))
+    b0 = (v[0] < v[1]) and (v[0] < v[2])
+    b1 = (v[1] <= v[0]) and (v[1] < v[2])
+    b2 = (v[2] <= v[0]) and (v[2] <= v[1])
+    rv = np.array([float(b0), float(b1), float(b2)])
+    rv = rv / math.sqrt(float(rv @ rv))
+    return cross3(v, rv)
+
+
+def project2plane(sh: Shape, pts) -> np.ndarray:
+    """plane.jl:82-103: coordinates of the points in a frame of the plane (x, y in the plane, z along the normal)."""
+    p7 = sh.params7()
+    o_z = normalize3(p7[3:6])
+    o_x = normalize3(arbitrary_orthogonal(o_z))
+    o_y = normalize3(cross3(o_z, o_x))
+    V = np.asarray(pts, dtype=F) - p7[0:3]
+    return np.stack([V @ o_x, V @ o_y, V @ o_z], axis=1)
+
+
+def bitmapparameters(parameters, compatibility, beta: float, idsource=None):
+    """parameterspacebitmap.jl:12-46, literally (1-based cells kept as 0-based arrays [x-1, y-1]): the box is
+    widened by 0.1, a cell keeps the FIRST id projected into it, and places on the border (0, xs, ys) are
+    dropped ("boundserror") -- quirks included.  Returns (bitmap (xs, ys) bool, idxmap (xs, ys) int (0 = empty;
+    ids as given), (bx, by))."""
+    P = np.asarray(parameters, dtype=F)
+    comp = np.asarray(compatibility, dtype=bool)
+    ids = np.arange(1, len(P) + 1) if idsource is None else np.asarray(idsource)
+    assert len(P) == len(comp) == len(ids), "Everything must have the same length."
+    miv, mav = findAABB(P[:, :2])
+    minv, maxv = miv - 0.1, mav + 0.1
+    xs = int(np.round((maxv[0] - minv[0]) / beta))  # Julia's round: half to even, like numpy's
+    ys = int(np.round((maxv[1] - minv[1]) / beta))
+    assert xs > 0 and ys > 0, "max-min should be positive."
+    bx, by = (maxv[0] - minv[0]) / xs, (maxv[1] - minv[1]) / ys
+    bitmap = np.zeros((xs, ys), bool)
+    idxmap = np.zeros((xs, ys), np.int64)
+    for i in range(len(P)):
+        if not comp[i]:
+            continue
+        xp = int(math.ceil((P[i, 0] - minv[0]) / bx))
+        yp = int(math.ceil((P[i, 1] - minv[1]) / by))
+        if xp != 0 and yp != 0 and xp != xs and yp != ys:
+            if not bitmap[xp - 1, yp - 1]:
+                bitmap[xp - 1, yp - 1] = True
+                idxmap[xp - 1, yp - 1] = ids[i]
+    return bitmap, idxmap, (bx, by)
+
+
+def label_components(bimage: np.ndarray, eight: bool = False) -> np.ndarray:
+    """ImageMorphology.label_components as the reference uses it (parameterspacebitmap.jl:68): 0 = background,
+    components numbered in the order their first cell is met in COLUMN-MAJOR order (first index fastest),
+    4-connectivity (`1:ndims`) or 8-connectivity (`trues(3,3)`).  Plain flood fill."""
+    B = np.asarray(bimage, bool)
+    xs, ys = B.shape
+    lab = np.zeros((xs, ys), np.int64)
+    nxt = 0
+    nb = [(1, 0), (-1, 0), (0, 1), (0, -1)] + ([(1, 1), (1, -1), (-1, 1), (-1, -1)] if eight else [])
+    for y in range(ys):
+        for x in range(xs):
+            if not B[x, y] or lab[x, y]:
+                continue
+            nxt += 1
+            lab[x, y] = nxt
+            stack = [(x, y)]
+            while stack:
+                cx, cy = stack.pop()
+                for dx, dy in nb:
+                    ux, uy = cx + dx, cy + dy
+                    if 0 <= ux < xs and 0 <= uy < ys and B[ux, uy] and not lab[ux, uy]:
+                        lab[ux, uy] = nxt
+                        stack.append((ux, uy))
+    return lab
+
+
+def largestconncomp(bimage, indmap, connectivity="default") -> list:
+    """parameterspacebitmap.jl:60-109: the ids (`indmap[x][y]` = list of ids of the cell) of the largest
+    connected component, cells in column-major order.  connectivity: "default" / range(1, 3) = 4-connected,
+    "eight" / a 3x3 all-true array = 8-connected.  The first of equally large components wins (argmax)."""
+    if isinstance(connectivity, str):
+        if connectivity not in ("default", "eight"):
+            raise ValueError(f"No such key implemented: {connectivity}.")
+        eight = connectivity == "eight"
+    else:
+        eight = np.asarray(connectivity).ndim == 2
+    B = np.asarray(bimage, bool)
+    lab = label_components(B, eight)
+    nlab = int(lab.max())
+    if nlab == 0:
+        raise ValueError("collection must be non-empty")  # the reference's argmax on an empty list (its own TODO)
+    sizes = np.bincount(lab.ravel(), minlength=nlab + 1)
+    best = int(np.argmax(sizes[1:])) + 1
+    inds = []
+    xs, ys = B.shape
+    for y in range(ys):
+        for x in range(xs):
+            if lab[x, y] == best:
+                cell = indmap[x][y]
+                inds.extend(cell if isinstance(cell, (list, tuple, np.ndarray)) else [cell])
+    return inds
+
+
+# ---- the extension: the third compatibility criterion as a filter on an inlier list -----------------
+# (definition shared with rsc_bitmap.cu).  2-D parameters of a point on the shape:
+#   plane     project2plane(...)[:, :2]                                    (the reference's own frame)
+#   sphere    (R phi, R sin(lat)) about the z axis -- Lambert's equal-area cylinder; phi wraps
+#   cylinder  (R phi, h) in the frame (x, y, axis), x = arbitrary_orthogonal(axis); phi wraps
+#   cone      (r_ref phi, s): azimuth about the axis and slant distance from the apex, r_ref = sin(opang/2) times
+#             the mid slant distance of the given points (so that cells are ~square there); phi wraps
+# Cells: ix = floor((u - umin) / bu), iy = floor((v - vmin) / bv) over the bounding box of the parameters, with
+# nu = max(1, round(range / beta)) cells (wrapping axis: nu = max(3, round(2 pi R / beta)) cells over the full
+# turn); a component is 4- or 8-connected (x wraps where phi does); the largest one by number of CELLS wins,
+# ties go to the component holding the smallest column-major cell index; its points are kept, in input order.
+
+
+def shape_parameters2d(sh: Shape, pts):
+    """(params (n, 2), wrap_period_or_None)"""
+    P = np.asarray(pts, dtype=F)
+    p7 = sh.params7()
+    if sh.kind == PLANE:
+        return project2plane(sh, P)[:, :2], None
+    if sh.kind == SPHERE:
+        R = float(p7[3])
+        V = P - p7[0:3]
+        r = np.sqrt((V * V).sum(1))
+        phi = np.arctan2(V[:, 1], V[:, 0])
+        return np.stack([R * phi, R * (V[:, 2] / r)], axis=1), 2 * math.pi * R
+    if sh.kind == CYLINDER:
+        a = normalize3(p7[0:3])
+        ox = normalize3(arbitrary_orthogonal(a))
+        oy = normalize3(cross3(a, ox))
+        V = P - p7[3:6]
+        R = float(p7[6])
+        phi = np.arctan2(V @ oy, V @ ox)
+        return np.stack([R * phi, V @ a], axis=1), 2 * math.pi * R
+    a = normalize3(p7[3:6])
+    ox = normalize3(arbitrary_orthogonal(a))
+    oy = normalize3(cross3(a, ox))
+    V = P - p7[0:3]
+    s = np.sqrt((V * V).sum(1))
+    phi = np.arctan2(V @ oy, V @ ox)
+    r_ref = abs(math.sin(float(p7[6]) / 2)) * 0.5 * (float(s.min()) + float(s.max())) if len(s) else 1.0
+    r_ref = max(r_ref, 1e-300)
+    return np.stack([r_ref * phi, s], axis=1), 2 * math.pi * r_ref
+
+
+def bitmap_filter(sh: Shape, pts, beta: float, eight: bool = False):
+    """indices (into pts, ascending) of the points whose parameter-space cell belongs to the largest connected
+    component; also returns (nu, nv, number of components, cells of the largest)."""
+    P = np.asarray(pts, dtype=F)
+    if len(P) == 0:
+        return np.zeros(0, np.int64), (0, 0, 0, 0)
+    uv, period = shape_parameters2d(sh, P)
+    vmin, vmax = float(uv[:, 1].min()), float(uv[:, 1].max())
+    nv = max(1, int(np.round((vmax - vmin) / beta)))
+    bv = (vmax - vmin) / nv if vmax > vmin else 1.0
+    if period is None:
+        umin, umax = float(uv[:, 0].min()), float(uv[:, 0].max())
+        nu = max(1, int(np.round((umax - umin) / beta)))
+        bu = (umax - umin) / nu if umax > umin else 1.0
+    else:
+        umin = -period / 2
+        nu = max(3, int(np.round(period / beta)))
+        bu = period / nu
+    ix = np.minimum(np.floor((uv[:, 0] - umin) / bu).astype(np.int64), nu - 1)
+    iy = np.minimum(np.floor((uv[:, 1] - vmin) / bv).astype(np.int64), nv - 1)
+    ix = np.maximum(ix, 0)
+    B = np.zeros((nu, nv), bool)
+    B[ix, iy] = True
+    # union-find free labelling with optional wrap in x: flood fill
+    lab = np.full((nu, nv), -1, np.int64)
+    nb = [(1, 0), (-1, 0), (0, 1), (0, -1)] + ([(1, 1), (1, -1), (-1, 1), (-1, -1)] if eight else [])
+    sizes, roots = [], []
+    for y in range(nv):
+        for x in range(nu):
+            if not B[x, y] or lab[x, y] >= 0:
+                continue
+            k = len(sizes)
+            lab[x, y] = k
+            cnt, stack = 0, [(x, y)]
+            while stack:
+                cx, cy = stack.pop()
+                cnt += 1
+                for dx, dy in nb:
+                    ux, uy = cx + dx, cy + dy
+                    if period is not None:
+                        ux %= nu
+                    if 0 <= ux < nu and 0 <= uy < nv and B[ux, uy] and lab[ux, uy] < 0:
+                        lab[ux, uy] = k
+                        stack.append((ux, uy))
+            sizes.append(cnt)
+            roots.append(x + nu * y)
+    best = max(range(len(sizes)), key=lambda k: (sizes[k], -roots[k]))
+    keep = np.flatnonzero(lab[ix, iy] == best)
+    return keep, (nu, nv, len(sizes), sizes[best])
+
+
 def morton3(q: np.ndarray, D: int) -> np.ndarray:
     """interleave the D low bits of q[:,0], q[:,1], q[:,2] (x is the most significant of each triple)"""
     code = np.zeros(len(q), np.int64)
