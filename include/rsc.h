@@ -250,6 +250,17 @@ int32_t rsc_refit_extract(rsc_cloud* cloud, const rsc_params* params, const rsc_
 int32_t rsc_refit_lsq(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cand, double band,
                       rsc_cand* out, int64_t* n_used, double* rms);
 
+/* Extension (second half): the paper's third compatibility criterion, which the reference
+ * documents and leaves out (docs/src/ransac.md:106-112; src/parameterspacebitmap.jl is dead code there) --
+ * keep, of the points idx[0..n) (local indices, e.g. an inlier list of rsc_refit_extract(..., disable = 0)),
+ * those whose cell in the shape's 2-D parameter-space bitmap (cell size ~ beta) belongs to the LARGEST
+ * connected component (4-connected, or 8-connected with eight != 0; the azimuth axis of spheres, cylinders
+ * and cones wraps).  out_idx (capacity n) receives them in input order, *out_n their number; info[4]
+ * (nullable) = cells along u, cells along v, number of components, cells of the largest.  Definition:
+ * oracle/ransac_oracle.py::bitmap_filter. */
+int32_t rsc_bitmap_filter(rsc_cloud* cloud, const rsc_cand* cand, double beta, int32_t eight, const int64_t* idx, int64_t n,
+                          int64_t* out_idx, int64_t* out_n, int32_t* info);
+
 /* ---- point-range sharding over the GPUs of one box (one process per GPU) ----------------------
  * The path shards by point range: every rank scores/refits the points it owns and the
  * per-candidate counts are summed with an int32 all-reduce.  Two layouts:

@@ -1159,35 +1159,55 @@ def largestconncomp(bimage, indmap, connectivity="default") -> list:
 # ties go to the component holding the smallest column-major cell index; its points are kept, in input order.
 
 
+def _dot_rows(V, o):
+    """row-wise dot product, summed left to right without contraction (what rsc_bitmap.cu computes)"""
+    return (V[:, 0] * o[0] + V[:, 1] * o[1]) + V[:, 2] * o[2]
+
+
 def shape_parameters2d(sh: Shape, pts):
-    """(params (n, 2), wrap_period_or_None)"""
+    """(raw parameters (n, 2), scale of the first one or None, wraps?) -- u = scale * raw[:, 0] where a scale is
+    given (cone: it depends on the points), else raw[:, 0]"""
     P = np.asarray(pts, dtype=F)
     p7 = sh.params7()
     if sh.kind == PLANE:
-        return project2plane(sh, P)[:, :2], None
+        o_z = normalize3(p7[3:6])
+        o_x = normalize3(arbitrary_orthogonal(o_z))
+        o_y = normalize3(cross3(o_z, o_x))
+        V = P - p7[0:3]
+        return np.stack([_dot_rows(V, o_x), _dot_rows(V, o_y)], axis=1), None, False
     if sh.kind == SPHERE:
         R = float(p7[3])
         V = P - p7[0:3]
-        r = np.sqrt((V * V).sum(1))
+        r = np.sqrt(_dot_rows(V, V.T))
         phi = np.arctan2(V[:, 1], V[:, 0])
-        return np.stack([R * phi, R * (V[:, 2] / r)], axis=1), 2 * math.pi * R
+        return np.stack([R * phi, R * (V[:, 2] / r)], axis=1), None, True
     if sh.kind == CYLINDER:
         a = normalize3(p7[0:3])
         ox = normalize3(arbitrary_orthogonal(a))
         oy = normalize3(cross3(a, ox))
         V = P - p7[3:6]
         R = float(p7[6])
-        phi = np.arctan2(V @ oy, V @ ox)
-        return np.stack([R * phi, V @ a], axis=1), 2 * math.pi * R
+        phi = np.arctan2(_dot_rows(V, oy), _dot_rows(V, ox))
+        return np.stack([R * phi, _dot_rows(V, a)], axis=1), None, True
     a = normalize3(p7[3:6])
     ox = normalize3(arbitrary_orthogonal(a))
     oy = normalize3(cross3(a, ox))
     V = P - p7[0:3]
-    s = np.sqrt((V * V).sum(1))
-    phi = np.arctan2(V @ oy, V @ ox)
-    r_ref = abs(math.sin(float(p7[6]) / 2)) * 0.5 * (float(s.min()) + float(s.max())) if len(s) else 1.0
+    s = np.sqrt(_dot_rows(V, V.T))
+    phi = np.arctan2(_dot_rows(V, oy), _dot_rows(V, ox))
+    r_ref = abs(math.sin(float(p7[6]) / 2)) * (0.5 * (float(s.min()) + float(s.max()))) if len(s) else 1.0
     r_ref = max(r_ref, 1e-300)
-    return np.stack([r_ref * phi, s], axis=1), 2 * math.pi * r_ref
+    return np.stack([phi, s], axis=1), r_ref, True
+
+
+def bitmap_period(sh: Shape, scale) -> float:
+    """length of the wrapping axis: the full turn"""
+    p7 = sh.params7()
+    if sh.kind == SPHERE:
+        return 2 * math.pi * float(p7[3])
+    if sh.kind == CYLINDER:
+        return 2 * math.pi * float(p7[6])
+    return 2 * math.pi * scale
 
 
 def bitmap_filter(sh: Shape, pts, beta: float, eight: bool = False):
@@ -1196,7 +1216,10 @@ def bitmap_filter(sh: Shape, pts, beta: float, eight: bool = False):
     P = np.asarray(pts, dtype=F)
     if len(P) == 0:
         return np.zeros(0, np.int64), (0, 0, 0, 0)
-    uv, period = shape_parameters2d(sh, P)
+    uv, scale, wraps = shape_parameters2d(sh, P)
+    if scale is not None:
+        uv = np.stack([scale * uv[:, 0], uv[:, 1]], axis=1)
+    period = bitmap_period(sh, scale) if wraps else None
     vmin, vmax = float(uv[:, 1].min()), float(uv[:, 1].max())
     nv = max(1, int(np.round((vmax - vmin) / beta)))
     bv = (vmax - vmin) / nv if vmax > vmin else 1.0

@@ -11,6 +11,7 @@ from .cloud import RANSACCloud, makesubsets
 from .confidence import ConfidenceInterval, E, estimatescore, estimatescore_f64, isoverlap, notsoconfident, prob
 from .fitting import (
     IterationCandidates,
+    bitmap_filter,
     findhighestscore,
     fit,
     fit_batch,

@@ -103,6 +103,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_double)]),
     "rsc_refit_lsq": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), C.c_double, C.POINTER(rsc_cand),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "rsc_bitmap_filter": (C.c_int32, [_P, C.POINTER(rsc_cand), C.c_double, C.c_int32, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     "rsc_ctx_set_allreduce": (C.c_int32, [_P, _P, _P]),
     "rsc_comm_unique_id": (C.c_int32, [_P]),
     "rsc_ctx_comm_init": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),

@@ -143,6 +143,20 @@ def scorecandidate(pc: RANSACCloud, candidate: FittedShape, subsetID: int, param
     return scorecandidates(pc, [candidate], subsetID, params)[0]
 
 
+def bitmap_filter(s: FittedShape, pc: RANSACCloud, idx, beta: float, eight: bool = False):
+    """Extension (the paper's third compatibility criterion, docs/src/ransac.md:106-112; dead code in the
+    reference, src/parameterspacebitmap.jl): of the points `idx`, those whose cell of the shape's parameter-space
+    bitmap (cell size ~ beta) lies in the largest connected component.  Returns (kept indices, info dict)."""
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    out = np.zeros(max(1, len(idx)), dtype=np.int64)
+    n = C.c_int64()
+    info = (C.c_int32 * 4)()
+    cand = s.to_cand()
+    pc.ctx.check(lib.rsc_bitmap_filter(pc.handle, C.byref(cand), float(beta), int(eight), idx.ctypes.data, len(idx), out.ctypes.data,
+                                       C.byref(n), info))
+    return out[: n.value].copy(), {"nu": info[0], "nv": info[1], "components": info[2], "largest_cells": info[3]}
+
+
 # ---- refit (fitting.jl:57; shapes/*.jl refit) + invalidate_indexes! (fitting.jl:197) -----------
 def refit(s: FittedShape, pc: RANSACCloud, params, disable: bool = False) -> ExtractedShape:
     cand = s.to_cand()
