@@ -64,6 +64,12 @@ extern "C" {
  * Int64 wrap, Q9).  Needs every subset uploaded with rsc_cloud_set_subset. */
 #define RSC_SCORE_PROGRESSIVE 16u
 
+/* extension switch (off by default): rsc_ransac_run keeps, of every extracted shape's compatible points, only
+ * those in the largest connected component of its parameter-space bitmap (rsc_bitmap_filter) -- the paper's
+ * third compatibility criterion, which the reference documents and leaves out (docs/src/ransac.md:106-112).
+ * Cell size / connectivity: rsc_ctx_set_bitmap.  Not with sharded storage. */
+#define RSC_EXTRACT_BITMAP 32u
+
 /* which counter plays `s` in prob(n,s,N,k): utilities.jl:297-300 */
 #define RSC_S_LENGTHC 0
 #define RSC_S_ALLCAND 1
@@ -258,6 +264,7 @@ int32_t rsc_refit_lsq(rsc_cloud* cloud, const rsc_params* params, const rsc_cand
  * and cones wraps).  out_idx (capacity n) receives them in input order, *out_n their number; info[4]
  * (nullable) = cells along u, cells along v, number of components, cells of the largest.  Definition:
  * oracle/ransac_oracle.py::bitmap_filter. */
+int32_t rsc_ctx_set_bitmap(rsc_ctx* ctx, double beta, int32_t eight); /* parameters of RSC_EXTRACT_BITMAP */
 int32_t rsc_bitmap_filter(rsc_cloud* cloud, const rsc_cand* cand, double beta, int32_t eight, const int64_t* idx, int64_t n,
                           int64_t* out_idx, int64_t* out_n, int32_t* info);
 

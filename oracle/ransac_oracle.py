@@ -1148,15 +1148,28 @@ def largestconncomp(bimage, indmap, connectivity="default") -> list:
 
 # ---- the extension: the third compatibility criterion as a filter on an inlier list -----------------
 # (definition shared with rsc_bitmap.cu).  2-D parameters of a point on the shape:
-#   plane     project2plane(...)[:, :2]                                    (the reference's own frame)
+#   plane     the first two coordinates of project2plane's frame (plane.jl:82-103) built with stable_orthogonal
 #   sphere    (R phi, R sin(lat)) about the z axis -- Lambert's equal-area cylinder; phi wraps
-#   cylinder  (R phi, h) in the frame (x, y, axis), x = arbitrary_orthogonal(axis); phi wraps
+#   cylinder  (R phi, h) in the frame (x, y, axis), x = stable_orthogonal(axis); phi wraps
 #   cone      (r_ref phi, s): azimuth about the axis and slant distance from the apex, r_ref = sin(opang/2) times
 #             the mid slant distance of the given points (so that cells are ~square there); phi wraps
 # Cells: ix = floor((u - umin) / bu), iy = floor((v - vmin) / bv) over the bounding box of the parameters, with
 # nu = max(1, round(range / beta)) cells (wrapping axis: nu = max(3, round(2 pi R / beta)) cells over the full
 # turn); a component is 4- or 8-connected (x wraps where phi does); the largest one by number of CELLS wins,
 # ties go to the component holding the smallest column-major cell index; its points are kept, in input order.
+
+
+def stable_orthogonal(vec) -> np.ndarray:
+    """arbitrary_orthogonal with the smallest component taken by MAGNITUDE: the reference's version (smallest by
+    value) returns the zero vector whenever the smallest component is the only non-zero one, e.g. for (0, 0, -1),
+    and its project2plane then yields NaNs.  Used by the extension's frames."""
+    v = normalize3(_v(vec))
+    a = np.abs(v)
+    b0 = (a[0] < a[1]) and (a[0] < a[2])
+    b1 = (a[1] <= a[0]) and (a[1] < a[2])
+    b2 = (a[2] <= a[0]) and (a[2] <= a[1])
+    rv = np.array([float(b0), float(b1), float(b2)])
+    return cross3(v, rv)
 
 
 def _dot_rows(V, o):
@@ -1171,7 +1184,7 @@ def shape_parameters2d(sh: Shape, pts):
     p7 = sh.params7()
     if sh.kind == PLANE:
         o_z = normalize3(p7[3:6])
-        o_x = normalize3(arbitrary_orthogonal(o_z))
+        o_x = normalize3(stable_orthogonal(o_z))
         o_y = normalize3(cross3(o_z, o_x))
         V = P - p7[0:3]
         return np.stack([_dot_rows(V, o_x), _dot_rows(V, o_y)], axis=1), None, False
@@ -1183,14 +1196,14 @@ def shape_parameters2d(sh: Shape, pts):
         return np.stack([R * phi, R * (V[:, 2] / r)], axis=1), None, True
     if sh.kind == CYLINDER:
         a = normalize3(p7[0:3])
-        ox = normalize3(arbitrary_orthogonal(a))
+        ox = normalize3(stable_orthogonal(a))
         oy = normalize3(cross3(a, ox))
         V = P - p7[3:6]
         R = float(p7[6])
         phi = np.arctan2(_dot_rows(V, oy), _dot_rows(V, ox))
         return np.stack([R * phi, _dot_rows(V, a)], axis=1), None, True
     a = normalize3(p7[3:6])
-    ox = normalize3(arbitrary_orthogonal(a))
+    ox = normalize3(stable_orthogonal(a))
     oy = normalize3(cross3(a, ox))
     V = P - p7[0:3]
     s = np.sqrt(_dot_rows(V, V.T))
@@ -1411,12 +1424,15 @@ def ransac(
     octree: Optional[MortonOctree] = None,
     progressive: bool = False,
     lsq: bool = False,
+    bitmap: Optional[Tuple[float, bool]] = None,
 ) -> List[Extracted]:
     """iterations.jl:14-21 + :35-162.
 
     `progressive=True` (extension) refines overlapping scores on further subsets before
     the extraction test (refine_progressive); intervals are then the float64 ones (estimatescore_f64).
     `lsq=True` (extension) refits the best candidate by least squares before extracting it.
+    `bitmap=(beta, eight)` (extension) extracts only the compatible points in the largest connected
+    component of the shape's parameter-space bitmap (bitmap_filter; docs/src/ransac.md:106-112).
 
     `minimal_sets(k, i)` may supply the index triple of minimal set i of iteration k (or None
     for a failed sample); by default the Philox sampler above is used with set_id =
@@ -1501,6 +1517,8 @@ def ransac(
                 if lsq:
                     shapes[best] = lsq_refine(shapes[best], pc, params)[0]
                 ip = refit(shapes[best], pc, params)
+                if bitmap is not None and len(ip):
+                    ip = ip[bitmap_filter(shapes[best], pc.vertices[ip], bitmap[0], bitmap[1])[0]]
                 tr.evals += int(pc.isenabled.sum())
                 pc.isenabled[ip] = False
                 extracted.append(Extracted(shapes[best], ip))

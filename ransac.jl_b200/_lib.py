@@ -103,6 +103,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_double)]),
     "rsc_refit_lsq": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), C.c_double, C.POINTER(rsc_cand),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
+    "rsc_ctx_set_bitmap": (C.c_int32, [_P, C.c_double, C.c_int32]),
     "rsc_bitmap_filter": (C.c_int32, [_P, C.POINTER(rsc_cand), C.c_double, C.c_int32, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     "rsc_ctx_set_allreduce": (C.c_int32, [_P, _P, _P]),
     "rsc_comm_unique_id": (C.c_int32, [_P]),
@@ -162,6 +163,7 @@ def loaded() -> bool:
 
 
 RSC_SCORE_PROGRESSIVE = 16  # compat_flags: progressive subset scoring in rsc_ransac_run (extension)
+RSC_EXTRACT_BITMAP = 32  # compat_flags: keep the largest connected component of the parameter-space bitmap (extension)
 RSC_REFIT_LSQ = 8  # compat_flags: least-squares refit before each extraction (extension, include/rsc.h)
 RSC_SAMPLER_OCTREE = 2  # compat_flags: level-weighted octree-cell sampler (extension, include/rsc.h)
 

@@ -189,12 +189,15 @@ static void h_normalize(const double* a, double* o) {
 static void h_cross(const double* a, const double* b, double* o) {
   o[0] = a[1] * b[2] - a[2] * b[1], o[1] = a[2] * b[0] - a[0] * b[2], o[2] = a[0] * b[1] - a[1] * b[0];
 }
-static void h_arbitrary_orthogonal(const double* vec, double* o) {  // utilities.jl:84-92
+// utilities.jl:84-92 with the smallest component taken by magnitude (oracle: stable_orthogonal; the reference's
+// version returns the zero vector for e.g. (0, 0, -1))
+static void h_arbitrary_orthogonal(const double* vec, double* o) {
   double v[3];
   h_normalize(vec, v);
-  const bool b0 = (v[0] < v[1]) && (v[0] < v[2]);
-  const bool b1 = (v[1] <= v[0]) && (v[1] < v[2]);
-  const bool b2 = (v[2] <= v[0]) && (v[2] <= v[1]);
+  const double a[3] = {fabs(v[0]), fabs(v[1]), fabs(v[2])};
+  const bool b0 = (a[0] < a[1]) && (a[0] < a[2]);
+  const bool b1 = (a[1] <= a[0]) && (a[1] < a[2]);
+  const bool b2 = (a[2] <= a[0]) && (a[2] <= a[1]);
   const double rv[3] = {b0 ? 1.0 : 0.0, b1 ? 1.0 : 0.0, b2 ? 1.0 : 0.0};
   h_cross(v, rv, o);
 }
@@ -335,6 +338,14 @@ int32_t bitmap_filter_dev(rsc_cloud* cloud, const rsc_cand& cand, double beta, b
 }  // namespace rsc
 
 using namespace rsc;
+
+extern "C" int32_t rsc_ctx_set_bitmap(rsc_ctx* ctx, double beta, int32_t eight) {
+  if (!ctx) return RSC_E_ARG;
+  if (!(beta > 0.0)) return fail(ctx, RSC_E_ARG, "set_bitmap: beta must be positive");
+  ctx->bitmap_beta = beta;
+  ctx->bitmap_eight = eight != 0;
+  return RSC_OK;
+}
 
 extern "C" int32_t rsc_bitmap_filter(rsc_cloud* cloud, const rsc_cand* cand, double beta, int32_t eight, const int64_t* idx, int64_t n,
                                      int64_t* out_idx, int64_t* out_n, int32_t* info) {

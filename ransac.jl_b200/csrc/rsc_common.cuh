@@ -102,6 +102,8 @@ struct rsc_ctx {
   void* comm = nullptr;                  // ncclComm_t of rsc_ctx_comm_init (rsc_comm.cu); allreduce then points into the library
   int rank = 0, nranks = 1;
   int64_t allreduce_calls = 0, allreduce_bytes = 0;
+  double bitmap_beta = 0.0;  // RSC_EXTRACT_BITMAP: cell size of the parameter-space bitmap (rsc_ctx_set_bitmap)
+  int bitmap_eight = 0;
   void* pinned = nullptr;    // small pinned staging area
   size_t pinned_cap = 0;
 };
@@ -271,6 +273,11 @@ int32_t scan_u32(rsc_ctx* ctx, const uint32_t* counts, int n, unsigned long long
 // events before the real pass, so that its duration is not an event pair around one ~70 us launch
 int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& cand, cudaStream_t st, int timed_reps = 1);
 int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st);
+int32_t refit_mask_from_list(rsc_cloud* cloud, const int64_t* d_list, int64_t n, cudaStream_t st);
+// parameter-space bitmap filter (rsc_bitmap.cu): the points of d_idx whose cell lies in the largest connected
+// component -> d_out (capacity n); synchronises `st`
+int32_t bitmap_filter_dev(rsc_cloud* cloud, const rsc_cand& cand, double beta, bool eight, const int64_t* d_idx, int64_t n,
+                          int64_t* d_out, int64_t* out_n, int32_t* info, cudaStream_t st);
 // least-squares refit of *cand in place (rsc_lsq.cu); synchronises `st`
 int32_t lsq_refine(rsc_cloud* cloud, const rsc_params* params, double band, rsc_cand* cand, int64_t* n_used, double* rms,
                    cudaStream_t st);

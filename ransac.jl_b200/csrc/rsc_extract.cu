@@ -316,6 +316,36 @@ int32_t refit_mask_enqueue(rsc_cloud* cloud, const Thresh& th, const rsc_cand& c
   return RSC_OK;
 }
 
+__global__ void mask_from_list_kernel(const int64_t* __restrict__ list, int64_t n, int64_t global_offset, uint32_t* __restrict__ inl) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = list[i] - global_offset;
+  atomicOr(inl + (p >> 5), 1u << (p & 31));
+}
+
+// Replace the inlier mask of the last refit_mask_enqueue by the points of `d_list` (n global indices, a subset
+// of that mask: the parameter-space bitmap filter) and redo the per-CTA counts / offsets / total.
+int32_t refit_mask_from_list(rsc_cloud* cloud, const int64_t* d_list, int64_t n, cudaStream_t st) {
+  rsc_ctx* ctx = cloud->ctx;
+  const int64_t n_pad = cloud->n_pad;
+  const int64_t words = n_pad / 32;
+  const int nblocks = (int)((n_pad + kExPts - 1) / kExPts);
+  char* b = ctx->idxbuf.as<char>();
+  uint32_t* inl = reinterpret_cast<uint32_t*>(b);
+  unsigned long long* offsets = reinterpret_cast<unsigned long long*>(b + ((size_t)words * 4 + 15) / 16 * 16);
+  uint32_t* block_counts = reinterpret_cast<uint32_t*>(offsets + nblocks);
+  RSC_CUDA(ctx, cudaMemsetAsync(inl, 0, (size_t)words * 4, st));
+  if (n > 0) {
+    mask_from_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_list, n, cloud->global_offset, inl);
+    RSC_CUDA(ctx, cudaGetLastError());
+  }
+  block_count_kernel<<<(nblocks + 255) / 256, 256, 0, st>>>(inl, words, block_counts, nblocks);
+  RSC_CUDA(ctx, cudaGetLastError());
+  scan_counts_kernel<<<1, 1024, 0, st>>>(block_counts, nblocks, offsets, ctx->misc2.as<unsigned long long>());
+  RSC_CUDA(ctx, cudaGetLastError());
+  return RSC_OK;
+}
+
 int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cudaStream_t st) {
   rsc_ctx* ctx = cloud->ctx;
   const int64_t n_pad = cloud->n_pad;

@@ -241,7 +241,10 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
   if (shard && !ctx->allreduce)
     return fail(ctx, RSC_E_STATE, "ransac_run: sharded storage needs a communicator (rsc_ctx_comm_init or rsc_ctx_set_allreduce)");
   if (shard && cloud->n_global >= 2147483647LL) return fail(ctx, RSC_E_ARG, "ransac_run: sharded storage supports clouds below 2^31 points");
-  if (shard && (p->compat_flags & RSC_REFIT_LSQ)) return fail(ctx, RSC_E_STATE, "ransac_run: RSC_REFIT_LSQ is not available on sharded storage");
+  if (shard && (p->compat_flags & (RSC_REFIT_LSQ | RSC_EXTRACT_BITMAP)))
+    return fail(ctx, RSC_E_STATE, "ransac_run: RSC_REFIT_LSQ / RSC_EXTRACT_BITMAP are not available on sharded storage");
+  if ((p->compat_flags & RSC_EXTRACT_BITMAP) && !(ctx->bitmap_beta > 0.0))
+    return fail(ctx, RSC_E_STATE, "ransac_run: RSC_EXTRACT_BITMAP needs rsc_ctx_set_bitmap(ctx, beta, eight) first");
   const int64_t N = cloud->n_global > 0 ? cloud->n_global : cloud->n;
   const int64_t M = sub.m_global > 0 ? sub.m_global : sub.m;
   const int S = p->minsubsetN;
@@ -445,6 +448,21 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
       RUN_CUDA(ls.olden.ensure((size_t)swords * 4));
       RUN_CUDA(cudaMemcpyAsync(ls.olden.p, sub.enabled, (size_t)swords * 4, cudaMemcpyDeviceToDevice, st));
       if ((rc = refit_mask_enqueue(cloud, thr, shape, st))) return rc;
+      if (p->compat_flags & RSC_EXTRACT_BITMAP) {  // extension: only the largest connected component in parameter space
+        unsigned long long tot = 0;
+        RUN_CUDA(cudaMemcpyAsync(&tot, ctx->misc2.p, 8, cudaMemcpyDeviceToHost, st));
+        RUN_CUDA(sync());
+        if (tot > 0) {
+          RUN_CUDA(ctx->misc.ensure((size_t)tot * 16));
+          int64_t* lst = ctx->misc.as<int64_t>();
+          if ((rc = refit_write_enqueue(cloud, lst, false, st))) return rc;  // the list, nothing disabled yet
+          int64_t kept = 0;
+          if ((rc = bitmap_filter_dev(cloud, shape, ctx->bitmap_beta, ctx->bitmap_eight != 0, lst, (int64_t)tot, lst + tot, &kept, nullptr, st)))
+            return rc;
+          ++run->syncs;
+          if ((rc = refit_mask_from_list(cloud, lst + tot, kept, st))) return rc;
+        }
+      }
       // the inlier mask words (ctx->idxbuf) and this rank's inlier count (ctx->misc2) are on the device
       if ((rc = refit_write_enqueue(cloud, run->d_idx + run->off.back(), true, st))) return rc;
       if (shard) {  // the replicated whole-cloud mask follows; the ranks' inlier counts ride along
@@ -459,6 +477,7 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
       // launch without a round trip.  Masked form (the least-squares refit moves the shape, so the bound
       // does not hold; also the fallback): score against the whole slice under the mask old & ~new.
       const int nst = store.n;
+      // (the bitmap filter only removes points from the list, so the bound still holds with it)
       bool masked = (p->compat_flags & RSC_REFIT_LSQ) != 0 || getenv("RSC_K5_MASKED") != nullptr;
       PointSet dps = sps;
       // hit counts [nst] + two flags that ride with them through the all-reduce: guard-band queue overflow,

@@ -181,6 +181,10 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     delete run;
     return fail(ctx, RSC_E_STATE, "ransac_run: the extension switches are not available on sharded storage");
   }
+  if (p->compat_flags & RSC_EXTRACT_BITMAP) {
+    delete run;
+    return fail(ctx, RSC_E_STATE, "ransac_run: RSC_EXTRACT_BITMAP cannot be combined with RSC_SCORE_PROGRESSIVE / RSC_SAMPLER_OCTREE");
+  }
   if (!ctx->loop_scratch) ctx->loop_scratch = new LoopScratch();
   LoopScratch& ls = *static_cast<LoopScratch*>(ctx->loop_scratch);
   Store& store = ls.store;

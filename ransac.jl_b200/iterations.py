@@ -27,7 +27,7 @@ def _all_builtin(params) -> bool:
 
 
 def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = False, seed: int = 1234,
-           sampler: str = "root", progressive: bool = False, lsq: bool = False) -> Tuple[List[ExtractedShape], float]:
+           sampler: str = "root", progressive: bool = False, lsq: bool = False, bitmap=None) -> Tuple[List[ExtractedShape], float]:
     """Run efficient RANSAC on `pc`; returns (extracted shapes, seconds).
 
     `reset_rand=True` pins the sampler seed to 1234 like `Random.seed!(1234)` (iterations.jl:36);
@@ -39,20 +39,28 @@ def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = 
     the reference's "TODO: refine if best.overlap", iterations.jl:110; `RSC_SCORE_PROGRESSIVE` in the
     device loop) and leaves the number of extra (candidate, subset) evaluations in `pc.last_refined`.
     `lsq=True` (extension) refits the best candidate by least squares to the compatible points within
-    3 eps before it is extracted (`fitting.lsq_refit`; the paper's refit, docs/src/ransac.md:163-169)."""
+    3 eps before it is extracted (`fitting.lsq_refit`; the paper's refit, docs/src/ransac.md:163-169).
+    `bitmap=(beta, eight)` (extension) extracts, of every shape's compatible points, only those in the largest
+    connected component of its parameter-space bitmap (`fitting.bitmap_filter`, `RSC_EXTRACT_BITMAP`; the paper's
+    third compatibility criterion, which the reference documents and leaves out, docs/src/ransac.md:106-112)."""
     if setenabled:
         pc.enable_all()
     if reset_rand:
         seed = 1234
     if _all_builtin(params):
-        return _ransac_device(pc, params, seed, sampler, lsq, progressive)
+        return _ransac_device(pc, params, seed, sampler, lsq, progressive, bitmap)
+    if bitmap is not None:
+        raise ValueError("the bitmap filter is only available in the device loop (built-in shape types)")
     if sampler != "root":
         raise ValueError("the octree sampler is only available in the device loop (built-in shape types)")
     return _ransac_host(pc, params, seed, progressive, lsq)
 
 
-def _ransac_device(pc, params, seed, sampler="root", lsq=False, progressive=False):
+def _ransac_device(pc, params, seed, sampler="root", lsq=False, progressive=False, bitmap=None):
     cp = to_c(params)
+    if bitmap is not None:
+        pc.ctx.check(lib.rsc_ctx_set_bitmap(pc.ctx.h, float(bitmap[0]), int(bool(bitmap[1]))))
+        cp.compat_flags |= _lib.RSC_EXTRACT_BITMAP
     if progressive:
         for j in range(len(pc.subsets)):  # the refinement scores on the subsets 2..r too
             pc.upload_subset(j)

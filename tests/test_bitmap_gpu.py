@@ -55,7 +55,7 @@ def test_patches_on_every_shape_type(eight):
     ax = np.array([0.2, 0.9, 0.4]); ax /= np.linalg.norm(ax)
     ctr = np.array([3.0, 0.0, -2.0]); ctr = ctr - ax * float(ax @ ctr)
     cyl = R.FittedCylinder(ax, ctr, 2.5, True)
-    ox = O.normalize3(O.arbitrary_orthogonal(ax)); oy = O.normalize3(O.cross3(ax, ox))
+    ox = O.normalize3(O.stable_orthogonal(ax)); oy = O.normalize3(O.cross3(ax, ox))
     def band(phi_lo, phi_hi, h0, h1, n):
         phi, h = rng.uniform(phi_lo, phi_hi, n), rng.uniform(h0, h1, n)
         return ctr + 2.5 * (np.cos(phi)[:, None] * ox + np.sin(phi)[:, None] * oy) + h[:, None] * ax
@@ -67,7 +67,7 @@ def test_patches_on_every_shape_type(eight):
     def cpatch(phi0, w, s0, s1, n):
         phi, s = rng.uniform(phi0 - w, phi0 + w, n), rng.uniform(s0, s1, n)
         half = math.radians(25)
-        ox2 = O.normalize3(O.arbitrary_orthogonal(np.array([0.0, 0.0, -1.0]))); oy2 = O.normalize3(O.cross3(np.array([0.0, 0.0, -1.0]), ox2))
+        ox2 = O.normalize3(O.stable_orthogonal(np.array([0.0, 0.0, -1.0]))); oy2 = O.normalize3(O.cross3(np.array([0.0, 0.0, -1.0]), ox2))
         rad = np.cos(phi)[:, None] * ox2 + np.sin(phi)[:, None] * oy2
         return cone.apex + s[:, None] * (math.cos(half) * np.array([0.0, 0.0, -1.0]) + math.sin(half) * rad)
     kept, ncomp = _check(R, cone, np.vstack([cpatch(3.0, 0.8, 6, 12, 5000), cpatch(0.0, 0.1, 2, 2.5, 200)]), 0.3, eight)
@@ -78,7 +78,7 @@ def test_diagonal_chain_needs_eight_connectivity():
     import ransac_jl_b200 as R
 
     plane = R.FittedPlane(np.zeros(3), np.array([0.0, 0.0, 1.0]))
-    ox = O.normalize3(O.arbitrary_orthogonal(np.array([0.0, 0.0, 1.0]))); oy = O.normalize3(O.cross3(np.array([0.0, 0.0, 1.0]), ox))
+    ox = O.normalize3(O.stable_orthogonal(np.array([0.0, 0.0, 1.0]))); oy = O.normalize3(O.cross3(np.array([0.0, 0.0, 1.0]), ox))
     k = np.arange(40)
     chain = (k[:, None] + 0.5) * ox + (k[:, None] + 0.5) * oy     # one point per diagonal cell
     block = np.array([[60 + i + 0.5, 5 + j + 0.5] for i in range(4) for j in range(4)])
@@ -110,3 +110,38 @@ def test_on_refit_inliers_of_a_noisy_scene():
             assert (info["nu"], info["nv"], info["components"], info["largest_cells"]) == stats
             assert len(got) > 0.8 * len(ex.inpoints)  # the primitive itself is one piece; outliers near its surface are not
     pc.close()
+
+
+def test_loop_with_the_bitmap_switch_matches_the_oracle_loop():
+    """RSC_EXTRACT_BITMAP inside rsc_ransac_run on a scene with two separate coplanar patches: without the filter
+    they are extracted as one plane, with it the large patch, the sphere and then the small patch -- and the
+    device loop equals the oracle's loop with the same filter (shapes, inlier lists, isenabled)"""
+    import ransac_jl_b200 as R
+    from tests.helpers import oracle_params
+
+    rng = np.random.default_rng(7)
+    A = np.c_[rng.uniform(0, 20, (12000, 2)), rng.normal(0, 0.02, 12000)]
+    B = np.c_[rng.uniform(60, 70, (3000, 2)), rng.normal(0, 0.02, 3000)]
+    d = rng.normal(size=(8000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    S = np.array([30, 30, 15.0]) + 6 * d
+    out = rng.uniform(-10, 80, (5000, 3))
+    no = rng.normal(size=(5000, 3))
+    no /= np.linalg.norm(no, axis=1, keepdims=True)
+    V = np.vstack([A, B, S, out]).astype(np.float32)
+    N = np.vstack([np.tile([0, 0, 1.0], (15000, 1)), d, no]).astype(np.float32)
+    perm = rng.permutation(len(V))
+    V, N = V[perm], N[perm]
+    pc = R.RANSACCloud(V, N, 4)
+    params = R.ransacparameters(iteration={"tau": 300, "minsubsetN": 128, "itermax": 80})
+    plain, _ = R.ransac(pc, params, True, seed=5)
+    assert [len(e.inpoints) for e in plain[:2]] == [15000, 8000]
+    got, _ = R.ransac(pc, params, True, seed=5, bitmap=(1.5, False))
+    oc = O.Cloud(V, N, [s.copy() for s in pc.subsets])
+    want = O.ransac(oc, oracle_params(params), True, seed=5, bitmap=(1.5, False))
+    assert [len(e.inpoints) for e in want] == [12000, 8000, 3000]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape.to_cand().type == w.shape.kind
+        np.testing.assert_array_equal(g.inpoints, w.inpoints)
+    np.testing.assert_array_equal(pc.isenabled, oc.isenabled)
