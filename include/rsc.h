@@ -114,7 +114,9 @@ typedef struct rsc_params {
   double sphere_par;   /* sphere.sphere_par */
   double minconeopang; /* cone.minconeopang */
   uint32_t compat_flags;
-  uint32_t reserved;
+  uint32_t lw_period; /* RSC_SAMPLER_OCTREE: the level weights are refreshed every lw_period iterations (0 or 1 = after
+                         every iteration, the reference's schedule, iterations.jl:148); larger periods let the loop
+                         batch its iterations -- the results depend on the period, not on the batching */
 } rsc_params;
 
 /* cumulative counters / device timers of a context */

@@ -42,7 +42,7 @@ struct RscParams          # 160 bytes
     sphere_par::Float64
     minconeopang::Float64
     compat_flags::UInt32
-    reserved::UInt32
+    lw_period::UInt32         # RSC_SAMPLER_OCTREE: refresh period of the level weights (0/1 = every iteration)
 end
 
 const KIND = Dict{Any,Int32}(FittedPlane => 0, FittedSphere => 1, FittedCylinder => 2, FittedCone => 3)

@@ -1425,6 +1425,7 @@ def ransac(
     progressive: bool = False,
     lsq: bool = False,
     bitmap: Optional[Tuple[float, bool]] = None,
+    lw_period: int = 1,
 ) -> List[Extracted]:
     """iterations.jl:14-21 + :35-162.
 
@@ -1530,7 +1531,8 @@ def ransac(
                 inpts = [inpts[j] for j in keep]
                 evaluated = [evaluated[j] for j in keep]
         if octree is not None:
-            levelweight = updatelevelweight(levelweight, levelscore)  # iterations.jl:148
+            if k % max(1, lw_period) == 0:  # lw_period = 1: after every iteration, the reference's schedule
+                levelweight = updatelevelweight(levelweight, levelscore)  # iterations.jl:148
             tr.levelweight = levelweight.copy()
         s = cc[sidx[it["terminate_s"]]]
         if prob(tau, s, pc.size, drawN) > prob_det:

@@ -42,7 +42,7 @@ class rsc_params(C.Structure):
         ("sphere_par", C.c_double),
         ("minconeopang", C.c_double),
         ("compat_flags", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("lw_period", C.c_uint32),
     ]
 
 

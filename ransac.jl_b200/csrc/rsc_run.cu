@@ -120,13 +120,14 @@ using namespace rsc;
 // per octree level: number of new candidates and the sum of their scores (fitting.jl:184 adds E(score)
 // per candidate; E is affine in the count, so the host adds the closed form of the sum)
 __global__ void level_stats_kernel(const int32_t* __restrict__ out_set, const int32_t* __restrict__ set_level,
-                                   const int32_t* __restrict__ score, int n, long long* __restrict__ lv /*[2][11]*/) {
+                                   const int32_t* __restrict__ score, int n, int S, long long* __restrict__ lv /*[nb][2][11]*/) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int l = set_level[out_set[i]] - 1;
   if (l < 0 || l >= 11) return;
-  atomicAdd((unsigned long long*)(lv + l), 1ull);
-  atomicAdd((unsigned long long*)(lv + 11 + l), (unsigned long long)score[i]);
+  long long* row = lv + (size_t)(out_set[i] / S) * 22;  // the batch iteration the candidate's minimal set belongs to
+  atomicAdd((unsigned long long*)(row + l), 1ull);
+  atomicAdd((unsigned long long*)(row + 11 + l), (unsigned long long)score[i]);
 }
 
 extern "C" {
@@ -251,7 +252,12 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   };
   const bool cells_mode = (p->compat_flags & RSC_SAMPLER_OCTREE) != 0;
   const int nlv = cloud->cells.nlevels;
-  const int Bmax = cells_mode ? 1 : (getenv("RSC_BATCH") ? std::max(1, std::min(16, atoi(getenv("RSC_BATCH")))) : 16);
+  // cell sampler: the level weights are refreshed every `lw_period` iterations (params.lw_period; 1 = after every
+  // iteration, the reference's schedule, iterations.jl:148); a speculative batch never crosses a refresh, so the
+  // results for a given period do not depend on the batch size
+  const int lw_period = cells_mode ? std::max(1, (int)p->lw_period) : 1;
+  const int Bcap = getenv("RSC_BATCH") ? std::max(1, std::min(16, atoi(getenv("RSC_BATCH")))) : 16;
+  const int Bmax = cells_mode ? std::min(Bcap, lw_period) : Bcap;
   const int Bmin = getenv("RSC_BATCH_MIN") ? std::max(1, atoi(getenv("RSC_BATCH_MIN"))) : 8;  // batch size after an extraction (swept on c2/c4: 8-16 best)
   int B = 1;  // iterations per speculative batch
   bool terminated = false;
@@ -287,7 +293,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     }
     run->nlevels = nlv;
     for (int l = 0; l < nlv; ++l) run->levelweight[l] = 1.0 / nlv, run->levelscore[l] = 0.0;
-    RUN_CUDA(lvbuf.ensure(2 * 11 * 8));
+    RUN_CUDA(lvbuf.ensure((size_t)16 * 22 * 8));
   }
 
   if (prog)
@@ -310,7 +316,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   RUN_CUDA(store.reserve((size_t)maxnew * Bmax, st));  // room for the first batches without re-allocations
   for (int k = 1; k <= p->itermax && !terminated;) {
     if (n_enabled < p->tau) break;  // iterations.jl:75
-    const int nb = std::min(B, p->itermax - k + 1);
+    int nb = std::min(B, p->itermax - k + 1);
+    if (cells_mode) nb = std::min(nb, lw_period - (k - 1) % lw_period);  // up to the next refresh of the level weights
     const auto tk0 = now();
     // ---- K1: nb * minsubsetN minimal sets -> candidates (device, compacted in reference order) ----
     FitScratch fs;
@@ -335,7 +342,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     int64_t best[2] = {-1, 0};
     long long seg_keys[18];
     for (int j = 0; j < 18; ++j) seg_keys[j] = -1;
-    long long lv_host[22] = {0};
+    long long lv_host[16 * 22] = {0};
     for (int attempt = 0;; ++attempt) {
       store.n = store_n0;
       int32_t ovf = 0;
@@ -366,11 +373,11 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
         RUN_CUDA(cudaGetLastError());
         RUN_CUDA(cudaMemcpyAsync(&ovf, cv + 2 * n_new, 4, cudaMemcpyDeviceToHost, st));
         if (cells_mode) {
-          RUN_CUDA(cudaMemsetAsync(lvbuf.p, 0, 2 * 11 * 8, st));
+          RUN_CUDA(cudaMemsetAsync(lvbuf.p, 0, (size_t)nb * 22 * 8, st));
           level_stats_kernel<<<(n_new + 255) / 256, 256, 0, st>>>(fs.out_set, fs.level, store.score[store.cur].as<int32_t>() + store.n,
-                                                                  n_new, lvbuf.as<long long>());
+                                                                  n_new, S, lvbuf.as<long long>());
           RUN_CUDA(cudaGetLastError());
-          RUN_CUDA(cudaMemcpyAsync(lv_host, lvbuf.p, 2 * 11 * 8, cudaMemcpyDeviceToHost, st));
+          RUN_CUDA(cudaMemcpyAsync(lv_host, lvbuf.p, (size_t)nb * 22 * 8, cudaMemcpyDeviceToHost, st));
         }
         store.n += n_new;
       }
@@ -414,9 +421,10 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     counters[2] = (int64_t)kk * S;
     counters[0] = store.n;
     if (cells_mode && n_new > 0) {  // levelscore[level] += sum of E = -n + (N+2)/(M+2) (sum sigma + n)
+      const long long* lvj = lv_host + (size_t)j * 22;
       for (int l = 0; l < nlv; ++l)
-        if (lv_host[l])
-          run->levelscore[l] += (-(double)lv_host[l]) + ((double)(N + 2) / (double)(sub.m + 2)) * (double)(lv_host[11 + l] + lv_host[l]);
+        if (lvj[l])
+          run->levelscore[l] += (-(double)lvj[l]) + ((double)(N + 2) / (double)(sub.m + 2)) * (double)(lvj[11 + l] + lvj[l]);
     }
     if (seg_keys[j] > bestkey) bestkey = seg_keys[j];  // first maximum wins: the key carries the store index
     best[0] = bestkey >= 0 ? (int64_t)(0x7fffffff - (bestkey & 0xffffffffll)) : -1;
@@ -566,7 +574,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
         }
       }
     }
-    if (cells_mode) rsc_update_levelweight(run->levelweight, run->levelscore, nlv);  // iterations.jl:148
+    if (cells_mode && kk % lw_period == 0) rsc_update_levelweight(run->levelweight, run->levelscore, nlv);  // iterations.jl:148
     // iterations.jl:151-156
     if (prob_((double)p->tau, (double)counters[p->terminate_s], (double)N, (double)p->drawN) > p->prob_det) terminated = true;
     }  // iterations of the batch

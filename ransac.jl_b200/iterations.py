@@ -27,14 +27,16 @@ def _all_builtin(params) -> bool:
 
 
 def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = False, seed: int = 1234,
-           sampler: str = "root", progressive: bool = False, lsq: bool = False, bitmap=None) -> Tuple[List[ExtractedShape], float]:
+           sampler: str = "root", progressive: bool = False, lsq: bool = False, bitmap=None,
+           lw_period: int = 1) -> Tuple[List[ExtractedShape], float]:
     """Run efficient RANSAC on `pc`; returns (extracted shapes, seconds).
 
     `reset_rand=True` pins the sampler seed to 1234 like `Random.seed!(1234)` (iterations.jl:36);
     the Philox stream is of course not Julia's.  `sampler="octree"` (extension, needs
     `pc.build_cells()`) draws the minimal sets from level-weighted octree cells -- what the reference
     is written for -- instead of from the root cell, which is what its shipped code does (Q1); the
-    final level weights are left in `pc.levelweight`.  `progressive=True` (extension) refines
+    final level weights are left in `pc.levelweight`; `lw_period=P` refreshes the level weights every P iterations
+    instead of after each one, which lets the device loop batch its iterations (same results at any batch size).  `progressive=True` (extension) refines
     overlapping scores on further subsets before each extraction test (`fitting.refine_progressive`,
     the reference's "TODO: refine if best.overlap", iterations.jl:110; `RSC_SCORE_PROGRESSIVE` in the
     device loop) and leaves the number of extra (candidate, subset) evaluations in `pc.last_refined`.
@@ -48,7 +50,7 @@ def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = 
     if reset_rand:
         seed = 1234
     if _all_builtin(params):
-        return _ransac_device(pc, params, seed, sampler, lsq, progressive, bitmap)
+        return _ransac_device(pc, params, seed, sampler, lsq, progressive, bitmap, lw_period)
     if bitmap is not None:
         raise ValueError("the bitmap filter is only available in the device loop (built-in shape types)")
     if sampler != "root":
@@ -56,8 +58,9 @@ def ransac(pc: RANSACCloud, params, setenabled: bool = True, reset_rand: bool = 
     return _ransac_host(pc, params, seed, progressive, lsq)
 
 
-def _ransac_device(pc, params, seed, sampler="root", lsq=False, progressive=False, bitmap=None):
+def _ransac_device(pc, params, seed, sampler="root", lsq=False, progressive=False, bitmap=None, lw_period=1):
     cp = to_c(params)
+    cp.lw_period = max(1, int(lw_period))  # octree sampler: refresh period of the level weights (1 = every iteration)
     if bitmap is not None:
         pc.ctx.check(lib.rsc_ctx_set_bitmap(pc.ctx.h, float(bitmap[0]), int(bool(bitmap[1]))))
         cp.compat_flags |= _lib.RSC_EXTRACT_BITMAP

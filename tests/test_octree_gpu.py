@@ -104,6 +104,37 @@ def test_loop_with_cell_sampler_matches_oracle(R):
     assert [len(x.inpoints) for x in a] == [len(x.inpoints) for x in b]
 
 
+def test_cell_sampler_batched_with_a_refresh_period_matches_oracle_and_batch1(R, monkeypatch):
+    """lw_period = 8: the level weights are refreshed every 8 iterations, so the loop can run up to 8 iterations
+    per speculative batch; the results equal the oracle's loop with the same period AND the run forced to one
+    iteration per batch (RSC_BATCH=1) -- the period defines the result, the batching does not"""
+    sc = _scene(60_000, seed=93)
+    params = R.ransacparameters(iteration={"tau": 500, "minsubsetN": 128, "itermax": 48})
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4).build_cells(8)
+    batched, _ = R.ransac(pc, params, True, seed=13, sampler="octree", lw_period=8)
+    lw_b = pc.levelweight.copy()
+    monkeypatch.setenv("RSC_BATCH", "1")
+    single, _ = R.ransac(pc, params, True, seed=13, sampler="octree", lw_period=8)
+    monkeypatch.delenv("RSC_BATCH")
+    assert len(batched) == len(single)
+    for a, b in zip(batched, single):
+        assert list(a.shape.to_cand().p) == list(b.shape.to_cand().p)
+        np.testing.assert_array_equal(a.inpoints, b.inpoints)
+    np.testing.assert_array_equal(lw_b, pc.levelweight)
+    oc = O.MortonOctree(sc.vertices, 8)
+    opc = O.Cloud(sc.vertices, sc.normals, [s.copy() for s in pc.subsets])
+    tr = O.RansacTrace()
+    want = O.ransac(opc, oracle_params(params), True, seed=13, trace=tr, octree=oc, lw_period=8)
+    assert len(batched) == len(want) and len(want) >= 3
+    for got, w in zip(batched, want):
+        assert got.shape.to_cand().type == w.shape.kind
+        np.testing.assert_array_equal(got.inpoints, w.inpoints)
+    np.testing.assert_allclose(lw_b, tr.levelweight, rtol=1e-12)
+    # a different period is a different (equally valid) schedule
+    other, _ = R.ransac(pc, params, True, seed=13, sampler="octree", lw_period=1)
+    assert len(other) >= 3
+
+
 def test_reference_grid_leaf_depth(R):
     # test/octree.jl:116-139 on the device structure: 6^3 grid, every leaf at depth 3
     ps = (np.array([[i, j, k] for i in range(6) for j in range(6) for k in range(6)], float) / 3).astype(np.float32)

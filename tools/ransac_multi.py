@@ -28,6 +28,7 @@ ap.add_argument("--sampler", default="root", choices=["root", "octree"])
 ap.add_argument("--levels", type=int, default=8, help="octree levels of the cell sampler")
 ap.add_argument("--itermax", type=int, default=0)
 ap.add_argument("--progressive", type=int, default=0, help="1: progressive subset scoring (RSC_SCORE_PROGRESSIVE)")
+ap.add_argument("--lw-period", type=int, default=1, help="octree sampler: refresh the level weights every P iterations")
 ap.add_argument("--lsq", type=int, default=0, help="1: least-squares refit before each extraction (RSC_REFIT_LSQ)")
 args = ap.parse_args()
 
@@ -86,7 +87,8 @@ torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 t0 = time.perf_counter()
-ex, secs = R.ransac(pc, params, True, seed=2024, sampler=args.sampler, lsq=bool(args.lsq), progressive=bool(args.progressive))
+ex, secs = R.ransac(pc, params, True, seed=2024, sampler=args.sampler, lsq=bool(args.lsq), progressive=bool(args.progressive),
+                    lw_period=args.lw_period)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 tt = torch.tensor([dt], device="cuda")
@@ -106,7 +108,7 @@ if rank == 0:
     print(json.dumps({"scene": args.scene, "points": int(sc.vertices.shape[0]), "n_gpus": world, "ransac_seconds": float(tt.item()),
                       "shapes": [[R.strt(e.shape), int(len(e.inpoints))] for e in ex][:40], "n_shapes": len(ex),
                       "points_extracted": int(sum(len(e.inpoints) for e in ex)), "evals": int(st.evals),
-                      "sets_drawn": int(st.sets_drawn), "matches_unsharded": ok, "sampler": args.sampler, "lsq": bool(args.lsq), "progressive": bool(args.progressive), "refined": int(getattr(pc, "last_refined", 0)),
+                      "sets_drawn": int(st.sets_drawn), "matches_unsharded": ok, "sampler": args.sampler, "lw_period": args.lw_period, "lsq": bool(args.lsq), "progressive": bool(args.progressive), "refined": int(getattr(pc, "last_refined", 0)),
                       "device_loop_seconds": float(getattr(pc, "last_run_seconds", float("nan"))),
                       "build_cells_seconds": t_cells,
                       "levelweight": [round(float(x), 4) for x in getattr(pc, "levelweight", [])]}))
