@@ -1530,6 +1530,14 @@ def ransac(
                 scores = [scores[j] for j in keep]
                 inpts = [inpts[j] for j in keep]
                 evaluated = [evaluated[j] for j in keep]
+                if progressive:
+                    # the survivors' subset-1 inliers are all still enabled, but their inliers in the subsets 2..r may
+                    # just have been extracted: a refined score falls back to the (exact) subset-1 score
+                    M1 = len(pc.subsets[0])
+                    for j in range(len(shapes)):
+                        if evaluated[j][0] > 1:
+                            evaluated[j] = [1, len(inpts[j]), M1]
+                            scores[j] = estimatescore_f64(M1, pc.size, len(inpts[j]))
         if octree is not None:
             if k % max(1, lw_period) == 0:  # lw_period = 1: after every iteration, the reference's schedule
                 levelweight = updatelevelweight(levelweight, levelscore)  # iterations.jl:148

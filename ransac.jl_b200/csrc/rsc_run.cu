@@ -55,11 +55,11 @@ __global__ void gather_cands_kernel(const rsc_cand* __restrict__ store, const in
 // sigma[i] compatible points among their M[i] points; interval from the union, in float64 without the
 // reference's Int64 wrap (Q9) -- same operation order as oracle/ransac_oracle.py::estimatescore_f64.
 struct ProgMirror {
-  std::vector<int64_t> sigma, M;
+  std::vector<int64_t> sigma, M, sigma1;  // sigma1: the subset-1 count (what a refined score falls back to after an extraction)
   std::vector<int32_t> lvl;
   std::vector<double> lo, hi, E;
   size_t size() const { return E.size(); }
-  void clear() { sigma.clear(), M.clear(), lvl.clear(), lo.clear(), hi.clear(), E.clear(); }
+  void clear() { sigma.clear(), M.clear(), sigma1.clear(), lvl.clear(), lo.clear(), hi.clear(), E.clear(); }
   static void interval(int64_t m, int64_t N, int64_t sg, double* lo, double* hi, double* E) {
     const double Np = (double)(-2 - m), x = (double)(-2 - N), n = (double)(-1 - sg);
     const double xn = x * n;
@@ -73,7 +73,7 @@ struct ProgMirror {
   void push(int64_t sg, int64_t m, int64_t N) {
     double a, b, e;
     interval(m, N, sg, &a, &b, &e);
-    sigma.push_back(sg), M.push_back(m), lvl.push_back(1), lo.push_back(a), hi.push_back(b), E.push_back(e);
+    sigma.push_back(sg), M.push_back(m), sigma1.push_back(sg), lvl.push_back(1), lo.push_back(a), hi.push_back(b), E.push_back(e);
   }
   void add(size_t i, int64_t sg, int64_t m, int64_t N) {
     sigma[i] += sg, M[i] += m, lvl[i] += 1;
@@ -93,8 +93,17 @@ struct ProgMirror {
   void compact(const std::vector<uint32_t>& keep) {
     size_t o = 0;
     for (size_t i = 0; i < E.size(); ++i)
-      if (keep[i]) sigma[o] = sigma[i], M[o] = M[i], lvl[o] = lvl[i], lo[o] = lo[i], hi[o] = hi[i], E[o] = E[i], ++o;
-    sigma.resize(o), M.resize(o), lvl.resize(o), lo.resize(o), hi.resize(o), E.resize(o);
+      if (keep[i]) sigma[o] = sigma[i], M[o] = M[i], sigma1[o] = sigma1[i], lvl[o] = lvl[i], lo[o] = lo[i], hi[o] = hi[i], E[o] = E[i], ++o;
+    sigma.resize(o), M.resize(o), sigma1.resize(o), lvl.resize(o), lo.resize(o), hi.resize(o), E.resize(o);
+  }
+  // after an extraction: the survivors' subset-1 inliers are all still enabled, but their inliers in the subsets
+  // 2..r may just have been extracted -- a refined score falls back to the (exact) subset-1 score
+  void reset_refined(int64_t m1, int64_t N) {
+    for (size_t i = 0; i < E.size(); ++i)
+      if (lvl[i] > 1) {
+        sigma[i] = sigma1[i], M[i] = m1, lvl[i] = 1;
+        interval(m1, N, sigma1[i], &lo[i], &hi[i], &E[i]);
+      }
   }
 };
 
@@ -566,6 +575,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
             RUN_CUDA(cudaMemcpyAsync(keep_h.data(), keep, (size_t)nst * 4, cudaMemcpyDeviceToHost, st));
             RUN_CUDA(cudaStreamSynchronize(st));
             mirror.compact(keep_h);
+            mirror.reset_refined(sub.m, N);
           }
           store.cur = nxt;
           store.n = (int)kept;

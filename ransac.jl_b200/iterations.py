@@ -170,6 +170,11 @@ def _ransac_host(pc, params, seed, progressive=False, lsq=False):
                     en = pc.isenabled
                     dead = [j for j in range(len(scored)) if not en[scored.inpoints[j]].all()]
                     scored.deleteat(dead)
+                    if progressive:  # refined scores may count points of the subsets 2..r that were just extracted
+                        for j in range(len(scored)):
+                            if scored.evaluated[j][0] > 1:
+                                scored.evaluated[j] = [1, len(scored.inpoints[j]), M1]
+                                scored.scores[j] = estimatescore_f64(M1, pc.size, len(scored.inpoints[j]))
         if prob(tau, cc[sidx[it["terminate_s"]]], pc.size, drawN) > prob_det:
             break
     return extracted, int((time.time() - t0) * 100) / 100.0
