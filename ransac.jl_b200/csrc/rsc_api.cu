@@ -139,6 +139,10 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->hstage[b]) cudaFreeHost(ctx->hstage[b]);
+    if (ctx->hstage_free[b]) cudaEventDestroy(ctx->hstage_free[b]);
+  }
   for (cudaEvent_t e : {ctx->ev0, ctx->ev1, ctx->evk0, ctx->evk1, ctx->evr0, ctx->evr1})
     if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -2,7 +2,10 @@
 // AoS host arrays -> SoA float32 in HBM, the enabled bitmask (BitArray.chunks layout), and the
 // gathered contiguous copies of the random subsets (octree.jl:129-135) that scoring streams.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <thread>
 
 #include "rsc_common.cuh"
 
@@ -160,6 +163,79 @@ int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st) {
 
 constexpr int64_t kChunkPts = 2 << 20;  // upload granularity (48 MB of float32 AoS per chunk)
 
+// ---- pageable host memory <-> device through page-locked staging filled by worker threads ----------------
+static int host_copy_threads() {
+  if (const char* e = getenv("RSC_COPY_THREADS")) return std::max(1, std::min(32, atoi(e)));
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(4u, hw / 4));
+}
+
+static void par_memcpy(void* dst, const void* src, size_t bytes, int nthreads) {
+  if (nthreads <= 1 || bytes < ((size_t)4 << 20)) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = (bytes / nthreads + 4095) / 4096 * 4096;
+  std::vector<std::thread> th;
+  for (int t = 1; t < nthreads; ++t) {
+    const size_t off = (size_t)t * per;
+    if (off >= bytes) break;
+    const size_t len = std::min(per, bytes - off);
+    th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+  }
+  memcpy(dst, src, std::min(per, bytes));
+  for (auto& x : th) x.join();
+}
+
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+static int32_t ensure_hstage(rsc_ctx* ctx, size_t bytes) {
+  if (ctx->hstage_cap >= bytes) return RSC_OK;
+  for (int b = 0; b < 2; ++b) {
+    if (ctx->hstage[b]) cudaFreeHost(ctx->hstage[b]);
+    ctx->hstage[b] = nullptr;
+    if (!ctx->hstage_free[b]) RSC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->hstage_free[b], cudaEventDisableTiming));
+  }
+  ctx->hstage_cap = 0;
+  for (int b = 0; b < 2; ++b) RSC_CUDA(ctx, cudaMallocHost(&ctx->hstage[b], bytes));
+  ctx->hstage_cap = bytes;
+  return RSC_OK;
+}
+
+// device -> pageable host, `bytes` from d_src: DMA into the page-locked staging, worker threads copy out
+int32_t staged_d2h(rsc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return RSC_OK;
+  if (bytes < ((size_t)8 << 20) || !is_pageable(h_dst)) {
+    RSC_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    RSC_CUDA(ctx, cudaStreamSynchronize(st));
+    return RSC_OK;
+  }
+  const size_t piece = (size_t)32 << 20;
+  if (int32_t rc = ensure_hstage(ctx, std::max(piece, ctx->hstage_cap))) return rc;
+  const int nt = host_copy_threads();
+  const size_t np = (bytes + piece - 1) / piece;
+  for (size_t i = 0; i <= np; ++i) {
+    if (i < np) {  // DMA piece i into buffer i & 1
+      const size_t off = i * piece, len = std::min(piece, bytes - off);
+      RSC_CUDA(ctx, cudaMemcpyAsync(ctx->hstage[i & 1], (const char*)d_src + off, len, cudaMemcpyDeviceToHost, st));
+      RSC_CUDA(ctx, cudaEventRecord(ctx->hstage_free[i & 1], st));
+    }
+    if (i > 0) {  // copy piece i - 1 out while piece i is in flight
+      const size_t off = (i - 1) * piece, len = std::min(piece, bytes - off);
+      RSC_CUDA(ctx, cudaEventSynchronize(ctx->hstage_free[(i - 1) & 1]));
+      par_memcpy((char*)h_dst + off, ctx->hstage[(i - 1) & 1], len, nt);
+    }
+  }
+  return RSC_OK;
+}
+
 // host AoS -> device SoA into the cloud's existing buffers, in chunks on the copy stream:
 // H2D of chunk i+1 overlaps the transposition of chunk i and -- because the call returns as soon as
 // everything is enqueued -- whatever scoring the caller launches next (rsc_score walks the chunks
@@ -188,13 +264,30 @@ static int32_t cloud_upload(rsc_cloud* c, const T* xyz, const T* nrm) {
   RSC_CUDA(ctx, cudaGetLastError());
   const size_t cbytes = (size_t)3 * kChunkPts * sizeof(T);
   for (int b = 0; b < 2; ++b) RSC_CUDA(ctx, ctx->stage[b].ensure(2 * cbytes));
+  // pageable caller arrays of a large cloud: worker threads copy each chunk into page-locked staging and the DMA
+  // engine takes it from there (cudaMemcpy from pageable memory is a single-threaded staged copy, ~10 GB/s)
+  const bool staged = n >= ((int64_t)1 << 20) && !getenv("RSC_NO_STAGED_UPLOAD") && is_pageable(xyz) && is_pageable(nrm);
+  const int nt = staged ? host_copy_threads() : 1;
+  if (staged)
+    if (int32_t rcs = ensure_hstage(ctx, 2 * cbytes)) return rcs;
   for (int i = 0; i < nchunks; ++i) {
     const int64_t off = (int64_t)i * kChunkPts;
     const int64_t cnt = n - off < kChunkPts ? n - off : kChunkPts;
     T* sx = ctx->stage[i & 1].as<T>();
     T* sn = sx + 3 * kChunkPts;
-    RSC_CUDA(ctx, cudaMemcpyAsync(sx, xyz + 3 * off, (size_t)3 * cnt * sizeof(T), cudaMemcpyHostToDevice, cs));
-    RSC_CUDA(ctx, cudaMemcpyAsync(sn, nrm + 3 * off, (size_t)3 * cnt * sizeof(T), cudaMemcpyHostToDevice, cs));
+    if (staged) {
+      const size_t half = (size_t)3 * cnt * sizeof(T);
+      char* hs = static_cast<char*>(ctx->hstage[i & 1]);
+      if (i >= 2) RSC_CUDA(ctx, cudaEventSynchronize(ctx->hstage_free[i & 1]));  // the DMA of chunk i - 2 has left this buffer
+      par_memcpy(hs, xyz + 3 * off, half, nt);
+      par_memcpy(hs + cbytes, nrm + 3 * off, half, nt);
+      RSC_CUDA(ctx, cudaMemcpyAsync(sx, hs, half, cudaMemcpyHostToDevice, cs));
+      RSC_CUDA(ctx, cudaMemcpyAsync(sn, hs + cbytes, half, cudaMemcpyHostToDevice, cs));
+      RSC_CUDA(ctx, cudaEventRecord(ctx->hstage_free[i & 1], cs));
+    } else {
+      RSC_CUDA(ctx, cudaMemcpyAsync(sx, xyz + 3 * off, (size_t)3 * cnt * sizeof(T), cudaMemcpyHostToDevice, cs));
+      RSC_CUDA(ctx, cudaMemcpyAsync(sn, nrm + 3 * off, (size_t)3 * cnt * sizeof(T), cudaMemcpyHostToDevice, cs));
+    }
     // bounds layout: [2i, 2i+1] this chunk, [2*nchunks, 2*nchunks+1] whole cloud
     aos_to_soa_kernel<T><<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(sx, sn, off, cnt, c->n_pad, c->soa,
                                                                         c->d_bounds + 2 * i, c->d_bounds + 2 * nchunks);

@@ -221,6 +221,7 @@ struct rsc_run {
   std::vector<rsc_cand> shapes;
   std::vector<int64_t> off{0};  // off[i]..off[i+1]: list of shape i inside d_idx
   int64_t* d_idx = nullptr;
+  rsc_ctx* ctx = nullptr;  // the context the run was made on (must outlive the run)
   int device = 0;
   int iterations = 0;
   int64_t refined = 0;  // progressive scoring: (candidate, subset) evaluations beyond subset 1

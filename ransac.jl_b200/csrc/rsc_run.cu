@@ -175,6 +175,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   cudaStream_t st = ctx->stream;
   const auto t0 = std::chrono::steady_clock::now();
   rsc_run* run = new rsc_run();
+  run->ctx = ctx;
   // the reference's behaviour (no extension switch): the loop with the bookkeeping on the device (rsc_loop.cu)
   if (!(p->compat_flags & (RSC_SCORE_PROGRESSIVE | RSC_SAMPLER_OCTREE)) && !getenv("RSC_LOOP_HOSTWALK")) {
     const int32_t rcd = ransac_loop_device(cloud, p, seed, run);
@@ -645,6 +646,7 @@ int32_t rsc_run_inpoints(const rsc_run* r, int32_t i, int64_t* out_idx) {
   const int64_t n = r->off[i + 1] - r->off[i];
   if (n == 0) return RSC_OK;
   if (cudaSetDevice(r->device) != cudaSuccess) return RSC_E_CUDA;
+  if (r->ctx) return staged_d2h(r->ctx, out_idx, r->d_idx + r->off[i], (size_t)n * sizeof(int64_t), r->ctx->stream);
   return cudaMemcpy(out_idx, r->d_idx + r->off[i], (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost) == cudaSuccess ? RSC_OK
                                                                                                                         : RSC_E_CUDA;
 }
