@@ -264,9 +264,11 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
   const int64_t sps_word0 = sps.enabled - sub.enabled;
   // small-batch scorer (rsc_small.cu) limits: beyond them the tiled kernel is the faster one
   const bool use_small = getenv("RSC_NO_SMALL") == nullptr;
-  constexpr int kSmallMaxCands = 1024;
-  constexpr double kSmallMaxEvals = 2.0e9;
-  long long rate_seen = -1;  // largest number of new candidates per iteration seen so far (-1: no batch yet)
+  // (measured on c4, profiles/r2h_launches_ransac_c4_summary.json: small kernel ~60 us at ~100 candidates x 312 k
+  // points and linear in the candidates, tiled path ~190 us flat at this size -> cross-over near 1e8 evaluations)
+  constexpr int kSmallMaxCands = 4096;
+  constexpr double kSmallMaxEvals = 1.2e8;
+  long long rate_seen = -1;  // recent number of new candidates per iteration (-1: no batch yet)
   const int Bmax = getenv("RSC_BATCH") ? std::max(1, std::min(kMaxBatch, atoi(getenv("RSC_BATCH")))) : 16;
   const int Bmin = getenv("RSC_BATCH_MIN") ? std::max(1, std::min(Bmax, atoi(getenv("RSC_BATCH_MIN")))) : std::min(8, Bmax);
   int B = 1;
@@ -345,7 +347,8 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
     if (use_small && rate_seen >= 0) {
       const long long want = std::max<long long>(128, 4ll * rate_seen * nb + 64);
       const long long cap = std::min<long long>((want + 127) / 128 * 128, (long long)maxnew * nb);
-      if (cap <= kSmallMaxCands && (double)cap * (double)std::max<int64_t>(sps.n_pad, 1) <= kSmallMaxEvals) cap_new = (int)cap;
+      // the launch is sized for `cap` but its cost follows the ACTUAL number (expected: cap / 4)
+      if (cap <= kSmallMaxCands && (double)(cap / 4) * (double)std::max<int64_t>(sps.n_pad, 1) <= kSmallMaxEvals) cap_new = (int)cap;
     }
     bool scored = false;
     if (cap_new > 0) {
@@ -387,7 +390,7 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
       RUN_CUDA(sync());
       n_new = hio->seg[nb];
     }
-    rate_seen = std::max<long long>(rate_seen, (n_new + nb - 1) / nb);
+    rate_seen = std::max<long long>((n_new + nb - 1) / nb, rate_seen / 2);  // the yield falls as shapes are extracted: follow it
     const auto tk1 = now();
     t_fit += secs(tk0, tk1);
     // ---- classic path: K2 (tiled) on subset 1 + K3 (repeated with a larger guard-band queue if that overflowed) ----

@@ -330,3 +330,31 @@ def test_adversarial_candidates_match_oracle(R):
         np.testing.assert_array_equal(R.unpack_mask(masks[i], pc.size), wmask[i], err_msg=f"candidate {i} kind {oshapes[i].kind}")
     for i in range(0, len(cands), 7):
         np.testing.assert_array_equal(R.refit(cands[i], pc, params).inpoints, np.flatnonzero(wmask[i]))
+
+
+def test_float64_cloud_decides_on_the_float32_roundings():
+    """rsc_cloud_create_f64 rounds the coordinates to float32 on upload (documented in include/rsc.h, README,
+    INTEGRATION.md): masks and counts are the float64 oracle's on the ROUNDED coordinates, bit for bit -- and
+    differ from the oracle on the unrounded ones only for points within float32 resolution of a threshold."""
+    import ransac_jl_b200 as R
+    from ransac_jl_b200 import scenes
+    from tests.helpers import oracle_mask, oracle_params
+
+    sc = scenes.scene_mixed(61, 60_000, noise_frac=0.004, jitter_deg=2.0, outlier_frac=0.2)
+    rng = np.random.default_rng(5)
+    V64 = sc.vertices.astype(np.float64) + rng.uniform(-1e-6, 1e-6, sc.vertices.shape)  # not float32-representable
+    N64 = sc.normals.astype(np.float64) + rng.uniform(-1e-8, 1e-8, sc.normals.shape)
+    pc = R.RANSACCloud(V64, N64, [np.arange(len(V64), dtype=np.int64)])
+    assert pc.vertices.dtype == np.float64
+    params = R.ransacparameters()
+    cands = [p.shape for p in sc.primitives] + scenes.perturbed_candidates(sc, 6, seed=2)
+    counts, masks = R.score_counts(pc, cands, 0, params, want_masks=True)
+    op = oracle_params(params)
+    Vr, Nr = V64.astype(np.float32).astype(np.float64), N64.astype(np.float32).astype(np.float64)
+    differ = 0
+    for i, sh in enumerate(cands):
+        got = R.unpack_mask(masks[i], len(V64))
+        np.testing.assert_array_equal(got, oracle_mask(sh, Vr, Nr, op))
+        differ += int((got != oracle_mask(sh, V64, N64, op)).sum())
+    assert differ <= 20  # a handful of threshold cases at most
+    pc.close()
