@@ -217,33 +217,43 @@ __device__ inline bool full_rank3(const double* A, int c) {
   return s[0] > tol && s[1] > tol && s[2] > tol;
 }
 
+// x = A \ b for a 3 x 3 system: Gaussian elimination with partial pivoting (first maximum wins, one row swap per
+// column -- the same pivot sequence and operation order as oracle.c::solve3), written on scalars with selects so
+// that the rows stay in registers (indexing rows by a run-time pivot put the matrix in local memory)
 __device__ inline bool solve3(const double* A, const double* b, double* x) {
-  double M[3][4];
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) M[i][j] = A[i * 3 + j];
-    M[i][3] = b[i];
-  }
-  for (int col = 0; col < 3; ++col) {
-    int piv = col;
-    for (int r = col + 1; r < 3; ++r)
-      if (fabs(M[r][col]) > fabs(M[piv][col])) piv = r;
-    if (M[piv][col] == 0.0) return false;
-    if (piv != col)
-      for (int j = 0; j < 4; ++j) {
-        const double t = M[col][j];
-        M[col][j] = M[piv][j];
-        M[piv][j] = t;
-      }
-    for (int r = col + 1; r < 3; ++r) {
-      const double fct = M[r][col] / M[col][col];
-      for (int j = col; j < 4; ++j) M[r][j] -= fct * M[col][j];
+  double r0[4] = {A[0], A[1], A[2], b[0]}, r1[4] = {A[3], A[4], A[5], b[1]}, r2[4] = {A[6], A[7], A[8], b[2]};
+  auto swap_rows = [](double* u, double* v, bool doit) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double a = u[j], c = v[j];
+      u[j] = doit ? c : a;
+      v[j] = doit ? a : c;
     }
+  };
+  {  // column 0: pivot = first row with the largest |entry|
+    const bool p1 = fabs(r1[0]) > fabs(r0[0]);
+    const bool p2 = fabs(r2[0]) > fabs(p1 ? r1[0] : r0[0]);
+    swap_rows(r0, r1, p1 && !p2);
+    swap_rows(r0, r2, p2);
+    if (r0[0] == 0.0) return false;
+    const double f1 = r1[0] / r0[0];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r1[j] -= f1 * r0[j];
+    const double f2 = r2[0] / r0[0];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r2[j] -= f2 * r0[j];
   }
-  for (int i = 2; i >= 0; --i) {
-    double s = M[i][3];
-    for (int j = i + 1; j < 3; ++j) s -= M[i][j] * x[j];
-    x[i] = s / M[i][i];
+  {  // column 1
+    swap_rows(r1, r2, fabs(r2[1]) > fabs(r1[1]));
+    if (r1[1] == 0.0) return false;
+    const double f2 = r2[1] / r1[1];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) r2[j] -= f2 * r1[j];
   }
+  if (r2[2] == 0.0) return false;
+  x[2] = r2[3] / r2[2];
+  x[1] = (r1[3] - r1[2] * x[2]) / r1[1];
+  x[0] = ((r0[3] - r0[1] * x[1]) - r0[2] * x[2]) / r0[0];
   return true;
 }
 
