@@ -345,7 +345,8 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
     // decide_kernel says so and the batch is scored again the classic way.)
     int cap_new = -1;
     if (use_small && rate_seen >= 0) {
-      const long long want = std::max<long long>(128, 4ll * rate_seen * nb + 64);
+      long long want = std::max<long long>(128, 4ll * rate_seen * nb + 64);
+      if (const char* e = getenv("RSC_SMALL_CAP")) want = std::max(1, atoi(e));  // test hook: force undersized launches
       const long long cap = std::min<long long>((want + 127) / 128 * 128, (long long)maxnew * nb);
       // the launch is sized for `cap` but its cost follows the ACTUAL number (expected: cap / 4)
       if (cap <= kSmallMaxCands && (double)(cap / 4) * (double)std::max<int64_t>(sps.n_pad, 1) <= kSmallMaxEvals) cap_new = (int)cap;
@@ -367,7 +368,7 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
           store.flags[store.cur].as<uint8_t>() + store_n0);
       RUN_CUDA(cudaGetLastError());
       seg_argmax_kernel<<<nb, 256, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), dev->seg, store_n0,
-                                             dev->seg_keys);
+                                             dev->seg_keys, cap_new);  // never reads past the candidates this launch was sized for
       RUN_CUDA(cudaGetLastError());
       if (store_n0 >= 1) {
         argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0, dev->oldbest);

@@ -176,11 +176,13 @@ static __global__ void seg_bounds_kernel(const int32_t* __restrict__ out_set, co
 
 // per batch iteration: arg-max key (score << 32 | 0x7fffffff - store index; -1 if empty) over its new candidates
 static __global__ void __launch_bounds__(256) seg_argmax_kernel(const int32_t* __restrict__ score, const uint8_t* __restrict__ flags,
-                                                         const int32_t* __restrict__ seg, int store_n0, long long* __restrict__ keys) {
+                                                         const int32_t* __restrict__ seg, int store_n0, long long* __restrict__ keys,
+                                                         int limit = 0x7fffffff /* candidates actually scored (sync-free path) */) {
   __shared__ long long best[8];
   const int j = blockIdx.x;
   long long b = -1;
-  for (int i = seg[j] + threadIdx.x; i < seg[j + 1]; i += blockDim.x) {
+  const int hi = min(seg[j + 1], limit);
+  for (int i = seg[j] + threadIdx.x; i < hi; i += blockDim.x) {
     const int g = store_n0 + i;
     if (flags[g] & 1u) {
       const long long key = ((long long)score[g] << 32) | (long long)(0x7fffffff - g);

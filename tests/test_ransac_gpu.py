@@ -147,3 +147,27 @@ def test_tiny_guard_queue_and_wide_cones_match_oracle(R):
     _compare_runs(R, extracted, want)
     assert len(extracted) >= 3
     np.testing.assert_array_equal(pc.isenabled, oc.isenabled)
+
+
+def test_undersized_sync_free_launch_falls_back_and_matches_oracle(R, monkeypatch):
+    """the sync-free batch path sizes its launch by a prediction of the number of new candidates; with the
+    prediction forced to 128 (RSC_SMALL_CAP) most batches of this scene hold more, decide_kernel reports it and
+    the batch is scored again the classic way -- results must still equal the oracle's loop"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(87, 60_000, noise_frac=0.002, jitter_deg=1.0, outlier_frac=0.05, counts=(3, 1, 1, 1))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4)
+    params = R.ransacparameters(iteration={"tau": 600, "minsubsetN": 2048, "itermax": 40})
+    monkeypatch.setenv("RSC_SMALL_CAP", "128")
+    extracted, _ = R.ransac(pc, params, True, seed=3)
+    monkeypatch.delenv("RSC_SMALL_CAP")
+    plain, _ = R.ransac(pc, params, True, seed=3)
+    assert [len(e.inpoints) for e in extracted] == [len(e.inpoints) for e in plain]
+    from oracle import c_oracle  # the NumPy loop needs minutes for this many candidates
+
+    want, en, _ = c_oracle.ransac(sc.vertices, sc.normals, pc.subsets[0], oracle_params(params), 3)
+    assert len(want) == len(extracted) >= 3
+    for got, w in zip(extracted, want):
+        assert got.shape.to_cand().type == w[0]
+        np.testing.assert_array_equal(got.inpoints, w[3])
+    np.testing.assert_array_equal(pc.isenabled, en)
