@@ -165,10 +165,11 @@ def run(which: str, rank: int, world: int, local: int, dist=None, n_override: in
     if world > 1:
         shard.init_comm(ctx)
 
-    def make_cloud():
+    def make_cloud(v=None, nn=None):
+        v, nn = (V, Nn) if v is None else (v, nn)
         if world > 1:
-            return R.RANSACCloud(V, Nn, sub0, device=local, shard=(lo, n))
-        return R.RANSACCloud(V, Nn, sub0, device=local)
+            return R.RANSACCloud(v, nn, sub0, device=local, shard=(lo, n))
+        return R.RANSACCloud(v, nn, sub0, device=local)
 
     # warm-up: allocations, NCCL channels, kernel loading, GPU clocks (the scene generation left the GPU idle)
     pc = make_cloud()
@@ -193,6 +194,27 @@ def run(which: str, rank: int, world: int, local: int, dist=None, n_override: in
         pc.close()
     res, ex, enabled_local = best
     res = dict(res, seconds_all_runs=all_secs, timing=f"best of {reps} runs (all listed), each from pageable host arrays to the result on the host")
+    # the same call with the caller's arrays in PAGE-LOCKED memory (include/rsc.h: read by DMA, no staging copy on the host)
+    try:
+        tv, tn = torch.from_numpy(V).pin_memory(), torch.from_numpy(Nn).pin_memory()
+        pin = []
+        for rep in range(2):
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            pc = make_cloud(tv.numpy(), tn.numpy())
+            pc.count_enabled()
+            t1 = time.perf_counter()
+            ex_p, _ = R.ransac(pc, params, True, seed=2024)
+            t2 = time.perf_counter()
+            pin.append((allmax(t2 - t0), allmax(t1 - t0)))
+            assert [len(e.inpoints) for e in ex_p] == [len(e.inpoints) for e in ex]
+            pc.close()
+        res["page_locked_host_arrays"] = {"seconds": min(p[0] for p in pin), "upload_seconds": min(p[1] for p in pin),
+                                          "seconds_all_runs": [p[0] for p in pin]}
+        del tv, tn
+    except Exception as e:  # informational
+        res["page_locked_host_arrays"] = {"error": repr(e)}
     for e in ex:
         e.local_idx = e.inpoints - lo
     out = {"scene": which, "points": n, "n_gpus": world, "subsets": r, "iteration": it,
