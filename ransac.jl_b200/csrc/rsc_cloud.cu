@@ -167,7 +167,7 @@ constexpr int64_t kChunkPts = 2 << 20;  // upload granularity (48 MB of float32 
 static int host_copy_threads() {
   if (const char* e = getenv("RSC_COPY_THREADS")) return std::max(1, std::min(32, atoi(e)));
   const unsigned hw = std::thread::hardware_concurrency();
-  return (int)std::max(1u, std::min(4u, hw / 4));
+  return (int)std::max(1u, std::min(8u, hw / 2));  // c5 upload on a 16-thread host: 2 / 4 / 8 / 12 threads -> 0.17 / 0.11 / 0.08 / 0.085 s
 }
 
 static void par_memcpy(void* dst, const void* src, size_t bytes, int nthreads) {
