@@ -71,3 +71,49 @@ def test_two_rank_gloo_count_and_mask_reduction():
         assert p.exitcode == 0
     ok_counts, ok_mask = q.get(timeout=5)
     assert ok_counts and ok_mask
+
+
+def _worker_lists(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ransac_jl_b200 as R
+    from ransac_jl_b200 import shard
+    from tools import ransac_e2e
+
+    n = 50_000
+    rng = np.random.default_rng(9)  # the same "whole" result on every rank
+    shapes = [R.FittedPlane(np.zeros(3), np.array([0.0, 0.0, 1.0])), R.FittedSphere(np.ones(3), 2.0, True)]
+    whole = [np.sort(rng.choice(n, k, replace=False)).astype(np.int64) for k in (7000, 1200)]
+    lo, hi = shard.partition(n, world)[rank]
+    mine = [R.ExtractedShape(s, w[(w >= lo) & (w < hi)]) for s, w in zip(shapes, whole)]
+
+    def allsum(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    dg = ransac_e2e.digest(mine, allsum)                     # additive over the ranks' parts
+    full = ransac_e2e.digest([R.ExtractedShape(s, w) for s, w in zip(shapes, whole)], lambda a: a)
+    joined = shard.gather_extracted(mine)                    # parts concatenated in rank order = the ascending list
+    ok = dg == full and all(np.array_equal(j.inpoints, w) for j, w in zip(joined, whole))
+    if rank == 0:
+        q.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_distributed_inlier_lists_digest_and_gather():
+    """sharded storage leaves every inlier list distributed over the ranks: the digest bench.py compares across
+    GPU counts is additive over the parts, and gather_extracted restores the ascending global lists"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_lists, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=5)
