@@ -171,3 +171,49 @@ def test_undersized_sync_free_launch_falls_back_and_matches_oracle(R, monkeypatc
         assert got.shape.to_cand().type == w[0]
         np.testing.assert_array_equal(got.inpoints, w[3])
     np.testing.assert_array_equal(pc.isenabled, en)
+
+
+@pytest.mark.parametrize("extract_s,terminate_s", [("allcand", "lengthC"), ("lengthC", "allcand"), ("nofminset", "allcand")])
+def test_counter_policies_of_the_decision_kernel_match_oracle(R, extract_s, terminate_s):
+    """chooseS (utilities.jl:297-300): the extraction and termination tests may read any of the three counters
+    (candidates in the store, candidates ever scored, minimal sets drawn); decide_kernel keeps all three per
+    batch iteration -- shapes, inlier lists, isenabled and the iteration count equal the C oracle's loop"""
+    from oracle import c_oracle
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(89, 50_000, noise_frac=0.002, jitter_deg=1.0, outlier_frac=0.1, counts=(2, 1, 1, 1))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4)
+    params = R.ransacparameters(iteration={"tau": 500, "minsubsetN": 256, "itermax": 80, "extract_s": extract_s,
+                                           "terminate_s": terminate_s})
+    extracted, _ = R.ransac(pc, params, True, seed=21)
+    want, en, info = c_oracle.ransac(sc.vertices, sc.normals, pc.subsets[0], oracle_params(params), 21)
+    assert len(extracted) == len(want)
+    for got, w in zip(extracted, want):
+        assert got.shape.to_cand().type == w[0]
+        np.testing.assert_array_equal(got.inpoints, w[3])
+    np.testing.assert_array_equal(pc.isenabled, en)
+    assert pc.last_run_iterations == info["iterations"]
+
+
+def test_drawn_four_points_and_resume_match_oracle(R):
+    """drawN = 4 (the fourth point only validates, like the reference's 4-point known-answer sets) through the
+    generic fit kernel, then ransac(pc, params, false) on what is left -- both against the C oracle's loop"""
+    from oracle import c_oracle
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(90, 40_000, noise_frac=0.001, jitter_deg=0.5, outlier_frac=0.1, counts=(2, 1, 1, 0))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4)
+    params = R.ransacparameters(iteration={"drawN": 4, "tau": 400, "minsubsetN": 512, "itermax": 30})
+    op = oracle_params(params)
+    first, _ = R.ransac(pc, params, True, seed=31)
+    want1, en1, _ = c_oracle.ransac(sc.vertices, sc.normals, pc.subsets[0], op, 31)
+    assert len(first) == len(want1) >= 2
+    for got, w in zip(first, want1):
+        np.testing.assert_array_equal(got.inpoints, w[3])
+    np.testing.assert_array_equal(pc.isenabled, en1)
+    second, _ = R.ransac(pc, params, False, seed=32)  # continues on the remaining points
+    want2, en2, _ = c_oracle.ransac(sc.vertices, sc.normals, pc.subsets[0], op, 32, enabled=en1)
+    assert len(second) == len(want2)
+    for got, w in zip(second, want2):
+        np.testing.assert_array_equal(got.inpoints, w[3])
+    np.testing.assert_array_equal(pc.isenabled, en2)
