@@ -291,6 +291,8 @@ int32_t rsc_comm_unique_id(void* out);
  * all-reduce on the context stream with ncclAllReduce(int32, sum).  Collective. */
 int32_t rsc_ctx_comm_init(rsc_ctx* ctx, const void* unique_id, int32_t rank, int32_t nranks);
 int32_t rsc_ctx_comm_destroy(rsc_ctx* ctx);
+/* all-reduces the library has issued through its own communicator on this context, and their payload */
+int32_t rsc_ctx_comm_stats(rsc_ctx* ctx, int64_t* calls, int64_t* bytes);
 /* sums `count` int32 elements at DEVICE pointer d_buf over the ranks (in place) with the context's
  * communicator or callback, enqueued on `stream` (NULL = the context stream); no synchronisation.  This is
  * what follows rsc_score_dev on a shard: per-candidate counts of the ranks' point ranges -> counts of the cloud. */

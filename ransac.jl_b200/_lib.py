@@ -109,6 +109,7 @@ SIGNATURES = {
     "rsc_comm_unique_id": (C.c_int32, [_P]),
     "rsc_ctx_comm_init": (C.c_int32, [_P, _P, C.c_int32, C.c_int32]),
     "rsc_ctx_comm_destroy": (C.c_int32, [_P]),
+    "rsc_ctx_comm_stats": (C.c_int32, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rsc_ctx_allreduce": (C.c_int32, [_P, _P, C.c_int64, _P]),
     "rsc_run_shape_total": (C.c_int64, [_P, C.c_int32]),
     "rsc_run_syncs": (C.c_int32, [_P, C.POINTER(C.c_int32)]),

@@ -114,6 +114,13 @@ int32_t rsc_ctx_allreduce(rsc_ctx* ctx, int32_t* d_buf, int64_t count, void* str
   return RSC_OK;
 }
 
+int32_t rsc_ctx_comm_stats(rsc_ctx* ctx, int64_t* calls, int64_t* bytes) {
+  if (!ctx) return RSC_E_ARG;
+  if (calls) *calls = ctx->allreduce_calls;
+  if (bytes) *bytes = ctx->allreduce_bytes;
+  return RSC_OK;
+}
+
 int32_t rsc_ctx_comm_destroy(rsc_ctx* ctx) {
   if (!ctx) return RSC_E_ARG;
   if (!ctx->comm) return RSC_OK;

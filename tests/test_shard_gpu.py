@@ -109,3 +109,36 @@ def test_two_ranks_one_gpu_match_c_oracle(which, layout):
     np.testing.assert_array_equal(enabled, en)
     # 2 synchronisations per batch + 1 per extraction (+ set-up)
     assert syncs <= 2 * batches + len(want) + 8
+
+
+def test_library_nccl_communicator_single_rank():
+    """the library's own NCCL path on one GPU: rsc_comm_unique_id + rsc_ctx_comm_init with one rank (libnccl.so.2
+    is dlopen-ed here), then the device loop with a point range -- every count / hit / mask exchange goes through
+    ncclAllReduce on the context stream and the result equals the plain run"""
+    import ctypes as C
+
+    import ransac_jl_b200 as R
+    from ransac_jl_b200 import scenes
+    from ransac_jl_b200._lib import lib
+
+    sc, r, itp, seed = _scene("noisy")
+    params = R.ransacparameters(iteration=itp)
+    ctx = R.Context(0)  # a context of its own: the communicator stays with it
+    pc = R.RANSACCloud(sc.vertices, sc.normals, r, ctx=ctx)
+    plain, _ = R.ransac(pc, params, True, seed=seed)
+    ident = (C.c_uint8 * 128)()
+    ctx.check(lib.rsc_comm_unique_id(ident))
+    ctx.check(lib.rsc_ctx_comm_init(ctx.h, ident, 0, 1))
+    try:
+        ctx.check(lib.rsc_cloud_set_range(pc.handle, 0, pc.size))
+        viacomm, _ = R.ransac(pc, params, True, seed=seed)
+        calls, nbytes = C.c_int64(), C.c_int64()
+        ctx.check(lib.rsc_ctx_comm_stats(ctx.h, C.byref(calls), C.byref(nbytes)))
+    finally:
+        ctx.check(lib.rsc_ctx_comm_destroy(ctx.h))
+    assert calls.value >= 2 * len(plain) and nbytes.value > 0
+    assert len(plain) == len(viacomm) >= 3
+    for a, b in zip(plain, viacomm):
+        assert list(a.shape.to_cand().p) == list(b.shape.to_cand().p)
+        np.testing.assert_array_equal(a.inpoints, b.inpoints)
+    pc.close()
