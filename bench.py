@@ -523,7 +523,7 @@ def time_culled_variant(R, pc, cands, params, reps=3):
             "pairs_total": info["pairs_total"], "pairs_survived": info["pairs_survived"],
             "surviving_fraction": info["pairs_survived"] / max(1, info["pairs_total"]),
             "G_evals_s_reference_equivalent": evals / (min(ms) * 1e-3) / 1e9,
-            "note": "skips (candidate, 512-point Morton tile) pairs that provably hold no compatible point; same counts"}
+            "note": "skips (candidate, 128-point Morton tile) pairs that provably hold no compatible point; same counts"}
 
 
 def time_masks_variant(R, lib, C, torch, sc, cands, params, local, dev, npts=4 << 20):

@@ -188,7 +188,7 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
                   int32_t subset_id, int32_t* counts, uint32_t* masks);
 /* Extension: the same counts as rsc_score(cloud, params, cands, C, -1, counts, NULL) -- whole cloud,
  * counts only -- without evaluating the pairs that cannot match.  Needs rsc_cloud_build_cells (Morton
- * order): every 512-point tile of the Morton-ordered cloud has a bounding sphere (c, r); the distance
+ * order): every 128-point tile of the Morton-ordered cloud has a bounding sphere (c, r); the distance
  * functions of compatibles* are 1-Lipschitz in the point, so |dist(c)| > eps + r proves that no point
  * of the tile is compatible and the (candidate, tile) pair is skipped.  The surviving pairs go through
  * the same FP32 forms, guard band and float64 decisions as rsc_score: the counts are identical.

@@ -366,6 +366,58 @@ __device__ __forceinline__ void eval2x4(const float2* r, const float* px, const 
 #undef RSC_Q
 }
 
+// Packed evaluation of TWO POINTS against one candidate (the transposed mapping of rsc_cull.cu: a lane owns
+// points, the candidate's record is a warp-uniform scalar operand).  Each half performs exactly the scalar
+// sequence of eval<T>() (same roundings, same guard band).  r: the used fields of the record.
+template <int T>
+__device__ __forceinline__ float2 evalp(const float* r, float2 X, float2 Y, float2 Z, float2 NX, float2 NY, float2 NZ,
+                                        float eps, float cosa) {
+  if constexpr (T == RSC_PLANE) {
+    const float2 d = fma2(bc2(r[0]), X, fma2(bc2(r[1]), Y, fma2(bc2(r[2]), Z, bc2(r[3]))));
+    const float2 e = add2(abs2(d), bc2(-eps));
+    const float2 nt = fma2(bc2(r[4]), NX, fma2(bc2(r[5]), NY, fma2(bc2(r[6]), NZ, bc2(cosa))));
+    return max2_nan(e, nt);
+  } else if constexpr (T == RSC_SPHERE) {
+    const float2 vx = fma2(bc2(r[0]), X, bc2(r[1])), vy = fma2(bc2(r[0]), Y, bc2(r[2])), vz = fma2(bc2(r[0]), Z, bc2(r[3]));
+    const float2 vv = fma2(vx, vx, fma2(vy, vy, mul2(vz, vz)));
+    const float2 d = fma2(vv, rsqrt2(vv), bc2(r[4]));
+    const float2 e = add2(abs2(d), bc2(-eps));
+    const float2 s = fma2(vx, NX, fma2(vy, NY, fma2(vz, NZ, bc2(r[5]))));
+    const float2 nt = fma2(bc2(cosa), d, neg2(s));
+    return max2_nan(e, nt);
+  } else {
+    const float2 vx = fma2(bc2(r[0]), X, bc2(r[1])), vy = fma2(bc2(r[0]), Y, bc2(r[2])), vz = fma2(bc2(r[0]), Z, bc2(r[3]));
+    const float2 h = fma2(bc2(r[4]), vx, fma2(bc2(r[5]), vy, mul2(bc2(r[6]), vz)));
+    const float2 wx = fma2(bc2(-r[4]), h, vx), wy = fma2(bc2(-r[5]), h, vy), wz = fma2(bc2(-r[6]), h, vz);
+    const float2 ww = fma2(wx, wx, fma2(wy, wy, mul2(wz, wz)));
+    if constexpr (T == RSC_CYLINDER) {
+      const float2 d = fma2(ww, rsqrt2(ww), bc2(r[7]));
+      const float2 e = add2(abs2(d), bc2(-eps));
+      const float2 wn = fma2(wx, NX, fma2(wy, NY, fma2(wz, NZ, bc2(r[8]))));
+      const float2 nt = fma2(bc2(cosa), d, neg2(wn));
+      return max2_nan(e, nt);
+    } else {
+      const float2 rho = mul2(ww, rsqrt2(ww));
+      const float2 wn = fma2(wx, NX, fma2(wy, NY, mul2(wz, NZ)));
+      const float2 an = fma2(bc2(r[4]), NX, fma2(bc2(r[5]), NY, mul2(bc2(r[6]), NZ)));
+      if constexpr (T == kConeWide) {
+        const float2 d = fma2(neg2(rho), bc2(r[7]), h);
+        const float2 e = add2(abs2(d), bc2(r[8]));
+        const float2 t1 = fma2(bc2(r[0]), an, bc2(r[9]));
+        const float2 cw = mul2(bc2(r[10]), wn);
+        const float2 nt = fma2(rho, t1, neg2(cw));
+        return max2_nan(e, nt);
+      } else {
+        const float2 d = fma2(h, bc2(r[7]), neg2(rho));
+        const float2 e = add2(abs2(d), bc2(r[8]));
+        const float2 t1 = fma2(bc2(r[7]), an, bc2(r[9]));
+        const float2 nt = fma2(rho, t1, neg2(wn));
+        return max2_nan(e, nt);
+      }
+    }
+  }
+}
+
 // runtime-type version for the (rare) slow path; `type` is a COLUMN type (col_type())
 __device__ __forceinline__ float eval_any(int type, const float* r, float px, float py, float pz,
                                           float nx, float ny, float nz, float eps, float cosa) {

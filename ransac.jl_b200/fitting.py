@@ -109,7 +109,7 @@ def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: i
 
 def score_counts_culled(pc: RANSACCloud, candidates: Sequence[FittedShape], params):
     """Extension: the counts of `score_counts(pc, candidates, -1, params)` (whole cloud) without
-    evaluating the (candidate, 512-point Morton tile) pairs that provably hold no compatible point
+    evaluating the (candidate, 128-point Morton tile) pairs that provably hold no compatible point
     (`rsc_score_culled`; needs `pc.build_cells()`).  Returns (counts, info) with info = pairs_total,
     pairs_survived, kernel_ms."""
     Cn = len(candidates)
