@@ -26,52 +26,82 @@
 
 namespace rsc {
 
+int32_t cull_tile_spheres(rsc_ctx* ctx, const PointSet& ps, float4* tiles, cudaStream_t st);
+
 constexpr int kCullThreads = 128;
 constexpr int kCullWarps = kCullThreads / 32;
-constexpr int kCullTile = 128;                   // points of a warp's tile: one bounding sphere each
-constexpr int kCullPts = kCullTile / 32;         // 4 points per lane = 2 packed pairs
-constexpr int kCullChunk = 256;                  // candidates staged in shared memory per step
-constexpr int kCullSQ = 1024;                    // per-CTA staging of queued pairs (one global atomic per flush, not per pair)
+constexpr int kCullTile = 128;                       // points of a warp's tile: one bounding sphere each
+constexpr int kCullGroup = kCullTile * kCullWarps;   // points of a CTA's group of tiles (= kTile): one sphere too
+constexpr int kCullSuper = 2048;                     // most candidates of one work item (capacity of the tiles' survivor lists)
 #ifndef RSC_CULL_MINB
 #define RSC_CULL_MINB 4
 #endif
 constexpr int kCullMinB = RSC_CULL_MINB;  // CTAs per SM the kernel is compiled for (registers: 65536 / (128 kCullMinB))
+static_assert(kCullGroup == kTile, "a group of tiles is one padding unit of the point sets");
 
 struct CullArgs {
-  PointSet ps;          // the points in Morton order (rows of n_pad floats; n_pad a multiple of 512)
-  const float4* tiles;  // bounding sphere of every 128-point tile: centre, radius
-  int ngroups;          // n_pad / 512: a CTA takes the four tiles of a group, one per warp
-  int nranges;          // the candidates are split into nranges runs of chunks_per_range chunks
-  int chunks_per_range;
-  const float* rec;     // [C][kRecFields] compiled records, candidate-major
-  const uint8_t* col;   // [C] column types
+  PointSet ps;           // the points in Morton order (rows of n_pad floats; n_pad a multiple of 512)
+  const float4* tiles;   // bounding sphere of every 128-point tile: centre, radius
+  const float4* groups;  // bounding sphere of every 512-point group of four tiles
+  int ngroups;           // n_pad / 512: a CTA takes the four tiles of a group, one per warp
+  int nranges;           // the candidates are split into nranges runs of cands_per_range (<= kCullSuper, multiple of 128)
+  int cands_per_range;
+  const float* rec;      // [C][kRecFields] compiled records, SORTED by column type
+  const uint8_t* col;    // [C] column types (sorted)
+  const int32_t* orig;   // [C] sorted slot -> index of the candidate
   const rsc_cand* cands;
-  const int32_t* d_C;   // number of candidates on the device (nullptr: C)
+  const int32_t* d_C;    // number of candidates on the device (nullptr: C)
   Thresh th;
   int C;
   int32_t* cv;  // [C] compatible real points
   int32_t* ce;  // [C] compatible enabled points
   unsigned long long* stats;  // [0] surviving (candidate, tile) pairs, [1] pairs decided in FP64
   uint32_t* work;             // dynamic work counter (items handed out)
-  uint2* queue;               // in-band pairs (candidate, position) waiting for their float64 decision
+  uint2* queue;               // (slot, 32-point block) whose margins touch the guard band: decided by cull_fix_kernel
   uint32_t qcap;
-  uint32_t* qn;               // entries appended (may exceed qcap: the excess was decided inline)
-  int inline_fp64;            // != 0: no queue, every in-band pair is decided on the spot (RSC_CULL_INLINE=1)
+  uint32_t* qn;               // entries appended (beyond qcap: decided inline)
+  int inline_fp64;            // != 0: no queue, every in-band block is decided on the spot (RSC_CULL_INLINE=1)
 };
 
-__device__ __forceinline__ int cull_count(const CullArgs& a) { return a.d_C ? min(*a.d_C, a.C) : a.C; }
+__device__ __forceinline__ int cull_count(const CullArgs& a) { return a.d_C ? max(0, min(*a.d_C, a.C)) : a.C; }
+
+// ---- candidate compiler: FP32 records sorted by column type (a warp of the scorer then runs one formula) ----
+__global__ void cull_hist_kernel(const rsc_cand* __restrict__ cands, int C, const int32_t* __restrict__ d_C, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[kColTypes];
+  if (threadIdx.x < kColTypes) h[threadIdx.x] = 0;
+  __syncthreads();
+  const int n = d_C ? max(0, min(*d_C, C)) : C;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(&h[col_type(cands[i])], 1u);
+  __syncthreads();
+  if (threadIdx.x < kColTypes && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
 
 __global__ void cull_compile_kernel(const rsc_cand* __restrict__ cands, int C, const int32_t* __restrict__ d_C, Thresh th, float pmax,
-                                    float nmax, float* __restrict__ rec, uint8_t* __restrict__ col) {
+                                    float nmax, const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor,
+                                    float* __restrict__ rec, uint8_t* __restrict__ col, int32_t* __restrict__ orig) {
+  const int n = d_C ? max(0, min(*d_C, C)) : C;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (d_C ? min(*d_C, C) : C)) return;
+  if (i >= n) return;
   const rsc_cand c = cands[i];
   const int ct = col_type(c);
+  uint32_t base = 0;
+  for (int t = 0; t < ct; ++t) base += hist[t];
+  // one atomic per (warp, type): the lanes of a type take consecutive slots
+  const uint32_t peers = __match_any_sync(__activemask(), ct);
+  const int leader = __ffs(peers) - 1;
+  uint32_t first = 0;
+  if ((int)(threadIdx.x & 31) == leader) first = atomicAdd(&cursor[ct], (uint32_t)__popc(peers));
+  first = __shfl_sync(peers, first, leader);
+  const uint32_t slot = base + first + (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
   float r[kRecFields];
   compile_record(c, ct, th, pmax, nmax, r);
-#pragma unroll
-  for (int f = 0; f < kRecFields; ++f) rec[(size_t)i * kRecFields + f] = r[f];
-  col[i] = (uint8_t)ct;
+  float4* out = reinterpret_cast<float4*>(rec + (size_t)slot * kRecFields);
+  out[0] = make_float4(r[0], r[1], r[2], r[3]);
+  out[1] = make_float4(r[4], r[5], r[6], r[7]);
+  out[2] = make_float4(r[8], r[9], r[10], r[11]);
+  col[slot] = (uint8_t)ct;
+  orig[slot] = i;
 }
 
 __global__ void morton_gather_kernel(const float* __restrict__ soa, int64_t n_pad, const uint32_t* __restrict__ perm, int64_t n,
@@ -84,16 +114,17 @@ __global__ void morton_gather_kernel(const float* __restrict__ soa, int64_t n_pa
   for (int f = 0; f < 6; ++f) msoa[f * n_pad + i] = real ? soa[f * n_pad + j] : 0.f;
 }
 
-// one warp per 128-point tile: centre of the bounding box, radius = largest distance of a point to it (rounded up)
+// one warp per tile of `tile_pts` points: centre of the bounding box, radius = largest distance of a point to it
+// (rounded up)
 __global__ void __launch_bounds__(256) tile_sphere_kernel(const float* __restrict__ X, const float* __restrict__ Y,
-                                                          const float* __restrict__ Z, int64_t n, int ntiles,
+                                                          const float* __restrict__ Z, int64_t n, int tile_pts, int ntiles,
                                                           float4* __restrict__ tiles) {
   const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (tile >= ntiles) return;
-  const int64_t base = (int64_t)tile * kCullTile;
+  const int64_t base = (int64_t)tile * tile_pts;
   float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-  for (int k = lane; k < kCullTile; k += 32) {
+  for (int k = lane; k < tile_pts; k += 32) {
     const int64_t j = base + k;
     if (j < n) {
       const float p[3] = {X[j], Y[j], Z[j]};
@@ -110,7 +141,7 @@ __global__ void __launch_bounds__(256) tile_sphere_kernel(const float* __restric
     }
   const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
   float r2 = 0.f;
-  for (int k = lane; k < kCullTile; k += 32) {
+  for (int k = lane; k < tile_pts; k += 32) {
     const int64_t j = base + k;
     if (j < n) {
       const float dx = X[j] - cx, dy = Y[j] - cy, dz = Z[j] - cz;
@@ -120,11 +151,12 @@ __global__ void __launch_bounds__(256) tile_sphere_kernel(const float* __restric
 #pragma unroll
   for (int s = 16; s; s >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, s));
   if (lane == 0) {
-    // NaN / Inf coordinates: an infinite radius, the tile is never culled; a tile of padding only: culled by everyone
+    // NaN / Inf coordinates: an infinite radius, the tile is never culled; a tile of padding only: radius -1
+    // (whether it is culled or not does not matter: its points are not valid)
     float r = sqrtf(r2) * 1.00001f + 1e-30f;
     if (!(r < 3.0e38f) || !(fabsf(cx) < 3.0e38f) || !(fabsf(cy) < 3.0e38f) || !(fabsf(cz) < 3.0e38f)) r = __int_as_float(0x7f800000);
-    if (base >= n) r = -1.f;
-    tiles[tile] = make_float4(base >= n ? 0.f : cx, base >= n ? 0.f : cy, base >= n ? 0.f : cz, r);
+    const bool empty = base >= n;
+    tiles[tile] = make_float4(empty ? 0.f : cx, empty ? 0.f : cy, empty ? 0.f : cz, empty ? -1.f : r);
   }
 }
 
@@ -161,12 +193,12 @@ __device__ __forceinline__ bool cull_far(int col, const float* r, float4 ts, flo
   return d > lim * 1.0001f + 8.f * band;
 }
 
-// the points of a lane: 4 of its warp's 128-point tile as two packed pairs (points q = 2i, 2i + 1 sit at
-// tile base + 32 q + lane), plus their valid / enabled bits in the order the margins' signs are collected
-struct CullPoints {
-  float2 x[kCullPts / 2], y[kCullPts / 2], z[kCullPts / 2], nx[kCullPts / 2], ny[kCullPts / 2], nz[kCullPts / 2];
-  uint32_t valid, enabled;  // bit (kCullPts - 1 - q): point q of this lane
-};
+__device__ __forceinline__ void load_rec(const float* __restrict__ rec, int slot, float* r) {
+  const float4* g = reinterpret_cast<const float4*>(rec + (size_t)slot * kRecFields);
+  const float4 r0 = g[0], r1 = g[1], r2 = g[2];
+  r[0] = r0.x, r[1] = r0.y, r[2] = r0.z, r[3] = r0.w, r[4] = r1.x, r[5] = r1.y, r[6] = r1.z, r[7] = r1.w;
+  r[8] = r2.x, r[9] = r2.y, r[10] = r2.z, r[11] = r2.w;
+}
 
 // the FP64 decision of one in-band pair; out of line so that its registers (and code) do not weigh on the FP32 loop
 __device__ __noinline__ uint32_t cull_exact(const rsc_cand* __restrict__ cp, const Thresh* th, float px, float py, float pz, float nx,
@@ -182,203 +214,199 @@ __device__ __noinline__ uint32_t cull_exact(const rsc_cand* __restrict__ cp, con
   return ex::compat(c, tr, *th, p, n) ? 1u : 0u;
 }
 
-// float64 decision of one queued pair, added to the counts (the FP32 pass counted nothing for it)
-__device__ __forceinline__ void cull_fix_one(const CullArgs& a, uint2 e) {
-  const uint32_t cand = e.x;
-  const int64_t j = (int64_t)e.y;
-  const uint32_t ok = cull_exact(a.cands + cand, &a.th, a.ps.x[j], a.ps.y[j], a.ps.z[j], a.ps.nx[j], a.ps.ny[j], a.ps.nz[j]);
-  if (ok) {
-    atomicAdd(a.cv + cand, 1);
-    if ((a.ps.enabled[j >> 5] >> (j & 31)) & 1u) atomicAdd(a.ce + cand, 1);
-  }
+// One point of a block whose margins touch the guard band, decided from scratch: FP32 margin where it is
+// sure, the reference's float64 operation order where it is not (or NaN).  Returns 1 for a compatible point.
+__device__ __forceinline__ uint32_t cull_decide(const CullArgs& a, int slot, int ct, const float* r, int64_t j, uint32_t* exact) {
+  const float px = a.ps.x[j], py = a.ps.y[j], pz = a.ps.z[j], nx = a.ps.nx[j], ny = a.ps.ny[j], nz = a.ps.nz[j];
+  const int pt = public_type(ct);
+  const float m = eval_any(ct, r, px, py, pz, nx, ny, nz, a.th.eps[pt], a.th.cosa[pt]);
+  if (fabsf(m) > r[kBandField]) return m < 0.f ? 1u : 0u;
+  ++*exact;
+  return cull_exact(a.cands + a.orig[slot], &a.th, px, py, pz, nx, ny, nz);
 }
 
-// the rare continuation of cull_narrow: some margin of this lane is inside the guard band (or NaN).  Those points
-// leave the sign word and go to the float64 queue (or are decided here when the staging area is full).
-__device__ __noinline__ uint32_t cull_ambiguous(const CullArgs* a, float band, int cand, float m0, float m1, float m2, float m3,
-                                                uint32_t acc, uint32_t valid, uint32_t enabled, uint32_t j0, uint2* sq, uint32_t* sqn,
-                                                int* nexact) {
-  const float m[kCullPts] = {m0, m1, m2, m3};
-#pragma unroll
-  for (int q = 0; q < kCullPts; ++q) {
-    const uint32_t bit = 1u << (kCullPts - 1 - q);
-    if (fabsf(m[q]) > band) continue;  // sure (false for NaN)
-    acc &= ~bit;
-    if (!(valid & bit)) continue;  // padding counts for nothing
-    const uint32_t j = j0 + 32u * q;
-    const uint32_t slot = a->inline_fp64 ? (uint32_t)kCullSQ : atomicAdd(sqn, 1u);
-    if (slot < (uint32_t)kCullSQ) {
-      sq[slot] = make_uint2((uint32_t)cand, j);
-    } else {  // staging full (e.g. a needle cone: every pair is in-band): decide on the spot
-      const uint32_t ok = cull_exact(a->cands + cand, &a->th, a->ps.x[j], a->ps.y[j], a->ps.z[j], a->ps.nx[j], a->ps.ny[j], a->ps.nz[j]);
-      if (ok) acc |= bit;
-      ++*nexact;
-    }
-  }
-  return acc;
+// the same for a whole 32-point block by ONE lane (only when the queue is full or switched off); returns the
+// block's inlier bits in the order of the scorer's sign words (point k of the block in bit 31 - k)
+__device__ __noinline__ uint32_t cull_block_inline(const CullArgs* a, int slot, int ct, int64_t j0, unsigned long long* n_exact) {
+  float r[kRecFields];
+  load_rec(a->rec, slot, r);
+  uint32_t bits = 0, ex_n = 0;
+  for (int k = 0; k < 32; ++k) bits |= cull_decide(*a, slot, ct, r, j0 + k, &ex_n) << (31 - k);
+  *n_exact += ex_n;
+  return bits;
 }
 
-// one surviving (candidate, tile) pair: the warp's 128 points against the record at sr (shared memory, broadcast
-// reads).  Returns this lane's counts: compatible real points | compatible enabled points << 16.
+// A batch of up to 32 surviving (candidate, tile) pairs of one warp: lane = candidate (its record in registers),
+// the tile's 128 points stream through as broadcast shared-memory reads, two points per packed operation.
+// No reduction: every lane counts for its own candidate.  wp: the warp's points, pair i at wp + 12 i as
+// (x, x') (y, y') (z, z') (nx, nx') (ny, ny') (nz, nz').
 template <int T>
-__device__ __forceinline__ uint32_t cull_narrow(const CullArgs& a, const float* __restrict__ sr, int cand, const CullPoints& P,
-                                                uint32_t j0, uint2* sq, uint32_t* sqn, int* nexact) {
-  float r[12];
-  {
-    const float4* s4 = reinterpret_cast<const float4*>(sr);
-    const float4 a0 = s4[0], a1 = s4[1], a2 = s4[2];
-    r[0] = a0.x, r[1] = a0.y, r[2] = a0.z, r[3] = a0.w, r[4] = a1.x, r[5] = a1.y, r[6] = a1.z, r[7] = a1.w;
-    r[8] = a2.x, r[9] = a2.y, r[10] = a2.z, r[11] = a2.w;
-  }
-  const float band = r[kBandField];
+__device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __restrict__ wp, const float* r, int slot, int64_t base,
+                                            const uint32_t* __restrict__ wm, unsigned long long* n_exact) {
   constexpr int PT = public_type(T);
   const float eps = a.th.eps[PT], cosa = a.th.cosa[PT];
-  const float2 m0 = evalp<T>(r, P.x[0], P.y[0], P.z[0], P.nx[0], P.ny[0], P.nz[0], eps, cosa);
-  const float2 m1 = evalp<T>(r, P.x[1], P.y[1], P.z[1], P.nx[1], P.ny[1], P.nz[1], eps, cosa);
-  // the inlier bit is the sign of the margin: funnel-shifted into a word, point 0 ends up in bit 3
-  uint32_t acc = __funnelshift_l(__float_as_uint(m0.x), 0u, 1);
-  acc = __funnelshift_l(__float_as_uint(m0.y), acc, 1);
-  acc = __funnelshift_l(__float_as_uint(m1.x), acc, 1);
-  acc = __funnelshift_l(__float_as_uint(m1.y), acc, 1);
-  const float amin = fmin_nan(fmin_nan(fabsf(m0.x), fabsf(m0.y)), fmin_nan(fabsf(m1.x), fabsf(m1.y)));
-  if (!(amin > band)) acc = cull_ambiguous(&a, band, cand, m0.x, m0.y, m1.x, m1.y, acc, P.valid, P.enabled, j0, sq, sqn, nexact);
-  return (uint32_t)__popc(acc & P.valid) | ((uint32_t)__popc(acc & P.enabled) << 16);
+  const float band = r[kBandField];
+  int cv = 0, ce = 0;
+#pragma unroll 1
+  for (int g = 0; g < kCullTile / 32; ++g) {
+    uint32_t acc = 0;
+    float amin = __int_as_float(0x7f800000);
+    const float4* q = reinterpret_cast<const float4*>(wp + g * 16 * 12);
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const float4 a0 = q[3 * i], a1 = q[3 * i + 1], a2 = q[3 * i + 2];
+      const float2 m = evalp<T>(r, make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w),
+                                make_float2(a2.x, a2.y), make_float2(a2.z, a2.w), eps, cosa);
+      // the inlier bit is the sign of the margin: funnel-shifted into the block's word (point 0 ends up in bit 31)
+      acc = __funnelshift_l(__float_as_uint(m.x), acc, 1);
+      acc = __funnelshift_l(__float_as_uint(m.y), acc, 1);
+      amin = fmin_nan(amin, fmin_nan(fabsf(m.x), fabsf(m.y)));
+    }
+    if (!(amin > band)) {  // some margin of the block is inside the guard band (or NaN): the block is decided apart
+      const uint32_t qs = a.inline_fp64 ? a.qcap : atomicAdd(a.qn, 1u);
+      if (qs < a.qcap) {
+        a.queue[qs] = make_uint2((uint32_t)slot, (uint32_t)((base >> 5) + g));
+        acc = 0;
+      } else {
+        acc = cull_block_inline(&a, slot, T, base + 32 * g, n_exact);
+      }
+    }
+    cv += __popc(acc & wm[g]);  // the block's valid / enabled words in sign-word order (shared memory, broadcast)
+    ce += __popc(acc & wm[4 + g]);
+  }
+  const int o = a.orig[slot];
+  if (cv) atomicAdd(a.cv + o, cv);
+  if (ce) atomicAdd(a.ce + o, ce);
 }
 
 __global__ void __launch_bounds__(kCullThreads, kCullMinB) cull_score_kernel(const __grid_constant__ CullArgs a) {
-  __shared__ __align__(16) float srec[kCullChunk][kRecFields];
-  __shared__ uint8_t scol[kCullChunk];
-  __shared__ uint2 sq[kCullSQ];
-  __shared__ uint32_t sqn, sbase, sitem;
+  __shared__ __align__(16) float wpts[kCullWarps][kCullTile / 2 * 12];  // the four tiles' points as packed pairs
+  __shared__ uint32_t wmask[kCullWarps][2 * (kCullTile / 32)];          // their valid / enabled words in sign-word order
+  __shared__ float4 wsph[kCullWarps];                                   // their bounding spheres
+  __shared__ uint16_t wlist[kCullWarps][kCullSuper];  // per tile: the candidates (relative to the item's first) that pass its sphere
+  __shared__ uint32_t wn[kCullWarps], bnext, sitem;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = cull_count(a);
-  if (tid == 0) sqn = 0;
-  __syncthreads();
-  // append the staged pairs to the global queue (entries beyond its capacity are decided here)
-  auto flush = [&]() {
-    const uint32_t cnt = sqn < (uint32_t)kCullSQ ? sqn : (uint32_t)kCullSQ;
-    if (tid == 0) sbase = atomicAdd(a.qn, cnt);
-    __syncthreads();
-    for (uint32_t i = tid; i < cnt; i += kCullThreads) {
-      const uint32_t g = sbase + i;
-      if (g < a.qcap)
-        a.queue[g] = sq[i];
-      else
-        cull_fix_one(a, sq[i]);
-    }
-    __syncthreads();
-    if (tid == 0) sqn = 0;
-    __syncthreads();
-  };
-  unsigned long long n_surv = 0;
-  int n_exact = 0;
+  unsigned long long n_surv = 0, n_exact = 0;
   const uint32_t nitems = (uint32_t)a.ngroups * (uint32_t)a.nranges;
   for (;;) {
-    __syncthreads();  // everybody is done with sitem / srec of the previous item
-    if (tid == 0) sitem = atomicAdd(a.work, 1u);
+    __syncthreads();  // everybody is done with the previous item's lists and points
+    if (tid == 0) sitem = atomicAdd(a.work, 1u), bnext = 0;
+    if (tid < kCullWarps) wn[tid] = 0;
     __syncthreads();
     const uint32_t item = sitem;
     if (item >= nitems) break;
     const int group = (int)(item % (uint32_t)a.ngroups), range = (int)(item / (uint32_t)a.ngroups);
-    const int tile = group * kCullWarps + warp;
-    const int64_t base = (int64_t)tile * kCullTile;
-    CullPoints P;
+    const int c_lo = range * a.cands_per_range;
+    const int c_hi = min(C, c_lo + a.cands_per_range);
+    if (c_lo >= c_hi) continue;  // uniform
+    // ---- warp w: the 128 points of tile w -> shared memory as packed pairs ----
     {
-      float px[kCullPts], py[kCullPts], pz[kCullPts], qx[kCullPts], qy[kCullPts], qz[kCullPts];
-      P.valid = 0, P.enabled = 0;
+      const int tile = group * kCullWarps + warp;
+      const int64_t base = (int64_t)tile * kCullTile;
+      float* wp = wpts[warp];
 #pragma unroll
-      for (int q = 0; q < kCullPts; ++q) {
-        const int64_t j = base + q * 32 + lane;
-        px[q] = a.ps.x[j], py[q] = a.ps.y[j], pz[q] = a.ps.z[j];
-        qx[q] = a.ps.nx[j], qy[q] = a.ps.ny[j], qz[q] = a.ps.nz[j];
-        const uint32_t bit = 1u << (kCullPts - 1 - q);
-        if (j < a.ps.n) P.valid |= bit;
-        if ((a.ps.enabled[j >> 5] >> lane) & 1u) P.enabled |= bit;
+      for (int g = 0; g < kCullTile / 32; ++g) {
+        const int64_t j = base + g * 32 + lane;
+        const int pp = g * 32 + lane;
+        float* dst = wp + (pp >> 1) * 12 + (pp & 1);
+        dst[0] = a.ps.x[j], dst[2] = a.ps.y[j], dst[4] = a.ps.z[j], dst[6] = a.ps.nx[j], dst[8] = a.ps.ny[j], dst[10] = a.ps.nz[j];
+        const uint32_t v = __ballot_sync(0xffffffffu, j < a.ps.n);
+        if (lane == 0) wmask[warp][g] = __brev(v), wmask[warp][4 + g] = __brev(v & a.ps.enabled[(base >> 5) + g]);
       }
-      P.enabled &= P.valid;
+      if (lane == 0) wsph[warp] = a.tiles[tile];
+    }
+    __syncthreads();
+    // ---- broad phase, a candidate per thread: the group's sphere first, then the four tiles' spheres ----
+    {
+      const float4 gs = a.groups[group];
+      float rn[kRecFields];
+      int ctn = 0;
+      int c = c_lo + tid;
+      if (c < c_hi) load_rec(a.rec, c, rn), ctn = a.col[c];
+      for (int c0 = c_lo; c0 < c_hi; c0 += kCullThreads) {
+        float r[kRecFields];
 #pragma unroll
-      for (int i = 0; i < kCullPts / 2; ++i) {
-        P.x[i] = make_float2(px[2 * i], px[2 * i + 1]), P.y[i] = make_float2(py[2 * i], py[2 * i + 1]);
-        P.z[i] = make_float2(pz[2 * i], pz[2 * i + 1]), P.nx[i] = make_float2(qx[2 * i], qx[2 * i + 1]);
-        P.ny[i] = make_float2(qy[2 * i], qy[2 * i + 1]), P.nz[i] = make_float2(qz[2 * i], qz[2 * i + 1]);
+        for (int f = 0; f < kRecFields; ++f) r[f] = rn[f];
+        const int ct = ctn;
+        const int cn = c + kCullThreads;
+        if (cn < c_hi) load_rec(a.rec, cn, rn), ctn = a.col[cn];  // the next candidate's record is on its way
+        if (c < c_hi) {
+          const float eps = a.th.eps[public_type(ct)];
+          if (!cull_far(ct, r, gs, eps)) {
+#pragma unroll
+            for (int w = 0; w < kCullWarps; ++w)
+              if (!cull_far(ct, r, wsph[w], eps)) wlist[w][atomicAdd(&wn[w], 1u)] = (uint16_t)(c - c_lo);
+          }
+        }
+        c = cn;
       }
     }
-    const float4 ts = a.tiles[tile];
-    const uint32_t j0 = (uint32_t)(base + lane);
-    const int c_lo = range * a.chunks_per_range * kCullChunk;
-    const int c_hi = min(C, c_lo + a.chunks_per_range * kCullChunk);
-    for (int c0 = c_lo; c0 < c_hi; c0 += kCullChunk) {
-      if (c0 != c_lo) __syncthreads();  // the previous chunk's records are no longer read
-      if (sqn > (uint32_t)kCullSQ / 2) flush();  // uniform: every thread reads the same sqn after a barrier
-      // ---- stage the chunk's records (coalesced 16-byte copies) ----
-      const int nc = min(kCullChunk, c_hi - c0);
-      {
-        const float4* g = reinterpret_cast<const float4*>(a.rec + (size_t)c0 * kRecFields);
-        float4* s = reinterpret_cast<float4*>(&srec[0][0]);
-        for (int i = tid; i < nc * (kRecFields / 4); i += kCullThreads) s[i] = g[i];
-        for (int i = tid; i < nc; i += kCullThreads) scol[i] = a.col[c0 + i];
-      }
-      __syncthreads();
-      // ---- per warp: broad phase (a candidate per lane against the tile's sphere), then the survivors ----
-#pragma unroll 1
-      for (int k0 = 0; k0 < nc; k0 += 32) {
-        const int s = k0 + lane;
-        bool keep = false;
-        if (s < nc) {
-          float r[kRecFields];
-          const float4* s4 = reinterpret_cast<const float4*>(srec[s]);
-          const float4 r0 = s4[0], r1 = s4[1], r2 = s4[2];
-          r[0] = r0.x, r[1] = r0.y, r[2] = r0.z, r[3] = r0.w, r[4] = r1.x, r[5] = r1.y, r[6] = r1.z, r[7] = r1.w;
-          r[8] = r2.x, r[9] = r2.y, r[10] = r2.z, r[11] = r2.w;
-          const int ct = scol[s];
-          keep = !cull_far(ct, r, ts, a.th.eps[public_type(ct)]);
-        }
-        uint32_t mm = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) n_surv += __popc(mm);
-        while (mm) {
-          const int b = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const int sv = k0 + b;
-          const int cand = c0 + sv;
-          uint32_t cnt;
-          switch (scol[sv]) {
-            case RSC_PLANE:
-              cnt = cull_narrow<RSC_PLANE>(a, srec[sv], cand, P, j0, sq, &sqn, &n_exact);
-              break;
-            case RSC_SPHERE:
-              cnt = cull_narrow<RSC_SPHERE>(a, srec[sv], cand, P, j0, sq, &sqn, &n_exact);
-              break;
-            case RSC_CYLINDER:
-              cnt = cull_narrow<RSC_CYLINDER>(a, srec[sv], cand, P, j0, sq, &sqn, &n_exact);
-              break;
-            case kConeWide:
-              cnt = cull_narrow<kConeWide>(a, srec[sv], cand, P, j0, sq, &sqn, &n_exact);
-              break;
-            default:
-              cnt = cull_narrow<RSC_CONE>(a, srec[sv], cand, P, j0, sq, &sqn, &n_exact);
-              break;
-          }
-          cnt = __reduce_add_sync(0xffffffffu, cnt);
-          if (lane == 0 && cnt) {
-            if (cnt & 0xffffu) atomicAdd(a.cv + cand, (int)(cnt & 0xffffu));
-            if (cnt >> 16) atomicAdd(a.ce + cand, (int)(cnt >> 16));
-          }
-        }
-      }
+    __syncthreads();
+    // ---- narrow phase: batches of 32 (candidate, tile) pairs, handed out to whichever warp is free ----
+    uint32_t nb[kCullWarps], total = 0;
+#pragma unroll
+    for (int w = 0; w < kCullWarps; ++w) {
+      nb[w] = (wn[w] + 31u) >> 5;
+      total += nb[w];
+      if (warp == w) n_surv += wn[w];
+    }
+    for (;;) {
+      uint32_t b = 0;
+      if (lane == 0) b = atomicAdd(&bnext, 1u);
+      b = __shfl_sync(0xffffffffu, b, 0);
+      if (b >= total) break;
+      int w = 0;
+#pragma unroll
+      for (int t = 0; t < kCullWarps - 1; ++t)
+        if (w == t && b >= nb[t]) b -= nb[t], w = t + 1;
+      const int e = (int)b * 32 + lane;
+      const bool active = e < (int)wn[w];
+      const int slot = c_lo + (int)wlist[w][active ? e : 0];  // idle lanes shadow entry 0 (and add nothing)
+      float r[kRecFields];
+      load_rec(a.rec, slot, r);
+      const int ct = active ? (int)a.col[slot] : -1;
+      const float* wp = wpts[w];
+      const uint32_t* wm = wmask[w];
+      const int64_t base = (int64_t)(group * kCullWarps + w) * kCullTile;
+      // one formula at a time (the candidates are sorted by type: a batch rarely holds more than one)
+      if (__any_sync(0xffffffffu, ct == RSC_PLANE) && ct == RSC_PLANE) cull_narrow<RSC_PLANE>(a, wp, r, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == RSC_SPHERE) && ct == RSC_SPHERE) cull_narrow<RSC_SPHERE>(a, wp, r, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == RSC_CYLINDER) && ct == RSC_CYLINDER) cull_narrow<RSC_CYLINDER>(a, wp, r, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == RSC_CONE) && ct == RSC_CONE) cull_narrow<RSC_CONE>(a, wp, r, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == kConeWide) && ct == kConeWide) cull_narrow<kConeWide>(a, wp, r, slot, base, wm, &n_exact);
+      __syncwarp();
     }
   }
-  __syncthreads();
-  if (sqn) flush();
-  n_exact = __reduce_add_sync(0xffffffffu, n_exact);
-  if (lane == 0 && n_exact) atomicAdd(a.stats + 1, (unsigned long long)n_exact);
   if (lane == 0 && n_surv) atomicAdd(a.stats, n_surv);
+  n_exact = __reduce_add_sync(0xffffffffu, (unsigned)n_exact);
+  if (lane == 0 && n_exact) atomicAdd(a.stats + 1, n_exact);
 }
 
-// float64 decisions of the queued pairs: one thread per pair, all lanes busy
+// the queued 32-point blocks, a warp each: lane = point, decided from scratch
 __global__ void __launch_bounds__(256) cull_fix_kernel(const __grid_constant__ CullArgs a) {
   const uint32_t n = *a.qn < a.qcap ? *a.qn : a.qcap;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) cull_fix_one(a, a.queue[i]);
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(a.stats + 1, (unsigned long long)*a.qn);
+  const int lane = threadIdx.x & 31;
+  const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  uint32_t ex_n = 0;
+  for (uint32_t i = w0; i < n; i += nw) {
+    const uint2 e = a.queue[i];
+    const int slot = (int)e.x;
+    const int64_t j = (int64_t)e.y * 32 + lane;
+    float r[kRecFields];
+    load_rec(a.rec, slot, r);
+    const int ct = a.col[slot];
+    const uint32_t ok = cull_decide(a, slot, ct, r, j, &ex_n);
+    const uint32_t okm = __ballot_sync(0xffffffffu, ok != 0 && j < a.ps.n);
+    if (lane == 0) {
+      const int o = a.orig[slot];
+      const int cv = __popc(okm), ce = __popc(okm & a.ps.enabled[e.y]);
+      if (cv) atomicAdd(a.cv + o, cv);
+      if (ce) atomicAdd(a.ce + o, ce);
+    }
+  }
+  ex_n = __reduce_add_sync(0xffffffffu, ex_n);
+  if (lane == 0 && ex_n) atomicAdd(a.stats + 1, (unsigned long long)ex_n);
 }
 
 __global__ void cull_policy_kernel(const rsc_cand* __restrict__ cands, int C, const int32_t* __restrict__ cv,
@@ -393,9 +421,9 @@ static int32_t cull_prepare(rsc_cloud* cloud, cudaStream_t st) {
   rsc_ctx* ctx = cloud->ctx;
   rsc_cells& c = cloud->cells;
   if (c.msoa) return RSC_OK;
-  const int ntiles = (int)(cloud->n_pad / kCullTile);
+  const int ntiles = (int)(cloud->n_pad / kCullTile), ngroups = (int)(cloud->n_pad / kCullGroup);
   RSC_CUDA(ctx, cudaMalloc(&c.msoa, (size_t)6 * cloud->n_pad * sizeof(float)));
-  cudaError_t e = cudaMalloc(&c.tiles, (size_t)ntiles * sizeof(float4));
+  cudaError_t e = cudaMalloc(&c.tiles, (size_t)(ntiles + ngroups) * sizeof(float4));
   if (e != cudaSuccess) {
     cudaFree(c.msoa);
     c.msoa = nullptr;
@@ -403,66 +431,78 @@ static int32_t cull_prepare(rsc_cloud* cloud, cudaStream_t st) {
   }
   morton_gather_kernel<<<(unsigned)((cloud->n_pad + 255) / 256), 256, 0, st>>>(cloud->soa, cloud->n_pad, c.perm, cloud->n, c.msoa);
   RSC_CUDA(ctx, cudaGetLastError());
-  tile_sphere_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(c.msoa, c.msoa + cloud->n_pad, c.msoa + 2 * cloud->n_pad, cloud->n, ntiles,
-                                                       reinterpret_cast<float4*>(c.tiles));
-  RSC_CUDA(ctx, cudaGetLastError());
-  return RSC_OK;
+  PointSet ps;
+  ps.x = c.msoa, ps.y = c.msoa + cloud->n_pad, ps.z = c.msoa + 2 * cloud->n_pad;
+  ps.n = cloud->n, ps.n_pad = cloud->n_pad;
+  return cull_tile_spheres(ctx, ps, reinterpret_cast<float4*>(c.tiles), st);
 }
 
-// bounding spheres of the 128-point tiles of a point set that already is in a spatially coherent order
+// bounding spheres of a point set that already is in a spatially coherent order: n_pad / 128 tile spheres followed
+// by n_pad / 512 group spheres (`tiles` holds n_pad / 128 + n_pad / 512 entries)
 int32_t cull_tile_spheres(rsc_ctx* ctx, const PointSet& ps, float4* tiles, cudaStream_t st) {
-  const int ntiles = (int)(ps.n_pad / kCullTile);
+  const int ntiles = (int)(ps.n_pad / kCullTile), ngroups = (int)(ps.n_pad / kCullGroup);
   if (ntiles == 0) return RSC_OK;
-  tile_sphere_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(ps.x, ps.y, ps.z, ps.n, ntiles, tiles);
+  tile_sphere_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(ps.x, ps.y, ps.z, ps.n, kCullTile, ntiles, tiles);
+  RSC_CUDA(ctx, cudaGetLastError());
+  tile_sphere_kernel<<<(ngroups + 7) / 8, 256, 0, st>>>(ps.x, ps.y, ps.z, ps.n, kCullGroup, ngroups, tiles + ntiles);
   RSC_CUDA(ctx, cudaGetLastError());
   return RSC_OK;
 }
 
 // Enqueue the culled scoring of up to C_cap candidates on the device (their number may itself live on the
-// device: d_C) against the Morton-ordered point set ps with tile spheres `tiles`.  cv / ce [C_cap] receive the
-// compatible real / enabled points of every candidate.  No synchronisation; d_stats (2 x u64, optional) gets
-// the surviving (candidate, tile) pairs and the pairs decided in float64.
+// device: d_C) against the Morton-ordered point set ps with the spheres of cull_tile_spheres.  cv / ce [C_cap]
+// receive the compatible real / enabled points of every candidate.  No synchronisation; d_stats (2 x u64,
+// optional) gets the surviving (candidate, tile) pairs and the pairs decided in float64.
 int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const float4* tiles, const Thresh& th,
                      const rsc_cand* d_cands, int C_cap, const int32_t* d_C, int32_t* cv, int32_t* ce, unsigned long long* d_stats,
                      cudaStream_t st) {
-  if (C_cap <= 0 || ps.n_pad <= 0) return RSC_OK;
-  // scratch: [rec][col][stats 2 x u64][qn, work][queue]
-  const size_t o_col = (size_t)C_cap * kRecFields * sizeof(float);
+  if (C_cap <= 0) return RSC_OK;
+  RSC_CUDA(ctx, cudaMemsetAsync(cv, 0, (size_t)C_cap * sizeof(int32_t), st));
+  RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C_cap * sizeof(int32_t), st));
+  if (ps.n_pad <= 0) return RSC_OK;
+  if (C_cap >= (1 << 24)) return fail(ctx, RSC_E_ARG, "score_culled: too many candidates");
+  // scratch: [rec][orig][col][stats 2 x u64 | qn, work | hist 5 | cursor 5][queue]
+  const size_t o_orig = (size_t)C_cap * kRecFields * sizeof(float);
+  const size_t o_col = o_orig + (size_t)C_cap * sizeof(int32_t);
   const size_t o_ctr = (o_col + (size_t)C_cap + 15) / 16 * 16;
-  const size_t o_queue = o_ctr + 32;
-  int64_t qcap = (int64_t)((double)C_cap * (double)ps.n / 4096.0);
+  const size_t o_queue = o_ctr + 64;
+  int64_t qcap = (int64_t)((double)C_cap * (double)ps.n / 8192.0);
   qcap = qcap < (1 << 16) ? (1 << 16) : qcap > (8 << 20) ? (8 << 20) : qcap;
   RSC_CUDA(ctx, ctx->cullbuf.ensure(o_queue + (size_t)qcap * sizeof(uint2)));
   char* b = ctx->cullbuf.as<char>();
   float* d_rec = reinterpret_cast<float*>(b);
+  int32_t* d_orig = reinterpret_cast<int32_t*>(b + o_orig);
   uint8_t* d_col = reinterpret_cast<uint8_t*>(b + o_col);
   unsigned long long* ctr = reinterpret_cast<unsigned long long*>(b + o_ctr);
-  RSC_CUDA(ctx, cudaMemsetAsync(ctr, 0, 32, st));
-  RSC_CUDA(ctx, cudaMemsetAsync(cv, 0, (size_t)C_cap * sizeof(int32_t), st));
-  RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C_cap * sizeof(int32_t), st));
-  cull_compile_kernel<<<(C_cap + 127) / 128, 128, 0, st>>>(d_cands, C_cap, d_C, th, cloud->pmax, cloud->nmax, d_rec, d_col);
+  uint32_t* ctr32 = reinterpret_cast<uint32_t*>(ctr + 2);  // qn, work, hist[5], cursor[5]
+  RSC_CUDA(ctx, cudaMemsetAsync(ctr, 0, 64, st));
+  cull_hist_kernel<<<(C_cap + 255) / 256, 256, 0, st>>>(d_cands, C_cap, d_C, ctr32 + 2);
+  RSC_CUDA(ctx, cudaGetLastError());
+  cull_compile_kernel<<<(C_cap + 127) / 128, 128, 0, st>>>(d_cands, C_cap, d_C, th, cloud->pmax, cloud->nmax, ctr32 + 2, ctr32 + 7, d_rec,
+                                                          d_col, d_orig);
   RSC_CUDA(ctx, cudaGetLastError());
   CullArgs a;
   a.ps = ps;
   a.tiles = tiles;
-  a.ngroups = (int)(ps.n_pad / (kCullTile * kCullWarps));
-  const int chunks = (C_cap + kCullChunk - 1) / kCullChunk;
-  // enough work items to balance the persistent grid: split the candidates when the point set is small
+  a.groups = tiles + ps.n_pad / kCullTile;
+  a.ngroups = (int)(ps.n_pad / kCullGroup);
+  // work items = groups x candidate ranges: at most kCullSuper candidates each, fewer when the point set is small
+  // (enough items to balance the persistent grid)
   const int cap = ctx->sm_count * kCullMinB;
-  int nranges = 1;
-  while (nranges < chunks && (int64_t)a.ngroups * nranges < 8ll * cap) nranges *= 2;
-  a.chunks_per_range = (chunks + nranges - 1) / nranges;
-  a.nranges = (chunks + a.chunks_per_range - 1) / a.chunks_per_range;
-  a.rec = d_rec, a.col = d_col, a.cands = d_cands, a.d_C = d_C;
+  int per = kCullSuper;
+  while (per > kCullThreads && (int64_t)a.ngroups * ((C_cap + per - 1) / per) < 8ll * cap) per /= 2;
+  a.cands_per_range = per;
+  a.nranges = (C_cap + per - 1) / per;
+  a.rec = d_rec, a.col = d_col, a.orig = d_orig, a.cands = d_cands, a.d_C = d_C;
   a.th = th;
   a.C = C_cap;
   a.cv = cv, a.ce = ce;
   a.stats = d_stats ? d_stats : ctr;
-  a.qn = reinterpret_cast<uint32_t*>(ctr + 2);
-  a.work = a.qn + 1;
+  a.qn = ctr32;
+  a.work = ctr32 + 1;
   a.queue = reinterpret_cast<uint2*>(b + o_queue);
   a.qcap = (uint32_t)qcap;
-  // in-band pairs: queued for cull_fix_kernel (default) or decided on the spot (RSC_CULL_INLINE=1) -- both
+  // in-band blocks: queued for cull_fix_kernel (default) or decided on the spot (RSC_CULL_INLINE=1) -- both
   // validated against the dense path (tests/test_cull_gpu.py)
   a.inline_fp64 = getenv("RSC_CULL_INLINE") ? atoi(getenv("RSC_CULL_INLINE")) : 0;
   const int64_t items = (int64_t)a.ngroups * a.nranges;
