@@ -57,10 +57,10 @@ struct CullArgs {
   int32_t* ce;  // [C] compatible enabled points
   unsigned long long* stats;  // [0] surviving (candidate, tile) pairs, [1] pairs decided in FP64
   uint32_t* work;             // dynamic work counter (items handed out)
-  uint2* queue;               // (slot, 32-point block) whose margins touch the guard band: decided by cull_fix_kernel
-  uint32_t qcap;
-  uint32_t* qn;               // entries appended (beyond qcap: decided inline)
-  int inline_fp64;            // != 0: no queue, every in-band block is decided on the spot (RSC_CULL_INLINE=1)
+  uint2* pairs;               // (slot, position) of the pairs inside the guard band: decided in float64 by cull_pair_kernel
+  uint32_t pcap;
+  uint32_t* pn;               // entries appended (beyond pcap: decided inline)
+  int inline_fp64;            // != 0: no queue, every in-band pair is decided on the spot (RSC_CULL_INLINE=1)
 };
 
 __device__ __forceinline__ int cull_count(const CullArgs& a) { return a.d_C ? max(0, min(*a.d_C, a.C)) : a.C; }
@@ -214,38 +214,21 @@ __device__ __noinline__ uint32_t cull_exact(const rsc_cand* __restrict__ cp, con
   return ex::compat(c, tr, *th, p, n) ? 1u : 0u;
 }
 
-// One point of a block whose margins touch the guard band, decided from scratch: FP32 margin where it is
-// sure, the reference's float64 operation order where it is not (or NaN).  Returns 1 for a compatible point.
-__device__ __forceinline__ uint32_t cull_decide(const CullArgs& a, int slot, int ct, const float* r, int64_t j, uint32_t* exact) {
-  const float px = a.ps.x[j], py = a.ps.y[j], pz = a.ps.z[j], nx = a.ps.nx[j], ny = a.ps.ny[j], nz = a.ps.nz[j];
-  const int pt = public_type(ct);
-  const float m = eval_any(ct, r, px, py, pz, nx, ny, nz, a.th.eps[pt], a.th.cosa[pt]);
-  if (fabsf(m) > r[kBandField]) return m < 0.f ? 1u : 0u;
-  ++*exact;
-  return cull_exact(a.cands + a.orig[slot], &a.th, px, py, pz, nx, ny, nz);
-}
-
-// the same for a whole 32-point block by ONE lane (only when the queue is full or switched off); returns the
-// block's inlier bits in the order of the scorer's sign words (point k of the block in bit 31 - k)
-__device__ __noinline__ uint32_t cull_block_inline(const CullArgs* a, int slot, int ct, int64_t j0, unsigned long long* n_exact) {
-  float r[kRecFields];
-  load_rec(a->rec, slot, r);
-  uint32_t bits = 0, ex_n = 0;
-  for (int k = 0; k < 32; ++k) bits |= cull_decide(*a, slot, ct, r, j0 + k, &ex_n) << (31 - k);
-  *n_exact += ex_n;
-  return bits;
-}
-
-// A batch of up to 32 surviving (candidate, tile) pairs of one warp: lane = candidate (its record in registers),
-// the tile's 128 points stream through as broadcast shared-memory reads, two points per packed operation.
-// No reduction: every lane counts for its own candidate.  wp: the warp's points, pair i at wp + 12 i as
-// (x, x') (y, y') (z, z') (nx, nx') (ny, ny') (nz, nz').
+// A batch of up to 32 surviving (candidate, tile) pairs: lane = candidate (its record in registers), the tile's 128
+// points stream through as broadcast shared-memory reads, two points per packed operation.  No reduction: every
+// lane counts for its own candidate.  wp: the tile's points, pair i at wp + 12 i as (x, x') (y, y') (z, z')
+// (nx, nx') (ny, ny') (nz, nz').  ALL lanes run the formula of type T (the warp stays converged); `mine` marks the
+// lanes whose candidate really is of that type -- only they count.
+// A 32-point block with a margin inside the guard band (or NaN) is redone by the whole warp on the spot, lane =
+// point, record of the owning lane by shuffles: sure points are counted from the FP32 sign, the in-band pairs go to
+// the float64 pair queue (cull_pair_kernel adds their counts).
 template <int T>
-__device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __restrict__ wp, const float* r, int slot, int64_t base,
-                                            const uint32_t* __restrict__ wm, unsigned long long* n_exact) {
+__device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __restrict__ wp, const float* r, bool mine, int slot,
+                                            int64_t base, const uint32_t* __restrict__ wm, unsigned long long* n_exact) {
   constexpr int PT = public_type(T);
   const float eps = a.th.eps[PT], cosa = a.th.cosa[PT];
   const float band = r[kBandField];
+  const int lane = threadIdx.x & 31;
   int cv = 0, ce = 0;
 #pragma unroll 1
   for (int g = 0; g < kCullTile / 32; ++g) {
@@ -262,21 +245,51 @@ __device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __re
       acc = __funnelshift_l(__float_as_uint(m.y), acc, 1);
       amin = fmin_nan(amin, fmin_nan(fabsf(m.x), fabsf(m.y)));
     }
-    if (!(amin > band)) {  // some margin of the block is inside the guard band (or NaN): the block is decided apart
-      const uint32_t qs = a.inline_fp64 ? a.qcap : atomicAdd(a.qn, 1u);
-      if (qs < a.qcap) {
-        a.queue[qs] = make_uint2((uint32_t)slot, (uint32_t)((base >> 5) + g));
-        acc = 0;
-      } else {
-        acc = cull_block_inline(&a, slot, T, base + 32 * g, n_exact);
+    const uint32_t vmask = wm[g];  // the block's valid / enabled words in sign-word order (shared memory, broadcast)
+    uint32_t ambm = __ballot_sync(0xffffffffu, mine && !(amin > band));
+    while (ambm) {  // (uniform) some lane's block touches the guard band: the warp redoes it, lane = point
+      const int src = __ffs(ambm) - 1;
+      ambm &= ambm - 1;
+      float rr[RecN<T>::n];
+#pragma unroll
+      for (int f = 0; f < RecN<T>::n; ++f) rr[f] = __shfl_sync(0xffffffffu, r[f], src);
+      const float bb = __shfl_sync(0xffffffffu, band, src);
+      const int sslot = __shfl_sync(0xffffffffu, slot, src);
+      const float* pp = wp + ((g * 32 + lane) >> 1) * 12 + (lane & 1);
+      const float px = pp[0], py = pp[2], pz = pp[4], nx = pp[6], ny = pp[8], nz = pp[10];
+      const float m = eval<T>(rr, px, py, pz, nx, ny, nz, eps, cosa);
+      const bool real = (vmask >> (31 - lane)) & 1u;
+      const bool sure = fabsf(m) > bb;  // false for NaN
+      uint32_t ok = (sure && m < 0.f) ? 1u : 0u;
+      const uint32_t unsure = __ballot_sync(0xffffffffu, real && !sure);
+      if (unsure) {
+        uint32_t b0 = a.pcap;
+        if (!a.inline_fp64) {
+          if (lane == 0) b0 = atomicAdd(a.pn, (uint32_t)__popc(unsure));
+          b0 = __shfl_sync(0xffffffffu, b0, 0);
+        }
+        if (real && !sure) {
+          const uint32_t ps = a.inline_fp64 ? a.pcap : b0 + (uint32_t)__popc(unsure & ((1u << lane) - 1u));
+          const int64_t j = base + g * 32 + lane;
+          if (ps < a.pcap) {
+            a.pairs[ps] = make_uint2((uint32_t)sslot, (uint32_t)j);
+          } else {  // queue full or switched off: the reference's float64 decision right here
+            ok = cull_exact(a.cands + a.orig[sslot], &a.th, px, py, pz, nx, ny, nz);
+            ++*n_exact;
+          }
+        }
       }
+      const uint32_t okm = __ballot_sync(0xffffffffu, ok != 0);
+      if (lane == src) acc = __brev(okm);
     }
-    cv += __popc(acc & wm[g]);  // the block's valid / enabled words in sign-word order (shared memory, broadcast)
+    cv += __popc(acc & vmask);
     ce += __popc(acc & wm[4 + g]);
   }
-  const int o = a.orig[slot];
-  if (cv) atomicAdd(a.cv + o, cv);
-  if (ce) atomicAdd(a.ce + o, ce);
+  if (mine) {
+    const int o = a.orig[slot];
+    if (cv) atomicAdd(a.cv + o, cv);
+    if (ce) atomicAdd(a.ce + o, ce);
+  }
 }
 
 __global__ void __launch_bounds__(kCullThreads, kCullMinB) cull_score_kernel(const __grid_constant__ CullArgs a) {
@@ -369,12 +382,12 @@ __global__ void __launch_bounds__(kCullThreads, kCullMinB) cull_score_kernel(con
       const float* wp = wpts[w];
       const uint32_t* wm = wmask[w];
       const int64_t base = (int64_t)(group * kCullWarps + w) * kCullTile;
-      // one formula at a time (the candidates are sorted by type: a batch rarely holds more than one)
-      if (__any_sync(0xffffffffu, ct == RSC_PLANE) && ct == RSC_PLANE) cull_narrow<RSC_PLANE>(a, wp, r, slot, base, wm, &n_exact);
-      if (__any_sync(0xffffffffu, ct == RSC_SPHERE) && ct == RSC_SPHERE) cull_narrow<RSC_SPHERE>(a, wp, r, slot, base, wm, &n_exact);
-      if (__any_sync(0xffffffffu, ct == RSC_CYLINDER) && ct == RSC_CYLINDER) cull_narrow<RSC_CYLINDER>(a, wp, r, slot, base, wm, &n_exact);
-      if (__any_sync(0xffffffffu, ct == RSC_CONE) && ct == RSC_CONE) cull_narrow<RSC_CONE>(a, wp, r, slot, base, wm, &n_exact);
-      if (__any_sync(0xffffffffu, ct == kConeWide) && ct == kConeWide) cull_narrow<kConeWide>(a, wp, r, slot, base, wm, &n_exact);
+      // one formula at a time, all lanes in step (the candidates are sorted by type: a batch rarely holds more than one)
+      if (__any_sync(0xffffffffu, ct == RSC_PLANE)) cull_narrow<RSC_PLANE>(a, wp, r, ct == RSC_PLANE, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == RSC_SPHERE)) cull_narrow<RSC_SPHERE>(a, wp, r, ct == RSC_SPHERE, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == RSC_CYLINDER)) cull_narrow<RSC_CYLINDER>(a, wp, r, ct == RSC_CYLINDER, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == RSC_CONE)) cull_narrow<RSC_CONE>(a, wp, r, ct == RSC_CONE, slot, base, wm, &n_exact);
+      if (__any_sync(0xffffffffu, ct == kConeWide)) cull_narrow<kConeWide>(a, wp, r, ct == kConeWide, slot, base, wm, &n_exact);
       __syncwarp();
     }
   }
@@ -383,30 +396,19 @@ __global__ void __launch_bounds__(kCullThreads, kCullMinB) cull_score_kernel(con
   if (lane == 0 && n_exact) atomicAdd(a.stats + 1, n_exact);
 }
 
-// the queued 32-point blocks, a warp each: lane = point, decided from scratch
-__global__ void __launch_bounds__(256) cull_fix_kernel(const __grid_constant__ CullArgs a) {
-  const uint32_t n = *a.qn < a.qcap ? *a.qn : a.qcap;
-  const int lane = threadIdx.x & 31;
-  const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-  uint32_t ex_n = 0;
-  for (uint32_t i = w0; i < n; i += nw) {
-    const uint2 e = a.queue[i];
-    const int slot = (int)e.x;
-    const int64_t j = (int64_t)e.y * 32 + lane;
-    float r[kRecFields];
-    load_rec(a.rec, slot, r);
-    const int ct = a.col[slot];
-    const uint32_t ok = cull_decide(a, slot, ct, r, j, &ex_n);
-    const uint32_t okm = __ballot_sync(0xffffffffu, ok != 0 && j < a.ps.n);
-    if (lane == 0) {
-      const int o = a.orig[slot];
-      const int cv = __popc(okm), ce = __popc(okm & a.ps.enabled[e.y]);
-      if (cv) atomicAdd(a.cv + o, cv);
-      if (ce) atomicAdd(a.ce + o, ce);
+// float64 decisions of the in-band pairs: one thread per pair, all lanes busy
+__global__ void __launch_bounds__(256) cull_pair_kernel(const __grid_constant__ CullArgs a) {
+  const uint32_t n = *a.pn < a.pcap ? *a.pn : a.pcap;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint2 e = a.pairs[i];
+    const int64_t j = (int64_t)e.y;
+    if (cull_exact(a.cands + a.orig[e.x], &a.th, a.ps.x[j], a.ps.y[j], a.ps.z[j], a.ps.nx[j], a.ps.ny[j], a.ps.nz[j])) {
+      const int o = a.orig[e.x];
+      atomicAdd(a.cv + o, 1);
+      if ((a.ps.enabled[j >> 5] >> (j & 31)) & 1u) atomicAdd(a.ce + o, 1);
     }
   }
-  ex_n = __reduce_add_sync(0xffffffffu, ex_n);
-  if (lane == 0 && ex_n) atomicAdd(a.stats + 1, (unsigned long long)ex_n);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && n) atomicAdd(a.stats + 1, (unsigned long long)n);
 }
 
 __global__ void cull_policy_kernel(const rsc_cand* __restrict__ cands, int C, const int32_t* __restrict__ cv,
@@ -461,11 +463,11 @@ int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, c
   RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C_cap * sizeof(int32_t), st));
   if (ps.n_pad <= 0) return RSC_OK;
   if (C_cap >= (1 << 24)) return fail(ctx, RSC_E_ARG, "score_culled: too many candidates");
-  // scratch: [rec][orig][col][stats 2 x u64 | qn, work | hist 5 | cursor 5][queue]
+  // scratch: [rec][orig][col][stats 2 x u64 | pn, work | hist 5 | cursor 5][pair queue]
   const size_t o_orig = (size_t)C_cap * kRecFields * sizeof(float);
   const size_t o_col = o_orig + (size_t)C_cap * sizeof(int32_t);
   const size_t o_ctr = (o_col + (size_t)C_cap + 15) / 16 * 16;
-  const size_t o_queue = o_ctr + 64;
+  const size_t o_queue = o_ctr + 96;
   int64_t qcap = (int64_t)((double)C_cap * (double)ps.n / 8192.0);
   qcap = qcap < (1 << 16) ? (1 << 16) : qcap > (8 << 20) ? (8 << 20) : qcap;
   RSC_CUDA(ctx, ctx->cullbuf.ensure(o_queue + (size_t)qcap * sizeof(uint2)));
@@ -474,8 +476,8 @@ int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, c
   int32_t* d_orig = reinterpret_cast<int32_t*>(b + o_orig);
   uint8_t* d_col = reinterpret_cast<uint8_t*>(b + o_col);
   unsigned long long* ctr = reinterpret_cast<unsigned long long*>(b + o_ctr);
-  uint32_t* ctr32 = reinterpret_cast<uint32_t*>(ctr + 2);  // qn, work, hist[5], cursor[5]
-  RSC_CUDA(ctx, cudaMemsetAsync(ctr, 0, 64, st));
+  uint32_t* ctr32 = reinterpret_cast<uint32_t*>(ctr + 2);  // pn, work, hist[5], cursor[5]
+  RSC_CUDA(ctx, cudaMemsetAsync(ctr, 0, 96, st));
   cull_hist_kernel<<<(C_cap + 255) / 256, 256, 0, st>>>(d_cands, C_cap, d_C, ctr32 + 2);
   RSC_CUDA(ctx, cudaGetLastError());
   cull_compile_kernel<<<(C_cap + 127) / 128, 128, 0, st>>>(d_cands, C_cap, d_C, th, cloud->pmax, cloud->nmax, ctr32 + 2, ctr32 + 7, d_rec,
@@ -498,18 +500,18 @@ int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, c
   a.C = C_cap;
   a.cv = cv, a.ce = ce;
   a.stats = d_stats ? d_stats : ctr;
-  a.qn = ctr32;
+  a.pn = ctr32;
   a.work = ctr32 + 1;
-  a.queue = reinterpret_cast<uint2*>(b + o_queue);
-  a.qcap = (uint32_t)qcap;
-  // in-band blocks: queued for cull_fix_kernel (default) or decided on the spot (RSC_CULL_INLINE=1) -- both
+  a.pairs = reinterpret_cast<uint2*>(b + o_queue);
+  a.pcap = (uint32_t)qcap;
+  // in-band pairs: queued for cull_pair_kernel (default) or decided on the spot (RSC_CULL_INLINE=1) -- both
   // validated against the dense path (tests/test_cull_gpu.py)
   a.inline_fp64 = getenv("RSC_CULL_INLINE") ? atoi(getenv("RSC_CULL_INLINE")) : 0;
   const int64_t items = (int64_t)a.ngroups * a.nranges;
   const int grid = (int)(items < cap ? items : cap);
   cull_score_kernel<<<grid, kCullThreads, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
-  cull_fix_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a);
+  cull_pair_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
   return RSC_OK;
 }
