@@ -195,6 +195,13 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
  * Optional outs: (candidate, tile) pairs in total / surviving the test, CUDA-event time of the kernel. */
 int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C,
                          int32_t* counts, int64_t* pairs_total, int64_t* pairs_survived, double* kernel_ms);
+/* The same against an uploaded subset (counts == rsc_score(..., subset_id, counts, NULL)).  Needs no
+ * rsc_cloud_build_cells: the first call sorts a copy of the subset into Morton order (kept with the subset, its
+ * isenabled bits follow every change).  rsc_ransac_run uses this path by itself for large candidate batches
+ * (environment RSC_LOOP_CULL = 0 switches that off, 2 forces it for every batch). */
+int32_t rsc_score_culled_subset(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C,
+                                int32_t subset_id, int32_t* counts, int64_t* pairs_total, int64_t* pairs_survived,
+                                double* kernel_ms);
 /* device-pointer variant: d_cands/d_counts live on the context's device; enqueues on `stream`
  * (NULL = the context stream) and returns without synchronising. */
 int32_t rsc_score_dev(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* d_cands, int32_t C,

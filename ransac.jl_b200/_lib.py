@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libransac_b200.so")
+LIB_PATH = os.environ.get("RSC_LIB_PATH") or os.path.join(_HERE, "libransac_b200.so")  # (the override is for kernel-variant experiments)
 
 RSC_PLANE, RSC_SPHERE, RSC_CYLINDER, RSC_CONE = 0, 1, 2, 3
 RSC_NTYPES = 4
@@ -99,6 +99,8 @@ SIGNATURES = {
     "rsc_level_cumsum": (None, [_P, C.c_int32, _P]),
     "rsc_update_levelweight": (None, [_P, _P, C.c_int32]),
     "rsc_refit_extract": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), _P, C.POINTER(C.c_int64), C.c_int32]),
+    "rsc_score_culled_subset": (C.c_int32, [_P, C.POINTER(rsc_params), _P, C.c_int32, C.c_int32, _P, C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "rsc_score_culled": (C.c_int32, [_P, C.POINTER(rsc_params), _P, C.c_int32, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_double)]),
     "rsc_refit_lsq": (C.c_int32, [_P, C.POINTER(rsc_params), C.POINTER(rsc_cand), C.c_double, C.POINTER(rsc_cand),

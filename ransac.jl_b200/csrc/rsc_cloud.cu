@@ -157,6 +157,10 @@ int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st) {
     const int64_t threads = words * 32;
     gather_enabled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cloud->enabled, s.idx, s.m, words, s.enabled);
     RSC_CUDA(ctx, cudaGetLastError());
+    if (s.cen) {  // the Morton view of the culled scorer follows
+      gather_enabled_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(cloud->enabled, s.cidx, s.m, words, s.cen);
+      RSC_CUDA(ctx, cudaGetLastError());
+    }
   }
   return RSC_OK;
 }
@@ -398,6 +402,7 @@ int32_t rsc_cloud_update(rsc_cloud* c, const float* xyz, const float* nrm, int64
   for (size_t i = 0; i < c->subsets.size(); ++i) {  // gathered subset copies follow the new coordinates
     rsc_subset& s = c->subsets[i];
     if (!s.soa) continue;
+    s.release_cull_view();  // new coordinates: the Morton view is rebuilt when it is next needed
     if (s.m > 0) {
       gather_subset_kernel<<<(unsigned)((s.m + 255) / 256), 256, 0, c->ctx->stream>>>(c->soa, c->n_pad, s.idx, s.m, s.m_pad, s.soa);
       RSC_CUDA(c->ctx, cudaGetLastError());
@@ -424,6 +429,7 @@ void rsc_cloud_destroy(rsc_cloud* c) {
     if (s.enabled) cudaFree(s.enabled);
     if (s.valid) cudaFree(s.valid);
     if (s.idx) cudaFree(s.idx);
+    s.release_cull_view();
   }
   if (c->soa) cudaFree(c->soa);
   if (c->g_enabled) cudaFree(c->g_enabled);
@@ -457,6 +463,7 @@ int32_t rsc_cloud_set_subset(rsc_cloud* c, int32_t subset_id, const int64_t* idx
   rsc_subset& s = c->subsets[subset_id];
   if (s.soa) {
     cudaFree(s.soa), cudaFree(s.enabled), cudaFree(s.valid), cudaFree(s.idx);
+    s.release_cull_view();
     s = rsc_subset();
   }
   s.m = m;
@@ -532,9 +539,12 @@ int32_t rsc_cloud_enable_all(rsc_cloud* c) {
     fill_valid_kernel<<<(unsigned)((c->g_words + 255) / 256), 256, 0, ctx->stream>>>(c->g_enabled, nullptr, c->n_global, c->g_words);
     RSC_CUDA(ctx, cudaGetLastError());
   }
-  for (auto& s : c->subsets)
-    if (s.soa)
-      RSC_CUDA(ctx, cudaMemcpyAsync(s.enabled, s.valid, (size_t)(s.m_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  for (auto& s : c->subsets) {
+    if (!s.soa) continue;
+    RSC_CUDA(ctx, cudaMemcpyAsync(s.enabled, s.valid, (size_t)(s.m_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    // (the Morton view of the culled scorer has its real points in front too: the same words)
+    if (s.cen) RSC_CUDA(ctx, cudaMemcpyAsync(s.cen, s.valid, (size_t)(s.m_pad / 32) * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   RSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return RSC_OK;
 }

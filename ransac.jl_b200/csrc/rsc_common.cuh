@@ -120,6 +120,19 @@ struct rsc_subset {
   uint32_t* enabled = nullptr; // m_pad/32 words
   uint32_t* valid = nullptr;
   int64_t* idx = nullptr;      // m local point indices (device)
+  // Morton-ordered view for the culled scorer (rsc_cull.cu), built on first use by subset_cull_view():
+  // the same m points in a spatially coherent order + bounding spheres of their 128 / 512-point tiles
+  float* csoa = nullptr;       // 6 * m_pad floats
+  uint32_t* cen = nullptr;     // m_pad/32 words: pc.isenabled in that order (kept current with `enabled`)
+  int64_t* cidx = nullptr;     // m local point indices in that order
+  void* ctiles = nullptr;      // float4 [m_pad/128 + m_pad/512]
+  void release_cull_view() {
+    if (csoa) cudaFree(csoa);
+    if (cen) cudaFree(cen);
+    if (cidx) cudaFree(cidx);
+    if (ctiles) cudaFree(ctiles);
+    csoa = nullptr, cen = nullptr, cidx = nullptr, ctiles = nullptr;
+  }
 };
 
 // flattened octree of a cloud (rsc_octree.cu): Morton-sorted codes, cells = contiguous code ranges
@@ -236,6 +249,17 @@ int32_t audit_margins(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, 
 int32_t cloud_ready(rsc_cloud* cloud);
 // refresh the gathered enabled bits of every uploaded subset from the cloud's enabled mask
 int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st);
+// culled scorer (rsc_cull.cu) and the Morton view of a subset it runs on (rsc_octree.cu)
+int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st);
+int32_t cull_tile_spheres(rsc_ctx* ctx, const PointSet& ps, float4* tiles, cudaStream_t st);
+int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const float4* tiles, const Thresh& th,
+                     const rsc_cand* d_cands, int C_cap, const int32_t* d_C, int32_t* cv, int32_t* ce, unsigned long long* d_stats,
+                     cudaStream_t st);
+// K2 of the loops for `n_new` new candidates on a subset (or this rank's slice `ps` of it): the culled scorer on
+// the subset's Morton view when the slice is the whole subset and the batch is large enough to pay, else the dense
+// tiled kernel.  *d_ovf (device, optional) receives the dense path's guard-band queue overflow flag (0 when culled).
+int32_t loop_score_new(rsc_ctx* ctx, rsc_cloud* cloud, rsc_subset& sub, const PointSet& ps, bool whole_subset, const Thresh& th,
+                       const rsc_cand* d_cands, int n_new, int32_t* cv, int32_t* ce, int32_t* d_ovf, cudaStream_t st);
 
 // group-major masks of the last score_enqueue(want_masks) -> candidate-major [C][ceil(m/32)] (d_out, or ctx->masks_cm)
 int32_t masks_to_candidate_major(rsc_ctx* ctx, int32_t C, int64_t m, cudaStream_t st, uint32_t* d_out = nullptr);

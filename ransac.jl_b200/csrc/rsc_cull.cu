@@ -36,6 +36,10 @@ constexpr int kCullSuper = 2048;                     // most candidates of one w
 #ifndef RSC_CULL_MINB
 #define RSC_CULL_MINB 4
 #endif
+#ifndef RSC_CULL_UNROLL
+#define RSC_CULL_UNROLL 4  // point pairs in flight per lane in the narrow phase
+#endif
+constexpr int kCullUnroll = RSC_CULL_UNROLL;
 constexpr int kCullMinB = RSC_CULL_MINB;  // CTAs per SM the kernel is compiled for (registers: 65536 / (128 kCullMinB))
 static_assert(kCullGroup == kTile, "a group of tiles is one padding unit of the point sets");
 
@@ -235,7 +239,7 @@ __device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __re
     uint32_t acc = 0;
     float amin = __int_as_float(0x7f800000);
     const float4* q = reinterpret_cast<const float4*>(wp + g * 16 * 12);
-#pragma unroll 4
+#pragma unroll kCullUnroll
     for (int i = 0; i < 16; ++i) {
       const float4 a0 = q[3 * i], a1 = q[3 * i + 1], a2 = q[3 * i + 2];
       const float2 m = evalp<T>(r, make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w),
@@ -516,13 +520,48 @@ int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, c
   return RSC_OK;
 }
 
+// did the dense path's guard-band queues overflow? (same test as rsc_loop.cuh::queue_overflow_kernel)
+__global__ void dense_overflow_kernel(const uint32_t* __restrict__ wl_count, uint32_t cap, int32_t* __restrict__ out) {
+  *out = (wl_count[0] > cap || wl_count[1] > cap) ? 1 : 0;
+}
+
+// K2 of the loops (see rsc_common.cuh).  Cross-over: the dense kernel scores ~1.6e12 pairs/s after ~40 us of fixed
+// cost; the culled one pays ~25 us of fixed cost plus a broad phase per (candidate, 512-point group) -- it wins
+// once a batch holds a few hundred candidates on a subset of a few hundred thousand points.
+int32_t loop_score_new(rsc_ctx* ctx, rsc_cloud* cloud, rsc_subset& sub, const PointSet& ps, bool whole_subset, const Thresh& th,
+                       const rsc_cand* d_cands, int n_new, int32_t* cv, int32_t* ce, int32_t* d_ovf, cudaStream_t st) {
+  static const int mode = getenv("RSC_LOOP_CULL") ? atoi(getenv("RSC_LOOP_CULL")) : 1;  // 0: never, 1: when it pays, 2: always
+  static const double min_evals = getenv("RSC_LOOP_CULL_MIN") ? atof(getenv("RSC_LOOP_CULL_MIN")) : 4e8;
+  const bool cull = mode != 0 && whole_subset && n_new > 0 && sub.m > 0 && (mode == 2 || (double)n_new * (double)sub.m >= min_evals);
+  if (!cull) {
+    if (int32_t rc = score_enqueue(ctx, cloud, ps, th, d_cands, n_new, nullptr, false, st, cv, ce)) return rc;
+    if (d_ovf) {
+      dense_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, d_ovf);
+      RSC_CUDA(ctx, cudaGetLastError());
+    }
+    return RSC_OK;
+  }
+  if (int32_t rc = subset_cull_view(cloud, sub, st)) return rc;
+  PointSet cps;
+  cps.x = sub.csoa, cps.y = sub.csoa + sub.m_pad, cps.z = sub.csoa + 2 * sub.m_pad;
+  cps.nx = sub.csoa + 3 * sub.m_pad, cps.ny = sub.csoa + 4 * sub.m_pad, cps.nz = sub.csoa + 5 * sub.m_pad;
+  cps.enabled = sub.cen, cps.valid = nullptr;
+  cps.n = sub.m, cps.n_pad = sub.m_pad;
+  if (int32_t rc = cull_enqueue(ctx, cloud, cps, reinterpret_cast<const float4*>(sub.ctiles), th, d_cands, n_new, nullptr, cv, ce, nullptr, st))
+    return rc;
+  if (d_ovf) RSC_CUDA(ctx, cudaMemsetAsync(d_ovf, 0, 4, st));  // nothing can overflow: pairs beyond the queue are decided inline
+  ctx->stats.score_launches += 1;
+  ctx->stats.evals += (int64_t)n_new * sub.m;
+  ctx->stats.cands_scored += n_new;
+  return RSC_OK;
+}
+
 }  // namespace rsc
 
 using namespace rsc;
 
-extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int32_t* counts,
-                                    int64_t* pairs_total, int64_t* pairs_survived, double* kernel_ms) {
-  if (!cloud) return RSC_E_ARG;
+static int32_t score_culled_impl(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int32_t subset_id,
+                                 int32_t* counts, int64_t* pairs_total, int64_t* pairs_survived, double* kernel_ms) {
   rsc_ctx* ctx = cloud->ctx;
   if (!params) return fail(ctx, RSC_E_ARG, "score_culled: params is null");
   if (C < 0 || (C > 0 && (!cands || !counts))) return fail(ctx, RSC_E_ARG, "score_culled: null candidates/counts");
@@ -537,10 +576,30 @@ extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, 
   if (C == 0) return RSC_OK;
   RSC_CUDA(ctx, cudaSetDevice(ctx->device));
   if (int32_t rc = cloud_ready(cloud)) return rc;
-  if (cloud->cells.nlevels == 0) return fail(ctx, RSC_E_STATE, "score_culled: needs rsc_cloud_build_cells (Morton order) first");
   cudaStream_t st = ctx->stream;
-  if (int32_t rc = cull_prepare(cloud, st)) return rc;
-  if (int32_t rc = cells_refresh_enabled(cloud, st)) return rc;
+  PointSet ps;
+  const float4* tiles = nullptr;
+  if (subset_id < 0) {
+    if (cloud->cells.nlevels == 0) return fail(ctx, RSC_E_STATE, "score_culled: needs rsc_cloud_build_cells (Morton order) first");
+    if (int32_t rc = cull_prepare(cloud, st)) return rc;
+    if (int32_t rc = cells_refresh_enabled(cloud, st)) return rc;
+    const float* m = cloud->cells.msoa;
+    ps.x = m, ps.y = m + cloud->n_pad, ps.z = m + 2 * cloud->n_pad;
+    ps.nx = m + 3 * cloud->n_pad, ps.ny = m + 4 * cloud->n_pad, ps.nz = m + 5 * cloud->n_pad;
+    ps.enabled = cloud->cells.en_sorted, ps.valid = nullptr;
+    ps.n = cloud->n, ps.n_pad = cloud->n_pad;
+    tiles = reinterpret_cast<const float4*>(cloud->cells.tiles);
+  } else {
+    if ((size_t)subset_id >= cloud->subsets.size() || !cloud->subsets[subset_id].soa)
+      return fail(ctx, RSC_E_ARG, "score_culled: subset has not been uploaded");
+    rsc_subset& sub = cloud->subsets[subset_id];
+    if (int32_t rc = subset_cull_view(cloud, sub, st)) return rc;
+    ps.x = sub.csoa, ps.y = sub.csoa + sub.m_pad, ps.z = sub.csoa + 2 * sub.m_pad;
+    ps.nx = sub.csoa + 3 * sub.m_pad, ps.ny = sub.csoa + 4 * sub.m_pad, ps.nz = sub.csoa + 5 * sub.m_pad;
+    ps.enabled = sub.cen, ps.valid = nullptr;
+    ps.n = sub.m, ps.n_pad = sub.m_pad;
+    tiles = reinterpret_cast<const float4*>(sub.ctiles);
+  }
   const Thresh th = make_thresh(params);
   // scratch: [cands][cv][ce][policy][stats]
   const size_t o_cv = (size_t)C * sizeof(rsc_cand);
@@ -552,16 +611,8 @@ extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, 
   unsigned long long* d_stats = reinterpret_cast<unsigned long long*>(b + o_stats);
   RSC_CUDA(ctx, cudaMemcpyAsync(d_c, cands, (size_t)C * sizeof(rsc_cand), cudaMemcpyHostToDevice, st));
   RSC_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 16, st));
-  PointSet ps;
-  const float* m = cloud->cells.msoa;
-  ps.x = m, ps.y = m + cloud->n_pad, ps.z = m + 2 * cloud->n_pad;
-  ps.nx = m + 3 * cloud->n_pad, ps.ny = m + 4 * cloud->n_pad, ps.nz = m + 5 * cloud->n_pad;
-  ps.enabled = cloud->cells.en_sorted, ps.valid = nullptr;
-  ps.n = cloud->n, ps.n_pad = cloud->n_pad;
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk0, st));
-  if (int32_t rc = cull_enqueue(ctx, cloud, ps, reinterpret_cast<const float4*>(cloud->cells.tiles), th, d_c, C, nullptr, d_cv, d_cv + C,
-                                d_stats, st))
-    return rc;
+  if (int32_t rc = cull_enqueue(ctx, cloud, ps, tiles, th, d_c, C, nullptr, d_cv, d_cv + C, d_stats, st)) return rc;
   RSC_CUDA(ctx, cudaEventRecord(ctx->evk1, st));
   cull_policy_kernel<<<(C + 255) / 256, 256, 0, st>>>(d_c, C, d_cv, d_cv + C, th.honour_enabled, d_cv + 2 * (size_t)C);
   RSC_CUDA(ctx, cudaGetLastError());
@@ -572,10 +623,23 @@ extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, 
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->evk0, ctx->evk1);
   if (kernel_ms) *kernel_ms = ms;
-  if (pairs_total) *pairs_total = (int64_t)C * (cloud->n_pad / kCullTile);
+  if (pairs_total) *pairs_total = (int64_t)C * (ps.n_pad / kCullTile);
   if (pairs_survived) *pairs_survived = (int64_t)hs[0];
-  ctx->stats.evals += (int64_t)C * cloud->n;
+  ctx->stats.evals += (int64_t)C * ps.n;
   ctx->stats.cands_scored += C;
   ctx->stats.exact_pairs += (int64_t)hs[1];
   return RSC_OK;
+}
+
+extern "C" int32_t rsc_score_culled(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int32_t* counts,
+                                    int64_t* pairs_total, int64_t* pairs_survived, double* kernel_ms) {
+  if (!cloud) return RSC_E_ARG;
+  return score_culled_impl(cloud, params, cands, C, -1, counts, pairs_total, pairs_survived, kernel_ms);
+}
+
+extern "C" int32_t rsc_score_culled_subset(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* cands, int32_t C, int32_t subset_id,
+                                           int32_t* counts, int64_t* pairs_total, int64_t* pairs_survived, double* kernel_ms) {
+  if (!cloud) return RSC_E_ARG;
+  if (subset_id < 0) return fail(cloud->ctx, RSC_E_ARG, "score_culled_subset: subset_id must be >= 0");
+  return score_culled_impl(cloud, params, cands, C, subset_id, counts, pairs_total, pairs_survived, kernel_ms);
 }

@@ -403,10 +403,9 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
         RUN_CUDA(cudaMemcpyAsync(dst, fs.out, (size_t)n_new * sizeof(rsc_cand), cudaMemcpyDeviceToDevice, st));
         int32_t* cv = ls.newcnt.as<int32_t>();
         int32_t* ce = cv + n_new;
-        if ((rc = score_enqueue(ctx, cloud, sps, th, dst, n_new, nullptr, false, st, cv, ce))) return rc;
+        // (the culled scorer on the subset's Morton view when the batch is large: same counts)
         // the overflow flag rides behind the counts, so that a sharded run decides to repeat collectively
-        queue_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, cv + 2 * n_new);
-        RUN_CUDA(cudaGetLastError());
+        if ((rc = loop_score_new(ctx, cloud, sub, sps, !ranged, th, dst, n_new, cv, ce, cv + 2 * n_new, st))) return rc;
         if (coll && ctx->allreduce(ctx->allreduce_user, cv, (int64_t)2 * n_new + 1, (void*)st))
           return fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce of the counts failed");
         finish_new_kernel<<<(n_new + 255) / 256, 256, 0, st>>>(dst, n_new, cv, ce, th.honour_enabled,

@@ -159,6 +159,96 @@ void cells_release(rsc_cloud* cloud) {
   c = rsc_cells();
 }
 
+// ---- Morton view of a subset copy for the culled scorer (rsc_cull.cu) ------------------------------------
+__global__ void __launch_bounds__(256) cull_view_gather_kernel(const float* __restrict__ soa, int64_t m_pad, const int64_t* __restrict__ idx,
+                                                               const uint32_t* __restrict__ perm, int64_t m, float* __restrict__ csoa,
+                                                               int64_t* __restrict__ cidx) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= m_pad) return;
+  const bool real = p < m;
+  const int64_t j = real ? (int64_t)perm[p] : 0;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) csoa[f * m_pad + p] = real ? soa[f * m_pad + j] : 0.f;
+  if (real) cidx[p] = idx[j];
+}
+
+// The subset's points sorted by a 30-bit Morton code (10 bits per axis inside the subset's bounding box; only the
+// ORDER matters, for how small the tiles' bounding spheres are -- counts do not depend on it), the cloud indices
+// and pc.isenabled in that order, and the spheres.  Kept with the subset until its coordinates change.
+int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st) {
+  rsc_ctx* ctx = cloud->ctx;
+  if (s.csoa) return RSC_OK;
+  if (s.m >= ((int64_t)1 << 31)) return fail(ctx, RSC_E_ARG, "culled scorer: subset too large");
+  const int64_t m = s.m, words = s.m_pad / 32;
+  const int64_t nsph = s.m_pad / 128 + s.m_pad / 512;
+  uint32_t *codes_in = nullptr, *codes_out = nullptr, *idx_in = nullptr, *perm = nullptr, *mm = nullptr;
+  void* tmp = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(codes_in), cudaFree(codes_out), cudaFree(idx_in), cudaFree(perm), cudaFree(mm), cudaFree(tmp);
+  };
+  auto bail = [&](cudaError_t e, const char* what) {
+    cleanup();
+    s.release_cull_view();
+    return fail_cuda(ctx, e, what);
+  };
+  cudaError_t e;
+#define CV(expr) \
+  if ((e = (expr)) != cudaSuccess) return bail(e, #expr)
+  CV(cudaMalloc(&s.csoa, (size_t)6 * s.m_pad * sizeof(float)));
+  CV(cudaMalloc(&s.cen, (size_t)words * 4));
+  CV(cudaMalloc(&s.cidx, (size_t)(m > 0 ? m : 1) * sizeof(int64_t)));
+  CV(cudaMalloc(&s.ctiles, (size_t)nsph * sizeof(float4)));
+  const size_t mm1 = (size_t)(m > 0 ? m : 1);
+  CV(cudaMalloc(&codes_in, mm1 * 4));
+  CV(cudaMalloc(&codes_out, mm1 * 4));
+  CV(cudaMalloc(&idx_in, mm1 * 4));
+  CV(cudaMalloc(&perm, mm1 * 4));
+  CV(cudaMalloc(&mm, 6 * 4));
+  if (m > 0) {
+    const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CV(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    bbox_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(s.soa, m, s.m_pad, mm);
+    CV(cudaGetLastError());
+    uint32_t got[6];
+    CV(cudaMemcpyAsync(got, mm, sizeof(got), cudaMemcpyDeviceToHost, st));
+    CV(cudaStreamSynchronize(st));
+    Quant q;
+    q.D = 10;
+    q.scale = 1024.0;
+    q.qmax = 1023u;
+    for (int a = 0; a < 3; ++a) {
+      const double lo = (double)ord2f(got[a]), hi = (double)ord2f(got[3 + a]);
+      q.lo[a] = lo;
+      q.w[a] = hi - lo;
+      if (!(q.w[a] > 0.0)) q.w[a] = 1.0;
+    }
+    morton_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(s.soa, m, s.m_pad, q, codes_in, idx_in);
+    CV(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CV(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes_in, codes_out, idx_in, perm, (int)m, 0, 30, st));
+    CV(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    CV(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes_in, codes_out, idx_in, perm, (int)m, 0, 30, st));
+  }
+  cull_view_gather_kernel<<<(unsigned)((s.m_pad + 255) / 256), 256, 0, st>>>(s.soa, s.m_pad, s.idx, perm, m, s.csoa, s.cidx);
+  CV(cudaGetLastError());
+  {
+    PointSet ps;
+    ps.x = s.csoa, ps.y = s.csoa + s.m_pad, ps.z = s.csoa + 2 * s.m_pad;
+    ps.n = m, ps.n_pad = s.m_pad;
+    if (int32_t rc = cull_tile_spheres(ctx, ps, reinterpret_cast<float4*>(s.ctiles), st)) {
+      cleanup();
+      s.release_cull_view();
+      return rc;
+    }
+  }
+  CV(cudaStreamSynchronize(st));
+#undef CV
+  cleanup();
+  // pc.isenabled in the new order
+  if (int32_t rc = refresh_subsets_enabled(cloud, st)) return rc;
+  return RSC_OK;
+}
+
 }  // namespace rsc
 
 using namespace rsc;

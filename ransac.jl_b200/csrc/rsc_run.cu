@@ -369,10 +369,9 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           ps.n_pad = shi - slo;
           ps.n = std::max<int64_t>(0, (sub.m < shi ? sub.m : shi) - slo);
         }
-        if ((rc = score_enqueue(ctx, cloud, ps, th, dst, n_new, nullptr, false, st, cv, ce))) goto done;
+        // (the culled scorer on the subset's Morton view when the batch is large: same counts)
         // overflow flag rides behind the counts, so that a sharded run decides to repeat collectively
-        queue_overflow_kernel<<<1, 1, 0, st>>>(ctx->wl_count.as<uint32_t>(), (uint32_t)ctx->wl_cap, cv + 2 * n_new);
-        RUN_CUDA(cudaGetLastError());
+        if ((rc = loop_score_new(ctx, cloud, sub, ps, !sharded, th, dst, n_new, cv, ce, cv + 2 * n_new, st))) goto done;
         if (sharded && (rc = ctx->allreduce(ctx->allreduce_user, cv, (int64_t)2 * n_new + 1, (void*)st))) {
           rc = fail(ctx, RSC_E_NCCL, "ransac_run: all-reduce callback failed");
           goto done;

@@ -107,11 +107,12 @@ def score_counts(pc: RANSACCloud, candidates: Sequence[FittedShape], subsetID: i
     return counts, masks
 
 
-def score_counts_culled(pc: RANSACCloud, candidates: Sequence[FittedShape], params):
-    """Extension: the counts of `score_counts(pc, candidates, -1, params)` (whole cloud) without
-    evaluating the (candidate, 128-point Morton tile) pairs that provably hold no compatible point
-    (`rsc_score_culled`; needs `pc.build_cells()`).  Returns (counts, info) with info = pairs_total,
-    pairs_survived, kernel_ms."""
+def score_counts_culled(pc: RANSACCloud, candidates: Sequence[FittedShape], params, subsetID: int = -1):
+    """Extension: the counts of `score_counts(pc, candidates, subsetID, params)` without evaluating the
+    (candidate, 128-point Morton tile) pairs that provably hold no compatible point.  subsetID = -1: the whole
+    cloud (`rsc_score_culled`; needs `pc.build_cells()`); subsetID >= 0 (0-based, like score_counts): that subset
+    (`rsc_score_culled_subset`; sorts a copy of the subset on first use).  Returns (counts, info) with info =
+    pairs_total, pairs_survived, kernel_ms."""
     Cn = len(candidates)
     counts = np.zeros(Cn, dtype=np.int32)
     if Cn == 0:
@@ -119,7 +120,11 @@ def score_counts_culled(pc: RANSACCloud, candidates: Sequence[FittedShape], para
     arr = pack_cands(candidates)
     cp = to_c(params)
     tot, sur, ms = C.c_int64(), C.c_int64(), C.c_double()
-    pc.ctx.check(lib.rsc_score_culled(pc.handle, C.byref(cp), arr, Cn, counts.ctypes.data, C.byref(tot), C.byref(sur), C.byref(ms)))
+    if subsetID >= 0:
+        pc.ctx.check(lib.rsc_score_culled_subset(pc.handle, C.byref(cp), arr, Cn, subsetID, counts.ctypes.data, C.byref(tot),
+                                                 C.byref(sur), C.byref(ms)))
+    else:
+        pc.ctx.check(lib.rsc_score_culled(pc.handle, C.byref(cp), arr, Cn, counts.ctypes.data, C.byref(tot), C.byref(sur), C.byref(ms)))
     return counts, {"pairs_total": tot.value, "pairs_survived": sur.value, "kernel_ms": ms.value}
 
 

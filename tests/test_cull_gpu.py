@@ -81,3 +81,59 @@ def test_culled_ragged_sizes_and_thresholds(R):
             dense, _ = R.score_counts(pc, cands, -1, params)
             got, _ = R.score_counts_culled(pc, cands, params)
             np.testing.assert_array_equal(got, dense, err_msg=f"n={n} eps={eps}")
+
+
+def test_culled_subset_counts_on_loop_like_candidates(R):
+    """the path rsc_ransac_run takes for large batches: thousands of fitted candidates of interleaved types (as
+    forcefitshapes! emits them) against a SUBSET copy (no build_cells: the subset is sorted on first use), with
+    disabled points -- counts equal the dense path's; and again after the mask changes"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(87, 60_000, noise_frac=0.002, jitter_deg=1.0, outlier_frac=0.05, counts=(3, 1, 1, 1))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 4)
+    params = R.ransacparameters(iteration={"tau": 600, "minsubsetN": 2048, "itermax": 40})
+    cands, _, _ = R.sample_fit(pc, params, 3, 0, 32768)
+    assert len(cands) > 1500 and len({type(c).__name__ for c in cands}) >= 3
+    for sid in (0, 2):
+        dense, _ = R.score_counts(pc, cands, sid, params)
+        got, info = R.score_counts_culled(pc, cands, params, subsetID=sid)
+        np.testing.assert_array_equal(got, dense, err_msg=f"subset {sid}")
+        assert info["pairs_survived"] < info["pairs_total"]
+    en = np.ones(pc.size, bool)
+    en[np.random.default_rng(5).random(pc.size) < 0.4] = False
+    pc.isenabled = en
+    dense, _ = R.score_counts(pc, cands, 0, params)
+    got, _ = R.score_counts_culled(pc, cands, params, subsetID=0)
+    np.testing.assert_array_equal(got, dense)
+    assert (dense > 0).sum() > 100
+
+
+def test_culled_subset_view_follows_enable_all_and_new_coordinates(R):
+    """the subset's Morton view is a cache: enable_all, isenabled assignments and a coordinate update must all reach it"""
+    from ransac_jl_b200 import scenes
+
+    sc = scenes.scene_mixed(31, 40_000, noise_frac=0.002, jitter_deg=1.0, outlier_frac=0.1, counts=(2, 1, 1, 1))
+    pc = R.RANSACCloud(sc.vertices, sc.normals, 2)
+    params = R.ransacparameters()
+    cands = scenes.perturbed_candidates(sc, 40, seed=5)
+
+    def same():
+        dense, _ = R.score_counts(pc, cands, 0, params)
+        got, _ = R.score_counts_culled(pc, cands, params, subsetID=0)
+        np.testing.assert_array_equal(got, dense)
+        return int(dense.sum())
+
+    full = same()
+    en = np.ones(pc.size, bool)
+    en[::3] = False
+    pc.isenabled = en
+    assert same() < full
+    pc.enable_all()
+    assert same() == full
+    # other points under the same subset indices (rsc_cloud_update re-gathers the subset copies)
+    from ransac_jl_b200._lib import lib
+
+    V = np.ascontiguousarray(sc.vertices[::-1], dtype=np.float32)
+    N = np.ascontiguousarray(sc.normals[::-1], dtype=np.float32)
+    pc.ctx.check(lib.rsc_cloud_update(pc.handle, V.ctypes.data, N.ctypes.data, pc.size))
+    assert same() > 0
