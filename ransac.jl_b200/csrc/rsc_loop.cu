@@ -371,8 +371,7 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
                                              dev->seg_keys, cap_new);  // never reads past the candidates this launch was sized for
       RUN_CUDA(cudaGetLastError());
       if (store_n0 >= 1) {
-        argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0, dev->oldbest);
-        RUN_CUDA(cudaGetLastError());
+        RUN_CUDA(argmax_enqueue(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0, dev->oldbest, ctx->sm_count, st));
       }
       decide_kernel<<<1, kMaxBatch, 0, st>>>(dev, nullptr, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), cap_new);
       RUN_CUDA(cudaGetLastError());
@@ -420,9 +419,8 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
         RUN_CUDA(cudaMemsetAsync(dev->seg_keys, 0xff, sizeof(dev->seg_keys), st));  // -1: no new candidate
       }
       if (store_n0 >= 1) {
-        argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0,
-                                          dev->oldbest);
-        RUN_CUDA(cudaGetLastError());
+        RUN_CUDA(argmax_enqueue(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0,
+                                          dev->oldbest, ctx->sm_count, st));
       }
       decide_kernel<<<1, kMaxBatch, 0, st>>>(dev, d_ovf, store_n0, nb, k, q, store.cands[store.cur].as<rsc_cand>(), -1);
       RUN_CUDA(cudaGetLastError());

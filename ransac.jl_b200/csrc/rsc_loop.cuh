@@ -56,6 +56,53 @@ static __global__ void __launch_bounds__(1024) argmax_kernel(const int32_t* __re
   }
 }
 
+// the same over a large store (cell sampler: millions of candidates) by many CTAs: partial maxima meet in
+// out[0] (as a key, by atomicMax), a one-thread kernel decodes it in place
+static __global__ void __launch_bounds__(256) argmax_part_kernel(const int32_t* __restrict__ score, const uint8_t* __restrict__ flags,
+                                                                  int n, long long* __restrict__ key_out) {
+  __shared__ long long best[8];
+  long long b = -1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (flags[i] & 1u) {
+      const long long key = ((long long)score[i] << 32) | (long long)(0x7fffffff - i);
+      b = key > b ? key : b;
+    }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const long long o = __shfl_xor_sync(0xffffffffu, b, d);
+    b = o > b ? o : b;
+  }
+  if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) b = best[w] > b ? best[w] : b;
+    if (b >= 0) atomicMax(key_out, b);
+  }
+}
+
+static __global__ void argmax_decode_kernel(int64_t* __restrict__ out) {
+  const long long b = (long long)out[0];
+  if (b < 0) {
+    out[0] = -1, out[1] = 0;
+  } else {
+    out[0] = 0x7fffffff - (int)(b & 0xffffffffll);
+    out[1] = (int)(b >> 32);
+  }
+}
+
+static cudaError_t argmax_enqueue(const int32_t* score, const uint8_t* flags, int n, int64_t* out, int sm_count, cudaStream_t st) {
+  if (n <= (1 << 16)) {
+    argmax_kernel<<<1, 1024, 0, st>>>(score, flags, n, out);
+    return cudaGetLastError();
+  }
+  cudaError_t e = cudaMemsetAsync(out, 0xff, 8, st);  // key -1
+  if (e != cudaSuccess) return e;
+  const int grid = std::min(sm_count * 4, (n + 2047) / 2048);
+  argmax_part_kernel<<<grid, 256, 0, st>>>(score, flags, n, reinterpret_cast<long long*>(out));
+  argmax_decode_kernel<<<1, 1, 0, st>>>(out);
+  return cudaGetLastError();
+}
+
 // ---- K5 helpers -----------------------------------------------------------------------------------
 // per word of the subset mask: how many bits were cleared by the extraction
 static __global__ void newly_count_kernel(const uint32_t* __restrict__ old_en, const uint32_t* __restrict__ new_en, int64_t words,
@@ -149,7 +196,7 @@ struct Store {
 // device buffers per run cost 10-25 ms of a 40 ms loop)
 struct LoopScratch {
   Store store;
-  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf, prog;
+  DevBuf newcnt, hostio, olden, nscratch, nvalid, nmeta, lvbuf, prog, ntiles;
 };
 
 }  // namespace rsc

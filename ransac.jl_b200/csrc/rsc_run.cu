@@ -112,7 +112,7 @@ void loop_scratch_free(rsc_ctx* ctx) {
   if (!ls) return;
   ls->store.release();
   ls->newcnt.release(), ls->hostio.release(), ls->olden.release(), ls->nscratch.release(), ls->nvalid.release(), ls->nmeta.release();
-  ls->lvbuf.release(), ls->prog.release();
+  ls->lvbuf.release(), ls->prog.release(), ls->ntiles.release();
   delete ls;
   ctx->loop_scratch = nullptr;
 }
@@ -214,7 +214,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
     shi = cloud->range_hi >= cloud->n_pad ? sub.m_pad : (int64_t)((double)cloud->range_hi / cloud->n_pad * sub.m_pad) / kTile * kTile;
   }
   DevBuf &newcnt = ls.newcnt, &hostio = ls.hostio, &olden = ls.olden, &nscratch = ls.nscratch, &nvalid = ls.nvalid, &nmeta = ls.nmeta,
-         &lvbuf = ls.lvbuf;
+         &lvbuf = ls.lvbuf, &ntiles = ls.ntiles;
+  static const int k5_cull_mode = getenv("RSC_LOOP_CULL") ? atoi(getenv("RSC_LOOP_CULL")) : 1;
   const bool prog = (p->compat_flags & RSC_SCORE_PROGRESSIVE) != 0;
   const int nsub = (int)cloud->subsets.size();
   ProgMirror mirror;
@@ -391,9 +392,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
         store.n += n_new;
       }
       if (store_n0 >= 1) {  // best of the candidates stored before this batch
-        argmax_kernel<<<1, 1024, 0, st>>>(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0,
-                                          hostio.as<int64_t>());
-        RUN_CUDA(cudaGetLastError());
+        RUN_CUDA(argmax_enqueue(store.score[store.cur].as<int32_t>(), store.flags[store.cur].as<uint8_t>(), store_n0,
+                                          hostio.as<int64_t>(), ctx->sm_count, st));
         RUN_CUDA(cudaMemcpyAsync(best, hostio.p, 16, cudaMemcpyDeviceToHost, st));
       }
       if (n_new > 0) {  // and of every iteration's new candidates
@@ -489,10 +489,15 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           RUN_CUDA(cudaMemcpyAsync(&total, ctx->misc2.p, 8, cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaStreamSynchronize(st));
           t_exb += secs(tka, now());
-          // keep the subset's enabled words of before the extraction
+          // keep the subset's enabled words of before the extraction.  When the subset has a Morton view (the culled
+          // scorer ran on it) K5 works on the view: the newly disabled points then come out spatially sorted and the
+          // store can be re-scored against them by the culled scorer too (the SET of points is the same)
           const int64_t swords = sub.m_pad / 32;
+          const bool k5_view = sub.cen != nullptr && !sharded;
+          const uint32_t* sub_en = k5_view ? sub.cen : sub.enabled;
+          const float* sub_soa = k5_view ? sub.csoa : sub.soa;
           RUN_CUDA(olden.ensure((size_t)swords * 4));
-          RUN_CUDA(cudaMemcpyAsync(olden.p, sub.enabled, (size_t)swords * 4, cudaMemcpyDeviceToDevice, st));
+          RUN_CUDA(cudaMemcpyAsync(olden.p, sub_en, (size_t)swords * 4, cudaMemcpyDeviceToDevice, st));
           int64_t* d_out = run->d_idx + run->off.back();
           if ((rc = refit_write_enqueue(cloud, total ? d_out : nullptr, true, st))) goto done;
           run->shapes.push_back(shape);
@@ -513,7 +518,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           unsigned long long* wtot = woff + swords;
           uint32_t* keep = (uint32_t*)(nmeta.as<char>() + o_keep);
           unsigned long long* koff = (unsigned long long*)(nmeta.as<char>() + o_koff);
-          newly_count_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(olden.as<uint32_t>(), sub.enabled, swords, wcnt);
+          newly_count_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(olden.as<uint32_t>(), sub_en, swords, wcnt);
           RUN_CUDA(cudaGetLastError());
           if ((rc = scan_u32(ctx, wcnt, (int)swords, woff, wtot, st))) goto done;
           unsigned long long nnew_dis = 0;
@@ -523,6 +528,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
           RUN_CUDA(ctx->counts.ensure((size_t)3 * nst * 4));
           hit = ctx->counts.as<int32_t>() + 2 * (size_t)nst;
           unsigned long long kept = 0;
+          bool k5_culled = false;
           int nxt = store.cur ^ 1;
           for (int attempt = 0;; ++attempt) {  // repeated if the guard-band queue overflowed
           if (nnew_dis > 0) {
@@ -530,8 +536,8 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
             RUN_CUDA(nscratch.ensure((size_t)6 * sp * 4));
             RUN_CUDA(nvalid.ensure((size_t)(sp / 32) * 4));
             RUN_CUDA(cudaMemsetAsync(nscratch.p, 0, (size_t)6 * sp * 4, st));
-            newly_gather_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(olden.as<uint32_t>(), sub.enabled, swords, woff,
-                                                                                   sub.soa, sub.m_pad, nscratch.as<float>(), sp);
+            newly_gather_kernel<<<(unsigned)((swords + 255) / 256), 256, 0, st>>>(olden.as<uint32_t>(), sub_en, swords, woff, sub_soa,
+                                                                                   sub.m_pad, nscratch.as<float>(), sp);
             RUN_CUDA(cudaGetLastError());
             fill_valid_words_kernel<<<(unsigned)((sp / 32 + 255) / 256), 256, 0, st>>>(nvalid.as<uint32_t>(), (int64_t)nnew_dis, sp / 32);
             RUN_CUDA(cudaGetLastError());
@@ -544,9 +550,19 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
             ps.n_pad = sp;
             // replicated on every rank (the scratch set is tiny): no all-reduce needed
             // enabled == valid on the scratch set: the enabled-gated count (kept for every type) is the hit count
-            if ((rc = score_enqueue(ctx, cloud, ps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st,
-                                    ctx->counts.as<int32_t>(), hit)))
+            // a large store (cell sampler): most stored candidates are nowhere near the extracted shape -- and the dense
+            // path's candidate compiler is ONE CTA (3 ms for a store of a million candidates)
+            k5_culled = k5_view && k5_cull_mode != 0 && (k5_cull_mode == 2 || nst >= 4096 || (double)nst * (double)nnew_dis >= 2e8);
+            if (k5_culled) {
+              RUN_CUDA(ntiles.ensure((size_t)(sp / 128 + sp / 512) * sizeof(float4)));
+              if ((rc = cull_tile_spheres(ctx, ps, ntiles.as<float4>(), st))) goto done;
+              if ((rc = cull_enqueue(ctx, cloud, ps, ntiles.as<float4>(), th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr,
+                                     ctx->counts.as<int32_t>(), hit, nullptr, st)))
+                goto done;
+            } else if ((rc = score_enqueue(ctx, cloud, ps, th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr, false, st,
+                                           ctx->counts.as<int32_t>(), hit))) {
               goto done;
+            }
           } else {
             RUN_CUDA(cudaMemsetAsync(hit, 0, (size_t)nst * 4, st));
           }
@@ -560,7 +576,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
               keep, koff, nst, store.cands[nxt].as<rsc_cand>(), store.score[nxt].as<int32_t>(), store.flags[nxt].as<uint8_t>());
           RUN_CUDA(cudaGetLastError());
           uint32_t wln[2] = {0, 0};
-          if (nnew_dis > 0) RUN_CUDA(cudaMemcpyAsync(wln, ctx->wl_count.p, 8, cudaMemcpyDeviceToHost, st));
+          if (nnew_dis > 0 && !k5_culled) RUN_CUDA(cudaMemcpyAsync(wln, ctx->wl_count.p, 8, cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaMemcpyAsync(&kept, ktot, 8, cudaMemcpyDeviceToHost, st));
           RUN_CUDA(cudaStreamSynchronize(st));
           if (wln[0] <= ctx->wl_cap && wln[1] <= ctx->wl_cap) break;
