@@ -530,8 +530,9 @@ __global__ void dense_overflow_kernel(const uint32_t* __restrict__ wl_count, uin
 // once a batch holds a few hundred candidates on a subset of a few hundred thousand points.
 int32_t loop_score_new(rsc_ctx* ctx, rsc_cloud* cloud, rsc_subset& sub, const PointSet& ps, bool whole_subset, const Thresh& th,
                        const rsc_cand* d_cands, int n_new, int32_t* cv, int32_t* ce, int32_t* d_ovf, cudaStream_t st) {
-  static const int mode = getenv("RSC_LOOP_CULL") ? atoi(getenv("RSC_LOOP_CULL")) : 1;  // 0: never, 1: when it pays, 2: always
-  static const double min_evals = getenv("RSC_LOOP_CULL_MIN") ? atof(getenv("RSC_LOOP_CULL_MIN")) : 4e8;
+  // (read per call: tests switch it between runs)
+  const int mode = getenv("RSC_LOOP_CULL") ? atoi(getenv("RSC_LOOP_CULL")) : 1;  // 0: never, 1: when it pays, 2: always
+  const double min_evals = getenv("RSC_LOOP_CULL_MIN") ? atof(getenv("RSC_LOOP_CULL_MIN")) : 4e8;
   const bool cull = mode != 0 && whole_subset && n_new > 0 && sub.m > 0 && (mode == 2 || (double)n_new * (double)sub.m >= min_evals);
   if (!cull) {
     if (int32_t rc = score_enqueue(ctx, cloud, ps, th, d_cands, n_new, nullptr, false, st, cv, ce)) return rc;

@@ -215,7 +215,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
   }
   DevBuf &newcnt = ls.newcnt, &hostio = ls.hostio, &olden = ls.olden, &nscratch = ls.nscratch, &nvalid = ls.nvalid, &nmeta = ls.nmeta,
          &lvbuf = ls.lvbuf, &ntiles = ls.ntiles;
-  static const int k5_cull_mode = getenv("RSC_LOOP_CULL") ? atoi(getenv("RSC_LOOP_CULL")) : 1;
+  const int k5_cull_mode = getenv("RSC_LOOP_CULL") ? atoi(getenv("RSC_LOOP_CULL")) : 1;
   const bool prog = (p->compat_flags & RSC_SCORE_PROGRESSIVE) != 0;
   const int nsub = (int)cloud->subsets.size();
   ProgMirror mirror;

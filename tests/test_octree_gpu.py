@@ -82,7 +82,11 @@ def test_cell_sampler_matches_oracle(R):
     assert [(int(a), sh.to_cand().type) for a, sh in zip(sets, shapes)] == want
 
 
-def test_loop_with_cell_sampler_matches_oracle(R):
+@pytest.mark.parametrize("loop_cull", ["0", "2"], ids=["dense", "culled-scorer-in-K2-and-K5"])
+def test_loop_with_cell_sampler_matches_oracle(R, monkeypatch, loop_cull):
+    """both ways of scoring inside the loop: the dense kernels, and the culled scorer on the subset's Morton view for
+    every batch of new candidates (K2) and for the re-scoring of the store after an extraction (K5)"""
+    monkeypatch.setenv("RSC_LOOP_CULL", loop_cull)
     sc = _scene(60_000, seed=92)
     pc = R.RANSACCloud(sc.vertices, sc.normals, 4).build_cells(8)
     params = R.ransacparameters(iteration={"tau": 500, "minsubsetN": 128, "itermax": 50})

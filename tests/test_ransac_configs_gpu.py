@@ -30,10 +30,14 @@ def _check(R, sc, r, it, seed):
     return extracted, info
 
 
-def test_c2_full_loop_matches_c_oracle():
+@pytest.mark.parametrize("loop_cull", ["1", "2"], ids=["default", "culled-scorer-for-every-batch"])
+def test_c2_full_loop_matches_c_oracle(monkeypatch, loop_cull):
+    """RSC_LOOP_CULL=2: every batch of new candidates is scored by the culled scorer on the subset's Morton view
+    (by default only batches of >= 4e8 pairs are) -- same shapes, same lists"""
     import ransac_jl_b200 as R
     from ransac_jl_b200 import scenes
 
+    monkeypatch.setenv("RSC_LOOP_CULL", loop_cull)
     sc = scenes.scene_c2()
     ex, info = _check(R, sc, 32, {"tau": len(sc.vertices) // 100, "minsubsetN": 4096, "itermax": 200}, 2024)
     assert len(ex) >= 13 and info["iterations"] == 200
