@@ -161,20 +161,28 @@ function refit_extract!(dc::DeviceCloud, s::FittedShape, params; disable::Bool=t
 end
 
 """
-Extension: whole-cloud inlier counts of `cands` -- the counts `scorecandidate` would give on the whole
-cloud -- skipping the (candidate, 512-point Morton tile) pairs that provably hold no compatible point
-(`rsc_score_culled`).  Builds the Morton order on first use.  Returns `(counts, pairs_total, pairs_survived)`.
+Extension: inlier counts of `cands` -- the counts `scorecandidate` would give on the whole cloud
+(`subset = 0`) or on subset `subset` (1-based, like the reference's `subsetID`) -- skipping the
+(candidate, 128-point Morton tile) pairs that provably hold no compatible point (`rsc_score_culled`,
+`rsc_score_culled_subset`).  The whole-cloud form builds the Morton order on first use; the subset form sorts a
+copy of the subset on first use.  Returns `(counts, pairs_total, pairs_survived)`.
 """
-function score_culled(dc::DeviceCloud, cands::Vector{<:FittedShape}, params; octree_levels::Integer=11)
-    check(ccall((:rsc_cloud_cells_levels, LIB[]), Int32, (Ptr{Cvoid},), dc.h) > 0 ? Int32(0) :
-          ccall((:rsc_cloud_build_cells, LIB[]), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
+function score_culled(dc::DeviceCloud, cands::Vector{<:FittedShape}, params; subset::Integer=0, octree_levels::Integer=11)
     prm = Ref(toparams(params))
     arr = [tocand(c) for c in cands]
     counts = Vector{Int32}(undef, length(arr))
     tot = Ref{Int64}(0); sur = Ref{Int64}(0); ms = Ref{Float64}(0.0)
-    check(ccall((:rsc_score_culled, LIB[]), Int32,
-                (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Ptr{Int32}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
-                dc.h, prm, arr, length(arr), counts, tot, sur, ms))
+    if subset > 0
+        check(ccall((:rsc_score_culled_subset, LIB[]), Int32,
+                    (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Int32, Ptr{Int32}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
+                    dc.h, prm, arr, length(arr), subset - 1, counts, tot, sur, ms))
+    else
+        check(ccall((:rsc_cloud_cells_levels, LIB[]), Int32, (Ptr{Cvoid},), dc.h) > 0 ? Int32(0) :
+              ccall((:rsc_cloud_build_cells, LIB[]), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
+        check(ccall((:rsc_score_culled, LIB[]), Int32,
+                    (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Ptr{Int32}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
+                    dc.h, prm, arr, length(arr), counts, tot, sur, ms))
+    end
     Int.(counts), tot[], sur[]
 end
 
