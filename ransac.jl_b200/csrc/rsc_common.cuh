@@ -125,7 +125,7 @@ struct rsc_subset {
   float* csoa = nullptr;       // 6 * m_pad floats
   uint32_t* cen = nullptr;     // m_pad/32 words: pc.isenabled in that order (kept current with `enabled`)
   int64_t* cidx = nullptr;     // m local point indices in that order
-  void* ctiles = nullptr;      // float4 [m_pad/128 + m_pad/512]
+  void* ctiles = nullptr;      // float4 [cull_sphere_count(m_pad)]: spheres of the 128 / 512 / 4096-point tiles
   void release_cull_view() {
     if (csoa) cudaFree(csoa);
     if (cen) cudaFree(cen);
@@ -144,7 +144,7 @@ struct rsc_cells {
   uint8_t* leafdepth = nullptr;  // [n] by point index: first level whose cell holds <= 8 points
   uint32_t* en_sorted = nullptr; // [n_pad/32] pc.isenabled in Morton order
   float* msoa = nullptr;         // [6 n_pad] Morton-ordered SoA copy of the cloud (rsc_cull.cu, built on first use)
-  void* tiles = nullptr;         // [n_pad/512] float4 bounding sphere of every 512-point tile of msoa
+  void* tiles = nullptr;         // float4 [cull_sphere_count(n_pad)]: spheres of the 128 / 512 / 4096-point tiles of msoa
   bool en_valid = false;         // en_sorted matches the cloud's enabled mask
   rsc::DevBuf selbuf;            // rank/select index over en_sorted
   bool sel_valid = false;
@@ -251,6 +251,7 @@ int32_t cloud_ready(rsc_cloud* cloud);
 int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st);
 // culled scorer (rsc_cull.cu) and the Morton view of a subset it runs on (rsc_octree.cu)
 int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st);
+size_t cull_sphere_count(int64_t n_pad);  // float4 entries cull_tile_spheres writes (tiles, groups, blocks)
 int32_t cull_tile_spheres(rsc_ctx* ctx, const PointSet& ps, float4* tiles, cudaStream_t st);
 int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, const float4* tiles, const Thresh& th,
                      const rsc_cand* d_cands, int C_cap, const int32_t* d_C, int32_t* cv, int32_t* ce, unsigned long long* d_stats,

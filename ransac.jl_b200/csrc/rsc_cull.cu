@@ -26,12 +26,14 @@
 
 namespace rsc {
 
+size_t cull_sphere_count(int64_t n_pad);
 int32_t cull_tile_spheres(rsc_ctx* ctx, const PointSet& ps, float4* tiles, cudaStream_t st);
 
 constexpr int kCullThreads = 128;
 constexpr int kCullWarps = kCullThreads / 32;
 constexpr int kCullTile = 128;                       // points of a warp's tile: one bounding sphere each
 constexpr int kCullGroup = kCullTile * kCullWarps;   // points of a CTA's group of tiles (= kTile): one sphere too
+constexpr int kCullBlockGroups = 8;                  // groups per block (4096 points): the coarsest sphere (pre-pass)
 constexpr int kCullSuper = 2048;                     // most candidates of one work item (capacity of the tiles' survivor lists)
 #ifndef RSC_CULL_MINB
 #define RSC_CULL_MINB 4
@@ -47,6 +49,9 @@ struct CullArgs {
   PointSet ps;           // the points in Morton order (rows of n_pad floats; n_pad a multiple of 512)
   const float4* tiles;   // bounding sphere of every 128-point tile: centre, radius
   const float4* groups;  // bounding sphere of every 512-point group of four tiles
+  const float4* blocks;  // bounding sphere of every 4096-point block of eight groups
+  uint32_t* bbits;       // [nblocks][cwords] pre-pass: bit c = candidate c passes the block's sphere
+  int nblocks, cwords;
   int ngroups;           // n_pad / 512: a CTA takes the four tiles of a group, one per warp
   int nranges;           // the candidates are split into nranges runs of cands_per_range (<= kCullSuper, multiple of 128)
   int cands_per_range;
@@ -296,12 +301,33 @@ __device__ __forceinline__ void cull_narrow(const CullArgs& a, const float* __re
   }
 }
 
+// pre-pass: every candidate against every 4096-point block's sphere, a warp per (block, 32 candidates); the main
+// kernel then only looks at the candidates whose bit is set (a fifth of them on c3)
+__global__ void __launch_bounds__(256) cull_block_kernel(const __grid_constant__ CullArgs a) {
+  const int C = cull_count(a);
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= (int64_t)a.nblocks * a.cwords) return;
+  const int block = (int)(w / a.cwords), cw = (int)(w % a.cwords);
+  const int c = cw * 32 + lane;
+  bool keep = false;
+  if (c < C) {
+    float r[kRecFields];
+    load_rec(a.rec, c, r);
+    const int ct = a.col[c];
+    keep = !cull_far(ct, r, a.blocks[block], a.th.eps[public_type(ct)]);
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) a.bbits[w] = m;
+}
+
 __global__ void __launch_bounds__(kCullThreads, kCullMinB) cull_score_kernel(const __grid_constant__ CullArgs a) {
   __shared__ __align__(16) float wpts[kCullWarps][kCullTile / 2 * 12];  // the four tiles' points as packed pairs
   __shared__ uint32_t wmask[kCullWarps][2 * (kCullTile / 32)];          // their valid / enabled words in sign-word order
   __shared__ float4 wsph[kCullWarps];                                   // their bounding spheres
-  __shared__ uint16_t wlist[kCullWarps][kCullSuper];  // per tile: the candidates (relative to the item's first) that pass its sphere
-  __shared__ uint32_t wn[kCullWarps], bnext, sitem;
+  __shared__ uint16_t slist[kCullSuper];              // the item's candidates (relative to its first) that pass the block's sphere
+  __shared__ uint16_t wlist[kCullWarps][kCullSuper];  // per tile: those that pass the group's and the tile's sphere too
+  __shared__ uint32_t wn[kCullWarps], bnext, sitem, swtot[kCullWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = cull_count(a);
   unsigned long long n_surv = 0, n_exact = 0;
@@ -334,29 +360,51 @@ __global__ void __launch_bounds__(kCullThreads, kCullMinB) cull_score_kernel(con
       if (lane == 0) wsph[warp] = a.tiles[tile];
     }
     __syncthreads();
-    // ---- broad phase, a candidate per thread: the group's sphere first, then the four tiles' spheres ----
+    // ---- the item's candidates that passed the pre-pass (their block's sphere), in order: thread t expands the
+    // bits of word t behind an exclusive scan of the words' bit counts ----
+    int nlist = 0;
     {
+      const int nw = (c_hi - c_lo + 31) >> 5;  // <= kCullSuper / 32 <= kCullThreads words (c_lo is a multiple of 128)
+      const uint32_t* bw = a.bbits + (size_t)(group / kCullBlockGroups) * a.cwords + (c_lo >> 5);
+      uint32_t word = tid < nw ? bw[tid] : 0u;
+      if (tid < nw && (tid + 1) * 32 > c_hi - c_lo) word &= (1u << ((c_hi - c_lo) & 31)) - 1u;  // (bits beyond C are 0 anyway)
+      const int cnt = __popc(word);
+      int inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+      }
+      if (lane == 31) swtot[warp] = (uint32_t)inc;
+      __syncthreads();
+      int off = inc - cnt;
+#pragma unroll
+      for (int w = 0; w < kCullWarps; ++w) {
+        if (w < warp) off += (int)swtot[w];
+        nlist += (int)swtot[w];
+      }
+      while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        slist[off++] = (uint16_t)(tid * 32 + b);
+      }
+    }
+    __syncthreads();
+    // ---- broad phase, a listed candidate per thread: the group's sphere first, then the four tiles' spheres ----
+    if (nlist > 0) {
       const float4 gs = a.groups[group];
-      float rn[kRecFields];
-      int ctn = 0;
-      int c = c_lo + tid;
-      if (c < c_hi) load_rec(a.rec, c, rn), ctn = a.col[c];
-      for (int c0 = c_lo; c0 < c_hi; c0 += kCullThreads) {
+      for (int e = tid; e < nlist; e += kCullThreads) {
+        const int rel = (int)slist[e];
+        const int c = c_lo + rel;
         float r[kRecFields];
+        load_rec(a.rec, c, r);
+        const int ct = a.col[c];
+        const float eps = a.th.eps[public_type(ct)];
+        if (!cull_far(ct, r, gs, eps)) {
 #pragma unroll
-        for (int f = 0; f < kRecFields; ++f) r[f] = rn[f];
-        const int ct = ctn;
-        const int cn = c + kCullThreads;
-        if (cn < c_hi) load_rec(a.rec, cn, rn), ctn = a.col[cn];  // the next candidate's record is on its way
-        if (c < c_hi) {
-          const float eps = a.th.eps[public_type(ct)];
-          if (!cull_far(ct, r, gs, eps)) {
-#pragma unroll
-            for (int w = 0; w < kCullWarps; ++w)
-              if (!cull_far(ct, r, wsph[w], eps)) wlist[w][atomicAdd(&wn[w], 1u)] = (uint16_t)(c - c_lo);
-          }
+          for (int w = 0; w < kCullWarps; ++w)
+            if (!cull_far(ct, r, wsph[w], eps)) wlist[w][atomicAdd(&wn[w], 1u)] = (uint16_t)rel;
         }
-        c = cn;
       }
     }
     __syncthreads();
@@ -427,9 +475,8 @@ static int32_t cull_prepare(rsc_cloud* cloud, cudaStream_t st) {
   rsc_ctx* ctx = cloud->ctx;
   rsc_cells& c = cloud->cells;
   if (c.msoa) return RSC_OK;
-  const int ntiles = (int)(cloud->n_pad / kCullTile), ngroups = (int)(cloud->n_pad / kCullGroup);
   RSC_CUDA(ctx, cudaMalloc(&c.msoa, (size_t)6 * cloud->n_pad * sizeof(float)));
-  cudaError_t e = cudaMalloc(&c.tiles, (size_t)(ntiles + ngroups) * sizeof(float4));
+  cudaError_t e = cudaMalloc(&c.tiles, cull_sphere_count(cloud->n_pad) * sizeof(float4));
   if (e != cudaSuccess) {
     cudaFree(c.msoa);
     c.msoa = nullptr;
@@ -443,14 +490,22 @@ static int32_t cull_prepare(rsc_cloud* cloud, cudaStream_t st) {
   return cull_tile_spheres(ctx, ps, reinterpret_cast<float4*>(c.tiles), st);
 }
 
-// bounding spheres of a point set that already is in a spatially coherent order: n_pad / 128 tile spheres followed
-// by n_pad / 512 group spheres (`tiles` holds n_pad / 128 + n_pad / 512 entries)
+// bounding spheres of a point set that already is in a spatially coherent order: n_pad / 128 tile spheres, then
+// n_pad / 512 group spheres, then ceil(n_pad / 4096) block spheres (`tiles` holds cull_sphere_count(n_pad) entries)
+size_t cull_sphere_count(int64_t n_pad) {
+  return (size_t)(n_pad / kCullTile + n_pad / kCullGroup + (n_pad / kCullGroup + kCullBlockGroups - 1) / kCullBlockGroups);
+}
+
 int32_t cull_tile_spheres(rsc_ctx* ctx, const PointSet& ps, float4* tiles, cudaStream_t st) {
   const int ntiles = (int)(ps.n_pad / kCullTile), ngroups = (int)(ps.n_pad / kCullGroup);
+  const int nblocks = (ngroups + kCullBlockGroups - 1) / kCullBlockGroups;
   if (ntiles == 0) return RSC_OK;
   tile_sphere_kernel<<<(ntiles + 7) / 8, 256, 0, st>>>(ps.x, ps.y, ps.z, ps.n, kCullTile, ntiles, tiles);
   RSC_CUDA(ctx, cudaGetLastError());
   tile_sphere_kernel<<<(ngroups + 7) / 8, 256, 0, st>>>(ps.x, ps.y, ps.z, ps.n, kCullGroup, ngroups, tiles + ntiles);
+  RSC_CUDA(ctx, cudaGetLastError());
+  tile_sphere_kernel<<<(nblocks + 7) / 8, 256, 0, st>>>(ps.x, ps.y, ps.z, ps.n, kCullGroup * kCullBlockGroups, nblocks,
+                                                        tiles + ntiles + ngroups);
   RSC_CUDA(ctx, cudaGetLastError());
   return RSC_OK;
 }
@@ -467,11 +522,14 @@ int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, c
   RSC_CUDA(ctx, cudaMemsetAsync(ce, 0, (size_t)C_cap * sizeof(int32_t), st));
   if (ps.n_pad <= 0) return RSC_OK;
   if (C_cap >= (1 << 24)) return fail(ctx, RSC_E_ARG, "score_culled: too many candidates");
-  // scratch: [rec][orig][col][stats 2 x u64 | pn, work | hist 5 | cursor 5][pair queue]
+  // scratch: [rec][orig][col][stats 2 x u64 | pn, work | hist 5 | cursor 5][block bits][pair queue]
+  const int ngroups = (int)(ps.n_pad / kCullGroup), nblocks = (ngroups + kCullBlockGroups - 1) / kCullBlockGroups;
+  const int cwords = (C_cap + kCullThreads - 1) / kCullThreads * (kCullThreads / 32);  // whole 128-candidate ranges
   const size_t o_orig = (size_t)C_cap * kRecFields * sizeof(float);
   const size_t o_col = o_orig + (size_t)C_cap * sizeof(int32_t);
   const size_t o_ctr = (o_col + (size_t)C_cap + 15) / 16 * 16;
-  const size_t o_queue = o_ctr + 96;
+  const size_t o_bits = o_ctr + 96;
+  const size_t o_queue = (o_bits + (size_t)nblocks * cwords * 4 + 15) / 16 * 16;
   int64_t qcap = (int64_t)((double)C_cap * (double)ps.n / 8192.0);
   qcap = qcap < (1 << 16) ? (1 << 16) : qcap > (8 << 20) ? (8 << 20) : qcap;
   RSC_CUDA(ctx, ctx->cullbuf.ensure(o_queue + (size_t)qcap * sizeof(uint2)));
@@ -491,7 +549,10 @@ int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, c
   a.ps = ps;
   a.tiles = tiles;
   a.groups = tiles + ps.n_pad / kCullTile;
-  a.ngroups = (int)(ps.n_pad / kCullGroup);
+  a.ngroups = ngroups;
+  a.blocks = a.groups + ngroups;
+  a.nblocks = nblocks, a.cwords = cwords;
+  a.bbits = reinterpret_cast<uint32_t*>(b + o_bits);
   // work items = groups x candidate ranges: at most kCullSuper candidates each, fewer when the point set is small
   // (enough items to balance the persistent grid)
   const int cap = ctx->sm_count * kCullMinB;
@@ -513,6 +574,11 @@ int32_t cull_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet& ps, c
   a.inline_fp64 = getenv("RSC_CULL_INLINE") ? atoi(getenv("RSC_CULL_INLINE")) : 0;
   const int64_t items = (int64_t)a.ngroups * a.nranges;
   const int grid = (int)(items < cap ? items : cap);
+  {
+    const int64_t warps = (int64_t)nblocks * cwords;
+    cull_block_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(a);
+    RSC_CUDA(ctx, cudaGetLastError());
+  }
   cull_score_kernel<<<grid, kCullThreads, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
   cull_pair_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(a);

@@ -180,7 +180,7 @@ int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st) {
   if (s.csoa) return RSC_OK;
   if (s.m >= ((int64_t)1 << 31)) return fail(ctx, RSC_E_ARG, "culled scorer: subset too large");
   const int64_t m = s.m, words = s.m_pad / 32;
-  const int64_t nsph = s.m_pad / 128 + s.m_pad / 512;
+  const int64_t nsph = (int64_t)cull_sphere_count(s.m_pad);
   uint32_t *codes_in = nullptr, *codes_out = nullptr, *idx_in = nullptr, *perm = nullptr, *mm = nullptr;
   void* tmp = nullptr;
   auto cleanup = [&]() {

@@ -554,7 +554,7 @@ int32_t rsc_ransac_run(rsc_cloud* cloud, const rsc_params* p, uint64_t seed, rsc
             // path's candidate compiler is ONE CTA (3 ms for a store of a million candidates)
             k5_culled = k5_view && k5_cull_mode != 0 && (k5_cull_mode == 2 || nst >= 4096 || (double)nst * (double)nnew_dis >= 2e8);
             if (k5_culled) {
-              RUN_CUDA(ntiles.ensure((size_t)(sp / 128 + sp / 512) * sizeof(float4)));
+              RUN_CUDA(ntiles.ensure(cull_sphere_count(sp) * sizeof(float4)));
               if ((rc = cull_tile_spheres(ctx, ps, ntiles.as<float4>(), st))) goto done;
               if ((rc = cull_enqueue(ctx, cloud, ps, ntiles.as<float4>(), th, store.cands[store.cur].as<rsc_cand>(), nst, nullptr,
                                      ctx->counts.as<int32_t>(), hit, nullptr, st)))
