@@ -1,6 +1,7 @@
 """The culling criterion of rsc_score_culled (csrc/rsc_cull.cu::cull_far), modelled in NumPy float32:
-a (candidate, 512-point Morton tile) pair may only be skipped if the oracle finds no compatible point in
-the tile.  CPU test of the math (Lipschitz bounds, scaled cone records, non-unit cylinder axes, far
+a (candidate, Morton tile) pair may only be skipped if the oracle finds no compatible point in the tile -- at
+each of the three tile sizes the kernel tests (4096-point blocks in its pre-pass, 512-point groups, 128-point
+tiles).  CPU test of the math (Lipschitz bounds, scaled cone records, non-unit cylinder axes, far
 records of NaN/Inf candidates); the kernel itself is compared with the dense path on the GPU."""
 import math
 
@@ -10,10 +11,10 @@ from oracle import ransac_oracle as O
 from tests import fp32_model as M
 
 f32 = np.float32
-TILE = 512
+TILES = (128, 512, 4096)
 
 
-def morton_tiles(V, levels=9):
+def morton_tiles(V, levels=9, TILE=512):
     lo, hi = V.min(0), V.max(0)
     D = 1 << (levels - 1)
     w = np.where(hi > lo, hi - lo, 1.0)
@@ -66,8 +67,8 @@ def cull_far32(kind, rec, band, c, rt, eps):
         return bool(f32(d) > f32(lim) * f32(1.0001) + f32(8.0) * f32(band))
 
 
-def check_no_false_culls(shapes, V, N, params, levels):
-    tiles = morton_tiles(V, levels)
+def check_no_false_culls(shapes, V, N, params, levels, tile=512):
+    tiles = morton_tiles(V, levels, tile)
     pmax = float(np.sqrt((V.astype(f32).astype(np.float64) ** 2).sum(1).max()))
     nmax = float(np.sqrt((N.astype(f32).astype(np.float64) ** 2).sum(1).max()))
     culled = total = 0
@@ -104,8 +105,9 @@ def test_no_false_culls_on_a_noisy_scene():
 
     shapes = [to_oracle_shape(s) for s in scenes.perturbed_candidates(sc, 12, seed=7)]
     P = O.default_parameters()
-    culled, total = check_no_false_culls(shapes, V, N, P, 8)
-    assert culled > 0.3 * total, (culled, total)  # and the test culls something
+    for tile in TILES:
+        culled, total = check_no_false_culls(shapes, V, N, P, 8, tile)
+        assert culled > (0.3 if tile <= 512 else 0.1) * total, (tile, culled, total)  # and the test culls something
     P2 = O.ransacparameters(P, plane={"eps": 2.0}, sphere={"eps": 2.0}, cylinder={"eps": 2.0}, cone={"eps": 2.0})
     check_no_false_culls(shapes, V, N, P2, 8)
 
@@ -114,5 +116,6 @@ def test_no_false_culls_on_adversarial_candidates():
     from tests.helpers import adversarial_case
 
     shapes, V, N = adversarial_case()
-    culled, total = check_no_false_culls(shapes, V, N, O.default_parameters(), 6)
-    assert culled > 0
+    for tile in TILES:
+        culled, total = check_no_false_culls(shapes, V, N, O.default_parameters(), 6, tile)
+        assert culled > 0 or tile == 4096
