@@ -222,16 +222,16 @@ int32_t rsc_score(rsc_cloud* cloud, const rsc_params* params, const rsc_cand* ca
     RSC_CUDA(ctx, cudaEventRecord(ctx->ev0, st));
     int32_t* d_policy = ctx->counts.as<int32_t>() + 2 * (size_t)C;
     if (chunked && attempt == 0) {
-      const int nchunks = (int)((cloud->n + cloud->chunk_pts - 1) / cloud->chunk_pts);
+      const int nchunks = cloud->n_chunks();
       RSC_CUDA(ctx, ctx->wl_count.ensure(16));
       RSC_CUDA(ctx, cudaMemsetAsync(ctx->wl_count.as<uint32_t>() + 2, 0, sizeof(uint32_t), st));
       for (int i = 0; i < nchunks && !rc; ++i) {
-        const int64_t off = (int64_t)i * cloud->chunk_pts;
+        const int64_t off = cloud->chunk_begin(i);
         PointSet sl = ps;
         sl.x += off, sl.y += off, sl.z += off, sl.nx += off, sl.ny += off, sl.nz += off;
         sl.enabled += off / 32, sl.valid += off / 32;
-        sl.n = (cloud->n - off < cloud->chunk_pts) ? cloud->n - off : cloud->chunk_pts;
-        sl.n_pad = (i == nchunks - 1) ? cloud->n_pad - off : cloud->chunk_pts;
+        sl.n = cloud->chunk_begin(i + 1) - off;
+        sl.n_pad = (i == nchunks - 1) ? cloud->n_pad - off : sl.n;
         RSC_CUDA(ctx, cudaStreamWaitEvent(st, cloud->chunk_ev[i], 0));
         rc = score_enqueue(ctx, cloud, sl, th, ctx->cands.as<rsc_cand>(), C, i == nchunks - 1 ? d_policy : nullptr, false, st,
                            ctx->counts.as<int32_t>(), ctx->counts.as<int32_t>() + C, ctx->aux.as<double>(),

@@ -165,7 +165,15 @@ int32_t refresh_subsets_enabled(rsc_cloud* cloud, cudaStream_t st) {
   return RSC_OK;
 }
 
-constexpr int64_t kChunkPts = 2 << 20;  // upload granularity (48 MB of float32 AoS per chunk)
+// Upload granularity.  Through page-locked staging (pageable caller arrays): 2 Mi points (48 MB of float32 AoS), the
+// host copy of chunk i + 1 overlaps the DMA of chunk i.  Straight from the caller's page-locked arrays: 4 Mi points --
+// rsc_score follows the upload chunk by chunk and every chunk costs it a compile + two fix-up launches (c3 e2e step
+// 46.7 ms at 2 Mi / 2 Mi first, 45.7 ms at 4 Mi / 1 Mi first; tools/e2e_first_chunk.sh).  The FIRST chunk is a
+// quarter of that: its arrival is pure latency for whatever follows the upload.
+static int64_t chunk_points(bool staged) {
+  if (const char* e = getenv("RSC_CHUNK_PTS")) return std::max<int64_t>(1 << 16, std::min<int64_t>(16 << 20, atoll(e) / kTile * kTile));
+  return staged ? (2 << 20) : (4 << 20);
+}
 
 // ---- pageable host memory <-> device through page-locked staging filled by worker threads ----------------
 static int host_copy_threads() {
@@ -250,7 +258,14 @@ static int32_t cloud_upload(rsc_cloud* c, const T* xyz, const T* nrm) {
   cudaStream_t cs = ctx->copy_stream;
   const int64_t n = c->n;
   const int64_t words = c->n_pad / 32;
-  const int nchunks = (int)((n + kChunkPts - 1) / kChunkPts);
+  // pageable caller arrays of a large cloud: worker threads copy each chunk into page-locked staging and the DMA
+  // engine takes it from there (cudaMemcpy from pageable memory is a single-threaded staged copy, ~10 GB/s)
+  const bool staged = n >= ((int64_t)1 << 20) && !getenv("RSC_NO_STAGED_UPLOAD") && is_pageable(xyz) && is_pageable(nrm);
+  const int64_t kChunkPts = chunk_points(staged);
+  c->chunk_pts = kChunkPts;
+  c->chunk_first = getenv("RSC_FIRST_CHUNK_PTS") ? std::max<int64_t>(kTile, std::min<int64_t>(kChunkPts, atoll(getenv("RSC_FIRST_CHUNK_PTS")) / kTile * kTile))
+                                                 : kChunkPts / 4;
+  const int nchunks = c->n_chunks();
   // previous work on the compute stream may still read the old coordinates
   RSC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (!c->d_bounds || (int)c->chunk_ev.size() < nchunks) {
@@ -262,21 +277,17 @@ static int32_t cloud_upload(rsc_cloud* c, const T* xyz, const T* nrm) {
       c->chunk_ev.push_back(e);
     }
   }
-  c->chunk_pts = kChunkPts;
   RSC_CUDA(ctx, cudaMemsetAsync(c->d_bounds, 0, (size_t)(2 * nchunks + 2) * sizeof(uint32_t), cs));
   fill_valid_kernel<<<(unsigned)((words + 255) / 256), 256, 0, cs>>>(c->valid, c->enabled, n, words);
   RSC_CUDA(ctx, cudaGetLastError());
   const size_t cbytes = (size_t)3 * kChunkPts * sizeof(T);
   for (int b = 0; b < 2; ++b) RSC_CUDA(ctx, ctx->stage[b].ensure(2 * cbytes));
-  // pageable caller arrays of a large cloud: worker threads copy each chunk into page-locked staging and the DMA
-  // engine takes it from there (cudaMemcpy from pageable memory is a single-threaded staged copy, ~10 GB/s)
-  const bool staged = n >= ((int64_t)1 << 20) && !getenv("RSC_NO_STAGED_UPLOAD") && is_pageable(xyz) && is_pageable(nrm);
   const int nt = staged ? host_copy_threads() : 1;
   if (staged)
     if (int32_t rcs = ensure_hstage(ctx, 2 * cbytes)) return rcs;
   for (int i = 0; i < nchunks; ++i) {
-    const int64_t off = (int64_t)i * kChunkPts;
-    const int64_t cnt = n - off < kChunkPts ? n - off : kChunkPts;
+    const int64_t off = c->chunk_begin(i);
+    const int64_t cnt = c->chunk_begin(i + 1) - off;
     T* sx = ctx->stage[i & 1].as<T>();
     T* sn = sx + 3 * kChunkPts;
     if (staged) {
@@ -310,7 +321,7 @@ namespace rsc {
 int32_t cloud_ready(rsc_cloud* c) {
   if (!c || !c->pending) return RSC_OK;
   rsc_ctx* ctx = c->ctx;
-  const int nchunks = (int)((c->n + c->chunk_pts - 1) / c->chunk_pts);
+  const int nchunks = c->n_chunks();
   uint32_t hb[2];
   RSC_CUDA(ctx, cudaMemcpyAsync(hb, c->d_bounds + 2 * nchunks, sizeof(hb), cudaMemcpyDeviceToHost, ctx->copy_stream));
   RSC_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));

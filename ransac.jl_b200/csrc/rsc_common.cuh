@@ -165,7 +165,10 @@ struct rsc_cloud {
   // chunked upload in flight: chunk i is usable once chunk_ev[i] has fired on the copy stream
   bool pending = false;
   int64_t chunk_pts = 0;
+  int64_t chunk_first = 0;  // the first chunk is smaller: whatever follows the upload can start sooner
   std::vector<cudaEvent_t> chunk_ev;
+  int n_chunks() const { return n <= chunk_first ? 1 : 1 + (int)((n - chunk_first + chunk_pts - 1) / chunk_pts); }
+  int64_t chunk_begin(int i) const { return i == 0 ? 0 : std::min<int64_t>(n, chunk_first + (int64_t)(i - 1) * chunk_pts); }
   uint32_t* d_bounds = nullptr;  // per chunk: max |p|^2, max |n|^2 (float bits); last pair = whole cloud
   std::vector<rsc_subset> subsets;
   // rank/select index over `enabled` for the sampler (rsc_fit.cu); rebuilt lazily after any change
