@@ -127,7 +127,7 @@ void rsc_ctx_destroy(rsc_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   rsc::DevBuf* bufs[] = {&ctx->cands,    &ctx->rec,      &ctx->orig,     &ctx->slot_of, &ctx->blktab,
                          &ctx->counts,   &ctx->masks_gm, &ctx->masks_cm, &ctx->worklist, &ctx->wl_count, &ctx->pairs,
-                         &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf, &ctx->exq, &ctx->scanbuf, &ctx->lsqbuf, &ctx->cullbuf, &ctx->shardbuf, &ctx->gselbuf, &ctx->smallbuf};
+                         &ctx->aux,      &ctx->misc,     &ctx->misc2,    &ctx->idxbuf,  &ctx->fitbuf, &ctx->selbuf, &ctx->exq, &ctx->scanbuf, &ctx->lsqbuf, &ctx->cullbuf, &ctx->shardbuf, &ctx->gselbuf, &ctx->smallbuf, &ctx->viewtmp};
   for (auto* b : bufs) b->release();
   rsc::loop_scratch_free(ctx);
   if (ctx->comm) rsc_ctx_comm_destroy(ctx);

@@ -100,7 +100,7 @@ struct rsc_ctx {
   rsc_stats stats{};
   // scratch of the score path
   rsc::DevBuf cands, rec, orig, slot_of, blktab, counts, masks_gm, masks_cm, worklist, pairs, wl_count, aux;
-  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf, cullbuf, shardbuf, gselbuf, smallbuf;
+  rsc::DevBuf misc, misc2, idxbuf, fitbuf, selbuf, exq, scanbuf, lsqbuf, cullbuf, shardbuf, gselbuf, smallbuf, viewtmp;
   size_t wl_cap = 1u << 22;  // guard-band queue capacity (groups / pairs), grows on overflow
   rsc_allreduce_fn allreduce = nullptr;  // sums int32 device buffers across the ranks of a sharded run
   void* allreduce_user = nullptr;

@@ -599,7 +599,10 @@ int32_t loop_score_new(rsc_ctx* ctx, rsc_cloud* cloud, rsc_subset& sub, const Po
   // (read per call: tests switch it between runs)
   const int mode = getenv("RSC_LOOP_CULL") ? atoi(getenv("RSC_LOOP_CULL")) : 1;  // 0: never, 1: when it pays, 2: always
   const double min_evals = getenv("RSC_LOOP_CULL_MIN") ? atof(getenv("RSC_LOOP_CULL_MIN")) : 4e8;
-  const bool cull = mode != 0 && whole_subset && n_new > 0 && sub.m > 0 && (mode == 2 || (double)n_new * (double)sub.m >= min_evals);
+  // a subset without a Morton view yet: building one (a sort of the subset, four allocations) only pays for really
+  // large batches -- the cell sampler's (>= 5e9 pairs each on c4); c5's root-cell batches of ~3e8-6e8 pairs stay dense
+  const double need = sub.csoa ? min_evals : 10.0 * min_evals;
+  const bool cull = mode != 0 && whole_subset && n_new > 0 && sub.m > 0 && (mode == 2 || (double)n_new * (double)sub.m >= need);
   if (!cull) {
     if (int32_t rc = score_enqueue(ctx, cloud, ps, th, d_cands, n_new, nullptr, false, st, cv, ce)) return rc;
     if (d_ovf) {

@@ -181,13 +181,7 @@ int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st) {
   if (s.m >= ((int64_t)1 << 31)) return fail(ctx, RSC_E_ARG, "culled scorer: subset too large");
   const int64_t m = s.m, words = s.m_pad / 32;
   const int64_t nsph = (int64_t)cull_sphere_count(s.m_pad);
-  uint32_t *codes_in = nullptr, *codes_out = nullptr, *idx_in = nullptr, *perm = nullptr, *mm = nullptr;
-  void* tmp = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(codes_in), cudaFree(codes_out), cudaFree(idx_in), cudaFree(perm), cudaFree(mm), cudaFree(tmp);
-  };
   auto bail = [&](cudaError_t e, const char* what) {
-    cleanup();
     s.release_cull_view();
     return fail_cuda(ctx, e, what);
   };
@@ -198,12 +192,21 @@ int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st) {
   CV(cudaMalloc(&s.cen, (size_t)words * 4));
   CV(cudaMalloc(&s.cidx, (size_t)(m > 0 ? m : 1) * sizeof(int64_t)));
   CV(cudaMalloc(&s.ctiles, (size_t)nsph * sizeof(float4)));
+  // temporaries live in a scratch buffer of the context (no cudaMalloc / cudaFree per view: a cudaFree in the middle
+  // of a run synchronises the device and was seen to take tens of milliseconds): codes in/out, positions in/out,
+  // bounding box, CUB's workspace
   const size_t mm1 = (size_t)(m > 0 ? m : 1);
-  CV(cudaMalloc(&codes_in, mm1 * 4));
-  CV(cudaMalloc(&codes_out, mm1 * 4));
-  CV(cudaMalloc(&idx_in, mm1 * 4));
-  CV(cudaMalloc(&perm, mm1 * 4));
-  CV(cudaMalloc(&mm, 6 * 4));
+  const size_t o_cout = (mm1 * 4 + 255) / 256 * 256, o_iin = 2 * o_cout, o_perm = 3 * o_cout, o_mm = 4 * o_cout, o_tmp = o_mm + 256;
+  size_t tmp_bytes = 0;
+  CV(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                     (uint32_t*)nullptr, (int)mm1, 0, 30, st));
+  CV(ctx->viewtmp.ensure(o_tmp + tmp_bytes + 16));
+  char* b = ctx->viewtmp.as<char>();
+  uint32_t* codes_in = reinterpret_cast<uint32_t*>(b);
+  uint32_t* codes_out = reinterpret_cast<uint32_t*>(b + o_cout);
+  uint32_t* idx_in = reinterpret_cast<uint32_t*>(b + o_iin);
+  uint32_t* perm = reinterpret_cast<uint32_t*>(b + o_perm);
+  uint32_t* mm = reinterpret_cast<uint32_t*>(b + o_mm);
   if (m > 0) {
     const uint32_t init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     CV(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -224,10 +227,7 @@ int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st) {
     }
     morton_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(s.soa, m, s.m_pad, q, codes_in, idx_in);
     CV(cudaGetLastError());
-    size_t tmp_bytes = 0;
-    CV(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, codes_in, codes_out, idx_in, perm, (int)m, 0, 30, st));
-    CV(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
-    CV(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, codes_in, codes_out, idx_in, perm, (int)m, 0, 30, st));
+    CV(cub::DeviceRadixSort::SortPairs(b + o_tmp, tmp_bytes, codes_in, codes_out, idx_in, perm, (int)m, 0, 30, st));
   }
   cull_view_gather_kernel<<<(unsigned)((s.m_pad + 255) / 256), 256, 0, st>>>(s.soa, s.m_pad, s.idx, perm, m, s.csoa, s.cidx);
   CV(cudaGetLastError());
@@ -236,15 +236,12 @@ int32_t subset_cull_view(rsc_cloud* cloud, rsc_subset& s, cudaStream_t st) {
     ps.x = s.csoa, ps.y = s.csoa + s.m_pad, ps.z = s.csoa + 2 * s.m_pad;
     ps.n = m, ps.n_pad = s.m_pad;
     if (int32_t rc = cull_tile_spheres(ctx, ps, reinterpret_cast<float4*>(s.ctiles), st)) {
-      cleanup();
       s.release_cull_view();
       return rc;
     }
   }
-  CV(cudaStreamSynchronize(st));
 #undef CV
-  cleanup();
-  // pc.isenabled in the new order
+  // pc.isenabled in the new order (stream order keeps the scratch buffer safe: everything above was enqueued on st)
   if (int32_t rc = refresh_subsets_enabled(cloud, st)) return rc;
   return RSC_OK;
 }
