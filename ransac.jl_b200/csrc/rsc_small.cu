@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(kSmallThreads) small_score_kernel(const __grid
   const int C = small_count(a);
   const int lane = threadIdx.x & 31;
   const int64_t ntiles = a.ps.n_pad / kSmallThreads;  // n_pad is a multiple of 512
-  for (int c0 = 0; c0 < C; c0 += kSmallTile) {
+  // the candidate chunks are spread over gridDim.y (K5: a large store against few points would otherwise be one long
+  // serial walk in a handful of CTAs)
+  for (int c0 = blockIdx.y * kSmallTile; c0 < C; c0 += gridDim.y * kSmallTile) {
     const int ct = min(kSmallTile, C - c0);
     for (int i = threadIdx.x; i < ct * kRecFields; i += kSmallThreads) (&srec[0][0])[i] = a.rec[(size_t)c0 * kRecFields + i];
     for (int i = threadIdx.x; i < ct; i += kSmallThreads) {
@@ -142,8 +144,12 @@ int32_t score_small_enqueue(rsc_ctx* ctx, const rsc_cloud* cloud, const PointSet
   small_compile_kernel<<<(c_cap + 127) / 128, 128, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
   const int64_t ntiles = ps.n_pad / kSmallThreads;
-  const int grid = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 8);
-  small_score_kernel<<<grid, kSmallThreads, 0, st>>>(a);
+  const int gx = (int)std::min<int64_t>(ntiles, (int64_t)ctx->sm_count * 8);
+  // rows of candidate chunks: as many as there is room for beside the point tiles (a launch sized by a capacity
+  // expects a quarter of it, see the device loop)
+  const int chunks = ((d_count ? (c_cap + 3) / 4 : c_cap) + kSmallTile - 1) / kSmallTile;
+  const int gy = std::max(1, std::min(chunks, ctx->sm_count * 16 / gx));
+  small_score_kernel<<<dim3((unsigned)gx, (unsigned)gy), kSmallThreads, 0, st>>>(a);
   RSC_CUDA(ctx, cudaGetLastError());
   ctx->stats.score_launches += 1;
   return RSC_OK;
