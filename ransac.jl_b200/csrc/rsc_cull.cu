@@ -1,21 +1,26 @@
-// rsc_cull.cu -- whole-cloud scoring with Morton-tile culling (extension; same counts as rsc_score).
+// rsc_cull.cu -- scoring with Morton-tile culling (extension; the same counts as rsc_score).
 //
 // The dense K2 kernel (rsc_score.cu) evaluates every (candidate, point) pair, like the reference's
-// compatibles*.  Most of those pairs are far from the candidate's surface.  With the cloud in Morton
-// order (rsc_octree.cu) a tile of 512 consecutive points has a small bounding sphere (c, r), and every
-// distance function of the path (plane.jl:82-103, sphere.jl:163-166, cylinder.jl:209-214, the cone's
-// h sin - rho cos) is 1-Lipschitz in the point, so
+// compatibles*.  Most of those pairs are far from the candidate's surface.  With the points in Morton
+// order (rsc_octree.cu: the whole cloud after rsc_cloud_build_cells, or the Morton VIEW of a subset copy) a
+// tile of consecutive points has a small bounding sphere (c, r), and every distance function of the path
+// (plane.jl:82-103, sphere.jl:163-166, cylinder.jl:209-214, the cone's h sin - rho cos) is 1-Lipschitz in the
+// point, so
 //       |dist(c)| > eps + r   =>   no point of the tile is within eps   =>   the tile adds nothing
-// to the candidate's count.  tools/cull_estimate.py: 8 % of the pairs of config c3 survive that test.
+// to the candidate's count (cull_far; tests/test_cull_model.py).  7 % of the (candidate, 128-point tile) pairs of
+// config c3 survive.
 //
-// One kernel, no work lists: a CTA owns a tile (4 points per thread in registers) and walks the
-// candidates in chunks of 128 -- BROAD PHASE: thread t tests candidate chunk+t against the tile sphere
-// (the candidate's compiled FP32 record, one 48-byte load) and stages the survivors' records in shared
-// memory; NARROW PHASE: all threads loop over the survivors (warp-uniform), evaluate their 4 points
-// with the same eval<T>() forms and guard band as the dense kernel, decide in-band pairs in FP64 in the
-// reference's operation order -- queued through a per-CTA staging buffer for cull_fix_kernel, one thread per
-// pair (rsc_exact.cuh) -- and add the warp's count with one REDUX + atomic.
-// Counts only (masks would come out in Morton order), whole cloud only.
+// Three sphere levels: 4096-point blocks (pre-pass cull_block_kernel: a bit per (block, candidate)), 512-point
+// groups and 128-point tiles (inside cull_score_kernel: a CTA takes a group and a range of candidates, a thread
+// tests one candidate).  Survivors of a tile are evaluated in the dense kernel's mapping -- lane = candidate,
+// record in registers, the tile's points broadcast from shared memory, two points per packed FFMA2 -- in batches
+// of 32 handed out to whichever warp is free; a lane counts for its own candidate, no reductions.  Same FP32
+// forms and guard band as the dense kernel (evalp<T> in rsc_eval.cuh); a 32-point block that touches the band is
+// redone by the warp with lane = point, its in-band pairs are decided in float64 in the reference's operation order
+// by cull_pair_kernel (rsc_exact.cuh).  The records are sorted by column type first (cull_compile_kernel), so a
+// warp runs one formula.  DESIGN.md section 3 has the measurements and the history.
+// Counts only (masks would come out in Morton order).  Entry points: rsc_score_culled (whole cloud),
+// rsc_score_culled_subset, and loop_score_new / K5 of rsc_ransac_run (cull_enqueue on device-resident candidates).
 #include <math.h>
 #include <stdlib.h>
 
