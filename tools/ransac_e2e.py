@@ -125,7 +125,7 @@ def replay_local(extracted, V, N, params, nthreads):
 
 
 def run(which: str, rank: int, world: int, local: int, dist=None, n_override: int = 0, check: bool = True, cpu_loop: bool = True,
-        reps: int = 3):
+        reps: int = 5):
     import torch
 
     import ransac_jl_b200 as R
