@@ -275,8 +275,8 @@ namespace rsc {
 struct FitScratch {
   rsc_cand* dense;
   rsc_cand* out;
-  uint32_t* flags;
-  unsigned long long* offs;
+  uint32_t* okmask;  // ballot word per (group of 128 sets, type, warp): which sets gave a candidate
+  uint32_t* base;    // per group: candidates before it
   unsigned long long* total;
   int32_t* out_set;
   int64_t* idx;

@@ -551,24 +551,23 @@ __global__ void __launch_bounds__(128) sample_cells_kernel(int S, int k, uint64_
 // KK = 3: the minimal set of the reference's default drawN, everything in registers; KK = 0: f.k points (3..8)
 template <int KK>
 __global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* __restrict__ idx, int S, FitParams f,
-                                                  rsc_cand* __restrict__ dense, uint32_t* __restrict__ flags) {
+                                                  rsc_cand* __restrict__ dense, uint32_t* __restrict__ okmask) {
   constexpr int KA = KK ? KK : kMaxK;
   const int fk = KK ? KK : f.k;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int t = blockIdx.y;
-  if (s >= S) return;
   const size_t slot = (size_t)s * f.ntypes + t;
-  flags[slot] = 0;
+  bool ok = false;
+  // (a set the sampler could not draw has idx < 0: no candidate)
+  if (s < S && ((!src.G && !src.soa) || idx[(size_t)s * fk] >= 0)) {
   D3 p[KA], n[KA];
   if (src.G) {
-    if (idx[(size_t)s * fk] < 0) return;
     _Pragma("unroll") for (int q = 0; q < fk; ++q) {
       const float* g = src.G + ((size_t)s * fk + q) * 6;
       p[q] = D3{(double)g[0], (double)g[1], (double)g[2]};
       n[q] = D3{(double)g[3], (double)g[4], (double)g[5]};
     }
   } else if (src.soa) {
-    if (idx[(size_t)s * fk] < 0) return;
     _Pragma("unroll") for (int q = 0; q < fk; ++q) {
       const int64_t i = idx[(size_t)s * fk + q];
       p[q] = D3{(double)__ldg(src.soa + i), (double)__ldg(src.soa + src.n_pad + i), (double)__ldg(src.soa + 2 * src.n_pad + i)};
@@ -584,7 +583,6 @@ __global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* 
     }
   }
   rsc_cand c;
-  bool ok = false;
   switch (f.types[t]) {
     case RSC_PLANE:
       ok = fit_plane<KK>(p, n, f, &c);
@@ -599,21 +597,76 @@ __global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* 
       ok = fit_cone<KK>(p, n, f, &c);
       break;
   }
-  if (ok) {
-    dense[slot] = c;
-    flags[slot] = 1u;
+  if (ok) dense[slot] = c;
   }
+  // which of the warp's 32 sets gave a candidate of this type: one word per (group of 128 sets, type, warp)
+  const uint32_t m = __ballot_sync(0xffffffffu, ok);
+  if ((threadIdx.x & 31) == 0) okmask[((size_t)blockIdx.x * f.ntypes + t) * 4 + (threadIdx.x >> 5)] = m;
 }
 
-// order-preserving compaction of the dense candidates
-__global__ void compact_kernel(const rsc_cand* __restrict__ dense, const uint32_t* __restrict__ flags,
-                               const unsigned long long* __restrict__ offs, int total_slots, int ntypes,
-                               rsc_cand* __restrict__ out, int32_t* __restrict__ out_set) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_slots || !flags[i]) return;
-  const unsigned long long o = offs[i];
-  out[o] = dense[i];
-  if (out_set) out_set[o] = i / ntypes;
+// ---- order-preserving compaction of the dense candidates (slot order = set-major, type-minor) ----------------
+// The candidates are sparse (c4: ~0.1 % of the slots), so instead of a scan over all slots: the fit kernel leaves
+// one ballot word per (group of 128 sets, type, warp); ONE CTA scans the groups' bit counts (a group = 4 ntypes
+// words), and every candidate finds its rank inside its group from those words.
+__global__ void __launch_bounds__(1024) group_scan_kernel(const uint32_t* __restrict__ okmask, int G, int ntypes,
+                                                          uint32_t* __restrict__ base, unsigned long long* __restrict__ out_total) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry, chunk;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int g0 = 0; g0 < G; g0 += 1024) {
+    const int g = g0 + tid;
+    uint32_t cnt = 0;
+    if (g < G)
+      for (int i = 0; i < 4 * ntypes; ++i) cnt += __popc(okmask[(size_t)g * 4 * ntypes + i]);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t v = wsum[lane];
+      uint32_t vi = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, vi, d);
+        if (lane >= d) vi += o;
+      }
+      wsum[lane] = vi - v;
+      if (lane == 31) chunk = vi;
+    }
+    __syncthreads();
+    if (g < G) base[g] = carry + wsum[warp] + (inc - cnt);
+    __syncthreads();
+    if (tid == 0) carry += chunk;
+    __syncthreads();
+  }
+  if (tid == 0) *out_total = carry;
+}
+
+// same grid as the fit kernel: thread = (set, type)
+__global__ void __launch_bounds__(128) compact_kernel(const rsc_cand* __restrict__ dense, const uint32_t* __restrict__ okmask,
+                                                      const uint32_t* __restrict__ base, int ntypes, rsc_cand* __restrict__ out,
+                                                      int32_t* __restrict__ out_set) {
+  __shared__ uint32_t m[4 * RSC_NTYPES];  // [type][warp]
+  const int t = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x < 4 * ntypes) m[threadIdx.x] = okmask[(size_t)blockIdx.x * 4 * ntypes + threadIdx.x];
+  __syncthreads();
+  if (!((m[t * 4 + w] >> lane) & 1u)) return;
+  uint32_t rank = base[blockIdx.x];
+  const uint32_t below = (1u << lane) - 1u;
+  for (int tt = 0; tt < ntypes; ++tt) {
+    for (int ww = 0; ww < w; ++ww) rank += __popc(m[tt * 4 + ww]);  // sets of earlier warps, every type
+    rank += __popc(m[tt * 4 + w] & below);                            // earlier sets of this warp, every type
+    if (tt < t) rank += (m[tt * 4 + w] >> lane) & 1u;                 // this set, earlier types
+  }
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  out[rank] = dense[(size_t)s * ntypes + t];
+  if (out_set) out_set[rank] = s;
 }
 
 __global__ void scan_u32_kernel(const uint32_t* __restrict__ counts, int n, unsigned long long* __restrict__ offsets,
@@ -649,15 +702,16 @@ static int32_t carve(rsc_ctx* ctx, int S, int ntypes, int k, FitScratch* fs) {
     return o;
   };
   const size_t o_dense = take(slots * sizeof(rsc_cand)), o_out = take(slots * sizeof(rsc_cand));
-  const size_t o_flags = take(slots * 4), o_offs = take(slots * 8), o_total = take(8);
+  const size_t groups = ((size_t)S + 127) / 128;
+  const size_t o_flags = take(groups * 4 * (ntypes > 0 ? ntypes : 1) * 4), o_offs = take(groups * 4), o_total = take(8);
   const size_t o_set = take(slots * 4), o_idx = take((size_t)S * k * 8), o_level = take((size_t)S * 4);
   const size_t o_gath = take((size_t)S * k * 6 * 4);
   RSC_CUDA(ctx, ctx->fitbuf.ensure(off));
   char* b = ctx->fitbuf.as<char>();
   fs->dense = (rsc_cand*)(b + o_dense);
   fs->out = (rsc_cand*)(b + o_out);
-  fs->flags = (uint32_t*)(b + o_flags);
-  fs->offs = (unsigned long long*)(b + o_offs);
+  fs->okmask = (uint32_t*)(b + o_flags);
+  fs->base = (uint32_t*)(b + o_offs);
   fs->total = (unsigned long long*)(b + o_total);
   fs->out_set = (int32_t*)(b + o_set);
   fs->idx = (int64_t*)(b + o_idx);
@@ -908,12 +962,13 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
       use_idx = fs->idx;
     }
     if (k == 3)
-      fit_kernel<3><<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->flags);
+      fit_kernel<3><<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->okmask);
     else
-      fit_kernel<0><<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->flags);
+      fit_kernel<0><<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->okmask);
     RSC_CUDA(ctx, cudaGetLastError());
-    if ((rc = scan_u32(ctx, fs->flags, slots, fs->offs, fs->total, st))) return rc;
-    compact_kernel<<<(slots + 255) / 256, 256, 0, st>>>(fs->dense, fs->flags, fs->offs, slots, f.ntypes, fs->out, fs->out_set);
+    group_scan_kernel<<<1, 1024, 0, st>>>(fs->okmask, (S + 127) / 128, f.ntypes, fs->base, fs->total);
+    RSC_CUDA(ctx, cudaGetLastError());
+    compact_kernel<<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(fs->dense, fs->okmask, fs->base, f.ntypes, fs->out, fs->out_set);
     RSC_CUDA(ctx, cudaGetLastError());
   } else {
     RSC_CUDA(ctx, cudaMemsetAsync(fs->total, 0, 8, st));
