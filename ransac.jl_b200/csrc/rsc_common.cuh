@@ -285,7 +285,7 @@ struct FitScratch {
 };
 int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
                     const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
-                    FitScratch* fs, const double* cum = nullptr);
+                    FitScratch* fs, const double* cum = nullptr, int32_t* d_seg = nullptr, int sets_per_iter = 0, int nb = 0);
 int64_t count_mask_bits(rsc_ctx* ctx, const uint32_t* words, int64_t nwords);
 // device -> (pageable) host through page-locked staging and worker threads; synchronises `st`
 int32_t staged_d2h(rsc_ctx* ctx, void* h_dst, const void* d_src, size_t bytes, cudaStream_t st);

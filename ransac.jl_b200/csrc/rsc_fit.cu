@@ -608,8 +608,11 @@ __global__ void __launch_bounds__(128) fit_kernel(GatherSrc src, const int64_t* 
 // The candidates are sparse (c4: ~0.1 % of the slots), so instead of a scan over all slots: the fit kernel leaves
 // one ballot word per (group of 128 sets, type, warp); ONE CTA scans the groups' bit counts (a group = 4 ntypes
 // words), and every candidate finds its rank inside its group from those words.
+// seg (optional): the loops' segment bounds -- seg[j] = candidates of the sets before j * sets_per_iter, j = 0..nb;
+// needs sets_per_iter to be a multiple of 128 (then a segment starts at a group)
 __global__ void __launch_bounds__(1024) group_scan_kernel(const uint32_t* __restrict__ okmask, int G, int ntypes,
-                                                          uint32_t* __restrict__ base, unsigned long long* __restrict__ out_total) {
+                                                          uint32_t* __restrict__ base, unsigned long long* __restrict__ out_total,
+                                                          int32_t* __restrict__ seg, int sets_per_iter, int nb) {
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry, chunk;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -646,6 +649,10 @@ __global__ void __launch_bounds__(1024) group_scan_kernel(const uint32_t* __rest
     __syncthreads();
   }
   if (tid == 0) *out_total = carry;
+  if (seg && tid <= nb) {  // (the last barrier of the loop made base[] and carry visible)
+    const long long g = (long long)tid * sets_per_iter / 128;
+    seg[tid] = (tid == nb || g >= G) ? (int32_t)carry : (int32_t)base[g];
+  }
 }
 
 // same grid as the fit kernel: thread = (set, type)
@@ -917,7 +924,8 @@ int32_t fit_reserve(rsc_ctx* ctx, const rsc_params* params, int S) {
 // Q1), 3: level-weighted cell sampler on the flattened octree (`cum` = cumulative level weights)
 int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* params, int k, const double* dP,
                     const double* dN, const int64_t* d_idx, int S, uint64_t seed, uint64_t set0, cudaStream_t st,
-                    FitScratch* fs, const double* cum) {
+                    FitScratch* fs, const double* cum, int32_t* d_seg, int sets_per_iter, int nb) {
+  if (d_seg && (sets_per_iter <= 0 || sets_per_iter % 128 || nb < 0 || nb >= 1024)) return fail(ctx, RSC_E_ARG, "fit: segment bounds need sets_per_iter % 128 == 0");
   FitParams f;
   int32_t rc = make_fit_params(ctx, params, k, &f);
   if (rc) return rc;
@@ -966,12 +974,13 @@ int32_t fit_enqueue(rsc_ctx* ctx, rsc_cloud* cloud, int mode, const rsc_params* 
     else
       fit_kernel<0><<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(src, use_idx, S, f, fs->dense, fs->okmask);
     RSC_CUDA(ctx, cudaGetLastError());
-    group_scan_kernel<<<1, 1024, 0, st>>>(fs->okmask, (S + 127) / 128, f.ntypes, fs->base, fs->total);
+    group_scan_kernel<<<1, 1024, 0, st>>>(fs->okmask, (S + 127) / 128, f.ntypes, fs->base, fs->total, d_seg, sets_per_iter, nb);
     RSC_CUDA(ctx, cudaGetLastError());
     compact_kernel<<<dim3((S + 127) / 128, f.ntypes), 128, 0, st>>>(fs->dense, fs->okmask, fs->base, f.ntypes, fs->out, fs->out_set);
     RSC_CUDA(ctx, cudaGetLastError());
   } else {
     RSC_CUDA(ctx, cudaMemsetAsync(fs->total, 0, 8, st));
+    if (d_seg) RSC_CUDA(ctx, cudaMemsetAsync(d_seg, 0, (size_t)(nb + 1) * 4, st));
   }
   ctx->stats.sets_drawn += S;
   return RSC_OK;

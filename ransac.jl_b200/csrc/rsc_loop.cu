@@ -336,9 +336,15 @@ int32_t ransac_loop_device(rsc_cloud* cloud, const rsc_params* p, uint64_t seed,
     ++run->batches;
     // ---- K1: nb * minsubsetN minimal sets -> candidates (device, compacted in reference order) ----
     FitScratch fs;
-    if ((rc = fit_enqueue(ctx, cloud, 2, p, p->drawN, nullptr, nullptr, nullptr, S * nb, seed, (uint64_t)(k - 1) * S, st, &fs))) return rc;
-    seg_bounds_kernel<<<1, 96, 0, st>>>(fs.out_set, fs.total, S, nb, dev->seg);
-    RUN_CUDA(cudaGetLastError());
+    // (segment bounds of the batch's iterations: from the compaction itself when an iteration is whole groups of sets)
+    const bool seg_fused = S % 128 == 0;
+    if ((rc = fit_enqueue(ctx, cloud, 2, p, p->drawN, nullptr, nullptr, nullptr, S * nb, seed, (uint64_t)(k - 1) * S, st, &fs, nullptr,
+                          seg_fused ? dev->seg : nullptr, S, nb)))
+      return rc;
+    if (!seg_fused) {
+      seg_bounds_kernel<<<1, 96, 0, st>>>(fs.out_set, fs.total, S, nb, dev->seg);
+      RUN_CUDA(cudaGetLastError());
+    }
     const int store_n0 = store.n;
     // ---- sync-free path: K2 for a small batch, sized by a PREDICTION of the number of new candidates ----
     // (4 x the largest per-iteration yield seen so far; the true number stays on the device.  If more turn up,
