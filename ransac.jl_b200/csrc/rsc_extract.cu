@@ -9,7 +9,7 @@
 //                              (rsc_exact.cuh); patches their mask bits.  If the queue overflowed
 //                              (flat cones: every point is "ambiguous") it re-scans the whole range.
 //   3. block_count_kernel, scan_u32 (rsc_fit.cu)    exclusive scan of the per-CTA inlier counts
-//   4. extract_write_kernel    ascending global indices by stream compaction; clears enabled bits
+//   4. extract_write_kernel    ascending global indices by stream compaction (a warp per block); clears enabled bits
 #include <stdlib.h>
 
 #include "rsc_eval.cuh"
@@ -146,41 +146,41 @@ __global__ void __launch_bounds__(256) block_count_kernel(const uint32_t* __rest
 }
 
 
+// a WARP per 2048-point block (64 mask words, two per lane): exclusive scan of the words' bit counts, then every lane
+// writes the indices of its words' set bits (a thread per POINT spent 10 M threads on a mask with 2 % of its bits set)
 __global__ void __launch_bounds__(kExThreads) extract_write_kernel(const uint32_t* __restrict__ inl,
                                                                    const unsigned long long* __restrict__ offsets,
-                                                                   int64_t n_pad, int64_t global_offset,
+                                                                   int64_t n_pad, int nblocks, int64_t global_offset,
                                                                    int64_t* __restrict__ out,
                                                                    uint32_t* __restrict__ enabled /*nullable*/) {
-  __shared__ uint32_t woff[kExPts / 32];
-  const int64_t base = (int64_t)blockIdx.x * kExPts;
-  const int64_t w0 = base >> 5;
+  const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= nblocks) return;
   const int64_t nwords = n_pad >> 5;
-  if (threadIdx.x < 32) {  // exclusive scan over this CTA's 64 words (2 per lane)
-    const int lane = threadIdx.x;
-    const uint32_t a0 = (w0 + 2 * lane < nwords) ? __popc(inl[w0 + 2 * lane]) : 0;
-    const uint32_t a1 = (w0 + 2 * lane + 1 < nwords) ? __popc(inl[w0 + 2 * lane + 1]) : 0;
-    uint32_t s = a0 + a1, inc = s;
+  const int64_t wa = (int64_t)b * (kExPts / 32) + 2 * lane, wb = wa + 1;
+  uint32_t ma = wa < nwords ? inl[wa] : 0u, mb = wb < nwords ? inl[wb] : 0u;
+  const uint32_t a0 = __popc(ma), a1 = __popc(mb);
+  uint32_t s = a0 + a1, inc = s;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += o;
-    }
-    woff[2 * lane] = inc - s;
-    woff[2 * lane + 1] = inc - s + a0;
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
   }
-  __syncthreads();
-  const unsigned long long boff = offsets[blockIdx.x];
-#pragma unroll 2
-  for (int it = 0; it < kExPts / kExThreads; ++it) {
-    const int64_t p = base + it * kExThreads + threadIdx.x;
-    if (p >= n_pad) break;
-    const uint32_t w = inl[p >> 5];
-    const int bit = (int)(p & 31);
-    if (out && ((w >> bit) & 1u)) {
-      const unsigned long long pos = boff + woff[(p >> 5) - w0] + __popc(w & ((1u << bit) - 1u));
-      out[pos] = p + global_offset;
-    }
-    if (enabled && bit == 0 && w) enabled[p >> 5] &= ~w;
+  if (enabled) {
+    if (ma) enabled[wa] &= ~ma;
+    if (mb) enabled[wb] &= ~mb;
+  }
+  if (!out) return;
+  unsigned long long pos = offsets[b] + (inc - s);
+  while (ma) {
+    const int bit = __ffs(ma) - 1;
+    ma &= ma - 1;
+    out[pos++] = wa * 32 + bit + global_offset;
+  }
+  while (mb) {
+    const int bit = __ffs(mb) - 1;
+    mb &= mb - 1;
+    out[pos++] = wb * 32 + bit + global_offset;
   }
 }
 
@@ -317,8 +317,8 @@ int32_t refit_write_enqueue(rsc_cloud* cloud, int64_t* d_out, bool disable, cuda
   const uint32_t* inl = reinterpret_cast<const uint32_t*>(b);
   const unsigned long long* offsets =
       reinterpret_cast<const unsigned long long*>(b + ((size_t)(n_pad / 32) * 4 + 15) / 16 * 16);
-  extract_write_kernel<<<nblocks, kExThreads, 0, st>>>(inl, offsets, n_pad, cloud->global_offset, d_out,
-                                                       disable ? cloud->enabled : nullptr);
+  extract_write_kernel<<<(unsigned)(((int64_t)nblocks * 32 + kExThreads - 1) / kExThreads), kExThreads, 0, st>>>(
+      inl, offsets, n_pad, nblocks, cloud->global_offset, d_out, disable ? cloud->enabled : nullptr);
   RSC_CUDA(ctx, cudaGetLastError());
   if (disable) {
     cloud->enabled_changed();
