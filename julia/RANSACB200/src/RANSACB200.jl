@@ -16,7 +16,19 @@ using RANSAC: FittedShape, FittedPlane, FittedSphere, FittedCylinder, FittedCone
 using StaticArrays
 using Libdl
 
-const LIB = Ref{String}(get(ENV, "RANSAC_B200_LIB", "libransac_b200.so"))
+# The library is opened at RUN time (ENV["RANSAC_B200_LIB"] or the loader path) and its entry points are passed to
+# `ccall` as `dlsym` pointers: a `(name, library)` tuple must be a compile-time constant on older Julia 1.x, and a
+# constant would freeze the path of the machine that precompiled the package.
+const LIBHANDLE = Ref{Ptr{Cvoid}}(C_NULL)
+const SYMS = Dict{Symbol,Ptr{Cvoid}}()
+libpath() = get(ENV, "RANSAC_B200_LIB", "libransac_b200.so")
+function fn(name::Symbol)
+    get!(SYMS, name) do
+        LIBHANDLE[] == C_NULL && (LIBHANDLE[] = Libdl.dlopen(libpath()))
+        Libdl.dlsym(LIBHANDLE[], name)
+    end
+end
+__init__() = (LIBHANDLE[] = C_NULL; empty!(SYMS); nothing)   # pointers of a precompile session are never reused
 
 # ---- POD mirrors (include/rsc.h) -------------------------------------------------------------
 struct RscCand            # 64 bytes
@@ -78,18 +90,18 @@ end
 # ---- context / cloud handles ---------------------------------------------------------------------
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
 
-version() = ccall((:rsc_version, LIB[]), Int32, ())
+version() = ccall(fn(:rsc_version), Int32, ())
 
 function check(rc)
     rc == 0 && return
-    msg = unsafe_string(ccall((:rsc_last_error, LIB[]), Cstring, (Ptr{Cvoid},), CTX[]))
+    msg = unsafe_string(ccall(fn(:rsc_last_error), Cstring, (Ptr{Cvoid},), CTX[]))
     error("libransac_b200 error $rc: $msg")
 end
 
 function context(device::Integer=0)
     if CTX[] == C_NULL
         h = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:rsc_ctx_create, LIB[]), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h)
+        rc = ccall(fn(:rsc_ctx_create), Int32, (Int32, Ref{Ptr{Cvoid}}), device, h)
         rc == 0 || error("rsc_ctx_create failed ($rc): an sm_100 (B200) GPU is required, there is no CPU fallback")
         CTX[] = h[]
     end
@@ -104,26 +116,31 @@ mutable struct DeviceCloud
         ctx = context()
         h = Ref{Ptr{Cvoid}}(C_NULL)
         v, n = pc.vertices, pc.normals            # Vector{SVector{3,T}} is bit-compatible with T[3N]
+        if !(eltype(eltype(v)) == eltype(eltype(n)) && eltype(eltype(v)) in (Float32, Float64))
+            # mixed or other element types (RANSACCloud keeps the two eltypes apart, octree.jl:102-103): go through Float64
+            v = [SVector{3,Float64}(x) for x in v]
+            n = [SVector{3,Float64}(x) for x in n]
+        end
         GC.@preserve v n begin
             if eltype(eltype(v)) == Float32
-                check(ccall((:rsc_cloud_create, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Ref{Ptr{Cvoid}}),
+                check(ccall(fn(:rsc_cloud_create), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Int64, Ref{Ptr{Cvoid}}),
                             ctx, pointer(v), pointer(n), pc.size, h))
             else
-                check(ccall((:rsc_cloud_create_f64, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Ptr{Cvoid}}),
+                check(ccall(fn(:rsc_cloud_create_f64), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Ptr{Cvoid}}),
                             ctx, pointer(v), pointer(n), pc.size, h))
             end
         end
         idx = Int64.(pc.subsets[1] .- 1)          # 0-based on the C side
-        check(ccall((:rsc_cloud_set_subset, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int64), h[], 0, idx, length(idx)))
+        check(ccall(fn(:rsc_cloud_set_subset), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int64), h[], 0, idx, length(idx)))
         dc = new(h[], pc)
         push_enabled!(dc)
-        finalizer(d -> ccall((:rsc_cloud_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), d.h), dc)
+        finalizer(d -> ccall(fn(:rsc_cloud_destroy), Cvoid, (Ptr{Cvoid},), d.h), dc)
     end
 end
 
 # pc.isenabled is a BitArray: its `chunks` are exactly the UInt64 words the C ABI expects
-push_enabled!(dc) = check(ccall((:rsc_cloud_set_enabled, LIB[]), Int32, (Ptr{Cvoid}, Ptr{UInt64}), dc.h, dc.pc.isenabled.chunks))
-pull_enabled!(dc) = check(ccall((:rsc_cloud_get_enabled, LIB[]), Int32, (Ptr{Cvoid}, Ptr{UInt64}), dc.h, dc.pc.isenabled.chunks))
+push_enabled!(dc) = check(ccall(fn(:rsc_cloud_set_enabled), Int32, (Ptr{Cvoid}, Ptr{UInt64}), dc.h, dc.pc.isenabled.chunks))
+pull_enabled!(dc) = check(ccall(fn(:rsc_cloud_get_enabled), Int32, (Ptr{Cvoid}, Ptr{UInt64}), dc.h, dc.pc.isenabled.chunks))
 
 # ---- the operator API for built-in shapes ----------------------------------------------------------
 "`scorecandidates!` for a vector of built-in shapes: one launch, returns [(ConfidenceInterval, inpoints)]."
@@ -136,7 +153,7 @@ function scorecandidates(dc::DeviceCloud, cands::Vector{<:FittedShape}, subsetID
     counts = zeros(Int32, C)
     masks = zeros(UInt32, words, C)               # column c = row c of the C layout
     prm = Ref(toparams(params))
-    check(ccall((:rsc_score, LIB[]), Int32,
+    check(ccall(fn(:rsc_score), Int32,
                 (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Int32, Ptr{Int32}, Ptr{UInt32}),
                 dc.h, prm, recs, C, subsetID - 1, counts, masks))
     map(1:C) do c
@@ -153,7 +170,7 @@ function refit_extract!(dc::DeviceCloud, s::FittedShape, params; disable::Bool=t
     n = Ref{Int64}(0)
     prm = Ref(toparams(params))
     cand = Ref(tocand(s))
-    check(ccall((:rsc_refit_extract, LIB[]), Int32,
+    check(ccall(fn(:rsc_refit_extract), Int32,
                 (Ptr{Cvoid}, Ref{RscParams}, Ref{RscCand}, Ptr{Int64}, Ref{Int64}, Int32), dc.h, prm, cand, out, n, disable))
     resize!(out, n[])
     disable && pull_enabled!(dc)
@@ -173,13 +190,13 @@ function score_culled(dc::DeviceCloud, cands::Vector{<:FittedShape}, params; sub
     counts = Vector{Int32}(undef, length(arr))
     tot = Ref{Int64}(0); sur = Ref{Int64}(0); ms = Ref{Float64}(0.0)
     if subset > 0
-        check(ccall((:rsc_score_culled_subset, LIB[]), Int32,
+        check(ccall(fn(:rsc_score_culled_subset), Int32,
                     (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Int32, Ptr{Int32}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
                     dc.h, prm, arr, length(arr), subset - 1, counts, tot, sur, ms))
     else
-        check(ccall((:rsc_cloud_cells_levels, LIB[]), Int32, (Ptr{Cvoid},), dc.h) > 0 ? Int32(0) :
-              ccall((:rsc_cloud_build_cells, LIB[]), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
-        check(ccall((:rsc_score_culled, LIB[]), Int32,
+        check(ccall(fn(:rsc_cloud_cells_levels), Int32, (Ptr{Cvoid},), dc.h) > 0 ? Int32(0) :
+              ccall(fn(:rsc_cloud_build_cells), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
+        check(ccall(fn(:rsc_score_culled), Int32,
                     (Ptr{Cvoid}, Ref{RscParams}, Ptr{RscCand}, Int32, Ptr{Int32}, Ref{Int64}, Ref{Int64}, Ref{Float64}),
                     dc.h, prm, arr, length(arr), counts, tot, sur, ms))
     end
@@ -197,7 +214,7 @@ function refit_lsq(dc::DeviceCloud, s::FittedShape, params; band::Float64=3.0)
     out = Ref(tocand(s))
     n = Ref{Int64}(0)
     rms = Ref{Float64}(NaN)
-    check(ccall((:rsc_refit_lsq, LIB[]), Int32,
+    check(ccall(fn(:rsc_refit_lsq), Int32,
                 (Ptr{Cvoid}, Ref{RscParams}, Ref{RscCand}, Float64, Ref{RscCand}, Ref{Int64}, Ref{Float64}),
                 dc.h, prm, cand, band, out, n, rms))
     fromcand(out[]), n[], rms[]
@@ -211,7 +228,7 @@ function fit_batch(dc::DeviceCloud, idx::Matrix{Int}, params)
     out = Vector{RscCand}(undef, cap)
     out_set = Vector{Int32}(undef, cap)
     n = Ref{Int32}(0)
-    check(ccall((:rsc_fit_batch, LIB[]), Int32,
+    check(ccall(fn(:rsc_fit_batch), Int32,
                 (Ptr{Cvoid}, Ref{RscParams}, Ptr{Int64}, Int32, Ptr{RscCand}, Ptr{Int32}, Ref{Int32}),
                 dc.h, prm, Int64.(idx .- 1), S, out, out_set, n))
     [fromcand(out[i]) for i in 1:n[]], out_set[1:n[]] .+ 1
@@ -266,13 +283,13 @@ end
 "rank 0: the 128-byte NCCL id to hand to the other ranks (MPI.jl bcast, a socket, a file)"
 function comm_unique_id()
     id = zeros(UInt8, 128)
-    rc = ccall((:rsc_comm_unique_id, LIB[]), Int32, (Ptr{UInt8},), id)
+    rc = ccall(fn(:rsc_comm_unique_id), Int32, (Ptr{UInt8},), id)
     rc == 0 || error("rsc_comm_unique_id failed ($rc): libnccl.so.2 not loadable?")
     id
 end
 "every rank: NCCL communicator inside the library (collective)"
 comm_init(id::Vector{UInt8}, rank::Integer, nranks::Integer) =
-    check(ccall((:rsc_ctx_comm_init, LIB[]), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), context(), id, rank, nranks))
+    check(ccall(fn(:rsc_ctx_comm_init), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), context(), id, rank, nranks))
 
 """
     ransac(pc, params, setenabled; reset_rand=false, seed=1234, sampler=:root, octree_levels=8,
@@ -299,41 +316,41 @@ function ransac(pc::RANSACCloud, params, setenabled::Bool; reset_rand=false, see
     run = Ref{Ptr{Cvoid}}(C_NULL)
     p0 = toparams(params)
     if sampler == :octree
-        check(ccall((:rsc_cloud_build_cells, LIB[]), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
+        check(ccall(fn(:rsc_cloud_build_cells), Int32, (Ptr{Cvoid}, Int32), dc.h, octree_levels))
         p0 = RscParams((f === :compat_flags ? (p0.compat_flags | UInt32(2)) : getfield(p0, f) for f in fieldnames(RscParams))...)  # RSC_SAMPLER_OCTREE
     end
     withflag(p, bit) = RscParams((f === :compat_flags ? (p.compat_flags | UInt32(bit)) : getfield(p, f) for f in fieldnames(RscParams))...)
     if progressive   # RSC_SCORE_PROGRESSIVE: every subset must be on the device (subset 1 already is)
         for j in 2:length(pc.subsets)
             idx = Int64.(pc.subsets[j] .- 1)
-            check(ccall((:rsc_cloud_set_subset, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int64), dc.h, j - 1, idx, length(idx)))
+            check(ccall(fn(:rsc_cloud_set_subset), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int64), dc.h, j - 1, idx, length(idx)))
         end
         p0 = withflag(p0, 16)
     end
     lsq && (p0 = withflag(p0, 8))   # RSC_REFIT_LSQ
     prm = Ref(p0)
-    check(ccall((:rsc_ransac_run, LIB[]), Int32, (Ptr{Cvoid}, Ref{RscParams}, UInt64, Ref{Ptr{Cvoid}}),
+    check(ccall(fn(:rsc_ransac_run), Int32, (Ptr{Cvoid}, Ref{RscParams}, UInt64, Ref{Ptr{Cvoid}}),
                 dc.h, prm, reset_rand ? 1234 : seed, run))
     extracted = ExtractedShape[]
     try
-        for i in 0:ccall((:rsc_run_nshapes, LIB[]), Int32, (Ptr{Cvoid},), run[])-1
+        for i in 0:ccall(fn(:rsc_run_nshapes), Int32, (Ptr{Cvoid},), run[])-1
             c = Ref{RscCand}()
             n = Ref{Int64}(0)
-            check(ccall((:rsc_run_shape, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ref{RscCand}, Ref{Int64}), run[], i, c, n))
+            check(ccall(fn(:rsc_run_shape), Int32, (Ptr{Cvoid}, Int32, Ref{RscCand}, Ref{Int64}), run[], i, c, n))
             idx = Vector{Int64}(undef, n[])
-            n[] > 0 && check(ccall((:rsc_run_inpoints, LIB[]), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}), run[], i, idx))
+            n[] > 0 && check(ccall(fn(:rsc_run_inpoints), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}), run[], i, idx))
             push!(extracted, ExtractedShape(fromcand(c[]), idx .+ 1))
         end
-        secs = ccall((:rsc_run_seconds, LIB[]), Float64, (Ptr{Cvoid},), run[])
+        secs = ccall(fn(:rsc_run_seconds), Float64, (Ptr{Cvoid},), run[])
         lw = zeros(Float64, 11); ls = zeros(Float64, 11)
-        nl = ccall((:rsc_run_levelweight, LIB[]), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), run[], lw, ls)
+        nl = ccall(fn(:rsc_run_levelweight), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), run[], lw, ls)
         if nl > 0 && length(pc.levelweight) == nl
             pc.levelweight .= lw[1:nl]; pc.levelscore .= ls[1:nl]
         end
         pull_enabled!(dc)
         return extracted, trunc(secs, digits=2)
     finally
-        ccall((:rsc_run_destroy, LIB[]), Cvoid, (Ptr{Cvoid},), run[])
+        ccall(fn(:rsc_run_destroy), Cvoid, (Ptr{Cvoid},), run[])
     end
 end
 

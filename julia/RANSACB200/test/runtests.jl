@@ -10,7 +10,8 @@ using RANSAC
 using RANSACB200
 using JSON
 using StaticArrays: SVector
-using RANSAC: FittedPlane, FittedSphere, FittedCylinder, FittedCone, RANSACCloud, ransacparameters
+using RANSAC: FittedPlane, FittedSphere, FittedCylinder, FittedCone, FittedShape, ExtractedShape, IterationCandidates,
+              RANSACCloud, ransacparameters      # everything make_golden_helpers.jl expects in scope
 
 const GOLDEN = joinpath(@__DIR__, "..", "..", "..", "tests", "golden")
 include(joinpath(@__DIR__, "..", "..", "make_golden_helpers.jl"))

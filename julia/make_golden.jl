@@ -27,7 +27,7 @@ function main()
     N = [sv(v) for v in inp["normals"]]
     subsets = [Int.(s) .+ 1 for s in inp["subsets"]]
     cands = [shape_from(d) for d in inp["candidates"]]
-    out = Dict{String,Any}("format" => 1, "producer" => "RANSAC.jl $(pkgversion(RANSAC)) on Julia $(VERSION)")
+    out = Dict{String,Any}("format" => 1, "producer" => "RANSAC.jl $(isdefined(Base, :pkgversion) ? pkgversion(RANSAC) : "(version unknown: Julia < 1.9)") on Julia $(VERSION)")
 
     pc = RANSACCloud(P, N, subsets)                                                         # octree.jl:96-103
     pc.isenabled[Int.(inp["disabled"]) .+ 1] .= false
