@@ -1003,6 +1003,20 @@ def sample_minimal_set(pc: Cloud, drawN: int, stream: SetStream, enabled_idx: Op
 # --------------------------------------------------------------------------------------
 
 
+def smallestdistance(points):
+    """utilities.jl:187-199: smallest pairwise distance of a point list (O(n^2); not used by the loop -- its only
+    call, iterations.jl:55, is commented out -- restated so that EVERY vector of test/utilitytests.jl pins something)."""
+    P = np.asarray(points, dtype=F)
+    assert len(P) > 1, "At least two point is needed for that."
+    ld = float(np.sqrt(((P[1] - P[0]) ** 2).sum()))
+    for i in range(len(P)):
+        for j in range(len(P)):
+            if i != j:
+                d = float(np.sqrt(((P[i] - P[j]) ** 2).sum()))
+                ld = d if d < ld else ld
+    return ld
+
+
 def findAABB(points):
     """utilities.jl:125-136: axis-aligned bounding box (min corner, max corner) of a point list; the
     octree's root box (octree.jl:239).  NaN coordinates never replace a bound, like the reference's

@@ -181,3 +181,9 @@ def test_findAABB():
         pts = list(rng.random((30, dim))) + [np.full(dim, -1.0), np.full(dim, 2.0)]
         mn, mx = O.findAABB(pts)
         assert np.array_equal(mn, np.full(dim, -1.0)) and np.array_equal(mx, np.full(dim, 2.0))
+
+
+def test_smallestdistance():
+    """test/utilitytests.jl:29-39 (off the hot path; pinned for completeness)"""
+    assert np.isclose(O.smallestdistance([(0.0, 0), (1.0, 1), (2.2, 2)]), np.sqrt(2))
+    assert np.isclose(O.smallestdistance([(0.0, 0, 0), (1.0, 1, 1), (2.2, 2, 2)]), np.sqrt(3))
