@@ -1385,15 +1385,19 @@ def sample_minimal_set_octree(pc: "Cloud", oct: MortonOctree, drawN: int, stream
     return True, level, idx
 
 
-def updatelevelweight(levelweight: np.ndarray, levelscore: np.ndarray, x: float = 0.9) -> np.ndarray:
-    """octree.jl:198-205; unchanged while no level has a score yet (w == 0 would give NaN)."""
+def updatelevelweight(levelweight: np.ndarray, levelscore: np.ndarray) -> np.ndarray:
+    """octree.jl:198-205 with its default x = 9//10; unchanged while no level has a score yet (w == 0 would give NaN).
+    x is a Rational in the reference: `x*σ[i]` promotes it to Float64(9//10) = 0.9, but `(1-x)/length(P)` is the exact
+    rational 1//(10 n), converted only when it is added to the float term -- the correctly rounded 1/(10 n), whereas
+    the float expression (1 - 0.9)/n would be one ulp off."""
     P, sg = levelweight, levelscore
     w = 0.0
     for i in range(len(P)):
         w += sg[i] / P[i]
     if not w > 0.0:
         return P.copy()
-    return np.array([x * sg[i] / (w * P[i]) + (1 - x) / len(P) for i in range(len(P))])
+    floor_w = 1.0 / (10.0 * len(P))
+    return np.array([0.9 * sg[i] / (w * P[i]) + floor_w for i in range(len(P))])
 
 
 # --------------------------------------------------------------------------------------

@@ -1099,14 +1099,18 @@ void rsc_level_cumsum(const double* levelweight, int32_t nlevels, double* cum) {
   }
 }
 
-/* octree.jl:198-205 (x = 9/10); the weights stay unchanged while no level has a score (w = 0 would give NaN) */
+/* octree.jl:198-205; the weights stay unchanged while no level has a score (w = 0 would give NaN).  x is the
+ * Rational 9//10 there: x*sigma is Float64(9//10)*sigma, but (1-x)/length(P) stays the exact rational 1//(10 n) until
+ * it meets the float term, i.e. it enters as the correctly rounded 1/(10 n) -- not as (1 - 0.9)/n, which is 1 ulp off */
 void rsc_update_levelweight(double* levelweight, const double* levelscore, int32_t nlevels) {
+  if (nlevels > 11) nlevels = 11;
   double w = 0.0;
   for (int i = 0; i < nlevels; ++i) w += levelscore[i] / levelweight[i];
   if (!(w > 0.0)) return;
+  const double floor_w = 1.0 / (10.0 * (double)nlevels);
   double nw[11];
-  for (int i = 0; i < nlevels && i < 11; ++i) nw[i] = 0.9 * levelscore[i] / (w * levelweight[i]) + (1 - 0.9) / nlevels;
-  for (int i = 0; i < nlevels && i < 11; ++i) levelweight[i] = nw[i];
+  for (int i = 0; i < nlevels; ++i) nw[i] = 0.9 * levelscore[i] / (w * levelweight[i]) + floor_w;
+  for (int i = 0; i < nlevels; ++i) levelweight[i] = nw[i];
 }
 
 }  // extern "C"

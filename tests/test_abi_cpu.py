@@ -212,3 +212,39 @@ def test_null_handles_are_rejected_without_touching_the_device():
     L.rsc_ctx_destroy(None)
     L.rsc_run_destroy(None)
     assert L.rsc_last_error(None) is not None
+
+
+def test_update_levelweight_host_function_follows_the_reference_arithmetic():
+    """octree.jl:198-205 through the C ABI (a host function: no GPU needed) == the NumPy oracle, bit for bit, and both
+    == Julia's evaluation with x = 9//10: Float64(9//10)*sigma/(w*P) + Float64(1//(10 n)) (the rational survives until the sum)"""
+    from fractions import Fraction
+
+    import ransac_jl_b200 as R
+    from oracle import ransac_oracle as O
+
+    rng = np.random.default_rng(11)
+    differs_from_naive = 0
+    for n in (1, 3, 7, 8, 9, 11):
+        for _ in range(20):
+            P = rng.random(n) + 0.05
+            P /= P.sum()
+            sg = rng.random(n) * rng.integers(0, 2, n) * 1e4
+            want = O.updatelevelweight(P.copy(), sg.copy())
+            got = P.copy()
+            R._lib.lib.rsc_update_levelweight(got.ctypes.data, sg.ctypes.data, n)
+            assert np.array_equal(got, want)
+            w = 0.0
+            for i in range(n):
+                w += sg[i] / P[i]
+            if w > 0.0:
+                julia = np.array([0.9 * sg[i] / (w * P[i]) + float(Fraction(1, 10 * n)) for i in range(n)])
+                assert np.array_equal(got, julia)
+                naive = np.array([0.9 * sg[i] / (w * P[i]) + (1 - 0.9) / n for i in range(n)])
+                differs_from_naive += int(not np.array_equal(naive, julia))
+            else:
+                assert np.array_equal(got, P)  # no score yet: unchanged
+    assert differs_from_naive > 0  # the distinction is real: (1 - 0.9)/n is not the rational's rounding
+    cum = np.zeros(8)
+    lw = np.full(8, 1 / 8)
+    R._lib.lib.rsc_level_cumsum(lw.ctypes.data, 8, cum.ctypes.data)
+    assert np.array_equal(cum, O.level_cumsum(lw))
