@@ -34,6 +34,22 @@ def partition(n: int, world: int, align: int = ALIGN) -> List[Tuple[int, int]]:
     return out
 
 
+def exchange_comm_id(group=None) -> bytes:
+    """The 128-byte NCCL unique id of the library's communicator on every rank: rank 0 of the group draws it
+    (rsc_comm_unique_id; needs libnccl.so.2 but no GPU), torch.distributed -- any backend -- broadcasts it."""
+    import torch.distributed as dist
+
+    ident = [None]
+    if dist.get_rank(group) == 0:
+        buf = (C.c_uint8 * 128)()
+        rc = lib.rsc_comm_unique_id(buf)
+        if rc != 0:
+            raise _lib.RscError(rc, "rsc_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        ident = [bytes(buf)]
+    dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    return ident[0]
+
+
 def init_comm(ctx, group=None) -> None:
     """NCCL communicator of the library on `ctx` (one per process): rank 0 draws the NCCL unique id,
     torch.distributed broadcasts its 128 bytes, every rank calls rsc_ctx_comm_init (collective)."""
@@ -42,13 +58,7 @@ def init_comm(ctx, group=None) -> None:
     if getattr(ctx, "_comm", False):
         return
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    ident = [None]
-    if rank == 0:
-        buf = (C.c_uint8 * 128)()
-        ctx.check(lib.rsc_comm_unique_id(buf))
-        ident = [bytes(buf)]
-    dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-    buf = (C.c_uint8 * 128).from_buffer_copy(ident[0])
+    buf = (C.c_uint8 * 128).from_buffer_copy(exchange_comm_id(group))
     ctx.check(lib.rsc_ctx_comm_init(ctx.h, buf, rank, world))
     ctx._comm = True
 

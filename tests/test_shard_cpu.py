@@ -117,3 +117,42 @@ def test_two_rank_gloo_distributed_inlier_lists_digest_and_gather():
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=5)
+
+
+def _worker_comm_id(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+
+    from ransac_jl_b200 import shard
+    from ransac_jl_b200._lib import lib
+
+    ident = shard.exchange_comm_id()  # rank 0: the LIBRARY's rsc_comm_unique_id (dlopen of libnccl.so.2, no GPU needed)
+    got = [None] * world
+    dist.all_gather_object(got, ident)
+    # without a context the collective initialisation must refuse (no NCCL call, no hang)
+    buf = (C.c_uint8 * 128).from_buffer_copy(ident)
+    rc_null = lib.rsc_ctx_comm_init(None, buf, rank, world)
+    if rank == 0:
+        q.put((len(ident), all(g == ident for g in got), any(ident), int(rc_null)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_library_nccl_id_reaches_every_rank():
+    """the host plumbing of the in-library NCCL communicator (shard.init_comm = exchange_comm_id + rsc_ctx_comm_init):
+    the 128-byte id drawn by the library on rank 0 arrives unchanged on every rank over a gloo group"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_comm_id, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    n, same, nonzero, rc_null = q.get(timeout=5)
+    assert n == 128 and same and nonzero
+    assert rc_null != 0
